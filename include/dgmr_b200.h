@@ -1,0 +1,191 @@
+/*
+ * dgmr_b200.h -- C ABI of the B200-native DGMR hot path (libdgmr_b200.so).
+ *
+ * Drop-in boundary: the reference has no native code; its hot path is the
+ * PyTorch op call sites listed in SURVEY.md 2.2.  Each entry point below replaces one family
+ * of those call sites and cites it (paths relative to the reference repo root, `ref:`).
+ * The Python package `skillful_nowcasting_b200` binds these with ctypes
+ * and mirrors the reference's module API (DGMR, Generator, Sampler, ... dgmr/__init__.py:3-6).
+ *
+ * Conventions
+ *  - All pointers are DEVICE pointers owned by the caller (PyTorch allocates everything,
+ *    including workspaces); the library never allocates or frees caller-visible memory.
+ *  - Activations are fp32, channels-last: [N, D, H, W, C] contiguous (2-D convs: D == 1).
+ *    "Groups" G: the N images are G consecutive groups of N/G images; a group is one
+ *    *reference call* (one timestep / one frame).  Per-call quantities of the reference
+ *    (spectral-norm sigma, BatchNorm batch statistics) are per group here, which is how the
+ *    T calls of e.g. `[self.g1(h) for h in hidden_states]` (ref: dgmr/generators.py:154)
+ *    run as ONE launch with identical results.
+ *  - Every function is asynchronous on `stream` (a cudaStream_t), never synchronises the host,
+ *    returns 0 on success and a non-zero code on error; dgmr_last_error() gives the message
+ *    (thread-local).  Nothing aborts.
+ *  - Conv weights are consumed "packed": [tap][Cout][Cin] fp32 (tap = (kd*KH + kh)*KW + kw),
+ *    produced from the state-dict OIHW tensor by dgmr_pack_weight.
+ */
+#ifndef DGMR_B200_H
+#define DGMR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* dgmr_stream_t; /* cudaStream_t */
+
+enum { DGMR_ACT_NONE = 0, DGMR_ACT_RELU = 1 };
+/* conv algorithm selector */
+enum { DGMR_ALGO_AUTO = 0, DGMR_ALGO_SIMT = 1, DGMR_ALGO_UMMA = 2 };
+/* tensor-core operand precision: 1xTF32 (what cuDNN does by default for the reference) or
+ * 3xTF32 error-compensated (hi*hi + hi*lo + lo*hi), ~fp32 accuracy */
+enum { DGMR_PREC_TF32 = 0, DGMR_PREC_3XTF32 = 1 };
+
+const char* dgmr_last_error(void);
+int dgmr_abi_version(void);
+/* 1 if the tcgen05/TMA implicit-GEMM path can serve this conv shape (else the SIMT kernel is used) */
+int dgmr_conv_umma_supported(int N, int D, int H, int W, int Cin, int Cout, int kd, int kh, int kw);
+int dgmr_wgrad_umma_supported(int N, int D, int H, int W, int Cin, int Cout, int kd, int kh, int kw);
+
+/* ---- layout: generic strided gather  dst[i0..] (+)= src[i0..]
+ * replaces ref: PixelUnshuffle/PixelShuffle (dgmr/common.py:326,393; generators.py:123,178;
+ * discriminators.py:69,166), einops rearrange "b t c h w -> b (c t) h w" (common.py:423),
+ * torch.cat / torch.stack / permute (ConvGRU.py:69,78; discriminators.py:110,116), and the
+ * NCHW<->NHWC transposes at the module boundary.  Pure index permutation: bit-exact. */
+int dgmr_permute(const float* src, float* dst, int ndim, const int64_t* shape,
+                 const int64_t* src_strides, const int64_t* dst_strides, int accumulate,
+                 dgmr_stream_t stream);
+
+/* ---- pointwise */
+/* out = a*x + b*y (y may be NULL) ; ref: residual adds, torch.stack(...).mean(0) (dgmr/dgmr.py:180) */
+int dgmr_axpby(float a, const float* x, float b, const float* y, float* out, int64_t n, dgmr_stream_t stream);
+int dgmr_fill(float* x, float value, int64_t n, dgmr_stream_t stream);
+/* ref: torch.nn.ReLU / F.relu (dgmr/common.py:229-233) */
+int dgmr_relu_fwd(const float* x, float* y, int64_t n, dgmr_stream_t stream);
+int dgmr_relu_bwd(const float* dy, const float* x, float* dx, int64_t n, dgmr_stream_t stream);
+/* sum-pool with window (pd,ph,pw) in {1,2}, floor output dims, times `scale`.
+ * scale=1/(pd*ph*pw): AvgPool2d/3d forward (ref: dgmr/common.py:189-191, discriminators.py:68,165);
+ * scale=1: backward of nearest Upsample. */
+int dgmr_pool_sum(const float* x, float* y, int N, int D, int H, int W, int C, int pd, int ph, int pw,
+                  float scale, dgmr_stream_t stream);
+/* nearest replicate by (ud,uh,uw) times `scale`, x:[N,D,H,W,C] -> y:[N,D*ud,H*uh,W*uw,C] (output dims
+ * Do,Ho,Wo given explicitly so floor-pooled odd sizes back-propagate zeros to the dropped rim).
+ * scale=1: Upsample(nearest) forward (ref: dgmr/common.py:121,142,148); scale=1/window: AvgPool backward. */
+int dgmr_upsample(const float* x, float* y, int N, int D, int H, int W, int C, int ud, int uh, int uw,
+                  int Do, int Ho, int Wo, float scale, dgmr_stream_t stream);
+
+/* ---- ConvGRU gate arithmetic (ref: dgmr/layers/ConvGRU.py:72-82); `ld` = row pitch (floats) of the
+ * pre-activation tensors so that r|u can live side by side in one [rows, 2*Ch] conv output. */
+int dgmr_gru_gate_fwd(const float* pre_r, int ld, const float* h, float* rh, int64_t rows, int Ch, dgmr_stream_t stream);
+int dgmr_gru_blend_fwd(const float* pre_u, int ld, const float* h, const float* c, float* hnew,
+                       int64_t rows, int Ch, dgmr_stream_t stream);
+/* d_rh -> d_pre_r, dh (+= if accumulate) */
+int dgmr_gru_gate_bwd(const float* d_rh, const float* pre_r, int ld, const float* h, float* d_pre_r, int ldd,
+                      float* dh, int accumulate, int64_t rows, int Ch, dgmr_stream_t stream);
+/* d_hnew -> d_pre_u, dc, dh (+= if accumulate) */
+int dgmr_gru_blend_bwd(const float* d_hnew, const float* pre_u, int ld, const float* h, const float* c,
+                       float* d_pre_u, int ldd, float* dc, float* dh, int accumulate,
+                       int64_t rows, int Ch, dgmr_stream_t stream);
+
+/* ---- BatchNorm (ref: BatchNorm2d dgmr/common.py:38-39,108-109, generators.py:113; BatchNorm1d
+ * discriminators.py:102,194).  x: [G*rows, C]; batch statistics per (group, channel). */
+int dgmr_bn_stats(const float* x, double* sums /*[G][C][2], zeroed inside*/, int64_t rows, int G, int C, dgmr_stream_t stream);
+/* training: mean/var from sums, running stats updated sequentially over g (momentum, unbiased var);
+ * eval: running stats.  Outputs mean,invstd,a,b : [G][C], y = a*x + b. */
+int dgmr_bn_finalize(const double* sums, const float* gamma, const float* beta, float* running_mean,
+                     float* running_var, int64_t rows, int G, int C, float eps, float momentum, int training,
+                     float* mean, float* invstd, float* a, float* b, dgmr_stream_t stream);
+/* y = act(a[g,c]*x + b[g,c]); if up2: x is [G*Ng, H, W, C] and y is [G*Ng, 2H, 2W, C] (nearest). */
+int dgmr_bn_apply(const float* x, const float* a, const float* b, float* y, int64_t rows, int G, int C,
+                  int relu, int up2, int H, int W, dgmr_stream_t stream);
+/* red[g][c] = (sum dpre, sum dpre*xhat), dpre = dy*(y>0 if relu), dy pooled over the 2x2 replicas if up2 */
+int dgmr_bn_bwd_reduce(const float* dy, const float* x, const float* a, const float* b, const float* mean,
+                       const float* invstd, double* red /*[G][C][2], zeroed inside*/, int64_t rows, int G, int C,
+                       int relu, int up2, int H, int W, dgmr_stream_t stream);
+/* dx (training: full batch-stat backward; eval: a*dpre); dgamma/dbeta [C] (+= if accumulate) */
+int dgmr_bn_bwd_apply(const float* dy, const float* x, const float* a, const float* b, const float* mean,
+                      const float* invstd, const float* gamma, const double* red, float* dx, float* dgamma,
+                      float* dbeta, int accumulate, int64_t rows, int G, int C, int relu, int up2, int H, int W,
+                      int training, dgmr_stream_t stream);
+
+/* ---- spectral norm (ref: torch/nn/utils/parametrizations.py:495-527, applied at
+ * dgmr/layers/ConvGRU.py:29-55, common.py:43-66,113-137,192-215,350-384,451-455,
+ * generators.py:52,67,84,101,115, discriminators.py:100,192).
+ * W: [R][K] row-major (= weight.flatten(1)).  Performs the power iterations of `G` consecutive
+ * reference calls in one launch: for g in 0..G-1: (training) u<-norm(W v), v<-norm(W^T u);
+ * sigma_g = u.(W v).  Emits inv_sigma[g] and the (u_g, v_g) used, and leaves the final u,v in place.
+ * ws: >= (G+2)*R + 2*G + 8 floats of scratch. */
+int dgmr_sn_power_iter(const float* w, float* u, float* v, int R, int K, int G, float eps, int training,
+                       float* inv_sigma, float* u_hist, float* v_hist, float* ws, dgmr_stream_t stream);
+/* dW[r][k] += sum_g d_inv_sigma[g] * (-inv_sigma[g]^2) * u_g[r] v_g[k]  (u,v constants, as in torch) */
+int dgmr_sn_bwd(const float* d_inv_sigma, const float* inv_sigma, const float* u_hist, const float* v_hist,
+                float* dw, int R, int K, int G, int accumulate, dgmr_stream_t stream);
+
+/* ---- convolution (ref: every Conv2d/Conv3d call site: dgmr/layers/ConvGRU.py:72-81,
+ * common.py:71-83,141-154,222-236,290-300,413-424,486, generators.py:153,176-177,
+ * discriminators.py:113-133,203-211; F.linear heads as 1x1).  Stride 1, "same" zero padding,
+ * kernel extent 1 or 3 per dim. */
+/* w: OIHW(/OIDHW) [Cout][CinTot][taps]; packs input-channel slice [ci0, ci0+Cin).
+ * mode 0: forward pack  packed[tap][co][ci];  mode 1: dgrad pack  packed[taps-1-tap][ci][co]. */
+int dgmr_pack_weight(const float* w, float* packed, int Cout, int CinTot, int ci0, int Cin, int taps, int mode,
+                     dgmr_stream_t stream);
+/* inverse of mode 0 for gradients: gw[co][ci0+ci][tap] (+)= packed[tap][co][ci] */
+int dgmr_unpack_wgrad(const float* packed, float* gw, int Cout, int CinTot, int ci0, int Cin, int taps,
+                      int accumulate, dgmr_stream_t stream);
+/* y = act( conv(x, wp) * scale[g][co] + bias[co] + res )   (scale, bias, res optional = NULL)
+ * x:[N,D,H,W,Cin]  y,res:[N,D,H,W,Cout]  scale:[G][Cout]  g = n / (N/G) */
+/* precision DGMR_PREC_3XTF32 (tensor-core path): x/wp hold the hi parts, x_lo/wp_lo the lo parts
+ * (dgmr_split_tf32); otherwise x_lo/wp_lo are NULL. */
+int dgmr_conv_fwd(const float* x, const float* x_lo, const float* wp, const float* wp_lo, const float* bias,
+                  const float* scale, const float* res, float* y, int N, int D, int H, int W, int Cin, int Cout,
+                  int kd, int kh, int kw, int G, int act, int algo, int precision, dgmr_stream_t stream);
+/* backward prologue: dpre = dy*act'(y); dz = dpre*scale; dbias[co] (+)= sum dpre;
+ * dscale[g][co] = sum dpre*(y - bias - res)/scale  (the <dY, Y-b> identity of SURVEY.md 8a/a13).
+ * rows = pixels per group.  Any of dbias/dscale may be NULL. */
+int dgmr_conv_bwd_prep(const float* dy, const float* y, const float* res, const float* bias, const float* scale,
+                       float* dz, float* dbias, float* dscale, int64_t rows, int G, int Cout, int act,
+                       int accumulate_dbias, dgmr_stream_t stream);
+/* dwp[tap][co][ci] = sum_pixels dz[p][co] * x[p+tap][ci]   (dwp fully overwritten)
+ * xT/dzT: channel-major transposed copies [N][C][D][H][W] needed by the tensor-core path only
+ * (NULL for SIMT). */
+int dgmr_conv_wgrad(const float* x, const float* dz, const float* xT, const float* dzT, const float* xT_lo,
+                    const float* dzT_lo, float* dwp, int N, int D, int H, int W, int Cin, int Cout,
+                    int kd, int kh, int kw, int algo, int precision, dgmr_stream_t stream);
+
+/* ---- discriminator head (ref: dgmr/discriminators.py:129,209: sum(relu(x)) over H,W) */
+int dgmr_sumpool_relu_fwd(const float* x, float* y, int N, int HW, int C, dgmr_stream_t stream);
+int dgmr_sumpool_relu_bwd(const float* dy, const float* x, float* dx, int N, int HW, int C, dgmr_stream_t stream);
+
+/* ---- latent-stack attention (ref: dgmr/layers/Attention.py:9-20,71-85; note the reference
+ * feeds [C,H,W] tensors to einsums labelled "h w c": positions are (channel,row) pairs, the
+ * contracted axis is the image column).  q,k,v,out: [B,H,W,C] channels-last; beta: [B][L][L], L=C*H. */
+int dgmr_attention_fwd(const float* q, const float* k, const float* v, float* out, float* beta,
+                       int B, int H, int W, int C, dgmr_stream_t stream);
+int dgmr_attention_bwd(const float* dout, const float* q, const float* k, const float* v, const float* beta,
+                       float* dq, float* dk, float* dv, float* ws /*[B][L][L]*/, int B, int H, int W, int C,
+                       dgmr_stream_t stream);
+
+/* ---- losses (ref: dgmr/losses.py:307-319 hinge; :172-192 GridCellLoss + dgmr/dgmr.py:20-33 weight_fn) */
+/* scores: [2B][2] (real rows then generated rows; col 0 spatial, col 1 temporal).
+ * loss = sum_col mean relu(1-real) + mean relu(1+gen);  dscores = d loss/d scores */
+int dgmr_hinge_disc(const float* scores, int B, float* loss, float* dscores, dgmr_stream_t stream);
+/* loss = -mean(scores_gen) over n values; dscores = -1/n */
+int dgmr_hinge_gen(const float* scores, int n, float* loss, float* dscores, dgmr_stream_t stream);
+/* loss = sum |(gen-target)*max(target+1,cap)| * coef ; gen/target n elements */
+int dgmr_grid_cell_fwd(const float* gen, const float* target, float cap, float coef, float* loss,
+                       double* acc_ws /*1 double scratch*/, int64_t n, dgmr_stream_t stream);
+/* dgen = sign(gen-target)*max(target+1,cap)*coef*(*gout)   (gout: device scalar) */
+int dgmr_grid_cell_bwd(const float* gen, const float* target, float cap, float coef, const float* gout,
+                       float* dgen, int64_t n, dgmr_stream_t stream);
+
+/* ---- optimiser (ref: torch.optim.Adam built at dgmr/dgmr.py:292-300; eps 1e-8) on a flat buffer;
+ * g is multiplied by grad_scale first (1/world_size after the NCCL all-reduce). */
+int dgmr_adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+              float eps, int step, float grad_scale, dgmr_stream_t stream);
+
+/* ---- 3xTF32 support: hi = x & ~0x1fff, lo = x - hi */
+int dgmr_split_tf32(const float* x, float* hi, float* lo, int64_t n, dgmr_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

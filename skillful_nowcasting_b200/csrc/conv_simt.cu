@@ -1,0 +1,501 @@
+// Generic CUDA-core (fp32 FMA) implicit-GEMM convolution kernels + weight pack/unpack +
+// conv backward prologue + spectral-norm power iteration.
+// The SIMT conv kernels serve every shape the tensor-core path (conv_umma.cu) does not take
+// (tiny channel counts such as the 4-channel space-to-depth inputs, batch-1 latent stack,
+// 1x1/2x2 images deep in the discriminators) and are the on-device cross-check for it.
+#include "common.cuh"
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
+
+namespace dgmr {
+
+struct ConvDims {
+  int N, D, H, W, Cin, Cout, kd, kh, kw, G;
+};
+
+// ------------------------------------------------------------------ forward / dgrad
+// y[m][co] = act( sum_{tap,ci} x[pix(m)+tap][ci] * wp[tap][co][ci] * scale + bias + res )
+template <int BM, int BN, int BK>
+__global__ void __launch_bounds__(256) conv_simt_fwd_kernel(const float* __restrict__ x, const float* __restrict__ wp, const float* __restrict__ bias,
+                                                            const float* __restrict__ scale, const float* __restrict__ res, float* __restrict__ y,
+                                                            ConvDims d, int act) {
+  __shared__ __align__(16) float As[BK][BM + 4];
+  __shared__ __align__(16) float Bs[BK][BN + 4];
+  const int tid = threadIdx.x;
+  const int64_t M = (int64_t)d.N * d.D * d.H * d.W;
+  const int64_t m0 = (int64_t)blockIdx.x * BM;
+  const int n0 = blockIdx.y * BN;
+  const int lrow = tid >> 2, lk = (tid & 3) * 4;
+  // decode my load row's pixel
+  const int64_t mrow = m0 + lrow;
+  int pn = 0, pd_ = 0, ph_ = 0, pw_ = 0;
+  const bool mvalid = mrow < M;
+  if (mvalid) {
+    int64_t r = mrow;
+    pw_ = r % d.W; r /= d.W;
+    ph_ = r % d.H; r /= d.H;
+    pd_ = r % d.D; pn = r / d.D;
+  }
+  const int co_l = n0 + lrow;
+  const bool vec = (d.Cin & 3) == 0;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  const int ty = tid >> 4, tx = tid & 15;
+  const int taps = d.kd * d.kh * d.kw;
+  for (int tap = 0; tap < taps; ++tap) {
+    int tw = tap % d.kw, th = (tap / d.kw) % d.kh, td = tap / (d.kw * d.kh);
+    int iw = pw_ + tw - d.kw / 2, ih = ph_ + th - d.kh / 2, id = pd_ + td - d.kd / 2;
+    bool pvalid = mvalid && iw >= 0 && iw < d.W && ih >= 0 && ih < d.H && id >= 0 && id < d.D;
+    const float* xp = x + ((((int64_t)pn * d.D + id) * d.H + ih) * d.W + iw) * d.Cin;
+    const float* wrow = wp + ((int64_t)tap * d.Cout + co_l) * d.Cin;
+    for (int c0 = 0; c0 < d.Cin; c0 += BK) {
+      float a4[4] = {0.f, 0.f, 0.f, 0.f}, b4[4] = {0.f, 0.f, 0.f, 0.f};
+      int c = c0 + lk;
+      if (pvalid) {
+        if (vec && c + 3 < d.Cin) {
+          float4 t = *reinterpret_cast<const float4*>(xp + c);
+          a4[0] = t.x; a4[1] = t.y; a4[2] = t.z; a4[3] = t.w;
+        } else {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) if (c + i < d.Cin) a4[i] = xp[c + i];
+        }
+      }
+      if (co_l < d.Cout) {
+        if (vec && c + 3 < d.Cin) {
+          float4 t = *reinterpret_cast<const float4*>(wrow + c);
+          b4[0] = t.x; b4[1] = t.y; b4[2] = t.z; b4[3] = t.w;
+        } else {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) if (c + i < d.Cin) b4[i] = wrow[c + i];
+        }
+      }
+      __syncthreads();
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { As[lk + i][lrow] = a4[i]; Bs[lk + i][lrow] = b4[i]; }
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < BK; ++k) {
+        float4 av = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+        float4 bv = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+        float a_[4] = {av.x, av.y, av.z, av.w}, b_[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a_[i], b_[j], acc[i][j]);
+      }
+    }
+  }
+  const int64_t per_img = (int64_t)d.D * d.H * d.W;
+  const int imgs_per_group = d.N / d.G;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int64_t m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+    int g = (int)((m / per_img) / imgs_per_group);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int co = n0 + tx * 4 + j;
+      if (co >= d.Cout) continue;
+      float v = acc[i][j];
+      if (scale) v *= scale[(int64_t)g * d.Cout + co];
+      if (bias) v += bias[co];
+      if (res) v += res[m * d.Cout + co];
+      if (act == DGMR_ACT_RELU) v = fmaxf(v, 0.f);
+      y[m * d.Cout + co] = v;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ wgrad
+// dwp[tap][co][ci] += sum_{p in chunk} dz[p][co] * x[p+tap][ci]
+template <int BM, int BN, int BK>
+__global__ void __launch_bounds__(256) conv_simt_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dz, float* __restrict__ dwp,
+                                                              ConvDims d, int ci_tiles, int64_t chunk) {
+  __shared__ __align__(16) float As[BK][BM + 4];
+  __shared__ __align__(16) float Bs[BK][BN + 4];
+  const int tid = threadIdx.x;
+  const int co0 = (blockIdx.x / ci_tiles) * BM, ci0 = (blockIdx.x % ci_tiles) * BN;
+  const int tap = blockIdx.y;
+  const int tw = tap % d.kw, th = (tap / d.kw) % d.kh, td = tap / (d.kw * d.kh);
+  const int64_t M = (int64_t)d.N * d.D * d.H * d.W;
+  const int64_t p_begin = (int64_t)blockIdx.z * chunk;
+  const int64_t p_end = p_begin + chunk < M ? p_begin + chunk : M;
+  const int lk = tid >> 4, lq = (tid & 15) * 4;  // k row 0..15, 4 consecutive channels
+  const bool veca = (d.Cout & 3) == 0, vecb = (d.Cin & 3) == 0;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  const int ty = tid >> 4, tx = tid & 15;
+  for (int64_t p0 = p_begin; p0 < p_end; p0 += BK) {
+    int64_t p = p0 + lk;
+    float a4[4] = {0.f, 0.f, 0.f, 0.f}, b4[4] = {0.f, 0.f, 0.f, 0.f};
+    if (p < p_end) {
+      int co = co0 + lq;
+      const float* dp = dz + p * d.Cout;
+      if (veca && co + 3 < d.Cout) {
+        float4 t = *reinterpret_cast<const float4*>(dp + co);
+        a4[0] = t.x; a4[1] = t.y; a4[2] = t.z; a4[3] = t.w;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) if (co + i < d.Cout) a4[i] = dp[co + i];
+      }
+      int64_t r = p;
+      int pw_ = r % d.W; r /= d.W;
+      int ph_ = r % d.H; r /= d.H;
+      int pd_ = r % d.D; int pn = r / d.D;
+      int iw = pw_ + tw - d.kw / 2, ih = ph_ + th - d.kh / 2, id = pd_ + td - d.kd / 2;
+      if (iw >= 0 && iw < d.W && ih >= 0 && ih < d.H && id >= 0 && id < d.D) {
+        const float* xp = x + ((((int64_t)pn * d.D + id) * d.H + ih) * d.W + iw) * d.Cin;
+        int ci = ci0 + lq;
+        if (vecb && ci + 3 < d.Cin) {
+          float4 t = *reinterpret_cast<const float4*>(xp + ci);
+          b4[0] = t.x; b4[1] = t.y; b4[2] = t.z; b4[3] = t.w;
+        } else {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) if (ci + i < d.Cin) b4[i] = xp[ci + i];
+        }
+      }
+    }
+    __syncthreads();
+    *reinterpret_cast<float4*>(&As[lk][lq]) = make_float4(a4[0], a4[1], a4[2], a4[3]);
+    *reinterpret_cast<float4*>(&Bs[lk][lq]) = make_float4(b4[0], b4[1], b4[2], b4[3]);
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      float4 av = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      float4 bv = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      float a_[4] = {av.x, av.y, av.z, av.w}, b_[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a_[i], b_[j], acc[i][j]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int co = co0 + ty * 4 + i;
+    if (co >= d.Cout) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int ci = ci0 + tx * 4 + j;
+      if (ci >= d.Cin) continue;
+      atomicAdd(&dwp[((int64_t)tap * d.Cout + co) * d.Cin + ci], acc[i][j]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ pack / unpack
+__global__ void pack_weight_kernel(const float* __restrict__ w, float* __restrict__ packed, int Cout, int CinTot, int ci0, int Cin, int taps, int mode) {
+  int64_t total = (int64_t)taps * Cout * Cin;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    // iterate in destination order for coalesced writes
+    if (mode == 0) {
+      int ci = i % Cin; int64_t r = i / Cin; int co = r % Cout; int tap = r / Cout;
+      packed[i] = w[((int64_t)co * CinTot + ci0 + ci) * taps + tap];
+    } else {
+      int co = i % Cout; int64_t r = i / Cout; int ci = r % Cin; int tapf = r / Cin;
+      int tap = taps - 1 - tapf;
+      packed[i] = w[((int64_t)co * CinTot + ci0 + ci) * taps + tap];
+    }
+  }
+}
+__global__ void unpack_wgrad_kernel(const float* __restrict__ packed, float* __restrict__ gw, int Cout, int CinTot, int ci0, int Cin, int taps, int acc) {
+  int64_t total = (int64_t)taps * Cout * Cin;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    // iterate in gw order: (co, ci, tap)
+    int tap = i % taps; int64_t r = i / taps; int ci = r % Cin; int co = r / Cin;
+    float v = packed[((int64_t)tap * Cout + co) * Cin + ci];
+    int64_t o = ((int64_t)co * CinTot + ci0 + ci) * taps + tap;
+    if (acc) gw[o] += v; else gw[o] = v;
+  }
+}
+
+// ------------------------------------------------------------------ backward prologue
+// rows = pixels per group; grid (row chunks, G); 256 threads as (cpl channel lanes x rp row lanes)
+__global__ void conv_bwd_prep_kernel(const float* __restrict__ dy, const float* __restrict__ y, const float* __restrict__ res, const float* __restrict__ bias,
+                                     const float* __restrict__ scale, float* __restrict__ dz, float* __restrict__ dbias, float* __restrict__ dscale,
+                                     int64_t rows, int C, int64_t chunk, int act) {
+  extern __shared__ double sh[];
+  int g = blockIdx.y;
+  int cpl = C < 256 ? C : 256;
+  int rp = 256 / cpl;
+  int cl = threadIdx.x % cpl, rl = threadIdx.x / cpl;
+  int64_t r0 = (int64_t)blockIdx.x * chunk;
+  int64_t r1 = r0 + chunk < rows ? r0 + chunk : rows;
+  for (int c = cl; c < C; c += cpl) {
+    double s = 0.0, q = 0.0;
+    if (rl < rp) {
+      float sc = scale ? scale[(int64_t)g * C + c] : 1.f;
+      float bi = bias ? bias[c] : 0.f;
+      float fs = 0.f, fq = 0.f; int cnt = 0;
+      for (int64_t r = r0 + rl; r < r1; r += rp) {
+        int64_t o = ((int64_t)g * rows + r) * C + c;
+        float yv = y ? y[o] : 0.f;
+        float d = dy[o];
+        if (act == DGMR_ACT_RELU && !(yv > 0.f)) d = 0.f;
+        if (dz) dz[o] = d * sc;
+        fs += d;
+        if (dscale) { float zs = yv - bi - (res ? res[o] : 0.f); fq += d * zs; }
+        if (++cnt == 64) { s += fs; q += fq; fs = fq = 0.f; cnt = 0; }
+      }
+      s += fs; q += fq;
+      sh[(rl * cpl + cl) * 2] = s; sh[(rl * cpl + cl) * 2 + 1] = q;
+    }
+    __syncthreads();
+    if (rl == 0) {
+      for (int j = 1; j < rp; ++j) { s += sh[(j * cpl + cl) * 2]; q += sh[(j * cpl + cl) * 2 + 1]; }
+      if (dbias) atomicAdd(&dbias[c], (float)s);
+      if (dscale) {
+        float sc = scale[(int64_t)g * C + c];
+        atomicAdd(&dscale[(int64_t)g * C + c], (float)(q / (double)sc));
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------ spectral norm
+// Column-partitioned persistent cooperative kernel: CTA j keeps W[:, k0:k1) in shared memory
+// (the whole weight lives across the SMs' smem: <= 21 MB for the largest DGMR layer) and all
+// G reference calls' power iterations run inside ONE launch, two grid syncs per iteration.
+struct SnArgs {
+  const float* w; float* u; float* v; int R, K, G; float eps; int training;
+  float* inv_sigma; float* u_hist; float* v_hist;
+  float* t;   // [(G+1)][R] zeroed
+  float* nq;  // [G] zeroed
+  int kw; int in_smem;
+};
+__device__ __forceinline__ float block_sumsq(const float* __restrict__ a, int n, float* red) {
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) { float v = a[i]; s += v * v; }
+  s = warp_sum(s);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  float tot = 0.f;
+  for (int w = 0; w < (blockDim.x >> 5); ++w) tot += red[w];
+  return tot;
+}
+__global__ void __launch_bounds__(256) sn_power_iter_kernel(SnArgs a) {
+  cg::grid_group grid = cg::this_grid();
+  extern __shared__ float smem[];
+  const int R = a.R, K = a.K, kwmax = a.kw;
+  const int k0 = blockIdx.x * kwmax;
+  const int kw = (k0 + kwmax <= K) ? kwmax : (K - k0 > 0 ? K - k0 : 0);
+  float* ush = smem;                // [R]
+  float* vsh = ush + R;             // [kwmax]
+  float* qsh = vsh + kwmax;         // [kwmax]
+  float* red = qsh + kwmax;         // [32]
+  float* wsh = red + 32;            // [R][kwmax] if in_smem
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  if (a.in_smem) {
+    for (int r = warp; r < R; r += nwarps)
+      for (int k = lane; k < kw; k += 32) wsh[r * kwmax + k] = a.w[(int64_t)r * K + k0 + k];
+  }
+  for (int k = threadIdx.x; k < kw; k += blockDim.x) vsh[k] = a.v[k0 + k];
+  __syncthreads();
+  auto Wat = [&](int r, int k) -> float { return a.in_smem ? wsh[r * kwmax + k] : a.w[(int64_t)r * K + k0 + k]; };
+  // t[slot] += W[:, mine] v[mine]
+  auto matvec = [&](int slot) {
+    for (int r = warp; r < R; r += nwarps) {
+      float s = 0.f;
+      for (int k = lane; k < kw; k += 32) s += Wat(r, k) * vsh[k];
+      s = warp_sum(s);
+      if (lane == 0 && kw > 0) atomicAdd(&a.t[(int64_t)slot * R + r], s);
+    }
+  };
+  matvec(0);
+  grid.sync();
+  if (!a.training) {
+    // sigma = u0 . (W v0), same for all G calls
+    if (blockIdx.x == 0) {
+      float s = 0.f;
+      for (int r = threadIdx.x; r < R; r += blockDim.x) s += a.u[r] * a.t[r];
+      s = warp_sum(s);
+      if (lane == 0) red[warp] = s;
+      __syncthreads();
+      if (threadIdx.x == 0) { float tot = 0.f; for (int w = 0; w < nwarps; ++w) tot += red[w]; red[0] = 1.0f / tot; }
+      __syncthreads();
+      float inv = red[0];
+      for (int g = threadIdx.x; g < a.G; g += blockDim.x) a.inv_sigma[g] = inv;
+      for (int i = threadIdx.x; i < a.G * R; i += blockDim.x) a.u_hist[i] = a.u[i % R];
+    }
+    for (int g = 0; g < a.G; ++g)
+      for (int k = threadIdx.x; k < kw; k += blockDim.x) a.v_hist[(int64_t)g * K + k0 + k] = vsh[k];
+    return;
+  }
+  for (int g = 0; g < a.G; ++g) {
+    // u_g = normalize(t[g])   (every CTA recomputes it; R <= 768)
+    const float* tg = a.t + (int64_t)g * R;
+    float nrm = sqrtf(block_sumsq(tg, R, red));
+    float inv = 1.0f / fmaxf(nrm, a.eps);
+    for (int r = threadIdx.x; r < R; r += blockDim.x) ush[r] = tg[r] * inv;
+    for (int k = threadIdx.x; k < kwmax; k += blockDim.x) qsh[k] = 0.f;
+    __syncthreads();
+    if (blockIdx.x == 0) for (int r = threadIdx.x; r < R; r += blockDim.x) a.u_hist[(int64_t)g * R + r] = ush[r];
+    // q[mine] = W[:, mine]^T u
+    for (int k = lane; k < kw; k += 32) {
+      float s = 0.f;
+      for (int r = warp; r < R; r += nwarps) s += ush[r] * Wat(r, k);
+      atomicAdd(&qsh[k], s);
+    }
+    __syncthreads();
+    float part = 0.f;
+    for (int k = threadIdx.x; k < kw; k += blockDim.x) part += qsh[k] * qsh[k];
+    part = warp_sum(part);
+    if (lane == 0) red[warp] = part;
+    __syncthreads();
+    if (threadIdx.x == 0) { float tot = 0.f; for (int w = 0; w < nwarps; ++w) tot += red[w]; atomicAdd(&a.nq[g], tot); }
+    grid.sync();
+    float qn = sqrtf(*((volatile float*)&a.nq[g]));
+    float qinv = 1.0f / fmaxf(qn, a.eps);
+    for (int k = threadIdx.x; k < kw; k += blockDim.x) { float vv = qsh[k] * qinv; vsh[k] = vv; a.v_hist[(int64_t)g * K + k0 + k] = vv; }
+    __syncthreads();
+    matvec(g + 1);
+    grid.sync();
+    if (blockIdx.x == 0) {
+      const float* tn = a.t + (int64_t)(g + 1) * R;
+      float s = 0.f;
+      for (int r = threadIdx.x; r < R; r += blockDim.x) s += ush[r] * ((volatile const float*)tn)[r];
+      s = warp_sum(s);
+      __syncthreads();
+      if (lane == 0) red[warp] = s;
+      __syncthreads();
+      if (threadIdx.x == 0) { float tot = 0.f; for (int w = 0; w < nwarps; ++w) tot += red[w]; a.inv_sigma[g] = 1.0f / tot; }
+      __syncthreads();
+    }
+  }
+  // persist final u, v
+  if (blockIdx.x == 0) for (int r = threadIdx.x; r < R; r += blockDim.x) a.u[r] = ush[r];
+  for (int k = threadIdx.x; k < kw; k += blockDim.x) a.v[k0 + k] = vsh[k];
+}
+__global__ void sn_bwd_kernel(const float* __restrict__ dis, const float* __restrict__ is, const float* __restrict__ uh, const float* __restrict__ vh,
+                              float* __restrict__ dw, int R, int K, int G, int acc) {
+  int64_t total = (int64_t)R * K;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int k = i % K; int r = i / K;
+    float s = 0.f;
+    for (int g = 0; g < G; ++g) s += (-dis[g] * is[g] * is[g]) * uh[(int64_t)g * R + r] * vh[(int64_t)g * K + k];
+    if (acc) dw[i] += s; else dw[i] = s;
+  }
+}
+
+// exposed to conv_umma.cu / api
+int launch_conv_simt_fwd(const float* x, const float* wp, const float* bias, const float* scale, const float* res, float* y,
+                         int N, int D, int H, int W, int Cin, int Cout, int kd, int kh, int kw, int G, int act, cudaStream_t st) {
+  ConvDims d{N, D, H, W, Cin, Cout, kd, kh, kw, G};
+  int64_t M = (int64_t)N * D * H * W;
+  dim3 grid((unsigned)ceil_div(M, 64), (unsigned)ceil_div(Cout, 64));
+  conv_simt_fwd_kernel<64, 64, 16><<<grid, 256, 0, st>>>(x, wp, bias, scale, res, y, d, act);
+  DGMR_CHECK_LAUNCH("conv_simt_fwd");
+  return 0;
+}
+int launch_conv_simt_wgrad(const float* x, const float* dz, float* dwp, int N, int D, int H, int W, int Cin, int Cout, int kd, int kh, int kw, cudaStream_t st) {
+  ConvDims d{N, D, H, W, Cin, Cout, kd, kh, kw, 1};
+  int taps = kd * kh * kw;
+  int64_t M = (int64_t)N * D * H * W;
+  int co_tiles = (int)ceil_div(Cout, 64), ci_tiles = (int)ceil_div(Cin, 64);
+  int64_t base = (int64_t)co_tiles * ci_tiles * taps;
+  int64_t want = (int64_t)sm_count() * 4;
+  int64_t ksplit = ceil_div(want, base);
+  int64_t max_split = ceil_div(M, 256);
+  if (ksplit > max_split) ksplit = max_split;
+  if (ksplit < 1) ksplit = 1;
+  if (ksplit > 65535) ksplit = 65535;
+  int64_t chunk = ceil_div(ceil_div(M, ksplit), 16) * 16;
+  ksplit = ceil_div(M, chunk);
+  if (cudaMemsetAsync(dwp, 0, sizeof(float) * (size_t)taps * Cout * Cin, st) != cudaSuccess) { set_error("conv_simt_wgrad: memset failed"); return 2; }
+  dim3 grid((unsigned)(co_tiles * ci_tiles), (unsigned)taps, (unsigned)ksplit);
+  conv_simt_wgrad_kernel<64, 64, 16><<<grid, 256, 0, st>>>(x, dz, dwp, d, ci_tiles, chunk);
+  DGMR_CHECK_LAUNCH("conv_simt_wgrad");
+  return 0;
+}
+
+}  // namespace dgmr
+
+using namespace dgmr;
+
+extern "C" {
+
+int dgmr_pack_weight(const float* w, float* packed, int Cout, int CinTot, int ci0, int Cin, int taps, int mode, dgmr_stream_t stream) {
+  DGMR_REQUIRE(ci0 >= 0 && ci0 + Cin <= CinTot && (mode == 0 || mode == 1), "dgmr_pack_weight: bad slice/mode");
+  int64_t total = (int64_t)taps * Cout * Cin;
+  if (total == 0) return 0;
+  pack_weight_kernel<<<ew_grid(total, 256, 2), 256, 0, S(stream)>>>(w, packed, Cout, CinTot, ci0, Cin, taps, mode);
+  DGMR_CHECK_LAUNCH("dgmr_pack_weight");
+  return 0;
+}
+int dgmr_unpack_wgrad(const float* packed, float* gw, int Cout, int CinTot, int ci0, int Cin, int taps, int accumulate, dgmr_stream_t stream) {
+  DGMR_REQUIRE(ci0 >= 0 && ci0 + Cin <= CinTot, "dgmr_unpack_wgrad: bad slice");
+  int64_t total = (int64_t)taps * Cout * Cin;
+  if (total == 0) return 0;
+  unpack_wgrad_kernel<<<ew_grid(total, 256, 2), 256, 0, S(stream)>>>(packed, gw, Cout, CinTot, ci0, Cin, taps, accumulate);
+  DGMR_CHECK_LAUNCH("dgmr_unpack_wgrad");
+  return 0;
+}
+int dgmr_conv_bwd_prep(const float* dy, const float* y, const float* res, const float* bias, const float* scale, float* dz, float* dbias, float* dscale,
+                       int64_t rows, int G, int Cout, int act, int accumulate_dbias, dgmr_stream_t stream) {
+  DGMR_REQUIRE(rows > 0 && G > 0 && Cout > 0, "dgmr_conv_bwd_prep: bad dims");
+  DGMR_REQUIRE(!(dscale && !scale), "dgmr_conv_bwd_prep: dscale requested without scale");
+  DGMR_REQUIRE(!((act == DGMR_ACT_RELU || dscale) && !y), "dgmr_conv_bwd_prep: y required");
+  if (dbias && !accumulate_dbias) DGMR_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * Cout, S(stream)));
+  if (dscale) DGMR_CUDA(cudaMemsetAsync(dscale, 0, sizeof(float) * (size_t)G * Cout, S(stream)));
+  int64_t bpg = (int64_t)sm_count() * 4 / G; if (bpg < 1) bpg = 1;
+  int64_t chunk = ceil_div(rows, bpg); if (chunk < 64) chunk = 64;
+  dim3 grid((unsigned)ceil_div(rows, chunk), G);
+  conv_bwd_prep_kernel<<<grid, 256, 256 * 2 * sizeof(double), S(stream)>>>(dy, y, res, bias, scale, dz, dbias, dscale, rows, Cout, chunk, act);
+  DGMR_CHECK_LAUNCH("dgmr_conv_bwd_prep");
+  return 0;
+}
+
+int dgmr_sn_power_iter(const float* w, float* u, float* v, int R, int K, int G, float eps, int training, float* inv_sigma, float* u_hist, float* v_hist,
+                       float* ws, dgmr_stream_t stream) {
+  DGMR_REQUIRE(R > 0 && K > 0 && G > 0, "dgmr_sn_power_iter: bad dims");
+  static int max_smem = 0, coop = -1;
+  if (coop < 0) {
+    int dev = 0; cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+    cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  }
+  DGMR_REQUIRE(coop == 1, "dgmr_sn_power_iter: device lacks cooperative launch");
+  int sms = sm_count();
+  // CTAs: enough that a slice fits in smem and <= 256 columns each; few CTAs for small weights
+  int64_t budget = (int64_t)max_smem - (int64_t)(R + 32) * 4 - 1024;
+  int nb = (int)ceil_div((int64_t)R * K, 16384);
+  if (nb < 1) nb = 1;
+  if (nb < ceil_div(K, 256)) nb = (int)ceil_div(K, 256);
+  if (nb > sms) nb = sms;
+  if (nb > K) nb = K;
+  int kw = (int)ceil_div(K, nb);
+  int in_smem = 1;
+  // grow nb until the slice fits
+  while (((int64_t)R * kw + 2 * kw) * 4 > budget && nb < sms && nb < K) { ++nb; kw = (int)ceil_div(K, nb); }
+  if (((int64_t)R * kw + 2 * kw) * 4 > budget) in_smem = 0;
+  nb = (int)ceil_div(K, kw);
+  size_t sh = (size_t)(R + 2 * kw + 32) * 4 + (in_smem ? (size_t)R * kw * 4 : 0);
+  DGMR_REQUIRE(sh <= (size_t)max_smem, "dgmr_sn_power_iter: R=%d too large for shared memory", R);
+  DGMR_CUDA(cudaFuncSetAttribute(sn_power_iter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
+  SnArgs a;
+  a.w = w; a.u = u; a.v = v; a.R = R; a.K = K; a.G = G; a.eps = eps; a.training = training;
+  a.inv_sigma = inv_sigma; a.u_hist = u_hist; a.v_hist = v_hist;
+  a.t = ws; a.nq = ws + (size_t)(G + 1) * R; a.kw = kw; a.in_smem = in_smem;
+  DGMR_CUDA(cudaMemsetAsync(ws, 0, sizeof(float) * ((size_t)(G + 1) * R + G), S(stream)));
+  void* args[] = {&a};
+  cudaError_t e = cudaLaunchCooperativeKernel((void*)sn_power_iter_kernel, dim3(nb), dim3(256), args, sh, S(stream));
+  if (e != cudaSuccess) { set_error("dgmr_sn_power_iter: cooperative launch failed: %s (nb=%d smem=%zu)", cudaGetErrorString(e), nb, sh); return 2; }
+  return 0;
+}
+int dgmr_sn_bwd(const float* d_inv_sigma, const float* inv_sigma, const float* u_hist, const float* v_hist, float* dw, int R, int K, int G, int accumulate,
+                dgmr_stream_t stream) {
+  int64_t total = (int64_t)R * K;
+  sn_bwd_kernel<<<ew_grid(total, 256, 2), 256, 0, S(stream)>>>(d_inv_sigma, inv_sigma, u_hist, v_hist, dw, R, K, G, accumulate);
+  DGMR_CHECK_LAUNCH("dgmr_sn_bwd");
+  return 0;
+}
+
+}  // extern "C"

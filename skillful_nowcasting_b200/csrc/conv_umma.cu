@@ -1,0 +1,405 @@
+// tcgen05 / TMA implicit-GEMM convolution for sm_100a (forward and dgrad; wgrad variant below).
+//
+//   y[pixel][co] = act( (sum_{tap,ci} x[pixel+tap][ci] * wp[tap][co][ci]) * scale[g][co] + bias[co] + res )
+//
+// B200 mapping (no im2col, no cuDNN):
+//   * A operand: the channels-last activation [N,D,H,W,C] is described to TMA as a 5-D tensor
+//     {C,W,H,D,N}.  One pipeline stage = one filter tap x BK channels: a TMA box {BK,bw,bh,1,bn}
+//     (bw*bh*bn = 128 output pixels) at coordinate (c0, w0+kw-pw, h0+kh-ph, d0+kd-pd, n0).  The
+//     halo / zero padding is TMA's out-of-bounds zero fill, so the 128xBK tile lands in shared memory
+//     already in the K-major swizzled layout tcgen05.mma consumes.
+//   * B operand: packed weights [tap][Cout][Cin] as a 3-D tensor, box {BK,BN,1}.
+//   * D accumulator: 128 lanes x BN fp32 columns in TMEM; kind::tf32, M=128, N=BN<=256, K=8 per MMA.
+//   * warp roles: warp0 = TMA producer, warp1 = MMA issuer (single elected thread),
+//     warps 2-5 = epilogue (tcgen05.ld 32x32b, fused scale/bias/residual/ReLU, NHWC float4 stores).
+//   * mbarrier full/empty ring between TMA and MMA; tcgen05.commit frees stages and signals the epilogue.
+#include "common.cuh"
+#include <cuda.h>
+
+namespace dgmr {
+
+int launch_conv_simt_fwd(const float*, const float*, const float*, const float*, const float*, float*, int, int, int, int, int, int, int, int, int, int, int, cudaStream_t);
+int launch_conv_simt_wgrad(const float*, const float*, float*, int, int, int, int, int, int, int, int, int, cudaStream_t);
+
+// ------------------------------------------------------------------ driver entry point for tensor maps
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+static CUtensorMapSwizzle swizzle_for(int row_bytes) {
+  return row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+}
+static int make_tmap(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box, int row_bytes) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return 2; }
+  cuuint64_t gd[5]; cuuint64_t gs[4]; cuuint32_t bx[5]; cuuint32_t es[5];
+  for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+  for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   swizzle_for(row_bytes), CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d): rank %d dims [%llu %llu %llu %llu %llu] box [%u %u %u %u %u] row_bytes %d", (int)r, rank,
+              (unsigned long long)gd[0], (unsigned long long)(rank > 1 ? gd[1] : 0), (unsigned long long)(rank > 2 ? gd[2] : 0),
+              (unsigned long long)(rank > 3 ? gd[3] : 0), (unsigned long long)(rank > 4 ? gd[4] : 0), bx[0], rank > 1 ? bx[1] : 0, rank > 2 ? bx[2] : 0,
+              rank > 3 ? bx[3] : 0, rank > 4 ? bx[4] : 0, row_bytes);
+    return 2;
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  return done != 0;
+}
+// bounded wait: a wedged pipeline traps (host sees a launch failure) instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  long long t0 = 0;
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins == 1024u) t0 = clock64();
+    if (spins > 1024u && (spins & 1023u) == 0 && clock64() - t0 > 4000000000LL) {
+      printf("dgmr umma: mbarrier wait timeout (block %d,%d thread %d bar %u parity %u)\n", blockIdx.x, blockIdx.y, threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(dst), "l"(tm),
+               "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst), "l"(tm), "r"(bar),
+               "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc),
+               "r"(idesc), "r"(accumulate)
+               : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]),
+        "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+// K-major swizzled shared-memory matrix descriptor (sm_100 "version 1" format, see
+// cute/arch/mma_sm100_desc.hpp SmemDescriptor): start>>4 | LBO>>4 <<16 | SBO>>4 <<32 | 1<<46 | layout<<61
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t sbo_bytes, uint32_t layout_type) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFFu);
+  d |= (uint64_t)1u << 16;                         // LBO (unused for swizzled K-major; canonical value 1)
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1u << 46;                         // descriptor version (Blackwell)
+  d |= (uint64_t)layout_type << 61;
+  return d;
+}
+
+struct UmmaConvParams {
+  int N, D, H, W, Cin, Cout, kd, kh, kw, G;
+  int bw, bh, bn;        // spatial box: bw*bh*bn == 128
+  int tiles_w, tiles_h;  // W/bw, H/bh
+  int BK;                // channels per stage (32/16/8)
+  int BN;                // N tile (multiple of 16, <= 256)
+  int stages;
+  int tmem_cols;
+  int act;
+  const float* bias; const float* scale; const float* res; float* y;
+};
+
+constexpr int kUmmaThreads = 192;  // warp0 TMA, warp1 MMA, warps 2..5 epilogue
+
+__global__ void __launch_bounds__(kUmmaThreads, 1)
+conv_umma_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const UmmaConvParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024-B alignment
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t a_bytes = 128u * p.BK * 4u, b_bytes = (uint32_t)p.BN * p.BK * 4u;
+  const uint32_t b_bytes_al = (b_bytes + 1023u) & ~1023u;
+  const uint32_t stage_bytes = a_bytes + b_bytes_al;
+  const uint32_t bar_base = base + p.stages * stage_bytes;  // full[stages], empty[stages], tmem_full, tmem_ptr
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (p.stages + s); };
+  const uint32_t tmem_full_bar = bar_base + 8u * (2 * p.stages);
+  const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * p.stages + 1);
+  volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_addr - raw));
+
+  // ---- tile coordinates
+  int mt = blockIdx.x;
+  const int tw_i = mt % p.tiles_w; mt /= p.tiles_w;
+  const int th_i = mt % p.tiles_h; mt /= p.tiles_h;
+  const int d0 = mt % p.D; mt /= p.D;
+  const int n0 = mt * p.bn;
+  const int w0 = tw_i * p.bw, h0 = th_i * p.bh;
+  const int co0 = blockIdx.y * p.BN;
+  const int taps = p.kd * p.kh * p.kw;
+  const int kchunks = p.Cin / p.BK;
+  const int num_kb = taps * kchunks;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    mbar_init(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    __syncwarp();
+    tmem_alloc(tmem_ptr_addr, (uint32_t)p.tmem_cols);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_gen;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer
+      int s = 0; uint32_t ph = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int tap = kb / kchunks, c0 = (kb - tap * kchunks) * p.BK;
+        const int tkw = tap % p.kw, tkh = (tap / p.kw) % p.kh, tkd = tap / (p.kw * p.kh);
+        mbar_wait(empty_bar(s), ph ^ 1u);
+        mbar_expect_tx(full_bar(s), a_bytes + b_bytes);
+        const uint32_t sa = base + s * stage_bytes;
+        tma_load_5d(sa, &tmA, full_bar(s), c0, w0 + tkw - p.kw / 2, h0 + tkh - p.kh / 2, d0 + tkd - p.kd / 2, n0);
+        tma_load_3d(sa + a_bytes, &tmB, full_bar(s), c0, co0, tap);
+        if (++s == p.stages) { s = 0; ph ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((128u >> 4) << 24);
+      const uint32_t row_bytes = p.BK * 4u;
+      const uint32_t layout = row_bytes == 128 ? 2u : (row_bytes == 64 ? 4u : 6u);
+      const uint32_t sbo = 8u * row_bytes;
+      int s = 0; uint32_t ph = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(full_bar(s), ph);
+        tc_fence_after();
+        const uint32_t sa = base + s * stage_bytes;
+        const uint64_t adesc = make_desc(sa, sbo, layout);
+        const uint64_t bdesc = make_desc(sa + a_bytes, sbo, layout);
+        for (int k = 0; k < p.BK / 8; ++k) {
+          // advance 8 tf32 = 32 bytes along K inside the swizzle row: +2 in the (addr>>4) field
+          umma_tf32(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(empty_bar(s));
+        if (++s == p.stages) { s = 0; ph ^= 1u; }
+      }
+      umma_commit(tmem_full_bar);
+    }
+  } else {
+    // ===== epilogue: warp w may only touch TMEM lanes [32*(w%4), 32*(w%4)+32)
+    const int q = warp & 3;
+    const int r = q * 32 + lane;  // accumulator row = pixel within the tile
+    const int wl = r % p.bw, hl = (r / p.bw) % p.bh, nl = r / (p.bw * p.bh);
+    const int n = n0 + nl, h = h0 + hl, w = w0 + wl;
+    const bool valid = (n < p.N) && (h < p.H) && (w < p.W);
+    const int64_t m = (((int64_t)n * p.D + d0) * p.H + h) * p.W + w;
+    const int g = valid ? n / (p.N / p.G) : 0;
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+    const bool vec4 = (p.Cout & 3) == 0;
+    for (int c = 0; c < p.BN; c += 16) {
+      if (co0 + c >= p.Cout) break;   // warp-uniform
+      float v[16];
+      tmem_ld16(trow + (uint32_t)c, v);
+      if (!valid) continue;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int co = co0 + c + j;
+        if (co < p.Cout) {
+          float t = v[j];
+          if (p.scale) t *= __ldg(p.scale + (int64_t)g * p.Cout + co);
+          if (p.bias) t += __ldg(p.bias + co);
+          v[j] = t;
+        }
+      }
+      float* yp = p.y + m * p.Cout + co0 + c;
+      const float* rp = p.res ? p.res + m * p.Cout + co0 + c : nullptr;
+      if (vec4) {
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+          if (co0 + c + j < p.Cout) {
+            float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            if (rp) { float4 rr = *reinterpret_cast<const float4*>(rp + j); o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w; }
+            if (p.act == DGMR_ACT_RELU) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+            *reinterpret_cast<float4*>(yp + j) = o;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          if (co0 + c + j < p.Cout) {
+            float o = v[j];
+            if (rp) o += rp[j];
+            if (p.act == DGMR_ACT_RELU) o = fmaxf(o, 0.f);
+            yp[j] = o;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
+}
+
+// ------------------------------------------------------------------ host side
+static int pick_bk(int Cin) { return (Cin % 32 == 0) ? 32 : (Cin % 16 == 0) ? 16 : (Cin % 8 == 0) ? 8 : 0; }
+static bool pick_box(int N, int H, int W, int* bw, int* bh, int* bn) {
+  // bw*bh*bn == 128, bw | W, bh | H, bn | N.  Prefer wide rows (contiguous TMA lines).
+  for (int w = 32; w >= 1; w >>= 1) {
+    if (W % w) continue;
+    if (w > W) continue;
+    int rest = 128 / w;
+    for (int h = rest; h >= 1; h >>= 1) {
+      if (h > H || H % h) continue;
+      int n = rest / h;
+      if (n > N || N % n) continue;
+      if (w * h * n != 128) continue;
+      *bw = w; *bh = h; *bn = n;
+      return true;
+    }
+  }
+  return false;
+}
+static bool umma_fwd_ok(int N, int D, int H, int W, int Cin, int Cout, int kd, int kh, int kw, int G) {
+  int bw, bh, bn;
+  if (pick_bk(Cin) == 0) return false;
+  if (Cout < 8) return false;
+  if (!((kd == 1 || kd == 3) && (kh == 1 || kh == 3) && (kw == 1 || kw == 3))) return false;
+  if (!pick_box(N, H, W, &bw, &bh, &bn)) return false;
+  if (G < 1 || N % G) return false;
+  (void)D;
+  return true;
+}
+
+int launch_conv_umma_fwd(const float* x, const float* wp, const float* bias, const float* scale, const float* res, float* y, int N, int D, int H, int W, int Cin,
+                         int Cout, int kd, int kh, int kw, int G, int act, cudaStream_t st) {
+  UmmaConvParams p;
+  p.N = N; p.D = D; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.kd = kd; p.kh = kh; p.kw = kw; p.G = G;
+  if (!pick_box(N, H, W, &p.bw, &p.bh, &p.bn)) { set_error("conv_umma_fwd: no 128-pixel box for N=%d H=%d W=%d", N, H, W); return 1; }
+  p.tiles_w = W / p.bw; p.tiles_h = H / p.bh;
+  p.BK = pick_bk(Cin);
+  if (p.BK == 0) { set_error("conv_umma_fwd: Cin=%d not a multiple of 8", Cin); return 1; }
+  int ntiles = (int)ceil_div(Cout, 256);
+  p.BN = (int)(ceil_div(ceil_div(Cout, ntiles), 16) * 16);
+  p.act = act; p.bias = bias; p.scale = scale; p.res = res; p.y = y;
+  p.tmem_cols = 32; while (p.tmem_cols < p.BN) p.tmem_cols <<= 1;
+  const uint32_t a_bytes = 128u * p.BK * 4u, b_bytes = ((uint32_t)p.BN * p.BK * 4u + 1023u) & ~1023u;
+  const uint32_t stage_bytes = a_bytes + b_bytes;
+  int stages = (int)((200u * 1024u) / stage_bytes);
+  if (stages > 6) stages = 6;
+  if (stages < 2) { set_error("conv_umma_fwd: stage too large"); return 1; }
+  p.stages = stages;
+  size_t smem = (size_t)stages * stage_bytes + 1024 /*align slack*/ + 8 * (2 * stages + 2);
+  const int taps = kd * kh * kw;
+  CUtensorMap tmA, tmB;
+  {
+    uint64_t dims[5] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)D, (uint64_t)N};
+    uint64_t str[4] = {(uint64_t)Cin * 4, (uint64_t)W * Cin * 4, (uint64_t)H * W * Cin * 4, (uint64_t)D * H * W * Cin * 4};
+    uint32_t box[5] = {(uint32_t)p.BK, (uint32_t)p.bw, (uint32_t)p.bh, 1u, (uint32_t)p.bn};
+    int e = make_tmap(&tmA, x, 5, dims, str, box, p.BK * 4);
+    if (e) return e;
+  }
+  {
+    uint64_t dims[3] = {(uint64_t)Cin, (uint64_t)Cout, (uint64_t)taps};
+    uint64_t str[2] = {(uint64_t)Cin * 4, (uint64_t)Cout * Cin * 4};
+    uint32_t box[3] = {(uint32_t)p.BK, (uint32_t)p.BN, 1u};
+    int e = make_tmap(&tmB, wp, 3, dims, str, box, p.BK * 4);
+    if (e) return e;
+  }
+  static size_t smem_set = 0;
+  if (smem > smem_set) {
+    if (cudaFuncSetAttribute(conv_umma_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)) != cudaSuccess) {
+      set_error("conv_umma_fwd: cannot raise dynamic smem limit"); return 2;
+    }
+    smem_set = 220 * 1024;
+  }
+  int64_t mtiles = (int64_t)(N / p.bn) * D * p.tiles_h * p.tiles_w;
+  dim3 grid((unsigned)mtiles, (unsigned)ntiles);
+  conv_umma_fwd_kernel<<<grid, kUmmaThreads, smem, st>>>(tmA, tmB, p);
+  DGMR_CHECK_LAUNCH("conv_umma_fwd");
+  return 0;
+}
+
+}  // namespace dgmr
+
+using namespace dgmr;
+
+extern "C" {
+
+int dgmr_conv_umma_supported(int N, int D, int H, int W, int Cin, int Cout, int kd, int kh, int kw) {
+  return umma_fwd_ok(N, D, H, W, Cin, Cout, kd, kh, kw, 1) ? 1 : 0;
+}
+int dgmr_wgrad_umma_supported(int N, int D, int H, int W, int Cin, int Cout, int kd, int kh, int kw) {
+  (void)N; (void)D; (void)H; (void)W; (void)Cin; (void)Cout; (void)kd; (void)kh; (void)kw;
+  return 0;  // tensor-core wgrad lands in a later milestone; SIMT kernel serves it
+}
+
+int dgmr_conv_fwd(const float* x, const float* x_lo, const float* wp, const float* wp_lo, const float* bias, const float* scale, const float* res, float* y,
+                  int N, int D, int H, int W, int Cin, int Cout, int kd, int kh, int kw, int G, int act, int algo, int precision, dgmr_stream_t stream) {
+  DGMR_REQUIRE(N > 0 && D > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, "dgmr_conv_fwd: bad dims");
+  DGMR_REQUIRE((kd == 1 || kd == 3) && (kh == 1 || kh == 3) && (kw == 1 || kw == 3), "dgmr_conv_fwd: kernel extent must be 1 or 3");
+  DGMR_REQUIRE(G >= 1 && N % G == 0, "dgmr_conv_fwd: N=%d not divisible by G=%d", N, G);
+  DGMR_REQUIRE(act == DGMR_ACT_NONE || act == DGMR_ACT_RELU, "dgmr_conv_fwd: bad act");
+  (void)x_lo; (void)wp_lo;
+  bool ok = umma_fwd_ok(N, D, H, W, Cin, Cout, kd, kh, kw, G);
+  if (algo == DGMR_ALGO_UMMA) DGMR_REQUIRE(ok, "dgmr_conv_fwd: shape not supported by the tcgen05 path");
+  DGMR_REQUIRE(precision == DGMR_PREC_TF32 || algo == DGMR_ALGO_SIMT || !ok, "dgmr_conv_fwd: 3xTF32 not implemented on the tcgen05 path yet");
+  if (algo == DGMR_ALGO_UMMA || (algo == DGMR_ALGO_AUTO && ok))
+    return launch_conv_umma_fwd(x, wp, bias, scale, res, y, N, D, H, W, Cin, Cout, kd, kh, kw, G, act, S(stream));
+  return launch_conv_simt_fwd(x, wp, bias, scale, res, y, N, D, H, W, Cin, Cout, kd, kh, kw, G, act, S(stream));
+}
+
+int dgmr_conv_wgrad(const float* x, const float* dz, const float* xT, const float* dzT, const float* xT_lo, const float* dzT_lo, float* dwp, int N, int D,
+                    int H, int W, int Cin, int Cout, int kd, int kh, int kw, int algo, int precision, dgmr_stream_t stream) {
+  (void)xT; (void)dzT; (void)xT_lo; (void)dzT_lo; (void)precision;
+  DGMR_REQUIRE(algo != DGMR_ALGO_UMMA, "dgmr_conv_wgrad: tcgen05 wgrad not available yet");
+  return launch_conv_simt_wgrad(x, dz, dwp, N, D, H, W, Cin, Cout, kd, kh, kw, S(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,694 @@
+// HBM-bound kernels of the DGMR hot path: layout permutes, pooling/upsampling, ConvGRU gate
+// arithmetic, BatchNorm (grouped batch statistics), losses, Adam.  All fp32, channels-last.
+// Design rule (B200): these are bandwidth kernels -> coalesced along C, float4 where C%4==0,
+// grid-stride with grids sized in multiples of the SM count, no shared-memory staging needed.
+#include "common.cuh"
+#include <mutex>
+#include <string.h>
+#include <math.h>
+
+namespace dgmr {
+
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;
+  }
+  return n;
+}
+
+// ------------------------------------------------------------------ permute
+struct PermuteArgs {
+  int ndim;
+  int64_t shape[8], sstr[8], dstr[8];
+};
+__global__ void permute_kernel(const float* __restrict__ src, float* __restrict__ dst, PermuteArgs a, int64_t total, int acc) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t rem = i, so = 0, dof = 0;
+#pragma unroll
+    for (int d = 7; d >= 0; --d) {
+      if (d < a.ndim) {
+        int64_t q = rem / a.shape[d];
+        int64_t r = rem - q * a.shape[d];
+        rem = q;
+        so += r * a.sstr[d];
+        dof += r * a.dstr[d];
+      }
+    }
+    float v = src[so];
+    if (acc) dst[dof] += v; else dst[dof] = v;
+  }
+}
+
+// ------------------------------------------------------------------ simple pointwise
+__global__ void axpby_kernel(float a, const float* __restrict__ x, float b, const float* __restrict__ y, float* __restrict__ out, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = y ? a * x[i] + b * y[i] : a * x[i];
+}
+__global__ void fill_kernel(float* x, float v, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) x[i] = v;
+}
+__global__ void relu_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) y[i] = fmaxf(x[i], 0.f);
+}
+__global__ void relu_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, float* __restrict__ dx, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) dx[i] = x[i] > 0.f ? dy[i] : 0.f;
+}
+__global__ void split_tf32_kernel(const float* __restrict__ x, float* __restrict__ hi, float* __restrict__ lo, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float v = x[i];
+    float h = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+    hi[i] = h;
+    lo[i] = v - h;
+  }
+}
+
+// ------------------------------------------------------------------ pool / upsample
+// y[n,do,ho,wo,c] = scale * sum_{window} x ; output dims floor(D/pd) ...
+__global__ void pool_sum_kernel(const float* __restrict__ x, float* __restrict__ y, int N, int D, int H, int W, int C,
+                                int pd, int ph, int pw, float scale) {
+  int Do = D / pd, Ho = H / ph, Wo = W / pw;
+  int64_t total = (int64_t)N * Do * Ho * Wo * C;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int c = i % C; int64_t r = i / C;
+    int wo = r % Wo; r /= Wo;
+    int ho = r % Ho; r /= Ho;
+    int dd = r % Do; int n = r / Do;
+    float s = 0.f;
+    for (int a = 0; a < pd; ++a)
+      for (int b = 0; b < ph; ++b)
+        for (int e = 0; e < pw; ++e)
+          s += x[((((int64_t)n * D + dd * pd + a) * H + ho * ph + b) * W + wo * pw + e) * C + c];
+    y[i] = s * scale;
+  }
+}
+// y[n,do,ho,wo,c] = scale * x[n,do/ud,ho/uh,wo/uw,c] if inside x's replicated extent else 0
+__global__ void upsample_kernel(const float* __restrict__ x, float* __restrict__ y, int N, int D, int H, int W, int C,
+                                int ud, int uh, int uw, int Do, int Ho, int Wo, float scale) {
+  int64_t total = (int64_t)N * Do * Ho * Wo * C;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int c = i % C; int64_t r = i / C;
+    int wo = r % Wo; r /= Wo;
+    int ho = r % Ho; r /= Ho;
+    int dd = r % Do; int n = r / Do;
+    int ds = dd / ud, hs = ho / uh, ws = wo / uw;
+    float v = 0.f;
+    if (ds < D && hs < H && ws < W) v = scale * x[((((int64_t)n * D + ds) * H + hs) * W + ws) * C + c];
+    y[i] = v;
+  }
+}
+
+// ------------------------------------------------------------------ ConvGRU gates (ref: dgmr/layers/ConvGRU.py:72-82)
+__global__ void gru_gate_fwd_kernel(const float* __restrict__ pre_r, int ld, const float* __restrict__ h, float* __restrict__ rh, int64_t rows, int Ch) {
+  int64_t total = rows * Ch;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = i / Ch; int c = i - r * Ch;
+    float g = 1.0f / (1.0f + expf(-pre_r[r * ld + c]));
+    rh[i] = g * h[i];
+  }
+}
+__global__ void gru_blend_fwd_kernel(const float* __restrict__ pre_u, int ld, const float* __restrict__ h, const float* __restrict__ c_, float* __restrict__ hn, int64_t rows, int Ch) {
+  int64_t total = rows * Ch;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = i / Ch; int c = i - r * Ch;
+    float u = 1.0f / (1.0f + expf(-pre_u[r * ld + c]));
+    hn[i] = u * h[i] + (1.0f - u) * c_[i];
+  }
+}
+__global__ void gru_gate_bwd_kernel(const float* __restrict__ d_rh, const float* __restrict__ pre_r, int ld, const float* __restrict__ h,
+                                    float* __restrict__ d_pre_r, int ldd, float* __restrict__ dh, int acc, int64_t rows, int Ch) {
+  int64_t total = rows * Ch;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = i / Ch; int c = i - r * Ch;
+    float g = 1.0f / (1.0f + expf(-pre_r[r * ld + c]));
+    float d = d_rh[i];
+    d_pre_r[r * ldd + c] = d * h[i] * g * (1.0f - g);
+    float v = d * g;
+    if (acc) dh[i] += v; else dh[i] = v;
+  }
+}
+__global__ void gru_blend_bwd_kernel(const float* __restrict__ d_hn, const float* __restrict__ pre_u, int ld, const float* __restrict__ h, const float* __restrict__ c_,
+                                     float* __restrict__ d_pre_u, int ldd, float* __restrict__ dc, float* __restrict__ dh, int acc, int64_t rows, int Ch) {
+  int64_t total = rows * Ch;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = i / Ch; int c = i - r * Ch;
+    float u = 1.0f / (1.0f + expf(-pre_u[r * ld + c]));
+    float d = d_hn[i];
+    d_pre_u[r * ldd + c] = d * (h[i] - c_[i]) * u * (1.0f - u);
+    dc[i] = d * (1.0f - u);
+    float v = d * u;
+    if (acc) dh[i] += v; else dh[i] = v;
+  }
+}
+
+// ------------------------------------------------------------------ BatchNorm
+// x: [G*rows, C].  Block = 256 threads: cpl = min(C,256) channel lanes x rp row lanes.
+// Each block reduces `chunk` rows of one group and atomically adds (double) into sums[g][c][0..1].
+__global__ void bn_stats_kernel(const float* __restrict__ x, double* __restrict__ sums, int64_t rows, int C, int64_t chunk) {
+  extern __shared__ double sh[];  // [rp][cpl][2]
+  int g = blockIdx.y;
+  int cpl = C < 256 ? C : 256;
+  int rp = 256 / cpl;
+  int cl = threadIdx.x % cpl, rl = threadIdx.x / cpl;
+  int64_t r0 = (int64_t)blockIdx.x * chunk;
+  int64_t r1 = r0 + chunk < rows ? r0 + chunk : rows;
+  const float* xg = x + (int64_t)g * rows * C;
+  for (int c = cl; c < C; c += cpl) {
+    double s = 0.0, q = 0.0;
+    if (rl < rp) {
+      float fs = 0.f, fq = 0.f;
+      int cnt = 0;
+      for (int64_t r = r0 + rl; r < r1; r += rp) {
+        float v = xg[r * C + c];
+        fs += v; fq += v * v;
+        if (++cnt == 64) { s += fs; q += fq; fs = fq = 0.f; cnt = 0; }
+      }
+      s += fs; q += fq;
+      sh[(rl * cpl + cl) * 2 + 0] = s;
+      sh[(rl * cpl + cl) * 2 + 1] = q;
+    }
+    __syncthreads();
+    if (rl == 0) {
+      for (int j = 1; j < rp; ++j) { s += sh[(j * cpl + cl) * 2]; q += sh[(j * cpl + cl) * 2 + 1]; }
+      atomicAdd(&sums[((int64_t)g * C + c) * 2 + 0], s);
+      atomicAdd(&sums[((int64_t)g * C + c) * 2 + 1], q);
+    }
+    __syncthreads();
+  }
+}
+__global__ void bn_finalize_kernel(const double* __restrict__ sums, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   float* __restrict__ rmean, float* __restrict__ rvar, int64_t rows, int G, int C, float eps, float mom, int training,
+                                   float* __restrict__ mean, float* __restrict__ invstd, float* __restrict__ a, float* __restrict__ b) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float ga = gamma ? gamma[c] : 1.f, be = beta ? beta[c] : 0.f;
+  float rm = rmean[c], rv = rvar[c];
+  for (int g = 0; g < G; ++g) {
+    float m, is;
+    if (training) {
+      double s = sums[((int64_t)g * C + c) * 2], q = sums[((int64_t)g * C + c) * 2 + 1];
+      double md = s / (double)rows;
+      double vd = q / (double)rows - md * md;
+      if (vd < 0) vd = 0;
+      m = (float)md;
+      float var = (float)vd;
+      is = 1.0f / sqrtf(var + eps);
+      float unb = rows > 1 ? (float)(vd * (double)rows / (double)(rows - 1)) : var;
+      rm = (1.f - mom) * rm + mom * m;
+      rv = (1.f - mom) * rv + mom * unb;
+    } else {
+      m = rm;
+      is = 1.0f / sqrtf(rv + eps);
+    }
+    int64_t o = (int64_t)g * C + c;
+    mean[o] = m; invstd[o] = is;
+    float aa = ga * is;
+    a[o] = aa; b[o] = be - m * aa;
+  }
+  if (training) { rmean[c] = rm; rvar[c] = rv; }
+}
+// y = act(a*x+b), optional nearest x2 upsample on write.  One thread per output element.
+__global__ void bn_apply_kernel(const float* __restrict__ x, const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ y,
+                                int64_t rows, int G, int C, int relu, int up2, int H, int W) {
+  int64_t orows = up2 ? rows * 4 : rows;
+  int64_t total = (int64_t)G * orows * C;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int c = i % C; int64_t r = i / C;  // global output row
+    int g = r / orows;
+    int64_t xr = r;
+    if (up2) {
+      int Wo = 2 * W, Ho = 2 * H;
+      int wo = r % Wo; int64_t t = r / Wo;
+      int ho = t % Ho; int64_t n = t / Ho;
+      xr = (n * H + (ho >> 1)) * W + (wo >> 1);
+    }
+    float v = a[(int64_t)g * C + c] * x[xr * C + c] + b[(int64_t)g * C + c];
+    y[i] = relu ? fmaxf(v, 0.f) : v;
+  }
+}
+// dpre at low-res row r, channel c (sums the 4 replicas if up2, applies relu mask)
+__device__ __forceinline__ float bn_dpre(const float* __restrict__ dy, int64_t r, int c, int C, int up2, int H, int W, float yv, int relu) {
+  float d;
+  if (up2) {
+    int w = r % W; int64_t t = r / W; int h = t % H; int64_t n = t / H;
+    int64_t base = ((n * 2 * H + 2 * h) * (2 * W) + 2 * w) * C + c;
+    d = dy[base] + dy[base + C] + dy[base + (int64_t)2 * W * C] + dy[base + (int64_t)2 * W * C + C];
+  } else {
+    d = dy[r * C + c];
+  }
+  if (relu && !(yv > 0.f)) d = 0.f;
+  return d;
+}
+__global__ void bn_bwd_reduce_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ a, const float* __restrict__ b,
+                                     const float* __restrict__ mean, const float* __restrict__ invstd, double* __restrict__ red,
+                                     int64_t rows, int C, int64_t chunk, int relu, int up2, int H, int W) {
+  extern __shared__ double sh[];
+  int g = blockIdx.y;
+  int cpl = C < 256 ? C : 256;
+  int rp = 256 / cpl;
+  int cl = threadIdx.x % cpl, rl = threadIdx.x / cpl;
+  int64_t r0 = (int64_t)blockIdx.x * chunk;
+  int64_t r1 = r0 + chunk < rows ? r0 + chunk : rows;
+  for (int c = cl; c < C; c += cpl) {
+    double s = 0.0, q = 0.0;
+    if (rl < rp) {
+      float aa = a[(int64_t)g * C + c], bb = b[(int64_t)g * C + c], m = mean[(int64_t)g * C + c], is = invstd[(int64_t)g * C + c];
+      float fs = 0.f, fq = 0.f; int cnt = 0;
+      for (int64_t r = r0 + rl; r < r1; r += rp) {
+        int64_t gr = (int64_t)g * rows + r;
+        float xv = x[gr * C + c];
+        float d = bn_dpre(dy, gr, c, C, up2, H, W, aa * xv + bb, relu);
+        fs += d; fq += d * (xv - m) * is;
+        if (++cnt == 64) { s += fs; q += fq; fs = fq = 0.f; cnt = 0; }
+      }
+      s += fs; q += fq;
+      sh[(rl * cpl + cl) * 2] = s; sh[(rl * cpl + cl) * 2 + 1] = q;
+    }
+    __syncthreads();
+    if (rl == 0) {
+      for (int j = 1; j < rp; ++j) { s += sh[(j * cpl + cl) * 2]; q += sh[(j * cpl + cl) * 2 + 1]; }
+      atomicAdd(&red[((int64_t)g * C + c) * 2], s);
+      atomicAdd(&red[((int64_t)g * C + c) * 2 + 1], q);
+    }
+    __syncthreads();
+  }
+}
+__global__ void bn_bwd_apply_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ a, const float* __restrict__ b,
+                                    const float* __restrict__ mean, const float* __restrict__ invstd, const double* __restrict__ red, float* __restrict__ dx,
+                                    int64_t rows, int G, int C, int relu, int up2, int H, int W, int training) {
+  int64_t total = (int64_t)G * rows * C;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int c = i % C; int64_t r = i / C; int g = r / rows;
+    int64_t o = (int64_t)g * C + c;
+    float aa = a[o], xv = x[i];
+    float d = bn_dpre(dy, r, c, C, up2, H, W, aa * xv + b[o], relu);
+    float v;
+    if (training) {
+      float xh = (xv - mean[o]) * invstd[o];
+      float m1 = (float)(red[o * 2] / (double)rows), m2 = (float)(red[o * 2 + 1] / (double)rows);
+      v = aa * (d - m1 - xh * m2);
+    } else {
+      v = aa * d;
+    }
+    dx[i] = v;
+  }
+}
+__global__ void bn_bwd_params_kernel(const double* __restrict__ red, float* __restrict__ dgamma, float* __restrict__ dbeta, int G, int C, int acc) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s = 0, q = 0;
+  for (int g = 0; g < G; ++g) { s += red[((int64_t)g * C + c) * 2]; q += red[((int64_t)g * C + c) * 2 + 1]; }
+  if (dgamma) { if (acc) dgamma[c] += (float)q; else dgamma[c] = (float)q; }
+  if (dbeta) { if (acc) dbeta[c] += (float)s; else dbeta[c] = (float)s; }
+}
+
+// ------------------------------------------------------------------ D head
+__global__ void sumpool_relu_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int N, int HW, int C) {
+  int64_t total = (int64_t)N * C;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int c = i % C; int64_t n = i / C;
+    float s = 0.f;
+    for (int p = 0; p < HW; ++p) s += fmaxf(x[(n * HW + p) * C + c], 0.f);
+    y[i] = s;
+  }
+}
+__global__ void sumpool_relu_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, float* __restrict__ dx, int N, int HW, int C) {
+  int64_t total = (int64_t)N * HW * C;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int c = i % C; int64_t n = i / ((int64_t)HW * C);
+    dx[i] = x[i] > 0.f ? dy[n * C + c] : 0.f;
+  }
+}
+
+// ------------------------------------------------------------------ attention (ref quirk: positions = (c,h), features = w)
+// Q[l][j] = q[b, h, j, c] with l = c*H + h, channels-last storage q[((b*H+h)*W+j)*C + c]
+__device__ __forceinline__ int64_t att_idx(int b, int l, int j, int H, int W, int C) {
+  int c = l / H, h = l - c * H;
+  return (((int64_t)b * H + h) * W + j) * C + c;
+}
+__global__ void attention_fwd_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v, float* __restrict__ out,
+                                     float* __restrict__ beta, int H, int W, int C) {
+  extern __shared__ float shf[];  // logits[L] + qrow[W] + red[32]
+  int L = C * H, l = blockIdx.x, b = blockIdx.y;
+  float* logit = shf; float* qrow = shf + L; float* red = qrow + W;
+  for (int j = threadIdx.x; j < W; j += blockDim.x) qrow[j] = q[att_idx(b, l, j, H, W, C)];
+  __syncthreads();
+  float mx = -INFINITY;
+  for (int m = threadIdx.x; m < L; m += blockDim.x) {
+    float s = 0.f;
+    for (int j = 0; j < W; ++j) s += qrow[j] * k[att_idx(b, m, j, H, W, C)];
+    logit[m] = s; mx = fmaxf(mx, s);
+  }
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  mx = red[0];
+  for (int w = 1; w < (blockDim.x >> 5); ++w) mx = fmaxf(mx, red[w]);
+  __syncthreads();
+  float sum = 0.f;
+  for (int m = threadIdx.x; m < L; m += blockDim.x) { float e = expf(logit[m] - mx); logit[m] = e; sum += e; }
+  sum = warp_sum(sum);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
+  __syncthreads();
+  sum = 0.f;
+  for (int w = 0; w < (blockDim.x >> 5); ++w) sum += red[w];
+  float inv = 1.0f / sum;
+  for (int m = threadIdx.x; m < L; m += blockDim.x) { float p = logit[m] * inv; logit[m] = p; beta[((int64_t)b * L + l) * L + m] = p; }
+  __syncthreads();
+  for (int j = threadIdx.x; j < W; j += blockDim.x) {
+    float s = 0.f;
+    for (int m = 0; m < L; ++m) s += logit[m] * v[att_idx(b, m, j, H, W, C)];
+    out[att_idx(b, l, j, H, W, C)] = s;
+  }
+}
+// per row l: dbeta, dlogit -> ws[b][l][:], dq row
+__global__ void attention_bwd1_kernel(const float* __restrict__ dout, const float* __restrict__ k, const float* __restrict__ v, const float* __restrict__ beta,
+                                      float* __restrict__ dq, float* __restrict__ ws, int H, int W, int C) {
+  extern __shared__ float shf[];  // dl[L] + dorow[W] + red[32]
+  int L = C * H, l = blockIdx.x, b = blockIdx.y;
+  float* dl = shf; float* dorow = shf + L; float* red = dorow + W;
+  for (int j = threadIdx.x; j < W; j += blockDim.x) dorow[j] = dout[att_idx(b, l, j, H, W, C)];
+  __syncthreads();
+  float dot = 0.f;
+  for (int m = threadIdx.x; m < L; m += blockDim.x) {
+    float s = 0.f;
+    for (int j = 0; j < W; ++j) s += dorow[j] * v[att_idx(b, m, j, H, W, C)];
+    dl[m] = s;
+    dot += s * beta[((int64_t)b * L + l) * L + m];
+  }
+  dot = warp_sum(dot);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = dot;
+  __syncthreads();
+  dot = 0.f;
+  for (int w = 0; w < (blockDim.x >> 5); ++w) dot += red[w];
+  for (int m = threadIdx.x; m < L; m += blockDim.x) {
+    float d = beta[((int64_t)b * L + l) * L + m] * (dl[m] - dot);
+    dl[m] = d; ws[((int64_t)b * L + l) * L + m] = d;
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < W; j += blockDim.x) {
+    float s = 0.f;
+    for (int m = 0; m < L; ++m) s += dl[m] * k[att_idx(b, m, j, H, W, C)];
+    dq[att_idx(b, l, j, H, W, C)] = s;
+  }
+}
+// per column m: dk[m][j] = sum_l dlogit[l][m] q[l][j]; dv[m][j] = sum_l beta[l][m] dout[l][j]
+__global__ void attention_bwd2_kernel(const float* __restrict__ dout, const float* __restrict__ q, const float* __restrict__ beta, const float* __restrict__ ws,
+                                      float* __restrict__ dk, float* __restrict__ dv, int H, int W, int C) {
+  int L = C * H, m = blockIdx.x, b = blockIdx.y;
+  for (int j = threadIdx.x; j < W; j += blockDim.x) {
+    float sk = 0.f, sv = 0.f;
+    for (int l = 0; l < L; ++l) {
+      sk += ws[((int64_t)b * L + l) * L + m] * q[att_idx(b, l, j, H, W, C)];
+      sv += beta[((int64_t)b * L + l) * L + m] * dout[att_idx(b, l, j, H, W, C)];
+    }
+    dk[att_idx(b, m, j, H, W, C)] = sk;
+    dv[att_idx(b, m, j, H, W, C)] = sv;
+  }
+}
+
+// ------------------------------------------------------------------ losses
+__global__ void hinge_disc_kernel(const float* __restrict__ s, int B, float* __restrict__ loss, float* __restrict__ ds) {
+  // single block; scores [2B][2]
+  __shared__ float red[32];
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < 4 * B; i += blockDim.x) {
+    int row = i >> 1;
+    float v = s[i], l, g;
+    if (row < B) { l = fmaxf(1.f - v, 0.f); g = (1.f - v) > 0.f ? -1.f / B : 0.f; }
+    else { l = fmaxf(1.f + v, 0.f); g = (1.f + v) > 0.f ? 1.f / B : 0.f; }
+    acc += l / B; ds[i] = g;
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) { float t = 0.f; for (int w = 0; w < (blockDim.x >> 5); ++w) t += red[w]; *loss = t; }
+}
+__global__ void hinge_gen_kernel(const float* __restrict__ s, int n, float* __restrict__ loss, float* __restrict__ ds) {
+  __shared__ float red[32];
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) { acc += s[i]; ds[i] = -1.f / n; }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) { float t = 0.f; for (int w = 0; w < (blockDim.x >> 5); ++w) t += red[w]; *loss = -t / n; }
+}
+__global__ void grid_cell_fwd_kernel(const float* __restrict__ gen, const float* __restrict__ tgt, float cap, double* __restrict__ acc, int64_t n) {
+  __shared__ double red[32];
+  double s = 0.0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float t = tgt[i];
+    s += (double)fabsf((gen[i] - t) * fmaxf(t + 1.f, cap));
+  }
+  s = warp_sum_d(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) { double t = 0; for (int w = 0; w < (blockDim.x >> 5); ++w) t += red[w]; atomicAdd(acc, t); }
+}
+__global__ void grid_cell_final_kernel(const double* __restrict__ acc, float coef, float* __restrict__ loss) { *loss = (float)(*acc) * coef; }
+__global__ void grid_cell_bwd_kernel(const float* __restrict__ gen, const float* __restrict__ tgt, float cap, float coef, const float* __restrict__ gout, float* __restrict__ dgen, int64_t n) {
+  float go = *gout * coef;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float t = tgt[i];
+    float w = fmaxf(t + 1.f, cap);
+    float d = (gen[i] - t) * w;
+    dgen[i] = d > 0.f ? w * go : (d < 0.f ? -w * go : 0.f);
+  }
+}
+
+// ------------------------------------------------------------------ Adam (torch.optim.Adam semantics)
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int64_t n,
+                            float lr, float b1, float b2, float eps, float bc1, float bc2_sqrt, float gs) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float gr = g[i] * gs;
+    float mi = b1 * m[i] + (1.f - b1) * gr;
+    float vi = b2 * v[i] + (1.f - b2) * gr * gr;
+    m[i] = mi; v[i] = vi;
+    float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] -= (lr / bc1) * (mi / denom);
+  }
+}
+
+}  // namespace dgmr
+
+using namespace dgmr;
+
+extern "C" {
+
+const char* dgmr_last_error(void) { return g_err; }
+int dgmr_abi_version(void) { return 1; }
+
+int dgmr_permute(const float* src, float* dst, int ndim, const int64_t* shape, const int64_t* sstr, const int64_t* dstr, int accumulate, dgmr_stream_t stream) {
+  DGMR_REQUIRE(ndim >= 1 && ndim <= 8, "dgmr_permute: ndim %d out of range", ndim);
+  PermuteArgs a; a.ndim = ndim;
+  int64_t total = 1;
+  for (int d = 0; d < 8; ++d) { a.shape[d] = 1; a.sstr[d] = 0; a.dstr[d] = 0; }
+  for (int d = 0; d < ndim; ++d) { a.shape[d] = shape[d]; a.sstr[d] = sstr[d]; a.dstr[d] = dstr[d]; total *= shape[d]; }
+  if (total == 0) return 0;
+  permute_kernel<<<ew_grid(total, 256, 2), 256, 0, S(stream)>>>(src, dst, a, total, accumulate);
+  DGMR_CHECK_LAUNCH("dgmr_permute");
+  return 0;
+}
+int dgmr_axpby(float a, const float* x, float b, const float* y, float* out, int64_t n, dgmr_stream_t stream) {
+  if (n == 0) return 0;
+  axpby_kernel<<<ew_grid(n, 256), 256, 0, S(stream)>>>(a, x, b, y, out, n);
+  DGMR_CHECK_LAUNCH("dgmr_axpby");
+  return 0;
+}
+int dgmr_fill(float* x, float value, int64_t n, dgmr_stream_t stream) {
+  if (n == 0) return 0;
+  fill_kernel<<<ew_grid(n, 256), 256, 0, S(stream)>>>(x, value, n);
+  DGMR_CHECK_LAUNCH("dgmr_fill");
+  return 0;
+}
+int dgmr_relu_fwd(const float* x, float* y, int64_t n, dgmr_stream_t stream) {
+  if (n == 0) return 0;
+  relu_fwd_kernel<<<ew_grid(n, 256), 256, 0, S(stream)>>>(x, y, n);
+  DGMR_CHECK_LAUNCH("dgmr_relu_fwd");
+  return 0;
+}
+int dgmr_relu_bwd(const float* dy, const float* x, float* dx, int64_t n, dgmr_stream_t stream) {
+  if (n == 0) return 0;
+  relu_bwd_kernel<<<ew_grid(n, 256), 256, 0, S(stream)>>>(dy, x, dx, n);
+  DGMR_CHECK_LAUNCH("dgmr_relu_bwd");
+  return 0;
+}
+int dgmr_split_tf32(const float* x, float* hi, float* lo, int64_t n, dgmr_stream_t stream) {
+  if (n == 0) return 0;
+  split_tf32_kernel<<<ew_grid(n, 256), 256, 0, S(stream)>>>(x, hi, lo, n);
+  DGMR_CHECK_LAUNCH("dgmr_split_tf32");
+  return 0;
+}
+int dgmr_pool_sum(const float* x, float* y, int N, int D, int H, int W, int C, int pd, int ph, int pw, float scale, dgmr_stream_t stream) {
+  DGMR_REQUIRE(pd >= 1 && ph >= 1 && pw >= 1 && pd <= 2 && ph <= 2 && pw <= 2, "dgmr_pool_sum: window must be 1 or 2");
+  int64_t total = (int64_t)N * (D / pd) * (H / ph) * (W / pw) * C;
+  if (total == 0) return 0;
+  pool_sum_kernel<<<ew_grid(total, 256, 2), 256, 0, S(stream)>>>(x, y, N, D, H, W, C, pd, ph, pw, scale);
+  DGMR_CHECK_LAUNCH("dgmr_pool_sum");
+  return 0;
+}
+int dgmr_upsample(const float* x, float* y, int N, int D, int H, int W, int C, int ud, int uh, int uw, int Do, int Ho, int Wo, float scale, dgmr_stream_t stream) {
+  DGMR_REQUIRE(Do >= D * ud && Ho >= H * uh && Wo >= W * uw, "dgmr_upsample: output smaller than replicated input");
+  int64_t total = (int64_t)N * Do * Ho * Wo * C;
+  if (total == 0) return 0;
+  upsample_kernel<<<ew_grid(total, 256, 2), 256, 0, S(stream)>>>(x, y, N, D, H, W, C, ud, uh, uw, Do, Ho, Wo, scale);
+  DGMR_CHECK_LAUNCH("dgmr_upsample");
+  return 0;
+}
+int dgmr_gru_gate_fwd(const float* pre_r, int ld, const float* h, float* rh, int64_t rows, int Ch, dgmr_stream_t stream) {
+  int64_t n = rows * Ch; if (n == 0) return 0;
+  gru_gate_fwd_kernel<<<ew_grid(n, 256, 2), 256, 0, S(stream)>>>(pre_r, ld, h, rh, rows, Ch);
+  DGMR_CHECK_LAUNCH("dgmr_gru_gate_fwd");
+  return 0;
+}
+int dgmr_gru_blend_fwd(const float* pre_u, int ld, const float* h, const float* c, float* hnew, int64_t rows, int Ch, dgmr_stream_t stream) {
+  int64_t n = rows * Ch; if (n == 0) return 0;
+  gru_blend_fwd_kernel<<<ew_grid(n, 256, 2), 256, 0, S(stream)>>>(pre_u, ld, h, c, hnew, rows, Ch);
+  DGMR_CHECK_LAUNCH("dgmr_gru_blend_fwd");
+  return 0;
+}
+int dgmr_gru_gate_bwd(const float* d_rh, const float* pre_r, int ld, const float* h, float* d_pre_r, int ldd, float* dh, int accumulate, int64_t rows, int Ch, dgmr_stream_t stream) {
+  int64_t n = rows * Ch; if (n == 0) return 0;
+  gru_gate_bwd_kernel<<<ew_grid(n, 256, 2), 256, 0, S(stream)>>>(d_rh, pre_r, ld, h, d_pre_r, ldd, dh, accumulate, rows, Ch);
+  DGMR_CHECK_LAUNCH("dgmr_gru_gate_bwd");
+  return 0;
+}
+int dgmr_gru_blend_bwd(const float* d_hnew, const float* pre_u, int ld, const float* h, const float* c, float* d_pre_u, int ldd, float* dc, float* dh, int accumulate, int64_t rows, int Ch, dgmr_stream_t stream) {
+  int64_t n = rows * Ch; if (n == 0) return 0;
+  gru_blend_bwd_kernel<<<ew_grid(n, 256, 2), 256, 0, S(stream)>>>(d_hnew, pre_u, ld, h, c, d_pre_u, ldd, dc, dh, accumulate, rows, Ch);
+  DGMR_CHECK_LAUNCH("dgmr_gru_blend_bwd");
+  return 0;
+}
+
+static int64_t bn_chunk(int64_t rows, int G) {
+  int64_t blocks_per_group = (int64_t)sm_count() * 4 / (G > 0 ? G : 1);
+  if (blocks_per_group < 1) blocks_per_group = 1;
+  int64_t chunk = ceil_div(rows, blocks_per_group);
+  if (chunk < 64) chunk = 64;
+  return chunk;
+}
+int dgmr_bn_stats(const float* x, double* sums, int64_t rows, int G, int C, dgmr_stream_t stream) {
+  DGMR_REQUIRE(rows > 0 && G > 0 && C > 0, "dgmr_bn_stats: bad dims");
+  DGMR_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * G * C, S(stream)));
+  int64_t chunk = bn_chunk(rows, G);
+  dim3 grid((unsigned)ceil_div(rows, chunk), G);
+  bn_stats_kernel<<<grid, 256, 256 * 2 * sizeof(double), S(stream)>>>(x, sums, rows, C, chunk);
+  DGMR_CHECK_LAUNCH("dgmr_bn_stats");
+  return 0;
+}
+int dgmr_bn_finalize(const double* sums, const float* gamma, const float* beta, float* running_mean, float* running_var, int64_t rows, int G, int C,
+                     float eps, float momentum, int training, float* mean, float* invstd, float* a, float* b, dgmr_stream_t stream) {
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, S(stream)>>>(sums, gamma, beta, running_mean, running_var, rows, G, C, eps, momentum, training, mean, invstd, a, b);
+  DGMR_CHECK_LAUNCH("dgmr_bn_finalize");
+  return 0;
+}
+int dgmr_bn_apply(const float* x, const float* a, const float* b, float* y, int64_t rows, int G, int C, int relu, int up2, int H, int W, dgmr_stream_t stream) {
+  int64_t total = (int64_t)G * rows * C * (up2 ? 4 : 1);
+  if (total == 0) return 0;
+  DGMR_REQUIRE(!up2 || (rows % ((int64_t)H * W) == 0), "dgmr_bn_apply: rows not a multiple of H*W");
+  bn_apply_kernel<<<ew_grid(total, 256, 2), 256, 0, S(stream)>>>(x, a, b, y, rows, G, C, relu, up2, H, W);
+  DGMR_CHECK_LAUNCH("dgmr_bn_apply");
+  return 0;
+}
+int dgmr_bn_bwd_reduce(const float* dy, const float* x, const float* a, const float* b, const float* mean, const float* invstd, double* red,
+                       int64_t rows, int G, int C, int relu, int up2, int H, int W, dgmr_stream_t stream) {
+  DGMR_CUDA(cudaMemsetAsync(red, 0, sizeof(double) * 2 * G * C, S(stream)));
+  int64_t chunk = bn_chunk(rows, G);
+  dim3 grid((unsigned)ceil_div(rows, chunk), G);
+  bn_bwd_reduce_kernel<<<grid, 256, 256 * 2 * sizeof(double), S(stream)>>>(dy, x, a, b, mean, invstd, red, rows, C, chunk, relu, up2, H, W);
+  DGMR_CHECK_LAUNCH("dgmr_bn_bwd_reduce");
+  return 0;
+}
+int dgmr_bn_bwd_apply(const float* dy, const float* x, const float* a, const float* b, const float* mean, const float* invstd, const float* gamma,
+                      const double* red, float* dx, float* dgamma, float* dbeta, int accumulate, int64_t rows, int G, int C, int relu, int up2,
+                      int H, int W, int training, dgmr_stream_t stream) {
+  (void)gamma;
+  int64_t total = (int64_t)G * rows * C;
+  if (dx && total) {
+    bn_bwd_apply_kernel<<<ew_grid(total, 256, 2), 256, 0, S(stream)>>>(dy, x, a, b, mean, invstd, red, dx, rows, G, C, relu, up2, H, W, training);
+    DGMR_CHECK_LAUNCH("dgmr_bn_bwd_apply");
+  }
+  if (dgamma || dbeta) {
+    bn_bwd_params_kernel<<<(C + 127) / 128, 128, 0, S(stream)>>>(red, dgamma, dbeta, G, C, accumulate);
+    DGMR_CHECK_LAUNCH("dgmr_bn_bwd_params");
+  }
+  return 0;
+}
+int dgmr_sumpool_relu_fwd(const float* x, float* y, int N, int HW, int C, dgmr_stream_t stream) {
+  int64_t n = (int64_t)N * C; if (n == 0) return 0;
+  sumpool_relu_fwd_kernel<<<ew_grid(n, 256, 1), 256, 0, S(stream)>>>(x, y, N, HW, C);
+  DGMR_CHECK_LAUNCH("dgmr_sumpool_relu_fwd");
+  return 0;
+}
+int dgmr_sumpool_relu_bwd(const float* dy, const float* x, float* dx, int N, int HW, int C, dgmr_stream_t stream) {
+  int64_t n = (int64_t)N * HW * C; if (n == 0) return 0;
+  sumpool_relu_bwd_kernel<<<ew_grid(n, 256, 1), 256, 0, S(stream)>>>(dy, x, dx, N, HW, C);
+  DGMR_CHECK_LAUNCH("dgmr_sumpool_relu_bwd");
+  return 0;
+}
+int dgmr_attention_fwd(const float* q, const float* k, const float* v, float* out, float* beta, int B, int H, int W, int C, dgmr_stream_t stream) {
+  int L = C * H;
+  size_t sh = (size_t)(L + W + 32) * sizeof(float);
+  DGMR_REQUIRE(sh <= 200 * 1024, "dgmr_attention_fwd: L=%d too large", L);
+  if (sh > 48 * 1024) DGMR_CUDA(cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
+  attention_fwd_kernel<<<dim3(L, B), 128, sh, S(stream)>>>(q, k, v, out, beta, H, W, C);
+  DGMR_CHECK_LAUNCH("dgmr_attention_fwd");
+  return 0;
+}
+int dgmr_attention_bwd(const float* dout, const float* q, const float* k, const float* v, const float* beta, float* dq, float* dk, float* dv, float* ws,
+                       int B, int H, int W, int C, dgmr_stream_t stream) {
+  int L = C * H;
+  size_t sh = (size_t)(L + W + 32) * sizeof(float);
+  DGMR_REQUIRE(sh <= 200 * 1024, "dgmr_attention_bwd: L=%d too large", L);
+  if (sh > 48 * 1024) DGMR_CUDA(cudaFuncSetAttribute(attention_bwd1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
+  attention_bwd1_kernel<<<dim3(L, B), 128, sh, S(stream)>>>(dout, k, v, beta, dq, ws, H, W, C);
+  DGMR_CHECK_LAUNCH("dgmr_attention_bwd1");
+  attention_bwd2_kernel<<<dim3(L, B), 32, 0, S(stream)>>>(dout, q, beta, ws, dk, dv, H, W, C);
+  DGMR_CHECK_LAUNCH("dgmr_attention_bwd2");
+  return 0;
+}
+int dgmr_hinge_disc(const float* scores, int B, float* loss, float* dscores, dgmr_stream_t stream) {
+  hinge_disc_kernel<<<1, 128, 0, S(stream)>>>(scores, B, loss, dscores);
+  DGMR_CHECK_LAUNCH("dgmr_hinge_disc");
+  return 0;
+}
+int dgmr_hinge_gen(const float* scores, int n, float* loss, float* dscores, dgmr_stream_t stream) {
+  hinge_gen_kernel<<<1, 128, 0, S(stream)>>>(scores, n, loss, dscores);
+  DGMR_CHECK_LAUNCH("dgmr_hinge_gen");
+  return 0;
+}
+int dgmr_grid_cell_fwd(const float* gen, const float* target, float cap, float coef, float* loss, double* acc, int64_t n, dgmr_stream_t stream) {
+  DGMR_REQUIRE(acc != nullptr, "dgmr_grid_cell_fwd: fp64 scratch (1 double) required");
+  DGMR_CUDA(cudaMemsetAsync(acc, 0, sizeof(double), S(stream)));
+  grid_cell_fwd_kernel<<<ew_grid(n, 256, 8), 256, 0, S(stream)>>>(gen, target, cap, acc, n);
+  DGMR_CHECK_LAUNCH("dgmr_grid_cell_fwd");
+  grid_cell_final_kernel<<<1, 1, 0, S(stream)>>>(acc, coef, loss);
+  DGMR_CHECK_LAUNCH("dgmr_grid_cell_final");
+  return 0;
+}
+int dgmr_grid_cell_bwd(const float* gen, const float* target, float cap, float coef, const float* gout, float* dgen, int64_t n, dgmr_stream_t stream) {
+  if (n == 0) return 0;
+  grid_cell_bwd_kernel<<<ew_grid(n, 256), 256, 0, S(stream)>>>(gen, target, cap, coef, gout, dgen, n);
+  DGMR_CHECK_LAUNCH("dgmr_grid_cell_bwd");
+  return 0;
+}
+int dgmr_adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps, int step, float grad_scale, dgmr_stream_t stream) {
+  if (n == 0) return 0;
+  DGMR_REQUIRE(step >= 1, "dgmr_adam: step must be >= 1");
+  float bc1 = (float)(1.0 - pow((double)beta1, (double)step));
+  float bc2s = (float)sqrt(1.0 - pow((double)beta2, (double)step));
+  adam_kernel<<<ew_grid(n, 256), 256, 0, S(stream)>>>(p, g, m, v, n, lr, beta1, beta2, eps, bc1, bc2s, grad_scale);
+  DGMR_CHECK_LAUNCH("dgmr_adam");
+  return 0;
+}
+
+}  // extern "C"
