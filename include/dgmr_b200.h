@@ -55,6 +55,10 @@ int dgmr_permute(const float* src, float* dst, int ndim, const int64_t* shape,
                  const int64_t* src_strides, const int64_t* dst_strides, int accumulate,
                  dgmr_stream_t stream);
 
+/* y[a][c] (+)= sum_r x[a][r][c]   (ref: torch.sum over stacked frame scores, discriminators.py:229-231,
+ * 135-137; backward of the latent batch-repeat generators.py:146-148) */
+int dgmr_reduce_mid(const float* x, float* y, int64_t A, int64_t R, int64_t C, int accumulate, dgmr_stream_t stream);
+
 /* ---- pointwise */
 /* out = a*x + b*y (y may be NULL) ; ref: residual adds, torch.stack(...).mean(0) (dgmr/dgmr.py:180) */
 int dgmr_axpby(float a, const float* x, float b, const float* y, float* out, int64_t n, dgmr_stream_t stream);
@@ -142,8 +146,8 @@ int dgmr_conv_fwd(const float* x, const float* x_lo, const float* wp, const floa
  * dscale[g][co] = sum dpre*(y - bias - res)/scale  (the <dY, Y-b> identity of SURVEY.md 8a/a13).
  * rows = pixels per group.  Any of dbias/dscale may be NULL. */
 int dgmr_conv_bwd_prep(const float* dy, const float* y, const float* res, const float* bias, const float* scale,
-                       float* dz, float* dbias, float* dscale, int64_t rows, int G, int Cout, int act,
-                       int accumulate_dbias, dgmr_stream_t stream);
+                       float* dz, float* dpre /*optional: unscaled dpre, = grad of res*/, float* dbias, float* dscale,
+                       int64_t rows, int G, int Cout, int act, int accumulate_dbias, dgmr_stream_t stream);
 /* dwp[tap][co][ci] = sum_pixels dz[p][co] * x[p+tap][ci]   (dwp fully overwritten)
  * xT/dzT: channel-major transposed copies [N][C][D][H][W] needed by the tensor-core path only
  * (NULL for SIMT). */
@@ -165,9 +169,9 @@ int dgmr_attention_bwd(const float* dout, const float* q, const float* k, const 
                        dgmr_stream_t stream);
 
 /* ---- losses (ref: dgmr/losses.py:307-319 hinge; :172-192 GridCellLoss + dgmr/dgmr.py:20-33 weight_fn) */
-/* scores: [2B][2] (real rows then generated rows; col 0 spatial, col 1 temporal).
- * loss = sum_col mean relu(1-real) + mean relu(1+gen);  dscores = d loss/d scores */
-int dgmr_hinge_disc(const float* scores, int B, float* loss, float* dscores, dgmr_stream_t stream);
+/* scores: [2B][cols] (real rows then generated rows; training uses cols=2: col 0 spatial, col 1 temporal).
+ * loss = sum_col ( mean relu(1-real) + mean relu(1+gen) );  dscores = d loss/d scores */
+int dgmr_hinge_disc(const float* scores, int B, int cols, float* loss, float* dscores, dgmr_stream_t stream);
 /* loss = -mean(scores_gen) over n values; dscores = -1/n */
 int dgmr_hinge_gen(const float* scores, int n, float* loss, float* dscores, dgmr_stream_t stream);
 /* loss = sum |(gen-target)*max(target+1,cap)| * coef ; gen/target n elements */

@@ -1,0 +1,287 @@
+"""ctypes binding of libdgmr_b200.so (the C ABI declared in include/dgmr_b200.h).
+
+PyTorch tensors cross this boundary as raw device pointers + the current CUDA stream; nothing
+else of torch is visible to the library.  There is NO CPU or library fallback: if the shared
+object is missing, or a tensor is not a contiguous fp32 CUDA tensor, calls raise RuntimeError.
+
+The argument types of every entry point are derived from the header itself, so the binding
+cannot drift from the ABI; `load()` also verifies that every declared symbol is exported.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import re
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+HEADER = os.path.join(os.path.dirname(_HERE), "include", "dgmr_b200.h")
+LIB_PATH = os.path.join(_HERE, "libdgmr_b200.so")
+
+ACT_NONE, ACT_RELU = 0, 1
+ALGO_AUTO, ALGO_SIMT, ALGO_UMMA = 0, 1, 2
+PREC_TF32, PREC_3XTF32 = 0, 1
+
+_CTYPES = {
+    "int": ctypes.c_int,
+    "int64_t": ctypes.c_int64,
+    "float": ctypes.c_float,
+    "dgmr_stream_t": ctypes.c_void_p,
+}
+
+
+def parse_header(path: str = HEADER) -> Dict[str, Tuple[str, List[Tuple[str, str]]]]:
+    """{name: (return type, [(ctype string, arg name), ...])} for every dgmr_* declaration."""
+    src = open(path).read()
+    src = re.sub(r"/\*.*?\*/", " ", src, flags=re.S)
+    out = {}
+    for m in re.finditer(r"\b(int|const char\*)\s+(dgmr_\w+)\s*\(([^;{]*?)\)\s*;", src, flags=re.S):
+        ret, name, args = m.group(1), m.group(2), " ".join(m.group(3).split())
+        alist = []
+        if args and args != "void":
+            for a in args.split(","):
+                a = a.strip()
+                mm = re.match(r"(.*?)(\w+)$", a)
+                alist.append((mm.group(1).strip(), mm.group(2)))
+        out[name] = (ret, alist)
+    return out
+
+
+def _to_ctype(t: str):
+    t = t.replace("const ", "").strip()
+    if t.endswith("*"):
+        return ctypes.c_void_p
+    return _CTYPES[t]
+
+
+_lib: Optional[ctypes.CDLL] = None
+_decls = None
+
+
+def load() -> ctypes.CDLL:
+    """dlopen the library and check every symbol declared in the header (works without a GPU)."""
+    global _lib, _decls
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `python __graft_entry__.py` "
+            "(the B200 path has no CPU or library fallback)")
+    lib = ctypes.CDLL(LIB_PATH)
+    decls = parse_header()
+    for name, (ret, args) in decls.items():
+        try:
+            fn = getattr(lib, name)
+        except AttributeError as e:  # pragma: no cover
+            raise RuntimeError(f"libdgmr_b200.so does not export {name} declared in {HEADER}") from e
+        fn.restype = ctypes.c_char_p if ret != "int" else ctypes.c_int
+        fn.argtypes = [_to_ctype(t) for t, _ in args]
+    _lib, _decls = lib, decls
+    return lib
+
+
+def _ptr(t: Optional[torch.Tensor], name: str = "tensor") -> Optional[int]:
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError(f"dgmr_b200: {name} must be a CUDA tensor (no CPU fallback exists)")
+    if not t.is_contiguous():
+        raise RuntimeError(f"dgmr_b200: {name} must be contiguous")
+    return t.data_ptr()
+
+
+def _f32(t: Optional[torch.Tensor], name: str):
+    if t is not None and t.dtype != torch.float32:
+        raise RuntimeError(f"dgmr_b200: {name} must be float32, got {t.dtype}")
+    return _ptr(t, name)
+
+
+def _f64(t: Optional[torch.Tensor], name: str):
+    if t is not None and t.dtype != torch.float64:
+        raise RuntimeError(f"dgmr_b200: {name} must be float64, got {t.dtype}")
+    return _ptr(t, name)
+
+
+class CudaBackend:
+    """Thin tensor-level view of the C ABI.  Method names/arguments mirror include/dgmr_b200.h.
+    `launches` counts kernel-launching entry-point calls (reported by bench.py as gpu_launches)."""
+
+    name = "cuda"
+
+    def __init__(self):
+        self.lib = load()
+        self.launches = 0
+
+    # -- plumbing
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def _call(self, name, *args):
+        self.launches += 1
+        rc = getattr(self.lib, name)(*args, self._stream())
+        if rc != 0:
+            raise RuntimeError(f"{name} failed ({rc}): {self.lib.dgmr_last_error().decode()}")
+
+    def _query(self, name, *args) -> int:
+        return int(getattr(self.lib, name)(*args))
+
+    # -- queries
+    def conv_umma_supported(self, N, D, H, W, Cin, Cout, kd, kh, kw) -> bool:
+        return bool(self._query("dgmr_conv_umma_supported", N, D, H, W, Cin, Cout, kd, kh, kw))
+
+    def wgrad_umma_supported(self, N, D, H, W, Cin, Cout, kd, kh, kw) -> bool:
+        return bool(self._query("dgmr_wgrad_umma_supported", N, D, H, W, Cin, Cout, kd, kh, kw))
+
+    # -- layout
+    def permute(self, src, dst, shape: Sequence[int], sstr: Sequence[int], dstr: Sequence[int], accumulate=False,
+                src_off: int = 0, dst_off: int = 0):
+        """src_off/dst_off: element offsets added to the base pointers (slices without torch views)."""
+        n = len(shape)
+        arr = ctypes.c_int64 * n
+        self._call("dgmr_permute", _f32(src, "src") + 4 * src_off, _f32(dst, "dst") + 4 * dst_off, n, arr(*shape), arr(*sstr),
+                   arr(*dstr), int(accumulate))
+
+    def reduce_mid(self, x, y, A, R, C, accumulate=False):
+        self._call("dgmr_reduce_mid", _f32(x, "x"), _f32(y, "y"), A, R, C, int(accumulate))
+
+    # -- pointwise
+    def axpby(self, a, x, b, y, out):
+        self._call("dgmr_axpby", float(a), _f32(x, "x"), float(b), _f32(y, "y"), _f32(out, "out"), out.numel())
+
+    def fill(self, x, value):
+        self._call("dgmr_fill", _f32(x, "x"), float(value), x.numel())
+
+    def relu_fwd(self, x, y):
+        self._call("dgmr_relu_fwd", _f32(x, "x"), _f32(y, "y"), x.numel())
+
+    def relu_bwd(self, dy, x, dx):
+        self._call("dgmr_relu_bwd", _f32(dy, "dy"), _f32(x, "x"), _f32(dx, "dx"), x.numel())
+
+    def split_tf32(self, x, hi, lo):
+        self._call("dgmr_split_tf32", _f32(x, "x"), _f32(hi, "hi"), _f32(lo, "lo"), x.numel())
+
+    def pool_sum(self, x, y, N, D, H, W, C, pd, ph, pw, scale):
+        self._call("dgmr_pool_sum", _f32(x, "x"), _f32(y, "y"), N, D, H, W, C, pd, ph, pw, float(scale))
+
+    def upsample(self, x, y, N, D, H, W, C, ud, uh, uw, Do, Ho, Wo, scale):
+        self._call("dgmr_upsample", _f32(x, "x"), _f32(y, "y"), N, D, H, W, C, ud, uh, uw, Do, Ho, Wo, float(scale))
+
+    # -- GRU
+    def gru_gate_fwd(self, pre_r, ld, h, rh, rows, Ch):
+        self._call("dgmr_gru_gate_fwd", _f32(pre_r, "pre_r"), ld, _f32(h, "h"), _f32(rh, "rh"), rows, Ch)
+
+    def gru_blend_fwd(self, pre_u, ld, h, c, hnew, rows, Ch):
+        self._call("dgmr_gru_blend_fwd", _f32(pre_u, "pre_u"), ld, _f32(h, "h"), _f32(c, "c"), _f32(hnew, "hnew"), rows, Ch)
+
+    def gru_gate_bwd(self, d_rh, pre_r, ld, h, d_pre_r, ldd, dh, accumulate, rows, Ch):
+        self._call("dgmr_gru_gate_bwd", _f32(d_rh, "d_rh"), _f32(pre_r, "pre_r"), ld, _f32(h, "h"), _f32(d_pre_r, "d_pre_r"), ldd,
+                   _f32(dh, "dh"), int(accumulate), rows, Ch)
+
+    def gru_blend_bwd(self, d_hnew, pre_u, ld, h, c, d_pre_u, ldd, dc, dh, accumulate, rows, Ch):
+        self._call("dgmr_gru_blend_bwd", _f32(d_hnew, "d_hnew"), _f32(pre_u, "pre_u"), ld, _f32(h, "h"), _f32(c, "c"),
+                   _f32(d_pre_u, "d_pre_u"), ldd, _f32(dc, "dc"), _f32(dh, "dh"), int(accumulate), rows, Ch)
+
+    # -- BatchNorm
+    def bn_stats(self, x, sums, rows, G, C):
+        self._call("dgmr_bn_stats", _f32(x, "x"), _f64(sums, "sums"), rows, G, C)
+
+    def bn_finalize(self, sums, gamma, beta, rmean, rvar, rows, G, C, eps, momentum, training, mean, invstd, a, b):
+        self._call("dgmr_bn_finalize", _f64(sums, "sums"), _f32(gamma, "gamma"), _f32(beta, "beta"), _f32(rmean, "running_mean"),
+                   _f32(rvar, "running_var"), rows, G, C, float(eps), float(momentum), int(training), _f32(mean, "mean"),
+                   _f32(invstd, "invstd"), _f32(a, "a"), _f32(b, "b"))
+
+    def bn_apply(self, x, a, b, y, rows, G, C, relu, up2, H, W):
+        self._call("dgmr_bn_apply", _f32(x, "x"), _f32(a, "a"), _f32(b, "b"), _f32(y, "y"), rows, G, C, int(relu), int(up2), H, W)
+
+    def bn_bwd_reduce(self, dy, x, a, b, mean, invstd, red, rows, G, C, relu, up2, H, W):
+        self._call("dgmr_bn_bwd_reduce", _f32(dy, "dy"), _f32(x, "x"), _f32(a, "a"), _f32(b, "b"), _f32(mean, "mean"),
+                   _f32(invstd, "invstd"), _f64(red, "red"), rows, G, C, int(relu), int(up2), H, W)
+
+    def bn_bwd_apply(self, dy, x, a, b, mean, invstd, gamma, red, dx, dgamma, dbeta, accumulate, rows, G, C, relu, up2, H, W, training):
+        self._call("dgmr_bn_bwd_apply", _f32(dy, "dy"), _f32(x, "x"), _f32(a, "a"), _f32(b, "b"), _f32(mean, "mean"),
+                   _f32(invstd, "invstd"), _f32(gamma, "gamma"), _f64(red, "red"), _f32(dx, "dx"), _f32(dgamma, "dgamma"),
+                   _f32(dbeta, "dbeta"), int(accumulate), rows, G, C, int(relu), int(up2), H, W, int(training))
+
+    # -- spectral norm
+    def sn_power_iter(self, w, u, v, R, K, G, eps, training, inv_sigma, u_hist, v_hist, ws):
+        self._call("dgmr_sn_power_iter", _f32(w, "w"), _f32(u, "u"), _f32(v, "v"), R, K, G, float(eps), int(training),
+                   _f32(inv_sigma, "inv_sigma"), _f32(u_hist, "u_hist"), _f32(v_hist, "v_hist"), _f32(ws, "ws"))
+
+    def sn_bwd(self, d_inv_sigma, inv_sigma, u_hist, v_hist, dw, R, K, G, accumulate):
+        self._call("dgmr_sn_bwd", _f32(d_inv_sigma, "d_inv_sigma"), _f32(inv_sigma, "inv_sigma"), _f32(u_hist, "u_hist"),
+                   _f32(v_hist, "v_hist"), _f32(dw, "dw"), R, K, G, int(accumulate))
+
+    # -- conv
+    def pack_weight(self, w, packed, Cout, CinTot, ci0, Cin, taps, mode):
+        self._call("dgmr_pack_weight", _f32(w, "w"), _f32(packed, "packed"), Cout, CinTot, ci0, Cin, taps, mode)
+
+    def unpack_wgrad(self, packed, gw, Cout, CinTot, ci0, Cin, taps, accumulate):
+        self._call("dgmr_unpack_wgrad", _f32(packed, "packed"), _f32(gw, "gw"), Cout, CinTot, ci0, Cin, taps, int(accumulate))
+
+    def conv_fwd(self, x, wp, bias, scale, res, y, N, D, H, W, Cin, Cout, kd, kh, kw, G, act, algo=ALGO_AUTO, precision=PREC_TF32,
+                 x_lo=None, wp_lo=None):
+        self._call("dgmr_conv_fwd", _f32(x, "x"), _f32(x_lo, "x_lo"), _f32(wp, "wp"), _f32(wp_lo, "wp_lo"), _f32(bias, "bias"),
+                   _f32(scale, "scale"), _f32(res, "res"), _f32(y, "y"), N, D, H, W, Cin, Cout, kd, kh, kw, G, act, algo, precision)
+
+    def conv_bwd_prep(self, dy, y, res, bias, scale, dz, dpre, dbias, dscale, rows, G, Cout, act, accumulate_dbias=False):
+        self._call("dgmr_conv_bwd_prep", _f32(dy, "dy"), _f32(y, "y"), _f32(res, "res"), _f32(bias, "bias"), _f32(scale, "scale"),
+                   _f32(dz, "dz"), _f32(dpre, "dpre"), _f32(dbias, "dbias"), _f32(dscale, "dscale"), rows, G, Cout, act,
+                   int(accumulate_dbias))
+
+    def conv_wgrad(self, x, dz, dwp, N, D, H, W, Cin, Cout, kd, kh, kw, algo=ALGO_AUTO, precision=PREC_TF32, xT=None, dzT=None,
+                   xT_lo=None, dzT_lo=None):
+        self._call("dgmr_conv_wgrad", _f32(x, "x"), _f32(dz, "dz"), _f32(xT, "xT"), _f32(dzT, "dzT"), _f32(xT_lo, "xT_lo"),
+                   _f32(dzT_lo, "dzT_lo"), _f32(dwp, "dwp"), N, D, H, W, Cin, Cout, kd, kh, kw, algo, precision)
+
+    # -- D head / attention / losses / optimiser
+    def sumpool_relu_fwd(self, x, y, N, HW, C):
+        self._call("dgmr_sumpool_relu_fwd", _f32(x, "x"), _f32(y, "y"), N, HW, C)
+
+    def sumpool_relu_bwd(self, dy, x, dx, N, HW, C):
+        self._call("dgmr_sumpool_relu_bwd", _f32(dy, "dy"), _f32(x, "x"), _f32(dx, "dx"), N, HW, C)
+
+    def attention_fwd(self, q, k, v, out, beta, B, H, W, C):
+        self._call("dgmr_attention_fwd", _f32(q, "q"), _f32(k, "k"), _f32(v, "v"), _f32(out, "out"), _f32(beta, "beta"), B, H, W, C)
+
+    def attention_bwd(self, dout, q, k, v, beta, dq, dk, dv, ws, B, H, W, C):
+        self._call("dgmr_attention_bwd", _f32(dout, "dout"), _f32(q, "q"), _f32(k, "k"), _f32(v, "v"), _f32(beta, "beta"),
+                   _f32(dq, "dq"), _f32(dk, "dk"), _f32(dv, "dv"), _f32(ws, "ws"), B, H, W, C)
+
+    def hinge_disc(self, scores, B, cols, loss, dscores):
+        self._call("dgmr_hinge_disc", _f32(scores, "scores"), B, cols, _f32(loss, "loss"), _f32(dscores, "dscores"))
+
+    def hinge_gen(self, scores, n, loss, dscores):
+        self._call("dgmr_hinge_gen", _f32(scores, "scores"), n, _f32(loss, "loss"), _f32(dscores, "dscores"))
+
+    def grid_cell_fwd(self, gen, target, cap, coef, loss, acc_ws):
+        self._call("dgmr_grid_cell_fwd", _f32(gen, "gen"), _f32(target, "target"), float(cap), float(coef), _f32(loss, "loss"),
+                   _f64(acc_ws, "acc_ws"), gen.numel())
+
+    def grid_cell_bwd(self, gen, target, cap, coef, gout, dgen):
+        self._call("dgmr_grid_cell_bwd", _f32(gen, "gen"), _f32(target, "target"), float(cap), float(coef), _f32(gout, "gout"),
+                   _f32(dgen, "dgen"), gen.numel())
+
+    def adam(self, p, g, m, v, lr, beta1, beta2, eps, step, grad_scale=1.0):
+        self._call("dgmr_adam", _f32(p, "p"), _f32(g, "g"), _f32(m, "m"), _f32(v, "v"), p.numel(), float(lr), float(beta1),
+                   float(beta2), float(eps), int(step), float(grad_scale))
+
+
+_backend = None
+
+
+def backend():
+    """The active backend.  Product code gets the CUDA library or an error — never a fallback.
+    (tests/ may inject a host emulator of the ABI through set_backend() to exercise host logic.)"""
+    global _backend
+    if _backend is None:
+        _backend = CudaBackend()
+    return _backend
+
+
+def set_backend(b):
+    global _backend
+    old = _backend
+    _backend = b
+    return old

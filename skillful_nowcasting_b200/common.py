@@ -1,0 +1,217 @@
+"""Generator building blocks and the two conditioning stacks on the B200 path.
+
+Public constructors / forward signatures / state-dict keys follow the reference's dgmr/common.py
+(GBlock :17, UpsampleGBlock :87, DBlock :158, LBlock :241, ContextConditioningStack :303,
+LatentConditioningStack :427).  Every `forward` takes and returns NCHW tensors like the reference;
+internally each block has a channels-last `run(x, G)` used when blocks are chained, where G is the
+number of reference calls folded into the batch dimension (per-call BatchNorm statistics and
+spectral-norm sigmas become per-group quantities).
+"""
+from __future__ import annotations
+
+from typing import Tuple
+
+import torch
+import torch.nn as nn
+from huggingface_hub import PyTorchModelHubMixin
+
+from . import ops
+from .layers.Attention import AttentionLayer
+from .layers.core import BatchNorm, PlainConv, SNConv
+from .ops import ACT_NONE, ACT_RELU
+
+
+def _kernel(conv_type: str, k: int):
+    if conv_type == "standard":
+        return (k, k)
+    if conv_type == "3d":
+        return (k, k, k)
+    if conv_type == "coord":
+        raise NotImplementedError("conv_type='coord' (CoordConv) is outside the B200 hot path (SURVEY.md 2, row 8)")
+    raise ValueError(f"{conv_type} is not a recognized Conv method")
+
+
+class GBlock(nn.Module):
+    """Residual generator block without upsampling (ref: dgmr/common.py:17-84)."""
+
+    def __init__(self, input_channels: int = 12, output_channels: int = 12, conv_type: str = "standard",
+                 spectral_normalized_eps=0.0001):
+        super().__init__()
+        self.input_channels, self.output_channels = input_channels, output_channels
+        self.bn1 = BatchNorm(input_channels)
+        self.bn2 = BatchNorm(input_channels)
+        e = spectral_normalized_eps
+        self.conv_1x1 = SNConv(input_channels, output_channels, _kernel(conv_type, 1), eps=e)
+        self.first_conv_3x3 = SNConv(input_channels, input_channels, _kernel(conv_type, 3), eps=e)
+        self.last_conv_3x3 = SNConv(input_channels, output_channels, _kernel(conv_type, 3), eps=e)
+
+    def run(self, x, G: int = 1):
+        sc = x if x.shape[-1] == self.output_channels else self.conv_1x1.run(x, G)
+        y = self.bn1.run(x, G, relu=True)
+        y = self.first_conv_3x3.run(y, G)
+        y = self.bn2.run(y, G, relu=True)
+        return self.last_conv_3x3.run(y, G, res=sc)  # residual add fused in the conv epilogue
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        return ops.cl_to_nchw(self.run(ops.nchw_to_cl(x)))
+
+
+class UpsampleGBlock(nn.Module):
+    """Residual generator block with nearest x2 upsampling (ref: dgmr/common.py:87-155)."""
+
+    def __init__(self, input_channels: int = 12, output_channels: int = 12, conv_type: str = "standard",
+                 spectral_normalized_eps=0.0001):
+        super().__init__()
+        self.input_channels, self.output_channels = input_channels, output_channels
+        self.bn1 = BatchNorm(input_channels)
+        self.bn2 = BatchNorm(input_channels)
+        e = spectral_normalized_eps
+        self.conv_1x1 = SNConv(input_channels, output_channels, _kernel(conv_type, 1), eps=e)
+        self.first_conv_3x3 = SNConv(input_channels, input_channels, _kernel(conv_type, 3), eps=e)
+        self.last_conv_3x3 = SNConv(input_channels, output_channels, _kernel(conv_type, 3), eps=e)
+
+    def run(self, x, G: int = 1):
+        # conv1x1(up2(x)) == up2(conv1x1(x)) bit-for-bit (pointwise conv commutes with replication): 4x fewer MACs
+        sc = ops.upsample2(self.conv_1x1.run(x, G))
+        y = self.bn1.run(x, G, relu=True, up2=True)  # BN -> ReLU -> nearest x2 in one pass
+        y = self.first_conv_3x3.run(y, G)
+        y = self.bn2.run(y, G, relu=True)
+        return self.last_conv_3x3.run(y, G, res=sc)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        return ops.cl_to_nchw(self.run(ops.nchw_to_cl(x)))
+
+
+class DBlock(nn.Module):
+    """Residual down block, 2-D or 3-D (ref: dgmr/common.py:158-238)."""
+
+    def __init__(self, input_channels: int = 12, output_channels: int = 12, conv_type: str = "standard",
+                 first_relu: bool = True, keep_same_output: bool = False):
+        super().__init__()
+        self.input_channels, self.output_channels = input_channels, output_channels
+        self.first_relu, self.keep_same_output, self.conv_type = first_relu, keep_same_output, conv_type
+        self.conv_1x1 = SNConv(input_channels, output_channels, _kernel(conv_type, 1))
+        self.first_conv_3x3 = SNConv(input_channels, output_channels, _kernel(conv_type, 3))
+        self.last_conv_3x3 = SNConv(output_channels, output_channels, _kernel(conv_type, 3))
+
+    def _pool(self, x):
+        return ops.avg_pool(x, 2, 2, 2) if self.conv_type == "3d" else ops.avg_pool(x, 1, 2, 2)
+
+    def run(self, x, G: int = 1):
+        if self.input_channels != self.output_channels:
+            x1 = self.conv_1x1.run(x, G)
+            if not self.keep_same_output:
+                x1 = self._pool(x1)
+        else:
+            x1 = x
+        y = ops.relu(x) if self.first_relu else x
+        y = self.first_conv_3x3.run(y, G, act=ACT_RELU)  # the ReLU between the convs is fused
+        if self.keep_same_output:
+            return self.last_conv_3x3.run(y, G, res=x1)
+        y = self._pool(self.last_conv_3x3.run(y, G))
+        return ops.add(x1, y)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        return ops.cl_to_nchw(self.run(ops.nchw_to_cl(x)))
+
+
+class LBlock(nn.Module):
+    """Residual block of the latent stack, plain convolutions (ref: dgmr/common.py:241-300)."""
+
+    def __init__(self, input_channels: int = 12, output_channels: int = 12, kernel_size: int = 3, conv_type: str = "standard"):
+        super().__init__()
+        self.input_channels, self.output_channels = input_channels, output_channels
+        self.conv_1x1 = PlainConv(input_channels, output_channels - input_channels, _kernel(conv_type, 1))
+        self.first_conv_3x3 = PlainConv(input_channels, output_channels, _kernel(conv_type, kernel_size))
+        self.last_conv_3x3 = PlainConv(output_channels, output_channels, _kernel(conv_type, kernel_size))
+
+    def run(self, x):
+        if self.input_channels < self.output_channels:
+            sc = ops.concat_channels(x, self.conv_1x1.run(x))
+        else:
+            sc = x
+        y = self.first_conv_3x3.run(ops.relu(x), act=ACT_RELU)
+        return self.last_conv_3x3.run(y, res=sc)
+
+    def forward(self, x) -> torch.Tensor:
+        return ops.cl_to_nchw(self.run(ops.nchw_to_cl(x)))
+
+
+class ContextConditioningStack(nn.Module, PyTorchModelHubMixin):
+    """ref: dgmr/common.py:303-424.  The 4 context frames run as 4 groups of one launch."""
+
+    def __init__(self, input_channels: int = 1, output_channels: int = 768, num_context_steps: int = 4,
+                 conv_type: str = "standard"):
+        super().__init__()
+        self.input_channels, self.num_context_steps = input_channels, num_context_steps
+        oc, ic, t = output_channels, input_channels, num_context_steps
+        self.d1 = DBlock(4 * ic, ((oc // 4) * ic) // t, conv_type=conv_type)
+        self.d2 = DBlock(((oc // 4) * ic) // t, ((oc // 2) * ic) // t, conv_type=conv_type)
+        self.d3 = DBlock(((oc // 2) * ic) // t, (oc * ic) // t, conv_type=conv_type)
+        self.d4 = DBlock((oc * ic) // t, (oc * 2 * ic) // t, conv_type=conv_type)
+        k3 = _kernel(conv_type, 3)
+        self.conv1 = SNConv((oc // 4) * ic, (oc // 8) * ic, k3)
+        self.conv2 = SNConv((oc // 2) * ic, (oc // 4) * ic, k3)
+        self.conv3 = SNConv(oc * ic, (oc // 2) * ic, k3)
+        self.conv4 = SNConv(oc * 2 * ic, oc * ic, k3)
+
+    def run(self, x: torch.Tensor):
+        """x: [B,T,C,H,W] (reference layout) -> 4 channels-last states [B,1,h,w,c], largest first."""
+        x = x.contiguous()
+        b, t, c, h, w = x.shape
+        h2, w2 = h // 2, w // 2
+        # space-to-depth (PixelUnshuffle(2), :393) and regrouping to timestep-major in ONE permute:
+        # dst[t, b, h2, w2, c*4 + i*2 + j] = x[b, t, c, 2*h2+i, 2*w2+j]
+        ds = ops.contig_strides((t, b, h2, w2, 4 * c))
+        s = ops.permute(x, (t * b, 1, h2, w2, 4 * c), (b, t, c, h2, w2, 2, 2),
+                        (t * c * h * w, c * h * w, h * w, 2 * w, 2, w, 1),
+                        (ds[1], ds[0], 4, ds[2], ds[3], 2, 1))
+        outs = []
+        for blk, mix in ((self.d1, self.conv1), (self.d2, self.conv2), (self.d3, self.conv3), (self.d4, self.conv4)):
+            s = blk.run(s, G=t)
+            _, _, hh, ww, cc = s.shape
+            # "b t c h w -> b (c t) h w" (:423): mixed[b, h, w, c*T + t] = s[t, b, h, w, c]
+            mixed = ops.permute(s, (b, 1, hh, ww, cc * t), (t, b, hh * ww, cc),
+                                (b * hh * ww * cc, hh * ww * cc, cc, 1), (1, hh * ww * cc * t, cc * t, t))
+            outs.append(mix.run(mixed, 1, act=ACT_RELU))
+        return tuple(outs)
+
+    def forward(self, x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+        return tuple(ops.cl_to_nchw(s) for s in self.run(x))
+
+
+class LatentConditioningStack(nn.Module, PyTorchModelHubMixin):
+    """ref: dgmr/common.py:427-497.  Batch is always 1; z is drawn on the CPU default generator exactly
+    like the reference's `Normal(0,1).sample(shape)` so seeds reproduce."""
+
+    def __init__(self, shape: (int, int, int) = (8, 8, 8), output_channels: int = 768, use_attention: bool = True):
+        super().__init__()
+        self.shape = tuple(shape)
+        self.use_attention = use_attention
+        self.conv_3x3 = SNConv(shape[0], shape[0], (3, 3))
+        self.l_block1 = LBlock(shape[0], output_channels // 32)
+        self.l_block2 = LBlock(output_channels // 32, output_channels // 16)
+        self.l_block3 = LBlock(output_channels // 16, output_channels // 4)
+        if self.use_attention:
+            self.att_block = AttentionLayer(output_channels // 4, output_channels // 4)
+        self.l_block4 = LBlock(output_channels // 4, output_channels)
+
+    def sample_z(self, like: torch.Tensor) -> torch.Tensor:
+        s = tuple(self.shape) + (1,)
+        z = torch.normal(torch.zeros(s), torch.ones(s))  # == distribution.sample(self.shape), CPU RNG (:481)
+        # [C,H,W,1] -> channels-last [1,1,H,W,C]
+        z = z.squeeze(-1).permute(1, 2, 0).contiguous().unsqueeze(0).unsqueeze(0)
+        return z.to(device=like.device, dtype=like.dtype)
+
+    def run(self, x: torch.Tensor):
+        z = self.sample_z(x)
+        z = self.conv_3x3.run(z, 1)
+        z = self.l_block1.run(z)
+        z = self.l_block2.run(z)
+        z = self.l_block3.run(z)
+        if self.use_attention:
+            z = self.att_block.run(z)
+        return self.l_block4.run(z)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        return ops.cl_to_nchw(self.run(x))

@@ -218,8 +218,8 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ packed, float* __r
 // ------------------------------------------------------------------ backward prologue
 // rows = pixels per group; grid (row chunks, G); 256 threads as (cpl channel lanes x rp row lanes)
 __global__ void conv_bwd_prep_kernel(const float* __restrict__ dy, const float* __restrict__ y, const float* __restrict__ res, const float* __restrict__ bias,
-                                     const float* __restrict__ scale, float* __restrict__ dz, float* __restrict__ dbias, float* __restrict__ dscale,
-                                     int64_t rows, int C, int64_t chunk, int act) {
+                                     const float* __restrict__ scale, float* __restrict__ dz, float* __restrict__ dpre, float* __restrict__ dbias,
+                                     float* __restrict__ dscale, int64_t rows, int C, int64_t chunk, int act) {
   extern __shared__ double sh[];
   int g = blockIdx.y;
   int cpl = C < 256 ? C : 256;
@@ -239,6 +239,7 @@ __global__ void conv_bwd_prep_kernel(const float* __restrict__ dy, const float* 
         float d = dy[o];
         if (act == DGMR_ACT_RELU && !(yv > 0.f)) d = 0.f;
         if (dz) dz[o] = d * sc;
+        if (dpre) dpre[o] = d;
         fs += d;
         if (dscale) { float zs = yv - bi - (res ? res[o] : 0.f); fq += d * zs; }
         if (++cnt == 64) { s += fs; q += fq; fs = fq = 0.f; cnt = 0; }
@@ -438,8 +439,8 @@ int dgmr_unpack_wgrad(const float* packed, float* gw, int Cout, int CinTot, int 
   DGMR_CHECK_LAUNCH("dgmr_unpack_wgrad");
   return 0;
 }
-int dgmr_conv_bwd_prep(const float* dy, const float* y, const float* res, const float* bias, const float* scale, float* dz, float* dbias, float* dscale,
-                       int64_t rows, int G, int Cout, int act, int accumulate_dbias, dgmr_stream_t stream) {
+int dgmr_conv_bwd_prep(const float* dy, const float* y, const float* res, const float* bias, const float* scale, float* dz, float* dpre, float* dbias,
+                       float* dscale, int64_t rows, int G, int Cout, int act, int accumulate_dbias, dgmr_stream_t stream) {
   DGMR_REQUIRE(rows > 0 && G > 0 && Cout > 0, "dgmr_conv_bwd_prep: bad dims");
   DGMR_REQUIRE(!(dscale && !scale), "dgmr_conv_bwd_prep: dscale requested without scale");
   DGMR_REQUIRE(!((act == DGMR_ACT_RELU || dscale) && !y), "dgmr_conv_bwd_prep: y required");
@@ -448,7 +449,7 @@ int dgmr_conv_bwd_prep(const float* dy, const float* y, const float* res, const 
   int64_t bpg = (int64_t)sm_count() * 4 / G; if (bpg < 1) bpg = 1;
   int64_t chunk = ceil_div(rows, bpg); if (chunk < 64) chunk = 64;
   dim3 grid((unsigned)ceil_div(rows, chunk), G);
-  conv_bwd_prep_kernel<<<grid, 256, 256 * 2 * sizeof(double), S(stream)>>>(dy, y, res, bias, scale, dz, dbias, dscale, rows, Cout, chunk, act);
+  conv_bwd_prep_kernel<<<grid, 256, 256 * 2 * sizeof(double), S(stream)>>>(dy, y, res, bias, scale, dz, dpre, dbias, dscale, rows, Cout, chunk, act);
   DGMR_CHECK_LAUNCH("dgmr_conv_bwd_prep");
   return 0;
 }

@@ -72,6 +72,17 @@ __global__ void split_tf32_kernel(const float* __restrict__ x, float* __restrict
   }
 }
 
+// y[a][c] (+)= sum_r x[a][r][c]; grid (c blocks, r chunks, a)
+__global__ void reduce_mid_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t R, int64_t C, int64_t chunk) {
+  int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  int64_t a = blockIdx.z;
+  int64_t r0 = (int64_t)blockIdx.y * chunk, r1 = r0 + chunk < R ? r0 + chunk : R;
+  float s = 0.f;
+  for (int64_t r = r0; r < r1; ++r) s += x[(a * R + r) * C + c];
+  atomicAdd(&y[a * C + c], s);
+}
+
 // ------------------------------------------------------------------ pool / upsample
 // y[n,do,ho,wo,c] = scale * sum_{window} x ; output dims floor(D/pd) ...
 __global__ void pool_sum_kernel(const float* __restrict__ x, float* __restrict__ y, int N, int D, int H, int W, int C,
@@ -417,12 +428,12 @@ __global__ void attention_bwd2_kernel(const float* __restrict__ dout, const floa
 }
 
 // ------------------------------------------------------------------ losses
-__global__ void hinge_disc_kernel(const float* __restrict__ s, int B, float* __restrict__ loss, float* __restrict__ ds) {
-  // single block; scores [2B][2]
+__global__ void hinge_disc_kernel(const float* __restrict__ s, int B, int cols, float* __restrict__ loss, float* __restrict__ ds) {
+  // single block; scores [2B][cols]
   __shared__ float red[32];
   float acc = 0.f;
-  for (int i = threadIdx.x; i < 4 * B; i += blockDim.x) {
-    int row = i >> 1;
+  for (int i = threadIdx.x; i < 2 * B * cols; i += blockDim.x) {
+    int row = i / cols;
     float v = s[i], l, g;
     if (row < B) { l = fmaxf(1.f - v, 0.f); g = (1.f - v) > 0.f ? -1.f / B : 0.f; }
     else { l = fmaxf(1.f + v, 0.f); g = (1.f + v) > 0.f ? 1.f / B : 0.f; }
@@ -496,6 +507,20 @@ int dgmr_permute(const float* src, float* dst, int ndim, const int64_t* shape, c
   if (total == 0) return 0;
   permute_kernel<<<ew_grid(total, 256, 2), 256, 0, S(stream)>>>(src, dst, a, total, accumulate);
   DGMR_CHECK_LAUNCH("dgmr_permute");
+  return 0;
+}
+int dgmr_reduce_mid(const float* x, float* y, int64_t A, int64_t R, int64_t C, int accumulate, dgmr_stream_t stream) {
+  if (A * C == 0) return 0;
+  if (!accumulate) DGMR_CUDA(cudaMemsetAsync(y, 0, sizeof(float) * (size_t)(A * C), S(stream)));
+  if (R == 0) return 0;
+  DGMR_REQUIRE(A <= 65535, "dgmr_reduce_mid: A too large");
+  int64_t cb = ceil_div(C, 256);
+  int64_t want = ceil_div((int64_t)sm_count() * 4, cb * A);
+  if (want < 1) want = 1;
+  int64_t chunk = ceil_div(R, want); if (chunk < 8) chunk = 8;
+  int64_t rb = ceil_div(R, chunk); if (rb > 65535) { rb = 65535; chunk = ceil_div(R, rb); rb = ceil_div(R, chunk); }
+  reduce_mid_kernel<<<dim3((unsigned)cb, (unsigned)rb, (unsigned)A), 256, 0, S(stream)>>>(x, y, R, C, chunk);
+  DGMR_CHECK_LAUNCH("dgmr_reduce_mid");
   return 0;
 }
 int dgmr_axpby(float a, const float* x, float b, const float* y, float* out, int64_t n, dgmr_stream_t stream) {
@@ -656,8 +681,9 @@ int dgmr_attention_bwd(const float* dout, const float* q, const float* k, const 
   DGMR_CHECK_LAUNCH("dgmr_attention_bwd2");
   return 0;
 }
-int dgmr_hinge_disc(const float* scores, int B, float* loss, float* dscores, dgmr_stream_t stream) {
-  hinge_disc_kernel<<<1, 128, 0, S(stream)>>>(scores, B, loss, dscores);
+int dgmr_hinge_disc(const float* scores, int B, int cols, float* loss, float* dscores, dgmr_stream_t stream) {
+  DGMR_REQUIRE(B > 0 && cols > 0, "dgmr_hinge_disc: bad dims");
+  hinge_disc_kernel<<<1, 128, 0, S(stream)>>>(scores, B, cols, loss, dscores);
   DGMR_CHECK_LAUNCH("dgmr_hinge_disc");
   return 0;
 }

@@ -1,0 +1,91 @@
+"""ConvGRU on the B200 path (API of the reference's dgmr/layers/ConvGRU.py:8-111).
+
+Restructuring that keeps the reference's results (identities verified there):
+conv(cat[x, h]) = conv_x(x) + conv_h(h), so the input-dependent two thirds of every gate
+convolution are computed for ALL T timesteps in one launch (one group per timestep, each with its own
+spectral-norm sigma_t), and only the h-dependent third stays on the serial path.  The T power
+iterations a weight sees during one forward run inside a single spectral-norm launch.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Union
+
+import torch
+import torch.nn as nn
+
+from .. import ops
+from ..ops import ACT_NONE, ACT_RELU
+from .core import SNConv
+
+
+class ConvGRUCell(nn.Module):
+    """ref: dgmr/layers/ConvGRU.py:8-85 (three spectrally normalised 3x3 convs, eps 1e-4)."""
+
+    def __init__(self, input_channels: int, output_channels: int, kernel_size: int = 3, sn_eps: float = 0.0001):
+        super().__init__()
+        self._kernel_size = kernel_size
+        self._sn_eps = sn_eps
+        self.input_channels, self.output_channels = input_channels, output_channels
+        k = (kernel_size, kernel_size)
+        self.read_gate_conv = SNConv(input_channels, output_channels, k, eps=sn_eps)
+        self.update_gate_conv = SNConv(input_channels, output_channels, k, eps=sn_eps)
+        self.output_conv = SNConv(input_channels, output_channels, k, eps=sn_eps)
+
+    # ---- channels-last multi-step engine -------------------------------------------------
+    def run_sequence(self, xs: torch.Tensor, h0: torch.Tensor, T: int, shared_input: bool = False) -> torch.Tensor:
+        """xs: [T*B,1,H,W,Cx] timestep-major (or [1,1,H,W,Cx] with shared_input=True: the same input at every
+        step and for every batch element, as at the sampler's first level, ref: generators.py:146-149);
+        h0: [B,1,H,W,Ch].  Returns [T*B,1,H,W,Ch]."""
+        ch = self.output_channels
+        cx = self.input_channels - ch
+        B = h0.shape[0]
+        gates = (self.read_gate_conv, self.update_gate_conv, self.output_conv)
+        # one launch per weight: the T power iterations of this forward (ref: per-call parametrization)
+        scales = [g.scale_of(g.inv_sigma(T)) for g in gates]  # [T, Ch] each
+        xparts = []
+        for g, sc in zip(gates, scales):
+            if shared_input:
+                p = xs.numel()
+                x_rep = ops.repeat_mid(xs.reshape(1, p), T).reshape((T,) + tuple(xs.shape[1:]))
+                xp = ops.conv(x_rep, g.weight_orig, g.bias, sc, None, 0, cx, T, ACT_NONE)  # [T,1,H,W,Ch]
+                q = xp.numel() // T
+                xp = ops.repeat_mid(xp.reshape(T, q), B).reshape((T, B) + tuple(xp.shape[1:]))
+            else:
+                xp = ops.conv(xs, g.weight_orig, g.bias, sc, None, 0, cx, T, ACT_NONE)
+                xp = xp.reshape((T, B) + tuple(xp.shape[1:]))
+            xparts.append(xp.unbind(0))
+        srows = [sc.reshape(T, 1, ch).unbind(0) for sc in scales]
+        h = h0
+        outs = []
+        wr, wu, wc = (g.weight_orig for g in gates)
+        for t in range(T):
+            pre_r = ops.conv(h, wr, None, srows[0][t], xparts[0][t], cx, ch, 1, ACT_NONE)
+            pre_u = ops.conv(h, wu, None, srows[1][t], xparts[1][t], cx, ch, 1, ACT_NONE)
+            rh = ops.gru_gate(pre_r, h)
+            c = ops.conv(rh, wc, None, srows[2][t], xparts[2][t], cx, ch, 1, ACT_RELU)
+            h = ops.gru_blend(pre_u, h, c)
+            outs.append(h)
+        return torch.cat(outs, dim=0)
+
+    def forward(self, x: torch.Tensor, prev_state: torch.Tensor):
+        """NCHW in/out: (x [B,Cx,H,W], prev_state [B,Ch,H,W]) -> (out, new_state)."""
+        out = self.run_sequence(ops.nchw_to_cl(x), ops.nchw_to_cl(prev_state), 1)
+        out = ops.cl_to_nchw(out)
+        return out, out
+
+
+class ConvGRU(nn.Module):
+    """ref: dgmr/layers/ConvGRU.py:88-111."""
+
+    def __init__(self, input_channels: int, output_channels: int, kernel_size: int = 3, sn_eps=0.0001):
+        super().__init__()
+        self.cell = ConvGRUCell(input_channels, output_channels, kernel_size, sn_eps)
+
+    def forward(self, x: Union[torch.Tensor, Sequence[torch.Tensor]], hidden_state=None) -> torch.Tensor:
+        """x: list of T tensors [B,Cx,H,W] (or a tensor [T,B,Cx,H,W]); returns [T,B,Ch,H,W]."""
+        T = len(x)
+        xs = torch.cat([ops.nchw_to_cl(x[t]) for t in range(T)], dim=0)
+        out = self.cell.run_sequence(xs, ops.nchw_to_cl(hidden_state), T)
+        B = hidden_state.shape[0]
+        out = ops.cl_to_nchw(out)
+        return out.reshape((T, B) + tuple(out.shape[1:]))

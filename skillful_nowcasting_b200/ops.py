@@ -1,0 +1,695 @@
+"""Autograd layer over the C ABI: every function here is one (fused) kernel family of
+include/dgmr_b200.h with a hand-written backward that also runs through the C ABI.
+
+Internal activation format: contiguous fp32 channels-last tensors [N, D, H, W, C] (2-D: D == 1),
+images ordered group-major: N = G * (N // G), one *group* per reference call (timestep / frame).
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+from torch.autograd import Function
+
+from . import _lib
+from ._lib import ACT_NONE, ACT_RELU, ALGO_AUTO, ALGO_SIMT, ALGO_UMMA, PREC_TF32
+
+
+class config:
+    """Runtime knobs (tests flip these to cross-check the tensor-core path against the SIMT kernels)."""
+    conv_algo = ALGO_AUTO
+    wgrad_algo = ALGO_AUTO
+    precision = PREC_TF32
+
+
+def _be():
+    return _lib.backend()
+
+
+def _new(shape, like: torch.Tensor, dtype=torch.float32):
+    return torch.empty(tuple(shape), device=like.device, dtype=dtype)
+
+
+def _zeros(shape, like: torch.Tensor, dtype=torch.float32):
+    return torch.zeros(tuple(shape), device=like.device, dtype=dtype)
+
+
+def _c(t: Optional[torch.Tensor]):
+    return None if t is None else (t if t.is_contiguous() else t.contiguous())
+
+
+def contig_strides(shape: Sequence[int]) -> List[int]:
+    st, acc = [], 1
+    for s in reversed(shape):
+        st.append(acc)
+        acc *= s
+    return list(reversed(st))
+
+
+def _numel(shape):
+    n = 1
+    for s in shape:
+        n *= s
+    return n
+
+
+# ----------------------------------------------------------------------------- layout
+class _Permute(Function):
+    """dst[dstr . i] = src[sstr . i] for i in `shape`; backward gathers the other way.
+    The map must be injective on src (every src element read at most once)."""
+
+    @staticmethod
+    def forward(ctx, src, out_shape, shape, sstr, dstr, src_off, dst_off):
+        src = _c(src)
+        full = _numel(shape) == _numel(out_shape)
+        dst = _new(out_shape, src) if full else _zeros(out_shape, src)
+        _be().permute(src, dst, shape, sstr, dstr, False, src_off, dst_off)
+        ctx.meta = (tuple(src.shape), tuple(shape), tuple(sstr), tuple(dstr), src_off, dst_off)
+        return dst
+
+    @staticmethod
+    def backward(ctx, g):
+        src_shape, shape, sstr, dstr, src_off, dst_off = ctx.meta
+        g = _c(g)
+        full = _numel(shape) == _numel(src_shape)
+        gs = _new(src_shape, g) if full else _zeros(src_shape, g)
+        _be().permute(g, gs, shape, dstr, sstr, False, dst_off, src_off)
+        return gs, None, None, None, None, None, None
+
+
+def permute(src, out_shape, shape, sstr, dstr, src_off=0, dst_off=0):
+    return _Permute.apply(src, tuple(out_shape), tuple(shape), tuple(sstr), tuple(dstr), src_off, dst_off)
+
+
+def nchw_to_cl(x: torch.Tensor) -> torch.Tensor:
+    """[N,C,H,W] or [N,C,D,H,W] -> [N,D,H,W,C]."""
+    if x.dim() == 4:
+        n, c, h, w = x.shape
+        d = 1
+    else:
+        n, c, d, h, w = x.shape
+    if c == 1:
+        return x.reshape(n, d, h, w, 1)
+    sp = d * h * w
+    return permute(x, (n, d, h, w, c), (n, sp, c), (c * sp, 1, sp), (sp * c, c, 1))
+
+
+def cl_to_nchw(x: torch.Tensor, keep_depth: bool = False) -> torch.Tensor:
+    """[N,D,H,W,C] -> [N,C,H,W] (D == 1 and not keep_depth) or [N,C,D,H,W]."""
+    n, d, h, w, c = x.shape
+    out_shape = (n, c, d, h, w) if (keep_depth or d != 1) else (n, c, h, w)
+    if c == 1:
+        return x.reshape(out_shape)
+    sp = d * h * w
+    return permute(x, out_shape, (n, sp, c), (sp * c, c, 1), (c * sp, 1, sp))
+
+
+def space_to_depth(x: torch.Tensor) -> torch.Tensor:
+    """PixelUnshuffle(2) on channels-last: [N,D,H,W,C] -> [N,D,H/2,W/2,4C], channel c*4 + i*2 + j
+    (ref: torch PixelUnshuffle at dgmr/common.py:326,393; discriminators.py:69,166)."""
+    n, d, h, w, c = x.shape
+    h2, w2 = h // 2, w // 2
+    ss = contig_strides((n, d, h, w, c))
+    ds = contig_strides((n, d, h2, w2, 4 * c))
+    return permute(x, (n, d, h2, w2, 4 * c), (n, d, h2, w2, c, 2, 2),
+                   (ss[0], ss[1], 2 * ss[2], 2 * ss[3], 1, ss[2], ss[3]), (ds[0], ds[1], ds[2], ds[3], 4, 2, 1))
+
+
+class _ConcatC(Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        a, b = _c(a), _c(b)
+        ca, cb = a.shape[-1], b.shape[-1]
+        rows = a.numel() // ca
+        out = _new(tuple(a.shape[:-1]) + (ca + cb,), a)
+        _be().permute(a, out, (rows, ca), (ca, 1), (ca + cb, 1), False, 0, 0)
+        _be().permute(b, out, (rows, cb), (cb, 1), (ca + cb, 1), False, 0, ca)
+        ctx.meta = (tuple(a.shape), tuple(b.shape))
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        sa, sb = ctx.meta
+        g = _c(g)
+        ca, cb = sa[-1], sb[-1]
+        rows = _numel(sa) // ca
+        ga, gb = _new(sa, g), _new(sb, g)
+        _be().permute(g, ga, (rows, ca), (ca + cb, 1), (ca, 1), False, 0, 0)
+        _be().permute(g, gb, (rows, cb), (ca + cb, 1), (cb, 1), False, ca, 0)
+        return ga, gb
+
+
+def concat_channels(a, b):
+    return _ConcatC.apply(a, b)
+
+
+class _GatherFrames(Function):
+    """x: [N,T,P] (P = pixels*channels per frame) -> [G*N, P] with group g = frame idxs[g]
+    (ref: dgmr/discriminators.py:199-202; indices may repeat, so backward accumulates per group)."""
+
+    @staticmethod
+    def forward(ctx, x, idxs):
+        x = _c(x)
+        n, t, p = x.shape
+        out = _new((len(idxs) * n, p), x)
+        for g, i in enumerate(idxs):
+            _be().permute(x, out, (n, p), (t * p, 1), (p, 1), False, i * p, g * n * p)
+        ctx.meta = (tuple(x.shape), tuple(idxs))
+        return out
+
+    @staticmethod
+    def backward(ctx, go):
+        (n, t, p), idxs = ctx.meta
+        go = _c(go)
+        gx = _zeros((n, t, p), go)
+        for g, i in enumerate(idxs):
+            _be().permute(go, gx, (n, p), (p, 1), (t * p, 1), True, g * n * p, i * p)
+        return gx, None
+
+
+def gather_frames(x, idxs):
+    return _GatherFrames.apply(x, tuple(int(i) for i in idxs))
+
+
+class _RepeatMid(Function):
+    """x [A, P] -> [A, R, P] (broadcast); backward sums over R (ref: latent batch repeat generators.py:146-148)."""
+
+    @staticmethod
+    def forward(ctx, x, r):
+        x = _c(x)
+        a, p = x.shape
+        out = _new((a, r, p), x)
+        _be().permute(x, out, (a, r, p), (p, 0, 1), (r * p, p, 1), False, 0, 0)
+        ctx.r = r
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        g = _c(g)
+        a, r, p = g.shape
+        gx = _new((a, p), g)
+        _be().reduce_mid(g, gx, a, r, p, False)
+        return gx, None
+
+
+def repeat_mid(x, r):
+    return _RepeatMid.apply(x, r)
+
+
+class _ReduceMid(Function):
+    """x [A, R, C] -> [A, C] sum over R (ref: torch.sum over stacked per-frame scores, discriminators.py:229-231)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = _c(x)
+        a, r, c = x.shape
+        y = _new((a, c), x)
+        _be().reduce_mid(x, y, a, r, c, False)
+        ctx.r = r
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        g = _c(g)
+        a, c = g.shape
+        gx = _new((a, ctx.r, c), g)
+        _be().permute(g, gx, (a, ctx.r, c), (c, 0, 1), (ctx.r * c, c, 1), False, 0, 0)
+        return gx
+
+
+def reduce_mid(x):
+    return _ReduceMid.apply(x)
+
+
+# ----------------------------------------------------------------------------- pointwise
+class _Relu(Function):
+    @staticmethod
+    def forward(ctx, x):
+        x = _c(x)
+        y = torch.empty_like(x)
+        _be().relu_fwd(x, y)
+        ctx.save_for_backward(x)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        g = _c(g)
+        dx = torch.empty_like(x)
+        _be().relu_bwd(g, x, dx)
+        return dx
+
+
+def relu(x):
+    return _Relu.apply(x)
+
+
+class _Pool(Function):
+    """sum-pool * scale; backward = nearest upsample * scale."""
+
+    @staticmethod
+    def forward(ctx, x, pd, ph, pw, scale):
+        x = _c(x)
+        n, d, h, w, c = x.shape
+        y = _new((n, d // pd, h // ph, w // pw, c), x)
+        _be().pool_sum(x, y, n, d, h, w, c, pd, ph, pw, scale)
+        ctx.meta = (tuple(x.shape), pd, ph, pw, scale)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        (n, d, h, w, c), pd, ph, pw, scale = ctx.meta
+        g = _c(g)
+        gx = _new((n, d, h, w, c), g)
+        _be().upsample(g, gx, n, d // pd, h // ph, w // pw, c, pd, ph, pw, d, h, w, scale)
+        return gx, None, None, None, None
+
+
+def avg_pool(x, pd, ph, pw):
+    """AvgPool2d(2) / AvgPool3d(2) / AvgPool3d((1,2,2)) (ref: dgmr/common.py:189-191; discriminators.py:68,165)."""
+    return _Pool.apply(x, pd, ph, pw, 1.0 / (pd * ph * pw))
+
+
+class _Upsample2(Function):
+    @staticmethod
+    def forward(ctx, x):
+        x = _c(x)
+        n, d, h, w, c = x.shape
+        y = _new((n, d, 2 * h, 2 * w, c), x)
+        _be().upsample(x, y, n, d, h, w, c, 1, 2, 2, d, 2 * h, 2 * w, 1.0)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        g = _c(g)
+        n, d, h2, w2, c = g.shape
+        gx = _new((n, d, h2 // 2, w2 // 2, c), g)
+        _be().pool_sum(g, gx, n, d, h2, w2, c, 1, 2, 2, 1.0)
+        return gx
+
+
+def upsample2(x):
+    """Upsample(scale_factor=2, nearest) (ref: dgmr/common.py:121)."""
+    return _Upsample2.apply(x)
+
+
+# ----------------------------------------------------------------------------- spectral norm
+class _SpectralSigma(Function):
+    """inv_sigma[g] for G consecutive reference calls of one spectrally normalised weight
+    (ref: torch/nn/utils/parametrizations.py:495-527).  u, v buffers are updated in place in training."""
+
+    @staticmethod
+    def forward(ctx, w, u, v, G, eps, training):
+        w = _c(w)
+        R = w.shape[0]
+        K = w.numel() // R
+        inv_sigma = _new((G,), w)
+        u_hist, v_hist = _new((G, R), w), _new((G, K), w)
+        ws = _new(((G + 2) * R + 2 * G + 8,), w)
+        _be().sn_power_iter(w, u, v, R, K, G, eps, training, inv_sigma, u_hist, v_hist, ws)
+        ctx.save_for_backward(inv_sigma, u_hist, v_hist)
+        ctx.meta = (tuple(w.shape), R, K, G)
+        ctx.mark_non_differentiable(u_hist, v_hist)
+        return inv_sigma, u_hist, v_hist
+
+    @staticmethod
+    def backward(ctx, g_is, _gu, _gv):
+        inv_sigma, u_hist, v_hist = ctx.saved_tensors
+        wshape, R, K, G = ctx.meta
+        dw = _new(wshape, inv_sigma)
+        _be().sn_bwd(_c(g_is), inv_sigma, u_hist, v_hist, dw, R, K, G, False)
+        return dw, None, None, None, None, None
+
+
+def spectral_inv_sigma(w, u, v, G, eps, training):
+    return _SpectralSigma.apply(w, u, v, G, eps, training)[0]
+
+
+# ----------------------------------------------------------------------------- convolution
+_pack_cache = {}
+
+
+def packed_weight(w: torch.Tensor, ci0: int, cin: int, mode: int) -> torch.Tensor:
+    """[tap][Cout][Cin] (mode 0) / flipped-transposed dgrad pack (mode 1) of the OIHW weight slice
+    [:, ci0:ci0+cin]; cached until the parameter's version counter moves."""
+    key = (w.data_ptr(), tuple(w.shape), ci0, cin, mode, str(w.device))
+    ver = w._version
+    hit = _pack_cache.get(key)
+    if hit is not None and hit[0] == ver:
+        return hit[1]
+    cout, cintot = w.shape[0], w.shape[1]
+    taps = w.numel() // (cout * cintot)
+    p = _new((taps * cout * cin,), w)
+    _be().pack_weight(_c(w.detach()), p, cout, cintot, ci0, cin, taps, mode)
+    _pack_cache[key] = (ver, p)
+    return p
+
+
+def clear_pack_cache():
+    _pack_cache.clear()
+
+
+class _Conv(Function):
+    """y = act( conv(x, w[:, ci0:ci0+cin]) * scale[g, co] + bias + res ).  Kernel extents 1 or 3, same padding."""
+
+    @staticmethod
+    def forward(ctx, x, w, bias, scale, res, ci0, cin, G, act):
+        x = _c(x)
+        n, d, h, wd, c = x.shape
+        assert c == cin, (c, cin)
+        cout = w.shape[0]
+        ks = tuple(w.shape[2:])
+        kd, kh, kw = (1,) * (3 - len(ks)) + ks
+        wp = packed_weight(w, ci0, cin, 0)
+        y = _new((n, d, h, wd, cout), x)
+        res_c, scale_c, bias_c = _c(res), _c(scale), _c(bias)
+        _be().conv_fwd(x, wp, bias_c, scale_c, res_c, y, n, d, h, wd, cin, cout, kd, kh, kw, G, act,
+                       config.conv_algo, config.precision)
+        need_s = scale is not None and scale.requires_grad
+        need_y = act == ACT_RELU or need_s
+        ctx.save_for_backward(x, w, bias_c, scale_c, res_c if need_s else None, y if need_y else None)
+        ctx.meta = (ci0, cin, G, act, (kd, kh, kw), res is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w, bias, scale, res, y = ctx.saved_tensors
+        ci0, cin, G, act, (kd, kh, kw), has_res = ctx.meta
+        be = _be()
+        dy = _c(dy)
+        n, d, h, wd, _ = x.shape
+        cout = w.shape[0]
+        rows = (n // G) * d * h * wd
+        need_x, need_w, need_b, need_s, need_r = (ctx.needs_input_grad[i] for i in range(5))
+        need_b = need_b and bias is not None
+        need_s = need_s and scale is not None
+        need_r = need_r and has_res
+        dz, dpre, dbias, dscale = dy, dy, None, None
+        if act == ACT_RELU or scale is not None or need_b:
+            need_dz = need_x or need_w
+            dz = _new(dy.shape, dy) if (need_dz and (act == ACT_RELU or scale is not None)) else None
+            dpre = _new(dy.shape, dy) if (need_r and act == ACT_RELU) else None
+            dbias = _new((cout,), dy) if need_b else None
+            dscale = _new((G, cout), dy) if need_s else None
+            be.conv_bwd_prep(dy, y, res if need_s else None, bias, scale, dz, dpre, dbias, dscale, rows, G, cout, act)
+            if dz is None:
+                dz = dy
+            if dpre is None:
+                dpre = dy
+        dx = dw = None
+        if need_x:
+            wpt = packed_weight(w, ci0, cin, 1)
+            dx = _new(x.shape, x)
+            be.conv_fwd(dz, wpt, None, None, None, dx, n, d, h, wd, cout, cin, kd, kh, kw, 1, ACT_NONE,
+                        config.conv_algo, config.precision)
+        if need_w:
+            taps = kd * kh * kw
+            dwp = _new((taps * cout * cin,), x)
+            be.conv_wgrad(x, dz, dwp, n, d, h, wd, cin, cout, kd, kh, kw, ALGO_SIMT if config.wgrad_algo == ALGO_AUTO else config.wgrad_algo,
+                          config.precision)
+            cintot = w.shape[1]
+            dw = _new(w.shape, x) if cin == cintot else _zeros(w.shape, x)
+            be.unpack_wgrad(dwp, dw, cout, cintot, ci0, cin, taps, False)
+        return dx, dw, dbias, dscale, (dpre if need_r else None), None, None, None, None
+
+
+def conv(x, w, bias=None, scale=None, res=None, ci0=0, cin=None, G=1, act=ACT_NONE):
+    if cin is None:
+        cin = w.shape[1]
+    return _Conv.apply(x, w, bias, scale, res, ci0, cin, G, act)
+
+
+# ----------------------------------------------------------------------------- BatchNorm
+class _BatchNorm(Function):
+    """y = act(BN(x)) with per-group batch statistics (training) or running statistics (eval),
+    optional fused ReLU and nearest x2 upsample of the output.  Running stats are updated in place,
+    sequentially over the G groups, exactly as G separate reference calls would
+    (ref: dgmr/common.py:74-82,145-153; generators.py:176)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, rmean, rvar, G, training, relu_, up2, eps, momentum):
+        be = _be()
+        x = _c(x)
+        n, d, h, w, c = x.shape
+        rows = (n // G) * d * h * w
+        sums = _new((G, c, 2), x, torch.float64)
+        if training:
+            if rows <= 1:
+                raise ValueError("Expected more than 1 value per channel when training")
+            be.bn_stats(x, sums, rows, G, c)
+        mean, invstd, a, b = (_new((G, c), x) for _ in range(4))
+        be.bn_finalize(sums, gamma, beta, rmean, rvar, rows, G, c, eps, momentum, training, mean, invstd, a, b)
+        y = _new((n, d, 2 * h, 2 * w, c) if up2 else (n, d, h, w, c), x)
+        be.bn_apply(x, a, b, y, rows, G, c, relu_, up2, h, w)
+        ctx.save_for_backward(x, gamma, a, b, mean, invstd)
+        ctx.meta = (G, training, relu_, up2)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, gamma, a, b, mean, invstd = ctx.saved_tensors
+        G, training, relu_, up2 = ctx.meta
+        be = _be()
+        dy = _c(dy)
+        n, d, h, w, c = x.shape
+        rows = (n // G) * d * h * w
+        red = _new((G, c, 2), x, torch.float64)
+        be.bn_bwd_reduce(dy, x, a, b, mean, invstd, red, rows, G, c, relu_, up2, h, w)
+        dx = _new(x.shape, x) if ctx.needs_input_grad[0] else None
+        dgamma = _new((c,), x) if (gamma is not None and ctx.needs_input_grad[1]) else None
+        dbeta = _new((c,), x) if (gamma is not None and ctx.needs_input_grad[2]) else None
+        be.bn_bwd_apply(dy, x, a, b, mean, invstd, gamma, red, dx, dgamma, dbeta, False, rows, G, c, relu_, up2, h, w, training)
+        return dx, dgamma, dbeta, None, None, None, None, None, None, None, None
+
+
+def batch_norm(x, gamma, beta, rmean, rvar, G, training, relu_=False, up2=False, eps=1e-5, momentum=0.1):
+    return _BatchNorm.apply(x, gamma, beta, rmean, rvar, G, training, relu_, up2, eps, momentum)
+
+
+# ----------------------------------------------------------------------------- ConvGRU gate arithmetic
+class _GruGate(Function):
+    """rh = sigmoid(pre_r) * h   (ref: dgmr/layers/ConvGRU.py:72,78)."""
+
+    @staticmethod
+    def forward(ctx, pre_r, h):
+        pre_r, h = _c(pre_r), _c(h)
+        ch = h.shape[-1]
+        rows = h.numel() // ch
+        rh = torch.empty_like(h)
+        _be().gru_gate_fwd(pre_r, ch, h, rh, rows, ch)
+        ctx.save_for_backward(pre_r, h)
+        return rh
+
+    @staticmethod
+    def backward(ctx, g):
+        pre_r, h = ctx.saved_tensors
+        g = _c(g)
+        ch = h.shape[-1]
+        rows = h.numel() // ch
+        dpre, dh = torch.empty_like(pre_r), torch.empty_like(h)
+        _be().gru_gate_bwd(g, pre_r, ch, h, dpre, ch, dh, False, rows, ch)
+        return dpre, dh
+
+
+class _GruBlend(Function):
+    """h' = u*h + (1-u)*c, u = sigmoid(pre_u)   (ref: dgmr/layers/ConvGRU.py:75,82)."""
+
+    @staticmethod
+    def forward(ctx, pre_u, h, c):
+        pre_u, h, c = _c(pre_u), _c(h), _c(c)
+        ch = h.shape[-1]
+        rows = h.numel() // ch
+        hn = torch.empty_like(h)
+        _be().gru_blend_fwd(pre_u, ch, h, c, hn, rows, ch)
+        ctx.save_for_backward(pre_u, h, c)
+        return hn
+
+    @staticmethod
+    def backward(ctx, g):
+        pre_u, h, c = ctx.saved_tensors
+        g = _c(g)
+        ch = h.shape[-1]
+        rows = h.numel() // ch
+        dpre, dh, dc = torch.empty_like(pre_u), torch.empty_like(h), torch.empty_like(c)
+        _be().gru_blend_bwd(g, pre_u, ch, h, c, dpre, ch, dc, dh, False, rows, ch)
+        return dpre, dh, dc
+
+
+def gru_gate(pre_r, h):
+    return _GruGate.apply(pre_r, h)
+
+
+def gru_blend(pre_u, h, c):
+    return _GruBlend.apply(pre_u, h, c)
+
+
+# ----------------------------------------------------------------------------- discriminator head
+class _SumpoolRelu(Function):
+    """[N,1,H,W,C] -> [N,C]: sum over H,W of relu(x)  (ref: dgmr/discriminators.py:129,209)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = _c(x)
+        n, d, h, w, c = x.shape
+        y = _new((n, c), x)
+        _be().sumpool_relu_fwd(x, y, n, d * h * w, c)
+        ctx.save_for_backward(x)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        n, d, h, w, c = x.shape
+        dx = torch.empty_like(x)
+        _be().sumpool_relu_bwd(_c(g), x, dx, n, d * h * w, c)
+        return dx
+
+
+def sumpool_relu(x):
+    return _SumpoolRelu.apply(x)
+
+
+# ----------------------------------------------------------------------------- attention
+class _Attention(Function):
+    """ref: dgmr/layers/Attention.py:9-20 (with the reference's [C,H,W]-as-"h w c" axis convention)."""
+
+    @staticmethod
+    def forward(ctx, q, k, v):
+        q, k, v = _c(q), _c(k), _c(v)
+        b, d, h, w, c = q.shape
+        L = c * h
+        out = torch.empty_like(v)
+        beta = _new((b, L, L), q)
+        _be().attention_fwd(q, k, v, out, beta, b, h, w, c)
+        ctx.save_for_backward(q, k, v, beta)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        q, k, v, beta = ctx.saved_tensors
+        b, d, h, w, c = q.shape
+        dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+        ws = torch.empty_like(beta)
+        _be().attention_bwd(_c(g), q, k, v, beta, dq, dk, dv, ws, b, h, w, c)
+        return dq, dk, dv
+
+
+def attention(q, k, v):
+    return _Attention.apply(q, k, v)
+
+
+# ----------------------------------------------------------------------------- losses
+class _HingeDisc(Function):
+    """ref: dgmr/losses.py:307-313 applied to the spatial and temporal columns and summed (dgmr/dgmr.py:166-168).
+    scores: [2B, 2, 1]: real rows first, then generated."""
+
+    @staticmethod
+    def forward(ctx, scores):
+        scores = _c(scores)
+        b = scores.shape[0] // 2
+        cols = scores.numel() // (2 * b)
+        loss = _new((), scores)
+        ds = torch.empty_like(scores)
+        _be().hinge_disc(scores, b, cols, loss, ds)
+        ctx.save_for_backward(ds)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        (ds,) = ctx.saved_tensors
+        return ds * g
+
+
+class _HingeGen(Function):
+    """ref: dgmr/losses.py:316-319."""
+
+    @staticmethod
+    def forward(ctx, scores):
+        scores = _c(scores)
+        loss = _new((), scores)
+        ds = torch.empty_like(scores)
+        _be().hinge_gen(scores, scores.numel(), loss, ds)
+        ctx.save_for_backward(ds)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        (ds,) = ctx.saved_tensors
+        return ds * g
+
+
+class _GridCell(Function):
+    """ref: dgmr/losses.py:172-192 + weight_fn dgmr/dgmr.py:20-33 (max(y+1, cap); `/T*H*W` precedence)."""
+
+    @staticmethod
+    def forward(ctx, gen, target, cap):
+        gen, target = _c(gen), _c(target)
+        coef = float(target.size(3) * target.size(4)) / float(target.size(1))
+        loss = _new((), gen)
+        acc = _new((1,), gen, torch.float64)
+        _be().grid_cell_fwd(gen, target, cap, coef, loss, acc)
+        ctx.save_for_backward(gen, target)
+        ctx.meta = (cap, coef)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        gen, target = ctx.saved_tensors
+        cap, coef = ctx.meta
+        dgen = torch.empty_like(gen)
+        _be().grid_cell_bwd(gen, target, cap, coef, _c(g), dgen)
+        return dgen, None, None
+
+
+def hinge_disc(scores):
+    return _HingeDisc.apply(scores)
+
+
+def hinge_gen(scores):
+    return _HingeGen.apply(scores)
+
+
+def grid_cell(gen, target, cap):
+    return _GridCell.apply(gen, target, cap)
+
+
+class _MeanK(Function):
+    """mean over a list of equally shaped tensors (ref: torch.stack(predictions).mean(0), dgmr/dgmr.py:180)."""
+
+    @staticmethod
+    def forward(ctx, *xs):
+        k = len(xs)
+        out = torch.empty_like(xs[0])
+        _be().axpby(1.0 / k, _c(xs[0]), 0.0, None, out)
+        for x in xs[1:]:
+            _be().axpby(1.0, out, 1.0 / k, _c(x), out)
+        ctx.k = k
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        g = _c(g)
+        gi = torch.empty_like(g)
+        _be().axpby(1.0 / ctx.k, g, 0.0, None, gi)
+        return tuple(gi for _ in range(ctx.k))
+
+
+class _Add(Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        a, b = _c(a), _c(b)
+        out = torch.empty_like(a)
+        _be().axpby(1.0, a, 1.0, b, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, g
+
+
+def add(a, b):
+    return _Add.apply(a, b)
+
+
+def mean_k(xs):
+    return xs[0] if len(xs) == 1 else _MeanK.apply(*xs)

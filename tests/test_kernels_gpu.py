@@ -1,0 +1,198 @@
+"""Per-kernel parity: every C-ABI entry point on the GPU against the host emulator (tests/emu_backend.py,
+the plain-torch restatement of each kernel) on identical seeded inputs.  Tolerances are stated per test:
+bit-exact for index permutations, 1e-5-ish for fp32 pointwise / reductions, TF32-level for tensor-core convs.
+"""
+import pytest
+import torch
+
+from emu_backend import EmuBackend
+
+pytestmark = pytest.mark.gpu
+
+
+def _both(method, args, cuda_backend, rtol=1e-5, atol=1e-6, kwargs=None, check=None):
+    """Run `method` on the emulator (CPU copies) and on CUDA (device copies); compare every tensor argument."""
+    kwargs = kwargs or {}
+    emu = EmuBackend()
+    a_cpu = [a.clone() if torch.is_tensor(a) else a for a in args]
+    a_gpu = [a.cuda() if torch.is_tensor(a) else a for a in args]
+    getattr(emu, method)(*a_cpu, **kwargs)
+    getattr(cuda_backend, method)(*a_gpu, **kwargs)
+    torch.cuda.synchronize()
+    for i, (c, g) in enumerate(zip(a_cpu, a_gpu)):
+        if torch.is_tensor(c) and (check is None or i in check):
+            g = g.cpu()
+            if c.dtype == torch.float64:
+                c, g = c.float(), g.float()
+            err = (c - g).abs().max().item() if c.numel() else 0.0
+            ref = c.abs().max().item() if c.numel() else 0.0
+            assert err <= atol + rtol * max(ref, 1e-30), f"{method}: arg {i} max err {err:.3e} (ref max {ref:.3e})"
+
+
+def test_permute_and_reduce(cuda_backend):
+    torch.manual_seed(0)
+    src = torch.randn(2 * 3 * 4 * 5)
+    dst = torch.zeros(2 * 3 * 4 * 5)
+    _both("permute", [src, dst, (2, 3, 4, 5), (60, 20, 5, 1), (5, 10, 30, 1)], cuda_backend, rtol=0, atol=0)
+    dst = torch.randn(130)
+    _both("permute", [src, dst, (4, 5), (5, 1), (10, 1), True, 7, 3], cuda_backend, rtol=0, atol=1e-7)
+    x = torch.randn(3 * 37 * 50)
+    _both("reduce_mid", [x, torch.zeros(150), 3, 37, 50], cuda_backend)
+
+
+def test_pointwise(cuda_backend):
+    torch.manual_seed(1)
+    n = 10007
+    x, y = torch.randn(n), torch.randn(n)
+    _both("axpby", [0.5, x, -2.0, y, torch.empty(n)], cuda_backend)
+    _both("axpby", [0.25, x, 0.0, None, torch.empty(n)], cuda_backend)
+    _both("relu_fwd", [x, torch.empty(n)], cuda_backend, rtol=0, atol=0)
+    _both("relu_bwd", [y, x, torch.empty(n)], cuda_backend, rtol=0, atol=0)
+    _both("split_tf32", [x, torch.empty(n), torch.empty(n)], cuda_backend, rtol=0, atol=0)
+    _both("fill", [torch.empty(n), 3.5], cuda_backend, rtol=0, atol=0)
+
+
+@pytest.mark.parametrize("dims,win", [((2, 1, 8, 12, 5), (1, 2, 2)), ((2, 5, 6, 6, 3), (2, 2, 2)), ((1, 22, 4, 4, 1), (1, 2, 2))])
+def test_pool_upsample(cuda_backend, dims, win):
+    torch.manual_seed(2)
+    n, d, h, w, c = dims
+    pd, ph, pw = win
+    x = torch.randn(dims)
+    y = torch.empty(n, d // pd, h // ph, w // pw, c)
+    _both("pool_sum", [x, y, n, d, h, w, c, pd, ph, pw, 0.25], cuda_backend)
+    g = torch.randn(n, d // pd, h // ph, w // pw, c)
+    _both("upsample", [g, torch.empty(dims), n, d // pd, h // ph, w // pw, c, pd, ph, pw, d, h, w, 0.5], cuda_backend)
+
+
+def test_gru_pointwise(cuda_backend):
+    torch.manual_seed(3)
+    rows, ch = 300, 24
+    pre, h, c, g = (torch.randn(rows, ch) for _ in range(4))
+    _both("gru_gate_fwd", [pre, ch, h, torch.empty(rows, ch), rows, ch], cuda_backend, atol=1e-6)
+    _both("gru_blend_fwd", [pre, ch, h, c, torch.empty(rows, ch), rows, ch], cuda_backend, atol=1e-6)
+    _both("gru_gate_bwd", [g, pre, ch, h, torch.empty(rows, ch), ch, torch.empty(rows, ch), False, rows, ch], cuda_backend, atol=1e-6)
+    _both("gru_blend_bwd", [g, pre, ch, h, c, torch.empty(rows, ch), ch, torch.empty(rows, ch), torch.empty(rows, ch), False, rows, ch],
+          cuda_backend, atol=1e-6)
+
+
+@pytest.mark.parametrize("G,rows,C,relu,up2", [(1, 500, 24, True, False), (3, 2 * 8 * 8, 96, True, True), (4, 6, 768, False, False), (2, 4 * 4, 4, True, True)])
+def test_batchnorm(cuda_backend, G, rows, C, relu, up2):
+    torch.manual_seed(4)
+    H = W = int((rows // 2) ** 0.5) if up2 else 1
+    x = torch.randn(G * rows, C) * 2 + 0.5
+    sums = torch.zeros(G, C, 2, dtype=torch.float64)
+    _both("bn_stats", [x, sums, rows, G, C], cuda_backend, rtol=1e-5)
+    EmuBackend().bn_stats(x, sums, rows, G, C)
+    gamma, beta = torch.rand(C) + 0.5, torch.randn(C)
+    for training in (True, False):
+        rm, rv = torch.randn(C) * 0.1, torch.rand(C) + 0.5
+        outs = [torch.empty(G, C) for _ in range(4)]
+        _both("bn_finalize", [sums, gamma, beta, rm, rv, rows, G, C, 1e-5, 0.1, training] + outs, cuda_backend, rtol=1e-5, atol=1e-6)
+    rm, rv = torch.zeros(C), torch.ones(C)
+    mean, invstd, a, b = (torch.empty(G, C) for _ in range(4))
+    EmuBackend().bn_finalize(sums, gamma, beta, rm, rv, rows, G, C, 1e-5, 0.1, True, mean, invstd, a, b)
+    y = torch.empty(G * rows * (4 if up2 else 1), C)
+    _both("bn_apply", [x, a, b, y, rows, G, C, relu, up2, H, W], cuda_backend, atol=1e-6)
+    dy = torch.randn_like(y)
+    red = torch.zeros(G, C, 2, dtype=torch.float64)
+    _both("bn_bwd_reduce", [dy, x, a, b, mean, invstd, red, rows, G, C, relu, up2, H, W], cuda_backend, rtol=1e-4, atol=1e-4)
+    EmuBackend().bn_bwd_reduce(dy, x, a, b, mean, invstd, red, rows, G, C, relu, up2, H, W)
+    for training in (True, False):
+        _both("bn_bwd_apply", [dy, x, a, b, mean, invstd, gamma, red, torch.empty(G * rows, C), torch.empty(C), torch.empty(C), False,
+                               rows, G, C, relu, up2, H, W, training], cuda_backend, rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("R,K,G", [(24, 36, 1), (48, 432, 4), (1, 768, 8), (384, 3456, 18), (768, 6912, 3), (96, 2592, 2)])
+def test_spectral_norm(cuda_backend, R, K, G):
+    torch.manual_seed(5)
+    w = torch.randn(R, K) / K ** 0.5
+    u = torch.nn.functional.normalize(torch.randn(R), dim=0)
+    v = torch.nn.functional.normalize(torch.randn(K), dim=0)
+    for training in (True, False):
+        args = [w, u.clone(), v.clone(), R, K, G, 1e-4, training, torch.empty(G), torch.empty(G, R), torch.empty(G, K),
+                torch.zeros((G + 2) * R + 2 * G + 8)]
+        # power iteration is a contraction towards the top singular pair: fp32 reordering stays ~1e-6; u,v sign is fixed by the start
+        _both("sn_power_iter", args, cuda_backend, rtol=2e-4, atol=2e-5, check={1, 2, 8, 9, 10})
+    dis, isg = torch.randn(G), torch.rand(G) + 0.5
+    uh, vh = torch.randn(G, R), torch.randn(G, K)
+    _both("sn_bwd", [dis, isg, uh, vh, torch.zeros(R, K), R, K, G, False], cuda_backend, rtol=1e-4, atol=1e-5)
+
+
+def test_pack_unpack(cuda_backend):
+    torch.manual_seed(6)
+    cout, cintot, taps = 10, 12, 9
+    w = torch.randn(cout, cintot, taps)
+    for mode in (0, 1):
+        _both("pack_weight", [w, torch.empty(taps * cout * 8), cout, cintot, 4, 8, taps, mode], cuda_backend, rtol=0, atol=0)
+    p = torch.randn(taps * cout * 8)
+    _both("unpack_wgrad", [p, torch.zeros(cout, cintot, taps), cout, cintot, 4, 8, taps, False], cuda_backend, rtol=0, atol=0)
+    _both("unpack_wgrad", [p, torch.randn(cout, cintot, taps), cout, cintot, 0, 8, taps, True], cuda_backend, rtol=0, atol=1e-6)
+
+
+CONV_SHAPES_SIMT = [
+    # N, D, H, W, Cin, Cout, kd, kh, kw, G
+    (2, 1, 8, 8, 4, 24, 1, 3, 3, 1),
+    (4, 1, 6, 10, 12, 20, 1, 3, 3, 2),
+    (2, 1, 5, 7, 7, 3, 1, 1, 1, 1),
+    (2, 4, 6, 6, 4, 8, 3, 3, 3, 1),
+    (3, 1, 1, 1, 768, 1, 1, 1, 1, 3),
+    (1, 1, 4, 4, 96, 48, 1, 3, 3, 1),
+]
+
+
+def _conv_args(shape, act, with_res, with_scale, with_bias=True):
+    n, d, h, w, cin, cout, kd, kh, kw, g = shape
+    taps = kd * kh * kw
+    x = torch.randn(n, d, h, w, cin)
+    wp = torch.randn(taps * cout * cin) / (taps * cin) ** 0.5
+    bias = torch.randn(cout) if with_bias else None
+    scale = (torch.rand(g, cout) + 0.5) if with_scale else None
+    res = torch.randn(n, d, h, w, cout) if with_res else None
+    y = torch.empty(n, d, h, w, cout)
+    return [x, wp, bias, scale, res, y, n, d, h, w, cin, cout, kd, kh, kw, g, act]
+
+
+@pytest.mark.parametrize("shape", CONV_SHAPES_SIMT)
+@pytest.mark.parametrize("act,with_res,with_scale", [(0, False, False), (1, True, True)])
+def test_conv_simt(cuda_backend, shape, act, with_res, with_scale):
+    torch.manual_seed(7)
+    args = _conv_args(shape, act, with_res, with_scale)
+    _both("conv_fwd", args, cuda_backend, rtol=2e-5, atol=2e-5, kwargs=dict(algo=1))
+    n, d, h, w, cin, cout, kd, kh, kw, g = shape
+    x, dz = torch.randn(n, d, h, w, cin), torch.randn(n, d, h, w, cout)
+    _both("conv_wgrad", [x, dz, torch.zeros(kd * kh * kw * cout * cin), n, d, h, w, cin, cout, kd, kh, kw], cuda_backend,
+          rtol=5e-5, atol=5e-5, kwargs=dict(algo=1))
+
+
+@pytest.mark.parametrize("G,rows,C,act", [(1, 300, 24, 0), (3, 64, 48, 1), (2, 17, 4, 1)])
+def test_conv_bwd_prep(cuda_backend, G, rows, C, act):
+    torch.manual_seed(8)
+    dy, y, res = (torch.randn(G * rows, C) for _ in range(3))
+    bias, scale = torch.randn(C), torch.rand(G, C) + 0.5
+    args = [dy, y, res, bias, scale, torch.empty(G * rows, C), torch.empty(G * rows, C), torch.zeros(C), torch.zeros(G, C), rows, G, C, act]
+    _both("conv_bwd_prep", args, cuda_backend, rtol=1e-4, atol=1e-4)
+
+
+def test_head_attention_losses_adam(cuda_backend):
+    torch.manual_seed(9)
+    x = torch.randn(6, 4, 40)
+    _both("sumpool_relu_fwd", [x, torch.empty(6, 40), 6, 4, 40], cuda_backend)
+    _both("sumpool_relu_bwd", [torch.randn(6, 40), x, torch.empty(6, 4, 40), 6, 4, 40], cuda_backend, rtol=0, atol=0)
+    for (B, H, W, C) in [(1, 4, 4, 12), (2, 8, 8, 24)]:
+        q, k, v, do = (torch.randn(B, 1, H, W, C) for _ in range(4))
+        L = C * H
+        beta = torch.empty(B, L, L)
+        _both("attention_fwd", [q, k, v, torch.empty(B, 1, H, W, C), beta, B, H, W, C], cuda_backend, rtol=1e-4, atol=1e-5)
+        EmuBackend().attention_fwd(q, k, v, torch.empty(B, 1, H, W, C), beta, B, H, W, C)
+        _both("attention_bwd", [do, q, k, v, beta] + [torch.empty(B, 1, H, W, C) for _ in range(3)] + [torch.empty(B, L, L), B, H, W, C],
+              cuda_backend, rtol=1e-4, atol=1e-5)
+    s = torch.randn(8, 2) * 2
+    _both("hinge_disc", [s, 4, 2, torch.empty(()), torch.empty(8, 2)], cuda_backend)
+    _both("hinge_disc", [s.reshape(16, 1), 8, 1, torch.empty(()), torch.empty(16, 1)], cuda_backend)
+    _both("hinge_gen", [s, 16, torch.empty(()), torch.empty(8, 2)], cuda_backend)
+    gen, tgt = torch.rand(2, 4, 1, 32, 32) * 30, torch.rand(2, 4, 1, 32, 32) * 30
+    _both("grid_cell_fwd", [gen, tgt, 24.0, 256.0, torch.empty(()), torch.zeros(1, dtype=torch.float64)], cuda_backend, check={4})
+    _both("grid_cell_bwd", [gen, tgt, 24.0, 256.0, torch.tensor(0.7), torch.empty_like(gen)], cuda_backend)
+    n = 5000
+    p, g, m, vv = torch.randn(n), torch.randn(n), torch.rand(n), torch.rand(n)
+    _both("adam", [p, g, m, vv, 2e-4, 0.0, 0.999, 1e-8, 3, 0.5], cuda_backend, rtol=1e-5, atol=1e-7)

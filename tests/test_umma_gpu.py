@@ -1,0 +1,59 @@
+"""tcgen05 / TMA implicit-GEMM convolution against the fp32 emulator and against the SIMT kernel.
+
+Tolerance: kind::tf32 keeps 10 explicit mantissa bits of each operand (the same operand precision cuDNN uses
+by default for the reference's convs); with unit-variance data and 1/sqrt(K) weights the expected error of a
+K-term dot product is ~2^-11 * sqrt(2) relative to the output RMS, so 4e-3 * max|y| bounds it with margin.
+"""
+import pytest
+import torch
+
+from emu_backend import EmuBackend
+
+pytestmark = pytest.mark.gpu
+
+# N, D, H, W, Cin, Cout, kd, kh, kw, G
+UMMA_SHAPES = [
+    (2, 1, 16, 16, 32, 64, 1, 3, 3, 1),     # BK=32, single k-chunk per tap
+    (2, 1, 16, 16, 96, 48, 1, 3, 3, 2),     # 3 k-chunks, N=48
+    (4, 1, 8, 8, 64, 192, 1, 3, 3, 4),      # 8x8 images: box spans 2 images; groups
+    (8, 1, 4, 4, 128, 256, 1, 3, 3, 2),     # 4x4 images: 8 images per tile
+    (32, 1, 2, 2, 64, 32, 1, 3, 3, 1),      # 2x2 images
+    (2, 1, 32, 32, 48, 96, 1, 3, 3, 1),     # BK=16 (64-byte swizzle)
+    (2, 1, 16, 16, 24, 24, 1, 3, 3, 1),     # BK=8 (32-byte swizzle), Cout=24 -> BN=32 with OOB weight rows
+    (2, 1, 16, 16, 8, 48, 1, 3, 3, 1),      # Cin=8
+    (2, 1, 16, 16, 192, 384, 1, 1, 1, 1),   # 1x1, two N tiles of 192
+    (1, 4, 16, 16, 32, 48, 3, 3, 3, 1),     # 3-D conv
+    (2, 5, 8, 8, 48, 96, 3, 3, 3, 1),       # 3-D conv, odd depth, box spans 2 images
+    (2, 1, 64, 64, 96, 96, 1, 3, 3, 1),     # bigger
+    (2, 1, 8, 8, 768, 768, 1, 3, 3, 1),     # K = 6912, 3 N tiles
+]
+
+
+@pytest.mark.parametrize("shape", UMMA_SHAPES)
+@pytest.mark.parametrize("variant", ["plain", "fused"])
+def test_conv_umma(cuda_backend, shape, variant):
+    n, d, h, w, cin, cout, kd, kh, kw, g = shape
+    assert cuda_backend.conv_umma_supported(n, d, h, w, cin, cout, kd, kh, kw), "shape should be served by tcgen05 path"
+    torch.manual_seed(11)
+    taps = kd * kh * kw
+    x = torch.randn(n, d, h, w, cin)
+    wp = torch.randn(taps * cout * cin) / (taps * cin) ** 0.5
+    fused = variant == "fused"
+    bias = torch.randn(cout) if fused else None
+    scale = (torch.rand(g, cout) + 0.5) if fused else None
+    res = torch.randn(n, d, h, w, cout) if fused else None
+    act = 1 if fused else 0
+    y_ref = torch.empty(n, d, h, w, cout)
+    EmuBackend().conv_fwd(x, wp, bias, scale, res, y_ref, n, d, h, w, cin, cout, kd, kh, kw, g, act)
+    dev = lambda t: None if t is None else t.cuda()
+    y_umma = torch.full((n, d, h, w, cout), float("nan"), device="cuda")
+    cuda_backend.conv_fwd(dev(x), dev(wp), dev(bias), dev(scale), dev(res), y_umma, n, d, h, w, cin, cout, kd, kh, kw, g, act, algo=2)
+    y_simt = torch.empty(n, d, h, w, cout, device="cuda")
+    cuda_backend.conv_fwd(dev(x), dev(wp), dev(bias), dev(scale), dev(res), y_simt, n, d, h, w, cin, cout, kd, kh, kw, g, act, algo=1)
+    torch.cuda.synchronize()
+    ref_max = y_ref.abs().max().item()
+    e_simt = (y_simt.cpu() - y_ref).abs().max().item()
+    e_umma = (y_umma.cpu() - y_ref).abs().max().item()
+    assert e_simt <= 2e-5 * max(ref_max, 1), f"SIMT err {e_simt:.3e}"
+    assert not torch.isnan(y_umma).any(), "tcgen05 path left outputs unwritten"
+    assert e_umma <= 4e-3 * max(ref_max, 1), f"tcgen05 err {e_umma:.3e} (ref max {ref_max:.3e}, simt err {e_simt:.3e})"
