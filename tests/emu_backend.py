@@ -14,7 +14,8 @@ import torch.nn.functional as F
 
 
 def _view(t, off, shape, strides):
-    return torch.as_strided(t.reshape(-1), tuple(shape), tuple(strides), off)
+    flat = t.reshape(-1)  # contiguous input: a view; as_strided offsets are absolute in the storage
+    return torch.as_strided(flat, tuple(shape), tuple(strides), flat.storage_offset() + off)
 
 
 class EmuBackend:
