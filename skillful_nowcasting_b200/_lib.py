@@ -113,14 +113,22 @@ class CudaBackend:
     def __init__(self):
         self.lib = load()
         self.launches = 0
+        self.profile = None  # bench.py sets a list: (name, flops, ev0, ev1, tag) per call, CUDA events on the launch stream
 
     # -- plumbing
     def _stream(self):
         return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
-    def _call(self, name, *args):
+    def _call(self, name, *args, _tag=None, _flops=0.0):
         self.launches += 1
+        prof = self.profile
+        if prof is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
         rc = getattr(self.lib, name)(*args, self._stream())
+        if prof is not None:
+            e1.record()
+            prof.append((name, _flops, e0, e1, _tag or name.replace("dgmr_", "")))
         if rc != 0:
             raise RuntimeError(f"{name} failed ({rc}): {self.lib.dgmr_last_error().decode()}")
 
@@ -222,8 +230,13 @@ class CudaBackend:
 
     def conv_fwd(self, x, wp, bias, scale, res, y, N, D, H, W, Cin, Cout, kd, kh, kw, G, act, algo=ALGO_AUTO, precision=PREC_TF32,
                  x_lo=None, wp_lo=None):
+        tag = None
+        if self.profile is not None:
+            umma = algo == ALGO_UMMA or (algo == ALGO_AUTO and self.conv_umma_supported(N, D, H, W, Cin, Cout, kd, kh, kw))
+            tag = "conv_umma" if umma else "conv_simt"
         self._call("dgmr_conv_fwd", _f32(x, "x"), _f32(x_lo, "x_lo"), _f32(wp, "wp"), _f32(wp_lo, "wp_lo"), _f32(bias, "bias"),
-                   _f32(scale, "scale"), _f32(res, "res"), _f32(y, "y"), N, D, H, W, Cin, Cout, kd, kh, kw, G, act, algo, precision)
+                   _f32(scale, "scale"), _f32(res, "res"), _f32(y, "y"), N, D, H, W, Cin, Cout, kd, kh, kw, G, act, algo, precision,
+                   _tag=tag, _flops=2.0 * N * D * H * W * Cin * Cout * kd * kh * kw)
 
     def conv_bwd_prep(self, dy, y, res, bias, scale, dz, dpre, dbias, dscale, rows, G, Cout, act, accumulate_dbias=False):
         self._call("dgmr_conv_bwd_prep", _f32(dy, "dy"), _f32(y, "y"), _f32(res, "res"), _f32(bias, "bias"), _f32(scale, "scale"),
@@ -232,8 +245,13 @@ class CudaBackend:
 
     def conv_wgrad(self, x, dz, dwp, N, D, H, W, Cin, Cout, kd, kh, kw, algo=ALGO_AUTO, precision=PREC_TF32, xT=None, dzT=None,
                    xT_lo=None, dzT_lo=None):
+        tag = None
+        if self.profile is not None:
+            umma = algo == ALGO_UMMA or (algo == ALGO_AUTO and xT is not None and self.wgrad_umma_supported(N, D, H, W, Cin, Cout, kd, kh, kw))
+            tag = "wgrad_umma" if umma else "wgrad_simt"
         self._call("dgmr_conv_wgrad", _f32(x, "x"), _f32(dz, "dz"), _f32(xT, "xT"), _f32(dzT, "dzT"), _f32(xT_lo, "xT_lo"),
-                   _f32(dzT_lo, "dzT_lo"), _f32(dwp, "dwp"), N, D, H, W, Cin, Cout, kd, kh, kw, algo, precision)
+                   _f32(dzT_lo, "dzT_lo"), _f32(dwp, "dwp"), N, D, H, W, Cin, Cout, kd, kh, kw, algo, precision,
+                   _tag=tag, _flops=2.0 * N * D * H * W * Cin * Cout * kd * kh * kw)
 
     # -- D head / attention / losses / optimiser
     def sumpool_relu_fwd(self, x, y, N, HW, C):

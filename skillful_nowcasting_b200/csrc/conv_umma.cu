@@ -287,6 +287,134 @@ conv_umma_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   }
 }
 
+// ------------------------------------------------------------------ wgrad on tensor cores
+//   dwp[tap][co][ci] += sum_{pixels p in my K-slice} dz[p][co] * x[p + tap][ci]
+// GEMM view: M = Cout (128 per CTA), N = Cin tile, K = output pixels.  Both operands are read straight from the
+// channels-last tensors as MN-major tiles (the channel axis is contiguous, the K axis = pixels is the row axis):
+// one pipeline stage = 32 pixels x {128 co of dz, BN ci of x shifted by the tap}; the tap shift and the zero
+// padding are TMA coordinates / out-of-bounds fill.  Split-K over CTAs, fp32 red.add into the zeroed dwp.
+struct UmmaWgradParams {
+  int N, D, H, W, Cin, Cout, kd, kh, kw;
+  int bw, bh, bn;         // pixel box of one K block: bw*bh*bn == 32
+  int tiles_w, tiles_h;   // W/bw, H/bh
+  int aw;                 // channels per swizzle atom (32/16/8) -> atom row bytes aw*4
+  int BN;                 // ci tile (multiple of 16 and of aw, <= 256)
+  int ci_tiles;
+  int stages, tmem_cols;
+  int kb_total, kb_chunk;
+  float* dwp;
+};
+
+__global__ void __launch_bounds__(kUmmaThreads, 1)
+conv_umma_wgrad_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_constant__ CUtensorMap tmX, const UmmaWgradParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int KP = 32;                                   // pixels per stage
+  const uint32_t blk_bytes = (uint32_t)KP * p.aw * 4u;     // one channel-block [32 pixels][aw channels]
+  const int a_blocks = 128 / p.aw, b_blocks = p.BN / p.aw;
+  const uint32_t a_bytes = a_blocks * blk_bytes, b_bytes = b_blocks * blk_bytes;
+  const uint32_t stage_bytes = a_bytes + b_bytes;          // multiples of 1024 (KP*aw*4 >= 1024)
+  const uint32_t bar_base = base + p.stages * stage_bytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (p.stages + s); };
+  const uint32_t tmem_full_bar = bar_base + 8u * (2 * p.stages);
+  const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * p.stages + 1);
+  volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_addr - raw));
+
+  const int tap = blockIdx.y;
+  const int tkw = tap % p.kw, tkh = (tap / p.kw) % p.kh, tkd = tap / (p.kw * p.kh);
+  const int co0 = (blockIdx.z / p.ci_tiles) * 128, ci0 = (blockIdx.z % p.ci_tiles) * p.BN;
+  const int kb0 = blockIdx.x * p.kb_chunk;
+  const int kb1 = min(kb0 + p.kb_chunk, p.kb_total);
+  const int num_kb = kb1 - kb0;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmDz) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
+    for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    mbar_init(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) { __syncwarp(); tmem_alloc(tmem_ptr_addr, (uint32_t)p.tmem_cols); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_gen;
+
+  if (warp == 0) {
+    if (lane == 0 && num_kb > 0) {
+      int s = 0; uint32_t ph = 0;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        int t = kb;
+        const int wi = t % p.tiles_w; t /= p.tiles_w;
+        const int hi = t % p.tiles_h; t /= p.tiles_h;
+        const int d0 = t % p.D; t /= p.D;
+        const int n0 = t * p.bn, w0 = wi * p.bw, h0 = hi * p.bh;
+        mbar_wait(empty_bar(s), ph ^ 1u);
+        mbar_expect_tx(full_bar(s), a_bytes + b_bytes);
+        const uint32_t sa = base + s * stage_bytes;
+        for (int j = 0; j < a_blocks; ++j) tma_load_5d(sa + j * blk_bytes, &tmDz, full_bar(s), co0 + j * p.aw, w0, h0, d0, n0);
+        for (int j = 0; j < b_blocks; ++j)
+          tma_load_5d(sa + a_bytes + j * blk_bytes, &tmX, full_bar(s), ci0 + j * p.aw, w0 + tkw - p.kw / 2, h0 + tkh - p.kh / 2, d0 + tkd - p.kd / 2, n0);
+        if (++s == p.stages) { s = 0; ph ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && num_kb > 0) {
+      // instruction descriptor: f32 accum, tf32 x tf32, A and B MN-major, N = BN, M = 128
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(p.BN >> 3) << 17) | ((128u >> 4) << 24);
+      const uint32_t row_bytes = p.aw * 4u;
+      const uint32_t layout = row_bytes == 128 ? 2u : (row_bytes == 64 ? 4u : 6u);
+      const uint32_t sbo = 8u * row_bytes;   // next 8 pixels (K) inside a channel block
+      const uint32_t lbo = blk_bytes;        // next channel block (MN)
+      auto mn_desc = [&](uint32_t saddr) {
+        uint64_t d = 0;
+        d |= (uint64_t)((saddr >> 4) & 0x3FFFu);
+        d |= (uint64_t)((lbo >> 4) & 0x3FFFu) << 16;
+        d |= (uint64_t)((sbo >> 4) & 0x3FFFu) << 32;
+        d |= (uint64_t)1u << 46;
+        d |= (uint64_t)layout << 61;
+        return d;
+      };
+      int s = 0; uint32_t ph = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(full_bar(s), ph);
+        tc_fence_after();
+        const uint32_t sa = base + s * stage_bytes;
+        for (int k = 0; k < KP / 8; ++k) {
+          const uint64_t adesc = mn_desc(sa + k * sbo);
+          const uint64_t bdesc = mn_desc(sa + a_bytes + k * sbo);
+          umma_tf32(tmem_base, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(empty_bar(s));
+        if (++s == p.stages) { s = 0; ph ^= 1u; }
+      }
+      umma_commit(tmem_full_bar);
+    }
+  } else if (num_kb > 0) {
+    const int q = warp & 3;
+    const int co = co0 + q * 32 + lane;
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+    for (int c = 0; c < p.BN; c += 16) {
+      if (ci0 + c >= p.Cin) break;
+      float v[16];
+      tmem_ld16(trow + (uint32_t)c, v);
+      if (co >= p.Cout) continue;
+      float* dst = p.dwp + ((int64_t)tap * p.Cout + co) * p.Cin + ci0 + c;
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (ci0 + c + j < p.Cin) atomicAdd(dst + j, v[j]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { __syncwarp(); tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols); }
+}
+
 // ------------------------------------------------------------------ host side
 static int pick_bk(int Cin) { return (Cin % 32 == 0) ? 32 : (Cin % 16 == 0) ? 16 : (Cin % 8 == 0) ? 8 : 0; }
 static bool pick_box(int N, int H, int W, int* bw, int* bh, int* bn) {
@@ -366,6 +494,95 @@ int launch_conv_umma_fwd(const float* x, const float* wp, const float* bias, con
   return 0;
 }
 
+
+static bool pick_box32(int N, int H, int W, int* bw, int* bh, int* bn) {
+  for (int w = 32; w >= 1; w >>= 1) {
+    if (w > W || W % w) continue;
+    int rest = 32 / w;
+    for (int h = rest; h >= 1; h >>= 1) {
+      if (h > H || H % h) continue;
+      int n = rest / h;
+      if (n > N || N % n) continue;
+      *bw = w; *bh = h; *bn = n;
+      return true;
+    }
+  }
+  return false;
+}
+static int pick_aw(int Cin, int Cout) {
+  for (int aw = 32; aw >= 8; aw >>= 1)
+    if (Cin % aw == 0 && Cout % aw == 0) return aw;
+  return 0;
+}
+static bool umma_wgrad_ok(int N, int D, int H, int W, int Cin, int Cout, int kd, int kh, int kw) {
+  int bw, bh, bn;
+  (void)D;
+  if (pick_aw(Cin, Cout) == 0) return false;
+  if (Cin < 16 || Cout < 16) return false;
+  if (!((kd == 1 || kd == 3) && (kh == 1 || kh == 3) && (kw == 1 || kw == 3))) return false;
+  if (!pick_box32(N, H, W, &bw, &bh, &bn)) return false;
+  if ((int64_t)N * D * H * W < 4096) return false;   // tiny K: the SIMT kernel is as good
+  return true;
+}
+
+int launch_conv_umma_wgrad(const float* x, const float* dz, float* dwp, int N, int D, int H, int W, int Cin, int Cout, int kd, int kh, int kw, cudaStream_t st) {
+  UmmaWgradParams p;
+  p.N = N; p.D = D; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.kd = kd; p.kh = kh; p.kw = kw;
+  if (!pick_box32(N, H, W, &p.bw, &p.bh, &p.bn)) { set_error("conv_umma_wgrad: no 32-pixel box"); return 1; }
+  p.tiles_w = W / p.bw; p.tiles_h = H / p.bh;
+  p.aw = pick_aw(Cin, Cout);
+  if (p.aw == 0) { set_error("conv_umma_wgrad: channels not multiples of 8"); return 1; }
+  p.ci_tiles = (int)ceil_div(Cin, 256);
+  int bn_ci = (int)ceil_div(Cin, p.ci_tiles);
+  int unit = p.aw < 16 ? 16 : p.aw;
+  p.BN = (int)(ceil_div(bn_ci, unit) * unit);
+  p.tmem_cols = 32; while (p.tmem_cols < p.BN) p.tmem_cols <<= 1;
+  const uint32_t blk_bytes = 32u * p.aw * 4u;
+  const uint32_t stage_bytes = (128 / p.aw + p.BN / p.aw) * blk_bytes;
+  int stages = (int)((200u * 1024u) / stage_bytes);
+  if (stages > 6) stages = 6;
+  if (stages < 2) { set_error("conv_umma_wgrad: stage too large"); return 1; }
+  p.stages = stages;
+  size_t smem = (size_t)stages * stage_bytes + 1024 + 8 * (2 * stages + 2);
+  const int taps = kd * kh * kw;
+  const int co_tiles = (int)ceil_div(Cout, 128);
+  p.kb_total = (N / p.bn) * D * p.tiles_h * p.tiles_w;
+  int64_t base_ctas = (int64_t)taps * co_tiles * p.ci_tiles;
+  int64_t ksplit = ceil_div((int64_t)sm_count() * 2, base_ctas);
+  if (ksplit > p.kb_total / 8) ksplit = p.kb_total / 8;
+  if (ksplit < 1) ksplit = 1;
+  p.kb_chunk = (int)ceil_div(p.kb_total, ksplit);
+  ksplit = ceil_div(p.kb_total, p.kb_chunk);
+  p.dwp = dwp;
+  CUtensorMap tmDz, tmX;
+  {
+    uint64_t dims[5] = {(uint64_t)Cout, (uint64_t)W, (uint64_t)H, (uint64_t)D, (uint64_t)N};
+    uint64_t str[4] = {(uint64_t)Cout * 4, (uint64_t)W * Cout * 4, (uint64_t)H * W * Cout * 4, (uint64_t)D * H * W * Cout * 4};
+    uint32_t box[5] = {(uint32_t)p.aw, (uint32_t)p.bw, (uint32_t)p.bh, 1u, (uint32_t)p.bn};
+    int e = make_tmap(&tmDz, dz, 5, dims, str, box, p.aw * 4);
+    if (e) return e;
+  }
+  {
+    uint64_t dims[5] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)D, (uint64_t)N};
+    uint64_t str[4] = {(uint64_t)Cin * 4, (uint64_t)W * Cin * 4, (uint64_t)H * W * Cin * 4, (uint64_t)D * H * W * Cin * 4};
+    uint32_t box[5] = {(uint32_t)p.aw, (uint32_t)p.bw, (uint32_t)p.bh, 1u, (uint32_t)p.bn};
+    int e = make_tmap(&tmX, x, 5, dims, str, box, p.aw * 4);
+    if (e) return e;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(conv_umma_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)) != cudaSuccess) {
+      set_error("conv_umma_wgrad: cannot raise dynamic smem limit"); return 2;
+    }
+    attr_set = true;
+  }
+  if (cudaMemsetAsync(dwp, 0, sizeof(float) * (size_t)taps * Cout * Cin, st) != cudaSuccess) { set_error("conv_umma_wgrad: memset failed"); return 2; }
+  dim3 grid((unsigned)ksplit, (unsigned)taps, (unsigned)(co_tiles * p.ci_tiles));
+  conv_umma_wgrad_kernel<<<grid, kUmmaThreads, smem, st>>>(tmDz, tmX, p);
+  DGMR_CHECK_LAUNCH("conv_umma_wgrad");
+  return 0;
+}
+
 }  // namespace dgmr
 
 using namespace dgmr;
@@ -376,8 +593,7 @@ int dgmr_conv_umma_supported(int N, int D, int H, int W, int Cin, int Cout, int 
   return umma_fwd_ok(N, D, H, W, Cin, Cout, kd, kh, kw, 1) ? 1 : 0;
 }
 int dgmr_wgrad_umma_supported(int N, int D, int H, int W, int Cin, int Cout, int kd, int kh, int kw) {
-  (void)N; (void)D; (void)H; (void)W; (void)Cin; (void)Cout; (void)kd; (void)kh; (void)kw;
-  return 0;  // tensor-core wgrad lands in a later milestone; SIMT kernel serves it
+  return umma_wgrad_ok(N, D, H, W, Cin, Cout, kd, kh, kw) ? 1 : 0;
 }
 
 int dgmr_conv_fwd(const float* x, const float* x_lo, const float* wp, const float* wp_lo, const float* bias, const float* scale, const float* res, float* y,
@@ -397,8 +613,12 @@ int dgmr_conv_fwd(const float* x, const float* x_lo, const float* wp, const floa
 
 int dgmr_conv_wgrad(const float* x, const float* dz, const float* xT, const float* dzT, const float* xT_lo, const float* dzT_lo, float* dwp, int N, int D,
                     int H, int W, int Cin, int Cout, int kd, int kh, int kw, int algo, int precision, dgmr_stream_t stream) {
-  (void)xT; (void)dzT; (void)xT_lo; (void)dzT_lo; (void)precision;
-  DGMR_REQUIRE(algo != DGMR_ALGO_UMMA, "dgmr_conv_wgrad: tcgen05 wgrad not available yet");
+  (void)xT; (void)dzT; (void)xT_lo; (void)dzT_lo; (void)precision;  // MN-major tiles come straight from x / dz: no transposed copies needed
+  DGMR_REQUIRE(N > 0 && D > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, "dgmr_conv_wgrad: bad dims");
+  bool ok = umma_wgrad_ok(N, D, H, W, Cin, Cout, kd, kh, kw);
+  if (algo == DGMR_ALGO_UMMA) DGMR_REQUIRE(ok, "dgmr_conv_wgrad: shape not supported by the tcgen05 path");
+  if (algo == DGMR_ALGO_UMMA || (algo == DGMR_ALGO_AUTO && ok))
+    return launch_conv_umma_wgrad(x, dz, dwp, N, D, H, W, Cin, Cout, kd, kh, kw, S(stream));
   return launch_conv_simt_wgrad(x, dz, dwp, N, D, H, W, Cin, Cout, kd, kh, kw, S(stream));
 }
 

@@ -405,8 +405,7 @@ class _Conv(Function):
         if need_w:
             taps = kd * kh * kw
             dwp = _new((taps * cout * cin,), x)
-            be.conv_wgrad(x, dz, dwp, n, d, h, wd, cin, cout, kd, kh, kw, ALGO_SIMT if config.wgrad_algo == ALGO_AUTO else config.wgrad_algo,
-                          config.precision)
+            be.conv_wgrad(x, dz, dwp, n, d, h, wd, cin, cout, kd, kh, kw, config.wgrad_algo, config.precision)
             cintot = w.shape[1]
             dw = _new(w.shape, x) if cin == cintot else _zeros(w.shape, x)
             be.unpack_wgrad(dwp, dw, cout, cintot, ci0, cin, taps, False)

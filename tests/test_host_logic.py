@@ -7,6 +7,7 @@ import io
 import pytest
 import torch
 
+from block_cases import block_cases, run_block_case, run_conv_gru_case
 from oracle import dgmr_oracle as O
 from parity_util import (C1, GOLDEN, assert_grads_close, build_gan, c1_inputs, compare_grads, module_gan_forward,
                          oracle_gan_forward, rel_err)
@@ -36,66 +37,16 @@ def test_c1_gan_matches_fixture(emu, mode):
         compare_grads(got["g_grads"], fix[mode]["g_grads"], 5e-2, 2e-1, zero_floor=1e-5)
 
 
-def _block_cases():
-    from skillful_nowcasting_b200.common import DBlock, GBlock, LBlock, UpsampleGBlock
-    return [
-        ("g", lambda: GBlock(16, 16), lambda st, x, tr: O.g_block(st, "m", x, tr), (2, 16, 8, 8)),
-        ("g_proj", lambda: GBlock(16, 8), lambda st, x, tr: O.g_block(st, "m", x, tr), (2, 16, 8, 8)),
-        ("upg", lambda: UpsampleGBlock(16, 8), lambda st, x, tr: O.upsample_g_block(st, "m", x, tr), (2, 16, 8, 8)),
-        ("d", lambda: DBlock(8, 16), lambda st, x, tr: O.d_block(st, "m", x, tr), (2, 8, 8, 8)),
-        ("d3", lambda: DBlock(4, 8, conv_type="3d", first_relu=False), lambda st, x, tr: O.d_block(st, "m", x, tr, first_relu=False), (2, 4, 5, 8, 8)),
-        ("dkeep", lambda: DBlock(8, 8, keep_same_output=True), lambda st, x, tr: O.d_block(st, "m", x, tr, keep_same_output=True), (2, 8, 4, 4)),
-        ("l", lambda: LBlock(8, 24), lambda st, x, tr: O.l_block(st, "m", x), (1, 8, 4, 4)),
-    ]
-
-
-@pytest.mark.parametrize("case", _block_cases(), ids=lambda c: c[0])
+@pytest.mark.parametrize("case", block_cases(False), ids=lambda c: c[0])
 @pytest.mark.parametrize("training", [True, False])
 def test_block_forward_backward(emu, case, training):
     """Mirrors the reference's block smoke tests (tests/test_model.py:29-48) but checks values, buffers and grads."""
-    _, make, ofn, shape = case
-    torch.manual_seed(5)
-    mod = make()
-    mod.train(training)
-    st = O.clone_state({"m." + k: v for k, v in mod.state_dict().items()}, requires_grad=True)
-    x = torch.rand(shape)
-    xo = x.clone().requires_grad_(True)
-    xm = x.clone().requires_grad_(True)
-    ref = ofn(st, xo, training)
-    got = mod(xm)
-    assert got.shape == ref.shape
-    assert rel_err(got, ref) < 1e-5
-    w = torch.randn_like(ref)
-    names = [k for k in st if st[k].requires_grad]
-    rg = torch.autograd.grad((ref * w).sum(), [xo] + [st[k] for k in names], allow_unused=True)
-    params = dict(mod.named_parameters())
-    mg = torch.autograd.grad((got * w).sum(), [xm] + [params[k[2:]] for k in names], allow_unused=True)
-    assert_grads_close(["x"] + names, mg, rg, 2e-4)
-    for k, v in mod.state_dict().items():
-        if v.numel():
-            assert rel_err(v, st["m." + k]) < 1e-5, k
+    run_block_case(case, training, "cpu", 1e-5, 2e-4)
 
 
 def test_conv_gru_matches_oracle(emu):
     """ref test shape family: tests/test_model.py:51-81 (scaled down)."""
-    from skillful_nowcasting_b200.layers import ConvGRU
-
-    torch.manual_seed(6)
-    gru = ConvGRU(24 + 8, 8)
-    st = O.clone_state({"g." + k: v for k, v in gru.state_dict().items()}, requires_grad=True)
-    xs = [torch.rand(2, 24, 8, 8, requires_grad=True) for _ in range(4)]
-    xs2 = [x.detach().clone().requires_grad_(True) for x in xs]
-    h = torch.rand(2, 8, 8, 8)
-    ref = O.conv_gru(st, "g", xs, h, True)
-    got = gru(xs2, h)
-    assert got.shape == (4, 2, 8, 8, 8)
-    assert rel_err(got, ref) < 1e-5
-    w = torch.randn_like(ref)
-    names = [k for k in st if st[k].requires_grad]
-    rg = torch.autograd.grad((ref * w).sum(), xs + [st[k] for k in names])
-    params = dict(gru.named_parameters())
-    mg = torch.autograd.grad((got * w).sum(), xs2 + [params[k[2:]] for k in names])
-    assert_grads_close([f"x{i}" for i in range(4)] + names, mg, rg, 2e-4)
+    gru, xs, h = run_conv_gru_case("cpu", 1e-5, 2e-4)
     out, new = gru.cell(xs[0].detach(), h)
     assert out.shape == (2, 8, 8, 8) and torch.equal(out, new)
 

@@ -70,5 +70,44 @@ def test_c1_gan_against_fixture_and_oracle(cuda_backend, c1_state, algo, mode):
                     assert int(sd[k]) == int(v), k
         tn, th = (5e-2, 2e-1) if tc else (2e-3, 5e-2)
         compare_grads(got["d_grads"], ref["d_grads"], tn, th, zero_floor=1e-6)
-        compare_grads(got["g_grads"], ref["g_grads"], tn, th, zero_floor=1e-5)
+        # G gradients through the whole train-mode net are chaotic at the 1e-2 level even reference-vs-reference
+        # (tests/test_oracle.py); the tight gradient checks are the per-block tests below
+        compare_grads(got["g_grads"], ref["g_grads"], 2e-1 if tc else 5e-2, 1.0 if tc else 2e-1, zero_floor=1e-5)
     gen.cpu(); disc.cpu()
+
+
+# ------------------------------------------------------------------------------------------------ per-block parity
+from block_cases import block_cases, run_block_case, run_conv_gru_case  # noqa: E402
+
+
+@pytest.mark.parametrize("case", block_cases(False), ids=lambda c: c[0])
+@pytest.mark.parametrize("training", [True, False])
+def test_block_simt_fp32(cuda_backend, case, training):
+    """Narrow channel counts: served by the fp32 SIMT kernels -> fp32-level agreement with the oracle."""
+    from skillful_nowcasting_b200 import ops
+
+    ops.config.conv_algo = 1
+    try:
+        run_block_case(case, training, "cuda", 2e-5, 3e-4)
+    finally:
+        ops.config.conv_algo = 0
+
+
+@pytest.mark.parametrize("case", block_cases(True), ids=lambda c: c[0])
+@pytest.mark.parametrize("training", [True, False])
+def test_block_tensor_core(cuda_backend, case, training):
+    """Wide channel counts: served by the tcgen05 kind::tf32 kernels (1xTF32 operands, fp32 accumulate).
+    Forward within 1e-3 rel (the north-star tolerance); gradients of a freshly initialised block with batch-stat
+    BatchNorm amplify the 2^-11 operand rounding (SURVEY.md section 7 measures 4e-3..1.2e-2) -> 3e-2."""
+    run_block_case(case, training, "cuda", 1e-3, 3e-2, tol_buf=1e-3)
+
+
+def test_conv_gru_simt_and_tensor_core(cuda_backend):
+    from skillful_nowcasting_b200 import ops
+
+    ops.config.conv_algo = 1
+    try:
+        run_conv_gru_case("cuda", 2e-5, 3e-4)
+    finally:
+        ops.config.conv_algo = 0
+    run_conv_gru_case("cuda", 1e-3, 3e-2, cx=64, ch=32, s=16, T=4)

@@ -57,3 +57,40 @@ def test_conv_umma(cuda_backend, shape, variant):
     assert e_simt <= 2e-5 * max(ref_max, 1), f"SIMT err {e_simt:.3e}"
     assert not torch.isnan(y_umma).any(), "tcgen05 path left outputs unwritten"
     assert e_umma <= 4e-3 * max(ref_max, 1), f"tcgen05 err {e_umma:.3e} (ref max {ref_max:.3e}, simt err {e_simt:.3e})"
+
+
+# N, D, H, W, Cin, Cout, kd, kh, kw
+WGRAD_SHAPES = [
+    (4, 1, 32, 32, 32, 64, 1, 3, 3),      # aw=32, one ci tile
+    (4, 1, 32, 32, 96, 96, 1, 3, 3),      # M tile 128 > Cout=96 (OOB channel block), BN=96
+    (8, 1, 16, 16, 48, 96, 1, 3, 3),      # aw=16 (64-byte swizzle), pixel box 16x2
+    (16, 1, 8, 8, 64, 192, 1, 3, 3),      # 8x8 images: pixel box 8x4, two co tiles
+    (32, 1, 4, 4, 128, 256, 1, 3, 3),     # 4x4 images: box spans 2 images
+    (4, 1, 32, 32, 24, 24, 1, 3, 3),      # aw=8 (32-byte swizzle), BN=32 with OOB ci block
+    (2, 1, 64, 64, 192, 384, 1, 1, 1),    # 1x1
+    (2, 6, 16, 16, 48, 96, 3, 3, 3),      # 3-D
+    (2, 1, 16, 16, 768, 768, 1, 3, 3),    # 3 ci tiles x 6 co tiles
+]
+
+
+@pytest.mark.parametrize("shape", WGRAD_SHAPES)
+def test_wgrad_umma(cuda_backend, shape):
+    """tcgen05 wgrad (MN-major operands read straight from the channels-last tensors, split-K) vs fp32 emulator and SIMT."""
+    n, d, h, w, cin, cout, kd, kh, kw = shape
+    assert cuda_backend.wgrad_umma_supported(n, d, h, w, cin, cout, kd, kh, kw)
+    torch.manual_seed(12)
+    taps = kd * kh * kw
+    x, dz = torch.randn(n, d, h, w, cin), torch.randn(n, d, h, w, cout)
+    ref = torch.empty(taps * cout * cin)
+    EmuBackend().conv_wgrad(x, dz, ref, n, d, h, w, cin, cout, kd, kh, kw)
+    g_umma = torch.full((taps * cout * cin,), float("nan"), device="cuda")
+    g_simt = torch.empty(taps * cout * cin, device="cuda")
+    cuda_backend.conv_wgrad(x.cuda(), dz.cuda(), g_umma, n, d, h, w, cin, cout, kd, kh, kw, algo=2)
+    cuda_backend.conv_wgrad(x.cuda(), dz.cuda(), g_simt, n, d, h, w, cin, cout, kd, kh, kw, algo=1)
+    torch.cuda.synchronize()
+    ref_max = ref.abs().max().item()
+    e_simt = (g_simt.cpu() - ref).abs().max().item()
+    e_umma = (g_umma.cpu() - ref).abs().max().item()
+    assert e_simt <= 1e-4 * ref_max, f"SIMT err {e_simt:.3e}"
+    assert not torch.isnan(g_umma).any()
+    assert e_umma <= 4e-3 * ref_max, f"tcgen05 wgrad err {e_umma:.3e} (ref max {ref_max:.3e})"
