@@ -39,14 +39,16 @@ static EncodeTiledFn get_encode() {
 static CUtensorMapSwizzle swizzle_for(int row_bytes) {
   return row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
 }
-static int make_tmap(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box, int row_bytes) {
+static int make_tmap(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box, int row_bytes,
+                     bool atom32 = false) {
   EncodeTiledFn enc = get_encode();
   if (!enc) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return 2; }
   cuuint64_t gd[5]; cuuint64_t gs[4]; cuuint32_t bx[5]; cuuint32_t es[5];
   for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
   for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   swizzle_for(row_bytes), CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : swizzle_for(row_bytes), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (%d): rank %d dims [%llu %llu %llu %llu %llu] box [%u %u %u %u %u] row_bytes %d", (int)r, rank,
               (unsigned long long)gd[0], (unsigned long long)(rank > 1 ? gd[1] : 0), (unsigned long long)(rank > 2 ? gd[2] : 0),
@@ -365,10 +367,13 @@ conv_umma_wgrad_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_co
     if (lane == 0 && num_kb > 0) {
       // instruction descriptor: f32 accum, tf32 x tf32, A and B MN-major, N = BN, M = 128
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(p.BN >> 3) << 17) | ((128u >> 4) << 24);
-      const uint32_t row_bytes = p.aw * 4u;
-      const uint32_t layout = row_bytes == 128 ? 2u : (row_bytes == 64 ? 4u : 6u);
-      const uint32_t sbo = 8u * row_bytes;   // next 8 pixels (K) inside a channel block
-      const uint32_t lbo = blk_bytes;        // next channel block (MN)
+      // 32-bit MN-major operands need the 32-byte-atom swizzle (UMMA LayoutType SWIZZLE_128B_BASE32B = 1, written by TMA with
+      // CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): swizzle atom = 4 K-rows x 128 B, so SBO (next K atom) = 512 B; LBO (next
+      // 32-channel block along MN) = one [32 pixels][32 channels] block.  One MMA (K = 8 pixels) spans two K atoms.
+      const uint32_t layout = 1u;
+      const uint32_t sbo = 4u * 128u;
+      const uint32_t lbo = blk_bytes;
+      const uint32_t kstep = 8u * 128u;      // 8 pixels further along K
       auto mn_desc = [&](uint32_t saddr) {
         uint64_t d = 0;
         d |= (uint64_t)((saddr >> 4) & 0x3FFFu);
@@ -384,8 +389,8 @@ conv_umma_wgrad_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_co
         tc_fence_after();
         const uint32_t sa = base + s * stage_bytes;
         for (int k = 0; k < KP / 8; ++k) {
-          const uint64_t adesc = mn_desc(sa + k * sbo);
-          const uint64_t bdesc = mn_desc(sa + a_bytes + k * sbo);
+          const uint64_t adesc = mn_desc(sa + k * kstep);
+          const uint64_t bdesc = mn_desc(sa + a_bytes + k * kstep);
           umma_tf32(tmem_base, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
         }
         umma_commit(empty_bar(s));
@@ -510,9 +515,8 @@ static bool pick_box32(int N, int H, int W, int* bw, int* bh, int* bn) {
   return false;
 }
 static int pick_aw(int Cin, int Cout) {
-  for (int aw = 32; aw >= 8; aw >>= 1)
-    if (Cin % aw == 0 && Cout % aw == 0) return aw;
-  return 0;
+  // fp32 MN-major tiles exist only with 128-byte rows (32 channels); channel tails are TMA out-of-bounds zero fill
+  return (Cin % 4 == 0 && Cout % 4 == 0) ? 32 : 0;
 }
 static bool umma_wgrad_ok(int N, int D, int H, int W, int Cin, int Cout, int kd, int kh, int kw) {
   int bw, bh, bn;
@@ -521,7 +525,7 @@ static bool umma_wgrad_ok(int N, int D, int H, int W, int Cin, int Cout, int kd,
   if (Cin < 16 || Cout < 16) return false;
   if (!((kd == 1 || kd == 3) && (kh == 1 || kh == 3) && (kw == 1 || kw == 3))) return false;
   if (!pick_box32(N, H, W, &bw, &bh, &bn)) return false;
-  if ((int64_t)N * D * H * W < 4096) return false;   // tiny K: the SIMT kernel is as good
+  if ((int64_t)N * D * H * W < 1024) return false;   // tiny K: the SIMT kernel is as good
   return true;
 }
 
@@ -534,8 +538,7 @@ int launch_conv_umma_wgrad(const float* x, const float* dz, float* dwp, int N, i
   if (p.aw == 0) { set_error("conv_umma_wgrad: channels not multiples of 8"); return 1; }
   p.ci_tiles = (int)ceil_div(Cin, 256);
   int bn_ci = (int)ceil_div(Cin, p.ci_tiles);
-  int unit = p.aw < 16 ? 16 : p.aw;
-  p.BN = (int)(ceil_div(bn_ci, unit) * unit);
+  p.BN = (int)(ceil_div(bn_ci, p.aw) * p.aw);
   p.tmem_cols = 32; while (p.tmem_cols < p.BN) p.tmem_cols <<= 1;
   const uint32_t blk_bytes = 32u * p.aw * 4u;
   const uint32_t stage_bytes = (128 / p.aw + p.BN / p.aw) * blk_bytes;
@@ -559,14 +562,14 @@ int launch_conv_umma_wgrad(const float* x, const float* dz, float* dwp, int N, i
     uint64_t dims[5] = {(uint64_t)Cout, (uint64_t)W, (uint64_t)H, (uint64_t)D, (uint64_t)N};
     uint64_t str[4] = {(uint64_t)Cout * 4, (uint64_t)W * Cout * 4, (uint64_t)H * W * Cout * 4, (uint64_t)D * H * W * Cout * 4};
     uint32_t box[5] = {(uint32_t)p.aw, (uint32_t)p.bw, (uint32_t)p.bh, 1u, (uint32_t)p.bn};
-    int e = make_tmap(&tmDz, dz, 5, dims, str, box, p.aw * 4);
+    int e = make_tmap(&tmDz, dz, 5, dims, str, box, p.aw * 4, true);
     if (e) return e;
   }
   {
     uint64_t dims[5] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)D, (uint64_t)N};
     uint64_t str[4] = {(uint64_t)Cin * 4, (uint64_t)W * Cin * 4, (uint64_t)H * W * Cin * 4, (uint64_t)D * H * W * Cin * 4};
     uint32_t box[5] = {(uint32_t)p.aw, (uint32_t)p.bw, (uint32_t)p.bh, 1u, (uint32_t)p.bn};
-    int e = make_tmap(&tmX, x, 5, dims, str, box, p.aw * 4);
+    int e = make_tmap(&tmX, x, 5, dims, str, box, p.aw * 4, true);
     if (e) return e;
   }
   static bool attr_set = false;

@@ -29,7 +29,7 @@ class AttentionLayer(nn.Module):
         q, k, v = self.query.run(x), self.key.run(x), self.value.run(x)
         o = ops.attention(q, k, v)
         scale = self.gamma.view(1, 1).expand(1, self.output_channels).contiguous()
-        return self.last_conv.run(o, res=x, scale=scale)  # gamma * conv(o) + x, fused in the conv epilogue
+        return self.last_conv.run(o, res=x, scale=scale, exact_dscale=True)  # gamma * conv(o) + x, fused in the conv epilogue
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         return ops.cl_to_nchw(self.run(ops.nchw_to_cl(x)))

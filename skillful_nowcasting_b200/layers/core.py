@@ -122,8 +122,8 @@ class PlainConv(nn.Module):
         else:
             self.register_parameter("bias", None)
 
-    def run(self, x, act: int = ACT_NONE, res=None, scale=None):
-        return ops.conv(x, self.weight, self.bias, scale, res, 0, self.in_channels, 1, act)
+    def run(self, x, act: int = ACT_NONE, res=None, scale=None, exact_dscale=False):
+        return ops.conv(x, self.weight, self.bias, scale, res, 0, self.in_channels, 1, act, exact_dscale)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         return ops.cl_to_nchw(self.run(ops.nchw_to_cl(x)))

@@ -353,7 +353,7 @@ class _Conv(Function):
     """y = act( conv(x, w[:, ci0:ci0+cin]) * scale[g, co] + bias + res ).  Kernel extents 1 or 3, same padding."""
 
     @staticmethod
-    def forward(ctx, x, w, bias, scale, res, ci0, cin, G, act):
+    def forward(ctx, x, w, bias, scale, res, ci0, cin, G, act, exact_dscale=False):
         x = _c(x)
         n, d, h, wd, c = x.shape
         assert c == cin, (c, cin)
@@ -368,13 +368,13 @@ class _Conv(Function):
         need_s = scale is not None and scale.requires_grad
         need_y = act == ACT_RELU or need_s
         ctx.save_for_backward(x, w, bias_c, scale_c, res_c if need_s else None, y if need_y else None)
-        ctx.meta = (ci0, cin, G, act, (kd, kh, kw), res is not None)
+        ctx.meta = (ci0, cin, G, act, (kd, kh, kw), res is not None, exact_dscale)
         return y
 
     @staticmethod
     def backward(ctx, dy):
         x, w, bias, scale, res, y = ctx.saved_tensors
-        ci0, cin, G, act, (kd, kh, kw), has_res = ctx.meta
+        ci0, cin, G, act, (kd, kh, kw), has_res, exact_dscale = ctx.meta
         be = _be()
         dy = _c(dy)
         n, d, h, wd, _ = x.shape
@@ -392,6 +392,15 @@ class _Conv(Function):
             dbias = _new((cout,), dy) if need_b else None
             dscale = _new((G, cout), dy) if need_s else None
             be.conv_bwd_prep(dy, y, res if need_s else None, bias, scale, dz, dpre, dbias, dscale, rows, G, cout, act)
+            if need_s and exact_dscale:
+                # the <dY, Y-b-res>/scale identity divides by the scale, which may be exactly 0 (attention gamma starts at 0,
+                # ref: dgmr/layers/Attention.py:69): recompute the raw conv output and reduce <dpre, z> directly
+                assert act == ACT_NONE
+                z = _new(dy.shape, dy)
+                be.conv_fwd(x, packed_weight(w, ci0, cin, 0), None, None, None, z, n, d, h, wd, cin, cout, kd, kh, kw, 1, ACT_NONE,
+                            config.conv_algo, config.precision)
+                ones = torch.ones((G, cout), device=dy.device, dtype=dy.dtype)
+                be.conv_bwd_prep(dy, z, None, None, ones, None, None, None, dscale, rows, G, cout, ACT_NONE)
             if dz is None:
                 dz = dy
             if dpre is None:
@@ -409,13 +418,13 @@ class _Conv(Function):
             cintot = w.shape[1]
             dw = _new(w.shape, x) if cin == cintot else _zeros(w.shape, x)
             be.unpack_wgrad(dwp, dw, cout, cintot, ci0, cin, taps, False)
-        return dx, dw, dbias, dscale, (dpre if need_r else None), None, None, None, None
+        return dx, dw, dbias, dscale, (dpre if need_r else None), None, None, None, None, None
 
 
-def conv(x, w, bias=None, scale=None, res=None, ci0=0, cin=None, G=1, act=ACT_NONE):
+def conv(x, w, bias=None, scale=None, res=None, ci0=0, cin=None, G=1, act=ACT_NONE, exact_dscale=False):
     if cin is None:
         cin = w.shape[1]
-    return _Conv.apply(x, w, bias, scale, res, ci0, cin, G, act)
+    return _Conv.apply(x, w, bias, scale, res, ci0, cin, G, act, exact_dscale)
 
 
 # ----------------------------------------------------------------------------- BatchNorm

@@ -43,11 +43,11 @@ def test_c1_gan_against_fixture_and_oracle(cuda_backend, c1_state, algo, mode):
     gen.load_state_dict(g0); disc.load_state_dict(d0)
     gen.cuda(); disc.cuda()
     ops.clear_pack_cache()
-    ops.config.conv_algo = ALGOS[algo]
+    ops.config.conv_algo = ops.config.wgrad_algo = ALGOS[algo]
     try:
         got = module_gan_forward(gen, disc, x, y, training, seed=2, device="cuda")
     finally:
-        ops.config.conv_algo = 0
+        ops.config.conv_algo = ops.config.wgrad_algo = 0
     tc = algo == "auto"
     tol_out = (5e-2 if tc else 2e-3) if training else (1e-3 if tc else 2e-5)
     for name, r in (("oracle", ref), ("fixture", fix[mode] if have_fixture else None)):
@@ -86,11 +86,11 @@ def test_block_simt_fp32(cuda_backend, case, training):
     """Narrow channel counts: served by the fp32 SIMT kernels -> fp32-level agreement with the oracle."""
     from skillful_nowcasting_b200 import ops
 
-    ops.config.conv_algo = 1
+    ops.config.conv_algo = ops.config.wgrad_algo = 1
     try:
         run_block_case(case, training, "cuda", 2e-5, 3e-4)
     finally:
-        ops.config.conv_algo = 0
+        ops.config.conv_algo = ops.config.wgrad_algo = 0
 
 
 @pytest.mark.parametrize("case", block_cases(True), ids=lambda c: c[0])
@@ -105,9 +105,9 @@ def test_block_tensor_core(cuda_backend, case, training):
 def test_conv_gru_simt_and_tensor_core(cuda_backend):
     from skillful_nowcasting_b200 import ops
 
-    ops.config.conv_algo = 1
+    ops.config.conv_algo = ops.config.wgrad_algo = 1
     try:
         run_conv_gru_case("cuda", 2e-5, 3e-4)
     finally:
-        ops.config.conv_algo = 0
+        ops.config.conv_algo = ops.config.wgrad_algo = 0
     run_conv_gru_case("cuda", 1e-3, 3e-2, cx=64, ch=32, s=16, T=4)

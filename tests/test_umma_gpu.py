@@ -63,13 +63,13 @@ def test_conv_umma(cuda_backend, shape, variant):
 WGRAD_SHAPES = [
     (4, 1, 32, 32, 32, 64, 1, 3, 3),      # aw=32, one ci tile
     (4, 1, 32, 32, 96, 96, 1, 3, 3),      # M tile 128 > Cout=96 (OOB channel block), BN=96
-    (8, 1, 16, 16, 48, 96, 1, 3, 3),      # aw=16 (64-byte swizzle), pixel box 16x2
+    (8, 1, 16, 16, 48, 96, 1, 3, 3),      # Cin=48: second 32-channel block half out of bounds; pixel box 16x2
     (16, 1, 8, 8, 64, 192, 1, 3, 3),      # 8x8 images: pixel box 8x4, two co tiles
-    (32, 1, 4, 4, 128, 256, 1, 3, 3),     # 4x4 images: box spans 2 images
-    (4, 1, 32, 32, 24, 24, 1, 3, 3),      # aw=8 (32-byte swizzle), BN=32 with OOB ci block
+    (64, 1, 4, 4, 128, 256, 1, 3, 3),     # 4x4 images: box spans 2 images
+    (4, 1, 32, 32, 24, 24, 1, 3, 3),      # 24 channels inside one 32-channel block
     (2, 1, 64, 64, 192, 384, 1, 1, 1),    # 1x1
     (2, 6, 16, 16, 48, 96, 3, 3, 3),      # 3-D
-    (2, 1, 16, 16, 768, 768, 1, 3, 3),    # 3 ci tiles x 6 co tiles
+    (4, 1, 16, 16, 768, 768, 1, 3, 3),    # 3 ci tiles x 6 co tiles
 ]
 
 
