@@ -41,7 +41,11 @@ def _one_step(rank, world, port, out_path, seeds):
     g_opt = Adam(gen.parameters(), lr=5e-5, betas=(0.0, 0.999))
     d_opt = Adam(disc.parameters(), lr=2e-4, betas=(0.0, 0.999))
     flat_grads = []
+    buffers0 = [(m, {k: v.clone() for k, v in m.named_buffers()}) for m in (gen, disc)]
     for seed in seeds:  # single-process mode emulates both ranks' data and averages the gradients by hand
+        for m, snap in buffers0:  # every rank starts the step from the same u/v and BN running statistics
+            for k, v in m.named_buffers():
+                v.copy_(snap[k])
         torch.manual_seed(seed)
         x, y = torch.rand(1, 4, 1, 128, 128), torch.rand(1, 2, 1, 128, 128)
         g_opt.zero_grad(); d_opt.zero_grad()
