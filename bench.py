@@ -219,11 +219,23 @@ def main():
     torch.cuda.synchronize()
     prof, be.profile = be.profile, None
     agg = {}
-    for name, flops, ev0, ev1, tag in prof:
+    shapes = {}
+    for name, flops, ev0, ev1, tag, info in prof:
+        ms_ = ev0.elapsed_time(ev1)
         a = agg.setdefault(tag, [0.0, 0.0, 0])
         a[0] += flops
-        a[1] += ev0.elapsed_time(ev1)
+        a[1] += ms_
         a[2] += 1
+        b_ = shapes.setdefault((tag, info), [0.0, 0.0, 0])
+        b_[0] += flops
+        b_[1] += ms_
+        b_[2] += 1
+    dump = os.environ.get("DGMR_BENCH_DUMP")
+    if dump and rank == 0:
+        with open(dump, "w") as f:
+            f.write("tag\tshape\tcalls\tms\tTFLOP/s\n")
+            for (tag, info), (fl, ms_, n_) in sorted(shapes.items(), key=lambda kv: -kv[1][1]):
+                f.write(f"{tag}\t{info}\t{n_}\t{ms_:.3f}\t{(fl / (ms_ * 1e-3) / 1e12 if ms_ > 0 else 0):.1f}\n")
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()

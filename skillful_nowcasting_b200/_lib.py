@@ -119,7 +119,7 @@ class CudaBackend:
     def _stream(self):
         return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
-    def _call(self, name, *args, _tag=None, _flops=0.0):
+    def _call(self, name, *args, _tag=None, _flops=0.0, _info=""):
         self.launches += 1
         prof = self.profile
         if prof is not None:
@@ -128,7 +128,7 @@ class CudaBackend:
         rc = getattr(self.lib, name)(*args, self._stream())
         if prof is not None:
             e1.record()
-            prof.append((name, _flops, e0, e1, _tag or name.replace("dgmr_", "")))
+            prof.append((name, _flops, e0, e1, _tag or name.replace("dgmr_", ""), _info))
         if rc != 0:
             raise RuntimeError(f"{name} failed ({rc}): {self.lib.dgmr_last_error().decode()}")
 
@@ -215,7 +215,8 @@ class CudaBackend:
     # -- spectral norm
     def sn_power_iter(self, w, u, v, R, K, G, eps, training, inv_sigma, u_hist, v_hist, ws):
         self._call("dgmr_sn_power_iter", _f32(w, "w"), _f32(u, "u"), _f32(v, "v"), R, K, G, float(eps), int(training),
-                   _f32(inv_sigma, "inv_sigma"), _f32(u_hist, "u_hist"), _f32(v_hist, "v_hist"), _f32(ws, "ws"))
+                   _f32(inv_sigma, "inv_sigma"), _f32(u_hist, "u_hist"), _f32(v_hist, "v_hist"), _f32(ws, "ws"),
+                   _info=f"{R}x{K} G{G} train{int(training)}")
 
     def sn_bwd(self, d_inv_sigma, inv_sigma, u_hist, v_hist, dw, R, K, G, accumulate):
         self._call("dgmr_sn_bwd", _f32(d_inv_sigma, "d_inv_sigma"), _f32(inv_sigma, "inv_sigma"), _f32(u_hist, "u_hist"),
@@ -236,7 +237,8 @@ class CudaBackend:
             tag = "conv_umma" if umma else "conv_simt"
         self._call("dgmr_conv_fwd", _f32(x, "x"), _f32(x_lo, "x_lo"), _f32(wp, "wp"), _f32(wp_lo, "wp_lo"), _f32(bias, "bias"),
                    _f32(scale, "scale"), _f32(res, "res"), _f32(y, "y"), N, D, H, W, Cin, Cout, kd, kh, kw, G, act, algo, precision,
-                   _tag=tag, _flops=2.0 * N * D * H * W * Cin * Cout * kd * kh * kw)
+                   _tag=tag, _flops=2.0 * N * D * H * W * Cin * Cout * kd * kh * kw,
+                   _info=f"{N}x{D}x{H}x{W} {Cin}->{Cout} k{kd}{kh}{kw} G{G}")
 
     def conv_bwd_prep(self, dy, y, res, bias, scale, dz, dpre, dbias, dscale, rows, G, Cout, act, accumulate_dbias=False):
         self._call("dgmr_conv_bwd_prep", _f32(dy, "dy"), _f32(y, "y"), _f32(res, "res"), _f32(bias, "bias"), _f32(scale, "scale"),
@@ -251,7 +253,8 @@ class CudaBackend:
             tag = "wgrad_umma" if umma else "wgrad_simt"
         self._call("dgmr_conv_wgrad", _f32(x, "x"), _f32(dz, "dz"), _f32(xT, "xT"), _f32(dzT, "dzT"), _f32(xT_lo, "xT_lo"),
                    _f32(dzT_lo, "dzT_lo"), _f32(dwp, "dwp"), N, D, H, W, Cin, Cout, kd, kh, kw, algo, precision,
-                   _tag=tag, _flops=2.0 * N * D * H * W * Cin * Cout * kd * kh * kw)
+                   _tag=tag, _flops=2.0 * N * D * H * W * Cin * Cout * kd * kh * kw,
+                   _info=f"{N}x{D}x{H}x{W} {Cin}->{Cout} k{kd}{kh}{kw}")
 
     # -- D head / attention / losses / optimiser
     def sumpool_relu_fwd(self, x, y, N, HW, C):

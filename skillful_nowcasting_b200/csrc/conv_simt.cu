@@ -216,47 +216,87 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ packed, float* __r
 }
 
 // ------------------------------------------------------------------ backward prologue
-// rows = pixels per group; grid (row chunks, G); 256 threads as (cpl channel lanes x rp row lanes)
-__global__ void conv_bwd_prep_kernel(const float* __restrict__ dy, const float* __restrict__ y, const float* __restrict__ res, const float* __restrict__ bias,
-                                     const float* __restrict__ scale, float* __restrict__ dz, float* __restrict__ dpre, float* __restrict__ dbias,
-                                     float* __restrict__ dscale, int64_t rows, int C, int64_t chunk, int act) {
-  extern __shared__ double sh[];
-  int g = blockIdx.y;
-  int cpl = C < 256 ? C : 256;
-  int rp = 256 / cpl;
-  int cl = threadIdx.x % cpl, rl = threadIdx.x / cpl;
-  int64_t r0 = (int64_t)blockIdx.x * chunk;
-  int64_t r1 = r0 + chunk < rows ? r0 + chunk : rows;
-  for (int c = cl; c < C; c += cpl) {
-    double s = 0.0, q = 0.0;
+// rows = pixels per group; grid (row chunks, G); 256 threads as (cpl channel-vector lanes x rp row lanes).
+// V = 4: float4 path (Cout % 4 == 0), V = 1: scalar fallback.  One pass: reads dy (+y, +res), writes dz (+dpre),
+// and reduces dbias / dscale per channel -> HBM-bound, ~3 reads + 1-2 writes per element.
+template <int V>
+__global__ void __launch_bounds__(256) conv_bwd_prep_kernel(const float* __restrict__ dy, const float* __restrict__ y, const float* __restrict__ res,
+                                                            const float* __restrict__ bias, const float* __restrict__ scale, float* __restrict__ dz,
+                                                            float* __restrict__ dpre, float* __restrict__ dbias, float* __restrict__ dscale,
+                                                            int64_t rows, int C, int64_t chunk, int act) {
+  extern __shared__ double sh[];  // [rp][cpl][2*V]
+  const int g = blockIdx.y;
+  const int CV = C / V;
+  const int cpl = CV < 256 ? CV : 256;
+  const int rp = 256 / cpl;
+  const int cl = threadIdx.x % cpl, rl = threadIdx.x / cpl;
+  const int64_t r0 = (int64_t)blockIdx.x * chunk;
+  const int64_t r1 = r0 + chunk < rows ? r0 + chunk : rows;
+  for (int cv = cl; cv < CV; cv += cpl) {
+    const int c = cv * V;
+    double s[V], q[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) { s[i] = 0.0; q[i] = 0.0; }
     if (rl < rp) {
-      float sc = scale ? scale[(int64_t)g * C + c] : 1.f;
-      float bi = bias ? bias[c] : 0.f;
-      float fs = 0.f, fq = 0.f; int cnt = 0;
+      float sc[V], bi[V], fs[V], fq[V];
+#pragma unroll
+      for (int i = 0; i < V; ++i) { sc[i] = scale ? scale[(int64_t)g * C + c + i] : 1.f; bi[i] = bias ? bias[c + i] : 0.f; fs[i] = 0.f; fq[i] = 0.f; }
+      int cnt = 0;
       for (int64_t r = r0 + rl; r < r1; r += rp) {
-        int64_t o = ((int64_t)g * rows + r) * C + c;
-        float yv = y ? y[o] : 0.f;
-        float d = dy[o];
-        if (act == DGMR_ACT_RELU && !(yv > 0.f)) d = 0.f;
-        if (dz) dz[o] = d * sc;
-        if (dpre) dpre[o] = d;
-        fs += d;
-        if (dscale) { float zs = yv - bi - (res ? res[o] : 0.f); fq += d * zs; }
-        if (++cnt == 64) { s += fs; q += fq; fs = fq = 0.f; cnt = 0; }
+        const int64_t o = ((int64_t)g * rows + r) * C + c;
+        float d[V], yv[V], rv[V];
+        if (V == 4) {
+          float4 t = *reinterpret_cast<const float4*>(dy + o); d[0] = t.x; d[1] = t.y; d[2] = t.z; d[3] = t.w;
+          if (y) { float4 u = *reinterpret_cast<const float4*>(y + o); yv[0] = u.x; yv[1] = u.y; yv[2] = u.z; yv[3] = u.w; }
+          if (res && dscale) { float4 u = *reinterpret_cast<const float4*>(res + o); rv[0] = u.x; rv[1] = u.y; rv[2] = u.z; rv[3] = u.w; }
+        } else {
+          d[0] = dy[o];
+          if (y) yv[0] = y[o];
+          if (res && dscale) rv[0] = res[o];
+        }
+        float zo[V];
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+          float yy = y ? yv[i] : 0.f;
+          if (act == DGMR_ACT_RELU && !(yy > 0.f)) d[i] = 0.f;
+          zo[i] = d[i] * sc[i];
+          fs[i] += d[i];
+          if (dscale) fq[i] += d[i] * (yy - bi[i] - ((res) ? rv[i] : 0.f));
+        }
+        if (V == 4) {
+          if (dz) *reinterpret_cast<float4*>(dz + o) = make_float4(zo[0], zo[1], zo[2], zo[3]);
+          if (dpre) *reinterpret_cast<float4*>(dpre + o) = make_float4(d[0], d[1], d[2], d[3]);
+        } else {
+          if (dz) dz[o] = zo[0];
+          if (dpre) dpre[o] = d[0];
+        }
+        if (++cnt == 64) {
+#pragma unroll
+          for (int i = 0; i < V; ++i) { s[i] += fs[i]; q[i] += fq[i]; fs[i] = 0.f; fq[i] = 0.f; }
+          cnt = 0;
+        }
       }
-      s += fs; q += fq;
-      sh[(rl * cpl + cl) * 2] = s; sh[(rl * cpl + cl) * 2 + 1] = q;
-    }
-    __syncthreads();
-    if (rl == 0) {
-      for (int j = 1; j < rp; ++j) { s += sh[(j * cpl + cl) * 2]; q += sh[(j * cpl + cl) * 2 + 1]; }
-      if (dbias) atomicAdd(&dbias[c], (float)s);
-      if (dscale) {
-        float sc = scale[(int64_t)g * C + c];
-        atomicAdd(&dscale[(int64_t)g * C + c], (float)(q / (double)sc));
+#pragma unroll
+      for (int i = 0; i < V; ++i) { s[i] += fs[i]; q[i] += fq[i]; }
+      if (dbias || dscale) {
+#pragma unroll
+        for (int i = 0; i < V; ++i) { sh[((rl * cpl + cl) * V + i) * 2] = s[i]; sh[((rl * cpl + cl) * V + i) * 2 + 1] = q[i]; }
       }
     }
-    __syncthreads();
+    if (dbias || dscale) {
+      __syncthreads();
+      if (rl == 0) {
+        for (int j = 1; j < rp; ++j)
+#pragma unroll
+          for (int i = 0; i < V; ++i) { s[i] += sh[((j * cpl + cl) * V + i) * 2]; q[i] += sh[((j * cpl + cl) * V + i) * 2 + 1]; }
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+          if (dbias) atomicAdd(&dbias[c + i], (float)s[i]);
+          if (dscale) atomicAdd(&dscale[(int64_t)g * C + c + i], (float)(q[i] / (double)scale[(int64_t)g * C + c + i]));
+        }
+      }
+      __syncthreads();
+    }
   }
 }
 
@@ -446,10 +486,13 @@ int dgmr_conv_bwd_prep(const float* dy, const float* y, const float* res, const 
   DGMR_REQUIRE(!((act == DGMR_ACT_RELU || dscale) && !y), "dgmr_conv_bwd_prep: y required");
   if (dbias && !accumulate_dbias) DGMR_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * Cout, S(stream)));
   if (dscale) DGMR_CUDA(cudaMemsetAsync(dscale, 0, sizeof(float) * (size_t)G * Cout, S(stream)));
-  int64_t bpg = (int64_t)sm_count() * 4 / G; if (bpg < 1) bpg = 1;
+  int64_t bpg = (int64_t)sm_count() * 16 / G; if (bpg < 1) bpg = 1;
   int64_t chunk = ceil_div(rows, bpg); if (chunk < 64) chunk = 64;
   dim3 grid((unsigned)ceil_div(rows, chunk), G);
-  conv_bwd_prep_kernel<<<grid, 256, 256 * 2 * sizeof(double), S(stream)>>>(dy, y, res, bias, scale, dz, dpre, dbias, dscale, rows, Cout, chunk, act);
+  if (Cout % 4 == 0)
+    conv_bwd_prep_kernel<4><<<grid, 256, 256 * 8 * sizeof(double), S(stream)>>>(dy, y, res, bias, scale, dz, dpre, dbias, dscale, rows, Cout, chunk, act);
+  else
+    conv_bwd_prep_kernel<1><<<grid, 256, 256 * 2 * sizeof(double), S(stream)>>>(dy, y, res, bias, scale, dz, dpre, dbias, dscale, rows, Cout, chunk, act);
   DGMR_CHECK_LAUNCH("dgmr_conv_bwd_prep");
   return 0;
 }

@@ -464,8 +464,12 @@ int launch_conv_umma_fwd(const float* x, const float* wp, const float* bias, con
   p.tmem_cols = 32; while (p.tmem_cols < p.BN) p.tmem_cols <<= 1;
   const uint32_t a_bytes = 128u * p.BK * 4u, b_bytes = ((uint32_t)p.BN * p.BK * 4u + 1023u) & ~1023u;
   const uint32_t stage_bytes = a_bytes + b_bytes;
-  int stages = (int)((200u * 1024u) / stage_bytes);
+  // several CTAs per SM so one tile's epilogue / prologue overlaps another tile's main loop: aim at <= ~72 KB of
+  // pipeline per CTA (3 resident CTAs) but never fewer than 3 stages; big tiles fall back to 1-2 CTAs per SM
+  int stages = (int)((72u * 1024u) / stage_bytes);
+  if (stages < 3) stages = 3;
   if (stages > 6) stages = 6;
+  if ((uint32_t)stages * stage_bytes > 200u * 1024u) stages = (int)((200u * 1024u) / stage_bytes);
   if (stages < 2) { set_error("conv_umma_fwd: stage too large"); return 1; }
   p.stages = stages;
   size_t smem = (size_t)stages * stage_bytes + 1024 /*align slack*/ + 8 * (2 * stages + 2);
@@ -525,7 +529,7 @@ static bool umma_wgrad_ok(int N, int D, int H, int W, int Cin, int Cout, int kd,
   if (Cin < 16 || Cout < 16) return false;
   if (!((kd == 1 || kd == 3) && (kh == 1 || kh == 3) && (kw == 1 || kw == 3))) return false;
   if (!pick_box32(N, H, W, &bw, &bh, &bn)) return false;
-  if ((int64_t)N * D * H * W < 1024) return false;   // tiny K: the SIMT kernel is as good
+  if ((int64_t)N * D * H * W < 256) return false;   // tiny K: the SIMT kernel is as good
   return true;
 }
 
@@ -542,8 +546,10 @@ int launch_conv_umma_wgrad(const float* x, const float* dz, float* dwp, int N, i
   p.tmem_cols = 32; while (p.tmem_cols < p.BN) p.tmem_cols <<= 1;
   const uint32_t blk_bytes = 32u * p.aw * 4u;
   const uint32_t stage_bytes = (128 / p.aw + p.BN / p.aw) * blk_bytes;
-  int stages = (int)((200u * 1024u) / stage_bytes);
+  int stages = (int)((72u * 1024u) / stage_bytes);
+  if (stages < 3) stages = 3;
   if (stages > 6) stages = 6;
+  if ((uint32_t)stages * stage_bytes > 200u * 1024u) stages = (int)((200u * 1024u) / stage_bytes);
   if (stages < 2) { set_error("conv_umma_wgrad: stage too large"); return 1; }
   p.stages = stages;
   size_t smem = (size_t)stages * stage_bytes + 1024 + 8 * (2 * stages + 2);
@@ -551,8 +557,8 @@ int launch_conv_umma_wgrad(const float* x, const float* dz, float* dwp, int N, i
   const int co_tiles = (int)ceil_div(Cout, 128);
   p.kb_total = (N / p.bn) * D * p.tiles_h * p.tiles_w;
   int64_t base_ctas = (int64_t)taps * co_tiles * p.ci_tiles;
-  int64_t ksplit = ceil_div((int64_t)sm_count() * 2, base_ctas);
-  if (ksplit > p.kb_total / 8) ksplit = p.kb_total / 8;
+  int64_t ksplit = ceil_div((int64_t)sm_count() * 3, base_ctas);
+  if (ksplit > p.kb_total / 4) ksplit = p.kb_total / 4;
   if (ksplit < 1) ksplit = 1;
   p.kb_chunk = (int)ceil_div(p.kb_total, ksplit);
   ksplit = ceil_div(p.kb_total, p.kb_chunk);

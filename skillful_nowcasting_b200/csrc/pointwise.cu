@@ -54,6 +54,26 @@ __global__ void axpby_kernel(float a, const float* __restrict__ x, float b, cons
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     out[i] = y ? a * x[i] + b * y[i] : a * x[i];
 }
+__global__ void axpby4_kernel(float a, const float4* __restrict__ x, float b, const float4* __restrict__ y, float4* __restrict__ out, int64_t n4) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 u = x[i], r;
+    if (y) { float4 v = y[i]; r = make_float4(a * u.x + b * v.x, a * u.y + b * v.y, a * u.z + b * v.z, a * u.w + b * v.w); }
+    else r = make_float4(a * u.x, a * u.y, a * u.z, a * u.w);
+    out[i] = r;
+  }
+}
+__global__ void relu_fwd4_kernel(const float4* __restrict__ x, float4* __restrict__ y, int64_t n4) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 u = x[i];
+    y[i] = make_float4(fmaxf(u.x, 0.f), fmaxf(u.y, 0.f), fmaxf(u.z, 0.f), fmaxf(u.w, 0.f));
+  }
+}
+__global__ void relu_bwd4_kernel(const float4* __restrict__ dy, const float4* __restrict__ x, float4* __restrict__ dx, int64_t n4) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 u = x[i], d = dy[i];
+    dx[i] = make_float4(u.x > 0.f ? d.x : 0.f, u.y > 0.f ? d.y : 0.f, u.z > 0.f ? d.z : 0.f, u.w > 0.f ? d.w : 0.f);
+  }
+}
 __global__ void fill_kernel(float* x, float v, int64_t n) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) x[i] = v;
 }
@@ -114,6 +134,43 @@ __global__ void upsample_kernel(const float* __restrict__ x, float* __restrict__
     int ds = dd / ud, hs = ho / uh, ws = wo / uw;
     float v = 0.f;
     if (ds < D && hs < H && ws < W) v = scale * x[((((int64_t)n * D + ds) * H + hs) * W + ws) * C + c];
+    y[i] = v;
+  }
+}
+
+__global__ void pool_sum4_kernel(const float4* __restrict__ x, float4* __restrict__ y, int N, int D, int H, int W, int C4,
+                                 int pd, int ph, int pw, float scale) {
+  int Do = D / pd, Ho = H / ph, Wo = W / pw;
+  int64_t total = (int64_t)N * Do * Ho * Wo * C4;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int c = i % C4; int64_t r = i / C4;
+    int wo = r % Wo; r /= Wo;
+    int ho = r % Ho; r /= Ho;
+    int dd = r % Do; int n = r / Do;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int a = 0; a < pd; ++a)
+      for (int b = 0; b < ph; ++b)
+        for (int e = 0; e < pw; ++e) {
+          float4 v = x[((((int64_t)n * D + dd * pd + a) * H + ho * ph + b) * W + wo * pw + e) * C4 + c];
+          s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+        }
+    y[i] = make_float4(s.x * scale, s.y * scale, s.z * scale, s.w * scale);
+  }
+}
+__global__ void upsample4_kernel(const float4* __restrict__ x, float4* __restrict__ y, int N, int D, int H, int W, int C4,
+                                 int ud, int uh, int uw, int Do, int Ho, int Wo, float scale) {
+  int64_t total = (int64_t)N * Do * Ho * Wo * C4;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int c = i % C4; int64_t r = i / C4;
+    int wo = r % Wo; r /= Wo;
+    int ho = r % Ho; r /= Ho;
+    int dd = r % Do; int n = r / Do;
+    int ds = dd / ud, hs = ho / uh, ws = wo / uw;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ds < D && hs < H && ws < W) {
+      float4 u = x[((((int64_t)n * D + ds) * H + hs) * W + ws) * C4 + c];
+      v = make_float4(u.x * scale, u.y * scale, u.z * scale, u.w * scale);
+    }
     y[i] = v;
   }
 }
@@ -244,6 +301,26 @@ __global__ void bn_apply_kernel(const float* __restrict__ x, const float* __rest
     }
     float v = a[(int64_t)g * C + c] * x[xr * C + c] + b[(int64_t)g * C + c];
     y[i] = relu ? fmaxf(v, 0.f) : v;
+  }
+}
+__global__ void bn_apply4_kernel(const float4* __restrict__ x, const float4* __restrict__ a, const float4* __restrict__ b, float4* __restrict__ y,
+                                 int64_t rows, int G, int C4, int relu, int up2, int H, int W) {
+  int64_t orows = up2 ? rows * 4 : rows;
+  int64_t total = (int64_t)G * orows * C4;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int c = i % C4; int64_t r = i / C4;
+    int g = r / orows;
+    int64_t xr = r;
+    if (up2) {
+      int Wo = 2 * W, Ho = 2 * H;
+      int wo = r % Wo; int64_t t = r / Wo;
+      int ho = t % Ho; int64_t n = t / Ho;
+      xr = (n * H + (ho >> 1)) * W + (wo >> 1);
+    }
+    float4 aa = a[(int64_t)g * C4 + c], bb = b[(int64_t)g * C4 + c], u = x[xr * C4 + c];
+    float4 v = make_float4(aa.x * u.x + bb.x, aa.y * u.y + bb.y, aa.z * u.z + bb.z, aa.w * u.w + bb.w);
+    if (relu) v = make_float4(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f), fmaxf(v.z, 0.f), fmaxf(v.w, 0.f));
+    y[i] = v;
   }
 }
 // dpre at low-res row r, channel c (sums the 4 replicas if up2, applies relu mask)
@@ -523,9 +600,13 @@ int dgmr_reduce_mid(const float* x, float* y, int64_t A, int64_t R, int64_t C, i
   DGMR_CHECK_LAUNCH("dgmr_reduce_mid");
   return 0;
 }
+static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 int dgmr_axpby(float a, const float* x, float b, const float* y, float* out, int64_t n, dgmr_stream_t stream) {
   if (n == 0) return 0;
-  axpby_kernel<<<ew_grid(n, 256), 256, 0, S(stream)>>>(a, x, b, y, out, n);
+  if (n % 4 == 0 && al16(x) && al16(out) && (!y || al16(y)))
+    axpby4_kernel<<<ew_grid(n / 4, 256, 2), 256, 0, S(stream)>>>(a, (const float4*)x, b, (const float4*)y, (float4*)out, n / 4);
+  else
+    axpby_kernel<<<ew_grid(n, 256), 256, 0, S(stream)>>>(a, x, b, y, out, n);
   DGMR_CHECK_LAUNCH("dgmr_axpby");
   return 0;
 }
@@ -537,13 +618,19 @@ int dgmr_fill(float* x, float value, int64_t n, dgmr_stream_t stream) {
 }
 int dgmr_relu_fwd(const float* x, float* y, int64_t n, dgmr_stream_t stream) {
   if (n == 0) return 0;
-  relu_fwd_kernel<<<ew_grid(n, 256), 256, 0, S(stream)>>>(x, y, n);
+  if (n % 4 == 0 && al16(x) && al16(y))
+    relu_fwd4_kernel<<<ew_grid(n / 4, 256, 2), 256, 0, S(stream)>>>((const float4*)x, (float4*)y, n / 4);
+  else
+    relu_fwd_kernel<<<ew_grid(n, 256), 256, 0, S(stream)>>>(x, y, n);
   DGMR_CHECK_LAUNCH("dgmr_relu_fwd");
   return 0;
 }
 int dgmr_relu_bwd(const float* dy, const float* x, float* dx, int64_t n, dgmr_stream_t stream) {
   if (n == 0) return 0;
-  relu_bwd_kernel<<<ew_grid(n, 256), 256, 0, S(stream)>>>(dy, x, dx, n);
+  if (n % 4 == 0 && al16(x) && al16(dy) && al16(dx))
+    relu_bwd4_kernel<<<ew_grid(n / 4, 256, 2), 256, 0, S(stream)>>>((const float4*)dy, (const float4*)x, (float4*)dx, n / 4);
+  else
+    relu_bwd_kernel<<<ew_grid(n, 256), 256, 0, S(stream)>>>(dy, x, dx, n);
   DGMR_CHECK_LAUNCH("dgmr_relu_bwd");
   return 0;
 }
@@ -557,7 +644,10 @@ int dgmr_pool_sum(const float* x, float* y, int N, int D, int H, int W, int C, i
   DGMR_REQUIRE(pd >= 1 && ph >= 1 && pw >= 1 && pd <= 2 && ph <= 2 && pw <= 2, "dgmr_pool_sum: window must be 1 or 2");
   int64_t total = (int64_t)N * (D / pd) * (H / ph) * (W / pw) * C;
   if (total == 0) return 0;
-  pool_sum_kernel<<<ew_grid(total, 256, 2), 256, 0, S(stream)>>>(x, y, N, D, H, W, C, pd, ph, pw, scale);
+  if (C % 4 == 0 && al16(x) && al16(y))
+    pool_sum4_kernel<<<ew_grid(total / 4, 256, 1), 256, 0, S(stream)>>>((const float4*)x, (float4*)y, N, D, H, W, C / 4, pd, ph, pw, scale);
+  else
+    pool_sum_kernel<<<ew_grid(total, 256, 2), 256, 0, S(stream)>>>(x, y, N, D, H, W, C, pd, ph, pw, scale);
   DGMR_CHECK_LAUNCH("dgmr_pool_sum");
   return 0;
 }
@@ -565,7 +655,10 @@ int dgmr_upsample(const float* x, float* y, int N, int D, int H, int W, int C, i
   DGMR_REQUIRE(Do >= D * ud && Ho >= H * uh && Wo >= W * uw, "dgmr_upsample: output smaller than replicated input");
   int64_t total = (int64_t)N * Do * Ho * Wo * C;
   if (total == 0) return 0;
-  upsample_kernel<<<ew_grid(total, 256, 2), 256, 0, S(stream)>>>(x, y, N, D, H, W, C, ud, uh, uw, Do, Ho, Wo, scale);
+  if (C % 4 == 0 && al16(x) && al16(y))
+    upsample4_kernel<<<ew_grid(total / 4, 256, 1), 256, 0, S(stream)>>>((const float4*)x, (float4*)y, N, D, H, W, C / 4, ud, uh, uw, Do, Ho, Wo, scale);
+  else
+    upsample_kernel<<<ew_grid(total, 256, 2), 256, 0, S(stream)>>>(x, y, N, D, H, W, C, ud, uh, uw, Do, Ho, Wo, scale);
   DGMR_CHECK_LAUNCH("dgmr_upsample");
   return 0;
 }
@@ -595,7 +688,7 @@ int dgmr_gru_blend_bwd(const float* d_hnew, const float* pre_u, int ld, const fl
 }
 
 static int64_t bn_chunk(int64_t rows, int G) {
-  int64_t blocks_per_group = (int64_t)sm_count() * 4 / (G > 0 ? G : 1);
+  int64_t blocks_per_group = (int64_t)sm_count() * 16 / (G > 0 ? G : 1);
   if (blocks_per_group < 1) blocks_per_group = 1;
   int64_t chunk = ceil_div(rows, blocks_per_group);
   if (chunk < 64) chunk = 64;
@@ -620,7 +713,10 @@ int dgmr_bn_apply(const float* x, const float* a, const float* b, float* y, int6
   int64_t total = (int64_t)G * rows * C * (up2 ? 4 : 1);
   if (total == 0) return 0;
   DGMR_REQUIRE(!up2 || (rows % ((int64_t)H * W) == 0), "dgmr_bn_apply: rows not a multiple of H*W");
-  bn_apply_kernel<<<ew_grid(total, 256, 2), 256, 0, S(stream)>>>(x, a, b, y, rows, G, C, relu, up2, H, W);
+  if (C % 4 == 0 && al16(x) && al16(y) && al16(a) && al16(b))
+    bn_apply4_kernel<<<ew_grid(total / 4, 256, 1), 256, 0, S(stream)>>>((const float4*)x, (const float4*)a, (const float4*)b, (float4*)y, rows, G, C / 4, relu, up2, H, W);
+  else
+    bn_apply_kernel<<<ew_grid(total, 256, 2), 256, 0, S(stream)>>>(x, a, b, y, rows, G, C, relu, up2, H, W);
   DGMR_CHECK_LAUNCH("dgmr_bn_apply");
   return 0;
 }

@@ -142,3 +142,15 @@ def assert_grads_close(names, got, ref, tol, floor=1e-5):
         else:
             e = rel_err(a, b)
             assert e < tol, f"{n}: rel err {e:.3e} > {tol}"
+
+
+def global_grad_error(got, ref):
+    """||g - r|| / ||r|| over ALL parameters at once (oracle tensors only): the coarse end-to-end check used where
+    per-parameter comparison is dominated by chaotic amplification (train-mode TF32 end to end)."""
+    num = den = 0.0
+    for k, r in ref.items():
+        g = got[k].detach().double().cpu()
+        r = r.detach().double()
+        num += float(((g - r) ** 2).sum())
+        den += float((r ** 2).sum())
+    return (num / max(den, 1e-300)) ** 0.5

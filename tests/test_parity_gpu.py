@@ -10,8 +10,8 @@ Tolerances (rel = max|a-b| / max|b|):
 import pytest
 import torch
 
-from parity_util import (C1, GOLDEN, build_gan, c1_inputs, compare_grads, module_gan_forward, oracle_gan_forward, rel_err,
-                         state_checksum)
+from parity_util import (C1, GOLDEN, build_gan, c1_inputs, compare_grads, global_grad_error, module_gan_forward,
+                         oracle_gan_forward, rel_err, state_checksum)
 
 pytestmark = pytest.mark.gpu
 
@@ -68,11 +68,16 @@ def test_c1_gan_against_fixture_and_oracle(cuda_backend, c1_state, algo, mode):
                     assert rel_err(sd[k], v) < tol_out, k
                 elif "num_batches" in k:
                     assert int(sd[k]) == int(v), k
-        tn, th = (5e-2, 5e-1) if tc else (2e-3, 5e-2)
-        compare_grads(got["d_grads"], ref["d_grads"], tn, th, zero_floor=1e-6)
-        # G gradients through the whole train-mode net are chaotic at the 1e-2 level even reference-vs-reference
-        # (tests/test_oracle.py); the tight gradient checks are the per-block tests below
-        compare_grads(got["g_grads"], ref["g_grads"], 2e-1 if tc else 5e-2, 1.0 if tc else 2e-1, zero_floor=1e-5)
+        if tc:
+            # 1xTF32 operands end to end through batch-stat BatchNorm at fresh init: per-parameter agreement is chaotic
+            # (1.3e-2 on the forward already); check the whole gradient vector, tight checks are per block
+            assert global_grad_error(got["d_grads"], ref["d_grads"]) < 0.1
+            assert global_grad_error(got["g_grads"], ref["g_grads"]) < 0.3
+        else:
+            compare_grads(got["d_grads"], ref["d_grads"], 2e-3, 5e-2, zero_floor=1e-6)
+            # G gradients through the whole train-mode net are chaotic at the 1e-2 level even reference-vs-reference
+            # (tests/test_oracle.py); the tight gradient checks are the per-block tests below
+            compare_grads(got["g_grads"], ref["g_grads"], 5e-2, 2e-1, zero_floor=1e-5)
     gen.cpu(); disc.cpu()
 
 
