@@ -162,8 +162,9 @@ class ContextConditioningStack(nn.Module, PyTorchModelHubMixin):
         h2, w2 = h // 2, w // 2
         # space-to-depth (PixelUnshuffle(2), :393) and regrouping to timestep-major in ONE permute:
         # dst[t, b, h2, w2, c*4 + i*2 + j] = x[b, t, c, 2*h2+i, 2*w2+j]
-        ds = ops.contig_strides((t, b, h2, w2, 4 * c))
-        s = ops.permute(x, (t * b, 1, h2, w2, 4 * c), (b, t, c, h2, w2, 2, 2),
+        cpad = ops.pad8(4 * c)  # 4 -> 8 zero-padded channels: lets the tcgen05 path (K step 8) take the first DBlock
+        ds = ops.contig_strides((t, b, h2, w2, cpad))
+        s = ops.permute(x, (t * b, 1, h2, w2, cpad), (b, t, c, h2, w2, 2, 2),
                         (t * c * h * w, c * h * w, h * w, 2 * w, 2, w, 1),
                         (ds[1], ds[0], 4, ds[2], ds[3], 2, 1))
         outs = []

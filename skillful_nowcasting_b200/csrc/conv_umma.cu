@@ -442,7 +442,7 @@ static bool pick_box(int N, int H, int W, int* bw, int* bh, int* bn) {
 static bool umma_fwd_ok(int N, int D, int H, int W, int Cin, int Cout, int kd, int kh, int kw, int G) {
   int bw, bh, bn;
   if (pick_bk(Cin) == 0) return false;
-  if (Cout < 8) return false;
+  if (Cout < 4 || Cout % 4) return false;   // N tile rounds up to 16; missing weight rows are TMA zero fill
   if (!((kd == 1 || kd == 3) && (kh == 1 || kh == 3) && (kw == 1 || kw == 3))) return false;
   if (!pick_box(N, H, W, &bw, &bh, &bn)) return false;
   if (G < 1 || N % G) return false;
@@ -526,7 +526,7 @@ static bool umma_wgrad_ok(int N, int D, int H, int W, int Cin, int Cout, int kd,
   int bw, bh, bn;
   (void)D;
   if (pick_aw(Cin, Cout) == 0) return false;
-  if (Cin < 16 || Cout < 16) return false;
+  if (Cin < 4 || Cout < 4) return false;
   if (!((kd == 1 || kd == 3) && (kh == 1 || kh == 3) && (kw == 1 || kw == 3))) return false;
   if (!pick_box32(N, H, W, &bw, &bh, &bn)) return false;
   if ((int64_t)N * D * H * W < 256) return false;   // tiny K: the SIMT kernel is as good

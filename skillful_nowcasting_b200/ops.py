@@ -104,14 +104,20 @@ def cl_to_nchw(x: torch.Tensor, keep_depth: bool = False) -> torch.Tensor:
     return permute(x, out_shape, (n, sp, c), (sp * c, c, 1), (c * sp, 1, sp))
 
 
-def space_to_depth(x: torch.Tensor) -> torch.Tensor:
+def pad8(c: int) -> int:
+    return (c + 7) // 8 * 8
+
+
+def space_to_depth(x: torch.Tensor, pad: bool = True) -> torch.Tensor:
     """PixelUnshuffle(2) on channels-last: [N,D,H,W,C] -> [N,D,H/2,W/2,4C], channel c*4 + i*2 + j
-    (ref: torch PixelUnshuffle at dgmr/common.py:326,393; discriminators.py:69,166)."""
+    (ref: torch PixelUnshuffle at dgmr/common.py:326,393; discriminators.py:69,166).  With `pad` the channel axis is
+    zero-padded to a multiple of 8 (4 -> 8 for single-channel radar) so the tensor-core convs can consume it."""
     n, d, h, w, c = x.shape
     h2, w2 = h // 2, w // 2
+    co = pad8(4 * c) if pad else 4 * c
     ss = contig_strides((n, d, h, w, c))
-    ds = contig_strides((n, d, h2, w2, 4 * c))
-    return permute(x, (n, d, h2, w2, 4 * c), (n, d, h2, w2, c, 2, 2),
+    ds = contig_strides((n, d, h2, w2, co))
+    return permute(x, (n, d, h2, w2, co), (n, d, h2, w2, c, 2, 2),
                    (ss[0], ss[1], 2 * ss[2], 2 * ss[3], 1, ss[2], ss[3]), (ds[0], ds[1], ds[2], ds[3], 4, 2, 1))
 
 
@@ -345,6 +351,27 @@ def packed_weight(w: torch.Tensor, ci0: int, cin: int, mode: int) -> torch.Tenso
     return p
 
 
+def packed_weight_padded(w: torch.Tensor, ci0: int, cin: int, cin_p: int, mode: int) -> torch.Tensor:
+    """Like packed_weight but with the input-channel axis zero-padded to cin_p (the 4-channel space-to-depth inputs
+    are carried as 8 channels so that the tensor-core path, whose K step is 8 tf32, can serve them)."""
+    key = (w.data_ptr(), tuple(w.shape), ci0, cin, ("pad", cin_p, mode), str(w.device))
+    ver = w._version
+    hit = _pack_cache.get(key)
+    if hit is not None and hit[0] == ver:
+        return hit[1]
+    cout, cintot = w.shape[0], w.shape[1]
+    taps = w.numel() // (cout * cintot)
+    p = _zeros((taps * cout * cin_p,), w)
+    wd = _c(w.detach())
+    if mode == 0:   # p[tap][co][ci]
+        _be().permute(wd, p, (taps, cout, cin), (1, cintot * taps, taps), (cout * cin_p, cin_p, 1), False, ci0 * taps, 0)
+    else:           # p[taps-1-tap][ci][co]: the dense dgrad pack with its ci rows spread to pitch cin_p (extra rows stay zero)
+        dense = packed_weight(w, ci0, cin, 1)
+        _be().permute(dense, p, (taps, cin, cout), (cin * cout, cout, 1), (cin_p * cout, cout, 1), False, 0, 0)
+    _pack_cache[key] = (ver, p)
+    return p
+
+
 def clear_pack_cache():
     _pack_cache.clear()
 
@@ -356,14 +383,14 @@ class _Conv(Function):
     def forward(ctx, x, w, bias, scale, res, ci0, cin, G, act, exact_dscale=False):
         x = _c(x)
         n, d, h, wd, c = x.shape
-        assert c == cin, (c, cin)
+        assert c == cin or (c > cin and c == (cin + 7) // 8 * 8), (c, cin)   # c > cin: zero-padded input channels
         cout = w.shape[0]
         ks = tuple(w.shape[2:])
         kd, kh, kw = (1,) * (3 - len(ks)) + ks
-        wp = packed_weight(w, ci0, cin, 0)
+        wp = packed_weight(w, ci0, cin, 0) if c == cin else packed_weight_padded(w, ci0, cin, c, 0)
         y = _new((n, d, h, wd, cout), x)
         res_c, scale_c, bias_c = _c(res), _c(scale), _c(bias)
-        _be().conv_fwd(x, wp, bias_c, scale_c, res_c, y, n, d, h, wd, cin, cout, kd, kh, kw, G, act,
+        _be().conv_fwd(x, wp, bias_c, scale_c, res_c, y, n, d, h, wd, c, cout, kd, kh, kw, G, act,
                        config.conv_algo, config.precision)
         need_s = scale is not None and scale.requires_grad
         need_y = act == ACT_RELU or need_s
@@ -377,7 +404,7 @@ class _Conv(Function):
         ci0, cin, G, act, (kd, kh, kw), has_res, exact_dscale = ctx.meta
         be = _be()
         dy = _c(dy)
-        n, d, h, wd, _ = x.shape
+        n, d, h, wd, cp = x.shape   # cp > cin: zero-padded input channels
         cout = w.shape[0]
         rows = (n // G) * d * h * wd
         need_x, need_w, need_b, need_s, need_r = (ctx.needs_input_grad[i] for i in range(5))
@@ -407,17 +434,20 @@ class _Conv(Function):
                 dpre = dy
         dx = dw = None
         if need_x:
-            wpt = packed_weight(w, ci0, cin, 1)
+            wpt = packed_weight(w, ci0, cin, 1) if cp == cin else packed_weight_padded(w, ci0, cin, cp, 1)
             dx = _new(x.shape, x)
-            be.conv_fwd(dz, wpt, None, None, None, dx, n, d, h, wd, cout, cin, kd, kh, kw, 1, ACT_NONE,
+            be.conv_fwd(dz, wpt, None, None, None, dx, n, d, h, wd, cout, cp, kd, kh, kw, 1, ACT_NONE,
                         config.conv_algo, config.precision)
         if need_w:
             taps = kd * kh * kw
-            dwp = _new((taps * cout * cin,), x)
-            be.conv_wgrad(x, dz, dwp, n, d, h, wd, cin, cout, kd, kh, kw, config.wgrad_algo, config.precision)
+            dwp = _new((taps * cout * cp,), x)
+            be.conv_wgrad(x, dz, dwp, n, d, h, wd, cp, cout, kd, kh, kw, config.wgrad_algo, config.precision)
             cintot = w.shape[1]
             dw = _new(w.shape, x) if cin == cintot else _zeros(w.shape, x)
-            be.unpack_wgrad(dwp, dw, cout, cintot, ci0, cin, taps, False)
+            if cp == cin:
+                be.unpack_wgrad(dwp, dw, cout, cintot, ci0, cin, taps, False)
+            else:  # drop the padded channels: dw[co][ci0+ci][tap] = dwp[tap][co][ci], ci < cin
+                be.permute(dwp, dw, (taps, cout, cin), (cout * cp, cp, 1), (1, cintot * taps, taps), False, 0, ci0 * taps)
         return dx, dw, dbias, dscale, (dpre if need_r else None), None, None, None, None, None
 
 

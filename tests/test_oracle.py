@@ -15,8 +15,8 @@ def c1():
 
 def test_seeded_construction_matches_fixture_checksum(c1):
     fix = torch.load(GOLDEN)
-    assert state_checksum(c1[0]) == pytest.approx(fix["g_checksum"], rel=1e-12)
-    assert state_checksum(c1[1]) == pytest.approx(fix["d_checksum"], rel=1e-12)
+    assert state_checksum(c1[0]) == pytest.approx(fix["g_checksum"], rel=1e-8)
+    assert state_checksum(c1[1]) == pytest.approx(fix["d_checksum"], rel=1e-8)
 
 
 @pytest.mark.parametrize("mode", ["eval", "train"])

@@ -26,6 +26,8 @@ UMMA_SHAPES = [
     (2, 5, 8, 8, 48, 96, 3, 3, 3, 1),       # 3-D conv, odd depth, box spans 2 images
     (2, 1, 64, 64, 96, 96, 1, 3, 3, 1),     # bigger
     (2, 1, 8, 8, 768, 768, 1, 3, 3, 1),     # K = 6912, 3 N tiles
+    (2, 1, 32, 32, 48, 4, 1, 1, 1, 2),      # Cout=4 (sampler output conv / dgrad into a 4-channel input): N tile 16, 12 OOB rows
+    (2, 3, 16, 16, 48, 8, 3, 3, 3, 1),      # 3-D dgrad into the zero-padded 8-channel temporal-D input
 ]
 
 
@@ -70,6 +72,9 @@ WGRAD_SHAPES = [
     (2, 1, 64, 64, 192, 384, 1, 1, 1),    # 1x1
     (2, 6, 16, 16, 48, 96, 3, 3, 3),      # 3-D
     (4, 1, 16, 16, 768, 768, 1, 3, 3),    # 3 ci tiles x 6 co tiles
+    (4, 1, 32, 32, 8, 48, 1, 3, 3),       # zero-padded 4->8 channel input (first DBlocks)
+    (2, 4, 16, 16, 8, 48, 3, 3, 3),       # same, 3-D
+    (4, 1, 32, 32, 48, 4, 1, 1, 1),       # Cout=4
 ]
 
 
