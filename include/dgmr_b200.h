@@ -34,6 +34,11 @@ extern "C" {
 typedef void* dgmr_stream_t; /* cudaStream_t */
 
 enum { DGMR_ACT_NONE = 0, DGMR_ACT_RELU = 1 };
+/* OR-able flag: round the produced tensor-core operand (packed weights in dgmr_pack_weight's `mode`, dz in
+ * dgmr_conv_bwd_prep's `act`) to the nearest TF32 value.  tcgen05 kind::tf32 ignores the low 13 mantissa bits of its
+ * fp32 operands (truncation, biased); feeding it round-to-nearest values gives the unbiased rounding cuDNN applies
+ * for the reference's TF32 convolutions. */
+enum { DGMR_FLAG_ROUND_TF32 = 256 };
 /* conv algorithm selector */
 enum { DGMR_ALGO_AUTO = 0, DGMR_ALGO_SIMT = 1, DGMR_ALGO_UMMA = 2 };
 /* tensor-core operand precision: 1xTF32 (what cuDNN does by default for the reference) or
@@ -185,6 +190,10 @@ int dgmr_grid_cell_bwd(const float* gen, const float* target, float cap, float c
  * g is multiplied by grad_scale first (1/world_size after the NCCL all-reduce). */
 int dgmr_adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
               float eps, int step, float grad_scale, dgmr_stream_t stream);
+
+/* in place: x <- nearest TF32-representable value (cvt.rna.tf32.f32); applied to activations before they enter a
+ * tensor-core convolution (idempotent) */
+int dgmr_round_tf32(float* x, int64_t n, dgmr_stream_t stream);
 
 /* ---- 3xTF32 support: hi = x & ~0x1fff, lo = x - hi */
 int dgmr_split_tf32(const float* x, float* hi, float* lo, int64_t n, dgmr_stream_t stream);

@@ -23,6 +23,7 @@ LIB_PATH = os.path.join(_HERE, "libdgmr_b200.so")
 ACT_NONE, ACT_RELU = 0, 1
 ALGO_AUTO, ALGO_SIMT, ALGO_UMMA = 0, 1, 2
 PREC_TF32, PREC_3XTF32 = 0, 1
+FLAG_ROUND_TF32 = 256
 
 _CTYPES = {
     "int": ctypes.c_int,
@@ -166,6 +167,9 @@ class CudaBackend:
 
     def relu_bwd(self, dy, x, dx):
         self._call("dgmr_relu_bwd", _f32(dy, "dy"), _f32(x, "x"), _f32(dx, "dx"), x.numel())
+
+    def round_tf32(self, x):
+        self._call("dgmr_round_tf32", _f32(x, "x"), x.numel())
 
     def split_tf32(self, x, hi, lo):
         self._call("dgmr_split_tf32", _f32(x, "x"), _f32(hi, "hi"), _f32(lo, "lo"), x.numel())

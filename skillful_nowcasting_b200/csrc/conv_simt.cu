@@ -190,19 +190,36 @@ __global__ void __launch_bounds__(256) conv_simt_wgrad_kernel(const float* __res
 }
 
 // ------------------------------------------------------------------ pack / unpack
-__global__ void pack_weight_kernel(const float* __restrict__ w, float* __restrict__ packed, int Cout, int CinTot, int ci0, int Cin, int taps, int mode) {
+__device__ __forceinline__ float rna_tf32(float x) {  // round to nearest tf32 (10 explicit mantissa bits), low 13 bits zero
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
+__global__ void pack_weight_kernel(const float* __restrict__ w, float* __restrict__ packed, int Cout, int CinTot, int ci0, int Cin, int taps, int mode, int rnd) {
   int64_t total = (int64_t)taps * Cout * Cin;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     // iterate in destination order for coalesced writes
+    float v;
     if (mode == 0) {
       int ci = i % Cin; int64_t r = i / Cin; int co = r % Cout; int tap = r / Cout;
-      packed[i] = w[((int64_t)co * CinTot + ci0 + ci) * taps + tap];
+      v = w[((int64_t)co * CinTot + ci0 + ci) * taps + tap];
     } else {
       int co = i % Cout; int64_t r = i / Cout; int ci = r % Cin; int tapf = r / Cin;
       int tap = taps - 1 - tapf;
-      packed[i] = w[((int64_t)co * CinTot + ci0 + ci) * taps + tap];
+      v = w[((int64_t)co * CinTot + ci0 + ci) * taps + tap];
     }
+    packed[i] = rnd ? rna_tf32(v) : v;
   }
+}
+__global__ void round_tf32_kernel(float4* __restrict__ x, int64_t n4) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 v = x[i];
+    x[i] = make_float4(rna_tf32(v.x), rna_tf32(v.y), rna_tf32(v.z), rna_tf32(v.w));
+  }
+}
+__global__ void round_tf32_tail_kernel(float* __restrict__ x, int64_t start, int64_t n) {
+  int64_t i = start + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) x[i] = rna_tf32(x[i]);
 }
 __global__ void unpack_wgrad_kernel(const float* __restrict__ packed, float* __restrict__ gw, int Cout, int CinTot, int ci0, int Cin, int taps, int acc) {
   int64_t total = (int64_t)taps * Cout * Cin;
@@ -223,7 +240,7 @@ template <int V>
 __global__ void __launch_bounds__(256) conv_bwd_prep_kernel(const float* __restrict__ dy, const float* __restrict__ y, const float* __restrict__ res,
                                                             const float* __restrict__ bias, const float* __restrict__ scale, float* __restrict__ dz,
                                                             float* __restrict__ dpre, float* __restrict__ dbias, float* __restrict__ dscale,
-                                                            int64_t rows, int C, int64_t chunk, int act) {
+                                                            int64_t rows, int C, int64_t chunk, int act, int rnd) {
   extern __shared__ double sh[];  // [rp][cpl][2*V]
   const int g = blockIdx.y;
   const int CV = C / V;
@@ -260,6 +277,7 @@ __global__ void __launch_bounds__(256) conv_bwd_prep_kernel(const float* __restr
           float yy = y ? yv[i] : 0.f;
           if (act == DGMR_ACT_RELU && !(yy > 0.f)) d[i] = 0.f;
           zo[i] = d[i] * sc[i];
+          if (rnd) zo[i] = rna_tf32(zo[i]);
           fs[i] += d[i];
           if (dscale) fq[i] += d[i] * (yy - bi[i] - ((res) ? rv[i] : 0.f));
         }
@@ -309,11 +327,29 @@ struct SnArgs {
   float* inv_sigma; float* u_hist; float* v_hist;
   float* t;   // [(G+1)][R] zeroed
   float* nq;  // [G] zeroed
+  unsigned* bar;  // zeroed arrival counter of the grid barrier
   int kw; int in_smem;
 };
-__device__ __forceinline__ float block_sumsq(const float* __restrict__ a, int n, float* red) {
+// Grid-wide barrier for the co-resident (cooperatively launched) CTAs: one monotonically increasing arrival counter,
+// barrier k completes when it reaches k * gridDim.x.  ~1 us instead of the several us of cooperative_groups' grid.sync().
+__device__ __forceinline__ void sn_grid_barrier(unsigned* counter, unsigned& epoch) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    ++epoch;
+    const unsigned target = epoch * gridDim.x;
+    __threadfence();
+    atomicAdd(counter, 1u);
+    unsigned seen;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+    } while (seen < target);
+    __threadfence();
+  }
+  __syncthreads();
+}
+__device__ __forceinline__ float block_sumsq(const float* a, int n, float* red) {
   float s = 0.f;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) { float v = a[i]; s += v * v; }
+  for (int i = threadIdx.x; i < n; i += blockDim.x) { float v = __ldcg(a + i); s += v * v; }
   s = warp_sum(s);
   __syncthreads();
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
@@ -323,8 +359,8 @@ __device__ __forceinline__ float block_sumsq(const float* __restrict__ a, int n,
   return tot;
 }
 __global__ void __launch_bounds__(256) sn_power_iter_kernel(SnArgs a) {
-  cg::grid_group grid = cg::this_grid();
   extern __shared__ float smem[];
+  unsigned epoch = 0;   // only thread 0's copy is used
   const int R = a.R, K = a.K, kwmax = a.kw;
   const int k0 = blockIdx.x * kwmax;
   const int kw = (k0 + kwmax <= K) ? kwmax : (K - k0 > 0 ? K - k0 : 0);
@@ -351,12 +387,12 @@ __global__ void __launch_bounds__(256) sn_power_iter_kernel(SnArgs a) {
     }
   };
   matvec(0);
-  grid.sync();
+  sn_grid_barrier(a.bar, epoch);
   if (!a.training) {
     // sigma = u0 . (W v0), same for all G calls
     if (blockIdx.x == 0) {
       float s = 0.f;
-      for (int r = threadIdx.x; r < R; r += blockDim.x) s += a.u[r] * a.t[r];
+      for (int r = threadIdx.x; r < R; r += blockDim.x) s += a.u[r] * __ldcg(a.t + r);
       s = warp_sum(s);
       if (lane == 0) red[warp] = s;
       __syncthreads();
@@ -375,7 +411,7 @@ __global__ void __launch_bounds__(256) sn_power_iter_kernel(SnArgs a) {
     const float* tg = a.t + (int64_t)g * R;
     float nrm = sqrtf(block_sumsq(tg, R, red));
     float inv = 1.0f / fmaxf(nrm, a.eps);
-    for (int r = threadIdx.x; r < R; r += blockDim.x) ush[r] = tg[r] * inv;
+    for (int r = threadIdx.x; r < R; r += blockDim.x) ush[r] = __ldcg(tg + r) * inv;
     for (int k = threadIdx.x; k < kwmax; k += blockDim.x) qsh[k] = 0.f;
     __syncthreads();
     if (blockIdx.x == 0) for (int r = threadIdx.x; r < R; r += blockDim.x) a.u_hist[(int64_t)g * R + r] = ush[r];
@@ -392,17 +428,17 @@ __global__ void __launch_bounds__(256) sn_power_iter_kernel(SnArgs a) {
     if (lane == 0) red[warp] = part;
     __syncthreads();
     if (threadIdx.x == 0) { float tot = 0.f; for (int w = 0; w < nwarps; ++w) tot += red[w]; atomicAdd(&a.nq[g], tot); }
-    grid.sync();
-    float qn = sqrtf(*((volatile float*)&a.nq[g]));
+    sn_grid_barrier(a.bar, epoch);
+    float qn = sqrtf(__ldcg(a.nq + g));
     float qinv = 1.0f / fmaxf(qn, a.eps);
     for (int k = threadIdx.x; k < kw; k += blockDim.x) { float vv = qsh[k] * qinv; vsh[k] = vv; a.v_hist[(int64_t)g * K + k0 + k] = vv; }
     __syncthreads();
     matvec(g + 1);
-    grid.sync();
+    sn_grid_barrier(a.bar, epoch);
     if (blockIdx.x == 0) {
       const float* tn = a.t + (int64_t)(g + 1) * R;
       float s = 0.f;
-      for (int r = threadIdx.x; r < R; r += blockDim.x) s += ush[r] * ((volatile const float*)tn)[r];
+      for (int r = threadIdx.x; r < R; r += blockDim.x) s += ush[r] * __ldcg(tn + r);
       s = warp_sum(s);
       __syncthreads();
       if (lane == 0) red[warp] = s;
@@ -464,11 +500,21 @@ using namespace dgmr;
 extern "C" {
 
 int dgmr_pack_weight(const float* w, float* packed, int Cout, int CinTot, int ci0, int Cin, int taps, int mode, dgmr_stream_t stream) {
+  const int rnd = (mode & DGMR_FLAG_ROUND_TF32) ? 1 : 0;
+  mode &= ~DGMR_FLAG_ROUND_TF32;
   DGMR_REQUIRE(ci0 >= 0 && ci0 + Cin <= CinTot && (mode == 0 || mode == 1), "dgmr_pack_weight: bad slice/mode");
   int64_t total = (int64_t)taps * Cout * Cin;
   if (total == 0) return 0;
-  pack_weight_kernel<<<ew_grid(total, 256, 2), 256, 0, S(stream)>>>(w, packed, Cout, CinTot, ci0, Cin, taps, mode);
+  pack_weight_kernel<<<ew_grid(total, 256, 2), 256, 0, S(stream)>>>(w, packed, Cout, CinTot, ci0, Cin, taps, mode, rnd);
   DGMR_CHECK_LAUNCH("dgmr_pack_weight");
+  return 0;
+}
+int dgmr_round_tf32(float* x, int64_t n, dgmr_stream_t stream) {
+  if (n == 0) return 0;
+  DGMR_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15u) == 0, "dgmr_round_tf32: pointer must be 16-byte aligned");
+  int64_t n4 = n / 4;
+  if (n4) { round_tf32_kernel<<<ew_grid(n4, 256, 2), 256, 0, S(stream)>>>(reinterpret_cast<float4*>(x), n4); DGMR_CHECK_LAUNCH("dgmr_round_tf32"); }
+  if (n % 4) { round_tf32_tail_kernel<<<1, 4, 0, S(stream)>>>(x, n4 * 4, n); DGMR_CHECK_LAUNCH("dgmr_round_tf32_tail"); }
   return 0;
 }
 int dgmr_unpack_wgrad(const float* packed, float* gw, int Cout, int CinTot, int ci0, int Cin, int taps, int accumulate, dgmr_stream_t stream) {
@@ -481,6 +527,8 @@ int dgmr_unpack_wgrad(const float* packed, float* gw, int Cout, int CinTot, int 
 }
 int dgmr_conv_bwd_prep(const float* dy, const float* y, const float* res, const float* bias, const float* scale, float* dz, float* dpre, float* dbias,
                        float* dscale, int64_t rows, int G, int Cout, int act, int accumulate_dbias, dgmr_stream_t stream) {
+  const int rnd = (act & DGMR_FLAG_ROUND_TF32) ? 1 : 0;
+  act &= ~DGMR_FLAG_ROUND_TF32;
   DGMR_REQUIRE(rows > 0 && G > 0 && Cout > 0, "dgmr_conv_bwd_prep: bad dims");
   DGMR_REQUIRE(!(dscale && !scale), "dgmr_conv_bwd_prep: dscale requested without scale");
   DGMR_REQUIRE(!((act == DGMR_ACT_RELU || dscale) && !y), "dgmr_conv_bwd_prep: y required");
@@ -490,9 +538,9 @@ int dgmr_conv_bwd_prep(const float* dy, const float* y, const float* res, const 
   int64_t chunk = ceil_div(rows, bpg); if (chunk < 64) chunk = 64;
   dim3 grid((unsigned)ceil_div(rows, chunk), G);
   if (Cout % 4 == 0)
-    conv_bwd_prep_kernel<4><<<grid, 256, 256 * 8 * sizeof(double), S(stream)>>>(dy, y, res, bias, scale, dz, dpre, dbias, dscale, rows, Cout, chunk, act);
+    conv_bwd_prep_kernel<4><<<grid, 256, 256 * 8 * sizeof(double), S(stream)>>>(dy, y, res, bias, scale, dz, dpre, dbias, dscale, rows, Cout, chunk, act, rnd);
   else
-    conv_bwd_prep_kernel<1><<<grid, 256, 256 * 2 * sizeof(double), S(stream)>>>(dy, y, res, bias, scale, dz, dpre, dbias, dscale, rows, Cout, chunk, act);
+    conv_bwd_prep_kernel<1><<<grid, 256, 256 * 2 * sizeof(double), S(stream)>>>(dy, y, res, bias, scale, dz, dpre, dbias, dscale, rows, Cout, chunk, act, rnd);
   DGMR_CHECK_LAUNCH("dgmr_conv_bwd_prep");
   return 0;
 }
@@ -510,7 +558,7 @@ int dgmr_sn_power_iter(const float* w, float* u, float* v, int R, int K, int G, 
   int sms = sm_count();
   // CTAs: enough that a slice fits in smem and <= 256 columns each; few CTAs for small weights
   int64_t budget = (int64_t)max_smem - (int64_t)(R + 32) * 4 - 1024;
-  int nb = (int)ceil_div((int64_t)R * K, 16384);
+  int nb = (int)ceil_div((int64_t)R * K, 32768);
   if (nb < 1) nb = 1;
   if (nb < ceil_div(K, 256)) nb = (int)ceil_div(K, 256);
   if (nb > sms) nb = sms;
@@ -528,7 +576,8 @@ int dgmr_sn_power_iter(const float* w, float* u, float* v, int R, int K, int G, 
   a.w = w; a.u = u; a.v = v; a.R = R; a.K = K; a.G = G; a.eps = eps; a.training = training;
   a.inv_sigma = inv_sigma; a.u_hist = u_hist; a.v_hist = v_hist;
   a.t = ws; a.nq = ws + (size_t)(G + 1) * R; a.kw = kw; a.in_smem = in_smem;
-  DGMR_CUDA(cudaMemsetAsync(ws, 0, sizeof(float) * ((size_t)(G + 1) * R + G), S(stream)));
+  a.bar = reinterpret_cast<unsigned*>(ws + (size_t)(G + 1) * R + G);
+  DGMR_CUDA(cudaMemsetAsync(ws, 0, sizeof(float) * ((size_t)(G + 1) * R + G + 1), S(stream)));
   void* args[] = {&a};
   cudaError_t e = cudaLaunchCooperativeKernel((void*)sn_power_iter_kernel, dim3(nb), dim3(256), args, sh, S(stream));
   if (e != cudaSuccess) { set_error("dgmr_sn_power_iter: cooperative launch failed: %s (nb=%d smem=%zu)", cudaGetErrorString(e), nb, sh); return 2; }

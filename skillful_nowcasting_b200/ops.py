@@ -12,7 +12,7 @@ import torch
 from torch.autograd import Function
 
 from . import _lib
-from ._lib import ACT_NONE, ACT_RELU, ALGO_AUTO, ALGO_SIMT, ALGO_UMMA, PREC_TF32
+from ._lib import ACT_NONE, ACT_RELU, ALGO_AUTO, ALGO_SIMT, ALGO_UMMA, FLAG_ROUND_TF32, PREC_TF32
 
 
 class config:
@@ -20,6 +20,9 @@ class config:
     conv_algo = ALGO_AUTO
     wgrad_algo = ALGO_AUTO
     precision = PREC_TF32
+    # operands of tensor-core convs are rounded to the NEAREST tf32 value first (the MMA itself truncates, which is
+    # biased): weights while packing, activations in place (idempotent), dz in the backward prologue
+    round_tf32 = True
 
 
 def _be():
@@ -88,8 +91,8 @@ def nchw_to_cl(x: torch.Tensor) -> torch.Tensor:
         d = 1
     else:
         n, c, d, h, w = x.shape
-    if c == 1:
-        return x.reshape(n, d, h, w, 1)
+    if c == 1:  # same memory order; private copy because conv inputs may be rounded to tf32 in place
+        return permute(x, (n, d, h, w, 1), (n * d * h * w,), (1,), (1,))
     sp = d * h * w
     return permute(x, (n, d, h, w, c), (n, sp, c), (c * sp, 1, sp), (sp * c, c, 1))
 
@@ -335,9 +338,26 @@ def spectral_inv_sigma(w, u, v, G, eps, training):
 _pack_cache = {}
 
 
+def _round_(t: torch.Tensor) -> torch.Tensor:
+    """Round a conv operand to tf32 in place, once (the flag rides on the Python tensor object)."""
+    if not getattr(t, "_dgmr_tf32", False):
+        _be().round_tf32(t)
+        t._dgmr_tf32 = True
+    return t
+
+
+def _tc_fwd(n, d, h, w, cin, cout, kd, kh, kw) -> bool:
+    """Will dgmr_conv_fwd serve this shape on the tensor cores (and should operands therefore be tf32-rounded)?"""
+    return (config.round_tf32 and config.conv_algo != ALGO_SIMT and _be().conv_umma_supported(n, d, h, w, cin, cout, kd, kh, kw))
+
+
+def _tc_wgrad(n, d, h, w, cin, cout, kd, kh, kw) -> bool:
+    return (config.round_tf32 and config.wgrad_algo != ALGO_SIMT and _be().wgrad_umma_supported(n, d, h, w, cin, cout, kd, kh, kw))
+
+
 def packed_weight(w: torch.Tensor, ci0: int, cin: int, mode: int) -> torch.Tensor:
     """[tap][Cout][Cin] (mode 0) / flipped-transposed dgrad pack (mode 1) of the OIHW weight slice
-    [:, ci0:ci0+cin]; cached until the parameter's version counter moves."""
+    [:, ci0:ci0+cin]; cached until the parameter's version counter moves.  mode | FLAG_ROUND_TF32: tf32-rounded."""
     key = (w.data_ptr(), tuple(w.shape), ci0, cin, mode, str(w.device))
     ver = w._version
     hit = _pack_cache.get(key)
@@ -362,11 +382,11 @@ def packed_weight_padded(w: torch.Tensor, ci0: int, cin: int, cin_p: int, mode: 
     cout, cintot = w.shape[0], w.shape[1]
     taps = w.numel() // (cout * cintot)
     p = _zeros((taps * cout * cin_p,), w)
-    wd = _c(w.detach())
-    if mode == 0:   # p[tap][co][ci]
-        _be().permute(wd, p, (taps, cout, cin), (1, cintot * taps, taps), (cout * cin_p, cin_p, 1), False, ci0 * taps, 0)
-    else:           # p[taps-1-tap][ci][co]: the dense dgrad pack with its ci rows spread to pitch cin_p (extra rows stay zero)
-        dense = packed_weight(w, ci0, cin, 1)
+    rnd, mode = mode & FLAG_ROUND_TF32, mode & ~FLAG_ROUND_TF32
+    dense = packed_weight(w, ci0, cin, mode | rnd)
+    if mode == 0:   # p[tap][co][ci] with row pitch cin_p
+        _be().permute(dense, p, (taps * cout, cin), (cin, 1), (cin_p, 1), False, 0, 0)
+    else:           # p[taps-1-tap][ci][co]: ci rows spread to cin_p per tap (extra rows stay zero)
         _be().permute(dense, p, (taps, cin, cout), (cin * cout, cout, 1), (cin_p * cout, cout, 1), False, 0, 0)
     _pack_cache[key] = (ver, p)
     return p
@@ -387,7 +407,10 @@ class _Conv(Function):
         cout = w.shape[0]
         ks = tuple(w.shape[2:])
         kd, kh, kw = (1,) * (3 - len(ks)) + ks
-        wp = packed_weight(w, ci0, cin, 0) if c == cin else packed_weight_padded(w, ci0, cin, c, 0)
+        rnd = FLAG_ROUND_TF32 if _tc_fwd(n, d, h, wd, c, cout, kd, kh, kw) else 0
+        if rnd:
+            _round_(x)
+        wp = packed_weight(w, ci0, cin, rnd) if c == cin else packed_weight_padded(w, ci0, cin, c, rnd)
         y = _new((n, d, h, wd, cout), x)
         res_c, scale_c, bias_c = _c(res), _c(scale), _c(bias)
         _be().conv_fwd(x, wp, bias_c, scale_c, res_c, y, n, d, h, wd, c, cout, kd, kh, kw, G, act,
@@ -418,7 +441,9 @@ class _Conv(Function):
             dpre = _new(dy.shape, dy) if (need_r and act == ACT_RELU) else None
             dbias = _new((cout,), dy) if need_b else None
             dscale = _new((G, cout), dy) if need_s else None
-            be.conv_bwd_prep(dy, y, res if need_s else None, bias, scale, dz, dpre, dbias, dscale, rows, G, cout, act)
+            tc_bwd = (need_x and _tc_fwd(n, d, h, wd, cout, cp, kd, kh, kw)) or (need_w and _tc_wgrad(n, d, h, wd, cp, cout, kd, kh, kw))
+            be.conv_bwd_prep(dy, y, res if need_s else None, bias, scale, dz, dpre, dbias, dscale, rows, G, cout,
+                             act | (FLAG_ROUND_TF32 if (tc_bwd and dz is not None) else 0))
             if need_s and exact_dscale:
                 # the <dY, Y-b-res>/scale identity divides by the scale, which may be exactly 0 (attention gamma starts at 0,
                 # ref: dgmr/layers/Attention.py:69): recompute the raw conv output and reduce <dpre, z> directly
@@ -430,11 +455,16 @@ class _Conv(Function):
                 be.conv_bwd_prep(dy, z, None, None, ones, None, None, None, dscale, rows, G, cout, ACT_NONE)
             if dz is None:
                 dz = dy
+            elif tc_bwd:
+                dz._dgmr_tf32 = True
             if dpre is None:
                 dpre = dy
         dx = dw = None
+        if (need_x and _tc_fwd(n, d, h, wd, cout, cp, kd, kh, kw)) or (need_w and _tc_wgrad(n, d, h, wd, cp, cout, kd, kh, kw)):
+            _round_(dz)   # no-op for a dz the prologue already rounded
         if need_x:
-            wpt = packed_weight(w, ci0, cin, 1) if cp == cin else packed_weight_padded(w, ci0, cin, cp, 1)
+            rnd = FLAG_ROUND_TF32 if _tc_fwd(n, d, h, wd, cout, cp, kd, kh, kw) else 0
+            wpt = packed_weight(w, ci0, cin, 1 | rnd) if cp == cin else packed_weight_padded(w, ci0, cin, cp, 1 | rnd)
             dx = _new(x.shape, x)
             be.conv_fwd(dz, wpt, None, None, None, dx, n, d, h, wd, cout, cp, kd, kh, kw, 1, ACT_NONE,
                         config.conv_algo, config.precision)

@@ -61,6 +61,16 @@ class EmuBackend:
     def relu_bwd(self, dy, x, dx):
         dx.copy_(dy * (x > 0))
 
+    @staticmethod
+    def _rna_tf32(x):
+        u = x.contiguous().view(torch.int32).to(torch.int64) & 0xFFFFFFFF        # raw bit pattern (sign-magnitude)
+        r = (u + 0x1000) & 0xFFFFE000                                              # nearest, ties away in magnitude (cvt.rna)
+        r = torch.where(r >= 2 ** 31, r - 2 ** 32, r).to(torch.int32)
+        return r.view(torch.float32)
+
+    def round_tf32(self, x):
+        x.copy_(self._rna_tf32(x))
+
     def split_tf32(self, x, hi, lo):
         h = (x.view(torch.int32) & -8192).view(torch.float32)
         hi.copy_(h)
@@ -188,11 +198,14 @@ class EmuBackend:
 
     # ---- conv
     def pack_weight(self, w, packed, Cout, CinTot, ci0, Cin, taps, mode):
+        rnd, mode = bool(mode & 256), mode & ~256
         wv = w.reshape(Cout, CinTot, taps)[:, ci0:ci0 + Cin]
         if mode == 0:
             packed.copy_(wv.permute(2, 0, 1).reshape(-1))
         else:
             packed.copy_(wv.flip(2).permute(2, 1, 0).reshape(-1))
+        if rnd:
+            packed.copy_(self._rna_tf32(packed))
 
     def unpack_wgrad(self, packed, gw, Cout, CinTot, ci0, Cin, taps, accumulate):
         g = packed.reshape(taps, Cout, Cin).permute(1, 2, 0)
@@ -219,11 +232,14 @@ class EmuBackend:
         y.copy_(z.reshape(y.shape))
 
     def conv_bwd_prep(self, dy, y, res, bias, scale, dz, dpre, dbias, dscale, rows, G, Cout, act, accumulate_dbias=False):
+        rnd, act = bool(act & 256), act & ~256
         d = dy.reshape(G, rows, Cout)
         if act == 1:
             d = d * (y.reshape(G, rows, Cout) > 0)
         if dz is not None:
             dz.copy_((d * scale.reshape(G, 1, Cout) if scale is not None else d).reshape(dz.shape))
+            if rnd:
+                dz.copy_(self._rna_tf32(dz))
         if dpre is not None:
             dpre.copy_(d.reshape(dpre.shape))
         if dbias is not None:

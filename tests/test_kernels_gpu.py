@@ -50,6 +50,7 @@ def test_pointwise(cuda_backend):
     _both("relu_bwd", [y, x, torch.empty(n)], cuda_backend, rtol=0, atol=0)
     _both("split_tf32", [x, torch.empty(n), torch.empty(n)], cuda_backend, rtol=0, atol=0)
     _both("fill", [torch.empty(n), 3.5], cuda_backend, rtol=0, atol=0)
+    _both("round_tf32", [torch.randn(n) * 100], cuda_backend, rtol=0, atol=0)   # cvt.rna.tf32.f32, bit-exact
 
 
 @pytest.mark.parametrize("dims,win", [((2, 1, 8, 12, 5), (1, 2, 2)), ((2, 5, 6, 6, 3), (2, 2, 2)), ((1, 22, 4, 4, 1), (1, 2, 2))])
@@ -122,7 +123,7 @@ def test_pack_unpack(cuda_backend):
     torch.manual_seed(6)
     cout, cintot, taps = 10, 12, 9
     w = torch.randn(cout, cintot, taps)
-    for mode in (0, 1):
+    for mode in (0, 1, 256, 257):   # +256: tf32-rounded pack
         _both("pack_weight", [w, torch.empty(taps * cout * 8), cout, cintot, 4, 8, taps, mode], cuda_backend, rtol=0, atol=0)
     p = torch.randn(taps * cout * 8)
     _both("unpack_wgrad", [p, torch.zeros(cout, cintot, taps), cout, cintot, 4, 8, taps, False], cuda_backend, rtol=0, atol=0)
@@ -164,7 +165,7 @@ def test_conv_simt(cuda_backend, shape, act, with_res, with_scale):
           rtol=5e-5, atol=5e-5, kwargs=dict(algo=1))
 
 
-@pytest.mark.parametrize("G,rows,C,act", [(1, 300, 24, 0), (3, 64, 48, 1), (2, 17, 4, 1)])
+@pytest.mark.parametrize("G,rows,C,act", [(1, 300, 24, 0), (3, 64, 48, 1), (2, 17, 4, 1), (2, 40, 32, 257), (1, 33, 7, 1)])
 def test_conv_bwd_prep(cuda_backend, G, rows, C, act):
     torch.manual_seed(8)
     dy, y, res = (torch.randn(G * rows, C) for _ in range(3))
