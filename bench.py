@@ -114,6 +114,40 @@ def cpu_reference_steps(cfg, batch, steps, warmup, k):
                        f"{mean:.2f} s/step", s_per_step=mean)
 
 
+def gpu_reference_steps(cfg, batch, steps, warmup, k, dev):
+    """The reference's GPU path for the '>= 5x cuDNN-backed step' target: the same oracle port, tensors on cuda
+    (PyTorch eager, cuDNN convs with torch's default allow_tf32=True), minimal schedule like the B200 arm."""
+    from oracle import dgmr_oracle as O
+
+    gen, disc = build_oracle_state(cfg)
+    gs = {k_: v.to(dev) for k_, v in O.clone_state(gen.state_dict()).items()}
+    ds = {k_: v.to(dev) for k_, v in O.clone_state(disc.state_dict()).items()}
+    for st in (gs, ds):
+        for k_, v in st.items():
+            if v.is_floating_point() and not (k_.endswith("._u") or k_.endswith("._v") or "running_" in k_):
+                v.requires_grad_(True)
+    g_opt = O.AdamState([gs[n] for n in O._trainable(gs)], lr=5e-5)
+    d_opt = O.AdamState([ds[n] for n in O._trainable(ds)], lr=2e-4)
+    s = cfg["output_shape"]
+    x = torch.rand(batch, 4, 1, s, s, device=dev)
+    y = torch.rand(batch, cfg["forecast_steps"], 1, s, s, device=dev)
+    try:
+        for _ in range(warmup):
+            O.gan_step(gs, ds, g_opt, d_opt, x, y, cfg["forecast_steps"], (8, s // 32, s // 32), generation_steps=k)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            O.gan_step(gs, ds, g_opt, d_opt, x, y, cfg["forecast_steps"], (8, s // 32, s // 32), generation_steps=k)
+        e1.record()
+        torch.cuda.synchronize()
+    except torch.cuda.OutOfMemoryError:
+        return dict(batch=batch, error="out of memory")
+    ms = e0.elapsed_time(e1) / steps
+    return dict(batch=batch, ms_per_step=ms, value=batch * cfg["forecast_steps"] / (ms * 1e-3), unit="frames/s",
+                what="oracle port on cuda (PyTorch eager + cuDNN, allow_tf32 default), minimal schedule")
+
+
 # ----------------------------------------------------------------------------------------------------- GPU arm
 def main():
     ap = argparse.ArgumentParser()
@@ -129,6 +163,9 @@ def main():
     ap.add_argument("--context-channels", type=int, default=384)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-batch", type=int, default=1)
+    ap.add_argument("--ref-gpu", type=int, default=0, metavar="BATCH",
+                    help="also time the reference's own GPU path (the oracle port on cuda: PyTorch eager + cuDNN, TF32 convs "
+                         "allowed as in torch's default) at this batch; reported as `reference_gpu_eager`")
     args = ap.parse_args()
     cfg = dict(output_shape=args.size, forecast_steps=args.forecast_steps, latent_channels=args.latent_channels,
                context_channels=args.context_channels)
@@ -267,6 +304,8 @@ def main():
                            "summed CUDA-event durations"),
         kernel_breakdown_ms={k: round(v[1], 3) for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])},
     )
+    if args.ref_gpu:
+        line["reference_gpu_eager"] = gpu_reference_steps(cfg, args.ref_gpu, 2, 1, K, dev)
     if not args.no_cpu_baseline:
         r = cpu_reference_steps(cfg, args.cpu_batch, 1, 0, K)
         line["cpu_baseline"] = dict(value=r["value"], unit="frames/s", cores=r["cores"], kind="port", sample=r["sample"])

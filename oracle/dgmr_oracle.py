@@ -249,13 +249,13 @@ def context_stack(state: State, p: str, x: torch.Tensor, training: bool):
 
 
 def latent_stack(state: State, p: str, shape: Tuple[int, int, int], training: bool,
-                 z: Optional[torch.Tensor] = None, dtype=torch.float32) -> torch.Tensor:
+                 z: Optional[torch.Tensor] = None, dtype=torch.float32, device=None) -> torch.Tensor:
     """dgmr/common.py:469-497.  The reference draws z = Normal(0,1).sample(shape) on the
     CPU default generator (:481), which is `torch.randn(shape + (1,))` [probe, SURVEY 8a]."""
     q = (lambda n: f"{p}.{n}" if p else n)
     if z is None:
         z = torch.normal(torch.zeros(tuple(shape) + (1,)), torch.ones(tuple(shape) + (1,)))
-    z = z.permute(3, 0, 1, 2).to(dtype)
+    z = z.permute(3, 0, 1, 2).to(dtype=dtype, device=device)   # `.type_as(x)` in the reference (:483)
     z = sn_conv(state, q("conv_3x3"), z, training, SN_EPS_DEFAULT, 1)
     z = l_block(state, q("l_block1"), z)
     z = l_block(state, q("l_block2"), z)
@@ -292,7 +292,7 @@ def generator(state: State, x: torch.Tensor, forecast_steps: int, latent_shape, 
               z: Optional[torch.Tensor] = None) -> torch.Tensor:
     """dgmr/generators.py:207-212 (context stack, then latent stack, then sampler)."""
     cond = context_stack(state, "conditioning_stack", x, training)
-    lat = latent_stack(state, "latent_stack", latent_shape, training, z=z, dtype=x.dtype)
+    lat = latent_stack(state, "latent_stack", latent_shape, training, z=z, dtype=x.dtype, device=x.device)
     return sampler(state, "sampler", cond, lat, forecast_steps, training)
 
 
