@@ -39,6 +39,10 @@ enum { DGMR_ACT_NONE = 0, DGMR_ACT_RELU = 1 };
  * fp32 operands (truncation, biased); feeding it round-to-nearest values gives the unbiased rounding cuDNN applies
  * for the reference's TF32 convolutions. */
 enum { DGMR_FLAG_ROUND_TF32 = 256 };
+/* OR-able into dgmr_conv_fwd's `act`: y += conv(x, wp) * scale  (bias, res must be NULL, act NONE; y pre-initialised by the
+ * caller, e.g. with the residual).  The tensor-core path then splits the K loop over filter taps across CTAs (fp32 red.add
+ * into y), which is what fills the SMs for the small-M, large-K convolutions of the ConvGRU steps. */
+enum { DGMR_FLAG_ACCUMULATE = 512 };
 /* conv algorithm selector */
 enum { DGMR_ALGO_AUTO = 0, DGMR_ALGO_SIMT = 1, DGMR_ALGO_UMMA = 2 };
 /* tensor-core operand precision: 1xTF32 (what cuDNN does by default for the reference) or
@@ -85,15 +89,16 @@ int dgmr_upsample(const float* x, float* y, int N, int D, int H, int W, int C, i
 /* ---- ConvGRU gate arithmetic (ref: dgmr/layers/ConvGRU.py:72-82); `ld` = row pitch (floats) of the
  * pre-activation tensors so that r|u can live side by side in one [rows, 2*Ch] conv output. */
 int dgmr_gru_gate_fwd(const float* pre_r, int ld, const float* h, float* rh, int64_t rows, int Ch, dgmr_stream_t stream);
+/* relu_c != 0: `c` holds the candidate pre-activation and relu is applied here (ref: ConvGRU.py:81) */
 int dgmr_gru_blend_fwd(const float* pre_u, int ld, const float* h, const float* c, float* hnew,
-                       int64_t rows, int Ch, dgmr_stream_t stream);
+                       int64_t rows, int Ch, int relu_c, dgmr_stream_t stream);
 /* d_rh -> d_pre_r, dh (+= if accumulate) */
 int dgmr_gru_gate_bwd(const float* d_rh, const float* pre_r, int ld, const float* h, float* d_pre_r, int ldd,
                       float* dh, int accumulate, int64_t rows, int Ch, dgmr_stream_t stream);
 /* d_hnew -> d_pre_u, dc, dh (+= if accumulate) */
 int dgmr_gru_blend_bwd(const float* d_hnew, const float* pre_u, int ld, const float* h, const float* c,
                        float* d_pre_u, int ldd, float* dc, float* dh, int accumulate,
-                       int64_t rows, int Ch, dgmr_stream_t stream);
+                       int64_t rows, int Ch, int relu_c, dgmr_stream_t stream);
 
 /* ---- BatchNorm (ref: BatchNorm2d dgmr/common.py:38-39,108-109, generators.py:113; BatchNorm1d
  * discriminators.py:102,194).  x: [G*rows, C]; batch statistics per (group, channel). */

@@ -24,6 +24,7 @@ ACT_NONE, ACT_RELU = 0, 1
 ALGO_AUTO, ALGO_SIMT, ALGO_UMMA = 0, 1, 2
 PREC_TF32, PREC_3XTF32 = 0, 1
 FLAG_ROUND_TF32 = 256
+FLAG_ACCUMULATE = 512
 
 _CTYPES = {
     "int": ctypes.c_int,
@@ -184,16 +185,16 @@ class CudaBackend:
     def gru_gate_fwd(self, pre_r, ld, h, rh, rows, Ch):
         self._call("dgmr_gru_gate_fwd", _f32(pre_r, "pre_r"), ld, _f32(h, "h"), _f32(rh, "rh"), rows, Ch)
 
-    def gru_blend_fwd(self, pre_u, ld, h, c, hnew, rows, Ch):
-        self._call("dgmr_gru_blend_fwd", _f32(pre_u, "pre_u"), ld, _f32(h, "h"), _f32(c, "c"), _f32(hnew, "hnew"), rows, Ch)
+    def gru_blend_fwd(self, pre_u, ld, h, c, hnew, rows, Ch, relu_c=False):
+        self._call("dgmr_gru_blend_fwd", _f32(pre_u, "pre_u"), ld, _f32(h, "h"), _f32(c, "c"), _f32(hnew, "hnew"), rows, Ch, int(relu_c))
 
     def gru_gate_bwd(self, d_rh, pre_r, ld, h, d_pre_r, ldd, dh, accumulate, rows, Ch):
         self._call("dgmr_gru_gate_bwd", _f32(d_rh, "d_rh"), _f32(pre_r, "pre_r"), ld, _f32(h, "h"), _f32(d_pre_r, "d_pre_r"), ldd,
                    _f32(dh, "dh"), int(accumulate), rows, Ch)
 
-    def gru_blend_bwd(self, d_hnew, pre_u, ld, h, c, d_pre_u, ldd, dc, dh, accumulate, rows, Ch):
+    def gru_blend_bwd(self, d_hnew, pre_u, ld, h, c, d_pre_u, ldd, dc, dh, accumulate, rows, Ch, relu_c=False):
         self._call("dgmr_gru_blend_bwd", _f32(d_hnew, "d_hnew"), _f32(pre_u, "pre_u"), ld, _f32(h, "h"), _f32(c, "c"),
-                   _f32(d_pre_u, "d_pre_u"), ldd, _f32(dc, "dc"), _f32(dh, "dh"), int(accumulate), rows, Ch)
+                   _f32(d_pre_u, "d_pre_u"), ldd, _f32(dc, "dc"), _f32(dh, "dh"), int(accumulate), rows, Ch, int(relu_c))
 
     # -- BatchNorm
     def bn_stats(self, x, sums, rows, G, C):
@@ -238,7 +239,7 @@ class CudaBackend:
         tag = None
         if self.profile is not None:
             umma = algo == ALGO_UMMA or (algo == ALGO_AUTO and self.conv_umma_supported(N, D, H, W, Cin, Cout, kd, kh, kw))
-            tag = "conv_umma" if umma else "conv_simt"
+            tag = ("conv_umma_splitk" if act & FLAG_ACCUMULATE else "conv_umma") if umma else "conv_simt"
         self._call("dgmr_conv_fwd", _f32(x, "x"), _f32(x_lo, "x_lo"), _f32(wp, "wp"), _f32(wp_lo, "wp_lo"), _f32(bias, "bias"),
                    _f32(scale, "scale"), _f32(res, "res"), _f32(y, "y"), N, D, H, W, Cin, Cout, kd, kh, kw, G, act, algo, precision,
                    _tag=tag, _flops=2.0 * N * D * H * W * Cin * Cout * kd * kh * kw,

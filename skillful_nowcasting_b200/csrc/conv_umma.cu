@@ -141,6 +141,7 @@ struct UmmaConvParams {
   int stages;
   int tmem_cols;
   int act;
+  int split_taps;        // 1: blockIdx.z = filter tap, epilogue red.adds acc*scale into y
   const float* bias; const float* scale; const float* res; float* y;
 };
 
@@ -172,7 +173,8 @@ conv_umma_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   const int co0 = blockIdx.y * p.BN;
   const int taps = p.kd * p.kh * p.kw;
   const int kchunks = p.Cin / p.BK;
-  const int num_kb = taps * kchunks;
+  const int tap_begin = p.split_taps ? (int)blockIdx.z : 0;
+  const int num_kb = (p.split_taps ? 1 : taps) * kchunks;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -195,7 +197,8 @@ conv_umma_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       // ===== TMA producer
       int s = 0; uint32_t ph = 0;
       for (int kb = 0; kb < num_kb; ++kb) {
-        const int tap = kb / kchunks, c0 = (kb - tap * kchunks) * p.BK;
+        const int tapl = kb / kchunks, c0 = (kb - tapl * kchunks) * p.BK;
+        const int tap = tap_begin + tapl;
         const int tkw = tap % p.kw, tkh = (tap / p.kw) % p.kh, tkd = tap / (p.kw * p.kh);
         mbar_wait(empty_bar(s), ph ^ 1u);
         mbar_expect_tx(full_bar(s), a_bytes + b_bytes);
@@ -258,6 +261,12 @@ conv_umma_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       }
       float* yp = p.y + m * p.Cout + co0 + c;
       const float* rp = p.res ? p.res + m * p.Cout + co0 + c : nullptr;
+      if (p.split_taps) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (co0 + c + j < p.Cout) atomicAdd(yp + j, v[j]);
+        continue;
+      }
       if (vec4) {
 #pragma unroll
         for (int j = 0; j < 16; j += 4) {
@@ -451,8 +460,9 @@ static bool umma_fwd_ok(int N, int D, int H, int W, int Cin, int Cout, int kd, i
 }
 
 int launch_conv_umma_fwd(const float* x, const float* wp, const float* bias, const float* scale, const float* res, float* y, int N, int D, int H, int W, int Cin,
-                         int Cout, int kd, int kh, int kw, int G, int act, cudaStream_t st) {
+                         int Cout, int kd, int kh, int kw, int G, int act, cudaStream_t st, int accumulate = 0) {
   UmmaConvParams p;
+  p.split_taps = accumulate;
   p.N = N; p.D = D; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.kd = kd; p.kh = kh; p.kw = kw; p.G = G;
   if (!pick_box(N, H, W, &p.bw, &p.bh, &p.bn)) { set_error("conv_umma_fwd: no 128-pixel box for N=%d H=%d W=%d", N, H, W); return 1; }
   p.tiles_w = W / p.bw; p.tiles_h = H / p.bh;
@@ -497,7 +507,7 @@ int launch_conv_umma_fwd(const float* x, const float* wp, const float* bias, con
     smem_set = 220 * 1024;
   }
   int64_t mtiles = (int64_t)(N / p.bn) * D * p.tiles_h * p.tiles_w;
-  dim3 grid((unsigned)mtiles, (unsigned)ntiles);
+  dim3 grid((unsigned)mtiles, (unsigned)ntiles, (unsigned)(accumulate ? taps : 1));
   conv_umma_fwd_kernel<<<grid, kUmmaThreads, smem, st>>>(tmA, tmB, p);
   DGMR_CHECK_LAUNCH("conv_umma_fwd");
   return 0;
@@ -610,9 +620,16 @@ int dgmr_conv_fwd(const float* x, const float* x_lo, const float* wp, const floa
   DGMR_REQUIRE(N > 0 && D > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, "dgmr_conv_fwd: bad dims");
   DGMR_REQUIRE((kd == 1 || kd == 3) && (kh == 1 || kh == 3) && (kw == 1 || kw == 3), "dgmr_conv_fwd: kernel extent must be 1 or 3");
   DGMR_REQUIRE(G >= 1 && N % G == 0, "dgmr_conv_fwd: N=%d not divisible by G=%d", N, G);
+  const int accumulate = (act & DGMR_FLAG_ACCUMULATE) ? 1 : 0;
+  act &= ~DGMR_FLAG_ACCUMULATE;
   DGMR_REQUIRE(act == DGMR_ACT_NONE || act == DGMR_ACT_RELU, "dgmr_conv_fwd: bad act");
   (void)x_lo; (void)wp_lo;
   bool ok = umma_fwd_ok(N, D, H, W, Cin, Cout, kd, kh, kw, G);
+  if (accumulate) {
+    DGMR_REQUIRE(bias == nullptr && res == nullptr && act == DGMR_ACT_NONE, "dgmr_conv_fwd: ACCUMULATE excludes bias/res/act");
+    DGMR_REQUIRE(ok && algo != DGMR_ALGO_SIMT, "dgmr_conv_fwd: ACCUMULATE is a tensor-core-path mode");
+    return launch_conv_umma_fwd(x, wp, nullptr, scale, nullptr, y, N, D, H, W, Cin, Cout, kd, kh, kw, G, DGMR_ACT_NONE, S(stream), 1);
+  }
   if (algo == DGMR_ALGO_UMMA) DGMR_REQUIRE(ok, "dgmr_conv_fwd: shape not supported by the tcgen05 path");
   DGMR_REQUIRE(precision == DGMR_PREC_TF32 || algo == DGMR_ALGO_SIMT || !ok, "dgmr_conv_fwd: 3xTF32 not implemented on the tcgen05 path yet");
   if (algo == DGMR_ALGO_UMMA || (algo == DGMR_ALGO_AUTO && ok))

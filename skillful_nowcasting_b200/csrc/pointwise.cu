@@ -184,12 +184,14 @@ __global__ void gru_gate_fwd_kernel(const float* __restrict__ pre_r, int ld, con
     rh[i] = g * h[i];
   }
 }
-__global__ void gru_blend_fwd_kernel(const float* __restrict__ pre_u, int ld, const float* __restrict__ h, const float* __restrict__ c_, float* __restrict__ hn, int64_t rows, int Ch) {
+__global__ void gru_blend_fwd_kernel(const float* __restrict__ pre_u, int ld, const float* __restrict__ h, const float* __restrict__ c_, float* __restrict__ hn, int64_t rows, int Ch, int relu_c) {
   int64_t total = rows * Ch;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     int64_t r = i / Ch; int c = i - r * Ch;
     float u = 1.0f / (1.0f + expf(-pre_u[r * ld + c]));
-    hn[i] = u * h[i] + (1.0f - u) * c_[i];
+    float cv = c_[i];
+    if (relu_c) cv = fmaxf(cv, 0.f);
+    hn[i] = u * h[i] + (1.0f - u) * cv;
   }
 }
 __global__ void gru_gate_bwd_kernel(const float* __restrict__ d_rh, const float* __restrict__ pre_r, int ld, const float* __restrict__ h,
@@ -205,14 +207,16 @@ __global__ void gru_gate_bwd_kernel(const float* __restrict__ d_rh, const float*
   }
 }
 __global__ void gru_blend_bwd_kernel(const float* __restrict__ d_hn, const float* __restrict__ pre_u, int ld, const float* __restrict__ h, const float* __restrict__ c_,
-                                     float* __restrict__ d_pre_u, int ldd, float* __restrict__ dc, float* __restrict__ dh, int acc, int64_t rows, int Ch) {
+                                     float* __restrict__ d_pre_u, int ldd, float* __restrict__ dc, float* __restrict__ dh, int acc, int64_t rows, int Ch, int relu_c) {
   int64_t total = rows * Ch;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     int64_t r = i / Ch; int c = i - r * Ch;
     float u = 1.0f / (1.0f + expf(-pre_u[r * ld + c]));
     float d = d_hn[i];
-    d_pre_u[r * ldd + c] = d * (h[i] - c_[i]) * u * (1.0f - u);
-    dc[i] = d * (1.0f - u);
+    float cp = c_[i];
+    float cv = relu_c ? fmaxf(cp, 0.f) : cp;
+    d_pre_u[r * ldd + c] = d * (h[i] - cv) * u * (1.0f - u);
+    dc[i] = (relu_c && !(cp > 0.f)) ? 0.f : d * (1.0f - u);
     float v = d * u;
     if (acc) dh[i] += v; else dh[i] = v;
   }
@@ -668,9 +672,9 @@ int dgmr_gru_gate_fwd(const float* pre_r, int ld, const float* h, float* rh, int
   DGMR_CHECK_LAUNCH("dgmr_gru_gate_fwd");
   return 0;
 }
-int dgmr_gru_blend_fwd(const float* pre_u, int ld, const float* h, const float* c, float* hnew, int64_t rows, int Ch, dgmr_stream_t stream) {
+int dgmr_gru_blend_fwd(const float* pre_u, int ld, const float* h, const float* c, float* hnew, int64_t rows, int Ch, int relu_c, dgmr_stream_t stream) {
   int64_t n = rows * Ch; if (n == 0) return 0;
-  gru_blend_fwd_kernel<<<ew_grid(n, 256, 2), 256, 0, S(stream)>>>(pre_u, ld, h, c, hnew, rows, Ch);
+  gru_blend_fwd_kernel<<<ew_grid(n, 256, 2), 256, 0, S(stream)>>>(pre_u, ld, h, c, hnew, rows, Ch, relu_c);
   DGMR_CHECK_LAUNCH("dgmr_gru_blend_fwd");
   return 0;
 }
@@ -680,9 +684,9 @@ int dgmr_gru_gate_bwd(const float* d_rh, const float* pre_r, int ld, const float
   DGMR_CHECK_LAUNCH("dgmr_gru_gate_bwd");
   return 0;
 }
-int dgmr_gru_blend_bwd(const float* d_hnew, const float* pre_u, int ld, const float* h, const float* c, float* d_pre_u, int ldd, float* dc, float* dh, int accumulate, int64_t rows, int Ch, dgmr_stream_t stream) {
+int dgmr_gru_blend_bwd(const float* d_hnew, const float* pre_u, int ld, const float* h, const float* c, float* d_pre_u, int ldd, float* dc, float* dh, int accumulate, int64_t rows, int Ch, int relu_c, dgmr_stream_t stream) {
   int64_t n = rows * Ch; if (n == 0) return 0;
-  gru_blend_bwd_kernel<<<ew_grid(n, 256, 2), 256, 0, S(stream)>>>(d_hnew, pre_u, ld, h, c, d_pre_u, ldd, dc, dh, accumulate, rows, Ch);
+  gru_blend_bwd_kernel<<<ew_grid(n, 256, 2), 256, 0, S(stream)>>>(d_hnew, pre_u, ld, h, c, d_pre_u, ldd, dc, dh, accumulate, rows, Ch, relu_c);
   DGMR_CHECK_LAUNCH("dgmr_gru_blend_bwd");
   return 0;
 }

@@ -62,8 +62,8 @@ class ConvGRUCell(nn.Module):
             pre_r = ops.conv(h, wr, None, srows[0][t], xparts[0][t], cx, ch, 1, ACT_NONE)
             pre_u = ops.conv(h, wu, None, srows[1][t], xparts[1][t], cx, ch, 1, ACT_NONE)
             rh = ops.gru_gate(pre_r, h)
-            c = ops.conv(rh, wc, None, srows[2][t], xparts[2][t], cx, ch, 1, ACT_RELU)
-            h = ops.gru_blend(pre_u, h, c)
+            c = ops.conv(rh, wc, None, srows[2][t], xparts[2][t], cx, ch, 1, ACT_NONE)  # candidate pre-activation
+            h = ops.gru_blend(pre_u, h, c, relu_c=True)                                  # ReLU fused into the blend
             outs.append(h)
         return torch.cat(outs, dim=0)
 

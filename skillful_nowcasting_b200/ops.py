@@ -12,7 +12,7 @@ import torch
 from torch.autograd import Function
 
 from . import _lib
-from ._lib import ACT_NONE, ACT_RELU, ALGO_AUTO, ALGO_SIMT, ALGO_UMMA, FLAG_ROUND_TF32, PREC_TF32
+from ._lib import ACT_NONE, ACT_RELU, ALGO_AUTO, ALGO_SIMT, ALGO_UMMA, FLAG_ACCUMULATE, FLAG_ROUND_TF32, PREC_TF32
 
 
 class config:
@@ -23,6 +23,8 @@ class config:
     # operands of tensor-core convs are rounded to the NEAREST tf32 value first (the MMA itself truncates, which is
     # biased): weights while packing, activations in place (idempotent), dz in the backward prologue
     round_tf32 = True
+    # small-M / large-K convs (the ConvGRU steps) run split over the filter taps with fp32 red.add into the output
+    split_taps = True
 
 
 def _be():
@@ -355,6 +357,14 @@ def _tc_wgrad(n, d, h, w, cin, cout, kd, kh, kw) -> bool:
     return (config.round_tf32 and config.wgrad_algo != ALGO_SIMT and _be().wgrad_umma_supported(n, d, h, w, cin, cout, kd, kh, kw))
 
 
+def _use_split_taps(n, d, h, w, cin, cout, taps, has_bias, act) -> bool:
+    """Tap-split accumulate mode pays when the plain tiling leaves most SMs idle: few 128-pixel x 256-channel tiles, many taps."""
+    if not config.split_taps or taps == 1 or has_bias or act != ACT_NONE or config.conv_algo == ALGO_SIMT:
+        return False
+    tiles = ((n * d * h * w + 127) // 128) * ((cout + 255) // 256)
+    return tiles <= 64 and cin >= 32 and _be().conv_umma_supported(n, d, h, w, cin, cout, 1, 3, 3)
+
+
 def packed_weight(w: torch.Tensor, ci0: int, cin: int, mode: int) -> torch.Tensor:
     """[tap][Cout][Cin] (mode 0) / flipped-transposed dgrad pack (mode 1) of the OIHW weight slice
     [:, ci0:ci0+cin]; cached until the parameter's version counter moves.  mode | FLAG_ROUND_TF32: tf32-rounded."""
@@ -413,8 +423,16 @@ class _Conv(Function):
         wp = packed_weight(w, ci0, cin, rnd) if c == cin else packed_weight_padded(w, ci0, cin, c, rnd)
         y = _new((n, d, h, wd, cout), x)
         res_c, scale_c, bias_c = _c(res), _c(scale), _c(bias)
-        _be().conv_fwd(x, wp, bias_c, scale_c, res_c, y, n, d, h, wd, c, cout, kd, kh, kw, G, act,
-                       config.conv_algo, config.precision)
+        if _use_split_taps(n, d, h, wd, c, cout, kd * kh * kw, bias is not None, act) and _be().conv_umma_supported(n, d, h, wd, c, cout, kd, kh, kw):
+            if res_c is not None:
+                _be().axpby(1.0, res_c, 0.0, None, y)   # y starts as the residual, the taps accumulate on top
+            else:
+                _be().fill(y, 0.0)
+            _be().conv_fwd(x, wp, None, scale_c, None, y, n, d, h, wd, c, cout, kd, kh, kw, G, ACT_NONE | FLAG_ACCUMULATE,
+                           config.conv_algo, config.precision)
+        else:
+            _be().conv_fwd(x, wp, bias_c, scale_c, res_c, y, n, d, h, wd, c, cout, kd, kh, kw, G, act,
+                           config.conv_algo, config.precision)
         need_s = scale is not None and scale.requires_grad
         need_y = act == ACT_RELU or need_s
         ctx.save_for_backward(x, w, bias_c, scale_c, res_c if need_s else None, y if need_y else None)
@@ -466,8 +484,13 @@ class _Conv(Function):
             rnd = FLAG_ROUND_TF32 if _tc_fwd(n, d, h, wd, cout, cp, kd, kh, kw) else 0
             wpt = packed_weight(w, ci0, cin, 1 | rnd) if cp == cin else packed_weight_padded(w, ci0, cin, cp, 1 | rnd)
             dx = _new(x.shape, x)
-            be.conv_fwd(dz, wpt, None, None, None, dx, n, d, h, wd, cout, cp, kd, kh, kw, 1, ACT_NONE,
-                        config.conv_algo, config.precision)
+            if _use_split_taps(n, d, h, wd, cout, cp, kd * kh * kw, False, ACT_NONE) and be.conv_umma_supported(n, d, h, wd, cout, cp, kd, kh, kw):
+                be.fill(dx, 0.0)
+                be.conv_fwd(dz, wpt, None, None, None, dx, n, d, h, wd, cout, cp, kd, kh, kw, 1, ACT_NONE | FLAG_ACCUMULATE,
+                            config.conv_algo, config.precision)
+            else:
+                be.conv_fwd(dz, wpt, None, None, None, dx, n, d, h, wd, cout, cp, kd, kh, kw, 1, ACT_NONE,
+                            config.conv_algo, config.precision)
         if need_w:
             taps = kd * kh * kw
             dwp = _new((taps * cout * cp,), x)
@@ -563,13 +586,14 @@ class _GruBlend(Function):
     """h' = u*h + (1-u)*c, u = sigmoid(pre_u)   (ref: dgmr/layers/ConvGRU.py:75,82)."""
 
     @staticmethod
-    def forward(ctx, pre_u, h, c):
+    def forward(ctx, pre_u, h, c, relu_c):
         pre_u, h, c = _c(pre_u), _c(h), _c(c)
         ch = h.shape[-1]
         rows = h.numel() // ch
         hn = torch.empty_like(h)
-        _be().gru_blend_fwd(pre_u, ch, h, c, hn, rows, ch)
+        _be().gru_blend_fwd(pre_u, ch, h, c, hn, rows, ch, relu_c)
         ctx.save_for_backward(pre_u, h, c)
+        ctx.relu_c = relu_c
         return hn
 
     @staticmethod
@@ -579,16 +603,17 @@ class _GruBlend(Function):
         ch = h.shape[-1]
         rows = h.numel() // ch
         dpre, dh, dc = torch.empty_like(pre_u), torch.empty_like(h), torch.empty_like(c)
-        _be().gru_blend_bwd(g, pre_u, ch, h, c, dpre, ch, dc, dh, False, rows, ch)
-        return dpre, dh, dc
+        _be().gru_blend_bwd(g, pre_u, ch, h, c, dpre, ch, dc, dh, False, rows, ch, ctx.relu_c)
+        return dpre, dh, dc, None
 
 
 def gru_gate(pre_r, h):
     return _GruGate.apply(pre_r, h)
 
 
-def gru_blend(pre_u, h, c):
-    return _GruBlend.apply(pre_u, h, c)
+def gru_blend(pre_u, h, c, relu_c=False):
+    """relu_c: `c` is the candidate PRE-activation and the ReLU of ConvGRU.py:81 is applied inside the blend kernel."""
+    return _GruBlend.apply(pre_u, h, c, relu_c)
 
 
 # ----------------------------------------------------------------------------- discriminator head

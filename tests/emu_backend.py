@@ -92,9 +92,10 @@ class EmuBackend:
         g = torch.sigmoid(pre_r.reshape(rows, ld)[:, :Ch])
         rh.copy_((g * h.reshape(rows, Ch)).reshape(rh.shape))
 
-    def gru_blend_fwd(self, pre_u, ld, h, c, hnew, rows, Ch):
+    def gru_blend_fwd(self, pre_u, ld, h, c, hnew, rows, Ch, relu_c=False):
         u = torch.sigmoid(pre_u.reshape(rows, ld)[:, :Ch])
-        hnew.copy_((u * h.reshape(rows, Ch) + (1 - u) * c.reshape(rows, Ch)).reshape(hnew.shape))
+        cv = torch.relu(c.reshape(rows, Ch)) if relu_c else c.reshape(rows, Ch)
+        hnew.copy_((u * h.reshape(rows, Ch) + (1 - u) * cv).reshape(hnew.shape))
 
     def gru_gate_bwd(self, d_rh, pre_r, ld, h, d_pre_r, ldd, dh, accumulate, rows, Ch):
         g = torch.sigmoid(pre_r.reshape(rows, ld)[:, :Ch])
@@ -103,11 +104,16 @@ class EmuBackend:
         v = (d * g).reshape(dh.shape)
         dh.add_(v) if accumulate else dh.copy_(v)
 
-    def gru_blend_bwd(self, d_hnew, pre_u, ld, h, c, d_pre_u, ldd, dc, dh, accumulate, rows, Ch):
+    def gru_blend_bwd(self, d_hnew, pre_u, ld, h, c, d_pre_u, ldd, dc, dh, accumulate, rows, Ch, relu_c=False):
         u = torch.sigmoid(pre_u.reshape(rows, ld)[:, :Ch])
         d = d_hnew.reshape(rows, Ch)
-        d_pre_u.reshape(rows, ldd)[:, :Ch] = d * (h.reshape(rows, Ch) - c.reshape(rows, Ch)) * u * (1 - u)
-        dc.copy_((d * (1 - u)).reshape(dc.shape))
+        cp = c.reshape(rows, Ch)
+        cv = torch.relu(cp) if relu_c else cp
+        d_pre_u.reshape(rows, ldd)[:, :Ch] = d * (h.reshape(rows, Ch) - cv) * u * (1 - u)
+        g = d * (1 - u)
+        if relu_c:
+            g = g * (cp > 0)
+        dc.copy_(g.reshape(dc.shape))
         v = (d * u).reshape(dh.shape)
         dh.add_(v) if accumulate else dh.copy_(v)
 
@@ -223,6 +229,9 @@ class EmuBackend:
         z = self._conv_raw(x, wp, N, D, H, W, Cin, Cout, kd, kh, kw)
         if scale is not None:
             z = (z.reshape(G, -1, Cout) * scale.reshape(G, 1, Cout)).reshape(N, D, H, W, Cout)
+        if act & 512:  # DGMR_FLAG_ACCUMULATE
+            y.add_(z.reshape(y.shape))
+            return
         if bias is not None:
             z = z + bias
         if res is not None:

@@ -70,10 +70,11 @@ def test_gru_pointwise(cuda_backend):
     rows, ch = 300, 24
     pre, h, c, g = (torch.randn(rows, ch) for _ in range(4))
     _both("gru_gate_fwd", [pre, ch, h, torch.empty(rows, ch), rows, ch], cuda_backend, atol=1e-6)
-    _both("gru_blend_fwd", [pre, ch, h, c, torch.empty(rows, ch), rows, ch], cuda_backend, atol=1e-6)
+    for relu_c in (False, True):
+        _both("gru_blend_fwd", [pre, ch, h, c, torch.empty(rows, ch), rows, ch, relu_c], cuda_backend, atol=1e-6)
+        _both("gru_blend_bwd", [g, pre, ch, h, c, torch.empty(rows, ch), ch, torch.empty(rows, ch), torch.empty(rows, ch), False, rows, ch, relu_c],
+              cuda_backend, atol=1e-6)
     _both("gru_gate_bwd", [g, pre, ch, h, torch.empty(rows, ch), ch, torch.empty(rows, ch), False, rows, ch], cuda_backend, atol=1e-6)
-    _both("gru_blend_bwd", [g, pre, ch, h, c, torch.empty(rows, ch), ch, torch.empty(rows, ch), torch.empty(rows, ch), False, rows, ch],
-          cuda_backend, atol=1e-6)
 
 
 @pytest.mark.parametrize("G,rows,C,relu,up2", [(1, 500, 24, True, False), (3, 2 * 8 * 8, 96, True, True), (4, 6, 768, False, False), (2, 4 * 4, 4, True, True)])

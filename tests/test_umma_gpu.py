@@ -99,3 +99,21 @@ def test_wgrad_umma(cuda_backend, shape):
     assert e_simt <= 1e-4 * ref_max, f"SIMT err {e_simt:.3e}"
     assert not torch.isnan(g_umma).any()
     assert e_umma <= 4e-3 * ref_max, f"tcgen05 wgrad err {e_umma:.3e} (ref max {ref_max:.3e})"
+
+
+@pytest.mark.parametrize("shape", [(4, 1, 8, 8, 384, 384, 1, 3, 3, 1), (2, 1, 16, 16, 192, 192, 1, 3, 3, 2), (2, 3, 8, 8, 64, 96, 3, 3, 3, 1)])
+def test_conv_umma_accumulate_mode(cuda_backend, shape):
+    """DGMR_FLAG_ACCUMULATE: y += conv(x)*scale with the K loop split over filter taps across CTAs (ConvGRU step convs)."""
+    n, d, h, w, cin, cout, kd, kh, kw, g = shape
+    torch.manual_seed(13)
+    taps = kd * kh * kw
+    x = torch.randn(n, d, h, w, cin)
+    wp = torch.randn(taps * cout * cin) / (taps * cin) ** 0.5
+    scale = torch.rand(g, cout) + 0.5
+    y0 = torch.randn(n, d, h, w, cout)
+    y_ref = y0.clone()
+    EmuBackend().conv_fwd(x, wp, None, scale, None, y_ref, n, d, h, w, cin, cout, kd, kh, kw, g, 512)
+    y = y0.cuda()
+    cuda_backend.conv_fwd(x.cuda(), wp.cuda(), None, scale.cuda(), None, y, n, d, h, w, cin, cout, kd, kh, kw, g, 512)
+    torch.cuda.synchronize()
+    assert (y.cpu() - y_ref).abs().max().item() <= 4e-3 * y_ref.abs().max().item()
