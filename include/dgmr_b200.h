@@ -196,9 +196,9 @@ int dgmr_grid_cell_bwd(const float* gen, const float* target, float cap, float c
 int dgmr_adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
               float eps, int step, float grad_scale, dgmr_stream_t stream);
 
-/* in place: x <- nearest TF32-representable value (cvt.rna.tf32.f32); applied to activations before they enter a
- * tensor-core convolution (idempotent) */
-int dgmr_round_tf32(float* x, int64_t n, dgmr_stream_t stream);
+/* y <- nearest TF32-representable value of x (cvt.rna.tf32.f32; y may alias x; idempotent); applied to activations before
+ * they enter a tensor-core convolution: in place when the tensor feeds convolutions only, into a copy otherwise */
+int dgmr_round_tf32(const float* x, float* y, int64_t n, dgmr_stream_t stream);
 
 /* ---- 3xTF32 support: hi = x & ~0x1fff, lo = x - hi */
 int dgmr_split_tf32(const float* x, float* hi, float* lo, int64_t n, dgmr_stream_t stream);

@@ -169,8 +169,8 @@ class CudaBackend:
     def relu_bwd(self, dy, x, dx):
         self._call("dgmr_relu_bwd", _f32(dy, "dy"), _f32(x, "x"), _f32(dx, "dx"), x.numel())
 
-    def round_tf32(self, x):
-        self._call("dgmr_round_tf32", _f32(x, "x"), x.numel())
+    def round_tf32(self, x, y=None):
+        self._call("dgmr_round_tf32", _f32(x, "x"), _f32(x if y is None else y, "y"), x.numel())
 
     def split_tf32(self, x, hi, lo):
         self._call("dgmr_split_tf32", _f32(x, "x"), _f32(hi, "hi"), _f32(lo, "lo"), x.numel())

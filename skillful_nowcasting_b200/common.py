@@ -47,9 +47,9 @@ class GBlock(nn.Module):
 
     def run(self, x, G: int = 1):
         sc = x if x.shape[-1] == self.output_channels else self.conv_1x1.run(x, G)
-        y = self.bn1.run(x, G, relu=True)
+        y = ops.mark_conv_only(self.bn1.run(x, G, relu=True))
         y = self.first_conv_3x3.run(y, G)
-        y = self.bn2.run(y, G, relu=True)
+        y = ops.mark_conv_only(self.bn2.run(y, G, relu=True))
         return self.last_conv_3x3.run(y, G, res=sc)  # residual add fused in the conv epilogue
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
@@ -72,10 +72,10 @@ class UpsampleGBlock(nn.Module):
 
     def run(self, x, G: int = 1):
         # conv1x1(up2(x)) == up2(conv1x1(x)) bit-for-bit (pointwise conv commutes with replication): 4x fewer MACs
-        sc = ops.upsample2(self.conv_1x1.run(x, G))
-        y = self.bn1.run(x, G, relu=True, up2=True)  # BN -> ReLU -> nearest x2 in one pass
+        sc = ops.upsample2(self.conv_1x1.run(x, G))  # x also feeds BatchNorm: the conv rounds a private copy
+        y = ops.mark_conv_only(self.bn1.run(x, G, relu=True, up2=True))  # BN -> ReLU -> nearest x2 in one pass
         y = self.first_conv_3x3.run(y, G)
-        y = self.bn2.run(y, G, relu=True)
+        y = ops.mark_conv_only(self.bn2.run(y, G, relu=True))
         return self.last_conv_3x3.run(y, G, res=sc)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
@@ -99,13 +99,15 @@ class DBlock(nn.Module):
 
     def run(self, x, G: int = 1):
         if self.input_channels != self.output_channels:
+            # x is read by convolutions and by ReLU only (ReLU commutes with tf32 rounding): rounding in place is exact
+            ops.mark_conv_only(x)
             x1 = self.conv_1x1.run(x, G)
             if not self.keep_same_output:
                 x1 = self._pool(x1)
         else:
             x1 = x
-        y = ops.relu(x) if self.first_relu else x
-        y = self.first_conv_3x3.run(y, G, act=ACT_RELU)  # the ReLU between the convs is fused
+        y = ops.mark_conv_only(ops.relu(x)) if self.first_relu else x
+        y = ops.mark_conv_only(self.first_conv_3x3.run(y, G, act=ACT_RELU))  # the ReLU between the convs is fused
         if self.keep_same_output:
             return self.last_conv_3x3.run(y, G, res=x1)
         y = self._pool(self.last_conv_3x3.run(y, G))
@@ -130,7 +132,7 @@ class LBlock(nn.Module):
             sc = ops.concat_channels(x, self.conv_1x1.run(x))
         else:
             sc = x
-        y = self.first_conv_3x3.run(ops.relu(x), act=ACT_RELU)
+        y = ops.mark_conv_only(self.first_conv_3x3.run(ops.mark_conv_only(ops.relu(x)), act=ACT_RELU))
         return self.last_conv_3x3.run(y, res=sc)
 
     def forward(self, x) -> torch.Tensor:
@@ -174,7 +176,7 @@ class ContextConditioningStack(nn.Module, PyTorchModelHubMixin):
             # "b t c h w -> b (c t) h w" (:423): mixed[b, h, w, c*T + t] = s[t, b, h, w, c]
             mixed = ops.permute(s, (b, 1, hh, ww, cc * t), (t, b, hh * ww, cc),
                                 (b * hh * ww * cc, hh * ww * cc, cc, 1), (1, hh * ww * cc * t, cc * t, t))
-            outs.append(mix.run(mixed, 1, act=ACT_RELU))
+            outs.append(mix.run(ops.mark_conv_only(mixed), 1, act=ACT_RELU))
         return tuple(outs)
 
     def forward(self, x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:

@@ -211,15 +211,15 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, float* __restric
     packed[i] = rnd ? rna_tf32(v) : v;
   }
 }
-__global__ void round_tf32_kernel(float4* __restrict__ x, int64_t n4) {
+__global__ void round_tf32_kernel(const float4* x, float4* y, int64_t n4) {   // y may alias x
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     float4 v = x[i];
-    x[i] = make_float4(rna_tf32(v.x), rna_tf32(v.y), rna_tf32(v.z), rna_tf32(v.w));
+    y[i] = make_float4(rna_tf32(v.x), rna_tf32(v.y), rna_tf32(v.z), rna_tf32(v.w));
   }
 }
-__global__ void round_tf32_tail_kernel(float* __restrict__ x, int64_t start, int64_t n) {
+__global__ void round_tf32_tail_kernel(const float* x, float* y, int64_t start, int64_t n) {
   int64_t i = start + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (i < n) x[i] = rna_tf32(x[i]);
+  if (i < n) y[i] = rna_tf32(x[i]);
 }
 __global__ void unpack_wgrad_kernel(const float* __restrict__ packed, float* __restrict__ gw, int Cout, int CinTot, int ci0, int Cin, int taps, int acc) {
   int64_t total = (int64_t)taps * Cout * Cin;
@@ -509,12 +509,15 @@ int dgmr_pack_weight(const float* w, float* packed, int Cout, int CinTot, int ci
   DGMR_CHECK_LAUNCH("dgmr_pack_weight");
   return 0;
 }
-int dgmr_round_tf32(float* x, int64_t n, dgmr_stream_t stream) {
+int dgmr_round_tf32(const float* x, float* y, int64_t n, dgmr_stream_t stream) {
   if (n == 0) return 0;
-  DGMR_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15u) == 0, "dgmr_round_tf32: pointer must be 16-byte aligned");
+  DGMR_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15u) == 0, "dgmr_round_tf32: pointers must be 16-byte aligned");
   int64_t n4 = n / 4;
-  if (n4) { round_tf32_kernel<<<ew_grid(n4, 256, 2), 256, 0, S(stream)>>>(reinterpret_cast<float4*>(x), n4); DGMR_CHECK_LAUNCH("dgmr_round_tf32"); }
-  if (n % 4) { round_tf32_tail_kernel<<<1, 4, 0, S(stream)>>>(x, n4 * 4, n); DGMR_CHECK_LAUNCH("dgmr_round_tf32_tail"); }
+  if (n4) {
+    round_tf32_kernel<<<ew_grid(n4, 256, 2), 256, 0, S(stream)>>>(reinterpret_cast<const float4*>(x), reinterpret_cast<float4*>(y), n4);
+    DGMR_CHECK_LAUNCH("dgmr_round_tf32");
+  }
+  if (n % 4) { round_tf32_tail_kernel<<<1, 4, 0, S(stream)>>>(x, y, n4 * 4, n); DGMR_CHECK_LAUNCH("dgmr_round_tf32_tail"); }
   return 0;
 }
 int dgmr_unpack_wgrad(const float* packed, float* gw, int Cout, int CinTot, int ci0, int Cin, int taps, int accumulate, dgmr_stream_t stream) {

@@ -60,11 +60,12 @@ class Sampler(nn.Module, PyTorchModelHubMixin):
         hs = latent
         for lvl, (gru, c11, g, ug) in enumerate(levels):
             # level 0: identical latent input at every step and for every sample (generators.py:146-149)
-            hs = gru.cell.run_sequence(hs, init_states[3 - lvl], T, shared_input=(lvl == 0))
-            hs = c11.run(hs, T)
+            # each of these tensors is read by convolutions only -> their tf32 rounding may happen in place
+            hs = gru.cell.run_sequence(ops.mark_conv_only(hs), init_states[3 - lvl], T, shared_input=(lvl == 0))
+            hs = c11.run(ops.mark_conv_only(hs), T)
             hs = g.run(hs, T)
             hs = ug.run(hs, T)
-        hs = self.bn.run(hs, T, relu=True)
+        hs = ops.mark_conv_only(self.bn.run(hs, T, relu=True))
         hs = self.conv_1x1.run(hs, T)  # [T*B,1,h,w,4*Co]
         _, _, h, w, c4 = hs.shape
         co = c4 // 4

@@ -46,7 +46,7 @@ class ConvGRUCell(nn.Module):
         for g, sc in zip(gates, scales):
             if shared_input:
                 p = xs.numel()
-                x_rep = ops.repeat_mid(xs.reshape(1, p), T).reshape((T,) + tuple(xs.shape[1:]))
+                x_rep = ops.mark_conv_only(ops.repeat_mid(xs.reshape(1, p), T).reshape((T,) + tuple(xs.shape[1:])))
                 xp = ops.conv(x_rep, g.weight_orig, g.bias, sc, None, 0, cx, T, ACT_NONE)  # [T,1,H,W,Ch]
                 q = xp.numel() // T
                 xp = ops.repeat_mid(xp.reshape(T, q), B).reshape((T, B) + tuple(xp.shape[1:]))
@@ -59,9 +59,10 @@ class ConvGRUCell(nn.Module):
         outs = []
         wr, wu, wc = (g.weight_orig for g in gates)
         for t in range(T):
-            pre_r = ops.conv(h, wr, None, srows[0][t], xparts[0][t], cx, ch, 1, ACT_NONE)
-            pre_u = ops.conv(h, wu, None, srows[1][t], xparts[1][t], cx, ch, 1, ACT_NONE)
-            rh = ops.gru_gate(pre_r, h)
+            hop = ops.conv_operand(h)  # h also feeds the gate arithmetic: both gate convs share one tf32-rounded copy
+            pre_r = ops.conv(hop, wr, None, srows[0][t], xparts[0][t], cx, ch, 1, ACT_NONE)
+            pre_u = ops.conv(hop, wu, None, srows[1][t], xparts[1][t], cx, ch, 1, ACT_NONE)
+            rh = ops.mark_conv_only(ops.gru_gate(pre_r, h))
             c = ops.conv(rh, wc, None, srows[2][t], xparts[2][t], cx, ch, 1, ACT_NONE)  # candidate pre-activation
             h = ops.gru_blend(pre_u, h, c, relu_c=True)                                  # ReLU fused into the blend
             outs.append(h)

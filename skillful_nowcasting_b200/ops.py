@@ -23,6 +23,9 @@ class config:
     # operands of tensor-core convs are rounded to the NEAREST tf32 value first (the MMA itself truncates, which is
     # biased): weights while packing, activations in place (idempotent), dz in the backward prologue
     round_tf32 = True
+    _dbg_round_act = True   # debug knobs (finer control of what round_tf32 applies to)
+    _dbg_round_w = True
+    _dbg_round_dz = True
     # small-M / large-K convs (the ConvGRU steps) run split over the filter taps with fp32 red.add into the output
     split_taps = True
 
@@ -340,12 +343,44 @@ def spectral_inv_sigma(w, u, v, G, eps, training):
 _pack_cache = {}
 
 
+def mark_conv_only(t: torch.Tensor) -> torch.Tensor:
+    """Declare that `t` is consumed by convolutions only (or through sign-preserving ops such as ReLU), so its tf32
+    rounding may happen in place.  Anything else that reads a tensor (BatchNorm statistics, gate arithmetic, residuals)
+    must see the unrounded fp32 values, like in the reference, so unmarked conv inputs are rounded into a private copy."""
+    t._dgmr_conv_only = True
+    return t
+
+
 def _round_(t: torch.Tensor) -> torch.Tensor:
-    """Round a conv operand to tf32 in place, once (the flag rides on the Python tensor object)."""
-    if not getattr(t, "_dgmr_tf32", False):
+    """The tf32-rounded version of a conv operand: `t` itself if already rounded, rounded in place if it is conv-only
+    (flag rides on the Python tensor object), else a rounded copy."""
+    if getattr(t, "_dgmr_tf32", False):
+        return t
+    if getattr(t, "_dgmr_conv_only", False):
         _be().round_tf32(t)
         t._dgmr_tf32 = True
-    return t
+        return t
+    r = torch.empty_like(t)
+    _be().round_tf32(t, r)
+    r._dgmr_tf32 = True
+    return r
+
+
+class _ConvOperand(Function):
+    """Identity in autograd; forward hands out the tf32-rounded copy that several convs of the same input can share
+    (e.g. the read- and update-gate convs of one ConvGRU step both consume h)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return _round_(_c(x).detach()) if config.round_tf32 and config.conv_algo != ALGO_SIMT and _be().name == "cuda" else x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
+def conv_operand(x):
+    return _ConvOperand.apply(x)
 
 
 def _tc_fwd(n, d, h, w, cin, cout, kd, kh, kw) -> bool:
@@ -362,7 +397,7 @@ def _use_split_taps(n, d, h, w, cin, cout, taps, has_bias, act) -> bool:
     if not config.split_taps or taps == 1 or has_bias or act != ACT_NONE or config.conv_algo == ALGO_SIMT:
         return False
     tiles = ((n * d * h * w + 127) // 128) * ((cout + 255) // 256)
-    return tiles <= 64 and cin >= 32 and _be().conv_umma_supported(n, d, h, w, cin, cout, 1, 3, 3)
+    return tiles <= 16 and cin >= 32 and _be().conv_umma_supported(n, d, h, w, cin, cout, 1, 3, 3)
 
 
 def packed_weight(w: torch.Tensor, ci0: int, cin: int, mode: int) -> torch.Tensor:
@@ -418,8 +453,10 @@ class _Conv(Function):
         ks = tuple(w.shape[2:])
         kd, kh, kw = (1,) * (3 - len(ks)) + ks
         rnd = FLAG_ROUND_TF32 if _tc_fwd(n, d, h, wd, c, cout, kd, kh, kw) else 0
-        if rnd:
-            _round_(x)
+        if rnd and config._dbg_round_act:
+            x = _round_(x)
+        if not config._dbg_round_w:
+            rnd = 0
         wp = packed_weight(w, ci0, cin, rnd) if c == cin else packed_weight_padded(w, ci0, cin, c, rnd)
         y = _new((n, d, h, wd, cout), x)
         res_c, scale_c, bias_c = _c(res), _c(scale), _c(bias)
@@ -461,7 +498,7 @@ class _Conv(Function):
             dscale = _new((G, cout), dy) if need_s else None
             tc_bwd = (need_x and _tc_fwd(n, d, h, wd, cout, cp, kd, kh, kw)) or (need_w and _tc_wgrad(n, d, h, wd, cp, cout, kd, kh, kw))
             be.conv_bwd_prep(dy, y, res if need_s else None, bias, scale, dz, dpre, dbias, dscale, rows, G, cout,
-                             act | (FLAG_ROUND_TF32 if (tc_bwd and dz is not None) else 0))
+                             act | (FLAG_ROUND_TF32 if (tc_bwd and dz is not None and config._dbg_round_dz) else 0))
             if need_s and exact_dscale:
                 # the <dY, Y-b-res>/scale identity divides by the scale, which may be exactly 0 (attention gamma starts at 0,
                 # ref: dgmr/layers/Attention.py:69): recompute the raw conv output and reduce <dpre, z> directly
@@ -479,9 +516,11 @@ class _Conv(Function):
                 dpre = dy
         dx = dw = None
         if (need_x and _tc_fwd(n, d, h, wd, cout, cp, kd, kh, kw)) or (need_w and _tc_wgrad(n, d, h, wd, cp, cout, kd, kh, kw)):
-            _round_(dz)   # no-op for a dz the prologue already rounded
+            if config._dbg_round_dz and not getattr(dz, "_dgmr_tf32", False):
+                # dz == dy straight from autograd (no prologue ran): it may be shared with other backward nodes -> private copy
+                dz = _round_(dz)
         if need_x:
-            rnd = FLAG_ROUND_TF32 if _tc_fwd(n, d, h, wd, cout, cp, kd, kh, kw) else 0
+            rnd = FLAG_ROUND_TF32 if (_tc_fwd(n, d, h, wd, cout, cp, kd, kh, kw) and config._dbg_round_w) else 0
             wpt = packed_weight(w, ci0, cin, 1 | rnd) if cp == cin else packed_weight_padded(w, ci0, cin, cp, 1 | rnd)
             dx = _new(x.shape, x)
             if _use_split_taps(n, d, h, wd, cout, cp, kd * kh * kw, False, ACT_NONE) and be.conv_umma_supported(n, d, h, wd, cout, cp, kd, kh, kw):

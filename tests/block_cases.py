@@ -26,7 +26,7 @@ def block_cases(wide: bool):
     ]
 
 
-def run_block_case(case, training, device, tol_fwd, tol_grad, tol_buf=None):
+def run_block_case(case, training, device, tol_fwd, tol_grad, tol_buf=None, tol_l2=None):
     _, make, ofn, shape = case
     torch.manual_seed(5)
     mod = make()
@@ -45,13 +45,13 @@ def run_block_case(case, training, device, tol_fwd, tol_grad, tol_buf=None):
     rg = torch.autograd.grad((ref * w).sum(), [xo] + [st[k] for k in names], allow_unused=True)
     params = dict(mod.named_parameters())
     mg = torch.autograd.grad((got * w.to(device)).sum(), [xm] + [params[k[2:]] for k in names], allow_unused=True)
-    assert_grads_close(["x"] + names, [None if g is None else g.cpu() for g in mg], rg, tol_grad)
+    assert_grads_close(["x"] + names, [None if g is None else g.cpu() for g in mg], rg, tol_grad, tol_l2=tol_l2)
     for k, v in mod.state_dict().items():
         if v.numel():
             assert rel_err(v, st["m." + k]) < (tol_buf or tol_fwd), k
 
 
-def run_conv_gru_case(device, tol_fwd, tol_grad, cx=24, ch=8, s=8, T=4):
+def run_conv_gru_case(device, tol_fwd, tol_grad, cx=24, ch=8, s=8, T=4, tol_l2=None):
     from skillful_nowcasting_b200.layers import ConvGRU
 
     torch.manual_seed(6)
@@ -70,7 +70,7 @@ def run_conv_gru_case(device, tol_fwd, tol_grad, cx=24, ch=8, s=8, T=4):
     rg = torch.autograd.grad((ref * w).sum(), xs + [st[k] for k in names])
     params = dict(gru.named_parameters())
     mg = torch.autograd.grad((got * w.to(device)).sum(), xs2 + [params[k[2:]] for k in names])
-    assert_grads_close([f"x{i}" for i in range(T)] + names, [g.cpu() for g in mg], rg, tol_grad)
+    assert_grads_close([f"x{i}" for i in range(T)] + names, [g.cpu() for g in mg], rg, tol_grad, tol_l2=tol_l2)
     for k, v in gru.state_dict().items():
         assert rel_err(v, st["g." + k]) < max(tol_fwd, 2e-4) or not (k.endswith("_u") or k.endswith("_v")), k
     return gru, xs2, h

@@ -68,8 +68,8 @@ class EmuBackend:
         r = torch.where(r >= 2 ** 31, r - 2 ** 32, r).to(torch.int32)
         return r.view(torch.float32)
 
-    def round_tf32(self, x):
-        x.copy_(self._rna_tf32(x))
+    def round_tf32(self, x, y=None):
+        (x if y is None else y).copy_(self._rna_tf32(x))
 
     def split_tf32(self, x, hi, lo):
         h = (x.view(torch.int32) & -8192).view(torch.float32)

@@ -127,7 +127,7 @@ def compare_grads(got, ref, tol_norm, tol_head, zero_floor):
     return worst[:3]
 
 
-def assert_grads_close(names, got, ref, tol, floor=1e-5):
+def assert_grads_close(names, got, ref, tol, floor=1e-5, tol_l2=None):
     """Element-wise gradient comparison for block tests.  Gradients that are mathematically zero (a conv bias in front
     of a training-mode BatchNorm) show up as rounding noise on both sides: they are only required to stay tiny."""
     pairs = [(n, a, b) for n, a, b in zip(names, got, ref)]
@@ -142,6 +142,9 @@ def assert_grads_close(names, got, ref, tol, floor=1e-5):
         else:
             e = rel_err(a, b)
             assert e < tol, f"{n}: rel err {e:.3e} > {tol}"
+            if tol_l2 is not None:  # ||a-b||_2 / ||b||_2: insensitive to the handful of ReLU-mask flips tf32 rounding causes
+                e2 = float((a.double().cpu() - b.double()).norm() / b.double().norm())
+                assert e2 < tol_l2, f"{n}: L2 rel err {e2:.3e} > {tol_l2}"
 
 
 def global_grad_error(got, ref):
