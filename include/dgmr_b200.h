@@ -130,6 +130,16 @@ int dgmr_bn_bwd_apply(const float* dy, const float* x, const float* a, const flo
  * ws: >= (G+2)*R + 2*G + 8 floats of scratch. */
 int dgmr_sn_power_iter(const float* w, float* u, float* v, int R, int K, int G, float eps, int training,
                        float* inv_sigma, float* u_hist, float* v_hist, float* ws, dgmr_stream_t stream);
+/* All spectrally normalised layers of a module in ONE launch (CTAs split over the weights by size, each weight's CTA group
+ * iterating independently): `items` is a HOST array; every `ws` must be zero-initialised by the caller (same size rule). */
+typedef struct {
+  const float* w; float* u; float* v;            /* as in dgmr_sn_power_iter */
+  float* inv_sigma; float* u_hist; float* v_hist;
+  float* ws;
+  int R, K, G, training;
+  float eps;
+} dgmr_sn_item;
+int dgmr_sn_power_iter_multi(const dgmr_sn_item* items, int n, dgmr_stream_t stream);
 /* dW[r][k] += sum_g d_inv_sigma[g] * (-inv_sigma[g]^2) * u_g[r] v_g[k]  (u,v constants, as in torch) */
 int dgmr_sn_bwd(const float* d_inv_sigma, const float* inv_sigma, const float* u_hist, const float* v_hist,
                 float* dw, int R, int K, int G, int accumulate, dgmr_stream_t stream);

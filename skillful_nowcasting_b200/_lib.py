@@ -106,6 +106,13 @@ def _f64(t: Optional[torch.Tensor], name: str):
     return _ptr(t, name)
 
 
+class SnItem(ctypes.Structure):
+    """dgmr_sn_item of include/dgmr_b200.h."""
+    _fields_ = [("w", ctypes.c_void_p), ("u", ctypes.c_void_p), ("v", ctypes.c_void_p), ("inv_sigma", ctypes.c_void_p),
+                ("u_hist", ctypes.c_void_p), ("v_hist", ctypes.c_void_p), ("ws", ctypes.c_void_p), ("R", ctypes.c_int),
+                ("K", ctypes.c_int), ("G", ctypes.c_int), ("training", ctypes.c_int), ("eps", ctypes.c_float)]
+
+
 class CudaBackend:
     """Thin tensor-level view of the C ABI.  Method names/arguments mirror include/dgmr_b200.h.
     `launches` counts kernel-launching entry-point calls (reported by bench.py as gpu_launches)."""
@@ -222,6 +229,15 @@ class CudaBackend:
         self._call("dgmr_sn_power_iter", _f32(w, "w"), _f32(u, "u"), _f32(v, "v"), R, K, G, float(eps), int(training),
                    _f32(inv_sigma, "inv_sigma"), _f32(u_hist, "u_hist"), _f32(v_hist, "v_hist"), _f32(ws, "ws"),
                    _info=f"{R}x{K} G{G} train{int(training)}")
+
+    def sn_power_iter_multi(self, items):
+        """items: list of dicts(w,u,v,R,K,G,eps,training,inv_sigma,u_hist,v_hist,ws) -- every `ws` already zeroed."""
+        arr = (SnItem * len(items))()
+        for a, it in zip(arr, items):
+            for k in ("w", "u", "v", "inv_sigma", "u_hist", "v_hist", "ws"):
+                setattr(a, k, _f32(it[k], k))
+            a.R, a.K, a.G, a.training, a.eps = it["R"], it["K"], it["G"], int(it["training"]), float(it["eps"])
+        self._call("dgmr_sn_power_iter_multi", arr, len(items), _info=f"{len(items)} weights")
 
     def sn_bwd(self, d_inv_sigma, inv_sigma, u_hist, v_hist, dw, R, K, G, accumulate):
         self._call("dgmr_sn_bwd", _f32(d_inv_sigma, "d_inv_sigma"), _f32(inv_sigma, "inv_sigma"), _f32(u_hist, "u_hist"),

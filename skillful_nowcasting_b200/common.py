@@ -17,7 +17,7 @@ from huggingface_hub import PyTorchModelHubMixin
 
 from . import ops
 from .layers.Attention import AttentionLayer
-from .layers.core import BatchNorm, PlainConv, SNConv
+from .layers.core import BatchNorm, PlainConv, SNConv, prefetch_sigmas
 from .ops import ACT_NONE, ACT_RELU
 
 
@@ -45,6 +45,11 @@ class GBlock(nn.Module):
         self.first_conv_3x3 = SNConv(input_channels, input_channels, _kernel(conv_type, 3), eps=e)
         self.last_conv_3x3 = SNConv(input_channels, output_channels, _kernel(conv_type, 3), eps=e)
 
+    def sn_calls(self, G: int = 1):
+        """The spectrally normalised layers `run` will evaluate (conv_1x1 only when it projects, like the reference :71-74)."""
+        proj = [(self.conv_1x1, G)] if self.input_channels != self.output_channels else []
+        return proj + [(self.first_conv_3x3, G), (self.last_conv_3x3, G)]
+
     def run(self, x, G: int = 1):
         sc = x if x.shape[-1] == self.output_channels else self.conv_1x1.run(x, G)
         y = ops.mark_conv_only(self.bn1.run(x, G, relu=True))
@@ -69,6 +74,9 @@ class UpsampleGBlock(nn.Module):
         self.conv_1x1 = SNConv(input_channels, output_channels, _kernel(conv_type, 1), eps=e)
         self.first_conv_3x3 = SNConv(input_channels, input_channels, _kernel(conv_type, 3), eps=e)
         self.last_conv_3x3 = SNConv(input_channels, output_channels, _kernel(conv_type, 3), eps=e)
+
+    def sn_calls(self, G: int = 1):
+        return [(self.conv_1x1, G), (self.first_conv_3x3, G), (self.last_conv_3x3, G)]
 
     def run(self, x, G: int = 1):
         # conv1x1(up2(x)) == up2(conv1x1(x)) bit-for-bit (pointwise conv commutes with replication): 4x fewer MACs
@@ -96,6 +104,10 @@ class DBlock(nn.Module):
 
     def _pool(self, x):
         return ops.avg_pool(x, 2, 2, 2) if self.conv_type == "3d" else ops.avg_pool(x, 1, 2, 2)
+
+    def sn_calls(self, G: int = 1):
+        proj = [(self.conv_1x1, G)] if self.input_channels != self.output_channels else []
+        return proj + [(self.first_conv_3x3, G), (self.last_conv_3x3, G)]
 
     def run(self, x, G: int = 1):
         if self.input_channels != self.output_channels:
@@ -162,6 +174,9 @@ class ContextConditioningStack(nn.Module, PyTorchModelHubMixin):
         x = x.contiguous()
         b, t, c, h, w = x.shape
         h2, w2 = h // 2, w // 2
+        # every spectral norm of the stack in one launch: the DBlocks are called once per context frame, the mixers once
+        prefetch_sigmas([c_ for blk in (self.d1, self.d2, self.d3, self.d4) for c_ in blk.sn_calls(t)]
+                        + [(m, 1) for m in (self.conv1, self.conv2, self.conv3, self.conv4)])
         # space-to-depth (PixelUnshuffle(2), :393) and regrouping to timestep-major in ONE permute:
         # dst[t, b, h2, w2, c*4 + i*2 + j] = x[b, t, c, 2*h2+i, 2*w2+j]
         cpad = ops.pad8(4 * c)  # 4 -> 8 zero-padded channels: lets the tcgen05 path (K step 8) take the first DBlock

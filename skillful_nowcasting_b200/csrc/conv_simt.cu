@@ -4,8 +4,6 @@
 // (tiny channel counts such as the 4-channel space-to-depth inputs, batch-1 latent stack,
 // 1x1/2x2 images deep in the discriminators) and are the on-device cross-check for it.
 #include "common.cuh"
-#include <cooperative_groups.h>
-namespace cg = cooperative_groups;
 
 namespace dgmr {
 
@@ -319,33 +317,40 @@ __global__ void __launch_bounds__(256) conv_bwd_prep_kernel(const float* __restr
 }
 
 // ------------------------------------------------------------------ spectral norm
-// Column-partitioned persistent cooperative kernel: CTA j keeps W[:, k0:k1) in shared memory
-// (the whole weight lives across the SMs' smem: <= 21 MB for the largest DGMR layer) and all
-// G reference calls' power iterations run inside ONE launch, two grid syncs per iteration.
-struct SnArgs {
-  const float* w; float* u; float* v; int R, K, G; float eps; int training;
+// Column-partitioned persistent kernel: the CTAs of one weight each own a column slab W[:, k0:k1) (kept in shared memory
+// when it fits, streamed from L2 otherwise) and run ALL G power iterations of that weight inside one launch, two group
+// barriers per iteration.  The multi-weight entry point runs every spectrally normalised layer of a module (the 37 layers of
+// the sampler, ...) in ONE launch: CTAs are split over the weights in proportion to their size and each weight's CTA group
+// synchronises on its own arrival counter, so the per-iteration latency (a few global round trips) is paid once per
+// iteration for all layers together instead of once per layer.
+struct SnItem {
+  const float* w; float* u; float* v;
   float* inv_sigma; float* u_hist; float* v_hist;
-  float* t;   // [(G+1)][R] zeroed
-  float* nq;  // [G] zeroed
-  unsigned* bar;  // zeroed arrival counter of the grid barrier
-  int kw; int in_smem;
+  float* ws;          // zeroed: t[(G+1)][R], nq[G], barrier counter
+  int R, K, G, training;
+  float eps;
+  int cta_begin, cta_count, kw, in_smem;
 };
-// Grid-wide barrier for the co-resident (cooperatively launched) CTAs: one monotonically increasing arrival counter,
-// barrier k completes when it reaches k * gridDim.x.  ~1 us instead of the several us of cooperative_groups' grid.sync().
-__device__ __forceinline__ void sn_grid_barrier(unsigned* counter, unsigned& epoch) {
+constexpr int kSnMaxItems = 40;
+struct SnMultiArgs { SnItem it[kSnMaxItems]; int n; };
+
+// Barrier among `size` co-resident CTAs on a monotonically increasing counter (barrier k completes at k*size arrivals).
+__device__ __forceinline__ void sn_group_barrier(unsigned* counter, unsigned& epoch, unsigned size) {
   __syncthreads();
-  if (threadIdx.x == 0) {
-    ++epoch;
-    const unsigned target = epoch * gridDim.x;
-    __threadfence();
-    atomicAdd(counter, 1u);
-    unsigned seen;
-    do {
-      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
-    } while (seen < target);
-    __threadfence();
+  if (size > 1) {
+    if (threadIdx.x == 0) {
+      ++epoch;
+      const unsigned target = epoch * size;
+      __threadfence();
+      atomicAdd(counter, 1u);
+      unsigned seen;
+      do {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+      } while (seen < target);
+      __threadfence();
+    }
+    __syncthreads();
   }
-  __syncthreads();
 }
 __device__ __forceinline__ float block_sumsq(const float* a, int n, float* red) {
   float s = 0.f;
@@ -358,17 +363,20 @@ __device__ __forceinline__ float block_sumsq(const float* a, int n, float* red) 
   for (int w = 0; w < (blockDim.x >> 5); ++w) tot += red[w];
   return tot;
 }
-__global__ void __launch_bounds__(256) sn_power_iter_kernel(SnArgs a) {
-  extern __shared__ float smem[];
+__device__ void sn_run(const SnItem& a, const int rank, float* smem) {
   unsigned epoch = 0;   // only thread 0's copy is used
+  const unsigned size = (unsigned)a.cta_count;
   const int R = a.R, K = a.K, kwmax = a.kw;
-  const int k0 = blockIdx.x * kwmax;
+  const int k0 = rank * kwmax;
   const int kw = (k0 + kwmax <= K) ? kwmax : (K - k0 > 0 ? K - k0 : 0);
   float* ush = smem;                // [R]
   float* vsh = ush + R;             // [kwmax]
   float* qsh = vsh + kwmax;         // [kwmax]
   float* red = qsh + kwmax;         // [32]
   float* wsh = red + 32;            // [R][kwmax] if in_smem
+  float* t = a.ws;
+  float* nq = a.ws + (size_t)(a.G + 1) * R;
+  unsigned* bar = reinterpret_cast<unsigned*>(nq + a.G);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   if (a.in_smem) {
     for (int r = warp; r < R; r += nwarps)
@@ -376,23 +384,23 @@ __global__ void __launch_bounds__(256) sn_power_iter_kernel(SnArgs a) {
   }
   for (int k = threadIdx.x; k < kw; k += blockDim.x) vsh[k] = a.v[k0 + k];
   __syncthreads();
-  auto Wat = [&](int r, int k) -> float { return a.in_smem ? wsh[r * kwmax + k] : a.w[(int64_t)r * K + k0 + k]; };
+  auto Wat = [&](int r, int k) -> float { return a.in_smem ? wsh[r * kwmax + k] : __ldg(a.w + (int64_t)r * K + k0 + k); };
   // t[slot] += W[:, mine] v[mine]
   auto matvec = [&](int slot) {
     for (int r = warp; r < R; r += nwarps) {
       float s = 0.f;
       for (int k = lane; k < kw; k += 32) s += Wat(r, k) * vsh[k];
       s = warp_sum(s);
-      if (lane == 0 && kw > 0) atomicAdd(&a.t[(int64_t)slot * R + r], s);
+      if (lane == 0 && kw > 0) atomicAdd(&t[(int64_t)slot * R + r], s);
     }
   };
   matvec(0);
-  sn_grid_barrier(a.bar, epoch);
+  sn_group_barrier(bar, epoch, size);
   if (!a.training) {
     // sigma = u0 . (W v0), same for all G calls
-    if (blockIdx.x == 0) {
+    if (rank == 0) {
       float s = 0.f;
-      for (int r = threadIdx.x; r < R; r += blockDim.x) s += a.u[r] * __ldcg(a.t + r);
+      for (int r = threadIdx.x; r < R; r += blockDim.x) s += a.u[r] * __ldcg(t + r);
       s = warp_sum(s);
       if (lane == 0) red[warp] = s;
       __syncthreads();
@@ -408,18 +416,20 @@ __global__ void __launch_bounds__(256) sn_power_iter_kernel(SnArgs a) {
   }
   for (int g = 0; g < a.G; ++g) {
     // u_g = normalize(t[g])   (every CTA recomputes it; R <= 768)
-    const float* tg = a.t + (int64_t)g * R;
+    const float* tg = t + (int64_t)g * R;
     float nrm = sqrtf(block_sumsq(tg, R, red));
     float inv = 1.0f / fmaxf(nrm, a.eps);
     for (int r = threadIdx.x; r < R; r += blockDim.x) ush[r] = __ldcg(tg + r) * inv;
     for (int k = threadIdx.x; k < kwmax; k += blockDim.x) qsh[k] = 0.f;
     __syncthreads();
-    if (blockIdx.x == 0) for (int r = threadIdx.x; r < R; r += blockDim.x) a.u_hist[(int64_t)g * R + r] = ush[r];
-    // q[mine] = W[:, mine]^T u
-    for (int k = lane; k < kw; k += 32) {
+    if (rank == 0) for (int r = threadIdx.x; r < R; r += blockDim.x) a.u_hist[(int64_t)g * R + r] = ush[r];
+    // q[mine] = W[:, mine]^T u : warps split the rows, lanes the columns (coalesced rows of the slab)
+    for (int kb = 0; kb < kw; kb += 32) {
+      const int k = kb + lane;
       float s = 0.f;
-      for (int r = warp; r < R; r += nwarps) s += ush[r] * Wat(r, k);
-      atomicAdd(&qsh[k], s);
+      if (k < kw)
+        for (int r = warp; r < R; r += nwarps) s += ush[r] * Wat(r, k);
+      if (k < kw) atomicAdd(&qsh[k], s);
     }
     __syncthreads();
     float part = 0.f;
@@ -427,16 +437,16 @@ __global__ void __launch_bounds__(256) sn_power_iter_kernel(SnArgs a) {
     part = warp_sum(part);
     if (lane == 0) red[warp] = part;
     __syncthreads();
-    if (threadIdx.x == 0) { float tot = 0.f; for (int w = 0; w < nwarps; ++w) tot += red[w]; atomicAdd(&a.nq[g], tot); }
-    sn_grid_barrier(a.bar, epoch);
-    float qn = sqrtf(__ldcg(a.nq + g));
+    if (threadIdx.x == 0) { float tot = 0.f; for (int w = 0; w < nwarps; ++w) tot += red[w]; atomicAdd(&nq[g], tot); }
+    sn_group_barrier(bar, epoch, size);
+    float qn = sqrtf(__ldcg(nq + g));
     float qinv = 1.0f / fmaxf(qn, a.eps);
     for (int k = threadIdx.x; k < kw; k += blockDim.x) { float vv = qsh[k] * qinv; vsh[k] = vv; a.v_hist[(int64_t)g * K + k0 + k] = vv; }
     __syncthreads();
     matvec(g + 1);
-    sn_grid_barrier(a.bar, epoch);
-    if (blockIdx.x == 0) {
-      const float* tn = a.t + (int64_t)(g + 1) * R;
+    sn_group_barrier(bar, epoch, size);
+    if (rank == 0) {
+      const float* tn = t + (int64_t)(g + 1) * R;
       float s = 0.f;
       for (int r = threadIdx.x; r < R; r += blockDim.x) s += ush[r] * __ldcg(tn + r);
       s = warp_sum(s);
@@ -448,8 +458,19 @@ __global__ void __launch_bounds__(256) sn_power_iter_kernel(SnArgs a) {
     }
   }
   // persist final u, v
-  if (blockIdx.x == 0) for (int r = threadIdx.x; r < R; r += blockDim.x) a.u[r] = ush[r];
+  if (rank == 0) for (int r = threadIdx.x; r < R; r += blockDim.x) a.u[r] = ush[r];
   for (int k = threadIdx.x; k < kw; k += blockDim.x) a.v[k0 + k] = vsh[k];
+}
+__global__ void __launch_bounds__(256) sn_multi_kernel(const __grid_constant__ SnMultiArgs args) {
+  extern __shared__ float smem[];
+  const int bid = blockIdx.x;
+  for (int i = 0; i < args.n; ++i) {
+    const SnItem& it = args.it[i];
+    if (bid >= it.cta_begin && bid < it.cta_begin + it.cta_count) {
+      sn_run(it, bid - it.cta_begin, smem);
+      return;
+    }
+  }
 }
 __global__ void sn_bwd_kernel(const float* __restrict__ dis, const float* __restrict__ is, const float* __restrict__ uh, const float* __restrict__ vh,
                               float* __restrict__ dw, int R, int K, int G, int acc) {
@@ -548,42 +569,94 @@ int dgmr_conv_bwd_prep(const float* dy, const float* y, const float* res, const 
   return 0;
 }
 
-int dgmr_sn_power_iter(const float* w, float* u, float* v, int R, int K, int G, float eps, int training, float* inv_sigma, float* u_hist, float* v_hist,
-                       float* ws, dgmr_stream_t stream) {
-  DGMR_REQUIRE(R > 0 && K > 0 && G > 0, "dgmr_sn_power_iter: bad dims");
+static int sn_launch(SnMultiArgs& args, int total_ctas, size_t smem, cudaStream_t st) {
   static int max_smem = 0, coop = -1;
   if (coop < 0) {
     int dev = 0; cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
     cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
   }
-  DGMR_REQUIRE(coop == 1, "dgmr_sn_power_iter: device lacks cooperative launch");
+  if (coop != 1) { set_error("dgmr_sn_power_iter: device lacks cooperative launch"); return 1; }
+  if (smem > (size_t)max_smem) { set_error("dgmr_sn_power_iter: needs %zu B of shared memory (> %d)", smem, max_smem); return 1; }
+  static size_t smem_set = 0;
+  if (smem > smem_set) {
+    if (cudaFuncSetAttribute(sn_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { set_error("dgmr_sn_power_iter: smem attribute"); return 2; }
+    smem_set = smem;
+  }
+  void* kargs[] = {&args};
+  // cooperative launch = all CTAs co-resident, which the group barriers rely on
+  cudaError_t e = cudaLaunchCooperativeKernel((void*)sn_multi_kernel, dim3(total_ctas), dim3(256), kargs, smem, st);
+  if (e != cudaSuccess) { set_error("dgmr_sn_power_iter: cooperative launch failed: %s (ctas=%d smem=%zu)", cudaGetErrorString(e), total_ctas, smem); return 2; }
+  return 0;
+}
+static size_t sn_item_smem(const SnItem& it) { return (size_t)(it.R + 2 * it.kw + 32) * 4 + (it.in_smem ? (size_t)it.R * it.kw * 4 : 0); }
+
+int dgmr_sn_power_iter(const float* w, float* u, float* v, int R, int K, int G, float eps, int training, float* inv_sigma, float* u_hist, float* v_hist,
+                       float* ws, dgmr_stream_t stream) {
+  DGMR_REQUIRE(R > 0 && K > 0 && G > 0, "dgmr_sn_power_iter: bad dims");
+  const int64_t budget = 200 * 1024 - (int64_t)(R + 32) * 4 - 1024;
   int sms = sm_count();
-  // CTAs: enough that a slice fits in smem and <= 256 columns each; few CTAs for small weights
-  int64_t budget = (int64_t)max_smem - (int64_t)(R + 32) * 4 - 1024;
   int nb = (int)ceil_div((int64_t)R * K, 32768);
   if (nb < 1) nb = 1;
-  if (nb < ceil_div(K, 256)) nb = (int)ceil_div(K, 256);
   if (nb > sms) nb = sms;
   if (nb > K) nb = K;
   int kw = (int)ceil_div(K, nb);
   int in_smem = 1;
-  // grow nb until the slice fits
   while (((int64_t)R * kw + 2 * kw) * 4 > budget && nb < sms && nb < K) { ++nb; kw = (int)ceil_div(K, nb); }
   if (((int64_t)R * kw + 2 * kw) * 4 > budget) in_smem = 0;
   nb = (int)ceil_div(K, kw);
-  size_t sh = (size_t)(R + 2 * kw + 32) * 4 + (in_smem ? (size_t)R * kw * 4 : 0);
-  DGMR_REQUIRE(sh <= (size_t)max_smem, "dgmr_sn_power_iter: R=%d too large for shared memory", R);
-  DGMR_CUDA(cudaFuncSetAttribute(sn_power_iter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
-  SnArgs a;
+  SnMultiArgs args;
+  args.n = 1;
+  SnItem& a = args.it[0];
   a.w = w; a.u = u; a.v = v; a.R = R; a.K = K; a.G = G; a.eps = eps; a.training = training;
-  a.inv_sigma = inv_sigma; a.u_hist = u_hist; a.v_hist = v_hist;
-  a.t = ws; a.nq = ws + (size_t)(G + 1) * R; a.kw = kw; a.in_smem = in_smem;
-  a.bar = reinterpret_cast<unsigned*>(ws + (size_t)(G + 1) * R + G);
+  a.inv_sigma = inv_sigma; a.u_hist = u_hist; a.v_hist = v_hist; a.ws = ws;
+  a.cta_begin = 0; a.cta_count = nb; a.kw = kw; a.in_smem = in_smem;
   DGMR_CUDA(cudaMemsetAsync(ws, 0, sizeof(float) * ((size_t)(G + 1) * R + G + 1), S(stream)));
-  void* args[] = {&a};
-  cudaError_t e = cudaLaunchCooperativeKernel((void*)sn_power_iter_kernel, dim3(nb), dim3(256), args, sh, S(stream));
-  if (e != cudaSuccess) { set_error("dgmr_sn_power_iter: cooperative launch failed: %s (nb=%d smem=%zu)", cudaGetErrorString(e), nb, sh); return 2; }
+  return sn_launch(args, nb, sn_item_smem(a), S(stream));
+}
+
+int dgmr_sn_power_iter_multi(const dgmr_sn_item* items, int n, dgmr_stream_t stream) {
+  DGMR_REQUIRE(n >= 1, "dgmr_sn_power_iter_multi: empty");
+  const int sms = sm_count();
+  for (int base = 0; base < n; base += kSnMaxItems) {
+    const int m = n - base < kSnMaxItems ? n - base : kSnMaxItems;
+    SnMultiArgs args;
+    args.n = m;
+    double total = 0.0;
+    for (int i = 0; i < m; ++i) {
+      const dgmr_sn_item& s = items[base + i];
+      DGMR_REQUIRE(s.R > 0 && s.K > 0 && s.G > 0, "dgmr_sn_power_iter_multi: bad dims in item %d", base + i);
+      total += (double)s.R * s.K * (s.training ? s.G : 1);
+    }
+    DGMR_REQUIRE(m <= sms, "dgmr_sn_power_iter_multi: more weights than SMs");
+    // CTAs in proportion to the work, at least one each, never more than the SM count in total (co-residency)
+    int used = 0;
+    for (int i = 0; i < m; ++i) {
+      const dgmr_sn_item& s = items[base + i];
+      double c = (double)s.R * s.K * (s.training ? s.G : 1);
+      int cnt = (int)((sms - m) * c / total) + 1;
+      if (cnt > s.K) cnt = s.K;
+      args.it[i].cta_count = cnt;
+      used += cnt;
+    }
+    size_t smem = 0;
+    int begin = 0;
+    for (int i = 0; i < m; ++i) {
+      const dgmr_sn_item& s = items[base + i];
+      SnItem& a = args.it[i];
+      a.w = s.w; a.u = s.u; a.v = s.v; a.inv_sigma = s.inv_sigma; a.u_hist = s.u_hist; a.v_hist = s.v_hist; a.ws = s.ws;
+      a.R = s.R; a.K = s.K; a.G = s.G; a.training = s.training; a.eps = s.eps;
+      a.kw = (int)ceil_div(s.K, a.cta_count);
+      a.cta_count = (int)ceil_div(s.K, a.kw);   // drop CTAs that would own no column
+      a.cta_begin = begin; begin += a.cta_count;
+      a.in_smem = (((int64_t)a.R * a.kw + 2 * a.kw + a.R + 32) * 4 <= 160 * 1024) ? 1 : 0;
+      size_t need = sn_item_smem(a);
+      if (need > smem) smem = need;
+    }
+    (void)used;
+    int e = sn_launch(args, begin, smem, S(stream));
+    if (e) return e;
+  }
   return 0;
 }
 int dgmr_sn_bwd(const float* d_inv_sigma, const float* inv_sigma, const float* u_hist, const float* v_hist, float* dw, int R, int K, int G, int accumulate,

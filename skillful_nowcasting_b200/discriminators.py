@@ -11,7 +11,7 @@ from huggingface_hub import PyTorchModelHubMixin
 
 from . import ops
 from .common import DBlock
-from .layers.core import BatchNorm, SNConv
+from .layers.core import BatchNorm, SNConv, prefetch_sigmas
 
 
 def _head(rep, bn: BatchNorm, fc: SNConv, G: int):
@@ -49,6 +49,8 @@ class SpatialDiscriminator(nn.Module, PyTorchModelHubMixin):
         # same draw as the reference: CPU global RNG, with replacement, over all T frames (:199)
         idxs = torch.randint(low=0, high=t, size=(self.num_timesteps,)).tolist()
         G = len(idxs)
+        prefetch_sigmas(self.d1.sn_calls(G) + [c_ for d in self.intermediate_dblocks for c_ in d.sn_calls(G)] + self.d6.sn_calls(G)
+                        + [(self.fc, G)])
         rep = ops.gather_frames(x.reshape(n, t, c * h * w), idxs)          # [G*N, C*H*W] frame-major
         rep = ops.nchw_to_cl(rep.reshape(G * n, c, h, w))                  # [G*N,1,H,W,C]
         rep = ops.avg_pool(rep, 1, 2, 2)
@@ -87,6 +89,9 @@ class TemporalDiscriminator(nn.Module, PyTorchModelHubMixin):
             v = x.reshape(n, t, h, w, 1)
         else:
             v = ops.permute(x.contiguous(), (n, t, h, w, c), (n * t, c, h * w), (c * h * w, h * w, 1), (h * w * c, 1, c))
+        t2_ = (t // 2) // 2                # timesteps left after the two 3-D DBlocks
+        prefetch_sigmas(self.d1.sn_calls(1) + self.d2.sn_calls(1) + [c_ for d in self.intermediate_dblocks for c_ in d.sn_calls(t2_)]
+                        + self.d_last.sn_calls(t2_) + [(self.fc, t2_)])
         v = ops.avg_pool(v, 1, 2, 2)       # AvgPool3d((1,2,2)) (:106)
         v = ops.space_to_depth(v)          # PixelUnshuffle + permute to N,C,T,H,W (:108-110) == [N,T,h,w,4C] here
         v = self.d1.run(v, 1)              # 3-D DBlocks: T 22 -> 11 -> 5

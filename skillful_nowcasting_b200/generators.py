@@ -17,7 +17,7 @@ from huggingface_hub import PyTorchModelHubMixin
 from . import ops
 from .common import GBlock, UpsampleGBlock
 from .layers.ConvGRU import ConvGRU
-from .layers.core import BatchNorm, SNConv
+from .layers.core import BatchNorm, SNConv, prefetch_sigmas
 
 
 class Sampler(nn.Module, PyTorchModelHubMixin):
@@ -57,6 +57,12 @@ class Sampler(nn.Module, PyTorchModelHubMixin):
                   (self.convGRU2, self.gru_conv_1x1_2, self.g2, self.up_g2),
                   (self.convGRU3, self.gru_conv_1x1_3, self.g3, self.up_g3),
                   (self.convGRU4, self.gru_conv_1x1_4, self.g4, self.up_g4))
+        # all 37 spectral norms of the sampler (T power iterations each) in one launch
+        calls = [(self.conv_1x1, T)]
+        for gru, c11, g, ug in levels:
+            cell = gru.cell
+            calls += [(cell.read_gate_conv, T), (cell.update_gate_conv, T), (cell.output_conv, T), (c11, T)] + g.sn_calls(T) + ug.sn_calls(T)
+        prefetch_sigmas(calls)
         hs = latent
         for lvl, (gru, c11, g, ug) in enumerate(levels):
             # level 0: identical latent input at every step and for every sample (generators.py:146-149)

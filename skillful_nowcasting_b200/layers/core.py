@@ -86,7 +86,12 @@ class SNConv(nn.Module):
         return b._u, b._v
 
     def inv_sigma(self, G: int) -> torch.Tensor:
-        """1/sigma for the next G reference calls (power iteration advances G times in training)."""
+        """1/sigma for the next G reference calls (power iteration advances G times in training).  If the enclosing module
+        prefetched it (all of its spectral norms in one launch, see `prefetch_sigmas`), that result is consumed here."""
+        pending = self.__dict__.pop("_pending_sigma", None)
+        if pending is not None:
+            assert pending[0] == G, f"prefetched spectral norm for G={pending[0]} but used with G={G}"
+            return pending[1]
         u, v = self._uv
         return ops.spectral_inv_sigma(self.weight_orig, u, v, G, self.eps, self.training)
 
@@ -105,6 +110,23 @@ class SNConv(nn.Module):
             return y.reshape(x.shape[0], self.out_channels)
         keep = len(self.kernel) == 3
         return ops.cl_to_nchw(self.run(ops.nchw_to_cl(x)), keep_depth=keep)
+
+
+def prefetch_sigmas(calls):
+    """calls: [(SNConv, G), ...] that the caller is about to run, each exactly once.  Runs all their power iterations
+    (u, v updates included) in ONE kernel launch and parks each 1/sigma on its layer for the upcoming `inv_sigma(G)`."""
+    calls = [(l, g) for l, g in calls]
+    if len(calls) <= 1:
+        return
+    training = calls[0][0].training
+    assert all(l.training == training for l, _ in calls)
+    entries = []
+    for l, g in calls:
+        assert "_pending_sigma" not in l.__dict__, "a prefetched spectral norm was never consumed"
+        u, v = l._uv
+        entries.append((l.weight_orig, u, v, g, l.eps))
+    for (l, g), s in zip(calls, ops.spectral_inv_sigma_multi(entries, training)):
+        l.__dict__["_pending_sigma"] = (g, s)
 
 
 class PlainConv(nn.Module):

@@ -339,6 +339,61 @@ def spectral_inv_sigma(w, u, v, G, eps, training):
     return _SpectralSigma.apply(w, u, v, G, eps, training)[0]
 
 
+class _SpectralSigmaMulti(Function):
+    """_SpectralSigma for many weights in ONE launch (dgmr_sn_power_iter_multi).  Inputs: the n weights; meta carries the
+    (u, v, G, eps) of each.  Outputs: n inv_sigma tensors (views of one allocation)."""
+
+    @staticmethod
+    def forward(ctx, meta, training, *ws_):
+        n = len(ws_)
+        sizes, items = [], []
+        for w, (u, v, G, eps) in zip(ws_, meta):
+            R = w.shape[0]
+            K = w.numel() // R
+            sizes.append((R, K, G))
+        out_tot = sum(G + G * R + G * K for R, K, G in sizes)
+        ws_tot = sum((G + 2) * R + 2 * G + 8 for R, K, G in sizes)
+        out = _new((out_tot,), ws_[0])
+        scratch = _zeros((ws_tot,), ws_[0])
+        o = s = 0
+        res, hist = [], []
+        for w, (u, v, G, eps), (R, K, _) in zip(ws_, meta, sizes):
+            inv_sigma = out[o:o + G]; o += G
+            u_hist = out[o:o + G * R].view(G, R); o += G * R
+            v_hist = out[o:o + G * K].view(G, K); o += G * K
+            wsz = (G + 2) * R + 2 * G + 8
+            items.append(dict(w=_c(w.detach()), u=u, v=v, R=R, K=K, G=G, eps=eps, training=training, inv_sigma=inv_sigma,
+                              u_hist=u_hist, v_hist=v_hist, ws=scratch[s:s + wsz]))
+            s += wsz
+            res.append(inv_sigma)
+            hist.append((u_hist, v_hist))
+        _be().sn_power_iter_multi(items)
+        ctx.hist = hist
+        ctx.sizes = sizes
+        ctx.shapes = [tuple(w.shape) for w in ws_]
+        ctx.save_for_backward(*res)
+        return tuple(r.clone() for r in res) if False else tuple(res)
+
+    @staticmethod
+    def backward(ctx, *gs):
+        inv = ctx.saved_tensors
+        outs = []
+        for g, inv_sigma, (u_hist, v_hist), (R, K, G), shape, need in zip(gs, inv, ctx.hist, ctx.sizes, ctx.shapes, ctx.needs_input_grad[2:]):
+            if g is None or not need:
+                outs.append(None)
+                continue
+            dw = _new(shape, inv_sigma)
+            _be().sn_bwd(_c(g), _c(inv_sigma), u_hist, v_hist, dw, R, K, G, False)
+            outs.append(dw)
+        return (None, None) + tuple(outs)
+
+
+def spectral_inv_sigma_multi(entries, training):
+    """entries: list of (w, u, v, G, eps) -> list of inv_sigma[G] tensors, one kernel launch for all of them."""
+    meta = tuple((u, v, G, eps) for (_, u, v, G, eps) in entries)
+    return list(_SpectralSigmaMulti.apply(meta, training, *[e[0] for e in entries]))
+
+
 # ----------------------------------------------------------------------------- convolution
 _pack_cache = {}
 

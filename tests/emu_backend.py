@@ -197,6 +197,11 @@ class EmuBackend:
             v_hist[g] = v
             inv_sigma[g] = 1.0 / torch.dot(u, torch.mv(wm, v))
 
+    def sn_power_iter_multi(self, items):
+        for it in items:
+            self.sn_power_iter(it["w"], it["u"], it["v"], it["R"], it["K"], it["G"], it["eps"], it["training"], it["inv_sigma"],
+                               it["u_hist"], it["v_hist"], it["ws"])
+
     def sn_bwd(self, d_inv_sigma, inv_sigma, u_hist, v_hist, dw, R, K, G, accumulate):
         coef = -d_inv_sigma * inv_sigma * inv_sigma
         g = torch.einsum("g,gr,gk->rk", coef, u_hist, v_hist).reshape(dw.shape)

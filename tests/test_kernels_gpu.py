@@ -198,3 +198,30 @@ def test_head_attention_losses_adam(cuda_backend):
     n = 5000
     p, g, m, vv = torch.randn(n), torch.randn(n), torch.rand(n), torch.rand(n)
     _both("adam", [p, g, m, vv, 2e-4, 0.0, 0.999, 1e-8, 3, 0.5], cuda_backend, rtol=1e-5, atol=1e-7)
+
+
+@pytest.mark.parametrize("training", [True, False])
+def test_spectral_norm_multi(cuda_backend, training):
+    """All weights of a module in one launch (CTA groups per weight) vs the per-weight emulator."""
+    torch.manual_seed(10)
+    specs = [(768, 6912, 18), (384, 3456, 18), (384, 10368, 18), (192, 1728, 18), (96, 864, 18), (48, 432, 18), (768, 384, 18),
+             (24, 36, 4), (1, 768, 8), (96, 2592, 1), (4, 48, 18)] + [(96, 96 * 9, 18)] * 20
+    def make(dev):
+        torch.manual_seed(11)
+        items = []
+        for (R, K, G) in specs:
+            w = torch.randn(R, K) / K ** 0.5
+            u = torch.nn.functional.normalize(torch.randn(R), dim=0)
+            v = torch.nn.functional.normalize(torch.randn(K), dim=0)
+            it = dict(w=w, u=u, v=v, R=R, K=K, G=G, eps=1e-4, training=training, inv_sigma=torch.empty(G), u_hist=torch.empty(G, R),
+                      v_hist=torch.empty(G, K), ws=torch.zeros((G + 2) * R + 2 * G + 8))
+            items.append({k: (t.to(dev) if torch.is_tensor(t) else t) for k, t in it.items()})
+        return items
+    ref, got = make("cpu"), make("cuda")
+    EmuBackend().sn_power_iter_multi(ref)
+    cuda_backend.sn_power_iter_multi(got)
+    torch.cuda.synchronize()
+    for i, (a, b) in enumerate(zip(ref, got)):
+        for k in ("inv_sigma", "u_hist", "v_hist", "u", "v"):
+            err = (a[k] - b[k].cpu()).abs().max().item()
+            assert err <= 2e-5 + 2e-4 * a[k].abs().max().item(), (i, specs[i], k, err)
