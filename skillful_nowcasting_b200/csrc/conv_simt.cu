@@ -370,7 +370,7 @@ __device__ void sn_run(const SnItem& a, const int rank, float* smem) {
   const int k0 = rank * kwmax;
   const int kw = (k0 + kwmax <= K) ? kwmax : (K - k0 > 0 ? K - k0 : 0);
   float* ush = smem;                // [R]
-  float* vsh = ush + R;             // [kwmax]
+  float* vsh = ush + ((R + 3) & ~3); // [kwmax], 16-byte aligned
   float* qsh = vsh + kwmax;         // [kwmax]
   float* red = qsh + kwmax;         // [32]
   float* wsh = red + 32;            // [R][kwmax] if in_smem
@@ -384,14 +384,72 @@ __device__ void sn_run(const SnItem& a, const int rank, float* smem) {
   }
   for (int k = threadIdx.x; k < kw; k += blockDim.x) vsh[k] = a.v[k0 + k];
   __syncthreads();
-  auto Wat = [&](int r, int k) -> float { return a.in_smem ? wsh[r * kwmax + k] : __ldg(a.w + (int64_t)r * K + k0 + k); };
+  // slab access: shared-memory copy (pitch kwmax) or straight from global/L2 (pitch K).  float4 loads + 4-way unrolling keep
+  // enough bytes in flight per SM to stream the slab at memory speed (1024 threads per CTA).
+  const float* wb = a.in_smem ? wsh : a.w + k0;
+  const int64_t ld = a.in_smem ? kwmax : K;
+  const bool vec = ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(wb) & 15u) == 0) && ((kw & 3) == 0);
   // t[slot] += W[:, mine] v[mine]
   auto matvec = [&](int slot) {
     for (int r = warp; r < R; r += nwarps) {
+      const float* wr = wb + (int64_t)r * ld;
       float s = 0.f;
-      for (int k = lane; k < kw; k += 32) s += Wat(r, k) * vsh[k];
+      if (vec) {
+        const float4* w4 = reinterpret_cast<const float4*>(wr);
+        const float4* v4 = reinterpret_cast<const float4*>(vsh);
+        const int n4 = kw >> 2;
+        int k = lane;
+        for (; k + 96 < n4; k += 128) {
+          float4 a0 = w4[k], a1 = w4[k + 32], a2 = w4[k + 64], a3 = w4[k + 96];
+          float4 b0 = v4[k], b1 = v4[k + 32], b2 = v4[k + 64], b3 = v4[k + 96];
+          s += a0.x * b0.x + a0.y * b0.y + a0.z * b0.z + a0.w * b0.w + a1.x * b1.x + a1.y * b1.y + a1.z * b1.z + a1.w * b1.w +
+               a2.x * b2.x + a2.y * b2.y + a2.z * b2.z + a2.w * b2.w + a3.x * b3.x + a3.y * b3.y + a3.z * b3.z + a3.w * b3.w;
+        }
+        for (; k < n4; k += 32) { float4 a0 = w4[k], b0 = v4[k]; s += a0.x * b0.x + a0.y * b0.y + a0.z * b0.z + a0.w * b0.w; }
+      } else {
+        for (int k = lane; k < kw; k += 32) s += wr[k] * vsh[k];
+      }
       s = warp_sum(s);
       if (lane == 0 && kw > 0) atomicAdd(&t[(int64_t)slot * R + r], s);
+    }
+  };
+  // qsh[mine] += W[:, mine]^T u : warps split the rows, lanes own (groups of 4) columns
+  auto colsum = [&]() {
+    if (vec) {
+      const int n4 = kw >> 2;
+      for (int kb = 0; kb < n4; kb += 32) {
+        const int k = kb + lane;
+        if (k < n4) {
+          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+          int r = warp;
+          for (; r + 3 * nwarps < R; r += 4 * nwarps) {
+            float4 a0 = reinterpret_cast<const float4*>(wb + (int64_t)r * ld)[k];
+            float4 a1 = reinterpret_cast<const float4*>(wb + (int64_t)(r + nwarps) * ld)[k];
+            float4 a2 = reinterpret_cast<const float4*>(wb + (int64_t)(r + 2 * nwarps) * ld)[k];
+            float4 a3 = reinterpret_cast<const float4*>(wb + (int64_t)(r + 3 * nwarps) * ld)[k];
+            float u0 = ush[r], u1 = ush[r + nwarps], u2 = ush[r + 2 * nwarps], u3 = ush[r + 3 * nwarps];
+            acc.x += u0 * a0.x + u1 * a1.x + u2 * a2.x + u3 * a3.x;
+            acc.y += u0 * a0.y + u1 * a1.y + u2 * a2.y + u3 * a3.y;
+            acc.z += u0 * a0.z + u1 * a1.z + u2 * a2.z + u3 * a3.z;
+            acc.w += u0 * a0.w + u1 * a1.w + u2 * a2.w + u3 * a3.w;
+          }
+          for (; r < R; r += nwarps) {
+            float4 a0 = reinterpret_cast<const float4*>(wb + (int64_t)r * ld)[k];
+            float u0 = ush[r];
+            acc.x += u0 * a0.x; acc.y += u0 * a0.y; acc.z += u0 * a0.z; acc.w += u0 * a0.w;
+          }
+          atomicAdd(&qsh[4 * k], acc.x); atomicAdd(&qsh[4 * k + 1], acc.y); atomicAdd(&qsh[4 * k + 2], acc.z); atomicAdd(&qsh[4 * k + 3], acc.w);
+        }
+      }
+    } else {
+      for (int kb = 0; kb < kw; kb += 32) {
+        const int k = kb + lane;
+        if (k < kw) {
+          float s = 0.f;
+          for (int r = warp; r < R; r += nwarps) s += ush[r] * wb[(int64_t)r * ld + k];
+          atomicAdd(&qsh[k], s);
+        }
+      }
     }
   };
   matvec(0);
@@ -423,14 +481,7 @@ __device__ void sn_run(const SnItem& a, const int rank, float* smem) {
     for (int k = threadIdx.x; k < kwmax; k += blockDim.x) qsh[k] = 0.f;
     __syncthreads();
     if (rank == 0) for (int r = threadIdx.x; r < R; r += blockDim.x) a.u_hist[(int64_t)g * R + r] = ush[r];
-    // q[mine] = W[:, mine]^T u : warps split the rows, lanes the columns (coalesced rows of the slab)
-    for (int kb = 0; kb < kw; kb += 32) {
-      const int k = kb + lane;
-      float s = 0.f;
-      if (k < kw)
-        for (int r = warp; r < R; r += nwarps) s += ush[r] * Wat(r, k);
-      if (k < kw) atomicAdd(&qsh[k], s);
-    }
+    colsum();
     __syncthreads();
     float part = 0.f;
     for (int k = threadIdx.x; k < kw; k += blockDim.x) part += qsh[k] * qsh[k];
@@ -461,7 +512,7 @@ __device__ void sn_run(const SnItem& a, const int rank, float* smem) {
   if (rank == 0) for (int r = threadIdx.x; r < R; r += blockDim.x) a.u[r] = ush[r];
   for (int k = threadIdx.x; k < kw; k += blockDim.x) a.v[k0 + k] = vsh[k];
 }
-__global__ void __launch_bounds__(256) sn_multi_kernel(const __grid_constant__ SnMultiArgs args) {
+__global__ void __launch_bounds__(1024) sn_multi_kernel(const __grid_constant__ SnMultiArgs args) {
   extern __shared__ float smem[];
   const int bid = blockIdx.x;
   for (int i = 0; i < args.n; ++i) {
@@ -585,11 +636,11 @@ static int sn_launch(SnMultiArgs& args, int total_ctas, size_t smem, cudaStream_
   }
   void* kargs[] = {&args};
   // cooperative launch = all CTAs co-resident, which the group barriers rely on
-  cudaError_t e = cudaLaunchCooperativeKernel((void*)sn_multi_kernel, dim3(total_ctas), dim3(256), kargs, smem, st);
+  cudaError_t e = cudaLaunchCooperativeKernel((void*)sn_multi_kernel, dim3(total_ctas), dim3(1024), kargs, smem, st);
   if (e != cudaSuccess) { set_error("dgmr_sn_power_iter: cooperative launch failed: %s (ctas=%d smem=%zu)", cudaGetErrorString(e), total_ctas, smem); return 2; }
   return 0;
 }
-static size_t sn_item_smem(const SnItem& it) { return (size_t)(it.R + 2 * it.kw + 32) * 4 + (it.in_smem ? (size_t)it.R * it.kw * 4 : 0); }
+static size_t sn_item_smem(const SnItem& it) { return (size_t)(it.R + 4 + 2 * it.kw + 32) * 4 + (it.in_smem ? (size_t)it.R * it.kw * 4 : 0); }
 
 int dgmr_sn_power_iter(const float* w, float* u, float* v, int R, int K, int G, float eps, int training, float* inv_sigma, float* u_hist, float* v_hist,
                        float* ws, dgmr_stream_t stream) {
@@ -600,9 +651,9 @@ int dgmr_sn_power_iter(const float* w, float* u, float* v, int R, int K, int G, 
   if (nb < 1) nb = 1;
   if (nb > sms) nb = sms;
   if (nb > K) nb = K;
-  int kw = (int)ceil_div(K, nb);
+  int kw = (int)(ceil_div(ceil_div(K, nb), 4) * 4);
   int in_smem = 1;
-  while (((int64_t)R * kw + 2 * kw) * 4 > budget && nb < sms && nb < K) { ++nb; kw = (int)ceil_div(K, nb); }
+  while (((int64_t)R * kw + 2 * kw) * 4 > budget && nb < sms && nb < K) { ++nb; kw = (int)(ceil_div(ceil_div(K, nb), 4) * 4); }
   if (((int64_t)R * kw + 2 * kw) * 4 > budget) in_smem = 0;
   nb = (int)ceil_div(K, kw);
   SnMultiArgs args;
@@ -646,7 +697,7 @@ int dgmr_sn_power_iter_multi(const dgmr_sn_item* items, int n, dgmr_stream_t str
       SnItem& a = args.it[i];
       a.w = s.w; a.u = s.u; a.v = s.v; a.inv_sigma = s.inv_sigma; a.u_hist = s.u_hist; a.v_hist = s.v_hist; a.ws = s.ws;
       a.R = s.R; a.K = s.K; a.G = s.G; a.training = s.training; a.eps = s.eps;
-      a.kw = (int)ceil_div(s.K, a.cta_count);
+      a.kw = (int)(ceil_div(ceil_div(s.K, a.cta_count), 4) * 4);
       a.cta_count = (int)ceil_div(s.K, a.kw);   // drop CTAs that would own no column
       a.cta_begin = begin; begin += a.cta_count;
       a.in_smem = (((int64_t)a.R * a.kw + 2 * a.kw + a.R + 32) * 4 <= 160 * 1024) ? 1 : 0;
