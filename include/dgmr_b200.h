@@ -44,7 +44,7 @@ enum { DGMR_FLAG_ROUND_TF32 = 256 };
  * into y), which is what fills the SMs for the small-M, large-K convolutions of the ConvGRU steps. */
 enum { DGMR_FLAG_ACCUMULATE = 512 };
 /* conv algorithm selector */
-enum { DGMR_ALGO_AUTO = 0, DGMR_ALGO_SIMT = 1, DGMR_ALGO_UMMA = 2 };
+enum { DGMR_ALGO_AUTO = 0, DGMR_ALGO_SIMT = 1, DGMR_ALGO_UMMA = 2 /* plain tcgen05 kernel */, DGMR_ALGO_UMMA_PATCH = 3 /* halo-patch tcgen05 kernel */ };
 /* tensor-core operand precision: 1xTF32 (what cuDNN does by default for the reference) or
  * 3xTF32 error-compensated (hi*hi + hi*lo + lo*hi), ~fp32 accuracy */
 enum { DGMR_PREC_TF32 = 0, DGMR_PREC_3XTF32 = 1 };
@@ -54,6 +54,10 @@ int dgmr_abi_version(void);
 /* 1 if the tcgen05/TMA implicit-GEMM path can serve this conv shape (else the SIMT kernel is used) */
 int dgmr_conv_umma_supported(int N, int D, int H, int W, int Cin, int Cout, int kd, int kh, int kw);
 int dgmr_wgrad_umma_supported(int N, int D, int H, int W, int Cin, int Cout, int kd, int kh, int kw);
+
+/* debug probe (tests only): C[128][N] = A[r0:r0+128, 0:32] . B[N, 0:32]^T through TMA + tcgen05 with the A descriptor
+ * starting r0 rows into a swizzled 256-row tile; mode bit0 sets the descriptor base_offset field */
+int dgmr_debug_umma_shift(const float* A, const float* B, float* C, int N, int r0, int mode, dgmr_stream_t stream);
 
 /* ---- layout: generic strided gather  dst[i0..] (+)= src[i0..]
  * replaces ref: PixelUnshuffle/PixelShuffle (dgmr/common.py:326,393; generators.py:123,178;

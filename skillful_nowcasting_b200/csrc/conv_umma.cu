@@ -298,6 +298,214 @@ conv_umma_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   }
 }
 
+// ------------------------------------------------------------------ 3x3 convolution, halo-patch variant
+// The plain kernel above re-reads the activation tile once per filter tap (9x L2->SM amplification), which is what bounds
+// the high-resolution, low-channel layers (L2 bandwidth, not the tensor pipe).  Here the image is addressed in a padded,
+// flattened coordinate f = (h+1)*P + (w+1), P = W+2: the 128 (or 256) outputs of a tile are CONSECUTIVE f, the inputs of
+// filter tap (kh,kw) are the same run shifted by (kh-1)*P + (kw-1) rows, so ONE TMA box of whole padded image rows (zero
+// borders = TMA out-of-bounds fill) per 32-channel chunk feeds all 9 taps: the tcgen05 A descriptor simply starts at a
+// different 128-byte row of the swizzled patch (start addresses need not be swizzle-atom aligned, verified on hardware by
+// dgmr_debug_umma_shift).  Outputs that fall on the 2 padding columns are computed and discarded (2/P of the rows).
+// Persistent CTAs, separate activation-patch and weight rings, optionally two 128-row sub-tiles per weight stage (halves the
+// weight traffic) and double-buffered TMEM accumulators so the epilogue of one tile overlaps the MMAs of the next.
+struct PatchConvParams {
+  int N, D, H, W, Cin, Cout, kd, G;
+  int P, Rb;             // padded pitch W+2, padded rows per patch
+  int MT;                // 128-row sub-tiles per work item (1 or 2)
+  int NBUF;              // accumulator buffers (1 or 2)
+  int items_per_img;     // ceil(tiles_per_img / MT)
+  int BN, n_tiles;
+  int a_stages, b_stages;
+  int tmem_cols;
+  int act;
+  int64_t total_items;   // n_tiles * N * D * items_per_img
+  const float* bias; const float* scale; const float* res; float* y;
+};
+
+__global__ void __launch_bounds__(kUmmaThreads, 1)
+conv_umma_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const PatchConvParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t patch_bytes = (uint32_t)p.Rb * p.P * 128u;
+  const uint32_t patch_al = (patch_bytes + 1023u) & ~1023u;
+  const uint32_t b_bytes = (uint32_t)p.BN * 128u;
+  const uint32_t b_al = (b_bytes + 1023u) & ~1023u;
+  const uint32_t a_base = base, b_base = base + p.a_stages * patch_al;
+  const uint32_t bar_base = b_base + p.b_stages * b_al;
+  auto a_full = [&](int s) { return bar_base + 8u * s; };
+  auto a_empty = [&](int s) { return bar_base + 8u * (p.a_stages + s); };
+  auto b_full = [&](int s) { return bar_base + 8u * (2 * p.a_stages + s); };
+  auto b_empty = [&](int s) { return bar_base + 8u * (2 * p.a_stages + p.b_stages + s); };
+  auto acc_full = [&](int s) { return bar_base + 8u * (2 * p.a_stages + 2 * p.b_stages + s); };
+  auto acc_empty = [&](int s) { return bar_base + 8u * (2 * p.a_stages + 2 * p.b_stages + 2 + s); };
+  const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * p.a_stages + 2 * p.b_stages + 4);
+  volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_addr - raw));
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    for (int s = 0; s < p.a_stages; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1); }
+    for (int s = 0; s < p.b_stages; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(acc_full(s), 1); mbar_init(acc_empty(s), 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) { __syncwarp(); tmem_alloc(tmem_ptr_addr, (uint32_t)p.tmem_cols); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_gen;
+
+  const int chunks = p.Cin / 32;
+  const int a_per_item = p.kd * chunks;       // activation patches per work item
+  // work item -> (n_tile, image n, depth d, first flattened output fs)
+  auto decode = [&](int64_t item, int& nt, int& n, int& d, int& fs) {
+    int64_t t = item;
+    const int ii = (int)(t % p.items_per_img); t /= p.items_per_img;
+    d = (int)(t % p.D); t /= p.D;
+    n = (int)(t % p.N); t /= p.N;
+    nt = (int)t;
+    fs = p.P + 1 + 128 * p.MT * ii;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer: one activation patch per (kd, channel chunk), nine weight tiles per patch.  The patch of step s+1 is
+      // issued BEFORE the weight tiles of step s, so the (large) patch load overlaps a whole step of MMAs.
+      struct Cur { int64_t item; int kdi, c; };
+      auto valid = [&](const Cur& q) { return q.item < p.total_items; };
+      auto advance = [&](Cur& q) {
+        if (++q.c == chunks) { q.c = 0; if (++q.kdi == p.kd) { q.kdi = 0; q.item += gridDim.x; } }
+      };
+      uint32_t ai = 0, bi = 0;
+      auto issue_patch = [&](const Cur& q) {
+        int nt, n, d, fs; decode(q.item, nt, n, d, fs);
+        const int r_lo = (fs - p.P - 1) / p.P;            // first padded image row of the patch
+        const int sa = ai % p.a_stages; const uint32_t pha = (ai / p.a_stages) & 1u; ++ai;
+        mbar_wait(a_empty(sa), pha ^ 1u);
+        mbar_expect_tx(a_full(sa), patch_bytes);
+        tma_load_5d(a_base + sa * patch_al, &tmA, a_full(sa), q.c * 32, -1, r_lo - 1, d + q.kdi - p.kd / 2, n);
+      };
+      Cur ca{(int64_t)blockIdx.x, 0, 0}, cb = ca;
+      if (valid(ca)) { issue_patch(ca); advance(ca); }
+      while (valid(cb)) {
+        if (valid(ca)) { issue_patch(ca); advance(ca); }
+        int nt, n, d, fs; decode(cb.item, nt, n, d, fs);
+        for (int tap = 0; tap < 9; ++tap) {
+          const int sb = bi % p.b_stages; const uint32_t phb = (bi / p.b_stages) & 1u; ++bi;
+          mbar_wait(b_empty(sb), phb ^ 1u);
+          mbar_expect_tx(b_full(sb), b_bytes);
+          tma_load_3d(b_base + sb * b_al, &tmB, b_full(sb), cb.c * 32, nt * p.BN, cb.kdi * 9 + tap);
+        }
+        advance(cb);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((128u >> 4) << 24);
+      uint32_t ai = 0, bi = 0, it = 0;
+      for (int64_t item = blockIdx.x; item < p.total_items; item += gridDim.x, ++it) {
+        int nt, n, d, fs; decode(item, nt, n, d, fs);
+        const int r_lo = (fs - p.P - 1) / p.P;
+        const int buf = it % p.NBUF; const uint32_t phacc = (it / p.NBUF) & 1u;
+        mbar_wait(acc_empty(buf), phacc ^ 1u);
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + (uint32_t)(buf * p.MT * p.BN);
+        for (int a = 0; a < a_per_item; ++a) {
+          const int sa = ai % p.a_stages; const uint32_t pha = (ai / p.a_stages) & 1u; ++ai;
+          mbar_wait(a_full(sa), pha);
+          const uint32_t patch = a_base + sa * patch_al;
+          for (int tap = 0; tap < 9; ++tap) {
+            const int sb = bi % p.b_stages; const uint32_t phb = (bi / p.b_stages) & 1u; ++bi;
+            mbar_wait(b_full(sb), phb);
+            tc_fence_after();
+            const int th = tap / 3, tw = tap - th * 3;
+            const int j0 = fs + (th - 1) * p.P + (tw - 1) - r_lo * p.P;     // first patch row this tap reads (>= 0)
+            const uint64_t bdesc = make_desc(b_base + sb * b_al, 1024u, 2u);
+            for (int mt = 0; mt < p.MT; ++mt) {
+              const uint64_t adesc = make_desc(patch + (uint32_t)(j0 + 128 * mt) * 128u, 1024u, 2u);
+              for (int k = 0; k < 4; ++k)
+                umma_tf32(tacc + (uint32_t)(mt * p.BN), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (a | tap | k) != 0 ? 1u : 0u);
+            }
+            umma_commit(b_empty(sb));
+          }
+          umma_commit(a_empty(sa));
+        }
+        umma_commit(acc_full(buf));
+      }
+    }
+  } else {
+    // ===== epilogue warps
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const bool vec4 = (p.Cout & 3) == 0;
+    uint32_t it = 0;
+    for (int64_t item = blockIdx.x; item < p.total_items; item += gridDim.x, ++it) {
+      int nt, n, d, fs; decode(item, nt, n, d, fs);
+      const int buf = it % p.NBUF; const uint32_t phacc = (it / p.NBUF) & 1u;
+      const int co0 = nt * p.BN;
+      mbar_wait(acc_full(buf), phacc);
+      tc_fence_after();
+      for (int mt = 0; mt < p.MT; ++mt) {
+        const int f = fs + 128 * mt + r;
+        const int hp = f / p.P, wp = f - hp * p.P;
+        const bool valid = (wp >= 1) && (wp <= p.W) && (hp >= 1) && (hp <= p.H);
+        const int64_t m = (((int64_t)n * p.D + d) * p.H + (hp - 1)) * p.W + (wp - 1);
+        const int g = n / (p.N / p.G);
+        const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((buf * p.MT + mt) * p.BN);
+        for (int c = 0; c < p.BN; c += 16) {
+          if (co0 + c >= p.Cout) break;
+          float v[16];
+          tmem_ld16(trow + (uint32_t)c, v);
+          if (!valid) continue;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int co = co0 + c + j;
+            if (co < p.Cout) {
+              float t = v[j];
+              if (p.scale) t *= __ldg(p.scale + (int64_t)g * p.Cout + co);
+              if (p.bias) t += __ldg(p.bias + co);
+              v[j] = t;
+            }
+          }
+          float* yp = p.y + m * p.Cout + co0 + c;
+          const float* rp = p.res ? p.res + m * p.Cout + co0 + c : nullptr;
+          if (vec4) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+              if (co0 + c + j < p.Cout) {
+                float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                if (rp) { float4 rr = *reinterpret_cast<const float4*>(rp + j); o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w; }
+                if (p.act == DGMR_ACT_RELU) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                *reinterpret_cast<float4*>(yp + j) = o;
+              }
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              if (co0 + c + j < p.Cout) {
+                float o = v[j];
+                if (rp) o += rp[j];
+                if (p.act == DGMR_ACT_RELU) o = fmaxf(o, 0.f);
+                yp[j] = o;
+              }
+            }
+          }
+        }
+      }
+      // this warp is done reading the accumulator buffer
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(acc_empty(buf)) : "memory");
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { __syncwarp(); tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols); }
+}
+
 // ------------------------------------------------------------------ wgrad on tensor cores
 //   dwp[tap][co][ci] += sum_{pixels p in my K-slice} dz[p][co] * x[p + tap][ci]
 // GEMM view: M = Cout (128 per CTA), N = Cin tile, K = output pixels.  Both operands are read straight from the
@@ -427,6 +635,53 @@ conv_umma_wgrad_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_co
   tc_fence_before();
   __syncthreads();
   if (warp == 0) { __syncwarp(); tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols); }
+}
+
+// ------------------------------------------------------------------ descriptor probe (debug entry point)
+// C[128][N] = A[r0 : r0+128][0:32] . B[N][0:32]^T with A a 256-row K-major SWIZZLE_128B tile loaded by ONE TMA: validates
+// that a tcgen05 A descriptor may start at an arbitrary 128-byte row of a swizzled tile (needed to reuse one halo'd
+// activation patch for all filter taps).  mode bit0: set the descriptor's base_offset field to (addr >> 7) & 7.
+__global__ void __launch_bounds__(128, 1) umma_shift_probe_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                                                                  float* C, int N, int r0, int mode) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  const uint32_t a_bytes = 256u * 128u, b_bytes = (uint32_t)N * 128u;
+  const uint32_t bar = base + a_bytes + ((b_bytes + 1023u) & ~1023u);
+  const uint32_t done_bar = bar + 8, tmem_ptr_addr = bar + 16;
+  volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_addr - raw));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) { mbar_init(bar, 1); mbar_init(done_bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  if (warp == 0) { __syncwarp(); tmem_alloc(tmem_ptr_addr, 256); }
+  tc_fence_before(); __syncthreads(); tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_gen;
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(bar, a_bytes + b_bytes);
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(base), "l"(&tmA), "r"(bar), "r"(0), "r"(0) : "memory");
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(base + a_bytes), "l"(&tmB), "r"(bar), "r"(0), "r"(0) : "memory");
+    mbar_wait(bar, 0);
+    tc_fence_after();
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
+    const uint32_t sa = base + (uint32_t)r0 * 128u;
+    for (int k = 0; k < 4; ++k) {
+      uint64_t adesc = make_desc(sa, 1024u, 2u) + (uint64_t)(2 * k);
+      if (mode & 1) adesc |= (uint64_t)((sa >> 7) & 7u) << 49;
+      uint64_t bdesc = make_desc(base + a_bytes, 1024u, 2u) + (uint64_t)(2 * k);
+      umma_tf32(tmem_base, adesc, bdesc, idesc, k != 0 ? 1u : 0u);
+    }
+    umma_commit(done_bar);
+  }
+  __syncthreads();
+  mbar_wait(done_bar, 0);
+  tc_fence_after();
+  const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
+  for (int c = 0; c < N; c += 16) {
+    float v[16];
+    tmem_ld16(trow + (uint32_t)c, v);
+    for (int j = 0; j < 16; ++j) C[(size_t)(warp * 32 + lane) * N + c + j] = v[j];
+  }
+  tc_fence_before(); __syncthreads();
+  if (warp == 0) { __syncwarp(); tmem_dealloc(tmem_base, 256); }
 }
 
 // ------------------------------------------------------------------ host side
@@ -602,12 +857,93 @@ int launch_conv_umma_wgrad(const float* x, const float* dz, float* dwp, int N, i
   return 0;
 }
 
+
+static bool umma_patch_ok(int N, int D, int H, int W, int Cin, int Cout, int kd, int kh, int kw, int G) {
+  if (kh != 3 || kw != 3 || !(kd == 1 || kd == 3)) return false;
+  if (Cin % 32 != 0 || Cout % 4 != 0 || Cout < 4) return false;
+  if (W + 2 > 256 || (int64_t)H * W < 1024) return false;   // small images: a tile would be mostly padding -> plain kernel
+  if (G < 1 || N % G) return false;
+  (void)D;
+  return true;
+}
+
+int launch_conv_umma_patch(const float* x, const float* wp, const float* bias, const float* scale, const float* res, float* y, int N, int D, int H, int W,
+                           int Cin, int Cout, int kd, int G, int act, cudaStream_t st) {
+  PatchConvParams p;
+  p.N = N; p.D = D; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.kd = kd; p.G = G;
+  p.P = W + 2;
+  p.n_tiles = (int)ceil_div(Cout, 256);
+  p.BN = (int)(ceil_div(ceil_div(Cout, p.n_tiles), 16) * 16);
+  // two sub-tiles per weight stage when accumulators and shared memory allow; double-buffer the accumulators when they still fit
+  const uint32_t budget = 210u * 1024u;
+  const uint32_t b_al = (((uint32_t)p.BN * 128u) + 1023u) & ~1023u;
+  uint32_t patch_al = 0;
+  p.a_stages = 2;
+  bool fits = false;
+  for (p.MT = (2 * p.BN <= 512) ? 2 : 1; p.MT >= 1; --p.MT) {
+    const int span = 128 * p.MT + 2 * p.P + 2;
+    p.Rb = (int)ceil_div(p.P - 1 + span, p.P);
+    patch_al = (((uint32_t)p.Rb * p.P * 128u) + 1023u) & ~1023u;
+    if (2 * patch_al + 3 * b_al <= budget) { fits = true; break; }
+  }
+  if (!fits) return -1;
+  p.NBUF = (2 * p.MT * p.BN <= 512) ? 2 : 1;
+  const int tiles_per_img = (int)ceil_div((int64_t)H * p.P - 2, 128);
+  p.items_per_img = (int)ceil_div(tiles_per_img, p.MT);
+  p.total_items = (int64_t)p.n_tiles * N * D * p.items_per_img;
+  p.act = act; p.bias = bias; p.scale = scale; p.res = res; p.y = y;
+  int need_cols = p.NBUF * p.MT * p.BN;
+  p.tmem_cols = 32; while (p.tmem_cols < need_cols) p.tmem_cols <<= 1;
+  p.b_stages = (int)((budget - 2 * patch_al) / b_al);
+  if (p.b_stages > 8) p.b_stages = 8;
+  size_t smem = (size_t)p.a_stages * patch_al + (size_t)p.b_stages * b_al + 1024 + 8 * (2 * p.a_stages + 2 * p.b_stages + 6);
+  CUtensorMap tmA, tmB;
+  {
+    uint64_t dims[5] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)D, (uint64_t)N};
+    uint64_t str[4] = {(uint64_t)Cin * 4, (uint64_t)W * Cin * 4, (uint64_t)H * W * Cin * 4, (uint64_t)D * H * W * Cin * 4};
+    uint32_t box[5] = {32u, (uint32_t)p.P, (uint32_t)p.Rb, 1u, 1u};
+    int e = make_tmap(&tmA, x, 5, dims, str, box, 128);
+    if (e) return e;
+  }
+  {
+    const int taps = kd * 9;
+    uint64_t dims[3] = {(uint64_t)Cin, (uint64_t)Cout, (uint64_t)taps};
+    uint64_t str[2] = {(uint64_t)Cin * 4, (uint64_t)Cout * Cin * 4};
+    uint32_t box[3] = {32u, (uint32_t)p.BN, 1u};
+    int e = make_tmap(&tmB, wp, 3, dims, str, box, 128);
+    if (e) return e;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(conv_umma_patch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(226 * 1024)) != cudaSuccess) {
+      set_error("conv_umma_patch: cannot raise dynamic smem limit"); return 2;
+    }
+    attr_set = true;
+  }
+  int64_t grid = sm_count();
+  if (grid > p.total_items) grid = p.total_items;
+  conv_umma_patch_kernel<<<dim3((unsigned)grid), kUmmaThreads, smem, st>>>(tmA, tmB, p);
+  DGMR_CHECK_LAUNCH("conv_umma_patch");
+  return 0;
+}
+
 }  // namespace dgmr
 
 using namespace dgmr;
 
 extern "C" {
 
+int dgmr_debug_umma_shift(const float* A /*[256][32]*/, const float* B /*[N][32]*/, float* C /*[128][N]*/, int N, int r0, int mode, dgmr_stream_t stream) {
+  DGMR_REQUIRE(N % 16 == 0 && N >= 16 && N <= 256 && r0 >= 0 && r0 <= 128, "dgmr_debug_umma_shift: bad args");
+  CUtensorMap tmA, tmB;
+  { uint64_t dims[2] = {32, 256}; uint64_t str[1] = {128}; uint32_t box[2] = {32, 256}; int e = make_tmap(&tmA, A, 2, dims, str, box, 128); if (e) return e; }
+  { uint64_t dims[2] = {32, (uint64_t)N}; uint64_t str[1] = {128}; uint32_t box[2] = {32, (uint32_t)N}; int e = make_tmap(&tmB, B, 2, dims, str, box, 128); if (e) return e; }
+  size_t smem = 256 * 128 + ((size_t)N * 128 + 1023) / 1024 * 1024 + 1024 + 64;
+  if (cudaFuncSetAttribute(umma_shift_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { set_error("probe: smem attr"); return 2; }
+  umma_shift_probe_kernel<<<1, 128, smem, S(stream)>>>(tmA, tmB, C, N, r0, mode);
+  DGMR_CHECK_LAUNCH("umma_shift_probe");
+  return 0;
+}
 int dgmr_conv_umma_supported(int N, int D, int H, int W, int Cin, int Cout, int kd, int kh, int kw) {
   return umma_fwd_ok(N, D, H, W, Cin, Cout, kd, kh, kw, 1) ? 1 : 0;
 }
@@ -630,10 +966,16 @@ int dgmr_conv_fwd(const float* x, const float* x_lo, const float* wp, const floa
     DGMR_REQUIRE(ok && algo != DGMR_ALGO_SIMT, "dgmr_conv_fwd: ACCUMULATE is a tensor-core-path mode");
     return launch_conv_umma_fwd(x, wp, nullptr, scale, nullptr, y, N, D, H, W, Cin, Cout, kd, kh, kw, G, DGMR_ACT_NONE, S(stream), 1);
   }
-  if (algo == DGMR_ALGO_UMMA) DGMR_REQUIRE(ok, "dgmr_conv_fwd: shape not supported by the tcgen05 path");
+  if (algo == DGMR_ALGO_UMMA || algo == DGMR_ALGO_UMMA_PATCH) DGMR_REQUIRE(ok, "dgmr_conv_fwd: shape not supported by the tcgen05 path");
   DGMR_REQUIRE(precision == DGMR_PREC_TF32 || algo == DGMR_ALGO_SIMT || !ok, "dgmr_conv_fwd: 3xTF32 not implemented on the tcgen05 path yet");
-  if (algo == DGMR_ALGO_UMMA || (algo == DGMR_ALGO_AUTO && ok))
+  if (algo == DGMR_ALGO_UMMA || algo == DGMR_ALGO_UMMA_PATCH || (algo == DGMR_ALGO_AUTO && ok)) {
+    if (algo != DGMR_ALGO_UMMA && umma_patch_ok(N, D, H, W, Cin, Cout, kd, kh, kw, G)) {
+      int e = launch_conv_umma_patch(x, wp, bias, scale, res, y, N, D, H, W, Cin, Cout, kd, G, act, S(stream));
+      if (e >= 0) return e;   // -1: configuration does not fit in shared memory -> plain kernel
+    }
+    DGMR_REQUIRE(algo != DGMR_ALGO_UMMA_PATCH, "dgmr_conv_fwd: shape not supported by the halo-patch kernel");
     return launch_conv_umma_fwd(x, wp, bias, scale, res, y, N, D, H, W, Cin, Cout, kd, kh, kw, G, act, S(stream));
+  }
   return launch_conv_simt_fwd(x, wp, bias, scale, res, y, N, D, H, W, Cin, Cout, kd, kh, kw, G, act, S(stream));
 }
 

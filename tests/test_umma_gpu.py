@@ -117,3 +117,40 @@ def test_conv_umma_accumulate_mode(cuda_backend, shape):
     cuda_backend.conv_fwd(x.cuda(), wp.cuda(), None, scale.cuda(), None, y, n, d, h, w, cin, cout, kd, kh, kw, g, 512)
     torch.cuda.synchronize()
     assert (y.cpu() - y_ref).abs().max().item() <= 4e-3 * y_ref.abs().max().item()
+
+
+# N, D, H, W, Cin, Cout, kd, G
+PATCH_SHAPES = [
+    (2, 1, 32, 32, 32, 64, 1, 1),      # P=34
+    (3, 1, 64, 64, 96, 96, 1, 3),      # P=66, groups, odd batch
+    (2, 1, 128, 128, 96, 48, 1, 2),    # P=130, two sub-tiles per item, double-buffered accumulators
+    (2, 1, 32, 32, 384, 384, 1, 1),    # two N tiles of 192, single accumulator buffer
+    (1, 1, 64, 32, 64, 20, 1, 1),      # H != W, Cout not a multiple of 16
+    (2, 5, 32, 32, 96, 96, 3, 1),      # 3-D: 3 depth taps, odd depth
+    (1, 1, 40, 48, 32, 32, 1, 1),      # W not a power of two
+]
+
+
+@pytest.mark.parametrize("shape", PATCH_SHAPES)
+@pytest.mark.parametrize("variant", ["plain", "fused"])
+def test_conv_umma_patch(cuda_backend, shape, variant):
+    """Halo-patch persistent kernel (one activation patch feeds all 9 taps) vs fp32 emulator and the plain tcgen05 kernel."""
+    n, d, h, w, cin, cout, kd, g = shape
+    torch.manual_seed(14)
+    taps = kd * 9
+    x = torch.randn(n, d, h, w, cin)
+    wp = torch.randn(taps * cout * cin) / (taps * cin) ** 0.5
+    fused = variant == "fused"
+    bias = torch.randn(cout) if fused else None
+    scale = (torch.rand(g, cout) + 0.5) if fused else None
+    res = torch.randn(n, d, h, w, cout) if fused else None
+    act = 1 if fused else 0
+    y_ref = torch.empty(n, d, h, w, cout)
+    EmuBackend().conv_fwd(x, wp, bias, scale, res, y_ref, n, d, h, w, cin, cout, kd, 3, 3, g, act)
+    dev = lambda t: None if t is None else t.cuda()
+    y = torch.full((n, d, h, w, cout), float("nan"), device="cuda")
+    cuda_backend.conv_fwd(dev(x), dev(wp), dev(bias), dev(scale), dev(res), y, n, d, h, w, cin, cout, kd, 3, 3, g, act, algo=3)
+    torch.cuda.synchronize()
+    assert not torch.isnan(y).any(), "halo-patch kernel left outputs unwritten"
+    e = (y.cpu() - y_ref).abs().max().item()
+    assert e <= 4e-3 * max(y_ref.abs().max().item(), 1), f"halo-patch kernel err {e:.3e}"
