@@ -322,7 +322,8 @@ struct PatchConvParams {
   const float* bias; const float* scale; const float* res; float* y;
 };
 
-__global__ void __launch_bounds__(kUmmaThreads, 1)
+constexpr int kPatchThreads = 320;  // warp0 TMA, warp1 MMA, warps 2..9 epilogue
+__global__ void __launch_bounds__(kPatchThreads, 1)
 conv_umma_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const PatchConvParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -348,7 +349,7 @@ conv_umma_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
     for (int s = 0; s < p.a_stages; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1); }
     for (int s = 0; s < p.b_stages; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(acc_full(s), 1); mbar_init(acc_empty(s), 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(acc_full(s), 1); mbar_init(acc_empty(s), 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) { __syncwarp(); tmem_alloc(tmem_ptr_addr, (uint32_t)p.tmem_cols); }
@@ -437,8 +438,11 @@ conv_umma_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       }
     }
   } else {
-    // ===== epilogue warps
+    // ===== epilogue: 8 warps.  Warp group e = (warp-2)/4 takes sub-tile e (MT == 2) or column half e (MT == 1); inside a group
+    // warp w may only touch TMEM lanes [32*(w%4), +32).  Work proceeds in 32-column slabs with the 8 residual float4 loads of a
+    // slab issued before the TMEM reads so their latency overlaps (the epilogue is latency-, not bandwidth-bound).
     const int q = warp & 3;
+    const int eg = (warp - 2) >> 2;
     const int r = q * 32 + lane;
     const bool vec4 = (p.Cout & 3) == 0;
     uint32_t it = 0;
@@ -448,49 +452,55 @@ conv_umma_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       const int co0 = nt * p.BN;
       mbar_wait(acc_full(buf), phacc);
       tc_fence_after();
-      for (int mt = 0; mt < p.MT; ++mt) {
-        const int f = fs + 128 * mt + r;
-        const int hp = f / p.P, wp = f - hp * p.P;
-        const bool valid = (wp >= 1) && (wp <= p.W) && (hp >= 1) && (hp <= p.H);
-        const int64_t m = (((int64_t)n * p.D + d) * p.H + (hp - 1)) * p.W + (wp - 1);
-        const int g = n / (p.N / p.G);
-        const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((buf * p.MT + mt) * p.BN);
-        for (int c = 0; c < p.BN; c += 16) {
-          if (co0 + c >= p.Cout) break;
-          float v[16];
-          tmem_ld16(trow + (uint32_t)c, v);
-          if (!valid) continue;
+      const int mt = (p.MT == 2) ? eg : 0;
+      const int cbeg = (p.MT == 2) ? 0 : eg * ((p.BN / 2 + 31) / 32 * 32);
+      const int cend = (p.MT == 2) ? p.BN : (eg == 0 ? (p.BN / 2 + 31) / 32 * 32 : p.BN);
+      const int f = fs + 128 * mt + r;
+      const int hp = f / p.P, wp = f - hp * p.P;
+      const bool valid = (wp >= 1) && (wp <= p.W) && (hp >= 1) && (hp <= p.H);
+      const int64_t m = (((int64_t)n * p.D + d) * p.H + (hp - 1)) * p.W + (wp - 1);
+      const int g = n / (p.N / p.G);
+      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((buf * p.MT + mt) * p.BN);
+      const float* sc = p.scale ? p.scale + (int64_t)g * p.Cout : nullptr;
+      for (int c = cbeg; c < cend; c += 32) {
+        if (co0 + c >= p.Cout) break;
+        const bool second = (c + 16 < cend) && (co0 + c + 16 < p.Cout);
+        float4 rr[8];
+        const float* rp = (p.res && valid) ? p.res + m * p.Cout + co0 + c : nullptr;
+        if (rp && vec4) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int co = co0 + c + j;
-            if (co < p.Cout) {
-              float t = v[j];
-              if (p.scale) t *= __ldg(p.scale + (int64_t)g * p.Cout + co);
-              if (p.bias) t += __ldg(p.bias + co);
-              v[j] = t;
+          for (int j = 0; j < 8; ++j)
+            if (co0 + c + 4 * j < p.Cout && c + 4 * j < cend) rr[j] = *reinterpret_cast<const float4*>(rp + 4 * j);
+        }
+        float v[32];
+        tmem_ld16(trow + (uint32_t)c, v);
+        if (second) tmem_ld16(trow + (uint32_t)(c + 16), v + 16);
+        if (!valid) continue;
+        const int ncol = second ? 32 : 16;
+        float* yp = p.y + m * p.Cout + co0 + c;
+        if (vec4) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            if (4 * j < ncol && co0 + c + 4 * j < p.Cout) {
+              const int co = co0 + c + 4 * j;
+              float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+              if (sc) { float4 s4 = __ldg(reinterpret_cast<const float4*>(sc + co)); o.x *= s4.x; o.y *= s4.y; o.z *= s4.z; o.w *= s4.w; }
+              if (p.bias) { float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + co)); o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w; }
+              if (rp) { o.x += rr[j].x; o.y += rr[j].y; o.z += rr[j].z; o.w += rr[j].w; }
+              if (p.act == DGMR_ACT_RELU) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+              *reinterpret_cast<float4*>(yp + 4 * j) = o;
             }
           }
-          float* yp = p.y + m * p.Cout + co0 + c;
-          const float* rp = p.res ? p.res + m * p.Cout + co0 + c : nullptr;
-          if (vec4) {
-#pragma unroll
-            for (int j = 0; j < 16; j += 4) {
-              if (co0 + c + j < p.Cout) {
-                float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                if (rp) { float4 rr = *reinterpret_cast<const float4*>(rp + j); o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w; }
-                if (p.act == DGMR_ACT_RELU) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-                *reinterpret_cast<float4*>(yp + j) = o;
-              }
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              if (co0 + c + j < p.Cout) {
-                float o = v[j];
-                if (rp) o += rp[j];
-                if (p.act == DGMR_ACT_RELU) o = fmaxf(o, 0.f);
-                yp[j] = o;
-              }
+        } else {
+          for (int j = 0; j < ncol; ++j) {
+            const int co = co0 + c + j;
+            if (co < p.Cout) {
+              float o = v[j];
+              if (sc) o *= __ldg(sc + co);
+              if (p.bias) o += __ldg(p.bias + co);
+              if (rp) o += rp[j];
+              if (p.act == DGMR_ACT_RELU) o = fmaxf(o, 0.f);
+              yp[j] = o;
             }
           }
         }
@@ -867,6 +877,9 @@ static bool umma_patch_ok(int N, int D, int H, int W, int Cin, int Cout, int kd,
   return true;
 }
 
+// heuristic (AUTO only): persistent CTAs need a few tiles each to amortise their pipeline fill
+static bool umma_patch_profitable(int N, int D, int H, int W) { return (int64_t)N * D * H * W >= (int64_t)128 * 4 * sm_count(); }
+
 int launch_conv_umma_patch(const float* x, const float* wp, const float* bias, const float* scale, const float* res, float* y, int N, int D, int H, int W,
                            int Cin, int Cout, int kd, int G, int act, cudaStream_t st) {
   PatchConvParams p;
@@ -880,7 +893,8 @@ int launch_conv_umma_patch(const float* x, const float* wp, const float* bias, c
   uint32_t patch_al = 0;
   p.a_stages = 2;
   bool fits = false;
-  for (p.MT = (2 * p.BN <= 512) ? 2 : 1; p.MT >= 1; --p.MT) {
+  const int64_t tiles_total = (int64_t)p.n_tiles * N * D * ceil_div((int64_t)H * p.P - 2, 128);
+  for (p.MT = (2 * p.BN <= 512 && tiles_total >= 2 * (int64_t)sm_count()) ? 2 : 1; p.MT >= 1; --p.MT) {
     const int span = 128 * p.MT + 2 * p.P + 2;
     p.Rb = (int)ceil_div(p.P - 1 + span, p.P);
     patch_al = (((uint32_t)p.Rb * p.P * 128u) + 1023u) & ~1023u;
@@ -922,7 +936,7 @@ int launch_conv_umma_patch(const float* x, const float* wp, const float* bias, c
   }
   int64_t grid = sm_count();
   if (grid > p.total_items) grid = p.total_items;
-  conv_umma_patch_kernel<<<dim3((unsigned)grid), kUmmaThreads, smem, st>>>(tmA, tmB, p);
+  conv_umma_patch_kernel<<<dim3((unsigned)grid), kPatchThreads, smem, st>>>(tmA, tmB, p);
   DGMR_CHECK_LAUNCH("conv_umma_patch");
   return 0;
 }
@@ -969,7 +983,8 @@ int dgmr_conv_fwd(const float* x, const float* x_lo, const float* wp, const floa
   if (algo == DGMR_ALGO_UMMA || algo == DGMR_ALGO_UMMA_PATCH) DGMR_REQUIRE(ok, "dgmr_conv_fwd: shape not supported by the tcgen05 path");
   DGMR_REQUIRE(precision == DGMR_PREC_TF32 || algo == DGMR_ALGO_SIMT || !ok, "dgmr_conv_fwd: 3xTF32 not implemented on the tcgen05 path yet");
   if (algo == DGMR_ALGO_UMMA || algo == DGMR_ALGO_UMMA_PATCH || (algo == DGMR_ALGO_AUTO && ok)) {
-    if (algo != DGMR_ALGO_UMMA && umma_patch_ok(N, D, H, W, Cin, Cout, kd, kh, kw, G)) {
+    if (algo != DGMR_ALGO_UMMA && umma_patch_ok(N, D, H, W, Cin, Cout, kd, kh, kw, G) &&
+        (algo == DGMR_ALGO_UMMA_PATCH || umma_patch_profitable(N, D, H, W))) {
       int e = launch_conv_umma_patch(x, wp, bias, scale, res, y, N, D, H, W, Cin, Cout, kd, G, act, S(stream));
       if (e >= 0) return e;   // -1: configuration does not fit in shared memory -> plain kernel
     }

@@ -122,8 +122,8 @@ def test_conv_umma_accumulate_mode(cuda_backend, shape):
 # N, D, H, W, Cin, Cout, kd, G
 PATCH_SHAPES = [
     (2, 1, 32, 32, 32, 64, 1, 1),      # P=34
-    (3, 1, 64, 64, 96, 96, 1, 3),      # P=66, groups, odd batch
-    (2, 1, 128, 128, 96, 48, 1, 2),    # P=130, two sub-tiles per item, double-buffered accumulators
+    (9, 1, 64, 64, 96, 96, 1, 3),      # P=66, groups, odd batch, two sub-tiles per item
+    (4, 1, 128, 128, 96, 48, 1, 2),    # P=130, two sub-tiles per item, double-buffered accumulators
     (2, 1, 32, 32, 384, 384, 1, 1),    # two N tiles of 192, single accumulator buffer
     (1, 1, 64, 32, 64, 20, 1, 1),      # H != W, Cout not a multiple of 16
     (2, 5, 32, 32, 96, 96, 3, 1),      # 3-D: 3 depth taps, odd depth
