@@ -318,6 +318,7 @@ struct PatchConvParams {
   int a_stages, b_stages;
   int tmem_cols;
   int act;
+  int sb_vec;            // scale / bias pointers are 16-byte aligned (they may be views into a flat parameter buffer)
   int64_t total_items;   // n_tiles * N * D * items_per_img
   const float* bias; const float* scale; const float* res; float* y;
 };
@@ -484,8 +485,13 @@ conv_umma_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             if (4 * j < ncol && co0 + c + 4 * j < p.Cout) {
               const int co = co0 + c + 4 * j;
               float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-              if (sc) { float4 s4 = __ldg(reinterpret_cast<const float4*>(sc + co)); o.x *= s4.x; o.y *= s4.y; o.z *= s4.z; o.w *= s4.w; }
-              if (p.bias) { float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + co)); o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w; }
+              if (p.sb_vec) {
+                if (sc) { float4 s4 = __ldg(reinterpret_cast<const float4*>(sc + co)); o.x *= s4.x; o.y *= s4.y; o.z *= s4.z; o.w *= s4.w; }
+                if (p.bias) { float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + co)); o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w; }
+              } else {
+                if (sc) { o.x *= __ldg(sc + co); o.y *= __ldg(sc + co + 1); o.z *= __ldg(sc + co + 2); o.w *= __ldg(sc + co + 3); }
+                if (p.bias) { o.x += __ldg(p.bias + co); o.y += __ldg(p.bias + co + 1); o.z += __ldg(p.bias + co + 2); o.w += __ldg(p.bias + co + 3); }
+              }
               if (rp) { o.x += rr[j].x; o.y += rr[j].y; o.z += rr[j].z; o.w += rr[j].w; }
               if (p.act == DGMR_ACT_RELU) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
               *reinterpret_cast<float4*>(yp + 4 * j) = o;
@@ -906,6 +912,10 @@ int launch_conv_umma_patch(const float* x, const float* wp, const float* bias, c
   p.items_per_img = (int)ceil_div(tiles_per_img, p.MT);
   p.total_items = (int64_t)p.n_tiles * N * D * p.items_per_img;
   p.act = act; p.bias = bias; p.scale = scale; p.res = res; p.y = y;
+  p.sb_vec = (((reinterpret_cast<uintptr_t>(bias) | reinterpret_cast<uintptr_t>(scale)) & 15u) == 0) ? 1 : 0;
+  if (((reinterpret_cast<uintptr_t>(res) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(wp)) & 15u) != 0) {
+    set_error("conv_umma_patch: x / wp / res / y must be 16-byte aligned"); return 1;
+  }
   int need_cols = p.NBUF * p.MT * p.BN;
   p.tmem_cols = 32; while (p.tmem_cols < need_cols) p.tmem_cols <<= 1;
   p.b_stages = (int)((budget - 2 * patch_al) / b_al);

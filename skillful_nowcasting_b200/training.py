@@ -28,8 +28,9 @@ class Adam(torch.optim.Optimizer):
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps))
         self._params: List[torch.Tensor] = [p for g in self.param_groups for p in g["params"]]
         dev = self._params[0].device
-        n = sum(p.numel() for p in self._params)
-        self.flat_p = torch.empty(n, device=dev, dtype=torch.float32)
+        al = lambda k: (k + 63) // 64 * 64  # every parameter starts on a 256-byte boundary (vector loads, TMA); pads stay zero
+        n = sum(al(p.numel()) for p in self._params)
+        self.flat_p = torch.zeros(n, device=dev, dtype=torch.float32)
         self.flat_g = torch.zeros(n, device=dev, dtype=torch.float32)
         self.m = torch.zeros(n, device=dev, dtype=torch.float32)
         self.v = torch.zeros(n, device=dev, dtype=torch.float32)
@@ -40,7 +41,8 @@ class Adam(torch.optim.Optimizer):
                 self.flat_p[off:off + k].copy_(p.detach().reshape(-1))
                 p.data = self.flat_p[off:off + k].view(p.shape)
                 p.grad = self.flat_g[off:off + k].view(p.shape)
-                off += k
+                off += al(k)
+        self._al = al
         self.steps = 0
         self.process_group = process_group
 
@@ -51,7 +53,7 @@ class Adam(torch.optim.Optimizer):
             k = p.numel()
             if p.grad is None or p.grad.data_ptr() != self.flat_g.data_ptr() + 4 * off:
                 p.grad = self.flat_g[off:off + k].view(p.shape)
-            off += k
+            off += self._al(k)
 
     @torch.no_grad()
     def step(self, closure=None):
