@@ -112,7 +112,8 @@ int dgmr_bn_stats(const float* x, double* sums /*[G][C][2], zeroed inside*/, int
 int dgmr_bn_finalize(const double* sums, const float* gamma, const float* beta, float* running_mean,
                      float* running_var, int64_t rows, int G, int C, float eps, float momentum, int training,
                      float* mean, float* invstd, float* a, float* b, dgmr_stream_t stream);
-/* y = act(a[g,c]*x + b[g,c]); if up2: x is [G*Ng, H, W, C] and y is [G*Ng, 2H, 2W, C] (nearest). */
+/* y = act(a[g,c]*x + b[g,c]); if up2: x is [G*Ng, H, W, C] and y is [G*Ng, 2H, 2W, C] (nearest).
+ * relu | DGMR_FLAG_ROUND_TF32: y is written tf32-rounded (it feeds tensor-core convolutions only). */
 int dgmr_bn_apply(const float* x, const float* a, const float* b, float* y, int64_t rows, int G, int C,
                   int relu, int up2, int H, int W, dgmr_stream_t stream);
 /* red[g][c] = (sum dpre, sum dpre*xhat), dpre = dy*(y>0 if relu), dy pooled over the 2x2 replicas if up2 */

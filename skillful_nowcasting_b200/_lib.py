@@ -213,7 +213,7 @@ class CudaBackend:
                    _f32(invstd, "invstd"), _f32(a, "a"), _f32(b, "b"))
 
     def bn_apply(self, x, a, b, y, rows, G, C, relu, up2, H, W):
-        self._call("dgmr_bn_apply", _f32(x, "x"), _f32(a, "a"), _f32(b, "b"), _f32(y, "y"), rows, G, C, int(relu), int(up2), H, W)
+        self._call("dgmr_bn_apply", _f32(x, "x"), _f32(a, "a"), _f32(b, "b"), _f32(y, "y"), rows, G, C, int(relu), int(up2), H, W)  # relu may carry FLAG_ROUND_TF32
 
     def bn_bwd_reduce(self, dy, x, a, b, mean, invstd, red, rows, G, C, relu, up2, H, W):
         self._call("dgmr_bn_bwd_reduce", _f32(dy, "dy"), _f32(x, "x"), _f32(a, "a"), _f32(b, "b"), _f32(mean, "mean"),

@@ -52,9 +52,9 @@ class GBlock(nn.Module):
 
     def run(self, x, G: int = 1):
         sc = x if x.shape[-1] == self.output_channels else self.conv_1x1.run(x, G)
-        y = ops.mark_conv_only(self.bn1.run(x, G, relu=True))
+        y = ops.mark_conv_only(self.bn1.run(x, G, relu=True, conv_only=True))
         y = self.first_conv_3x3.run(y, G)
-        y = ops.mark_conv_only(self.bn2.run(y, G, relu=True))
+        y = ops.mark_conv_only(self.bn2.run(y, G, relu=True, conv_only=True))
         return self.last_conv_3x3.run(y, G, res=sc)  # residual add fused in the conv epilogue
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
@@ -81,9 +81,9 @@ class UpsampleGBlock(nn.Module):
     def run(self, x, G: int = 1):
         # conv1x1(up2(x)) == up2(conv1x1(x)) bit-for-bit (pointwise conv commutes with replication): 4x fewer MACs
         sc = ops.upsample2(self.conv_1x1.run(x, G))  # x also feeds BatchNorm: the conv rounds a private copy
-        y = ops.mark_conv_only(self.bn1.run(x, G, relu=True, up2=True))  # BN -> ReLU -> nearest x2 in one pass
+        y = ops.mark_conv_only(self.bn1.run(x, G, relu=True, up2=True, conv_only=True))  # BN -> ReLU -> nearest x2 in one pass
         y = self.first_conv_3x3.run(y, G)
-        y = ops.mark_conv_only(self.bn2.run(y, G, relu=True))
+        y = ops.mark_conv_only(self.bn2.run(y, G, relu=True, conv_only=True))
         return self.last_conv_3x3.run(y, G, res=sc)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:

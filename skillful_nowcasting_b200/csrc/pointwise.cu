@@ -26,6 +26,12 @@ int sm_count() {
   return n;
 }
 
+__device__ __forceinline__ float rna_tf32_pw(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
+
 // ------------------------------------------------------------------ permute
 struct PermuteArgs {
   int ndim;
@@ -290,7 +296,7 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, const float*
 }
 // y = act(a*x+b), optional nearest x2 upsample on write.  One thread per output element.
 __global__ void bn_apply_kernel(const float* __restrict__ x, const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ y,
-                                int64_t rows, int G, int C, int relu, int up2, int H, int W) {
+                                int64_t rows, int G, int C, int relu, int up2, int H, int W, int rnd) {
   int64_t orows = up2 ? rows * 4 : rows;
   int64_t total = (int64_t)G * orows * C;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -304,11 +310,12 @@ __global__ void bn_apply_kernel(const float* __restrict__ x, const float* __rest
       xr = (n * H + (ho >> 1)) * W + (wo >> 1);
     }
     float v = a[(int64_t)g * C + c] * x[xr * C + c] + b[(int64_t)g * C + c];
-    y[i] = relu ? fmaxf(v, 0.f) : v;
+    v = relu ? fmaxf(v, 0.f) : v;
+    y[i] = rnd ? rna_tf32_pw(v) : v;
   }
 }
 __global__ void bn_apply4_kernel(const float4* __restrict__ x, const float4* __restrict__ a, const float4* __restrict__ b, float4* __restrict__ y,
-                                 int64_t rows, int G, int C4, int relu, int up2, int H, int W) {
+                                 int64_t rows, int G, int C4, int relu, int up2, int H, int W, int rnd) {
   int64_t orows = up2 ? rows * 4 : rows;
   int64_t total = (int64_t)G * orows * C4;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -324,6 +331,7 @@ __global__ void bn_apply4_kernel(const float4* __restrict__ x, const float4* __r
     float4 aa = a[(int64_t)g * C4 + c], bb = b[(int64_t)g * C4 + c], u = x[xr * C4 + c];
     float4 v = make_float4(aa.x * u.x + bb.x, aa.y * u.y + bb.y, aa.z * u.z + bb.z, aa.w * u.w + bb.w);
     if (relu) v = make_float4(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f), fmaxf(v.z, 0.f), fmaxf(v.w, 0.f));
+    if (rnd) v = make_float4(rna_tf32_pw(v.x), rna_tf32_pw(v.y), rna_tf32_pw(v.z), rna_tf32_pw(v.w));
     y[i] = v;
   }
 }
@@ -390,6 +398,49 @@ __global__ void bn_bwd_apply_kernel(const float* __restrict__ dy, const float* _
       v = aa * (d - m1 - xh * m2);
     } else {
       v = aa * d;
+    }
+    dx[i] = v;
+  }
+}
+// float4 variant (C % 4 == 0): one thread per 4 channels of one low-res row
+__global__ void bn_bwd_apply4_kernel(const float* __restrict__ dy, const float4* __restrict__ x, const float4* __restrict__ a, const float4* __restrict__ b,
+                                     const float4* __restrict__ mean, const float4* __restrict__ invstd, const double* __restrict__ red, float4* __restrict__ dx,
+                                     int64_t rows, int G, int C4, int relu, int up2, int H, int W, int training) {
+  const int C = C4 * 4;
+  int64_t total = (int64_t)G * rows * C4;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int c4 = i % C4; int64_t r = i / C4; int g = r / rows;
+    int64_t o4 = (int64_t)g * C4 + c4;
+    float4 aa = a[o4], bb = b[o4], xv = x[i];
+    float4 d;
+    if (up2) {
+      int w = r % W; int64_t t = r / W; int h = t % H; int64_t n = t / H;
+      const float4* p0 = reinterpret_cast<const float4*>(dy + ((n * 2 * H + 2 * h) * (2 * (int64_t)W) + 2 * w) * C) + c4;
+      const float4* p1 = p0 + (int64_t)2 * W * C4;
+      float4 q0 = p0[0], q1 = p0[C4], q2 = p1[0], q3 = p1[C4];
+      d = make_float4(q0.x + q1.x + q2.x + q3.x, q0.y + q1.y + q2.y + q3.y, q0.z + q1.z + q2.z + q3.z, q0.w + q1.w + q2.w + q3.w);
+    } else {
+      d = reinterpret_cast<const float4*>(dy)[i];
+    }
+    if (relu) {
+      if (!(aa.x * xv.x + bb.x > 0.f)) d.x = 0.f;
+      if (!(aa.y * xv.y + bb.y > 0.f)) d.y = 0.f;
+      if (!(aa.z * xv.z + bb.z > 0.f)) d.z = 0.f;
+      if (!(aa.w * xv.w + bb.w > 0.f)) d.w = 0.f;
+    }
+    float4 v;
+    if (training) {
+      float4 m = mean[o4], is = invstd[o4];
+      const double inv = 1.0 / (double)rows;
+      const double* rp = red + o4 * 8;
+      float m1x = (float)(rp[0] * inv), m2x = (float)(rp[1] * inv), m1y = (float)(rp[2] * inv), m2y = (float)(rp[3] * inv);
+      float m1z = (float)(rp[4] * inv), m2z = (float)(rp[5] * inv), m1w = (float)(rp[6] * inv), m2w = (float)(rp[7] * inv);
+      v.x = aa.x * (d.x - m1x - (xv.x - m.x) * is.x * m2x);
+      v.y = aa.y * (d.y - m1y - (xv.y - m.y) * is.y * m2y);
+      v.z = aa.z * (d.z - m1z - (xv.z - m.z) * is.z * m2z);
+      v.w = aa.w * (d.w - m1w - (xv.w - m.w) * is.w * m2w);
+    } else {
+      v = make_float4(aa.x * d.x, aa.y * d.y, aa.z * d.z, aa.w * d.w);
     }
     dx[i] = v;
   }
@@ -714,13 +765,15 @@ int dgmr_bn_finalize(const double* sums, const float* gamma, const float* beta, 
   return 0;
 }
 int dgmr_bn_apply(const float* x, const float* a, const float* b, float* y, int64_t rows, int G, int C, int relu, int up2, int H, int W, dgmr_stream_t stream) {
+  const int rnd = (relu & DGMR_FLAG_ROUND_TF32) ? 1 : 0;   // output feeds tensor-core convs only: emit tf32-rounded values directly
+  relu &= ~DGMR_FLAG_ROUND_TF32;
   int64_t total = (int64_t)G * rows * C * (up2 ? 4 : 1);
   if (total == 0) return 0;
   DGMR_REQUIRE(!up2 || (rows % ((int64_t)H * W) == 0), "dgmr_bn_apply: rows not a multiple of H*W");
   if (C % 4 == 0 && al16(x) && al16(y) && al16(a) && al16(b))
-    bn_apply4_kernel<<<ew_grid(total / 4, 256, 1), 256, 0, S(stream)>>>((const float4*)x, (const float4*)a, (const float4*)b, (float4*)y, rows, G, C / 4, relu, up2, H, W);
+    bn_apply4_kernel<<<ew_grid(total / 4, 256, 1), 256, 0, S(stream)>>>((const float4*)x, (const float4*)a, (const float4*)b, (float4*)y, rows, G, C / 4, relu, up2, H, W, rnd);
   else
-    bn_apply_kernel<<<ew_grid(total, 256, 2), 256, 0, S(stream)>>>(x, a, b, y, rows, G, C, relu, up2, H, W);
+    bn_apply_kernel<<<ew_grid(total, 256, 2), 256, 0, S(stream)>>>(x, a, b, y, rows, G, C, relu, up2, H, W, rnd);
   DGMR_CHECK_LAUNCH("dgmr_bn_apply");
   return 0;
 }
@@ -739,7 +792,11 @@ int dgmr_bn_bwd_apply(const float* dy, const float* x, const float* a, const flo
   (void)gamma;
   int64_t total = (int64_t)G * rows * C;
   if (dx && total) {
-    bn_bwd_apply_kernel<<<ew_grid(total, 256, 2), 256, 0, S(stream)>>>(dy, x, a, b, mean, invstd, red, dx, rows, G, C, relu, up2, H, W, training);
+    if (C % 4 == 0 && al16(dy) && al16(x) && al16(dx) && al16(a) && al16(b) && al16(mean) && al16(invstd))
+      bn_bwd_apply4_kernel<<<ew_grid(total / 4, 256, 1), 256, 0, S(stream)>>>(dy, (const float4*)x, (const float4*)a, (const float4*)b, (const float4*)mean,
+                                                                               (const float4*)invstd, red, (float4*)dx, rows, G, C / 4, relu, up2, H, W, training);
+    else
+      bn_bwd_apply_kernel<<<ew_grid(total, 256, 2), 256, 0, S(stream)>>>(dy, x, a, b, mean, invstd, red, dx, rows, G, C, relu, up2, H, W, training);
     DGMR_CHECK_LAUNCH("dgmr_bn_bwd_apply");
   }
   if (dgamma || dbeta) {

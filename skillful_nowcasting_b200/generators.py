@@ -71,7 +71,7 @@ class Sampler(nn.Module, PyTorchModelHubMixin):
             hs = c11.run(ops.mark_conv_only(hs), T)
             hs = g.run(hs, T)
             hs = ug.run(hs, T)
-        hs = ops.mark_conv_only(self.bn.run(hs, T, relu=True))
+        hs = ops.mark_conv_only(self.bn.run(hs, T, relu=True, conv_only=True))
         hs = self.conv_1x1.run(hs, T)  # [T*B,1,h,w,4*Co]
         _, _, h, w, c4 = hs.shape
         co = c4 // 4

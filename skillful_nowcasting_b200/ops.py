@@ -612,7 +612,7 @@ class _BatchNorm(Function):
     (ref: dgmr/common.py:74-82,145-153; generators.py:176)."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, rmean, rvar, G, training, relu_, up2, eps, momentum):
+    def forward(ctx, x, gamma, beta, rmean, rvar, G, training, relu_, up2, eps, momentum, conv_only=False):
         be = _be()
         x = _c(x)
         n, d, h, w, c = x.shape
@@ -625,7 +625,10 @@ class _BatchNorm(Function):
         mean, invstd, a, b = (_new((G, c), x) for _ in range(4))
         be.bn_finalize(sums, gamma, beta, rmean, rvar, rows, G, c, eps, momentum, training, mean, invstd, a, b)
         y = _new((n, d, 2 * h, 2 * w, c) if up2 else (n, d, h, w, c), x)
-        be.bn_apply(x, a, b, y, rows, G, c, relu_, up2, h, w)
+        rnd = conv_only and config.round_tf32 and config.conv_algo != ALGO_SIMT and be.name == "cuda"
+        be.bn_apply(x, a, b, y, rows, G, c, int(relu_) | (FLAG_ROUND_TF32 if rnd else 0), up2, h, w)
+        if rnd:
+            y._dgmr_tf32 = True
         ctx.save_for_backward(x, gamma, a, b, mean, invstd)
         ctx.meta = (G, training, relu_, up2)
         return y
@@ -644,11 +647,12 @@ class _BatchNorm(Function):
         dgamma = _new((c,), x) if (gamma is not None and ctx.needs_input_grad[1]) else None
         dbeta = _new((c,), x) if (gamma is not None and ctx.needs_input_grad[2]) else None
         be.bn_bwd_apply(dy, x, a, b, mean, invstd, gamma, red, dx, dgamma, dbeta, False, rows, G, c, relu_, up2, h, w, training)
-        return dx, dgamma, dbeta, None, None, None, None, None, None, None, None
+        return dx, dgamma, dbeta, None, None, None, None, None, None, None, None, None
 
 
-def batch_norm(x, gamma, beta, rmean, rvar, G, training, relu_=False, up2=False, eps=1e-5, momentum=0.1):
-    return _BatchNorm.apply(x, gamma, beta, rmean, rvar, G, training, relu_, up2, eps, momentum)
+def batch_norm(x, gamma, beta, rmean, rvar, G, training, relu_=False, up2=False, eps=1e-5, momentum=0.1, conv_only=False):
+    """conv_only: the result is consumed by convolutions only, so it may be emitted tf32-rounded straight away."""
+    return _BatchNorm.apply(x, gamma, beta, rmean, rvar, G, training, relu_, up2, eps, momentum, conv_only)
 
 
 # ----------------------------------------------------------------------------- ConvGRU gate arithmetic

@@ -144,9 +144,12 @@ class EmuBackend:
         return x.reshape(G, rows, C)
 
     def bn_apply(self, x, a, b, y, rows, G, C, relu, up2, H, W):
+        rnd, relu = bool(int(relu) & 256), int(relu) & ~256
         v = x.reshape(G, rows, C) * a.reshape(G, 1, C) + b.reshape(G, 1, C)
         if relu:
             v = torch.relu(v)
+        if rnd:
+            v = self._rna_tf32(v)
         if up2:
             v = v.reshape(-1, H, W, C).repeat_interleave(2, 1).repeat_interleave(2, 2)
         y.copy_(v.reshape(y.shape))

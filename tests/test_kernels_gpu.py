@@ -95,6 +95,7 @@ def test_batchnorm(cuda_backend, G, rows, C, relu, up2):
     EmuBackend().bn_finalize(sums, gamma, beta, rm, rv, rows, G, C, 1e-5, 0.1, True, mean, invstd, a, b)
     y = torch.empty(G * rows * (4 if up2 else 1), C)
     _both("bn_apply", [x, a, b, y, rows, G, C, relu, up2, H, W], cuda_backend, atol=1e-6)
+    _both("bn_apply", [x, a, b, y, rows, G, C, int(relu) | 256, up2, H, W], cuda_backend, rtol=6e-4, atol=1e-6)  # tf32-rounded output
     dy = torch.randn_like(y)
     red = torch.zeros(G, C, 2, dtype=torch.float64)
     _both("bn_bwd_reduce", [dy, x, a, b, mean, invstd, red, rows, G, C, relu, up2, H, W], cuda_backend, rtol=1e-4, atol=1e-4)
