@@ -653,6 +653,126 @@ conv_umma_wgrad_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_co
   if (warp == 0) { __syncwarp(); tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols); }
 }
 
+// ------------------------------------------------------------------ wgrad, row variant (3 taps per CTA)
+// The plain wgrad kernel handles one filter tap per CTA and therefore reads dz and x nine times.  Here a K block is a run
+// of 32 output pixels of ONE image row; the x operand is loaded as a 34-pixel patch (1-pixel halo each side, TMA zero fill)
+// and the three taps kw = 0,1,2 of a filter row are three MMAs whose B descriptors start 0, 1, 2 rows into that patch; the dz
+// tile is shared by the three.  3 accumulators of BN columns in TMEM.  L2->SM traffic per tap drops ~3x.
+struct WgradRowParams {
+  int N, D, H, W, Cin, Cout, kd, kh;
+  int BN, ci_tiles, b_blocks;
+  int stages, tmem_cols;
+  int kb_total, kb_chunk, wsegs;
+  float* dwp;
+};
+constexpr uint32_t kRowPatchPitch = 36u * 128u;   // 34 patch rows, padded to a multiple of the 512-byte swizzle period
+
+__global__ void __launch_bounds__(kUmmaThreads, 1)
+conv_umma_wgrad_row_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_constant__ CUtensorMap tmX, const WgradRowParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t a_bytes = 4u * 4096u;                                   // 4 co blocks x [32 px][32 co]
+  const uint32_t b_span = (uint32_t)p.b_blocks * kRowPatchPitch;
+  const uint32_t stage_bytes = a_bytes + ((b_span + 1023u) & ~1023u);
+  const uint32_t tx_bytes = a_bytes + (uint32_t)p.b_blocks * 34u * 128u;
+  const uint32_t bar_base = base + p.stages * stage_bytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (p.stages + s); };
+  const uint32_t tmem_full_bar = bar_base + 8u * (2 * p.stages);
+  const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * p.stages + 1);
+  volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_addr - raw));
+
+  const int trow_i = blockIdx.y;                 // (kd, kh) filter row
+  const int tkh = trow_i % p.kh, tkd = trow_i / p.kh;
+  const int co0 = (blockIdx.z / p.ci_tiles) * 128, ci0 = (blockIdx.z % p.ci_tiles) * p.BN;
+  const int kb0 = blockIdx.x * p.kb_chunk;
+  const int kb1 = min(kb0 + p.kb_chunk, p.kb_total);
+  const int num_kb = kb1 - kb0;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmDz) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
+    for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    mbar_init(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) { __syncwarp(); tmem_alloc(tmem_ptr_addr, (uint32_t)p.tmem_cols); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_gen;
+
+  if (warp == 0) {
+    if (lane == 0 && num_kb > 0) {
+      int s = 0; uint32_t ph = 0;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        int t = kb;
+        const int ws = t % p.wsegs; t /= p.wsegs;
+        const int h = t % p.H; t /= p.H;
+        const int d = t % p.D; const int n = t / p.D;
+        const int w0 = ws * 32;
+        mbar_wait(empty_bar(s), ph ^ 1u);
+        mbar_expect_tx(full_bar(s), tx_bytes);
+        const uint32_t sa = base + s * stage_bytes;
+        for (int j = 0; j < 4; ++j) tma_load_5d(sa + j * 4096u, &tmDz, full_bar(s), co0 + j * 32, w0, h, d, n);
+        for (int j = 0; j < p.b_blocks; ++j)
+          tma_load_5d(sa + a_bytes + j * kRowPatchPitch, &tmX, full_bar(s), ci0 + j * 32, w0 - 1, h + tkh - p.kh / 2, d + tkd - p.kd / 2, n);
+        if (++s == p.stages) { s = 0; ph ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && num_kb > 0) {
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(p.BN >> 3) << 17) | ((128u >> 4) << 24);
+      auto mn_desc = [&](uint32_t saddr, uint32_t lbo) {
+        uint64_t d = 0;
+        d |= (uint64_t)((saddr >> 4) & 0x3FFFu);
+        d |= (uint64_t)((lbo >> 4) & 0x3FFFu) << 16;
+        d |= (uint64_t)((512u >> 4) & 0x3FFFu) << 32;   // SBO: next 4-row K atom
+        d |= (uint64_t)1u << 46;
+        d |= (uint64_t)1u << 61;                        // SWIZZLE_128B_BASE32B
+        return d;
+      };
+      int s = 0; uint32_t ph = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(full_bar(s), ph);
+        tc_fence_after();
+        const uint32_t sa = base + s * stage_bytes;
+        for (int dw = 0; dw < 3; ++dw)
+          for (int k = 0; k < 4; ++k)
+            umma_tf32(tmem_base + (uint32_t)(dw * p.BN), mn_desc(sa + k * 1024u, 4096u), mn_desc(sa + a_bytes + (uint32_t)(dw + 8 * k) * 128u, kRowPatchPitch),
+                      idesc, (kb | k) != 0 ? 1u : 0u);
+        umma_commit(empty_bar(s));
+        if (++s == p.stages) { s = 0; ph ^= 1u; }
+      }
+      umma_commit(tmem_full_bar);
+    }
+  } else if (num_kb > 0) {
+    const int q = warp & 3;
+    const int co = co0 + q * 32 + lane;
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    for (int dw = 0; dw < 3; ++dw) {
+      const int tap = trow_i * 3 + dw;
+      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(dw * p.BN);
+      for (int c = 0; c < p.BN; c += 16) {
+        if (ci0 + c >= p.Cin) break;
+        float v[16];
+        tmem_ld16(trow + (uint32_t)c, v);
+        if (co >= p.Cout) continue;
+        float* dst = p.dwp + ((int64_t)tap * p.Cout + co) * p.Cin + ci0 + c;
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (ci0 + c + j < p.Cin) atomicAdd(dst + j, v[j]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { __syncwarp(); tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols); }
+}
+
 // ------------------------------------------------------------------ descriptor probe (debug entry point)
 // C[128][N] = A[r0 : r0+128][0:32] . B[N][0:32]^T with A a 256-row K-major SWIZZLE_128B tile loaded by ONE TMA: validates
 // that a tcgen05 A descriptor may start at an arbitrary 128-byte row of a swizzled tile (needed to reuse one halo'd
@@ -951,6 +1071,67 @@ int launch_conv_umma_patch(const float* x, const float* wp, const float* bias, c
   return 0;
 }
 
+
+static bool umma_wgrad_row_ok(int N, int D, int H, int W, int Cin, int Cout, int kd, int kh, int kw) {
+  (void)N; (void)D; (void)H;
+  if (kw != 3 || !(kh == 1 || kh == 3) || !(kd == 1 || kd == 3)) return false;
+  if (W % 32 != 0 || Cin % 4 != 0 || Cout % 4 != 0) return false;
+  return true;
+}
+
+int launch_conv_umma_wgrad_row(const float* x, const float* dz, float* dwp, int N, int D, int H, int W, int Cin, int Cout, int kd, int kh, cudaStream_t st) {
+  WgradRowParams p;
+  p.N = N; p.D = D; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.kd = kd; p.kh = kh;
+  p.ci_tiles = (int)ceil_div(Cin, 160);
+  p.BN = (int)(ceil_div(ceil_div(Cin, p.ci_tiles), 32) * 32);
+  p.b_blocks = p.BN / 32;
+  p.tmem_cols = 32; while (p.tmem_cols < 3 * p.BN) p.tmem_cols <<= 1;
+  const uint32_t stage_bytes = 4u * 4096u + (((uint32_t)p.b_blocks * kRowPatchPitch + 1023u) & ~1023u);
+  int stages = (int)((200u * 1024u) / stage_bytes);
+  if (stages > 6) stages = 6;
+  if (stages < 2) { set_error("conv_umma_wgrad_row: stage too large"); return 1; }
+  p.stages = stages;
+  size_t smem = (size_t)stages * stage_bytes + 1024 + 8 * (2 * stages + 2);
+  const int taps = kd * kh * 3;
+  const int co_tiles = (int)ceil_div(Cout, 128);
+  p.wsegs = W / 32;
+  p.kb_total = N * D * H * p.wsegs;
+  int64_t base_ctas = (int64_t)kd * kh * co_tiles * p.ci_tiles;
+  int64_t ksplit = ceil_div((int64_t)sm_count() * 2, base_ctas);
+  if (ksplit > p.kb_total / 8) ksplit = p.kb_total / 8;
+  if (ksplit < 1) ksplit = 1;
+  p.kb_chunk = (int)ceil_div(p.kb_total, ksplit);
+  ksplit = ceil_div(p.kb_total, p.kb_chunk);
+  p.dwp = dwp;
+  CUtensorMap tmDz, tmX;
+  {
+    uint64_t dims[5] = {(uint64_t)Cout, (uint64_t)W, (uint64_t)H, (uint64_t)D, (uint64_t)N};
+    uint64_t str[4] = {(uint64_t)Cout * 4, (uint64_t)W * Cout * 4, (uint64_t)H * W * Cout * 4, (uint64_t)D * H * W * Cout * 4};
+    uint32_t box[5] = {32u, 32u, 1u, 1u, 1u};
+    int e = make_tmap(&tmDz, dz, 5, dims, str, box, 128, true);
+    if (e) return e;
+  }
+  {
+    uint64_t dims[5] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)D, (uint64_t)N};
+    uint64_t str[4] = {(uint64_t)Cin * 4, (uint64_t)W * Cin * 4, (uint64_t)H * W * Cin * 4, (uint64_t)D * H * W * Cin * 4};
+    uint32_t box[5] = {32u, 34u, 1u, 1u, 1u};
+    int e = make_tmap(&tmX, x, 5, dims, str, box, 128, true);
+    if (e) return e;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(conv_umma_wgrad_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)) != cudaSuccess) {
+      set_error("conv_umma_wgrad_row: cannot raise dynamic smem limit"); return 2;
+    }
+    attr_set = true;
+  }
+  if (cudaMemsetAsync(dwp, 0, sizeof(float) * (size_t)taps * Cout * Cin, st) != cudaSuccess) { set_error("conv_umma_wgrad_row: memset failed"); return 2; }
+  dim3 grid((unsigned)ksplit, (unsigned)(kd * kh), (unsigned)(co_tiles * p.ci_tiles));
+  conv_umma_wgrad_row_kernel<<<grid, kUmmaThreads, smem, st>>>(tmDz, tmX, p);
+  DGMR_CHECK_LAUNCH("conv_umma_wgrad_row");
+  return 0;
+}
+
 }  // namespace dgmr
 
 using namespace dgmr;
@@ -1009,7 +1190,10 @@ int dgmr_conv_wgrad(const float* x, const float* dz, const float* xT, const floa
   (void)xT; (void)dzT; (void)xT_lo; (void)dzT_lo; (void)precision;  // MN-major tiles come straight from x / dz: no transposed copies needed
   DGMR_REQUIRE(N > 0 && D > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, "dgmr_conv_wgrad: bad dims");
   bool ok = umma_wgrad_ok(N, D, H, W, Cin, Cout, kd, kh, kw);
-  if (algo == DGMR_ALGO_UMMA) DGMR_REQUIRE(ok, "dgmr_conv_wgrad: shape not supported by the tcgen05 path");
+  if (algo == DGMR_ALGO_UMMA || algo == DGMR_ALGO_UMMA_PATCH) DGMR_REQUIRE(ok, "dgmr_conv_wgrad: shape not supported by the tcgen05 path");
+  if (algo == DGMR_ALGO_UMMA_PATCH) DGMR_REQUIRE(umma_wgrad_row_ok(N, D, H, W, Cin, Cout, kd, kh, kw), "dgmr_conv_wgrad: shape not supported by the row kernel");
+  if (algo == DGMR_ALGO_UMMA_PATCH || (algo == DGMR_ALGO_AUTO && ok && umma_wgrad_row_ok(N, D, H, W, Cin, Cout, kd, kh, kw) && (int64_t)N * D * H * W >= 16384))
+    return launch_conv_umma_wgrad_row(x, dz, dwp, N, D, H, W, Cin, Cout, kd, kh, S(stream));
   if (algo == DGMR_ALGO_UMMA || (algo == DGMR_ALGO_AUTO && ok))
     return launch_conv_umma_wgrad(x, dz, dwp, N, D, H, W, Cin, Cout, kd, kh, kw, S(stream));
   return launch_conv_simt_wgrad(x, dz, dwp, N, D, H, W, Cin, Cout, kd, kh, kw, S(stream));

@@ -154,3 +154,32 @@ def test_conv_umma_patch(cuda_backend, shape, variant):
     assert not torch.isnan(y).any(), "halo-patch kernel left outputs unwritten"
     e = (y.cpu() - y_ref).abs().max().item()
     assert e <= 4e-3 * max(y_ref.abs().max().item(), 1), f"halo-patch kernel err {e:.3e}"
+
+
+# N, D, H, W, Cin, Cout, kd, kh
+WGRAD_ROW_SHAPES = [
+    (4, 1, 32, 32, 32, 64, 1, 3),
+    (2, 1, 64, 64, 96, 96, 1, 3),      # M tile 128 > Cout, BN = 96 (3 patch blocks)
+    (2, 1, 32, 64, 192, 48, 1, 3),     # two ci tiles of 96, W > H
+    (2, 1, 128, 128, 48, 24, 1, 3),    # channel tails inside a 32-channel block
+    (2, 4, 32, 32, 48, 96, 3, 3),      # 3-D
+    (1, 1, 32, 32, 768, 384, 1, 3),    # 5 ci tiles of 160, 3 co tiles
+    (2, 1, 32, 32, 8, 48, 1, 3),       # zero-padded 8-channel input
+]
+
+
+@pytest.mark.parametrize("shape", WGRAD_ROW_SHAPES)
+def test_wgrad_umma_row(cuda_backend, shape):
+    """Row variant: the three kw taps of a filter row share one dz tile and one 34-pixel x patch (shifted B descriptors)."""
+    n, d, h, w, cin, cout, kd, kh = shape
+    torch.manual_seed(15)
+    taps = kd * kh * 3
+    x, dz = torch.randn(n, d, h, w, cin), torch.randn(n, d, h, w, cout)
+    ref = torch.empty(taps * cout * cin)
+    EmuBackend().conv_wgrad(x, dz, ref, n, d, h, w, cin, cout, kd, kh, 3)
+    g = torch.full((taps * cout * cin,), float("nan"), device="cuda")
+    cuda_backend.conv_wgrad(x.cuda(), dz.cuda(), g, n, d, h, w, cin, cout, kd, kh, 3, algo=3)
+    torch.cuda.synchronize()
+    assert not torch.isnan(g).any()
+    e = (g.cpu() - ref).abs().max().item()
+    assert e <= 4e-3 * ref.abs().max().item(), f"row wgrad err {e:.3e} (ref max {ref.abs().max().item():.3e})"
