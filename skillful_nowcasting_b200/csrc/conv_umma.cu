@@ -311,6 +311,7 @@ conv_umma_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 struct PatchConvParams {
   int N, D, H, W, Cin, Cout, kd, G;
   int P, Rb;             // padded pitch W+2, padded rows per patch
+  int BK;                // channels per chunk: 32 (128-byte rows) or 16 (64-byte rows)
   int MT;                // 128-row sub-tiles per work item (1 or 2)
   int NBUF;              // accumulator buffers (1 or 2)
   int items_per_img;     // ceil(tiles_per_img / MT)
@@ -330,9 +331,10 @@ conv_umma_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t patch_bytes = (uint32_t)p.Rb * p.P * 128u;
+  const uint32_t row_bytes = (uint32_t)p.BK * 4u;
+  const uint32_t patch_bytes = (uint32_t)p.Rb * p.P * row_bytes;
   const uint32_t patch_al = (patch_bytes + 1023u) & ~1023u;
-  const uint32_t b_bytes = (uint32_t)p.BN * 128u;
+  const uint32_t b_bytes = (uint32_t)p.BN * row_bytes;
   const uint32_t b_al = (b_bytes + 1023u) & ~1023u;
   const uint32_t a_base = base, b_base = base + p.a_stages * patch_al;
   const uint32_t bar_base = b_base + p.b_stages * b_al;
@@ -359,7 +361,7 @@ conv_umma_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_gen;
 
-  const int chunks = p.Cin / 32;
+  const int chunks = p.Cin / p.BK;
   const int a_per_item = p.kd * chunks;       // activation patches per work item
   // work item -> (n_tile, image n, depth d, first flattened output fs)
   auto decode = [&](int64_t item, int& nt, int& n, int& d, int& fs) {
@@ -387,7 +389,7 @@ conv_umma_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         const int sa = ai % p.a_stages; const uint32_t pha = (ai / p.a_stages) & 1u; ++ai;
         mbar_wait(a_empty(sa), pha ^ 1u);
         mbar_expect_tx(a_full(sa), patch_bytes);
-        tma_load_5d(a_base + sa * patch_al, &tmA, a_full(sa), q.c * 32, -1, r_lo - 1, d + q.kdi - p.kd / 2, n);
+        tma_load_5d(a_base + sa * patch_al, &tmA, a_full(sa), q.c * p.BK, -1, r_lo - 1, d + q.kdi - p.kd / 2, n);
       };
       Cur ca{(int64_t)blockIdx.x, 0, 0}, cb = ca;
       if (valid(ca)) { issue_patch(ca); advance(ca); }
@@ -398,7 +400,7 @@ conv_umma_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           const int sb = bi % p.b_stages; const uint32_t phb = (bi / p.b_stages) & 1u; ++bi;
           mbar_wait(b_empty(sb), phb ^ 1u);
           mbar_expect_tx(b_full(sb), b_bytes);
-          tma_load_3d(b_base + sb * b_al, &tmB, b_full(sb), cb.c * 32, nt * p.BN, cb.kdi * 9 + tap);
+          tma_load_3d(b_base + sb * b_al, &tmB, b_full(sb), cb.c * p.BK, nt * p.BN, cb.kdi * 9 + tap);
         }
         advance(cb);
       }
@@ -407,6 +409,8 @@ conv_umma_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     if (lane == 0) {
       // ===== MMA issuer
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((128u >> 4) << 24);
+      const uint32_t layout = row_bytes == 128 ? 2u : 4u;
+      const int ksteps = p.BK / 8;
       uint32_t ai = 0, bi = 0, it = 0;
       for (int64_t item = blockIdx.x; item < p.total_items; item += gridDim.x, ++it) {
         int nt, n, d, fs; decode(item, nt, n, d, fs);
@@ -425,10 +429,10 @@ conv_umma_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             tc_fence_after();
             const int th = tap / 3, tw = tap - th * 3;
             const int j0 = fs + (th - 1) * p.P + (tw - 1) - r_lo * p.P;     // first patch row this tap reads (>= 0)
-            const uint64_t bdesc = make_desc(b_base + sb * b_al, 1024u, 2u);
+            const uint64_t bdesc = make_desc(b_base + sb * b_al, 8u * row_bytes, layout);
             for (int mt = 0; mt < p.MT; ++mt) {
-              const uint64_t adesc = make_desc(patch + (uint32_t)(j0 + 128 * mt) * 128u, 1024u, 2u);
-              for (int k = 0; k < 4; ++k)
+              const uint64_t adesc = make_desc(patch + (uint32_t)(j0 + 128 * mt) * row_bytes, 8u * row_bytes, layout);
+              for (int k = 0; k < ksteps; ++k)
                 umma_tf32(tacc + (uint32_t)(mt * p.BN), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (a | tap | k) != 0 ? 1u : 0u);
             }
             umma_commit(b_empty(sb));
@@ -996,26 +1000,37 @@ int launch_conv_umma_wgrad(const float* x, const float* dz, float* dwp, int N, i
 
 static bool umma_patch_ok(int N, int D, int H, int W, int Cin, int Cout, int kd, int kh, int kw, int G) {
   if (kh != 3 || kw != 3 || !(kd == 1 || kd == 3)) return false;
-  if (Cin % 32 != 0 || Cout % 4 != 0 || Cout < 4) return false;
-  if (W + 2 > 256 || (int64_t)H * W < 1024) return false;   // small images: a tile would be mostly padding -> plain kernel
+  if (Cin % 16 != 0 || Cout % 4 != 0 || Cout < 4) return false;
+  if (W + 2 > 256 || (int64_t)H * W < 256) return false;    // tiny images: a tile would be mostly padding -> plain kernel
   if (G < 1 || N % G) return false;
   (void)D;
   return true;
 }
 
 // heuristic (AUTO only): persistent CTAs need a few tiles each to amortise their pipeline fill
-static bool umma_patch_profitable(int N, int D, int H, int W) { return (int64_t)N * D * H * W >= (int64_t)128 * 4 * sm_count(); }
+static bool umma_patch_profitable(int N, int D, int H, int W) { return (int64_t)N * D * H * W >= (int64_t)128 * 32; }
 
 int launch_conv_umma_patch(const float* x, const float* wp, const float* bias, const float* scale, const float* res, float* y, int N, int D, int H, int W,
                            int Cin, int Cout, int kd, int G, int act, cudaStream_t st) {
   PatchConvParams p;
   p.N = N; p.D = D; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.kd = kd; p.G = G;
   p.P = W + 2;
+  p.BK = (Cin % 32 == 0) ? 32 : 16;
+  const uint32_t row_bytes = (uint32_t)p.BK * 4u;
   p.n_tiles = (int)ceil_div(Cout, 256);
+  {
+    // small problems: split Cout over more CTAs so that the weight traffic (the same for every M tile) is spread over the SMs
+    const int64_t m_items = (int64_t)N * D * ceil_div((int64_t)H * p.P - 2, 128);
+    int want = (int)ceil_div((int64_t)sm_count(), m_items);
+    int max_nt = Cout / 32 > 0 ? Cout / 32 : 1;
+    if (want > max_nt) want = max_nt;
+    if (want > p.n_tiles) p.n_tiles = want;
+  }
   p.BN = (int)(ceil_div(ceil_div(Cout, p.n_tiles), 16) * 16);
+  p.n_tiles = (int)ceil_div(Cout, p.BN);
   // two sub-tiles per weight stage when accumulators and shared memory allow; double-buffer the accumulators when they still fit
   const uint32_t budget = 210u * 1024u;
-  const uint32_t b_al = (((uint32_t)p.BN * 128u) + 1023u) & ~1023u;
+  const uint32_t b_al = (((uint32_t)p.BN * row_bytes) + 1023u) & ~1023u;
   uint32_t patch_al = 0;
   p.a_stages = 2;
   bool fits = false;
@@ -1023,7 +1038,7 @@ int launch_conv_umma_patch(const float* x, const float* wp, const float* bias, c
   for (p.MT = (2 * p.BN <= 512 && tiles_total >= 2 * (int64_t)sm_count()) ? 2 : 1; p.MT >= 1; --p.MT) {
     const int span = 128 * p.MT + 2 * p.P + 2;
     p.Rb = (int)ceil_div(p.P - 1 + span, p.P);
-    patch_al = (((uint32_t)p.Rb * p.P * 128u) + 1023u) & ~1023u;
+    patch_al = (((uint32_t)p.Rb * p.P * row_bytes) + 1023u) & ~1023u;
     if (2 * patch_al + 3 * b_al <= budget) { fits = true; break; }
   }
   if (!fits) return -1;
@@ -1045,16 +1060,16 @@ int launch_conv_umma_patch(const float* x, const float* wp, const float* bias, c
   {
     uint64_t dims[5] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)D, (uint64_t)N};
     uint64_t str[4] = {(uint64_t)Cin * 4, (uint64_t)W * Cin * 4, (uint64_t)H * W * Cin * 4, (uint64_t)D * H * W * Cin * 4};
-    uint32_t box[5] = {32u, (uint32_t)p.P, (uint32_t)p.Rb, 1u, 1u};
-    int e = make_tmap(&tmA, x, 5, dims, str, box, 128);
+    uint32_t box[5] = {(uint32_t)p.BK, (uint32_t)p.P, (uint32_t)p.Rb, 1u, 1u};
+    int e = make_tmap(&tmA, x, 5, dims, str, box, (int)row_bytes);
     if (e) return e;
   }
   {
     const int taps = kd * 9;
     uint64_t dims[3] = {(uint64_t)Cin, (uint64_t)Cout, (uint64_t)taps};
     uint64_t str[2] = {(uint64_t)Cin * 4, (uint64_t)Cout * Cin * 4};
-    uint32_t box[3] = {32u, (uint32_t)p.BN, 1u};
-    int e = make_tmap(&tmB, wp, 3, dims, str, box, 128);
+    uint32_t box[3] = {(uint32_t)p.BK, (uint32_t)p.BN, 1u};
+    int e = make_tmap(&tmB, wp, 3, dims, str, box, (int)row_bytes);
     if (e) return e;
   }
   static bool attr_set = false;

@@ -128,6 +128,10 @@ PATCH_SHAPES = [
     (1, 1, 64, 32, 64, 20, 1, 1),      # H != W, Cout not a multiple of 16
     (2, 5, 32, 32, 96, 96, 3, 1),      # 3-D: 3 depth taps, odd depth
     (1, 1, 40, 48, 32, 32, 1, 1),      # W not a power of two
+    (4, 1, 64, 64, 48, 48, 1, 1),      # Cin = 48: 16-channel chunks (64-byte rows)
+    (2, 6, 32, 32, 48, 96, 3, 1),      # same, 3-D
+    (16, 1, 16, 16, 192, 192, 1, 1),   # small images (ConvGRU step): Cout split over more CTAs
+    (16, 1, 32, 32, 96, 96, 1, 1),
 ]
 
 
