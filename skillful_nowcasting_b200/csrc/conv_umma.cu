@@ -147,13 +147,14 @@ struct UmmaConvParams {
 
 constexpr int kUmmaThreads = 192;  // warp0 TMA, warp1 MMA, warps 2..5 epilogue
 
+template <int BK>
 __global__ void __launch_bounds__(kUmmaThreads, 1)
 conv_umma_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const UmmaConvParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024-B alignment
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t a_bytes = 128u * p.BK * 4u, b_bytes = (uint32_t)p.BN * p.BK * 4u;
+  const uint32_t a_bytes = 128u * BK * 4u, b_bytes = (uint32_t)p.BN * BK * 4u;
   const uint32_t b_bytes_al = (b_bytes + 1023u) & ~1023u;
   const uint32_t stage_bytes = a_bytes + b_bytes_al;
   const uint32_t bar_base = base + p.stages * stage_bytes;  // full[stages], empty[stages], tmem_full, tmem_ptr
@@ -172,7 +173,7 @@ conv_umma_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   const int w0 = tw_i * p.bw, h0 = th_i * p.bh;
   const int co0 = blockIdx.y * p.BN;
   const int taps = p.kd * p.kh * p.kw;
-  const int kchunks = p.Cin / p.BK;
+  const int kchunks = p.Cin / BK;
   const int tap_begin = p.split_taps ? (int)blockIdx.z : 0;
   const int num_kb = (p.split_taps ? 1 : taps) * kchunks;
 
@@ -197,7 +198,7 @@ conv_umma_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       // ===== TMA producer
       int s = 0; uint32_t ph = 0;
       for (int kb = 0; kb < num_kb; ++kb) {
-        const int tapl = kb / kchunks, c0 = (kb - tapl * kchunks) * p.BK;
+        const int tapl = kb / kchunks, c0 = (kb - tapl * kchunks) * BK;
         const int tap = tap_begin + tapl;
         const int tkw = tap % p.kw, tkh = (tap / p.kw) % p.kh, tkd = tap / (p.kw * p.kh);
         mbar_wait(empty_bar(s), ph ^ 1u);
@@ -212,7 +213,7 @@ conv_umma_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     if (lane == 0) {
       // ===== MMA issuer
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((128u >> 4) << 24);
-      const uint32_t row_bytes = p.BK * 4u;
+      const uint32_t row_bytes = BK * 4u;
       const uint32_t layout = row_bytes == 128 ? 2u : (row_bytes == 64 ? 4u : 6u);
       const uint32_t sbo = 8u * row_bytes;
       int s = 0; uint32_t ph = 0;
@@ -222,10 +223,11 @@ conv_umma_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         const uint32_t sa = base + s * stage_bytes;
         const uint64_t adesc = make_desc(sa, sbo, layout);
         const uint64_t bdesc = make_desc(sa + a_bytes, sbo, layout);
-        for (int k = 0; k < p.BK / 8; ++k) {
-          // advance 8 tf32 = 32 bytes along K inside the swizzle row: +2 in the (addr>>4) field
-          umma_tf32(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
-        }
+        // advance 8 tf32 = 32 bytes along K inside the swizzle row: +2 in the (addr>>4) field.  Fully unrolled: the single
+        // issuing thread must spend far fewer cycles per MMA than the MMA itself takes (N/2 cycles).
+        umma_tf32(tmem_base, adesc, bdesc, idesc, kb != 0 ? 1u : 0u);
+#pragma unroll
+        for (int k = 1; k < BK / 8; ++k) umma_tf32(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, 1u);
         umma_commit(empty_bar(s));
         if (++s == p.stages) { s = 0; ph ^= 1u; }
       }
@@ -325,13 +327,14 @@ struct PatchConvParams {
 };
 
 constexpr int kPatchThreads = 320;  // warp0 TMA, warp1 MMA, warps 2..9 epilogue
+template <int BK, int MT>
 __global__ void __launch_bounds__(kPatchThreads, 1)
 conv_umma_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const PatchConvParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t row_bytes = (uint32_t)p.BK * 4u;
+  const uint32_t row_bytes = (uint32_t)BK * 4u;
   const uint32_t patch_bytes = (uint32_t)p.Rb * p.P * row_bytes;
   const uint32_t patch_al = (patch_bytes + 1023u) & ~1023u;
   const uint32_t b_bytes = (uint32_t)p.BN * row_bytes;
@@ -361,7 +364,7 @@ conv_umma_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_gen;
 
-  const int chunks = p.Cin / p.BK;
+  const int chunks = p.Cin / BK;
   const int a_per_item = p.kd * chunks;       // activation patches per work item
   // work item -> (n_tile, image n, depth d, first flattened output fs)
   auto decode = [&](int64_t item, int& nt, int& n, int& d, int& fs) {
@@ -370,7 +373,7 @@ conv_umma_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     d = (int)(t % p.D); t /= p.D;
     n = (int)(t % p.N); t /= p.N;
     nt = (int)t;
-    fs = p.P + 1 + 128 * p.MT * ii;
+    fs = p.P + 1 + 128 * MT * ii;
   };
 
   if (warp == 0) {
@@ -389,7 +392,7 @@ conv_umma_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         const int sa = ai % p.a_stages; const uint32_t pha = (ai / p.a_stages) & 1u; ++ai;
         mbar_wait(a_empty(sa), pha ^ 1u);
         mbar_expect_tx(a_full(sa), patch_bytes);
-        tma_load_5d(a_base + sa * patch_al, &tmA, a_full(sa), q.c * p.BK, -1, r_lo - 1, d + q.kdi - p.kd / 2, n);
+        tma_load_5d(a_base + sa * patch_al, &tmA, a_full(sa), q.c * BK, -1, r_lo - 1, d + q.kdi - p.kd / 2, n);
       };
       Cur ca{(int64_t)blockIdx.x, 0, 0}, cb = ca;
       if (valid(ca)) { issue_patch(ca); advance(ca); }
@@ -400,7 +403,7 @@ conv_umma_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           const int sb = bi % p.b_stages; const uint32_t phb = (bi / p.b_stages) & 1u; ++bi;
           mbar_wait(b_empty(sb), phb ^ 1u);
           mbar_expect_tx(b_full(sb), b_bytes);
-          tma_load_3d(b_base + sb * b_al, &tmB, b_full(sb), cb.c * p.BK, nt * p.BN, cb.kdi * 9 + tap);
+          tma_load_3d(b_base + sb * b_al, &tmB, b_full(sb), cb.c * BK, nt * p.BN, cb.kdi * 9 + tap);
         }
         advance(cb);
       }
@@ -409,8 +412,10 @@ conv_umma_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     if (lane == 0) {
       // ===== MMA issuer
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((128u >> 4) << 24);
-      const uint32_t layout = row_bytes == 128 ? 2u : 4u;
-      const int ksteps = p.BK / 8;
+      constexpr uint32_t layout = (BK == 32) ? 2u : 4u;
+      constexpr int ksteps = BK / 8;
+      const uint64_t adesc0 = make_desc(a_base, 8u * row_bytes, layout);
+      const uint64_t bdesc0 = make_desc(b_base, 8u * row_bytes, layout);
       uint32_t ai = 0, bi = 0, it = 0;
       for (int64_t item = blockIdx.x; item < p.total_items; item += gridDim.x, ++it) {
         int nt, n, d, fs; decode(item, nt, n, d, fs);
@@ -418,22 +423,27 @@ conv_umma_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         const int buf = it % p.NBUF; const uint32_t phacc = (it / p.NBUF) & 1u;
         mbar_wait(acc_empty(buf), phacc ^ 1u);
         tc_fence_after();
-        const uint32_t tacc = tmem_base + (uint32_t)(buf * p.MT * p.BN);
+        const uint32_t tacc = tmem_base + (uint32_t)(buf * MT * p.BN);
         for (int a = 0; a < a_per_item; ++a) {
           const int sa = ai % p.a_stages; const uint32_t pha = (ai / p.a_stages) & 1u; ++ai;
           mbar_wait(a_full(sa), pha);
-          const uint32_t patch = a_base + sa * patch_al;
           for (int tap = 0; tap < 9; ++tap) {
             const int sb = bi % p.b_stages; const uint32_t phb = (bi / p.b_stages) & 1u; ++bi;
             mbar_wait(b_full(sb), phb);
             tc_fence_after();
             const int th = tap / 3, tw = tap - th * 3;
             const int j0 = fs + (th - 1) * p.P + (tw - 1) - r_lo * p.P;     // first patch row this tap reads (>= 0)
-            const uint64_t bdesc = make_desc(b_base + sb * b_al, 8u * row_bytes, layout);
-            for (int mt = 0; mt < p.MT; ++mt) {
-              const uint64_t adesc = make_desc(patch + (uint32_t)(j0 + 128 * mt) * row_bytes, 8u * row_bytes, layout);
+            // descriptors differ from the per-stage base only in their 14-bit start-address field: one add each.
+            // Fully unrolled: the single issuing thread must spend far fewer cycles per MMA than the MMA takes (N/2 cycles).
+            const uint64_t bdesc = bdesc0 + (uint64_t)((sb * b_al) >> 4);
+            const uint64_t adesc = adesc0 + (uint64_t)((sa * patch_al + (uint32_t)j0 * row_bytes) >> 4);
+            const uint32_t acc0 = (a | tap) != 0 ? 1u : 0u;
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
               for (int k = 0; k < ksteps; ++k)
-                umma_tf32(tacc + (uint32_t)(mt * p.BN), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (a | tap | k) != 0 ? 1u : 0u);
+                umma_tf32(tacc + (uint32_t)(mt * p.BN), adesc + (uint64_t)(mt * 128 * (BK * 4 / 16) + 2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                          k == 0 ? acc0 : 1u);
             }
             umma_commit(b_empty(sb));
           }
@@ -457,15 +467,15 @@ conv_umma_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       const int co0 = nt * p.BN;
       mbar_wait(acc_full(buf), phacc);
       tc_fence_after();
-      const int mt = (p.MT == 2) ? eg : 0;
-      const int cbeg = (p.MT == 2) ? 0 : eg * ((p.BN / 2 + 31) / 32 * 32);
-      const int cend = (p.MT == 2) ? p.BN : (eg == 0 ? (p.BN / 2 + 31) / 32 * 32 : p.BN);
+      const int mt = (MT == 2) ? eg : 0;
+      const int cbeg = (MT == 2) ? 0 : eg * ((p.BN / 2 + 31) / 32 * 32);
+      const int cend = (MT == 2) ? p.BN : (eg == 0 ? (p.BN / 2 + 31) / 32 * 32 : p.BN);
       const int f = fs + 128 * mt + r;
       const int hp = f / p.P, wp = f - hp * p.P;
       const bool valid = (wp >= 1) && (wp <= p.W) && (hp >= 1) && (hp <= p.H);
       const int64_t m = (((int64_t)n * p.D + d) * p.H + (hp - 1)) * p.W + (wp - 1);
       const int g = n / (p.N / p.G);
-      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((buf * p.MT + mt) * p.BN);
+      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((buf * MT + mt) * p.BN);
       const float* sc = p.scale ? p.scale + (int64_t)g * p.Cout : nullptr;
       for (int c = cbeg; c < cend; c += 32) {
         if (co0 + c >= p.Cout) break;
@@ -894,16 +904,20 @@ int launch_conv_umma_fwd(const float* x, const float* wp, const float* bias, con
     int e = make_tmap(&tmB, wp, 3, dims, str, box, p.BK * 4);
     if (e) return e;
   }
-  static size_t smem_set = 0;
-  if (smem > smem_set) {
-    if (cudaFuncSetAttribute(conv_umma_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)) != cudaSuccess) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(conv_umma_fwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)) != cudaSuccess ||
+        cudaFuncSetAttribute(conv_umma_fwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)) != cudaSuccess ||
+        cudaFuncSetAttribute(conv_umma_fwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)) != cudaSuccess) {
       set_error("conv_umma_fwd: cannot raise dynamic smem limit"); return 2;
     }
-    smem_set = 220 * 1024;
+    attr_set = true;
   }
   int64_t mtiles = (int64_t)(N / p.bn) * D * p.tiles_h * p.tiles_w;
   dim3 grid((unsigned)mtiles, (unsigned)ntiles, (unsigned)(accumulate ? taps : 1));
-  conv_umma_fwd_kernel<<<grid, kUmmaThreads, smem, st>>>(tmA, tmB, p);
+  if (p.BK == 32) conv_umma_fwd_kernel<32><<<grid, kUmmaThreads, smem, st>>>(tmA, tmB, p);
+  else if (p.BK == 16) conv_umma_fwd_kernel<16><<<grid, kUmmaThreads, smem, st>>>(tmA, tmB, p);
+  else conv_umma_fwd_kernel<8><<<grid, kUmmaThreads, smem, st>>>(tmA, tmB, p);
   DGMR_CHECK_LAUNCH("conv_umma_fwd");
   return 0;
 }
@@ -1008,7 +1022,9 @@ static bool umma_patch_ok(int N, int D, int H, int W, int Cin, int Cout, int kd,
 }
 
 // heuristic (AUTO only): persistent CTAs need a few tiles each to amortise their pipeline fill
-static bool umma_patch_profitable(int N, int D, int H, int W) { return (int64_t)N * D * H * W >= (int64_t)128 * 32; }
+static bool umma_patch_profitable(int N, int D, int H, int W, int Cin) {
+  return Cin % 32 == 0 && (int64_t)H * W >= 1024 && (int64_t)N * D * H * W >= (int64_t)128 * 4 * sm_count();
+}
 
 int launch_conv_umma_patch(const float* x, const float* wp, const float* bias, const float* scale, const float* res, float* y, int N, int D, int H, int W,
                            int Cin, int Cout, int kd, int G, int act, cudaStream_t st) {
@@ -1074,14 +1090,22 @@ int launch_conv_umma_patch(const float* x, const float* wp, const float* bias, c
   }
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(conv_umma_patch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(226 * 1024)) != cudaSuccess) {
+    const int lim = 226 * 1024;
+    if (cudaFuncSetAttribute(conv_umma_patch_kernel<32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim) != cudaSuccess ||
+        cudaFuncSetAttribute(conv_umma_patch_kernel<32, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim) != cudaSuccess ||
+        cudaFuncSetAttribute(conv_umma_patch_kernel<16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim) != cudaSuccess ||
+        cudaFuncSetAttribute(conv_umma_patch_kernel<16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim) != cudaSuccess) {
       set_error("conv_umma_patch: cannot raise dynamic smem limit"); return 2;
     }
     attr_set = true;
   }
   int64_t grid = sm_count();
   if (grid > p.total_items) grid = p.total_items;
-  conv_umma_patch_kernel<<<dim3((unsigned)grid), kPatchThreads, smem, st>>>(tmA, tmB, p);
+  const dim3 g((unsigned)grid);
+  if (p.BK == 32 && p.MT == 2) conv_umma_patch_kernel<32, 2><<<g, kPatchThreads, smem, st>>>(tmA, tmB, p);
+  else if (p.BK == 32) conv_umma_patch_kernel<32, 1><<<g, kPatchThreads, smem, st>>>(tmA, tmB, p);
+  else if (p.MT == 2) conv_umma_patch_kernel<16, 2><<<g, kPatchThreads, smem, st>>>(tmA, tmB, p);
+  else conv_umma_patch_kernel<16, 1><<<g, kPatchThreads, smem, st>>>(tmA, tmB, p);
   DGMR_CHECK_LAUNCH("conv_umma_patch");
   return 0;
 }
@@ -1190,7 +1214,7 @@ int dgmr_conv_fwd(const float* x, const float* x_lo, const float* wp, const floa
   DGMR_REQUIRE(precision == DGMR_PREC_TF32 || algo == DGMR_ALGO_SIMT || !ok, "dgmr_conv_fwd: 3xTF32 not implemented on the tcgen05 path yet");
   if (algo == DGMR_ALGO_UMMA || algo == DGMR_ALGO_UMMA_PATCH || (algo == DGMR_ALGO_AUTO && ok)) {
     if (algo != DGMR_ALGO_UMMA && umma_patch_ok(N, D, H, W, Cin, Cout, kd, kh, kw, G) &&
-        (algo == DGMR_ALGO_UMMA_PATCH || umma_patch_profitable(N, D, H, W))) {
+        (algo == DGMR_ALGO_UMMA_PATCH || umma_patch_profitable(N, D, H, W, Cin))) {
       int e = launch_conv_umma_patch(x, wp, bias, scale, res, y, N, D, H, W, Cin, Cout, kd, G, act, S(stream));
       if (e >= 0) return e;   // -1: configuration does not fit in shared memory -> plain kernel
     }
