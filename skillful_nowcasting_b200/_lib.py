@@ -205,7 +205,7 @@ class CudaBackend:
 
     # -- BatchNorm
     def bn_stats(self, x, sums, rows, G, C):
-        self._call("dgmr_bn_stats", _f32(x, "x"), _f64(sums, "sums"), rows, G, C)
+        self._call("dgmr_bn_stats", _f32(x, "x"), _f64(sums, "sums"), rows, G, C, _flops=4.0 * rows * G * C, _info=f"rows{rows} G{G} C{C} (GB/s)")
 
     def bn_finalize(self, sums, gamma, beta, rmean, rvar, rows, G, C, eps, momentum, training, mean, invstd, a, b):
         self._call("dgmr_bn_finalize", _f64(sums, "sums"), _f32(gamma, "gamma"), _f32(beta, "beta"), _f32(rmean, "running_mean"),
@@ -213,7 +213,8 @@ class CudaBackend:
                    _f32(invstd, "invstd"), _f32(a, "a"), _f32(b, "b"))
 
     def bn_apply(self, x, a, b, y, rows, G, C, relu, up2, H, W):
-        self._call("dgmr_bn_apply", _f32(x, "x"), _f32(a, "a"), _f32(b, "b"), _f32(y, "y"), rows, G, C, int(relu), int(up2), H, W)  # relu may carry FLAG_ROUND_TF32
+        self._call("dgmr_bn_apply", _f32(x, "x"), _f32(a, "a"), _f32(b, "b"), _f32(y, "y"), rows, G, C, int(relu), int(up2), H, W,  # relu may carry FLAG_ROUND_TF32
+                   _flops=4.0 * rows * G * C * (5 if up2 else 2), _info=f"rows{rows} G{G} C{C} up{int(up2)} (GB/s)")
 
     def bn_bwd_reduce(self, dy, x, a, b, mean, invstd, red, rows, G, C, relu, up2, H, W):
         self._call("dgmr_bn_bwd_reduce", _f32(dy, "dy"), _f32(x, "x"), _f32(a, "a"), _f32(b, "b"), _f32(mean, "mean"),
@@ -262,9 +263,10 @@ class CudaBackend:
                    _info=f"{N}x{D}x{H}x{W} {Cin}->{Cout} k{kd}{kh}{kw} G{G}")
 
     def conv_bwd_prep(self, dy, y, res, bias, scale, dz, dpre, dbias, dscale, rows, G, Cout, act, accumulate_dbias=False):
+        nb = sum(t is not None for t in (dy, y, res, dz, dpre)) * 4.0 * rows * G * Cout   # bytes moved (profile only)
         self._call("dgmr_conv_bwd_prep", _f32(dy, "dy"), _f32(y, "y"), _f32(res, "res"), _f32(bias, "bias"), _f32(scale, "scale"),
                    _f32(dz, "dz"), _f32(dpre, "dpre"), _f32(dbias, "dbias"), _f32(dscale, "dscale"), rows, G, Cout, act,
-                   int(accumulate_dbias))
+                   int(accumulate_dbias), _flops=nb, _info=f"rows{rows} G{G} C{Cout} (GB/s)")
 
     def conv_wgrad(self, x, dz, dwp, N, D, H, W, Cin, Cout, kd, kh, kw, algo=ALGO_AUTO, precision=PREC_TF32, xT=None, dzT=None,
                    xT_lo=None, dzT_lo=None):
