@@ -15,6 +15,7 @@
 //   * mbarrier full/empty ring between TMA and MMA; tcgen05.commit frees stages and signals the epilogue.
 #include "common.cuh"
 #include <cuda.h>
+#include <stdlib.h>
 
 namespace dgmr {
 
@@ -1051,7 +1052,9 @@ int launch_conv_umma_patch(const float* x, const float* wp, const float* bias, c
   p.a_stages = 2;
   bool fits = false;
   const int64_t tiles_total = (int64_t)p.n_tiles * N * D * ceil_div((int64_t)H * p.P - 2, 128);
-  for (p.MT = (2 * p.BN <= 512 && tiles_total >= 2 * (int64_t)sm_count()) ? 2 : 1; p.MT >= 1; --p.MT) {
+  int mt_start = (2 * p.BN <= 512 && tiles_total >= 2 * (int64_t)sm_count()) ? 2 : 1;
+  if (const char* e = getenv("DGMR_PATCH_MT")) { int v = atoi(e); if (v == 1 || (v == 2 && 2 * p.BN <= 512)) mt_start = v; }   // tuning knob
+  for (p.MT = mt_start; p.MT >= 1; --p.MT) {
     const int span = 128 * p.MT + 2 * p.P + 2;
     p.Rb = (int)ceil_div(p.P - 1 + span, p.P);
     patch_al = (((uint32_t)p.Rb * p.P * row_bytes) + 1023u) & ~1023u;
