@@ -323,6 +323,7 @@ struct PatchConvParams {
   int tmem_cols;
   int act;
   int sb_vec;            // scale / bias pointers are 16-byte aligned (they may be views into a flat parameter buffer)
+  int dbg;               // tuning only (DGMR_PATCH_DBG): 1 = epilogue skips global traffic, 2 = issuer skips the MMAs
   int64_t total_items;   // n_tiles * N * D * items_per_img
   const float* bias; const float* scale; const float* res; float* y;
 };
@@ -350,6 +351,7 @@ conv_umma_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   auto acc_empty = [&](int s) { return bar_base + 8u * (2 * p.a_stages + 2 * p.b_stages + 2 + s); };
   const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * p.a_stages + 2 * p.b_stages + 4);
   volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_addr - raw));
+  const uint32_t epi_base = (tmem_ptr_addr + 8u + 127u) & ~127u;     // 8 epilogue warps x 2 KB transpose staging
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -439,6 +441,7 @@ conv_umma_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             const uint64_t bdesc = bdesc0 + (uint64_t)((sb * b_al) >> 4);
             const uint64_t adesc = adesc0 + (uint64_t)((sa * patch_al + (uint32_t)j0 * row_bytes) >> 4);
             const uint32_t acc0 = (a | tap) != 0 ? 1u : 0u;
+            if (!(p.dbg & 2))
 #pragma unroll
             for (int mt = 0; mt < MT; ++mt) {
 #pragma unroll
@@ -455,76 +458,84 @@ conv_umma_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     }
   } else {
     // ===== epilogue: 8 warps.  Warp group e = (warp-2)/4 takes sub-tile e (MT == 2) or column half e (MT == 1); inside a group
-    // warp w may only touch TMEM lanes [32*(w%4), +32).  Work proceeds in 32-column slabs with the 8 residual float4 loads of a
-    // slab issued before the TMEM reads so their latency overlaps (the epilogue is latency-, not bandwidth-bound).
+    // warp w may only touch TMEM lanes [32*(w%4), +32).  tcgen05.ld hands each lane one accumulator ROW; writing y (and reading
+    // the residual) that way touches 32 different lines per instruction with half-used sectors, which the profile showed as 3x
+    // L1->L2 write amplification on a kernel that is bound by the L2<->SM fabric.  So every 16-column chunk is transposed through
+    // a 2 KB per-warp staging tile: afterwards 4 adjacent lanes own 64 contiguous bytes of one row (whole sectors both ways).
     const int q = warp & 3;
     const int eg = (warp - 2) >> 2;
-    const int r = q * 32 + lane;
-    const bool vec4 = (p.Cout & 3) == 0;
+    const uint32_t stg = epi_base + (uint32_t)(warp - 2) * 2048u;
+    const int lr = lane >> 2, lc = lane & 3;
+    const uint32_t st_row = stg + (uint32_t)lane * 64u;
+    const uint32_t st_sw = (uint32_t)((lane >> 1) & 3);
     uint32_t it = 0;
     for (int64_t item = blockIdx.x; item < p.total_items; item += gridDim.x, ++it) {
       int nt, n, d, fs; decode(item, nt, n, d, fs);
       const int buf = it % p.NBUF; const uint32_t phacc = (it / p.NBUF) & 1u;
       const int co0 = nt * p.BN;
-      mbar_wait(acc_full(buf), phacc);
-      tc_fence_after();
       const int mt = (MT == 2) ? eg : 0;
-      const int cbeg = (MT == 2) ? 0 : eg * ((p.BN / 2 + 31) / 32 * 32);
-      const int cend = (MT == 2) ? p.BN : (eg == 0 ? (p.BN / 2 + 31) / 32 * 32 : p.BN);
-      const int f = fs + 128 * mt + r;
-      const int hp = f / p.P, wp = f - hp * p.P;
-      const bool valid = (wp >= 1) && (wp <= p.W) && (hp >= 1) && (hp <= p.H);
-      const int64_t m = (((int64_t)n * p.D + d) * p.H + (hp - 1)) * p.W + (wp - 1);
+      const int cbeg = (MT == 2) ? 0 : eg * ((p.BN / 2 + 15) / 16 * 16);
+      const int cend = (MT == 2) ? p.BN : (eg == 0 ? (p.BN / 2 + 15) / 16 * 16 : p.BN);
+      int64_t mrow[4]; bool vrow[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int f = fs + 128 * mt + q * 32 + lr + 8 * j;
+        const int hp = f / p.P, wp = f - hp * p.P;
+        vrow[j] = (wp >= 1) && (wp <= p.W) && (hp >= 1) && (hp <= p.H) && !(p.dbg & 1);
+        mrow[j] = ((((int64_t)n * p.D + d) * p.H + (hp - 1)) * p.W + (wp - 1)) * p.Cout + co0 + 4 * lc;
+      }
       const int g = n / (p.N / p.G);
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((buf * MT + mt) * p.BN);
       const float* sc = p.scale ? p.scale + (int64_t)g * p.Cout : nullptr;
-      for (int c = cbeg; c < cend; c += 32) {
+      float4 rr[4];
+      auto load_res = [&](int c, float4* dst) {
+        if (p.res == nullptr || c >= cend || co0 + c + 4 * lc >= p.Cout) return;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (vrow[j]) dst[j] = __ldg(reinterpret_cast<const float4*>(p.res + mrow[j] + c));
+      };
+      load_res(cbeg, rr);
+      mbar_wait(acc_full(buf), phacc);
+      tc_fence_after();
+      for (int c = cbeg; c < cend; c += 16) {
         if (co0 + c >= p.Cout) break;
-        const bool second = (c + 16 < cend) && (co0 + c + 16 < p.Cout);
-        float4 rr[8];
-        const float* rp = (p.res && valid) ? p.res + m * p.Cout + co0 + c : nullptr;
-        if (rp && vec4) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            if (co0 + c + 4 * j < p.Cout && c + 4 * j < cend) rr[j] = *reinterpret_cast<const float4*>(rp + 4 * j);
-        }
-        float v[32];
+        float4 rn[4];
+        load_res(c + 16, rn);                       // next chunk's residual is in flight while this chunk is transposed
+        float v[16];
         tmem_ld16(trow + (uint32_t)c, v);
-        if (second) tmem_ld16(trow + (uint32_t)(c + 16), v + 16);
-        if (!valid) continue;
-        const int ncol = second ? 32 : 16;
-        float* yp = p.y + m * p.Cout + co0 + c;
-        if (vec4) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            if (4 * j < ncol && co0 + c + 4 * j < p.Cout) {
-              const int co = co0 + c + 4 * j;
-              float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-              if (p.sb_vec) {
-                if (sc) { float4 s4 = __ldg(reinterpret_cast<const float4*>(sc + co)); o.x *= s4.x; o.y *= s4.y; o.z *= s4.z; o.w *= s4.w; }
-                if (p.bias) { float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + co)); o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w; }
-              } else {
-                if (sc) { o.x *= __ldg(sc + co); o.y *= __ldg(sc + co + 1); o.z *= __ldg(sc + co + 2); o.w *= __ldg(sc + co + 3); }
-                if (p.bias) { o.x += __ldg(p.bias + co); o.y += __ldg(p.bias + co + 1); o.z += __ldg(p.bias + co + 2); o.w += __ldg(p.bias + co + 3); }
-              }
-              if (rp) { o.x += rr[j].x; o.y += rr[j].y; o.z += rr[j].z; o.w += rr[j].w; }
-              if (p.act == DGMR_ACT_RELU) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-              *reinterpret_cast<float4*>(yp + 4 * j) = o;
-            }
-          }
-        } else {
-          for (int j = 0; j < ncol; ++j) {
-            const int co = co0 + c + j;
-            if (co < p.Cout) {
-              float o = v[j];
-              if (sc) o *= __ldg(sc + co);
-              if (p.bias) o += __ldg(p.bias + co);
-              if (rp) o += rp[j];
-              if (p.act == DGMR_ACT_RELU) o = fmaxf(o, 0.f);
-              yp[j] = o;
-            }
+        for (int k = 0; k < 4; ++k)
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(st_row + (((uint32_t)k ^ st_sw) << 4)), "f"(v[4 * k]), "f"(v[4 * k + 1]),
+                       "f"(v[4 * k + 2]), "f"(v[4 * k + 3]) : "memory");
+        __syncwarp();
+        const int co = co0 + c + 4 * lc;
+        const bool cok = co < p.Cout;
+        float4 s4 = make_float4(1.f, 1.f, 1.f, 1.f), b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (cok) {
+          if (p.sb_vec) {
+            if (sc) s4 = __ldg(reinterpret_cast<const float4*>(sc + co));
+            if (p.bias) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + co));
+          } else {
+            if (sc) s4 = make_float4(__ldg(sc + co), __ldg(sc + co + 1), __ldg(sc + co + 2), __ldg(sc + co + 3));
+            if (p.bias) b4 = make_float4(__ldg(p.bias + co), __ldg(p.bias + co + 1), __ldg(p.bias + co + 2), __ldg(p.bias + co + 3));
           }
         }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int row = lr + 8 * j;
+          float4 o;
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(o.x), "=f"(o.y), "=f"(o.z), "=f"(o.w)
+                       : "r"(stg + (uint32_t)row * 64u + (((uint32_t)lc ^ (uint32_t)((row >> 1) & 3)) << 4)) : "memory");
+          if (vrow[j] && cok) {
+            o.x = fmaf(o.x, s4.x, b4.x); o.y = fmaf(o.y, s4.y, b4.y); o.z = fmaf(o.z, s4.z, b4.z); o.w = fmaf(o.w, s4.w, b4.w);
+            if (p.res) { o.x += rr[j].x; o.y += rr[j].y; o.z += rr[j].z; o.w += rr[j].w; }
+            if (p.act == DGMR_ACT_RELU) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+            *reinterpret_cast<float4*>(p.y + mrow[j] + c) = o;
+          }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) rr[j] = rn[j];
       }
       // this warp is done reading the accumulator buffer
       tc_fence_before();
@@ -1046,7 +1057,7 @@ int launch_conv_umma_patch(const float* x, const float* wp, const float* bias, c
   p.BN = (int)(ceil_div(ceil_div(Cout, p.n_tiles), 16) * 16);
   p.n_tiles = (int)ceil_div(Cout, p.BN);
   // two sub-tiles per weight stage when accumulators and shared memory allow; double-buffer the accumulators when they still fit
-  const uint32_t budget = 210u * 1024u;
+  const uint32_t budget = 208u * 1024u;   // + 16 KB epilogue staging + barriers + alignment slack <= 226 KB
   const uint32_t b_al = (((uint32_t)p.BN * row_bytes) + 1023u) & ~1023u;
   uint32_t patch_al = 0;
   p.a_stages = 2;
@@ -1067,6 +1078,7 @@ int launch_conv_umma_patch(const float* x, const float* wp, const float* bias, c
   p.total_items = (int64_t)p.n_tiles * N * D * p.items_per_img;
   p.act = act; p.bias = bias; p.scale = scale; p.res = res; p.y = y;
   p.sb_vec = (((reinterpret_cast<uintptr_t>(bias) | reinterpret_cast<uintptr_t>(scale)) & 15u) == 0) ? 1 : 0;
+  p.dbg = 0; if (const char* e = getenv("DGMR_PATCH_DBG")) p.dbg = atoi(e);
   if (((reinterpret_cast<uintptr_t>(res) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(wp)) & 15u) != 0) {
     set_error("conv_umma_patch: x / wp / res / y must be 16-byte aligned"); return 1;
   }
@@ -1074,7 +1086,7 @@ int launch_conv_umma_patch(const float* x, const float* wp, const float* bias, c
   p.tmem_cols = 32; while (p.tmem_cols < need_cols) p.tmem_cols <<= 1;
   p.b_stages = (int)((budget - 2 * patch_al) / b_al);
   if (p.b_stages > 8) p.b_stages = 8;
-  size_t smem = (size_t)p.a_stages * patch_al + (size_t)p.b_stages * b_al + 1024 + 8 * (2 * p.a_stages + 2 * p.b_stages + 6);
+  size_t smem = (size_t)p.a_stages * patch_al + (size_t)p.b_stages * b_al + 1024 + 8 * (2 * p.a_stages + 2 * p.b_stages + 6) + 128 + 8 * 2048;
   CUtensorMap tmA, tmB;
   {
     uint64_t dims[5] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)D, (uint64_t)N};
