@@ -247,6 +247,63 @@ conv_umma_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     tc_fence_after();
     const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
     const bool vec4 = (p.Cout & 3) == 0;
+    if (vec4 && !p.split_taps) {
+      // Coalesced path (see the halo-patch kernel): transpose each 16-column chunk through 2 KB of the (now idle) pipeline
+      // stage memory so that 4 adjacent lanes own 64 contiguous bytes of one output row.
+      const uint32_t stg = base + (uint32_t)q * 2048u;
+      const int lr = lane >> 2, lc = lane & 3;
+      const uint32_t st_row = stg + (uint32_t)lane * 64u, st_sw = (uint32_t)((lane >> 1) & 3);
+      int64_t mrow[4]; bool vrow[4]; const float* srow[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int rj = q * 32 + lr + 8 * j;
+        const int wj = w0 + rj % p.bw, hj = h0 + (rj / p.bw) % p.bh, nj = n0 + rj / (p.bw * p.bh);
+        vrow[j] = (nj < p.N) && (hj < p.H) && (wj < p.W);
+        mrow[j] = ((((int64_t)nj * p.D + d0) * p.H + hj) * p.W + wj) * p.Cout + co0 + 4 * lc;
+        srow[j] = (p.scale && vrow[j]) ? p.scale + (int64_t)(nj / (p.N / p.G)) * p.Cout : nullptr;
+      }
+      float4 rr[4];
+      auto load_res = [&](int c, float4* dst) {
+        if (p.res == nullptr || c >= p.BN || co0 + c + 4 * lc >= p.Cout) return;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (vrow[j]) dst[j] = __ldg(reinterpret_cast<const float4*>(p.res + mrow[j] + c));
+      };
+      load_res(0, rr);
+      for (int c = 0; c < p.BN; c += 16) {
+        if (co0 + c >= p.Cout) break;
+        float4 rn[4];
+        load_res(c + 16, rn);
+        float v[16];
+        tmem_ld16(trow + (uint32_t)c, v);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(st_row + (((uint32_t)k ^ st_sw) << 4)), "f"(v[4 * k]), "f"(v[4 * k + 1]),
+                       "f"(v[4 * k + 2]), "f"(v[4 * k + 3]) : "memory");
+        __syncwarp();
+        const int co = co0 + c + 4 * lc;
+        const bool cok = co < p.Cout;
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (cok && p.bias) b4 = make_float4(__ldg(p.bias + co), __ldg(p.bias + co + 1), __ldg(p.bias + co + 2), __ldg(p.bias + co + 3));
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int row = lr + 8 * j;
+          float4 o;
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(o.x), "=f"(o.y), "=f"(o.z), "=f"(o.w)
+                       : "r"(stg + (uint32_t)row * 64u + (((uint32_t)lc ^ (uint32_t)((row >> 1) & 3)) << 4)) : "memory");
+          if (vrow[j] && cok) {
+            if (srow[j]) { o.x *= __ldg(srow[j] + co); o.y *= __ldg(srow[j] + co + 1); o.z *= __ldg(srow[j] + co + 2); o.w *= __ldg(srow[j] + co + 3); }
+            o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
+            if (p.res) { o.x += rr[j].x; o.y += rr[j].y; o.z += rr[j].z; o.w += rr[j].w; }
+            if (p.act == DGMR_ACT_RELU) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+            *reinterpret_cast<float4*>(p.y + mrow[j] + c) = o;
+          }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) rr[j] = rn[j];
+      }
+    } else
     for (int c = 0; c < p.BN; c += 16) {
       if (co0 + c >= p.Cout) break;   // warp-uniform
       float v[16];
