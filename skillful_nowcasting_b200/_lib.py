@@ -272,7 +272,7 @@ class CudaBackend:
                    xT_lo=None, dzT_lo=None):
         tag = None
         if self.profile is not None:
-            umma = algo == ALGO_UMMA or (algo == ALGO_AUTO and xT is not None and self.wgrad_umma_supported(N, D, H, W, Cin, Cout, kd, kh, kw))
+            umma = algo == ALGO_UMMA or (algo == ALGO_AUTO and self.wgrad_umma_supported(N, D, H, W, Cin, Cout, kd, kh, kw))
             tag = "wgrad_umma" if umma else "wgrad_simt"
         self._call("dgmr_conv_wgrad", _f32(x, "x"), _f32(dz, "dz"), _f32(xT, "xT"), _f32(dzT, "dzT"), _f32(xT_lo, "xT_lo"),
                    _f32(dzT_lo, "dzT_lo"), _f32(dwp, "dwp"), N, D, H, W, Cin, Cout, kd, kh, kw, algo, precision,

@@ -247,7 +247,7 @@ conv_umma_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     tc_fence_after();
     const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
     const bool vec4 = (p.Cout & 3) == 0;
-    if (vec4 && !p.split_taps) {
+    if (vec4) {
       // Coalesced path (see the halo-patch kernel): transpose each 16-column chunk through 2 KB of the (now idle) pipeline
       // stage memory so that 4 adjacent lanes own 64 contiguous bytes of one output row.
       const uint32_t stg = base + (uint32_t)q * 2048u;
@@ -293,6 +293,10 @@ conv_umma_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                        : "r"(stg + (uint32_t)row * 64u + (((uint32_t)lc ^ (uint32_t)((row >> 1) & 3)) << 4)) : "memory");
           if (vrow[j] && cok) {
             if (srow[j]) { o.x *= __ldg(srow[j] + co); o.y *= __ldg(srow[j] + co + 1); o.z *= __ldg(srow[j] + co + 2); o.w *= __ldg(srow[j] + co + 3); }
+            if (p.split_taps) {   // one filter tap per CTA: accumulate into y (pre-filled with the residual or zero)
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p.y + mrow[j] + c), "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w) : "memory");
+              continue;
+            }
             o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
             if (p.res) { o.x += rr[j].x; o.y += rr[j].y; o.z += rr[j].z; o.w += rr[j].w; }
             if (p.act == DGMR_ACT_RELU) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
@@ -641,10 +645,10 @@ conv_umma_wgrad_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_co
   const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * p.stages + 1);
   volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_addr - raw));
 
-  const int tap = blockIdx.y;
+  const int tap = blockIdx.x;
   const int tkw = tap % p.kw, tkh = (tap / p.kw) % p.kh, tkd = tap / (p.kw * p.kh);
   const int co0 = (blockIdx.z / p.ci_tiles) * 128, ci0 = (blockIdx.z % p.ci_tiles) * p.BN;
-  const int kb0 = blockIdx.x * p.kb_chunk;
+  const int kb0 = blockIdx.y * p.kb_chunk;
   const int kb1 = min(kb0 + p.kb_chunk, p.kb_total);
   const int num_kb = kb1 - kb0;
 
@@ -727,8 +731,9 @@ conv_umma_wgrad_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_co
       if (co >= p.Cout) continue;
       float* dst = p.dwp + ((int64_t)tap * p.Cout + co) * p.Cin + ci0 + c;
 #pragma unroll
-      for (int j = 0; j < 16; ++j)
-        if (ci0 + c + j < p.Cin) atomicAdd(dst + j, v[j]);
+      for (int j = 0; j < 16; j += 4)   // Cin % 4 == 0 (pick_aw): one 16-byte vector reduction per 4 channels
+        if (ci0 + c + j < p.Cin)
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(v[j]), "f"(v[j + 1]), "f"(v[j + 2]), "f"(v[j + 3]) : "memory");
     }
   }
   tc_fence_before();
@@ -767,10 +772,10 @@ conv_umma_wgrad_row_kernel(const __grid_constant__ CUtensorMap tmDz, const __gri
   const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * p.stages + 1);
   volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_addr - raw));
 
-  const int trow_i = blockIdx.y;                 // (kd, kh) filter row
+  const int trow_i = blockIdx.x;                 // (kd, kh) filter row: fastest index, so the CTAs sharing a pixel range are co-scheduled (L2 reuse)
   const int tkh = trow_i % p.kh, tkd = trow_i / p.kh;
   const int co0 = (blockIdx.z / p.ci_tiles) * 128, ci0 = (blockIdx.z % p.ci_tiles) * p.BN;
-  const int kb0 = blockIdx.x * p.kb_chunk;
+  const int kb0 = blockIdx.y * p.kb_chunk;
   const int kb1 = min(kb0 + p.kb_chunk, p.kb_total);
   const int num_kb = kb1 - kb0;
 
@@ -846,8 +851,9 @@ conv_umma_wgrad_row_kernel(const __grid_constant__ CUtensorMap tmDz, const __gri
         if (co >= p.Cout) continue;
         float* dst = p.dwp + ((int64_t)tap * p.Cout + co) * p.Cin + ci0 + c;
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
-          if (ci0 + c + j < p.Cin) atomicAdd(dst + j, v[j]);
+        for (int j = 0; j < 16; j += 4)
+          if (ci0 + c + j < p.Cin)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(v[j]), "f"(v[j + 1]), "f"(v[j + 2]), "f"(v[j + 3]) : "memory");
       }
     }
   }
@@ -1045,7 +1051,7 @@ int launch_conv_umma_wgrad(const float* x, const float* dz, float* dwp, int N, i
   const int co_tiles = (int)ceil_div(Cout, 128);
   p.kb_total = (N / p.bn) * D * p.tiles_h * p.tiles_w;
   int64_t base_ctas = (int64_t)taps * co_tiles * p.ci_tiles;
-  int64_t ksplit = ceil_div((int64_t)sm_count() * 3, base_ctas);
+  int64_t ksplit = ((int64_t)sm_count() * 3) / base_ctas;   // floor: never spill a few CTAs into an extra wave
   if (ksplit > p.kb_total / 4) ksplit = p.kb_total / 4;
   if (ksplit < 1) ksplit = 1;
   p.kb_chunk = (int)ceil_div(p.kb_total, ksplit);
@@ -1074,7 +1080,7 @@ int launch_conv_umma_wgrad(const float* x, const float* dz, float* dwp, int N, i
     attr_set = true;
   }
   if (cudaMemsetAsync(dwp, 0, sizeof(float) * (size_t)taps * Cout * Cin, st) != cudaSuccess) { set_error("conv_umma_wgrad: memset failed"); return 2; }
-  dim3 grid((unsigned)ksplit, (unsigned)taps, (unsigned)(co_tiles * p.ci_tiles));
+  dim3 grid((unsigned)taps, (unsigned)ksplit, (unsigned)(co_tiles * p.ci_tiles));
   conv_umma_wgrad_kernel<<<grid, kUmmaThreads, smem, st>>>(tmDz, tmX, p);
   DGMR_CHECK_LAUNCH("conv_umma_wgrad");
   return 0;
@@ -1091,8 +1097,10 @@ static bool umma_patch_ok(int N, int D, int H, int W, int Cin, int Cout, int kd,
 }
 
 // heuristic (AUTO only): persistent CTAs need a few tiles each to amortise their pipeline fill
-static bool umma_patch_profitable(int N, int D, int H, int W, int Cin) {
-  return Cin % 32 == 0 && (int64_t)H * W >= 1024 && (int64_t)N * D * H * W >= (int64_t)128 * 4 * sm_count();
+// and narrow outputs (Cout < 64) make every MMA so short that the per-tap barrier round trips dominate (measured: 96->48 at
+// 128^2 runs 289 TF/s on the plain kernel, 178 TF/s here).
+static bool umma_patch_profitable(int N, int D, int H, int W, int Cin, int Cout) {
+  return Cin % 32 == 0 && Cout >= 64 && (int64_t)H * W >= 1024 && (int64_t)N * D * H * W >= (int64_t)128 * 4 * sm_count();
 }
 
 int launch_conv_umma_patch(const float* x, const float* wp, const float* bias, const float* scale, const float* res, float* y, int N, int D, int H, int W,
@@ -1208,7 +1216,8 @@ int launch_conv_umma_wgrad_row(const float* x, const float* dz, float* dwp, int 
   p.wsegs = W / 32;
   p.kb_total = N * D * H * p.wsegs;
   int64_t base_ctas = (int64_t)kd * kh * co_tiles * p.ci_tiles;
-  int64_t ksplit = ceil_div((int64_t)sm_count() * 2, base_ctas);
+  // one CTA per SM (shared memory): fill exactly two waves, never spill a few CTAs into a third
+  int64_t ksplit = ((int64_t)sm_count() * 2) / base_ctas;
   if (ksplit > p.kb_total / 8) ksplit = p.kb_total / 8;
   if (ksplit < 1) ksplit = 1;
   p.kb_chunk = (int)ceil_div(p.kb_total, ksplit);
@@ -1237,7 +1246,7 @@ int launch_conv_umma_wgrad_row(const float* x, const float* dz, float* dwp, int 
     attr_set = true;
   }
   if (cudaMemsetAsync(dwp, 0, sizeof(float) * (size_t)taps * Cout * Cin, st) != cudaSuccess) { set_error("conv_umma_wgrad_row: memset failed"); return 2; }
-  dim3 grid((unsigned)ksplit, (unsigned)(kd * kh), (unsigned)(co_tiles * p.ci_tiles));
+  dim3 grid((unsigned)(kd * kh), (unsigned)ksplit, (unsigned)(co_tiles * p.ci_tiles));
   conv_umma_wgrad_row_kernel<<<grid, kUmmaThreads, smem, st>>>(tmDz, tmX, p);
   DGMR_CHECK_LAUNCH("conv_umma_wgrad_row");
   return 0;
@@ -1286,7 +1295,7 @@ int dgmr_conv_fwd(const float* x, const float* x_lo, const float* wp, const floa
   DGMR_REQUIRE(precision == DGMR_PREC_TF32 || algo == DGMR_ALGO_SIMT || !ok, "dgmr_conv_fwd: 3xTF32 not implemented on the tcgen05 path yet");
   if (algo == DGMR_ALGO_UMMA || algo == DGMR_ALGO_UMMA_PATCH || (algo == DGMR_ALGO_AUTO && ok)) {
     if (algo != DGMR_ALGO_UMMA && umma_patch_ok(N, D, H, W, Cin, Cout, kd, kh, kw, G) &&
-        (algo == DGMR_ALGO_UMMA_PATCH || umma_patch_profitable(N, D, H, W, Cin))) {
+        (algo == DGMR_ALGO_UMMA_PATCH || umma_patch_profitable(N, D, H, W, Cin, Cout))) {
       int e = launch_conv_umma_patch(x, wp, bias, scale, res, y, N, D, H, W, Cin, Cout, kd, G, act, S(stream));
       if (e >= 0) return e;   // -1: configuration does not fit in shared memory -> plain kernel
     }
@@ -1300,8 +1309,8 @@ int dgmr_conv_wgrad(const float* x, const float* dz, const float* xT, const floa
                     int H, int W, int Cin, int Cout, int kd, int kh, int kw, int algo, int precision, dgmr_stream_t stream) {
   (void)xT; (void)dzT; (void)xT_lo; (void)dzT_lo; (void)precision;  // MN-major tiles come straight from x / dz: no transposed copies needed
   DGMR_REQUIRE(N > 0 && D > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, "dgmr_conv_wgrad: bad dims");
-  bool ok = umma_wgrad_ok(N, D, H, W, Cin, Cout, kd, kh, kw);
-  if (algo == DGMR_ALGO_UMMA || algo == DGMR_ALGO_UMMA_PATCH) DGMR_REQUIRE(ok, "dgmr_conv_wgrad: shape not supported by the tcgen05 path");
+  bool ok = umma_wgrad_ok(N, D, H, W, Cin, Cout, kd, kh, kw) && (reinterpret_cast<uintptr_t>(dwp) & 15u) == 0;   // 16-byte vector reductions into dwp
+  if (algo == DGMR_ALGO_UMMA || algo == DGMR_ALGO_UMMA_PATCH) DGMR_REQUIRE(ok, "dgmr_conv_wgrad: shape not supported by the tcgen05 path (or dwp not 16-byte aligned)");
   if (algo == DGMR_ALGO_UMMA_PATCH) DGMR_REQUIRE(umma_wgrad_row_ok(N, D, H, W, Cin, Cout, kd, kh, kw), "dgmr_conv_wgrad: shape not supported by the row kernel");
   if (algo == DGMR_ALGO_UMMA_PATCH || (algo == DGMR_ALGO_AUTO && ok && umma_wgrad_row_ok(N, D, H, W, Cin, Cout, kd, kh, kw) && (int64_t)N * D * H * W >= 16384))
     return launch_conv_umma_wgrad_row(x, dz, dwp, N, D, H, W, Cin, Cout, kd, kh, S(stream));

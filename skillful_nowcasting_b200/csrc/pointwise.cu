@@ -263,6 +263,57 @@ __global__ void bn_stats_kernel(const float* __restrict__ x, double* __restrict_
     __syncthreads();
   }
 }
+// float4 variant (C % 4 == 0): thread = (row lane, 4-channel lane), 4 independent rows in flight per thread.
+__global__ void bn_stats4_kernel(const float4* __restrict__ x, double* __restrict__ sums, int64_t rows, int C4, int64_t chunk) {
+  extern __shared__ double sh[];  // [rp][cpl][8]
+  const int g = blockIdx.y;
+  const int cpl = C4 < 256 ? C4 : 256;
+  const int rp = 256 / cpl;
+  const int cl = threadIdx.x % cpl, rl = threadIdx.x / cpl;
+  const int64_t r0 = (int64_t)blockIdx.x * chunk;
+  const int64_t r1 = r0 + chunk < rows ? r0 + chunk : rows;
+  const float4* xg = x + (int64_t)g * rows * C4;
+  for (int cb = 0; cb < C4; cb += cpl) {   // block-uniform trip count (barriers inside)
+    const int c = cb + cl;
+    double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (rl < rp && c < C4) {
+      float fs[4] = {0.f, 0.f, 0.f, 0.f}, fq[4] = {0.f, 0.f, 0.f, 0.f};
+      int cnt = 0;
+      int64_t r = r0 + rl;
+      for (; r + 3 * (int64_t)rp < r1; r += 4 * (int64_t)rp) {
+        float4 v0 = xg[r * C4 + c], v1 = xg[(r + rp) * C4 + c], v2 = xg[(r + 2 * (int64_t)rp) * C4 + c], v3 = xg[(r + 3 * (int64_t)rp) * C4 + c];
+        fs[0] += (v0.x + v1.x) + (v2.x + v3.x); fq[0] += (v0.x * v0.x + v1.x * v1.x) + (v2.x * v2.x + v3.x * v3.x);
+        fs[1] += (v0.y + v1.y) + (v2.y + v3.y); fq[1] += (v0.y * v0.y + v1.y * v1.y) + (v2.y * v2.y + v3.y * v3.y);
+        fs[2] += (v0.z + v1.z) + (v2.z + v3.z); fq[2] += (v0.z * v0.z + v1.z * v1.z) + (v2.z * v2.z + v3.z * v3.z);
+        fs[3] += (v0.w + v1.w) + (v2.w + v3.w); fq[3] += (v0.w * v0.w + v1.w * v1.w) + (v2.w * v2.w + v3.w * v3.w);
+        if (++cnt == 16) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) { acc[2 * k] += fs[k]; acc[2 * k + 1] += fq[k]; fs[k] = fq[k] = 0.f; }
+          cnt = 0;
+        }
+      }
+      for (; r < r1; r += rp) {
+        float4 v = xg[r * C4 + c];
+        fs[0] += v.x; fq[0] += v.x * v.x; fs[1] += v.y; fq[1] += v.y * v.y; fs[2] += v.z; fq[2] += v.z * v.z; fs[3] += v.w; fq[3] += v.w * v.w;
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { acc[2 * k] += fs[k]; acc[2 * k + 1] += fq[k]; }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) sh[(rl * cpl + cl) * 8 + k] = acc[k];
+    }
+    __syncthreads();
+    // 8 values per 4-channel lane: spread the final cross-row reduction over 8*cpl threads
+    for (int t = threadIdx.x; t < cpl * 8; t += blockDim.x) {
+      const int lane4 = t >> 3, k = t & 7;
+      if (lane4 + cb < C4) {
+        double v = 0.0;
+        for (int j = 0; j < rp; ++j) v += sh[(j * cpl + lane4) * 8 + k];
+        atomicAdd(&sums[((int64_t)g * C4 * 4 + (int64_t)(cb + lane4) * 4 + (k >> 1)) * 2 + (k & 1)], v);
+      }
+    }
+    __syncthreads();
+  }
+}
 __global__ void bn_finalize_kernel(const double* __restrict__ sums, const float* __restrict__ gamma, const float* __restrict__ beta,
                                    float* __restrict__ rmean, float* __restrict__ rvar, int64_t rows, int G, int C, float eps, float mom, int training,
                                    float* __restrict__ mean, float* __restrict__ invstd, float* __restrict__ a, float* __restrict__ b) {
@@ -378,6 +429,76 @@ __global__ void bn_bwd_reduce_kernel(const float* __restrict__ dy, const float* 
       for (int j = 1; j < rp; ++j) { s += sh[(j * cpl + cl) * 2]; q += sh[(j * cpl + cl) * 2 + 1]; }
       atomicAdd(&red[((int64_t)g * C + c) * 2], s);
       atomicAdd(&red[((int64_t)g * C + c) * 2 + 1], q);
+    }
+    __syncthreads();
+  }
+}
+__global__ void bn_bwd_reduce4_kernel(const float* __restrict__ dy, const float4* __restrict__ x, const float4* __restrict__ a, const float4* __restrict__ b,
+                                      const float4* __restrict__ mean, const float4* __restrict__ invstd, double* __restrict__ red,
+                                      int64_t rows, int C4, int64_t chunk, int relu, int up2, int H, int W) {
+  extern __shared__ double sh[];  // [rp][cpl][8]
+  const int g = blockIdx.y;
+  const int C = C4 * 4;
+  const int cpl = C4 < 256 ? C4 : 256;
+  const int rp = 256 / cpl;
+  const int cl = threadIdx.x % cpl, rl = threadIdx.x / cpl;
+  const int64_t r0 = (int64_t)blockIdx.x * chunk;
+  const int64_t r1 = r0 + chunk < rows ? r0 + chunk : rows;
+  for (int cb = 0; cb < C4; cb += cpl) {   // block-uniform trip count (barriers inside)
+    const int c = cb + cl;
+    double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (rl < rp && c < C4) {
+      const int64_t o4 = (int64_t)g * C4 + c;
+      const float4 aa = a[o4], bb = b[o4], m = mean[o4], is = invstd[o4];
+      float fs[4] = {0.f, 0.f, 0.f, 0.f}, fq[4] = {0.f, 0.f, 0.f, 0.f};
+      int cnt = 0;
+      auto one = [&](int64_t r) {
+        const int64_t gr = (int64_t)g * rows + r;
+        const float4 xv = x[gr * C4 + c];
+        float4 d;
+        if (up2) {
+          int w = gr % W; int64_t t = gr / W; int h = t % H; int64_t n = t / H;
+          const float4* p0 = reinterpret_cast<const float4*>(dy + ((n * 2 * H + 2 * h) * (2 * (int64_t)W) + 2 * w) * C) + c;
+          const float4* p1 = p0 + (int64_t)2 * W * C4;
+          float4 q0 = p0[0], q1 = p0[C4], q2 = p1[0], q3 = p1[C4];
+          d = make_float4(q0.x + q1.x + q2.x + q3.x, q0.y + q1.y + q2.y + q3.y, q0.z + q1.z + q2.z + q3.z, q0.w + q1.w + q2.w + q3.w);
+        } else {
+          d = reinterpret_cast<const float4*>(dy)[gr * C4 + c];
+        }
+        if (relu) {
+          if (!(aa.x * xv.x + bb.x > 0.f)) d.x = 0.f;
+          if (!(aa.y * xv.y + bb.y > 0.f)) d.y = 0.f;
+          if (!(aa.z * xv.z + bb.z > 0.f)) d.z = 0.f;
+          if (!(aa.w * xv.w + bb.w > 0.f)) d.w = 0.f;
+        }
+        fs[0] += d.x; fq[0] += d.x * (xv.x - m.x) * is.x;
+        fs[1] += d.y; fq[1] += d.y * (xv.y - m.y) * is.y;
+        fs[2] += d.z; fq[2] += d.z * (xv.z - m.z) * is.z;
+        fs[3] += d.w; fq[3] += d.w * (xv.w - m.w) * is.w;
+      };
+      int64_t r = r0 + rl;
+      for (; r + (int64_t)rp < r1; r += 2 * (int64_t)rp) {
+        one(r); one(r + rp);
+        if (++cnt == 32) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) { acc[2 * k] += fs[k]; acc[2 * k + 1] += fq[k]; fs[k] = fq[k] = 0.f; }
+          cnt = 0;
+        }
+      }
+      for (; r < r1; r += rp) one(r);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { acc[2 * k] += fs[k]; acc[2 * k + 1] += fq[k]; }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) sh[(rl * cpl + cl) * 8 + k] = acc[k];
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < cpl * 8; t += blockDim.x) {
+      const int lane4 = t >> 3, k = t & 7;
+      if (lane4 + cb < C4) {
+        double v = 0.0;
+        for (int j = 0; j < rp; ++j) v += sh[(j * cpl + lane4) * 8 + k];
+        atomicAdd(&red[((int64_t)g * C + (int64_t)(cb + lane4) * 4 + (k >> 1)) * 2 + (k & 1)], v);
+      }
     }
     __syncthreads();
   }
@@ -754,7 +875,10 @@ int dgmr_bn_stats(const float* x, double* sums, int64_t rows, int G, int C, dgmr
   DGMR_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * G * C, S(stream)));
   int64_t chunk = bn_chunk(rows, G);
   dim3 grid((unsigned)ceil_div(rows, chunk), G);
-  bn_stats_kernel<<<grid, 256, 256 * 2 * sizeof(double), S(stream)>>>(x, sums, rows, C, chunk);
+  if (C % 4 == 0 && al16(x))
+    bn_stats4_kernel<<<grid, 256, 256 * 8 * sizeof(double), S(stream)>>>((const float4*)x, sums, rows, C / 4, chunk);
+  else
+    bn_stats_kernel<<<grid, 256, 256 * 2 * sizeof(double), S(stream)>>>(x, sums, rows, C, chunk);
   DGMR_CHECK_LAUNCH("dgmr_bn_stats");
   return 0;
 }
@@ -782,7 +906,11 @@ int dgmr_bn_bwd_reduce(const float* dy, const float* x, const float* a, const fl
   DGMR_CUDA(cudaMemsetAsync(red, 0, sizeof(double) * 2 * G * C, S(stream)));
   int64_t chunk = bn_chunk(rows, G);
   dim3 grid((unsigned)ceil_div(rows, chunk), G);
-  bn_bwd_reduce_kernel<<<grid, 256, 256 * 2 * sizeof(double), S(stream)>>>(dy, x, a, b, mean, invstd, red, rows, C, chunk, relu, up2, H, W);
+  if (C % 4 == 0 && al16(dy) && al16(x) && al16(a) && al16(b) && al16(mean) && al16(invstd))
+    bn_bwd_reduce4_kernel<<<grid, 256, 256 * 8 * sizeof(double), S(stream)>>>(dy, (const float4*)x, (const float4*)a, (const float4*)b, (const float4*)mean,
+                                                                              (const float4*)invstd, red, rows, C / 4, chunk, relu, up2, H, W);
+  else
+    bn_bwd_reduce_kernel<<<grid, 256, 256 * 2 * sizeof(double), S(stream)>>>(dy, x, a, b, mean, invstd, red, rows, C, chunk, relu, up2, H, W);
   DGMR_CHECK_LAUNCH("dgmr_bn_bwd_reduce");
   return 0;
 }
