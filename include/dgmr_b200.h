@@ -92,9 +92,11 @@ int dgmr_upsample(const float* x, float* y, int N, int D, int H, int W, int C, i
 
 /* ---- ConvGRU gate arithmetic (ref: dgmr/layers/ConvGRU.py:72-82); `ld` = row pitch (floats) of the
  * pre-activation tensors so that r|u can live side by side in one [rows, 2*Ch] conv output. */
-int dgmr_gru_gate_fwd(const float* pre_r, int ld, const float* h, float* rh, int64_t rows, int Ch, dgmr_stream_t stream);
+/* flags & DGMR_FLAG_ROUND_TF32: rh (a conv-only operand) is emitted tf32-rounded */
+int dgmr_gru_gate_fwd(const float* pre_r, int ld, const float* h, float* rh, int64_t rows, int Ch, int flags, dgmr_stream_t stream);
 /* relu_c != 0: `c` holds the candidate pre-activation and relu is applied here (ref: ConvGRU.py:81) */
-int dgmr_gru_blend_fwd(const float* pre_u, int ld, const float* h, const float* c, float* hnew,
+/* hnew_tf32 (nullable): tf32-rounded copy of hnew = the next step's conv operand */
+int dgmr_gru_blend_fwd(const float* pre_u, int ld, const float* h, const float* c, float* hnew, float* hnew_tf32,
                        int64_t rows, int Ch, int relu_c, dgmr_stream_t stream);
 /* d_rh -> d_pre_r, dh (+= if accumulate) */
 int dgmr_gru_gate_bwd(const float* d_rh, const float* pre_r, int ld, const float* h, float* d_pre_r, int ldd,

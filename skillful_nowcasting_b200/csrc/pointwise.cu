@@ -182,22 +182,49 @@ __global__ void upsample4_kernel(const float4* __restrict__ x, float4* __restric
 }
 
 // ------------------------------------------------------------------ ConvGRU gates (ref: dgmr/layers/ConvGRU.py:72-82)
-__global__ void gru_gate_fwd_kernel(const float* __restrict__ pre_r, int ld, const float* __restrict__ h, float* __restrict__ rh, int64_t rows, int Ch) {
+__device__ __forceinline__ float sigmoid_acc(float v) { return 1.0f / (1.0f + expf(-v)); }   // full-accuracy expf (parity with the oracle)
+__global__ void gru_gate_fwd_kernel(const float* __restrict__ pre_r, int ld, const float* __restrict__ h, float* __restrict__ rh, int64_t rows, int Ch, int rnd) {
   int64_t total = rows * Ch;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     int64_t r = i / Ch; int c = i - r * Ch;
-    float g = 1.0f / (1.0f + expf(-pre_r[r * ld + c]));
-    rh[i] = g * h[i];
+    float v = sigmoid_acc(pre_r[r * ld + c]) * h[i];
+    rh[i] = rnd ? rna_tf32_pw(v) : v;
   }
 }
-__global__ void gru_blend_fwd_kernel(const float* __restrict__ pre_u, int ld, const float* __restrict__ h, const float* __restrict__ c_, float* __restrict__ hn, int64_t rows, int Ch, int relu_c) {
+__global__ void gru_gate_fwd4_kernel(const float* __restrict__ pre_r, int ld, const float4* __restrict__ h, float4* __restrict__ rh, int64_t rows, int C4, int rnd) {
+  int64_t total = rows * C4;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = i / C4; int c = i - r * C4;
+    float4 p = *reinterpret_cast<const float4*>(pre_r + r * ld + 4 * c), hv = h[i];
+    float4 v = make_float4(sigmoid_acc(p.x) * hv.x, sigmoid_acc(p.y) * hv.y, sigmoid_acc(p.z) * hv.z, sigmoid_acc(p.w) * hv.w);
+    if (rnd) v = make_float4(rna_tf32_pw(v.x), rna_tf32_pw(v.y), rna_tf32_pw(v.z), rna_tf32_pw(v.w));
+    rh[i] = v;
+  }
+}
+__global__ void gru_blend_fwd_kernel(const float* __restrict__ pre_u, int ld, const float* __restrict__ h, const float* __restrict__ c_, float* __restrict__ hn,
+                                     float* __restrict__ hn_tf32, int64_t rows, int Ch, int relu_c) {
   int64_t total = rows * Ch;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     int64_t r = i / Ch; int c = i - r * Ch;
-    float u = 1.0f / (1.0f + expf(-pre_u[r * ld + c]));
+    float u = sigmoid_acc(pre_u[r * ld + c]);
     float cv = c_[i];
     if (relu_c) cv = fmaxf(cv, 0.f);
-    hn[i] = u * h[i] + (1.0f - u) * cv;
+    float v = u * h[i] + (1.0f - u) * cv;
+    hn[i] = v;
+    if (hn_tf32) hn_tf32[i] = rna_tf32_pw(v);
+  }
+}
+__global__ void gru_blend_fwd4_kernel(const float* __restrict__ pre_u, int ld, const float4* __restrict__ h, const float4* __restrict__ c_, float4* __restrict__ hn,
+                                      float4* __restrict__ hn_tf32, int64_t rows, int C4, int relu_c) {
+  int64_t total = rows * C4;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = i / C4; int c = i - r * C4;
+    float4 p = *reinterpret_cast<const float4*>(pre_u + r * ld + 4 * c), hv = h[i], cv = c_[i];
+    if (relu_c) cv = make_float4(fmaxf(cv.x, 0.f), fmaxf(cv.y, 0.f), fmaxf(cv.z, 0.f), fmaxf(cv.w, 0.f));
+    float ux = sigmoid_acc(p.x), uy = sigmoid_acc(p.y), uz = sigmoid_acc(p.z), uw = sigmoid_acc(p.w);
+    float4 v = make_float4(ux * hv.x + (1.0f - ux) * cv.x, uy * hv.y + (1.0f - uy) * cv.y, uz * hv.z + (1.0f - uz) * cv.z, uw * hv.w + (1.0f - uw) * cv.w);
+    hn[i] = v;
+    if (hn_tf32) hn_tf32[i] = make_float4(rna_tf32_pw(v.x), rna_tf32_pw(v.y), rna_tf32_pw(v.z), rna_tf32_pw(v.w));
   }
 }
 __global__ void gru_gate_bwd_kernel(const float* __restrict__ d_rh, const float* __restrict__ pre_r, int ld, const float* __restrict__ h,
@@ -838,15 +865,23 @@ int dgmr_upsample(const float* x, float* y, int N, int D, int H, int W, int C, i
   DGMR_CHECK_LAUNCH("dgmr_upsample");
   return 0;
 }
-int dgmr_gru_gate_fwd(const float* pre_r, int ld, const float* h, float* rh, int64_t rows, int Ch, dgmr_stream_t stream) {
+int dgmr_gru_gate_fwd(const float* pre_r, int ld, const float* h, float* rh, int64_t rows, int Ch, int flags, dgmr_stream_t stream) {
   int64_t n = rows * Ch; if (n == 0) return 0;
-  gru_gate_fwd_kernel<<<ew_grid(n, 256, 2), 256, 0, S(stream)>>>(pre_r, ld, h, rh, rows, Ch);
+  const int rnd = (flags & DGMR_FLAG_ROUND_TF32) ? 1 : 0;
+  if (Ch % 4 == 0 && ld % 4 == 0 && al16(pre_r) && al16(h) && al16(rh))
+    gru_gate_fwd4_kernel<<<ew_grid(n / 4, 256, 1), 256, 0, S(stream)>>>(pre_r, ld, (const float4*)h, (float4*)rh, rows, Ch / 4, rnd);
+  else
+    gru_gate_fwd_kernel<<<ew_grid(n, 256, 2), 256, 0, S(stream)>>>(pre_r, ld, h, rh, rows, Ch, rnd);
   DGMR_CHECK_LAUNCH("dgmr_gru_gate_fwd");
   return 0;
 }
-int dgmr_gru_blend_fwd(const float* pre_u, int ld, const float* h, const float* c, float* hnew, int64_t rows, int Ch, int relu_c, dgmr_stream_t stream) {
+int dgmr_gru_blend_fwd(const float* pre_u, int ld, const float* h, const float* c, float* hnew, float* hnew_tf32, int64_t rows, int Ch, int relu_c,
+                       dgmr_stream_t stream) {
   int64_t n = rows * Ch; if (n == 0) return 0;
-  gru_blend_fwd_kernel<<<ew_grid(n, 256, 2), 256, 0, S(stream)>>>(pre_u, ld, h, c, hnew, rows, Ch, relu_c);
+  if (Ch % 4 == 0 && ld % 4 == 0 && al16(pre_u) && al16(h) && al16(c) && al16(hnew) && al16(hnew_tf32))
+    gru_blend_fwd4_kernel<<<ew_grid(n / 4, 256, 1), 256, 0, S(stream)>>>(pre_u, ld, (const float4*)h, (const float4*)c, (float4*)hnew, (float4*)hnew_tf32, rows, Ch / 4, relu_c);
+  else
+    gru_blend_fwd_kernel<<<ew_grid(n, 256, 2), 256, 0, S(stream)>>>(pre_u, ld, h, c, hnew, hnew_tf32, rows, Ch, relu_c);
   DGMR_CHECK_LAUNCH("dgmr_gru_blend_fwd");
   return 0;
 }

@@ -42,18 +42,11 @@ class ConvGRUCell(nn.Module):
         gates = (self.read_gate_conv, self.update_gate_conv, self.output_conv)
         # one launch per weight: the T power iterations of this forward (ref: per-call parametrization)
         scales = [g.scale_of(g.inv_sigma(T)) for g in gates]  # [T, Ch] each
+        if ops.config.gru_sequence:
+            return self._run_fused(xs, h0, T, shared_input, scales)
         xparts = []
         for g, sc in zip(gates, scales):
-            if shared_input:
-                p = xs.numel()
-                x_rep = ops.mark_conv_only(ops.repeat_mid(xs.reshape(1, p), T).reshape((T,) + tuple(xs.shape[1:])))
-                xp = ops.conv(x_rep, g.weight_orig, g.bias, sc, None, 0, cx, T, ACT_NONE)  # [T,1,H,W,Ch]
-                q = xp.numel() // T
-                xp = ops.repeat_mid(xp.reshape(T, q), B).reshape((T, B) + tuple(xp.shape[1:]))
-            else:
-                xp = ops.conv(xs, g.weight_orig, g.bias, sc, None, 0, cx, T, ACT_NONE)
-                xp = xp.reshape((T, B) + tuple(xp.shape[1:]))
-            xparts.append(xp.unbind(0))
+            xparts.append(self._x_part(xs, g.weight_orig, g.bias, sc, T, B, cx, shared_input).unbind(0))
         srows = [sc.reshape(T, 1, ch).unbind(0) for sc in scales]
         h = h0
         outs = []
@@ -67,6 +60,35 @@ class ConvGRUCell(nn.Module):
             h = ops.gru_blend(pre_u, h, c, relu_c=True)                                  # ReLU fused into the blend
             outs.append(h)
         return torch.cat(outs, dim=0)
+
+    @staticmethod
+    def _x_part(xs, w, bias, sc, T, B, cx, shared_input):
+        """Input-dependent part of a gate pre-activation for all T steps: [T, B, 1, H, W, Cout] (bias and sigma_t applied)."""
+        if shared_input:
+            p = xs.numel()
+            x_rep = ops.mark_conv_only(ops.repeat_mid(xs.reshape(1, p), T).reshape((T,) + tuple(xs.shape[1:])))
+            xp = ops.conv(x_rep, w, bias, sc, None, 0, cx, T, ACT_NONE)  # [T,1,H,W,Cout]
+            q = xp.numel() // T
+            return ops.repeat_mid(xp.reshape(T, q), B).reshape((T, B) + tuple(xp.shape[1:]))
+        xp = ops.conv(xs, w, bias, sc, None, 0, cx, T, ACT_NONE)
+        return xp.reshape((T, B) + tuple(xp.shape[1:]))
+
+    def _run_fused(self, xs, h0, T, shared_input, scales):
+        """Read and update gates as ONE convolution (their weights, biases and per-step sigmas side by side along Cout), and the
+        whole recurrence as one autograd node (ops.gru_sequence): 2 serial convs per step instead of 3, weight gradients of all
+        steps in one launch."""
+        ch = self.output_channels
+        cx = self.input_channels - ch
+        B = h0.shape[0]
+        gr, gu, gc = self.read_gate_conv, self.update_gate_conv, self.output_conv
+        w_ru = torch.cat([gr.weight_orig, gu.weight_orig], dim=0)
+        b_ru = torch.cat([gr.bias, gu.bias], dim=0)
+        s_ru = torch.cat([scales[0], scales[1]], dim=1)                     # [T, 2Ch]
+        xru = self._x_part(xs, w_ru, b_ru, s_ru, T, B, cx, shared_input)
+        xc = self._x_part(xs, gc.weight_orig, gc.bias, scales[2], T, B, cx, shared_input)
+        xru = xru.reshape((T * B,) + tuple(xru.shape[2:]))
+        xc = xc.reshape((T * B,) + tuple(xc.shape[2:]))
+        return ops.gru_sequence(xru, xc, h0, w_ru, gc.weight_orig, s_ru, scales[2], T, cx)
 
     def forward(self, x: torch.Tensor, prev_state: torch.Tensor):
         """NCHW in/out: (x [B,Cx,H,W], prev_state [B,Ch,H,W]) -> (out, new_state)."""

@@ -28,6 +28,8 @@ class config:
     _dbg_round_dz = True
     # small-M / large-K convs (the ConvGRU steps) run split over the filter taps with fp32 red.add into the output
     split_taps = True
+    # ConvGRU: fused read|update gate conv + whole recurrence as one autograd node (False: the per-step reference wiring)
+    gru_sequence = True
 
 
 def _be():
@@ -457,26 +459,32 @@ def _use_split_taps(n, d, h, w, cin, cout, taps, has_bias, act) -> bool:
 
 def packed_weight(w: torch.Tensor, ci0: int, cin: int, mode: int) -> torch.Tensor:
     """[tap][Cout][Cin] (mode 0) / flipped-transposed dgrad pack (mode 1) of the OIHW weight slice
-    [:, ci0:ci0+cin]; cached until the parameter's version counter moves.  mode | FLAG_ROUND_TF32: tf32-rounded."""
+    [:, ci0:ci0+cin]; cached until the parameter's version counter moves.  mode | FLAG_ROUND_TF32: tf32-rounded.
+    Only nn.Parameters are cached: a temporary (e.g. the concatenated gate weights of a ConvGRU) can die and hand its
+    address + version 0 to the next temporary, which a (data_ptr, version) key cannot tell apart."""
+    cacheable = isinstance(w, torch.nn.Parameter)
     key = (w.data_ptr(), tuple(w.shape), ci0, cin, mode, str(w.device))
     ver = w._version
-    hit = _pack_cache.get(key)
-    if hit is not None and hit[0] == ver:
-        return hit[1]
+    if cacheable:
+        hit = _pack_cache.get(key)
+        if hit is not None and hit[0] == ver:
+            return hit[1]
     cout, cintot = w.shape[0], w.shape[1]
     taps = w.numel() // (cout * cintot)
     p = _new((taps * cout * cin,), w)
     _be().pack_weight(_c(w.detach()), p, cout, cintot, ci0, cin, taps, mode)
-    _pack_cache[key] = (ver, p)
+    if cacheable:
+        _pack_cache[key] = (ver, p)
     return p
 
 
 def packed_weight_padded(w: torch.Tensor, ci0: int, cin: int, cin_p: int, mode: int) -> torch.Tensor:
     """Like packed_weight but with the input-channel axis zero-padded to cin_p (the 4-channel space-to-depth inputs
     are carried as 8 channels so that the tensor-core path, whose K step is 8 tf32, can serve them)."""
+    cacheable = isinstance(w, torch.nn.Parameter)
     key = (w.data_ptr(), tuple(w.shape), ci0, cin, ("pad", cin_p, mode), str(w.device))
     ver = w._version
-    hit = _pack_cache.get(key)
+    hit = _pack_cache.get(key) if cacheable else None
     if hit is not None and hit[0] == ver:
         return hit[1]
     cout, cintot = w.shape[0], w.shape[1]
@@ -488,12 +496,28 @@ def packed_weight_padded(w: torch.Tensor, ci0: int, cin: int, cin_p: int, mode: 
         _be().permute(dense, p, (taps * cout, cin), (cin, 1), (cin_p, 1), False, 0, 0)
     else:           # p[taps-1-tap][ci][co]: ci rows spread to cin_p per tap (extra rows stay zero)
         _be().permute(dense, p, (taps, cin, cout), (cin * cout, cout, 1), (cin_p * cout, cout, 1), False, 0, 0)
-    _pack_cache[key] = (ver, p)
+    if cacheable:
+        _pack_cache[key] = (ver, p)
     return p
 
 
 def clear_pack_cache():
     _pack_cache.clear()
+
+
+def _conv_launch(x, wp, bias, scale, res, y, n, d, h, wd, c, cout, kd, kh, kw, G, act):
+    """y = act(conv(x, wp) * scale + bias + res) through the C ABI; picks the tap-split accumulate mode for launches that
+    would otherwise leave most SMs idle.  `res` may alias `y` (each element is read, then written, by the same thread)."""
+    be = _be()
+    if _use_split_taps(n, d, h, wd, c, cout, kd * kh * kw, bias is not None, act) and be.conv_umma_supported(n, d, h, wd, c, cout, kd, kh, kw):
+        if res is None:
+            be.fill(y, 0.0)
+        elif res.data_ptr() != y.data_ptr():
+            be.axpby(1.0, res, 0.0, None, y)   # y starts as the residual, the taps accumulate on top
+        be.conv_fwd(x, wp, None, scale, None, y, n, d, h, wd, c, cout, kd, kh, kw, G, ACT_NONE | FLAG_ACCUMULATE,
+                    config.conv_algo, config.precision)
+    else:
+        be.conv_fwd(x, wp, bias, scale, res, y, n, d, h, wd, c, cout, kd, kh, kw, G, act, config.conv_algo, config.precision)
 
 
 class _Conv(Function):
@@ -515,16 +539,7 @@ class _Conv(Function):
         wp = packed_weight(w, ci0, cin, rnd) if c == cin else packed_weight_padded(w, ci0, cin, c, rnd)
         y = _new((n, d, h, wd, cout), x)
         res_c, scale_c, bias_c = _c(res), _c(scale), _c(bias)
-        if _use_split_taps(n, d, h, wd, c, cout, kd * kh * kw, bias is not None, act) and _be().conv_umma_supported(n, d, h, wd, c, cout, kd, kh, kw):
-            if res_c is not None:
-                _be().axpby(1.0, res_c, 0.0, None, y)   # y starts as the residual, the taps accumulate on top
-            else:
-                _be().fill(y, 0.0)
-            _be().conv_fwd(x, wp, None, scale_c, None, y, n, d, h, wd, c, cout, kd, kh, kw, G, ACT_NONE | FLAG_ACCUMULATE,
-                           config.conv_algo, config.precision)
-        else:
-            _be().conv_fwd(x, wp, bias_c, scale_c, res_c, y, n, d, h, wd, c, cout, kd, kh, kw, G, act,
-                           config.conv_algo, config.precision)
+        _conv_launch(x, wp, bias_c, scale_c, res_c, y, n, d, h, wd, c, cout, kd, kh, kw, G, act)
         need_s = scale is not None and scale.requires_grad
         need_y = act == ACT_RELU or need_s
         ctx.save_for_backward(x, w, bias_c, scale_c, res_c if need_s else None, y if need_y else None)
@@ -578,13 +593,7 @@ class _Conv(Function):
             rnd = FLAG_ROUND_TF32 if (_tc_fwd(n, d, h, wd, cout, cp, kd, kh, kw) and config._dbg_round_w) else 0
             wpt = packed_weight(w, ci0, cin, 1 | rnd) if cp == cin else packed_weight_padded(w, ci0, cin, cp, 1 | rnd)
             dx = _new(x.shape, x)
-            if _use_split_taps(n, d, h, wd, cout, cp, kd * kh * kw, False, ACT_NONE) and be.conv_umma_supported(n, d, h, wd, cout, cp, kd, kh, kw):
-                be.fill(dx, 0.0)
-                be.conv_fwd(dz, wpt, None, None, None, dx, n, d, h, wd, cout, cp, kd, kh, kw, 1, ACT_NONE | FLAG_ACCUMULATE,
-                            config.conv_algo, config.precision)
-            else:
-                be.conv_fwd(dz, wpt, None, None, None, dx, n, d, h, wd, cout, cp, kd, kh, kw, 1, ACT_NONE,
-                            config.conv_algo, config.precision)
+            _conv_launch(dz, wpt, None, None, None, dx, n, d, h, wd, cout, cp, kd, kh, kw, 1, ACT_NONE)
         if need_w:
             taps = kd * kh * kw
             dwp = _new((taps * cout * cp,), x)
@@ -665,7 +674,7 @@ class _GruGate(Function):
         ch = h.shape[-1]
         rows = h.numel() // ch
         rh = torch.empty_like(h)
-        _be().gru_gate_fwd(pre_r, ch, h, rh, rows, ch)
+        _be().gru_gate_fwd(pre_r, ch, h, rh, rows, ch, 0)
         ctx.save_for_backward(pre_r, h)
         return rh
 
@@ -689,7 +698,7 @@ class _GruBlend(Function):
         ch = h.shape[-1]
         rows = h.numel() // ch
         hn = torch.empty_like(h)
-        _be().gru_blend_fwd(pre_u, ch, h, c, hn, rows, ch, relu_c)
+        _be().gru_blend_fwd(pre_u, ch, h, c, hn, None, rows, ch, relu_c)
         ctx.save_for_backward(pre_u, h, c)
         ctx.relu_c = relu_c
         return hn
@@ -712,6 +721,103 @@ def gru_gate(pre_r, h):
 def gru_blend(pre_u, h, c, relu_c=False):
     """relu_c: `c` is the candidate PRE-activation and the ReLU of ConvGRU.py:81 is applied inside the blend kernel."""
     return _GruBlend.apply(pre_u, h, c, relu_c)
+
+
+class _GruSequence(Function):
+    """All T steps of one ConvGRU (ref: dgmr/layers/ConvGRU.py:63-84 called T times by :103-110) as ONE autograd node.
+
+    Inputs are the input-dependent parts of the gate pre-activations (already scaled, bias added): xru [T*B,1,H,W,2Ch]
+    (read | update side by side) and xc [T*B,1,H,W,Ch]; the h-dependent parts stay on the serial path:
+        pre_ru_t = conv(h_{t-1}, W_ru[:, cx:]) * s_ru[t] + xru_t        (one conv for both gates)
+        rh_t     = sigmoid(pre_r_t) * h_{t-1}
+        c_t      = conv(rh_t, W_c[:, cx:]) * s_c[t] + xc_t
+        h_t      = u_t * h_{t-1} + (1 - u_t) * relu(c_t)
+    Backward walks the steps in reverse with the data gradients only; the two weight gradients are ONE wgrad launch each
+    over all T*B images (the conv operands and the scaled output gradients of every step sit in contiguous buffers)."""
+
+    @staticmethod
+    def forward(ctx, xru, xc, h0, w_ru, w_c, s_ru, s_c, T, cx):
+        be = _be()
+        xru, xc, h0, s_ru, s_c = _c(xru), _c(xc), _c(h0), _c(s_ru), _c(s_c)
+        B, d, H, W, ch = h0.shape
+        assert d == 1 and xru.shape == (T * B, 1, H, W, 2 * ch) and xc.shape == (T * B, 1, H, W, ch), (xru.shape, xc.shape, h0.shape)
+        rows = B * H * W
+        rnd_ru = FLAG_ROUND_TF32 if _tc_fwd(B, 1, H, W, ch, 2 * ch, 1, 3, 3) else 0
+        rnd_c = FLAG_ROUND_TF32 if _tc_fwd(B, 1, H, W, ch, ch, 1, 3, 3) else 0
+        wp_ru = packed_weight(w_ru, cx, ch, rnd_ru)
+        wp_c = packed_weight(w_c, cx, ch, rnd_c)
+        out = _new((T * B, 1, H, W, ch), h0)
+        pru = _new((T * B, 1, H, W, 2 * ch), h0)
+        cp = _new((T * B, 1, H, W, ch), h0)
+        rh = _new((T * B, 1, H, W, ch), h0)
+        # conv operand of step t = h_{t-1}; when the tensor-core path rounds operands it reads a rounded private copy (the gate
+        # arithmetic must see the unrounded state), written by the previous step's blend kernel
+        hop = _new((T * B, 1, H, W, ch), h0) if rnd_ru else None
+        if rnd_ru:
+            be.round_tf32(h0, hop[0:B])
+        pru_flat = pru.view(-1)
+        for t in range(T):
+            sl = slice(t * B, (t + 1) * B)
+            h_prev = h0 if t == 0 else out[(t - 1) * B:t * B]
+            a = hop[sl] if rnd_ru else h_prev
+            _conv_launch(a, wp_ru, None, s_ru[t:t + 1], xru[sl], pru[sl], B, 1, H, W, ch, 2 * ch, 1, 3, 3, 1, ACT_NONE)
+            be.gru_gate_fwd(pru[sl], 2 * ch, h_prev, rh[sl], rows, ch, rnd_c)
+            _conv_launch(rh[sl], wp_c, None, s_c[t:t + 1], xc[sl], cp[sl], B, 1, H, W, ch, ch, 1, 3, 3, 1, ACT_NONE)
+            nxt = hop[(t + 1) * B:(t + 2) * B] if (rnd_ru and t + 1 < T) else None
+            be.gru_blend_fwd(pru_flat[t * rows * 2 * ch + ch:], 2 * ch, h_prev, cp[sl], out[sl], nxt, rows, ch, True)
+        ctx.save_for_backward(xru, xc, h0, w_ru, w_c, s_ru, s_c, out, pru, cp, rh, hop)
+        ctx.meta = (T, cx, bool(rnd_c))
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        xru, xc, h0, w_ru, w_c, s_ru, s_c, out, pru, cp, rh, hop = ctx.saved_tensors
+        T, cx, rh_rounded = ctx.meta
+        be = _be()
+        B, _, H, W, ch = h0.shape
+        rows = B * H * W
+        tc_dg_ru = _tc_fwd(B, 1, H, W, 2 * ch, ch, 1, 3, 3)
+        tc_dg_c = _tc_fwd(B, 1, H, W, ch, ch, 1, 3, 3)
+        tc_wg_ru = _tc_wgrad(T * B, 1, H, W, ch, 2 * ch, 1, 3, 3)
+        tc_wg_c = _tc_wgrad(T * B, 1, H, W, ch, ch, 1, 3, 3)
+        wpt_ru = packed_weight(w_ru, cx, ch, 1 | (FLAG_ROUND_TF32 if tc_dg_ru else 0))
+        wpt_c = packed_weight(w_c, cx, ch, 1 | (FLAG_ROUND_TF32 if tc_dg_c else 0))
+        gh = _c(dout).clone()                        # running dL/dh_t: starts as the output gradient, steps add their carry
+        dh0 = _new(h0.shape, h0)
+        dxru, dzru = torch.empty_like(pru), torch.empty_like(pru)
+        dxc, dzc = torch.empty_like(cp), torch.empty_like(cp)
+        ds_ru, ds_c = _new((T, 2 * ch), h0), _new((T, ch), h0)
+        drh = _new(h0.shape, h0)
+        pru_flat, dxru_flat = pru.view(-1), dxru.view(-1)
+        f_ru = ACT_NONE | (FLAG_ROUND_TF32 if (tc_dg_ru or tc_wg_ru) else 0)
+        f_c = ACT_NONE | (FLAG_ROUND_TF32 if (tc_dg_c or tc_wg_c) else 0)
+        for t in range(T - 1, -1, -1):
+            sl = slice(t * B, (t + 1) * B)
+            h_prev = h0 if t == 0 else out[(t - 1) * B:t * B]
+            tgt = dh0 if t == 0 else gh[(t - 1) * B:t * B]
+            off = t * rows * 2 * ch
+            # h_t = u h + (1-u) relu(c):  d pre_u -> dxru[:, ch:], d c_pre -> dxc, u * dh_t -> tgt
+            be.gru_blend_bwd(gh[sl], pru_flat[off + ch:], 2 * ch, h_prev, cp[sl], dxru_flat[off + ch:], 2 * ch, dxc[sl], tgt, t > 0, rows, ch, True)
+            be.conv_bwd_prep(dxc[sl], cp[sl], xc[sl], None, s_c[t:t + 1], dzc[sl], None, None, ds_c[t:t + 1], rows, 1, ch, f_c)
+            _conv_launch(dzc[sl], wpt_c, None, None, None, drh, B, 1, H, W, ch, ch, 1, 3, 3, 1, ACT_NONE)
+            # rh = r h:  d pre_r -> dxru[:, :ch], r * drh added to tgt
+            be.gru_gate_bwd(drh, pru[sl], 2 * ch, h_prev, dxru[sl], 2 * ch, tgt, True, rows, ch)
+            be.conv_bwd_prep(dxru[sl], pru[sl], xru[sl], None, s_ru[t:t + 1], dzru[sl], None, None, ds_ru[t:t + 1], rows, 1, 2 * ch, f_ru)
+            _conv_launch(dzru[sl], wpt_ru, None, None, tgt, tgt, B, 1, H, W, 2 * ch, ch, 1, 3, 3, 1, ACT_NONE)
+        # weight gradients: one launch per weight over all T*B images
+        xop = hop if hop is not None else torch.cat([h0, out[:(T - 1) * B]], dim=0)
+        dws = []
+        for wt, x_all, dz_all, co in ((w_ru, xop, dzru, 2 * ch), (w_c, rh, dzc, ch)):
+            dwp = _new((9 * co * ch,), h0)
+            be.conv_wgrad(x_all, dz_all, dwp, T * B, 1, H, W, ch, co, 1, 3, 3, config.wgrad_algo, config.precision)
+            dw = _zeros(wt.shape, h0)
+            be.unpack_wgrad(dwp, dw, co, wt.shape[1], cx, ch, 9, False)
+            dws.append(dw)
+        return dxru, dxc, dh0, dws[0], dws[1], ds_ru, ds_c, None, None
+
+
+def gru_sequence(xru, xc, h0, w_ru, w_c, s_ru, s_c, T, cx):
+    return _GruSequence.apply(xru, xc, h0, w_ru, w_c, s_ru, s_c, T, cx)
 
 
 # ----------------------------------------------------------------------------- discriminator head

@@ -13,6 +13,11 @@ import torch
 import torch.nn.functional as F
 
 
+def _rows(t, rows, ld, ch):
+    """[rows, ch] window with row pitch ld starting at t's first element (t may be a 1-D tail slice of a wider buffer)."""
+    return torch.as_strided(t, (rows, ch), (ld, 1), t.storage_offset())
+
+
 def _view(t, off, shape, strides):
     flat = t.reshape(-1)  # contiguous input: a view; as_strided offsets are absolute in the storage
     return torch.as_strided(flat, tuple(shape), tuple(strides), flat.storage_offset() + off)
@@ -88,28 +93,34 @@ class EmuBackend:
         y.copy_(out.reshape(y.shape))
 
     # ---- GRU
-    def gru_gate_fwd(self, pre_r, ld, h, rh, rows, Ch):
-        g = torch.sigmoid(pre_r.reshape(rows, ld)[:, :Ch])
-        rh.copy_((g * h.reshape(rows, Ch)).reshape(rh.shape))
+    def gru_gate_fwd(self, pre_r, ld, h, rh, rows, Ch, flags=0):
+        g = torch.sigmoid(_rows(pre_r, rows, ld, Ch))
+        v = g * h.reshape(rows, Ch)
+        if flags & 256:
+            v = self._rna_tf32(v)
+        rh.copy_(v.reshape(rh.shape))
 
-    def gru_blend_fwd(self, pre_u, ld, h, c, hnew, rows, Ch, relu_c=False):
-        u = torch.sigmoid(pre_u.reshape(rows, ld)[:, :Ch])
+    def gru_blend_fwd(self, pre_u, ld, h, c, hnew, hnew_tf32, rows, Ch, relu_c=False):
+        u = torch.sigmoid(_rows(pre_u, rows, ld, Ch))
         cv = torch.relu(c.reshape(rows, Ch)) if relu_c else c.reshape(rows, Ch)
-        hnew.copy_((u * h.reshape(rows, Ch) + (1 - u) * cv).reshape(hnew.shape))
+        v = u * h.reshape(rows, Ch) + (1 - u) * cv
+        hnew.copy_(v.reshape(hnew.shape))
+        if hnew_tf32 is not None:
+            hnew_tf32.copy_(self._rna_tf32(v).reshape(hnew_tf32.shape))
 
     def gru_gate_bwd(self, d_rh, pre_r, ld, h, d_pre_r, ldd, dh, accumulate, rows, Ch):
-        g = torch.sigmoid(pre_r.reshape(rows, ld)[:, :Ch])
+        g = torch.sigmoid(_rows(pre_r, rows, ld, Ch))
         d = d_rh.reshape(rows, Ch)
-        d_pre_r.reshape(rows, ldd)[:, :Ch] = d * h.reshape(rows, Ch) * g * (1 - g)
+        _rows(d_pre_r, rows, ldd, Ch)[...] = d * h.reshape(rows, Ch) * g * (1 - g)
         v = (d * g).reshape(dh.shape)
         dh.add_(v) if accumulate else dh.copy_(v)
 
     def gru_blend_bwd(self, d_hnew, pre_u, ld, h, c, d_pre_u, ldd, dc, dh, accumulate, rows, Ch, relu_c=False):
-        u = torch.sigmoid(pre_u.reshape(rows, ld)[:, :Ch])
+        u = torch.sigmoid(_rows(pre_u, rows, ld, Ch))
         d = d_hnew.reshape(rows, Ch)
         cp = c.reshape(rows, Ch)
         cv = torch.relu(cp) if relu_c else cp
-        d_pre_u.reshape(rows, ldd)[:, :Ch] = d * (h.reshape(rows, Ch) - cv) * u * (1 - u)
+        _rows(d_pre_u, rows, ldd, Ch)[...] = d * (h.reshape(rows, Ch) - cv) * u * (1 - u)
         g = d * (1 - u)
         if relu_c:
             g = g * (cp > 0)

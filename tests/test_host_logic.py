@@ -44,10 +44,18 @@ def test_block_forward_backward(emu, case, training):
     run_block_case(case, training, "cpu", 1e-5, 2e-4)
 
 
-def test_conv_gru_matches_oracle(emu):
-    """ref test shape family: tests/test_model.py:51-81 (scaled down)."""
-    gru, xs, h = run_conv_gru_case("cpu", 1e-5, 2e-4)
-    out, new = gru.cell(xs[0].detach(), h)
+@pytest.mark.parametrize("fused", [True, False])
+def test_conv_gru_matches_oracle(emu, fused):
+    """ref test shape family: tests/test_model.py:51-81 (scaled down).  fused: read|update gates as one conv and the whole
+    recurrence as one autograd node (ops.gru_sequence); False: the per-step wiring."""
+    from skillful_nowcasting_b200 import ops
+    old = ops.config.gru_sequence
+    ops.config.gru_sequence = fused
+    try:
+        gru, xs, h = run_conv_gru_case("cpu", 1e-5, 2e-4)
+        out, new = gru.cell(xs[0].detach(), h)
+    finally:
+        ops.config.gru_sequence = old
     assert out.shape == (2, 8, 8, 8) and torch.equal(out, new)
 
 

@@ -111,12 +111,18 @@ def test_block_tensor_core(cuda_backend, case, training):
     run_block_case(case, training, "cuda", 1e-3, 1.5e-1, tol_buf=1e-3, tol_l2=5e-2)
 
 
-def test_conv_gru_simt_and_tensor_core(cuda_backend):
+@pytest.mark.parametrize("fused", [True, False])
+def test_conv_gru_simt_and_tensor_core(cuda_backend, fused):
+    """fused: ops.gru_sequence (one conv for both gates, one autograd node, batched weight gradients); False: per-step wiring."""
     from skillful_nowcasting_b200 import ops
 
+    old = ops.config.gru_sequence
+    ops.config.gru_sequence = fused
     ops.config.conv_algo = ops.config.wgrad_algo = 1
     try:
         run_conv_gru_case("cuda", 2e-5, 3e-4)
+        ops.config.conv_algo = ops.config.wgrad_algo = 0
+        run_conv_gru_case("cuda", 1e-3, 1.5e-1, cx=64, ch=32, s=16, T=4, tol_l2=5e-2)
     finally:
         ops.config.conv_algo = ops.config.wgrad_algo = 0
-    run_conv_gru_case("cuda", 1e-3, 1.5e-1, cx=64, ch=32, s=16, T=4, tol_l2=5e-2)
+        ops.config.gru_sequence = old
