@@ -174,7 +174,7 @@ conv_umma_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   const int w0 = tw_i * p.bw, h0 = th_i * p.bh;
   const int co0 = blockIdx.y * p.BN;
   const int taps = p.kd * p.kh * p.kw;
-  const int kchunks = p.Cin / BK;
+  const int kchunks = (p.Cin + BK - 1) / BK;   // the last chunk may be a channel tail (zero-filled by TMA, fewer k-steps)
   const int tap_begin = p.split_taps ? (int)blockIdx.z : 0;
   const int num_kb = (p.split_taps ? 1 : taps) * kchunks;
 
@@ -217,6 +217,8 @@ conv_umma_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       const uint32_t row_bytes = BK * 4u;
       const uint32_t layout = row_bytes == 128 ? 2u : (row_bytes == 64 ? 4u : 6u);
       const uint32_t sbo = 8u * row_bytes;
+      const int tail_ks = (p.Cin % BK) ? (p.Cin % BK) / 8 : BK / 8;
+      int chunk_i = 0;
       int s = 0; uint32_t ph = 0;
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(full_bar(s), ph);
@@ -227,8 +229,15 @@ conv_umma_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         // advance 8 tf32 = 32 bytes along K inside the swizzle row: +2 in the (addr>>4) field.  Fully unrolled: the single
         // issuing thread must spend far fewer cycles per MMA than the MMA itself takes (N/2 cycles).
         umma_tf32(tmem_base, adesc, bdesc, idesc, kb != 0 ? 1u : 0u);
+        if (++chunk_i == kchunks) {       // last chunk of this tap: possibly a channel tail with fewer valid k-steps
+          chunk_i = 0;
 #pragma unroll
-        for (int k = 1; k < BK / 8; ++k) umma_tf32(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, 1u);
+          for (int k = 1; k < BK / 8; ++k)
+            if (k < tail_ks) umma_tf32(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, 1u);
+        } else {
+#pragma unroll
+          for (int k = 1; k < BK / 8; ++k) umma_tf32(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, 1u);
+        }
         umma_commit(empty_bar(s));
         if (++s == p.stages) { s = 0; ph ^= 1u; }
       }
@@ -428,7 +437,7 @@ conv_umma_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_gen;
 
-  const int chunks = p.Cin / BK;
+  const int chunks = (p.Cin + BK - 1) / BK;    // last chunk may be a channel tail (TMA zero fill, fewer k-steps)
   const int a_per_item = p.kd * chunks;       // activation patches per work item
   // work item -> (n_tile, image n, depth d, first flattened output fs)
   auto decode = [&](int64_t item, int& nt, int& n, int& d, int& fs) {
@@ -449,14 +458,14 @@ conv_umma_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       auto advance = [&](Cur& q) {
         if (++q.c == chunks) { q.c = 0; if (++q.kdi == p.kd) { q.kdi = 0; q.item += gridDim.x; } }
       };
-      uint32_t ai = 0, bi = 0;
+      int sa = 0, sb = 0; uint32_t pha = 0, phb = 0;
       auto issue_patch = [&](const Cur& q) {
         int nt, n, d, fs; decode(q.item, nt, n, d, fs);
         const int r_lo = (fs - p.P - 1) / p.P;            // first padded image row of the patch
-        const int sa = ai % p.a_stages; const uint32_t pha = (ai / p.a_stages) & 1u; ++ai;
         mbar_wait(a_empty(sa), pha ^ 1u);
         mbar_expect_tx(a_full(sa), patch_bytes);
         tma_load_5d(a_base + sa * patch_al, &tmA, a_full(sa), q.c * BK, -1, r_lo - 1, d + q.kdi - p.kd / 2, n);
+        if (++sa == p.a_stages) { sa = 0; pha ^= 1u; }
       };
       Cur ca{(int64_t)blockIdx.x, 0, 0}, cb = ca;
       if (valid(ca)) { issue_patch(ca); advance(ca); }
@@ -464,10 +473,10 @@ conv_umma_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         if (valid(ca)) { issue_patch(ca); advance(ca); }
         int nt, n, d, fs; decode(cb.item, nt, n, d, fs);
         for (int tap = 0; tap < 9; ++tap) {
-          const int sb = bi % p.b_stages; const uint32_t phb = (bi / p.b_stages) & 1u; ++bi;
           mbar_wait(b_empty(sb), phb ^ 1u);
           mbar_expect_tx(b_full(sb), b_bytes);
           tma_load_3d(b_base + sb * b_al, &tmB, b_full(sb), cb.c * BK, nt * p.BN, cb.kdi * 9 + tap);
+          if (++sb == p.b_stages) { sb = 0; phb ^= 1u; }
         }
         advance(cb);
       }
@@ -478,9 +487,10 @@ conv_umma_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((128u >> 4) << 24);
       constexpr uint32_t layout = (BK == 32) ? 2u : 4u;
       constexpr int ksteps = BK / 8;
+      const int tail_ks = (p.Cin % BK) ? (p.Cin % BK) / 8 : ksteps;
       const uint64_t adesc0 = make_desc(a_base, 8u * row_bytes, layout);
       const uint64_t bdesc0 = make_desc(b_base, 8u * row_bytes, layout);
-      uint32_t ai = 0, bi = 0, it = 0;
+      int sa = 0, sb = 0; uint32_t pha = 0, phb = 0, it = 0;   // ring positions advance incrementally: no divisions in the issue loop
       for (int64_t item = blockIdx.x; item < p.total_items; item += gridDim.x, ++it) {
         int nt, n, d, fs; decode(item, nt, n, d, fs);
         const int r_lo = (fs - p.P - 1) / p.P;
@@ -488,11 +498,13 @@ conv_umma_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         mbar_wait(acc_empty(buf), phacc ^ 1u);
         tc_fence_after();
         const uint32_t tacc = tmem_base + (uint32_t)(buf * MT * p.BN);
+        int chunk_i = 0;
         for (int a = 0; a < a_per_item; ++a) {
-          const int sa = ai % p.a_stages; const uint32_t pha = (ai / p.a_stages) & 1u; ++ai;
+          const bool tail_now = (++chunk_i == chunks) && tail_ks != ksteps;   // channel-tail chunk: fewer valid k-steps
+          if (chunk_i == chunks) chunk_i = 0;
           mbar_wait(a_full(sa), pha);
+#pragma unroll
           for (int tap = 0; tap < 9; ++tap) {
-            const int sb = bi % p.b_stages; const uint32_t phb = (bi / p.b_stages) & 1u; ++bi;
             mbar_wait(b_full(sb), phb);
             tc_fence_after();
             const int th = tap / 3, tw = tap - th * 3;
@@ -502,17 +514,29 @@ conv_umma_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             const uint64_t bdesc = bdesc0 + (uint64_t)((sb * b_al) >> 4);
             const uint64_t adesc = adesc0 + (uint64_t)((sa * patch_al + (uint32_t)j0 * row_bytes) >> 4);
             const uint32_t acc0 = (a | tap) != 0 ? 1u : 0u;
-            if (!(p.dbg & 2))
+            if (p.dbg & 2) {
+            } else if (!tail_now) {
 #pragma unroll
-            for (int mt = 0; mt < MT; ++mt) {
+              for (int mt = 0; mt < MT; ++mt) {
 #pragma unroll
-              for (int k = 0; k < ksteps; ++k)
-                umma_tf32(tacc + (uint32_t)(mt * p.BN), adesc + (uint64_t)(mt * 128 * (BK * 4 / 16) + 2 * k), bdesc + (uint64_t)(2 * k), idesc,
-                          k == 0 ? acc0 : 1u);
+                for (int k = 0; k < ksteps; ++k)
+                  umma_tf32(tacc + (uint32_t)(mt * p.BN), adesc + (uint64_t)(mt * 128 * (BK * 4 / 16) + 2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                            k == 0 ? acc0 : 1u);
+              }
+            } else {
+#pragma unroll
+              for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+                for (int k = 0; k < ksteps; ++k)
+                  if (k < tail_ks) umma_tf32(tacc + (uint32_t)(mt * p.BN), adesc + (uint64_t)(mt * 128 * (BK * 4 / 16) + 2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                                             k == 0 ? acc0 : 1u);
+              }
             }
             umma_commit(b_empty(sb));
+            if (++sb == p.b_stages) { sb = 0; phb ^= 1u; }
           }
           umma_commit(a_empty(sa));
+          if (++sa == p.a_stages) { sa = 0; pha ^= 1u; }
         }
         umma_commit(acc_full(buf));
       }
@@ -910,18 +934,32 @@ __global__ void __launch_bounds__(128, 1) umma_shift_probe_kernel(const __grid_c
 }
 
 // ------------------------------------------------------------------ host side
-static int pick_bk(int Cin) { return (Cin % 32 == 0) ? 32 : (Cin % 16 == 0) ? 16 : (Cin % 8 == 0) ? 8 : 0; }
+// channels per K block: 32 (128-byte rows) whenever Cin >= 32 -- a channel tail (Cin % 32 in {8,16,24}) is a last block whose
+// missing channels are TMA out-of-bounds zero fill and whose MMAs stop after the valid k-steps (64-byte-row TMA boxes move
+// half the bytes per row at the same per-row cost); 16 / 8 only for genuinely narrow inputs
+static int pick_bk(int Cin) { return (Cin % 8 != 0) ? 0 : (Cin >= 32) ? 32 : (Cin % 16 == 0) ? 16 : 8; }
 static bool pick_box(int N, int H, int W, int* bw, int* bh, int* bn) {
-  // bw*bh*bn == 128, bw | W, bh | H, bn | N.  Prefer wide rows (contiguous TMA lines).
+  // bw*bh*bn == 128, bw | W, bh | H.  Prefer wide rows (contiguous TMA lines).  bn need not divide N (nor be <= N): images
+  // past the end are TMA zero fill and their accumulator rows are discarded, so a 1x8x8 input still gets a (half-empty) tile.
   for (int w = 32; w >= 1; w >>= 1) {
-    if (W % w) continue;
-    if (w > W) continue;
+    if (w > W || W % w) continue;
     int rest = 128 / w;
     for (int h = rest; h >= 1; h >>= 1) {
       if (h > H || H % h) continue;
       int n = rest / h;
-      if (n > N || N % n) continue;
-      if (w * h * n != 128) continue;
+      if (w * h * n != 128 || n > 256) continue;
+      if (n > 1 && N % n != 0 && (int64_t)N * H * W >= 128 * 8) continue;   // big batches: keep looking for an exact fit first
+      *bw = w; *bh = h; *bn = n;
+      return true;
+    }
+  }
+  for (int w = 32; w >= 1; w >>= 1) {
+    if (w > W || W % w) continue;
+    int rest = 128 / w;
+    for (int h = rest; h >= 1; h >>= 1) {
+      if (h > H || H % h) continue;
+      int n = rest / h;
+      if (w * h * n != 128 || n > 256) continue;
       *bw = w; *bh = h; *bn = n;
       return true;
     }
@@ -988,7 +1026,7 @@ int launch_conv_umma_fwd(const float* x, const float* wp, const float* bias, con
     }
     attr_set = true;
   }
-  int64_t mtiles = (int64_t)(N / p.bn) * D * p.tiles_h * p.tiles_w;
+  int64_t mtiles = ceil_div(N, p.bn) * D * p.tiles_h * p.tiles_w;
   dim3 grid((unsigned)mtiles, (unsigned)ntiles, (unsigned)(accumulate ? taps : 1));
   if (p.BK == 32) conv_umma_fwd_kernel<32><<<grid, kUmmaThreads, smem, st>>>(tmA, tmB, p);
   else if (p.BK == 16) conv_umma_fwd_kernel<16><<<grid, kUmmaThreads, smem, st>>>(tmA, tmB, p);
@@ -1089,7 +1127,7 @@ int launch_conv_umma_wgrad(const float* x, const float* dz, float* dwp, int N, i
 
 static bool umma_patch_ok(int N, int D, int H, int W, int Cin, int Cout, int kd, int kh, int kw, int G) {
   if (kh != 3 || kw != 3 || !(kd == 1 || kd == 3)) return false;
-  if (Cin % 16 != 0 || Cout % 4 != 0 || Cout < 4) return false;
+  if (Cin % 8 != 0 || (Cin < 32 && Cin != 16) || Cout % 4 != 0 || Cout < 4) return false;
   if (W + 2 > 256 || (int64_t)H * W < 256) return false;    // tiny images: a tile would be mostly padding -> plain kernel
   if (G < 1 || N % G) return false;
   (void)D;
@@ -1108,7 +1146,7 @@ int launch_conv_umma_patch(const float* x, const float* wp, const float* bias, c
   PatchConvParams p;
   p.N = N; p.D = D; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.kd = kd; p.G = G;
   p.P = W + 2;
-  p.BK = (Cin % 32 == 0) ? 32 : 16;
+  p.BK = (Cin >= 32) ? 32 : 16;
   const uint32_t row_bytes = (uint32_t)p.BK * 4u;
   p.n_tiles = (int)ceil_div(Cout, 256);
   {

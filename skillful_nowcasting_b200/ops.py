@@ -454,7 +454,7 @@ def _use_split_taps(n, d, h, w, cin, cout, taps, has_bias, act) -> bool:
     if not config.split_taps or taps == 1 or has_bias or act != ACT_NONE or config.conv_algo == ALGO_SIMT:
         return False
     tiles = ((n * d * h * w + 127) // 128) * ((cout + 255) // 256)
-    return tiles <= 16 and cin >= 32 and _be().conv_umma_supported(n, d, h, w, cin, cout, 1, 3, 3)
+    return tiles <= 32 and cin >= 32 and _be().conv_umma_supported(n, d, h, w, cin, cout, 1, 3, 3)   # measured crossover (tests/time_gru_conv.py)
 
 
 def packed_weight(w: torch.Tensor, ci0: int, cin: int, mode: int) -> torch.Tensor:

@@ -18,7 +18,12 @@ UMMA_SHAPES = [
     (4, 1, 8, 8, 64, 192, 1, 3, 3, 4),      # 8x8 images: box spans 2 images; groups
     (8, 1, 4, 4, 128, 256, 1, 3, 3, 2),     # 4x4 images: 8 images per tile
     (32, 1, 2, 2, 64, 32, 1, 3, 3, 1),      # 2x2 images
-    (2, 1, 32, 32, 48, 96, 1, 3, 3, 1),     # BK=16 (64-byte swizzle)
+    (2, 1, 32, 32, 48, 96, 1, 3, 3, 1),     # Cin=48: 32-channel block + 16-channel tail block (TMA zero fill, 2 k-steps)
+    (2, 1, 32, 32, 16, 96, 1, 3, 3, 1),     # BK=16 (64-byte swizzle)
+    (2, 1, 16, 16, 72, 64, 1, 3, 3, 1),     # Cin=72: two full blocks + 8-channel tail
+    (1, 1, 8, 8, 768, 768, 1, 3, 3, 1),     # one 8x8 image (latent stack): half-empty 128-pixel tile, second image out of bounds
+    (3, 1, 8, 8, 64, 48, 1, 3, 3, 3),       # N=3 not a multiple of the 2-image box
+    (1, 1, 4, 4, 32, 32, 1, 3, 3, 1),       # 16 pixels in a 128-pixel tile
     (2, 1, 16, 16, 24, 24, 1, 3, 3, 1),     # BK=8 (32-byte swizzle), Cout=24 -> BN=32 with OOB weight rows
     (2, 1, 16, 16, 8, 48, 1, 3, 3, 1),      # Cin=8
     (2, 1, 16, 16, 192, 384, 1, 1, 1, 1),   # 1x1, two N tiles of 192
@@ -128,7 +133,8 @@ PATCH_SHAPES = [
     (1, 1, 64, 32, 64, 20, 1, 1),      # H != W, Cout not a multiple of 16
     (2, 5, 32, 32, 96, 96, 3, 1),      # 3-D: 3 depth taps, odd depth
     (1, 1, 40, 48, 32, 32, 1, 1),      # W not a power of two
-    (4, 1, 64, 64, 48, 48, 1, 1),      # Cin = 48: 16-channel chunks (64-byte rows)
+    (4, 1, 64, 64, 48, 48, 1, 1),      # Cin = 48: 32-channel chunk + 16-channel tail chunk
+    (4, 1, 64, 64, 16, 48, 1, 1),      # Cin = 16: 16-channel chunks (64-byte rows)
     (2, 6, 32, 32, 48, 96, 3, 1),      # same, 3-D
     (16, 1, 16, 16, 192, 192, 1, 1),   # small images (ConvGRU step): Cout split over more CTAs
     (16, 1, 32, 32, 96, 96, 1, 1),
