@@ -58,6 +58,9 @@ int dgmr_wgrad_umma_supported(int N, int D, int H, int W, int Cin, int Cout, int
 /* debug probe (tests only): C[128][N] = A[r0:r0+128, 0:32] . B[N, 0:32]^T through TMA + tcgen05 with the A descriptor
  * starting r0 rows into a swizzled 256-row tile; mode bit0 sets the descriptor base_offset field */
 int dgmr_debug_umma_shift(const float* A, const float* B, float* C, int N, int r0, int mode, dgmr_stream_t stream);
+/* tuning probe: cycles per kind::tf32 MMA (M=128, N, K=8) issued by one thread per CTA; mode 0 back to back, 1 commit per 8, 2 commit+wait per 8;
+ * shift_rows: the A descriptor starts that many 128-byte rows into the swizzled tile (the halo-patch kernels' tap offsets) */
+int dgmr_debug_umma_rate(float* out, int blocks, int N, int iters, int mode, int shift_rows, dgmr_stream_t stream);
 
 /* ---- layout: generic strided gather  dst[i0..] (+)= src[i0..]
  * replaces ref: PixelUnshuffle/PixelShuffle (dgmr/common.py:326,393; generators.py:123,178;

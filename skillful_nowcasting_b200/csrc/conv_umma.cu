@@ -108,6 +108,53 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+// ---- CTA-pair (cta_group::2) variants: two CTAs of a cluster on the two SMs of a TPC share one MMA stream.  Each CTA stages its own
+// 128 x K activation rows and HALF of the N x K weight tile; the leader (cluster rank 0) issues M = 256 MMAs that read both shared
+// memories and write both tensor memories.
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t addr, uint32_t rank) {
+  uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank)); return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_5d_2sm(uint32_t dst, const CUtensorMap* tm, uint32_t bar_cluster, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile("cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(dst),
+               "l"(tm), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_2sm(uint32_t dst, const CUtensorMap* tm, uint32_t bar_cluster, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst), "l"(tm),
+               "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t smem_dst, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_tf32_2cta(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc),
+               "r"(idesc), "r"(accumulate)
+               : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {   // arrives on the barrier at this offset in BOTH CTAs
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+// One lane of a converged warp.  The role loops run WARP-UNIFORM (all 32 lanes execute the control flow and the address / descriptor
+// arithmetic, which the compiler can then keep in uniform registers) and only the async instructions are predicated on the elected
+// lane: inside an `if (lane == 0)` region every descriptor handed to UTCHMMA / UTMALDG went through an ELECT + R2UR.BROADCAST waterfall
+// loop (~140 cycles of dependent latency per MMA, measured 2.5x the tensor pipe's own 60-cycle minimum).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
@@ -140,6 +187,7 @@ struct UmmaConvParams {
   int BK;                // channels per stage (32/16/8)
   int BN;                // N tile (multiple of 16, <= 256)
   int stages;
+  int cg;                // stages per release group (stages % cg == 0): one tcgen05.commit hands cg stages back to the producer
   int tmem_cols;
   int act;
   int split_taps;        // 1: blockIdx.z = filter tap, epilogue red.adds acc*scale into y
@@ -194,24 +242,33 @@ conv_umma_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_gen;
 
+  // Role loops are warp-uniform with an elected issuing lane (see elect_one).  Pipeline stages are handed back to the producer in
+  // groups of p.cg: one tcgen05.commit per group, because a commit occupies the tensor pipe for ~780 cycles (dgmr_debug_umma_rate)
+  // while the 4 MMAs of one stage take 240 cycles at N <= 128.
   if (warp == 0) {
-    if (lane == 0) {
+    {
       // ===== TMA producer
-      int s = 0; uint32_t ph = 0;
+      int s = 0, g = 0, sg = 0; uint32_t ph = 0;
+      int tapl = 0, chunk = 0;
       for (int kb = 0; kb < num_kb; ++kb) {
-        const int tapl = kb / kchunks, c0 = (kb - tapl * kchunks) * BK;
+        const int c0 = chunk * BK;
         const int tap = tap_begin + tapl;
         const int tkw = tap % p.kw, tkh = (tap / p.kw) % p.kh, tkd = tap / (p.kw * p.kh);
-        mbar_wait(empty_bar(s), ph ^ 1u);
-        mbar_expect_tx(full_bar(s), a_bytes + b_bytes);
-        const uint32_t sa = base + s * stage_bytes;
-        tma_load_5d(sa, &tmA, full_bar(s), c0, w0 + tkw - p.kw / 2, h0 + tkh - p.kh / 2, d0 + tkd - p.kd / 2, n0);
-        tma_load_3d(sa + a_bytes, &tmB, full_bar(s), c0, co0, tap);
-        if (++s == p.stages) { s = 0; ph ^= 1u; }
+        if (sg == 0) mbar_wait(empty_bar(g), ph ^ 1u);
+        if (elect_one()) {
+          mbar_expect_tx(full_bar(s), a_bytes + b_bytes);
+          const uint32_t sa = base + s * stage_bytes;
+          tma_load_5d(sa, &tmA, full_bar(s), c0, w0 + tkw - p.kw / 2, h0 + tkh - p.kh / 2, d0 + tkd - p.kd / 2, n0);
+          tma_load_3d(sa + a_bytes, &tmB, full_bar(s), c0, co0, tap);
+        }
+        __syncwarp();
+        if (++chunk == kchunks) { chunk = 0; ++tapl; }
+        if (++sg == p.cg) { sg = 0; ++g; }
+        if (++s == p.stages) { s = 0; g = 0; ph ^= 1u; }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       // ===== MMA issuer
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((128u >> 4) << 24);
       const uint32_t row_bytes = BK * 4u;
@@ -219,29 +276,35 @@ conv_umma_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       const uint32_t sbo = 8u * row_bytes;
       const int tail_ks = (p.Cin % BK) ? (p.Cin % BK) / 8 : BK / 8;
       int chunk_i = 0;
-      int s = 0; uint32_t ph = 0;
+      int s = 0, g = 0, sg = 0; uint32_t ph = 0;
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(full_bar(s), ph);
         tc_fence_after();
         const uint32_t sa = base + s * stage_bytes;
         const uint64_t adesc = make_desc(sa, sbo, layout);
         const uint64_t bdesc = make_desc(sa + a_bytes, sbo, layout);
-        // advance 8 tf32 = 32 bytes along K inside the swizzle row: +2 in the (addr>>4) field.  Fully unrolled: the single
-        // issuing thread must spend far fewer cycles per MMA than the MMA itself takes (N/2 cycles).
-        umma_tf32(tmem_base, adesc, bdesc, idesc, kb != 0 ? 1u : 0u);
-        if (++chunk_i == kchunks) {       // last chunk of this tap: possibly a channel tail with fewer valid k-steps
-          chunk_i = 0;
+        const bool last_chunk = (++chunk_i == kchunks);   // last chunk of a tap: possibly a channel tail with fewer valid k-steps
+        if (last_chunk) chunk_i = 0;
+        const bool rel = (sg + 1 == p.cg) || (kb + 1 == num_kb);   // release this group (the final, possibly partial, one too)
+        if (elect_one()) {
+          // advance 8 tf32 = 32 bytes along K inside the swizzle row: +2 in the (addr>>4) field
+          umma_tf32(tmem_base, adesc, bdesc, idesc, kb != 0 ? 1u : 0u);
+          if (last_chunk) {
 #pragma unroll
-          for (int k = 1; k < BK / 8; ++k)
-            if (k < tail_ks) umma_tf32(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, 1u);
-        } else {
+            for (int k = 1; k < BK / 8; ++k)
+              if (k < tail_ks) umma_tf32(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, 1u);
+          } else {
 #pragma unroll
-          for (int k = 1; k < BK / 8; ++k) umma_tf32(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, 1u);
+            for (int k = 1; k < BK / 8; ++k) umma_tf32(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, 1u);
+          }
+          if (rel) umma_commit(empty_bar(g));
         }
-        umma_commit(empty_bar(s));
-        if (++s == p.stages) { s = 0; ph ^= 1u; }
+        __syncwarp();
+        if (++sg == p.cg) { sg = 0; ++g; }
+        if (++s == p.stages) { s = 0; g = 0; ph ^= 1u; }
       }
-      umma_commit(tmem_full_bar);
+      if (elect_one()) umma_commit(tmem_full_bar);
+      __syncwarp();
     }
   } else {
     // ===== epilogue: warp w may only touch TMEM lanes [32*(w%4), 32*(w%4)+32)
@@ -390,16 +453,20 @@ struct PatchConvParams {
   int items_per_img;     // ceil(tiles_per_img / MT)
   int BN, n_tiles;
   int a_stages, b_stages;
+  int tg;                // filter taps per weight-ring release (3 = one tcgen05.commit per filter row, 1 = per tap); b_stages % tg == 0
   int tmem_cols;
   int act;
   int sb_vec;            // scale / bias pointers are 16-byte aligned (they may be views into a flat parameter buffer)
-  int dbg;               // tuning only (DGMR_PATCH_DBG): 1 = epilogue skips global traffic, 2 = issuer skips the MMAs
-  int64_t total_items;   // n_tiles * N * D * items_per_img
+  int dbg;               // tuning only (DGMR_PATCH_DBG): 1 = epilogue skips global traffic, 2 = issuer skips the MMAs, 4 = no TMA loads
+  int64_t total_items;   // n_tiles * N * D * items_per_img (pair: n_tiles * qpairs * items_per_img)
+  int64_t qpairs;        // pair mode: ceil(N*D / 2) image-depth slice pairs
   const float* bias; const float* scale; const float* res; float* y;
 };
 
 constexpr int kPatchThreads = 320;  // warp0 TMA, warp1 MMA, warps 2..9 epilogue
-template <int BK, int MT>
+// PAIR: launched as clusters of 2 CTAs (one TPC); see the cta_group::2 helpers above.  The two CTAs of a pair work on the SAME tile
+// position of two different images, so their activation patches have identical shared-memory geometry (one A descriptor serves both).
+template <int BK, int MT, bool PAIR>
 __global__ void __launch_bounds__(kPatchThreads, 1)
 conv_umma_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const PatchConvParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -409,7 +476,10 @@ conv_umma_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   const uint32_t row_bytes = (uint32_t)BK * 4u;
   const uint32_t patch_bytes = (uint32_t)p.Rb * p.P * row_bytes;
   const uint32_t patch_al = (patch_bytes + 1023u) & ~1023u;
-  const uint32_t b_bytes = (uint32_t)p.BN * row_bytes;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const int64_t wid = PAIR ? (int64_t)(blockIdx.x >> 1) : (int64_t)blockIdx.x;      // worker (CTA or CTA pair) index
+  const int64_t nworkers = PAIR ? (int64_t)(gridDim.x >> 1) : (int64_t)gridDim.x;
+  const uint32_t b_bytes = (uint32_t)(PAIR ? p.BN / 2 : p.BN) * row_bytes;      // a pair splits the weight tile: half the rows per CTA
   const uint32_t b_al = (b_bytes + 1023u) & ~1023u;
   const uint32_t a_base = base, b_base = base + p.a_stages * patch_al;
   const uint32_t bar_base = b_base + p.b_stages * b_al;
@@ -426,14 +496,16 @@ conv_umma_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    // pair: the leader's full barriers collect both CTAs' bytes (one arrival: its own expect_tx of the doubled byte count -- the peer's
+    // bytes may land first, the phase cannot complete before that arrival); its acc_empty collects all 16 epilogue warps
     for (int s = 0; s < p.a_stages; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1); }
     for (int s = 0; s < p.b_stages; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(acc_full(s), 1); mbar_init(acc_empty(s), 8); }
+    for (int s = 0; s < 2; ++s) { mbar_init(acc_full(s), 1); mbar_init(acc_empty(s), PAIR ? 16 : 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 0) { __syncwarp(); tmem_alloc(tmem_ptr_addr, (uint32_t)p.tmem_cols); }
+  if (warp == 0) { __syncwarp(); if (PAIR) tmem_alloc2(tmem_ptr_addr, (uint32_t)p.tmem_cols); else tmem_alloc(tmem_ptr_addr, (uint32_t)p.tmem_cols); }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all(); else __syncthreads();     // pair: the peer's barriers must exist before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_gen;
 
@@ -443,55 +515,89 @@ conv_umma_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   auto decode = [&](int64_t item, int& nt, int& n, int& d, int& fs) {
     int64_t t = item;
     const int ii = (int)(t % p.items_per_img); t /= p.items_per_img;
-    d = (int)(t % p.D); t /= p.D;
-    n = (int)(t % p.N); t /= p.N;
+    if (PAIR) {   // image-depth slices q = 2*qp + rank; an odd tail leaves the peer a slice past the end (TMA zero fill, rows discarded)
+      const int64_t q = 2 * (t % p.qpairs) + rank; t /= p.qpairs;
+      n = (int)(q / p.D); d = (int)(q - (int64_t)n * p.D);
+    } else {
+      d = (int)(t % p.D); t /= p.D;
+      n = (int)(t % p.N); t /= p.N;
+    }
     nt = (int)t;
     fs = p.P + 1 + 128 * MT * ii;
   };
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ===== TMA producer: one activation patch per (kd, channel chunk), nine weight tiles per patch.  The patch of step s+1 is
+    {
+      // ===== TMA producer (warp-uniform loop, elected lane issues): one activation patch per (kd, channel chunk), nine weight tiles per patch.  The patch of step s+1 is
       // issued BEFORE the weight tiles of step s, so the (large) patch load overlaps a whole step of MMAs.
       struct Cur { int64_t item; int kdi, c; };
       auto valid = [&](const Cur& q) { return q.item < p.total_items; };
       auto advance = [&](Cur& q) {
-        if (++q.c == chunks) { q.c = 0; if (++q.kdi == p.kd) { q.kdi = 0; q.item += gridDim.x; } }
+        if (++q.c == chunks) { q.c = 0; if (++q.kdi == p.kd) { q.kdi = 0; q.item += nworkers; } }
       };
-      int sa = 0, sb = 0; uint32_t pha = 0, phb = 0;
+      int sa = 0, sb = 0, gb = 0, tb = 0; uint32_t pha = 0, phb = 0;
       auto issue_patch = [&](const Cur& q) {
         int nt, n, d, fs; decode(q.item, nt, n, d, fs);
         const int r_lo = (fs - p.P - 1) / p.P;            // first padded image row of the patch
         mbar_wait(a_empty(sa), pha ^ 1u);
-        mbar_expect_tx(a_full(sa), patch_bytes);
-        tma_load_5d(a_base + sa * patch_al, &tmA, a_full(sa), q.c * BK, -1, r_lo - 1, d + q.kdi - p.kd / 2, n);
+        if (p.dbg & 4) {            // tuning: no loads, the MMAs run on whatever is in shared memory
+          if (rank == 0 && elect_one()) mbar_expect_tx(a_full(sa), 0);
+        } else if (PAIR) {
+          const uint32_t lead = mapa_rank(a_full(sa), 0);
+          if (elect_one()) {
+            if (rank == 0) mbar_expect_tx(a_full(sa), 2u * patch_bytes);   // the leader arms for both CTAs' bytes; the peer only sends them
+            tma_load_5d_2sm(a_base + sa * patch_al, &tmA, lead, q.c * BK, -1, r_lo - 1, d + q.kdi - p.kd / 2, n);
+          }
+        } else if (elect_one()) {
+          mbar_expect_tx(a_full(sa), patch_bytes);
+          tma_load_5d(a_base + sa * patch_al, &tmA, a_full(sa), q.c * BK, -1, r_lo - 1, d + q.kdi - p.kd / 2, n);
+        }
+        __syncwarp();
         if (++sa == p.a_stages) { sa = 0; pha ^= 1u; }
       };
-      Cur ca{(int64_t)blockIdx.x, 0, 0}, cb = ca;
+      Cur ca{wid, 0, 0}, cb = ca;
       if (valid(ca)) { issue_patch(ca); advance(ca); }
       while (valid(cb)) {
         if (valid(ca)) { issue_patch(ca); advance(ca); }
         int nt, n, d, fs; decode(cb.item, nt, n, d, fs);
         for (int tap = 0; tap < 9; ++tap) {
-          mbar_wait(b_empty(sb), phb ^ 1u);
-          mbar_expect_tx(b_full(sb), b_bytes);
-          tma_load_3d(b_base + sb * b_al, &tmB, b_full(sb), cb.c * BK, nt * p.BN, cb.kdi * 9 + tap);
-          if (++sb == p.b_stages) { sb = 0; phb ^= 1u; }
+          // weight tiles are released in groups of p.tg taps: a tcgen05.commit costs the tensor pipe ~780 cycles (measured,
+          // dgmr_debug_umma_rate), more than the 8 MMAs of one tap at N <= 128, so one commit per tap would throttle the MMAs
+          if (tb == 0) mbar_wait(b_empty(gb), phb ^ 1u);
+          if (p.dbg & 4) {
+            if (rank == 0 && elect_one()) mbar_expect_tx(b_full(sb), 0);
+          } else if (PAIR) {
+            const uint32_t lead = mapa_rank(b_full(sb), 0);
+            if (elect_one()) {
+              if (rank == 0) mbar_expect_tx(b_full(sb), 2u * b_bytes);
+              tma_load_3d_2sm(b_base + sb * b_al, &tmB, lead, cb.c * BK, nt * p.BN + (int)rank * (p.BN / 2), cb.kdi * 9 + tap);
+            }
+          } else if (elect_one()) {
+            mbar_expect_tx(b_full(sb), b_bytes);
+            tma_load_3d(b_base + sb * b_al, &tmB, b_full(sb), cb.c * BK, nt * p.BN, cb.kdi * 9 + tap);
+          }
+          __syncwarp();
+          if (++tb == p.tg) { tb = 0; ++gb; }
+          if (++sb == p.b_stages) { sb = 0; gb = 0; phb ^= 1u; }
         }
         advance(cb);
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===== MMA issuer
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((128u >> 4) << 24);
+    if (rank == 0) {
+      // ===== MMA issuer (pair: the leader alone, with M = 256 instructions spanning both CTAs); warp-uniform loop, elected lane issues
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.BN >> 3) << 17) | (((PAIR ? 256u : 128u) >> 4) << 24);
       constexpr uint32_t layout = (BK == 32) ? 2u : 4u;
       constexpr int ksteps = BK / 8;
       const int tail_ks = (p.Cin % BK) ? (p.Cin % BK) / 8 : ksteps;
       const uint64_t adesc0 = make_desc(a_base, 8u * row_bytes, layout);
       const uint64_t bdesc0 = make_desc(b_base, 8u * row_bytes, layout);
-      int sa = 0, sb = 0; uint32_t pha = 0, phb = 0, it = 0;   // ring positions advance incrementally: no divisions in the issue loop
-      for (int64_t item = blockIdx.x; item < p.total_items; item += gridDim.x, ++it) {
+      auto mma = [](uint32_t dcol, uint64_t ad, uint64_t bd, uint32_t id, uint32_t acc) {
+        if (PAIR) umma_tf32_2cta(dcol, ad, bd, id, acc); else umma_tf32(dcol, ad, bd, id, acc);
+      };
+      auto commit = [](uint32_t bar) { if (PAIR) umma_commit_pair(bar); else umma_commit(bar); };
+      int sa = 0, sb = 0, gb = 0, tb = 0; uint32_t pha = 0, phb = 0, it = 0;   // ring positions advance incrementally: no divisions in the issue loop
+      for (int64_t item = wid; item < p.total_items; item += nworkers, ++it) {
         int nt, n, d, fs; decode(item, nt, n, d, fs);
         const int r_lo = (fs - p.P - 1) / p.P;
         const int buf = it % p.NBUF; const uint32_t phacc = (it / p.NBUF) & 1u;
@@ -514,31 +620,37 @@ conv_umma_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             const uint64_t bdesc = bdesc0 + (uint64_t)((sb * b_al) >> 4);
             const uint64_t adesc = adesc0 + (uint64_t)((sa * patch_al + (uint32_t)j0 * row_bytes) >> 4);
             const uint32_t acc0 = (a | tap) != 0 ? 1u : 0u;
+            if (elect_one()) {
             if (p.dbg & 2) {
             } else if (!tail_now) {
 #pragma unroll
               for (int mt = 0; mt < MT; ++mt) {
 #pragma unroll
                 for (int k = 0; k < ksteps; ++k)
-                  umma_tf32(tacc + (uint32_t)(mt * p.BN), adesc + (uint64_t)(mt * 128 * (BK * 4 / 16) + 2 * k), bdesc + (uint64_t)(2 * k), idesc,
-                            k == 0 ? acc0 : 1u);
+                  mma(tacc + (uint32_t)(mt * p.BN), adesc + (uint64_t)(mt * 128 * (BK * 4 / 16) + 2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                      k == 0 ? acc0 : 1u);
               }
             } else {
 #pragma unroll
               for (int mt = 0; mt < MT; ++mt) {
 #pragma unroll
                 for (int k = 0; k < ksteps; ++k)
-                  if (k < tail_ks) umma_tf32(tacc + (uint32_t)(mt * p.BN), adesc + (uint64_t)(mt * 128 * (BK * 4 / 16) + 2 * k), bdesc + (uint64_t)(2 * k), idesc,
-                                             k == 0 ? acc0 : 1u);
+                  if (k < tail_ks) mma(tacc + (uint32_t)(mt * p.BN), adesc + (uint64_t)(mt * 128 * (BK * 4 / 16) + 2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                                       k == 0 ? acc0 : 1u);
               }
             }
-            umma_commit(b_empty(sb));
-            if (++sb == p.b_stages) { sb = 0; phb ^= 1u; }
+            if (tb + 1 == p.tg) commit(b_empty(gb));
+            }
+            __syncwarp();
+            if (++tb == p.tg) { tb = 0; ++gb; }
+            if (++sb == p.b_stages) { sb = 0; gb = 0; phb ^= 1u; }
           }
-          umma_commit(a_empty(sa));
+          if (elect_one()) commit(a_empty(sa));
+          __syncwarp();
           if (++sa == p.a_stages) { sa = 0; pha ^= 1u; }
         }
-        umma_commit(acc_full(buf));
+        if (elect_one()) commit(acc_full(buf));
+        __syncwarp();
       }
     }
   } else {
@@ -554,7 +666,7 @@ conv_umma_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     const uint32_t st_row = stg + (uint32_t)lane * 64u;
     const uint32_t st_sw = (uint32_t)((lane >> 1) & 3);
     uint32_t it = 0;
-    for (int64_t item = blockIdx.x; item < p.total_items; item += gridDim.x, ++it) {
+    for (int64_t item = wid; item < p.total_items; item += nworkers, ++it) {
       int nt, n, d, fs; decode(item, nt, n, d, fs);
       const int buf = it % p.NBUF; const uint32_t phacc = (it / p.NBUF) & 1u;
       const int co0 = nt * p.BN;
@@ -566,7 +678,7 @@ conv_umma_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       for (int j = 0; j < 4; ++j) {
         const int f = fs + 128 * mt + q * 32 + lr + 8 * j;
         const int hp = f / p.P, wp = f - hp * p.P;
-        vrow[j] = (wp >= 1) && (wp <= p.W) && (hp >= 1) && (hp <= p.H) && !(p.dbg & 1);
+        vrow[j] = (wp >= 1) && (wp <= p.W) && (hp >= 1) && (hp <= p.H) && (n < p.N) && !(p.dbg & 1);
         mrow[j] = ((((int64_t)n * p.D + d) * p.H + (hp - 1)) * p.W + (wp - 1)) * p.Cout + co0 + 4 * lc;
       }
       const int g = n / (p.N / p.G);
@@ -625,12 +737,15 @@ conv_umma_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       // this warp is done reading the accumulator buffer
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(acc_empty(buf)) : "memory");
+      if (lane == 0) {
+        if (PAIR) mbar_arrive_cluster(mapa_rank(acc_empty(buf), 0));   // the leader's MMA thread waits for both CTAs' epilogues
+        else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(acc_empty(buf)) : "memory");
+      }
     }
   }
   tc_fence_before();
-  __syncthreads();
-  if (warp == 0) { __syncwarp(); tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols); }
+  if (PAIR) cluster_sync_all(); else __syncthreads();
+  if (warp == 0) { __syncwarp(); if (PAIR) tmem_dealloc2(tmem_base, (uint32_t)p.tmem_cols); else tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols); }
 }
 
 // ------------------------------------------------------------------ wgrad on tensor cores
@@ -690,7 +805,7 @@ conv_umma_wgrad_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_co
   const uint32_t tmem_base = *tmem_ptr_gen;
 
   if (warp == 0) {
-    if (lane == 0 && num_kb > 0) {
+    if (num_kb > 0) {      // warp-uniform loop, elected lane issues (see elect_one)
       int s = 0; uint32_t ph = 0;
       for (int kb = kb0; kb < kb1; ++kb) {
         int t = kb;
@@ -699,16 +814,19 @@ conv_umma_wgrad_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_co
         const int d0 = t % p.D; t /= p.D;
         const int n0 = t * p.bn, w0 = wi * p.bw, h0 = hi * p.bh;
         mbar_wait(empty_bar(s), ph ^ 1u);
-        mbar_expect_tx(full_bar(s), a_bytes + b_bytes);
-        const uint32_t sa = base + s * stage_bytes;
-        for (int j = 0; j < a_blocks; ++j) tma_load_5d(sa + j * blk_bytes, &tmDz, full_bar(s), co0 + j * p.aw, w0, h0, d0, n0);
-        for (int j = 0; j < b_blocks; ++j)
-          tma_load_5d(sa + a_bytes + j * blk_bytes, &tmX, full_bar(s), ci0 + j * p.aw, w0 + tkw - p.kw / 2, h0 + tkh - p.kh / 2, d0 + tkd - p.kd / 2, n0);
+        if (elect_one()) {
+          mbar_expect_tx(full_bar(s), a_bytes + b_bytes);
+          const uint32_t sa = base + s * stage_bytes;
+          for (int j = 0; j < a_blocks; ++j) tma_load_5d(sa + j * blk_bytes, &tmDz, full_bar(s), co0 + j * p.aw, w0, h0, d0, n0);
+          for (int j = 0; j < b_blocks; ++j)
+            tma_load_5d(sa + a_bytes + j * blk_bytes, &tmX, full_bar(s), ci0 + j * p.aw, w0 + tkw - p.kw / 2, h0 + tkh - p.kh / 2, d0 + tkd - p.kd / 2, n0);
+        }
+        __syncwarp();
         if (++s == p.stages) { s = 0; ph ^= 1u; }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && num_kb > 0) {
+    if (num_kb > 0) {
       // instruction descriptor: f32 accum, tf32 x tf32, A and B MN-major, N = BN, M = 128
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(p.BN >> 3) << 17) | ((128u >> 4) << 24);
       // 32-bit MN-major operands need the 32-byte-atom swizzle (UMMA LayoutType SWIZZLE_128B_BASE32B = 1, written by TMA with
@@ -732,15 +850,20 @@ conv_umma_wgrad_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_co
         mbar_wait(full_bar(s), ph);
         tc_fence_after();
         const uint32_t sa = base + s * stage_bytes;
-        for (int k = 0; k < KP / 8; ++k) {
-          const uint64_t adesc = mn_desc(sa + k * kstep);
-          const uint64_t bdesc = mn_desc(sa + a_bytes + k * kstep);
-          umma_tf32(tmem_base, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < KP / 8; ++k) {
+            const uint64_t adesc = mn_desc(sa + k * kstep);
+            const uint64_t bdesc = mn_desc(sa + a_bytes + k * kstep);
+            umma_tf32(tmem_base, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(empty_bar(s));
         }
-        umma_commit(empty_bar(s));
+        __syncwarp();
         if (++s == p.stages) { s = 0; ph ^= 1u; }
       }
-      umma_commit(tmem_full_bar);
+      if (elect_one()) umma_commit(tmem_full_bar);
+      __syncwarp();
     }
   } else if (num_kb > 0) {
     const int q = warp & 3;
@@ -817,25 +940,28 @@ conv_umma_wgrad_row_kernel(const __grid_constant__ CUtensorMap tmDz, const __gri
   const uint32_t tmem_base = *tmem_ptr_gen;
 
   if (warp == 0) {
-    if (lane == 0 && num_kb > 0) {
+    if (num_kb > 0) {      // warp-uniform loop, elected lane issues (see elect_one)
       int s = 0; uint32_t ph = 0;
+      int ws = kb0 % p.wsegs, h, d, n;
+      { int t = kb0 / p.wsegs; h = t % p.H; t /= p.H; d = t % p.D; n = t / p.D; }
       for (int kb = kb0; kb < kb1; ++kb) {
-        int t = kb;
-        const int ws = t % p.wsegs; t /= p.wsegs;
-        const int h = t % p.H; t /= p.H;
-        const int d = t % p.D; const int n = t / p.D;
         const int w0 = ws * 32;
         mbar_wait(empty_bar(s), ph ^ 1u);
-        mbar_expect_tx(full_bar(s), tx_bytes);
-        const uint32_t sa = base + s * stage_bytes;
-        for (int j = 0; j < 4; ++j) tma_load_5d(sa + j * 4096u, &tmDz, full_bar(s), co0 + j * 32, w0, h, d, n);
-        for (int j = 0; j < p.b_blocks; ++j)
-          tma_load_5d(sa + a_bytes + j * kRowPatchPitch, &tmX, full_bar(s), ci0 + j * 32, w0 - 1, h + tkh - p.kh / 2, d + tkd - p.kd / 2, n);
+        if (elect_one()) {
+          mbar_expect_tx(full_bar(s), tx_bytes);
+          const uint32_t sa = base + s * stage_bytes;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) tma_load_5d(sa + j * 4096u, &tmDz, full_bar(s), co0 + j * 32, w0, h, d, n);
+          for (int j = 0; j < p.b_blocks; ++j)
+            tma_load_5d(sa + a_bytes + j * kRowPatchPitch, &tmX, full_bar(s), ci0 + j * 32, w0 - 1, h + tkh - p.kh / 2, d + tkd - p.kd / 2, n);
+        }
+        __syncwarp();
+        if (++ws == p.wsegs) { ws = 0; if (++h == p.H) { h = 0; if (++d == p.D) { d = 0; ++n; } } }
         if (++s == p.stages) { s = 0; ph ^= 1u; }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && num_kb > 0) {
+    if (num_kb > 0) {
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(p.BN >> 3) << 17) | ((128u >> 4) << 24);
       auto mn_desc = [&](uint32_t saddr, uint32_t lbo) {
         uint64_t d = 0;
@@ -851,14 +977,20 @@ conv_umma_wgrad_row_kernel(const __grid_constant__ CUtensorMap tmDz, const __gri
         mbar_wait(full_bar(s), ph);
         tc_fence_after();
         const uint32_t sa = base + s * stage_bytes;
-        for (int dw = 0; dw < 3; ++dw)
-          for (int k = 0; k < 4; ++k)
-            umma_tf32(tmem_base + (uint32_t)(dw * p.BN), mn_desc(sa + k * 1024u, 4096u), mn_desc(sa + a_bytes + (uint32_t)(dw + 8 * k) * 128u, kRowPatchPitch),
-                      idesc, (kb | k) != 0 ? 1u : 0u);
-        umma_commit(empty_bar(s));
+        if (elect_one()) {
+#pragma unroll
+          for (int dw = 0; dw < 3; ++dw)
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_tf32(tmem_base + (uint32_t)(dw * p.BN), mn_desc(sa + k * 1024u, 4096u), mn_desc(sa + a_bytes + (uint32_t)(dw + 8 * k) * 128u, kRowPatchPitch),
+                        idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit(empty_bar(s));
+        }
+        __syncwarp();
         if (++s == p.stages) { s = 0; ph ^= 1u; }
       }
-      umma_commit(tmem_full_bar);
+      if (elect_one()) umma_commit(tmem_full_bar);
+      __syncwarp();
     }
   } else if (num_kb > 0) {
     const int q = warp & 3;
@@ -933,6 +1065,45 @@ __global__ void __launch_bounds__(128, 1) umma_shift_probe_kernel(const __grid_c
   if (warp == 0) { __syncwarp(); tmem_dealloc(tmem_base, 256); }
 }
 
+// ------------------------------------------------------------------ issue-rate probe (debug entry point)
+// One thread per CTA issues `iters` kind::tf32 MMAs (M = 128, given N, K = 8) on zeroed shared memory and reports the cycles per
+// MMA: mode 0 = back to back, mode 1 = a tcgen05.commit after every 8 MMAs staying 3 commits ahead (as the conv kernels do per
+// filter tap), mode 2 = commit + wait every 8 MMAs (fully serialised).  Separates the tensor pipe's own rate from the pipeline around it.
+__global__ void __launch_bounds__(128, 1) umma_rate_probe_kernel(float* out, int N, int iters, int mode, int shift_rows) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  const uint32_t a_base = base, b_base = base + 32768u, bar = base + 65536u, tptr = bar + 64u;
+  for (uint32_t i = threadIdx.x; i < 16384u; i += blockDim.x) reinterpret_cast<float*>(smem_raw + (base - raw))[i] = 0.f;
+  if (threadIdx.x == 0) { for (int i = 0; i < 4; ++i) mbar_init(bar + 8u * i, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  if (threadIdx.x < 32) { __syncwarp(); tmem_alloc(tptr, 256); }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  tc_fence_before(); __syncthreads(); tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_raw + (tptr - raw));
+  if (threadIdx.x == 0) {
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
+    const uint64_t ad = make_desc(a_base + (uint32_t)shift_rows * 128u, 1024u, 2u), bd = make_desc(b_base, 1024u, 2u);   // shift: A starts off the swizzle atom
+    uint32_t ph[4] = {0, 0, 0, 0};
+    const long long t0 = clock64();
+    for (int i = 0; i < iters; i += 8) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) umma_tf32(tmem_base, ad + (uint64_t)(2 * (k & 3)) + (uint64_t)((k >> 2) * 1024), bd + (uint64_t)(2 * (k & 3)), idesc, 1u);
+      if (mode >= 1) {
+        const int s = (i >> 3) & 3;
+        umma_commit(bar + 8u * s);
+        if (mode == 2) { mbar_wait(bar + 8u * s, ph[s]); ph[s] ^= 1u; }
+        else if (i >= 24) { const int w = ((i >> 3) + 1) & 3; mbar_wait(bar + 8u * w, ph[w]); ph[w] ^= 1u; }   // stay 3 commits ahead
+      }
+    }
+    if (mode == 0) { umma_commit(bar); mbar_wait(bar, 0); }
+    else if (mode == 1) { for (int j = 1; j <= 3; ++j) { const int w = ((iters >> 3) + j) & 3; mbar_wait(bar + 8u * w, ph[w]); ph[w] ^= 1u; } }
+    const long long t1 = clock64();
+    out[blockIdx.x] = (float)(t1 - t0) / (float)iters;
+  }
+  tc_fence_before(); __syncthreads();
+  if (threadIdx.x < 32) { __syncwarp(); tmem_dealloc(tmem_base, 256); }
+}
+
 // ------------------------------------------------------------------ host side
 // channels per K block: 32 (128-byte rows) whenever Cin >= 32 -- a channel tail (Cin % 32 in {8,16,24}) is a last block whose
 // missing channels are TMA out-of-bounds zero fill and whose MMAs stop after the valid k-steps (64-byte-row TMA boxes move
@@ -999,6 +1170,12 @@ int launch_conv_umma_fwd(const float* x, const float* wp, const float* bias, con
   if (stages > 6) stages = 6;
   if ((uint32_t)stages * stage_bytes > 200u * 1024u) stages = (int)((200u * 1024u) / stage_bytes);
   if (stages < 2) { set_error("conv_umma_fwd: stage too large"); return 1; }
+  p.cg = 1;
+  if (p.BN <= 160) {            // short MMAs: release stages in groups so that commits stay >= ~700 cycles of MMA work apart
+    if (stages >= 6) { stages = 6; p.cg = 3; }
+    else if (stages >= 4) { stages = 4; p.cg = 2; }
+  }
+  if (const char* e = getenv("DGMR_UMMA_CG")) { if (atoi(e) == 1) p.cg = 1; }   // tuning knob
   p.stages = stages;
   size_t smem = (size_t)stages * stage_bytes + 1024 /*align slack*/ + 8 * (2 * stages + 2);
   const int taps = kd * kh * kw;
@@ -1159,9 +1336,13 @@ int launch_conv_umma_patch(const float* x, const float* wp, const float* bias, c
   }
   p.BN = (int)(ceil_div(ceil_div(Cout, p.n_tiles), 16) * 16);
   p.n_tiles = (int)ceil_div(Cout, p.BN);
+  // CTA pairs (cta_group::2): each CTA stages half of every weight tile, so the weight ring is twice as deep in the same shared
+  // memory and the weight bytes per SM halve -- the ring depth is what starves the MMAs at 96..192 channels
+  int pair = (p.BK == 32 && (int64_t)N * D >= 2 && p.BN % 16 == 0 && sm_count() % 2 == 0) ? 1 : 0;
+  if (const char* e = getenv("DGMR_PATCH_PAIR")) pair = pair && atoi(e) != 0;   // tuning knob
   // two sub-tiles per weight stage when accumulators and shared memory allow; double-buffer the accumulators when they still fit
   const uint32_t budget = 208u * 1024u;   // + 16 KB epilogue staging + barriers + alignment slack <= 226 KB
-  const uint32_t b_al = (((uint32_t)p.BN * row_bytes) + 1023u) & ~1023u;
+  const uint32_t b_al = (((uint32_t)(pair ? p.BN / 2 : p.BN) * row_bytes) + 1023u) & ~1023u;
   uint32_t patch_al = 0;
   p.a_stages = 2;
   bool fits = false;
@@ -1178,7 +1359,8 @@ int launch_conv_umma_patch(const float* x, const float* wp, const float* bias, c
   p.NBUF = (2 * p.MT * p.BN <= 512) ? 2 : 1;
   const int tiles_per_img = (int)ceil_div((int64_t)H * p.P - 2, 128);
   p.items_per_img = (int)ceil_div(tiles_per_img, p.MT);
-  p.total_items = (int64_t)p.n_tiles * N * D * p.items_per_img;
+  p.qpairs = ceil_div((int64_t)N * D, 2);
+  p.total_items = (int64_t)p.n_tiles * (pair ? p.qpairs : (int64_t)N * D) * p.items_per_img;
   p.act = act; p.bias = bias; p.scale = scale; p.res = res; p.y = y;
   p.sb_vec = (((reinterpret_cast<uintptr_t>(bias) | reinterpret_cast<uintptr_t>(scale)) & 15u) == 0) ? 1 : 0;
   p.dbg = 0; if (const char* e = getenv("DGMR_PATCH_DBG")) p.dbg = atoi(e);
@@ -1188,7 +1370,10 @@ int launch_conv_umma_patch(const float* x, const float* wp, const float* bias, c
   int need_cols = p.NBUF * p.MT * p.BN;
   p.tmem_cols = 32; while (p.tmem_cols < need_cols) p.tmem_cols <<= 1;
   p.b_stages = (int)((budget - 2 * patch_al) / b_al);
-  if (p.b_stages > 8) p.b_stages = 8;
+  if (p.b_stages > 9) p.b_stages = 9;
+  p.tg = 1;
+  if (p.b_stages >= 6) { p.tg = 3; p.b_stages = p.b_stages / 3 * 3; }   // one release (commit) per filter row of 3 taps, >= 2 rows in flight
+  if (const char* e = getenv("DGMR_PATCH_TG")) { if (atoi(e) == 1) p.tg = 1; }   // tuning knob
   size_t smem = (size_t)p.a_stages * patch_al + (size_t)p.b_stages * b_al + 1024 + 8 * (2 * p.a_stages + 2 * p.b_stages + 6) + 128 + 8 * 2048;
   CUtensorMap tmA, tmB;
   {
@@ -1202,28 +1387,44 @@ int launch_conv_umma_patch(const float* x, const float* wp, const float* bias, c
     const int taps = kd * 9;
     uint64_t dims[3] = {(uint64_t)Cin, (uint64_t)Cout, (uint64_t)taps};
     uint64_t str[2] = {(uint64_t)Cin * 4, (uint64_t)Cout * Cin * 4};
-    uint32_t box[3] = {(uint32_t)p.BK, (uint32_t)p.BN, 1u};
+    uint32_t box[3] = {(uint32_t)p.BK, (uint32_t)(pair ? p.BN / 2 : p.BN), 1u};
     int e = make_tmap(&tmB, wp, 3, dims, str, box, (int)row_bytes);
     if (e) return e;
   }
   static bool attr_set = false;
   if (!attr_set) {
     const int lim = 226 * 1024;
-    if (cudaFuncSetAttribute(conv_umma_patch_kernel<32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim) != cudaSuccess ||
-        cudaFuncSetAttribute(conv_umma_patch_kernel<32, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim) != cudaSuccess ||
-        cudaFuncSetAttribute(conv_umma_patch_kernel<16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim) != cudaSuccess ||
-        cudaFuncSetAttribute(conv_umma_patch_kernel<16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim) != cudaSuccess) {
+    if (cudaFuncSetAttribute(conv_umma_patch_kernel<32, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim) != cudaSuccess ||
+        cudaFuncSetAttribute(conv_umma_patch_kernel<32, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim) != cudaSuccess ||
+        cudaFuncSetAttribute(conv_umma_patch_kernel<16, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim) != cudaSuccess ||
+        cudaFuncSetAttribute(conv_umma_patch_kernel<16, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim) != cudaSuccess ||
+        cudaFuncSetAttribute(conv_umma_patch_kernel<32, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim) != cudaSuccess ||
+        cudaFuncSetAttribute(conv_umma_patch_kernel<32, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim) != cudaSuccess) {
       set_error("conv_umma_patch: cannot raise dynamic smem limit"); return 2;
     }
     attr_set = true;
   }
+  if (pair) {
+    int64_t grid = sm_count();                       // even (checked above): one CTA pair per TPC
+    if (grid > 2 * p.total_items) grid = 2 * p.total_items;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(kPatchThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaError_t e = (p.MT == 2) ? cudaLaunchKernelEx(&cfg, conv_umma_patch_kernel<32, 2, true>, tmA, tmB, p)
+                                : cudaLaunchKernelEx(&cfg, conv_umma_patch_kernel<32, 1, true>, tmA, tmB, p);
+    if (e != cudaSuccess) { set_error("conv_umma_patch: cluster launch failed: %s", cudaGetErrorString(e)); return 2; }
+    return 0;
+  }
   int64_t grid = sm_count();
   if (grid > p.total_items) grid = p.total_items;
   const dim3 g((unsigned)grid);
-  if (p.BK == 32 && p.MT == 2) conv_umma_patch_kernel<32, 2><<<g, kPatchThreads, smem, st>>>(tmA, tmB, p);
-  else if (p.BK == 32) conv_umma_patch_kernel<32, 1><<<g, kPatchThreads, smem, st>>>(tmA, tmB, p);
-  else if (p.MT == 2) conv_umma_patch_kernel<16, 2><<<g, kPatchThreads, smem, st>>>(tmA, tmB, p);
-  else conv_umma_patch_kernel<16, 1><<<g, kPatchThreads, smem, st>>>(tmA, tmB, p);
+  if (p.BK == 32 && p.MT == 2) conv_umma_patch_kernel<32, 2, false><<<g, kPatchThreads, smem, st>>>(tmA, tmB, p);
+  else if (p.BK == 32) conv_umma_patch_kernel<32, 1, false><<<g, kPatchThreads, smem, st>>>(tmA, tmB, p);
+  else if (p.MT == 2) conv_umma_patch_kernel<16, 2, false><<<g, kPatchThreads, smem, st>>>(tmA, tmB, p);
+  else conv_umma_patch_kernel<16, 1, false><<<g, kPatchThreads, smem, st>>>(tmA, tmB, p);
   DGMR_CHECK_LAUNCH("conv_umma_patch");
   return 0;
 }
@@ -1305,6 +1506,15 @@ int dgmr_debug_umma_shift(const float* A /*[256][32]*/, const float* B /*[N][32]
   if (cudaFuncSetAttribute(umma_shift_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { set_error("probe: smem attr"); return 2; }
   umma_shift_probe_kernel<<<1, 128, smem, S(stream)>>>(tmA, tmB, C, N, r0, mode);
   DGMR_CHECK_LAUNCH("umma_shift_probe");
+  return 0;
+}
+int dgmr_debug_umma_rate(float* out /*[blocks]*/, int blocks, int N, int iters, int mode, int shift_rows, dgmr_stream_t stream) {
+  DGMR_REQUIRE(N % 16 == 0 && N >= 16 && N <= 256 && iters % 8 == 0 && iters >= 64 && blocks > 0, "dgmr_debug_umma_rate: bad args");
+  const size_t smem = 65536 + 1024 + 128;
+  if (cudaFuncSetAttribute(umma_rate_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { set_error("probe: smem attr"); return 2; }
+  DGMR_REQUIRE(shift_rows >= 0 && shift_rows <= 64, "dgmr_debug_umma_rate: bad shift");
+  umma_rate_probe_kernel<<<blocks, 128, smem, S(stream)>>>(out, N, iters, mode, shift_rows);
+  DGMR_CHECK_LAUNCH("umma_rate_probe");
   return 0;
 }
 int dgmr_conv_umma_supported(int N, int D, int H, int W, int Cin, int Cout, int kd, int kh, int kw) {
