@@ -158,7 +158,7 @@ class CudaBackend:
         n = len(shape)
         arr = ctypes.c_int64 * n
         self._call("dgmr_permute", _f32(src, "src") + 4 * src_off, _f32(dst, "dst") + 4 * dst_off, n, arr(*shape), arr(*sstr),
-                   arr(*dstr), int(accumulate))
+                   arr(*dstr), int(accumulate), _info=f"{tuple(shape)} s{tuple(sstr)} d{tuple(dstr)}")
 
     def reduce_mid(self, x, y, A, R, C, accumulate=False):
         self._call("dgmr_reduce_mid", _f32(x, "x"), _f32(y, "y"), A, R, C, int(accumulate))
@@ -177,16 +177,16 @@ class CudaBackend:
         self._call("dgmr_relu_bwd", _f32(dy, "dy"), _f32(x, "x"), _f32(dx, "dx"), x.numel())
 
     def round_tf32(self, x, y=None):
-        self._call("dgmr_round_tf32", _f32(x, "x"), _f32(x if y is None else y, "y"), x.numel())
+        self._call("dgmr_round_tf32", _f32(x, "x"), _f32(x if y is None else y, "y"), x.numel(), _info=f"n{x.numel()} {'inplace' if y is None else 'copy'}")
 
     def split_tf32(self, x, hi, lo):
         self._call("dgmr_split_tf32", _f32(x, "x"), _f32(hi, "hi"), _f32(lo, "lo"), x.numel())
 
     def pool_sum(self, x, y, N, D, H, W, C, pd, ph, pw, scale):
-        self._call("dgmr_pool_sum", _f32(x, "x"), _f32(y, "y"), N, D, H, W, C, pd, ph, pw, float(scale))
+        self._call("dgmr_pool_sum", _f32(x, "x"), _f32(y, "y"), N, D, H, W, C, pd, ph, pw, float(scale), _info=f"{N}x{D}x{H}x{W}x{C} /{pd}{ph}{pw}")
 
     def upsample(self, x, y, N, D, H, W, C, ud, uh, uw, Do, Ho, Wo, scale):
-        self._call("dgmr_upsample", _f32(x, "x"), _f32(y, "y"), N, D, H, W, C, ud, uh, uw, Do, Ho, Wo, float(scale))
+        self._call("dgmr_upsample", _f32(x, "x"), _f32(y, "y"), N, D, H, W, C, ud, uh, uw, Do, Ho, Wo, float(scale), _info=f"{N}x{D}x{H}x{W}x{C} *{ud}{uh}{uw}")
 
     # -- GRU
     def gru_gate_fwd(self, pre_r, ld, h, rh, rows, Ch, flags=0):
@@ -224,7 +224,7 @@ class CudaBackend:
     def bn_bwd_apply(self, dy, x, a, b, mean, invstd, gamma, red, dx, dgamma, dbeta, accumulate, rows, G, C, relu, up2, H, W, training):
         self._call("dgmr_bn_bwd_apply", _f32(dy, "dy"), _f32(x, "x"), _f32(a, "a"), _f32(b, "b"), _f32(mean, "mean"),
                    _f32(invstd, "invstd"), _f32(gamma, "gamma"), _f64(red, "red"), _f32(dx, "dx"), _f32(dgamma, "dgamma"),
-                   _f32(dbeta, "dbeta"), int(accumulate), rows, G, C, int(relu), int(up2), H, W, int(training))
+                   _f32(dbeta, "dbeta"), int(accumulate), rows, G, C, int(relu), int(up2), H, W, int(training), _info=f"rows{rows} G{G} C{C} up{int(up2)}")
 
     # -- spectral norm
     def sn_power_iter(self, w, u, v, R, K, G, eps, training, inv_sigma, u_hist, v_hist, ws):

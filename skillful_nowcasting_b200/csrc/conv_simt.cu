@@ -611,6 +611,7 @@ int dgmr_conv_bwd_prep(const float* dy, const float* y, const float* res, const 
   if (dscale) DGMR_CUDA(cudaMemsetAsync(dscale, 0, sizeof(float) * (size_t)G * Cout, S(stream)));
   int64_t bpg = (int64_t)sm_count() * 16 / G; if (bpg < 1) bpg = 1;
   int64_t chunk = ceil_div(rows, bpg); if (chunk < 64) chunk = 64;
+  if (ceil_div(rows, chunk) * G < sm_count()) { chunk = ceil_div(rows * G, (int64_t)sm_count()); if (chunk < 8) chunk = 8; }   // small tensors (ConvGRU steps): fill the SMs
   dim3 grid((unsigned)ceil_div(rows, chunk), G);
   if (Cout % 4 == 0)
     conv_bwd_prep_kernel<4><<<grid, 256, 256 * 8 * sizeof(double), S(stream)>>>(dy, y, res, bias, scale, dz, dpre, dbias, dscale, rows, Cout, chunk, act, rnd);

@@ -37,17 +37,21 @@ struct PermuteArgs {
   int ndim;
   int64_t shape[8], sstr[8], dstr[8];
 };
-__global__ void permute_kernel(const float* __restrict__ src, float* __restrict__ dst, PermuteArgs a, int64_t total, int acc) {
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    int64_t rem = i, so = 0, dof = 0;
+// I = uint32_t when all offsets fit 32 bits (up to 8 div/mod pairs per element: 64-bit ones dominate the kernel otherwise)
+template <typename I>
+__global__ void permute_kernel(const float* __restrict__ src, float* __restrict__ dst, PermuteArgs a, int64_t total_, int acc) {
+  const I total = (I)total_;
+  for (I i = blockIdx.x * (I)blockDim.x + threadIdx.x; i < total; i += (I)gridDim.x * blockDim.x) {
+    I rem = i, so = 0, dof = 0;
 #pragma unroll
     for (int d = 7; d >= 0; --d) {
       if (d < a.ndim) {
-        int64_t q = rem / a.shape[d];
-        int64_t r = rem - q * a.shape[d];
+        const I sh = (I)a.shape[d];
+        I q = rem / sh;
+        I r = rem - q * sh;
         rem = q;
-        so += r * a.sstr[d];
-        dof += r * a.dstr[d];
+        so += r * (I)a.sstr[d];
+        dof += r * (I)a.dstr[d];
       }
     }
     float v = src[so];
@@ -144,12 +148,14 @@ __global__ void upsample_kernel(const float* __restrict__ x, float* __restrict__
   }
 }
 
+// I = uint32_t when every index fits 32 bits (a 64-bit div/mod costs ~4x a 32-bit one and these kernels do several per element)
+template <typename I>
 __global__ void pool_sum4_kernel(const float4* __restrict__ x, float4* __restrict__ y, int N, int D, int H, int W, int C4,
                                  int pd, int ph, int pw, float scale) {
   int Do = D / pd, Ho = H / ph, Wo = W / pw;
-  int64_t total = (int64_t)N * Do * Ho * Wo * C4;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    int c = i % C4; int64_t r = i / C4;
+  const I total = (I)N * Do * Ho * Wo * C4;
+  for (I i = blockIdx.x * (I)blockDim.x + threadIdx.x; i < total; i += (I)gridDim.x * blockDim.x) {
+    int c = i % C4; I r = i / C4;
     int wo = r % Wo; r /= Wo;
     int ho = r % Ho; r /= Ho;
     int dd = r % Do; int n = r / Do;
@@ -157,24 +163,26 @@ __global__ void pool_sum4_kernel(const float4* __restrict__ x, float4* __restric
     for (int a = 0; a < pd; ++a)
       for (int b = 0; b < ph; ++b)
         for (int e = 0; e < pw; ++e) {
-          float4 v = x[((((int64_t)n * D + dd * pd + a) * H + ho * ph + b) * W + wo * pw + e) * C4 + c];
+          float4 v = x[((((I)n * D + dd * pd + a) * H + ho * ph + b) * W + wo * pw + e) * C4 + c];
           s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
         }
     y[i] = make_float4(s.x * scale, s.y * scale, s.z * scale, s.w * scale);
   }
 }
+// I = uint32_t when every index fits 32 bits (a 64-bit div/mod costs ~4x a 32-bit one and these kernels do several per element)
+template <typename I>
 __global__ void upsample4_kernel(const float4* __restrict__ x, float4* __restrict__ y, int N, int D, int H, int W, int C4,
                                  int ud, int uh, int uw, int Do, int Ho, int Wo, float scale) {
-  int64_t total = (int64_t)N * Do * Ho * Wo * C4;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    int c = i % C4; int64_t r = i / C4;
+  const I total = (I)N * Do * Ho * Wo * C4;
+  for (I i = blockIdx.x * (I)blockDim.x + threadIdx.x; i < total; i += (I)gridDim.x * blockDim.x) {
+    int c = i % C4; I r = i / C4;
     int wo = r % Wo; r /= Wo;
     int ho = r % Ho; r /= Ho;
     int dd = r % Do; int n = r / Do;
     int ds = dd / ud, hs = ho / uh, ws = wo / uw;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (ds < D && hs < H && ws < W) {
-      float4 u = x[((((int64_t)n * D + ds) * H + hs) * W + ws) * C4 + c];
+      float4 u = x[((((I)n * D + ds) * H + hs) * W + ws) * C4 + c];
       v = make_float4(u.x * scale, u.y * scale, u.z * scale, u.w * scale);
     }
     y[i] = v;
@@ -392,21 +400,23 @@ __global__ void bn_apply_kernel(const float* __restrict__ x, const float* __rest
     y[i] = rnd ? rna_tf32_pw(v) : v;
   }
 }
+// I = uint32_t when every index fits 32 bits (a 64-bit div/mod costs ~4x a 32-bit one and these kernels do several per element)
+template <typename I>
 __global__ void bn_apply4_kernel(const float4* __restrict__ x, const float4* __restrict__ a, const float4* __restrict__ b, float4* __restrict__ y,
                                  int64_t rows, int G, int C4, int relu, int up2, int H, int W, int rnd) {
-  int64_t orows = up2 ? rows * 4 : rows;
-  int64_t total = (int64_t)G * orows * C4;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    int c = i % C4; int64_t r = i / C4;
+  const I orows = (I)(up2 ? rows * 4 : rows);
+  const I total = (I)G * orows * C4;
+  for (I i = blockIdx.x * (I)blockDim.x + threadIdx.x; i < total; i += (I)gridDim.x * blockDim.x) {
+    int c = i % C4; I r = i / C4;
     int g = r / orows;
-    int64_t xr = r;
+    I xr = r;
     if (up2) {
       int Wo = 2 * W, Ho = 2 * H;
-      int wo = r % Wo; int64_t t = r / Wo;
-      int ho = t % Ho; int64_t n = t / Ho;
+      int wo = r % Wo; I t = r / Wo;
+      int ho = t % Ho; I n = t / Ho;
       xr = (n * H + (ho >> 1)) * W + (wo >> 1);
     }
-    float4 aa = a[(int64_t)g * C4 + c], bb = b[(int64_t)g * C4 + c], u = x[xr * C4 + c];
+    float4 aa = a[g * C4 + c], bb = b[g * C4 + c], u = x[xr * C4 + c];
     float4 v = make_float4(aa.x * u.x + bb.x, aa.y * u.y + bb.y, aa.z * u.z + bb.z, aa.w * u.w + bb.w);
     if (relu) v = make_float4(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f), fmaxf(v.z, 0.f), fmaxf(v.w, 0.f));
     if (rnd) v = make_float4(rna_tf32_pw(v.x), rna_tf32_pw(v.y), rna_tf32_pw(v.z), rna_tf32_pw(v.w));
@@ -551,18 +561,20 @@ __global__ void bn_bwd_apply_kernel(const float* __restrict__ dy, const float* _
   }
 }
 // float4 variant (C % 4 == 0): one thread per 4 channels of one low-res row
+// I = uint32_t when every index fits 32 bits (a 64-bit div/mod costs ~4x a 32-bit one and these kernels do several per element)
+template <typename I>
 __global__ void bn_bwd_apply4_kernel(const float* __restrict__ dy, const float4* __restrict__ x, const float4* __restrict__ a, const float4* __restrict__ b,
                                      const float4* __restrict__ mean, const float4* __restrict__ invstd, const double* __restrict__ red, float4* __restrict__ dx,
                                      int64_t rows, int G, int C4, int relu, int up2, int H, int W, int training) {
   const int C = C4 * 4;
-  int64_t total = (int64_t)G * rows * C4;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    int c4 = i % C4; int64_t r = i / C4; int g = r / rows;
+  const I total = (I)G * (I)rows * C4;
+  for (I i = blockIdx.x * (I)blockDim.x + threadIdx.x; i < total; i += (I)gridDim.x * blockDim.x) {
+    int c4 = i % C4; I r = i / C4; int g = r / (I)rows;
     int64_t o4 = (int64_t)g * C4 + c4;
     float4 aa = a[o4], bb = b[o4], xv = x[i];
     float4 d;
     if (up2) {
-      int w = r % W; int64_t t = r / W; int h = t % H; int64_t n = t / H;
+      int w = r % W; I t = r / W; int h = t % H; int64_t n = t / H;
       const float4* p0 = reinterpret_cast<const float4*>(dy + ((n * 2 * H + 2 * h) * (2 * (int64_t)W) + 2 * w) * C) + c4;
       const float4* p1 = p0 + (int64_t)2 * W * C4;
       float4 q0 = p0[0], q1 = p0[C4], q2 = p1[0], q3 = p1[C4];
@@ -785,7 +797,11 @@ int dgmr_permute(const float* src, float* dst, int ndim, const int64_t* shape, c
   for (int d = 0; d < 8; ++d) { a.shape[d] = 1; a.sstr[d] = 0; a.dstr[d] = 0; }
   for (int d = 0; d < ndim; ++d) { a.shape[d] = shape[d]; a.sstr[d] = sstr[d]; a.dstr[d] = dstr[d]; total *= shape[d]; }
   if (total == 0) return 0;
-  permute_kernel<<<ew_grid(total, 256, 2), 256, 0, S(stream)>>>(src, dst, a, total, accumulate);
+  int64_t max_s = 0, max_d = 0; bool nonneg = true;
+  for (int d = 0; d < ndim; ++d) { max_s += (shape[d] - 1) * sstr[d]; max_d += (shape[d] - 1) * dstr[d]; nonneg = nonneg && sstr[d] >= 0 && dstr[d] >= 0; }
+  const int64_t lim = (int64_t)1 << 31;
+  if (nonneg && total < lim && max_s < lim && max_d < lim) permute_kernel<uint32_t><<<ew_grid(total, 256, 2), 256, 0, S(stream)>>>(src, dst, a, total, accumulate);
+  else permute_kernel<int64_t><<<ew_grid(total, 256, 2), 256, 0, S(stream)>>>(src, dst, a, total, accumulate);
   DGMR_CHECK_LAUNCH("dgmr_permute");
   return 0;
 }
@@ -848,7 +864,8 @@ int dgmr_pool_sum(const float* x, float* y, int N, int D, int H, int W, int C, i
   int64_t total = (int64_t)N * (D / pd) * (H / ph) * (W / pw) * C;
   if (total == 0) return 0;
   if (C % 4 == 0 && al16(x) && al16(y))
-    pool_sum4_kernel<<<ew_grid(total / 4, 256, 1), 256, 0, S(stream)>>>((const float4*)x, (float4*)y, N, D, H, W, C / 4, pd, ph, pw, scale);
+    if ((int64_t)N * D * H * W * C < (int64_t)1 << 31) pool_sum4_kernel<uint32_t><<<ew_grid(total / 4, 256, 1), 256, 0, S(stream)>>>((const float4*)x, (float4*)y, N, D, H, W, C / 4, pd, ph, pw, scale);
+    else pool_sum4_kernel<int64_t><<<ew_grid(total / 4, 256, 1), 256, 0, S(stream)>>>((const float4*)x, (float4*)y, N, D, H, W, C / 4, pd, ph, pw, scale);
   else
     pool_sum_kernel<<<ew_grid(total, 256, 2), 256, 0, S(stream)>>>(x, y, N, D, H, W, C, pd, ph, pw, scale);
   DGMR_CHECK_LAUNCH("dgmr_pool_sum");
@@ -859,7 +876,8 @@ int dgmr_upsample(const float* x, float* y, int N, int D, int H, int W, int C, i
   int64_t total = (int64_t)N * Do * Ho * Wo * C;
   if (total == 0) return 0;
   if (C % 4 == 0 && al16(x) && al16(y))
-    upsample4_kernel<<<ew_grid(total / 4, 256, 1), 256, 0, S(stream)>>>((const float4*)x, (float4*)y, N, D, H, W, C / 4, ud, uh, uw, Do, Ho, Wo, scale);
+    if (total < (int64_t)1 << 31) upsample4_kernel<uint32_t><<<ew_grid(total / 4, 256, 1), 256, 0, S(stream)>>>((const float4*)x, (float4*)y, N, D, H, W, C / 4, ud, uh, uw, Do, Ho, Wo, scale);
+    else upsample4_kernel<int64_t><<<ew_grid(total / 4, 256, 1), 256, 0, S(stream)>>>((const float4*)x, (float4*)y, N, D, H, W, C / 4, ud, uh, uw, Do, Ho, Wo, scale);
   else
     upsample_kernel<<<ew_grid(total, 256, 2), 256, 0, S(stream)>>>(x, y, N, D, H, W, C, ud, uh, uw, Do, Ho, Wo, scale);
   DGMR_CHECK_LAUNCH("dgmr_upsample");
@@ -902,7 +920,7 @@ static int64_t bn_chunk(int64_t rows, int G) {
   int64_t blocks_per_group = (int64_t)sm_count() * 16 / (G > 0 ? G : 1);
   if (blocks_per_group < 1) blocks_per_group = 1;
   int64_t chunk = ceil_div(rows, blocks_per_group);
-  if (chunk < 64) chunk = 64;
+  if (chunk < 16) chunk = 16;
   return chunk;
 }
 int dgmr_bn_stats(const float* x, double* sums, int64_t rows, int G, int C, dgmr_stream_t stream) {
@@ -930,7 +948,8 @@ int dgmr_bn_apply(const float* x, const float* a, const float* b, float* y, int6
   if (total == 0) return 0;
   DGMR_REQUIRE(!up2 || (rows % ((int64_t)H * W) == 0), "dgmr_bn_apply: rows not a multiple of H*W");
   if (C % 4 == 0 && al16(x) && al16(y) && al16(a) && al16(b))
-    bn_apply4_kernel<<<ew_grid(total / 4, 256, 1), 256, 0, S(stream)>>>((const float4*)x, (const float4*)a, (const float4*)b, (float4*)y, rows, G, C / 4, relu, up2, H, W, rnd);
+    if (total < (int64_t)1 << 31) bn_apply4_kernel<uint32_t><<<ew_grid(total / 4, 256, 1), 256, 0, S(stream)>>>((const float4*)x, (const float4*)a, (const float4*)b, (float4*)y, rows, G, C / 4, relu, up2, H, W, rnd);
+    else bn_apply4_kernel<int64_t><<<ew_grid(total / 4, 256, 1), 256, 0, S(stream)>>>((const float4*)x, (const float4*)a, (const float4*)b, (float4*)y, rows, G, C / 4, relu, up2, H, W, rnd);
   else
     bn_apply_kernel<<<ew_grid(total, 256, 2), 256, 0, S(stream)>>>(x, a, b, y, rows, G, C, relu, up2, H, W, rnd);
   DGMR_CHECK_LAUNCH("dgmr_bn_apply");
@@ -956,8 +975,12 @@ int dgmr_bn_bwd_apply(const float* dy, const float* x, const float* a, const flo
   int64_t total = (int64_t)G * rows * C;
   if (dx && total) {
     if (C % 4 == 0 && al16(dy) && al16(x) && al16(dx) && al16(a) && al16(b) && al16(mean) && al16(invstd))
-      bn_bwd_apply4_kernel<<<ew_grid(total / 4, 256, 1), 256, 0, S(stream)>>>(dy, (const float4*)x, (const float4*)a, (const float4*)b, (const float4*)mean,
-                                                                               (const float4*)invstd, red, (float4*)dx, rows, G, C / 4, relu, up2, H, W, training);
+      if (total * (up2 ? 4 : 1) < (int64_t)1 << 31)
+        bn_bwd_apply4_kernel<uint32_t><<<ew_grid(total / 4, 256, 1), 256, 0, S(stream)>>>(dy, (const float4*)x, (const float4*)a, (const float4*)b, (const float4*)mean,
+                                                                                         (const float4*)invstd, red, (float4*)dx, rows, G, C / 4, relu, up2, H, W, training);
+      else
+        bn_bwd_apply4_kernel<int64_t><<<ew_grid(total / 4, 256, 1), 256, 0, S(stream)>>>(dy, (const float4*)x, (const float4*)a, (const float4*)b, (const float4*)mean,
+                                                                                        (const float4*)invstd, red, (float4*)dx, rows, G, C / 4, relu, up2, H, W, training);
     else
       bn_bwd_apply_kernel<<<ew_grid(total, 256, 2), 256, 0, S(stream)>>>(dy, x, a, b, mean, invstd, red, dx, rows, G, C, relu, up2, H, W, training);
     DGMR_CHECK_LAUNCH("dgmr_bn_bwd_apply");
