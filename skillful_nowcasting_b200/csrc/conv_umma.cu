@@ -1165,14 +1165,19 @@ int launch_conv_umma_fwd(const float* x, const float* wp, const float* bias, con
   const uint32_t stage_bytes = a_bytes + b_bytes;
   // several CTAs per SM so one tile's epilogue / prologue overlaps another tile's main loop: aim at <= ~72 KB of
   // pipeline per CTA (3 resident CTAs) but never fewer than 3 stages; big tiles fall back to 1-2 CTAs per SM
-  int stages = (int)((72u * 1024u) / stage_bytes);
+  // ... unless the whole grid fits in one or two CTAs per SM anyway (ConvGRU steps, latent stack): those launches are pure
+  // latency chains (K blocks / stages in flight x ~1.5 us per TMA round trip), so they get all the shared memory they can use
+  const int64_t ctas_total = ceil_div(N, p.bn) * D * (H / p.bh) * (W / p.bw) * ntiles * (accumulate ? kd * kh * kw : 1);
+  const int per_sm = (int)(ceil_div(ctas_total, (int64_t)sm_count()) >= 3 ? 3 : ceil_div(ctas_total, (int64_t)sm_count()));
+  const uint32_t pipe_budget = per_sm >= 3 ? 72u * 1024u : per_sm == 2 ? 104u * 1024u : 200u * 1024u;
+  int stages = (int)(pipe_budget / stage_bytes);
   if (stages < 3) stages = 3;
-  if (stages > 6) stages = 6;
+  if (stages > (per_sm >= 3 ? 6 : 12)) stages = per_sm >= 3 ? 6 : 12;
   if ((uint32_t)stages * stage_bytes > 200u * 1024u) stages = (int)((200u * 1024u) / stage_bytes);
   if (stages < 2) { set_error("conv_umma_fwd: stage too large"); return 1; }
   p.cg = 1;
   if (p.BN <= 160) {            // short MMAs: release stages in groups so that commits stay >= ~700 cycles of MMA work apart
-    if (stages >= 6) { stages = 6; p.cg = 3; }
+    if (stages >= 6) { stages = stages / 3 * 3; p.cg = 3; }
     else if (stages >= 4) { stages = 4; p.cg = 2; }
   }
   if (const char* e = getenv("DGMR_UMMA_CG")) { if (atoi(e) == 1) p.cg = 1; }   // tuning knob
