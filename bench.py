@@ -87,31 +87,80 @@ def build_oracle_state(cfg, seed=0):
     return gen, disc
 
 
-def cpu_reference_steps(cfg, batch, steps, warmup, k):
-    """The reference's own CPU implementation of the path = the oracle port (oracle/dgmr_oracle.py: torch fp32 on the
-    host cores, all threads), timed on a bounded sample: the same 256x256 4->18 GAN step at batch `batch`."""
+def usable_cores() -> int:
+    """Host cores this process may really use: affinity mask and cgroup quota, not os.cpu_count() (on a box with a CPU quota,
+    one thread per visible core oversubscribes the quota and the oracle crawls)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            n = min(n, max(1, int(int(quota) / int(period))))
+    except (OSError, ValueError):
+        pass
+    return max(1, min(n, 32))     # the oracle's many small ops do not scale past a few tens of threads
+
+
+# bounded samples of the workload, largest first: (image side, forecast steps).  The discriminator needs side >= 128.
+CPU_SAMPLES = ((128, 18), (128, 6), (128, 2))
+
+
+def _cpu_sample_child(argv):
+    """Child process: time `steps` oracle GAN steps of one bounded sample and print one JSON line."""
+    side, t, batch, steps, k, lat, ctx, threads = (int(v) for v in argv)
     from oracle import dgmr_oracle as O
 
-    torch.set_num_threads(os.cpu_count() or 1)
+    torch.set_num_threads(threads)
+    cfg = dict(output_shape=side, forecast_steps=t, latent_channels=lat, context_channels=ctx)
     gen, disc = build_oracle_state(cfg)
     gs = O.clone_state(gen.state_dict(), requires_grad=True)
     ds = O.clone_state(disc.state_dict(), requires_grad=True)
     g_opt = O.AdamState([gs[n] for n in O._trainable(gs)], lr=5e-5)
     d_opt = O.AdamState([ds[n] for n in O._trainable(ds)], lr=2e-4)
-    s = cfg["output_shape"]
     torch.manual_seed(1234)
-    x, y = torch.rand(batch, 4, 1, s, s), torch.rand(batch, cfg["forecast_steps"], 1, s, s)
+    x, y = torch.rand(batch, 4, 1, side, side), torch.rand(batch, t, 1, side, side)
     times = []
-    for i in range(warmup + steps):
+    for _ in range(steps):
         t0 = time.perf_counter()
-        O.gan_step(gs, ds, g_opt, d_opt, x, y, cfg["forecast_steps"], (8, s // 32, s // 32), generation_steps=k)
-        dt = time.perf_counter() - t0
-        if i >= warmup:
-            times.append(dt)
-    mean = sum(times) / len(times)
-    return dict(value=batch * cfg["forecast_steps"] / mean, unit="frames/s", cores=torch.get_num_threads(), kind="port",
-                sample=f"full GAN step (same 256x256 4->18 shapes and widths) at batch {batch}, {len(times)} timed step(s), "
-                       f"{mean:.2f} s/step", s_per_step=mean)
+        O.gan_step(gs, ds, g_opt, d_opt, x, y, t, (8, side // 32, side // 32), generation_steps=k)
+        times.append(time.perf_counter() - t0)
+        print(json.dumps(dict(times=times)), flush=True)      # partial results survive a timeout
+
+
+def cpu_reference_steps(cfg, batch, steps, warmup, k, budget_s=150.0):
+    """The reference's own CPU implementation of the path = the oracle port (oracle/dgmr_oracle.py: torch fp32 on the host
+    cores), timed on a BOUNDED sample and scaled to the metric's unit.  A sample is the same GAN step (same widths, same
+    schedule) on smaller frames / fewer lead times; its time is scaled by the pixel-and-frame ratio to the full
+    256x256 4->18 step (the step is convolution-dominated, cost ~ pixels x frames).  Runs in a child process under a wall-clock
+    budget so that a slow host can never stall the benchmark: on timeout the next smaller sample is tried."""
+    import subprocess
+
+    threads = usable_cores()
+    full_side, full_t = cfg["output_shape"], cfg["forecast_steps"]
+    n_steps = max(1, steps + warmup)
+    last_err = "no sample finished"
+    for side, t in CPU_SAMPLES:
+        side, t = min(side, full_side), min(t, full_t)
+        cmd = [sys.executable, os.path.abspath(__file__), "--cpu-sample-child", str(side), str(t), str(batch), str(n_steps), str(k),
+               str(cfg["latent_channels"]), str(cfg["context_channels"]), str(threads)]
+        t_start = time.perf_counter()
+        out = ""
+        try:
+            out = subprocess.run(cmd, capture_output=True, text=True, timeout=budget_s).stdout
+        except subprocess.TimeoutExpired as e:
+            out = e.stdout.decode() if isinstance(e.stdout, bytes) else (e.stdout or "")
+            last_err = f"sample {side}x{side} 4->{t} exceeded {budget_s:.0f} s"
+        lines = [ln for ln in out.splitlines() if ln.startswith("{")]
+        times = json.loads(lines[-1])["times"] if lines else []
+        budget_s = max(30.0, budget_s - (time.perf_counter() - t_start))
+        if len(times) > warmup or (times and len(times) == n_steps):
+            timed = times[warmup:] if len(times) > warmup else times
+            mean = sum(timed) / len(timed)
+            scale = (full_side * full_side * full_t) / float(side * side * t)
+            full_step_s = mean * scale
+            return dict(value=batch * full_t / full_step_s, unit="frames/s", cores=threads, kind="port", s_per_step=full_step_s,
+                        sample=f"oracle port, full GAN step (same widths and schedule) on {side}x{side} frames, 4->{t} lead times, batch {batch}: "
+                               f"{len(timed)} timed step(s) of {mean:.2f} s, scaled x{scale:.1f} (pixels x frames) to the 256x256 4->18 step")
+    return dict(value=None, unit="frames/s", cores=threads, kind="port", s_per_step=float("nan"), sample=f"unavailable: {last_err}")
 
 
 def gpu_reference_steps(cfg, batch, steps, warmup, k, dev):
@@ -181,9 +230,9 @@ def main():
         if rank != 0:
             return
         warm = min(args.warmup, 1)
-        r = cpu_reference_steps(cfg, args.cpu_batch, max(1, min(args.steps, 3)), warm, K)
+        r = cpu_reference_steps(cfg, args.cpu_batch, max(1, min(args.steps, 3)), warm, K, budget_s=240.0)
         line = dict(impl="reference", metric="radar frames/sec (G+D step, 256x256, 4->18)", value=r["value"], unit="frames/s",
-                    n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=r["s_per_step"] * 1e3, higher_is_better=True,
+                    n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=(r["s_per_step"] * 1e3 if r["value"] else None), higher_is_better=True,
                     scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
                     config=dict(workload=workload, note="CPU arm runs the oracle port on a bounded sample"),
                     cpu_baseline=dict(value=r["value"], unit="frames/s", cores=r["cores"], kind="port", sample=r["sample"]),
@@ -307,7 +356,7 @@ def main():
     if args.ref_gpu:
         line["reference_gpu_eager"] = gpu_reference_steps(cfg, args.ref_gpu, 2, 1, K, dev)
     if not args.no_cpu_baseline:
-        r = cpu_reference_steps(cfg, args.cpu_batch, 1, 0, K)
+        r = cpu_reference_steps(cfg, args.cpu_batch, 1, 0, K, budget_s=90.0)
         line["cpu_baseline"] = dict(value=r["value"], unit="frames/s", cores=r["cores"], kind="port", sample=r["sample"])
     print(json.dumps(line))
     if world > 1:
@@ -315,4 +364,7 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "--cpu-sample-child":
+        _cpu_sample_child(sys.argv[2:])
+    else:
+        main()
