@@ -247,6 +247,7 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout to the one JSON line (NCCL prints its version banner there)
         dist.init_process_group("nccl", device_id=dev)
     be = _lib.backend()  # raises if libdgmr_b200.so is missing: no fallback
     gen, disc = build_oracle_state(cfg, seed=0)  # identical replicas on every rank
