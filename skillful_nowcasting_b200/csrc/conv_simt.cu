@@ -257,41 +257,54 @@ __global__ void __launch_bounds__(256) conv_bwd_prep_kernel(const float* __restr
 #pragma unroll
       for (int i = 0; i < V; ++i) { sc[i] = scale ? scale[(int64_t)g * C + c + i] : 1.f; bi[i] = bias ? bias[c + i] : 0.f; fs[i] = 0.f; fq[i] = 0.f; }
       int cnt = 0;
-      for (int64_t r = r0 + rl; r < r1; r += rp) {
-        const int64_t o = ((int64_t)g * rows + r) * C + c;
-        float d[V], yv[V], rv[V];
+      // one row: loads are issued by `load`, consumed by `finish`, so that two rows' loads are in flight together below
+      struct Row { float d[V], yv[V], rv[V]; int64_t o; };
+      auto load = [&](int64_t r, Row& w) {
+        w.o = ((int64_t)g * rows + r) * C + c;
         if (V == 4) {
-          float4 t = *reinterpret_cast<const float4*>(dy + o); d[0] = t.x; d[1] = t.y; d[2] = t.z; d[3] = t.w;
-          if (y) { float4 u = *reinterpret_cast<const float4*>(y + o); yv[0] = u.x; yv[1] = u.y; yv[2] = u.z; yv[3] = u.w; }
-          if (res && dscale) { float4 u = *reinterpret_cast<const float4*>(res + o); rv[0] = u.x; rv[1] = u.y; rv[2] = u.z; rv[3] = u.w; }
+          float4 t = *reinterpret_cast<const float4*>(dy + w.o); w.d[0] = t.x; w.d[1] = t.y; w.d[2] = t.z; w.d[3] = t.w;
+          if (y) { float4 u = *reinterpret_cast<const float4*>(y + w.o); w.yv[0] = u.x; w.yv[1] = u.y; w.yv[2] = u.z; w.yv[3] = u.w; }
+          if (res && dscale) { float4 u = *reinterpret_cast<const float4*>(res + w.o); w.rv[0] = u.x; w.rv[1] = u.y; w.rv[2] = u.z; w.rv[3] = u.w; }
         } else {
-          d[0] = dy[o];
-          if (y) yv[0] = y[o];
-          if (res && dscale) rv[0] = res[o];
+          w.d[0] = dy[w.o];
+          if (y) w.yv[0] = y[w.o];
+          if (res && dscale) w.rv[0] = res[w.o];
         }
+      };
+      auto finish = [&](Row& w) {
         float zo[V];
 #pragma unroll
         for (int i = 0; i < V; ++i) {
-          float yy = y ? yv[i] : 0.f;
-          if (act == DGMR_ACT_RELU && !(yy > 0.f)) d[i] = 0.f;
-          zo[i] = d[i] * sc[i];
+          float yy = y ? w.yv[i] : 0.f;
+          if (act == DGMR_ACT_RELU && !(yy > 0.f)) w.d[i] = 0.f;
+          zo[i] = w.d[i] * sc[i];
           if (rnd) zo[i] = rna_tf32(zo[i]);
-          fs[i] += d[i];
-          if (dscale) fq[i] += d[i] * (yy - bi[i] - ((res) ? rv[i] : 0.f));
+          fs[i] += w.d[i];
+          if (dscale) fq[i] += w.d[i] * (yy - bi[i] - ((res) ? w.rv[i] : 0.f));
         }
         if (V == 4) {
-          if (dz) *reinterpret_cast<float4*>(dz + o) = make_float4(zo[0], zo[1], zo[2], zo[3]);
-          if (dpre) *reinterpret_cast<float4*>(dpre + o) = make_float4(d[0], d[1], d[2], d[3]);
+          if (dz) *reinterpret_cast<float4*>(dz + w.o) = make_float4(zo[0], zo[1], zo[2], zo[3]);
+          if (dpre) *reinterpret_cast<float4*>(dpre + w.o) = make_float4(w.d[0], w.d[1], w.d[2], w.d[3]);
         } else {
-          if (dz) dz[o] = zo[0];
-          if (dpre) dpre[o] = d[0];
+          if (dz) dz[w.o] = zo[0];
+          if (dpre) dpre[w.o] = w.d[0];
         }
-        if (++cnt == 64) {
+      };
+      auto flush = [&]() {
+        if (++cnt == 32) {
 #pragma unroll
           for (int i = 0; i < V; ++i) { s[i] += fs[i]; q[i] += fq[i]; fs[i] = 0.f; fq[i] = 0.f; }
           cnt = 0;
         }
+      };
+      int64_t r = r0 + rl;
+      for (; r + rp < r1; r += 2 * (int64_t)rp) {
+        Row a, b;
+        load(r, a); load(r + rp, b);
+        finish(a); finish(b);
+        flush();
       }
+      for (; r < r1; r += rp) { Row a; load(r, a); finish(a); flush(); }
 #pragma unroll
       for (int i = 0; i < V; ++i) { s[i] += fs[i]; q[i] += fq[i]; }
       if (dbias || dscale) {

@@ -1368,7 +1368,10 @@ int launch_conv_umma_patch(const float* x, const float* wp, const float* bias, c
   p.total_items = (int64_t)p.n_tiles * (pair ? p.qpairs : (int64_t)N * D) * p.items_per_img;
   p.act = act; p.bias = bias; p.scale = scale; p.res = res; p.y = y;
   p.sb_vec = (((reinterpret_cast<uintptr_t>(bias) | reinterpret_cast<uintptr_t>(scale)) & 15u) == 0) ? 1 : 0;
-  p.dbg = 0; if (const char* e = getenv("DGMR_PATCH_DBG")) p.dbg = atoi(e);
+  p.dbg = 0;
+#ifdef DGMR_TUNING      // the knob makes the kernel skip work (wrong results): only in tuning builds
+  if (const char* e = getenv("DGMR_PATCH_DBG")) p.dbg = atoi(e);
+#endif
   if (((reinterpret_cast<uintptr_t>(res) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(wp)) & 15u) != 0) {
     set_error("conv_umma_patch: x / wp / res / y must be 16-byte aligned"); return 1;
   }
