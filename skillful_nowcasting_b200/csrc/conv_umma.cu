@@ -762,6 +762,7 @@ struct UmmaWgradParams {
   int BN;                 // ci tile (multiple of 16 and of aw, <= 256)
   int ci_tiles;
   int stages, tmem_cols;
+  int cg;                 // stages per release group (one tcgen05.commit hands cg stages back); stages % cg == 0
   int kb_total, kb_chunk;
   float* dwp;
 };
@@ -805,15 +806,15 @@ conv_umma_wgrad_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_co
   const uint32_t tmem_base = *tmem_ptr_gen;
 
   if (warp == 0) {
-    if (num_kb > 0) {      // warp-uniform loop, elected lane issues (see elect_one)
-      int s = 0; uint32_t ph = 0;
+    if (num_kb > 0) {      // warp-uniform loop, elected lane issues (see elect_one); stages come back in groups of p.cg
+      int s = 0, g = 0, sg = 0; uint32_t ph = 0;
       for (int kb = kb0; kb < kb1; ++kb) {
         int t = kb;
         const int wi = t % p.tiles_w; t /= p.tiles_w;
         const int hi = t % p.tiles_h; t /= p.tiles_h;
         const int d0 = t % p.D; t /= p.D;
         const int n0 = t * p.bn, w0 = wi * p.bw, h0 = hi * p.bh;
-        mbar_wait(empty_bar(s), ph ^ 1u);
+        if (sg == 0) mbar_wait(empty_bar(g), ph ^ 1u);
         if (elect_one()) {
           mbar_expect_tx(full_bar(s), a_bytes + b_bytes);
           const uint32_t sa = base + s * stage_bytes;
@@ -822,7 +823,8 @@ conv_umma_wgrad_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_co
             tma_load_5d(sa + a_bytes + j * blk_bytes, &tmX, full_bar(s), ci0 + j * p.aw, w0 + tkw - p.kw / 2, h0 + tkh - p.kh / 2, d0 + tkd - p.kd / 2, n0);
         }
         __syncwarp();
-        if (++s == p.stages) { s = 0; ph ^= 1u; }
+        if (++sg == p.cg) { sg = 0; ++g; }
+        if (++s == p.stages) { s = 0; g = 0; ph ^= 1u; }
       }
     }
   } else if (warp == 1) {
@@ -845,11 +847,12 @@ conv_umma_wgrad_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_co
         d |= (uint64_t)layout << 61;
         return d;
       };
-      int s = 0; uint32_t ph = 0;
+      int s = 0, g = 0, sg = 0; uint32_t ph = 0;
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(full_bar(s), ph);
         tc_fence_after();
         const uint32_t sa = base + s * stage_bytes;
+        const bool rel = (sg + 1 == p.cg) || (kb + 1 == num_kb);
         if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < KP / 8; ++k) {
@@ -857,10 +860,11 @@ conv_umma_wgrad_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_co
             const uint64_t bdesc = mn_desc(sa + a_bytes + k * kstep);
             umma_tf32(tmem_base, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(empty_bar(s));
+          if (rel) umma_commit(empty_bar(g));
         }
         __syncwarp();
-        if (++s == p.stages) { s = 0; ph ^= 1u; }
+        if (++sg == p.cg) { sg = 0; ++g; }
+        if (++s == p.stages) { s = 0; g = 0; ph ^= 1u; }
       }
       if (elect_one()) umma_commit(tmem_full_bar);
       __syncwarp();
@@ -1260,11 +1264,14 @@ int launch_conv_umma_wgrad(const float* x, const float* dz, float* dwp, int N, i
   p.tmem_cols = 32; while (p.tmem_cols < p.BN) p.tmem_cols <<= 1;
   const uint32_t blk_bytes = 32u * p.aw * 4u;
   const uint32_t stage_bytes = (128 / p.aw + p.BN / p.aw) * blk_bytes;
-  int stages = (int)((72u * 1024u) / stage_bytes);
-  if (stages < 3) stages = 3;
-  if (stages > 6) stages = 6;
-  if ((uint32_t)stages * stage_bytes > 200u * 1024u) stages = (int)((200u * 1024u) / stage_bytes);
+  // one CTA per SM (launch bounds): use the shared memory for stages, handed back in groups so that a tcgen05.commit (which costs
+  // the pipe ~780 cycles) follows >= 8 MMAs (4 per stage, 128..512 cycles each group otherwise)
+  int stages = (int)((200u * 1024u) / stage_bytes);
+  if (stages > 8) stages = 8;
   if (stages < 2) { set_error("conv_umma_wgrad: stage too large"); return 1; }
+  p.cg = 1;
+  if (stages >= 6 && p.BN <= 128) { stages = stages / 3 * 3; p.cg = 3; }
+  else if (stages >= 4) { stages = stages / 2 * 2; p.cg = 2; }
   p.stages = stages;
   size_t smem = (size_t)stages * stage_bytes + 1024 + 8 * (2 * stages + 2);
   const int taps = kd * kh * kw;
