@@ -191,6 +191,7 @@ struct UmmaConvParams {
   int tmem_cols;
   int act;
   int split_taps;        // 1: blockIdx.z = filter tap, epilogue red.adds acc*scale into y
+  int n_tiles;           // persistent variant: Cout tiles
   const float* bias; const float* scale; const float* res; float* y;
 };
 
@@ -432,6 +433,193 @@ conv_umma_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     __syncwarp();
     tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
   }
+}
+
+// ------------------------------------------------------------------ plain conv, persistent variant
+// Same tiles and pipeline stages as conv_umma_fwd_kernel, but each CTA walks many tiles: barrier setup, TMEM allocation and the
+// pipeline fill are paid once per CTA instead of once per 128-pixel tile, the K-block stream of consecutive tiles is continuous
+// and the accumulator is double-buffered in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.  For launches with
+// many tiles and a short K loop (1x1 convs, narrow layers) the per-tile fixed cost was most of the time.
+template <int BK>
+__global__ void __launch_bounds__(kUmmaThreads, 1)
+conv_umma_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const UmmaConvParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t a_bytes = 128u * BK * 4u, b_bytes = (uint32_t)p.BN * BK * 4u;
+  const uint32_t b_bytes_al = (b_bytes + 1023u) & ~1023u;
+  const uint32_t stage_bytes = a_bytes + b_bytes_al;
+  const uint32_t bar_base = base + p.stages * stage_bytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (p.stages + s); };
+  auto tmem_full = [&](int bsel) { return bar_base + 8u * (2 * p.stages + bsel); };
+  auto tmem_empty = [&](int bsel) { return bar_base + 8u * (2 * p.stages + 2 + bsel); };
+  const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * p.stages + 4);
+  volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_addr - raw));
+  const uint32_t epi_base = (tmem_ptr_addr + 8u + 127u) & ~127u;     // 4 epilogue warps x 2 KB transpose staging
+
+  const int64_t mtiles = (int64_t)((p.N + p.bn - 1) / p.bn) * p.D * p.tiles_h * p.tiles_w;
+  const int64_t total_tiles = mtiles * p.n_tiles;
+  auto decode = [&](int64_t t, int& n0, int& d0, int& h0, int& w0, int& co0) {
+    int64_t mt = t % mtiles; co0 = (int)(t / mtiles) * p.BN;
+    const int tw_i = (int)(mt % p.tiles_w); mt /= p.tiles_w;
+    const int th_i = (int)(mt % p.tiles_h); mt /= p.tiles_h;
+    d0 = (int)(mt % p.D); mt /= p.D;
+    n0 = (int)mt * p.bn; w0 = tw_i * p.bw; h0 = th_i * p.bh;
+  };
+  const int taps = p.kd * p.kh * p.kw;
+  const int kchunks = (p.Cin + BK - 1) / BK;
+  const int num_kb = taps * kchunks;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int bsel = 0; bsel < 2; ++bsel) { mbar_init(tmem_full(bsel), 1); mbar_init(tmem_empty(bsel), 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) { __syncwarp(); tmem_alloc(tmem_ptr_addr, (uint32_t)p.tmem_cols); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_gen;
+
+  if (warp == 0) {
+    // ===== TMA producer: one continuous stream of K blocks over all of this CTA's tiles
+    int s = 0, g = 0, sg = 0; uint32_t ph = 0;
+    for (int64_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      int n0, d0, h0, w0, co0; decode(t, n0, d0, h0, w0, co0);
+      int tap = 0, chunk = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int c0 = chunk * BK;
+        const int tkw = tap % p.kw, tkh = (tap / p.kw) % p.kh, tkd = tap / (p.kw * p.kh);
+        if (sg == 0) mbar_wait(empty_bar(g), ph ^ 1u);
+        if (elect_one()) {
+          mbar_expect_tx(full_bar(s), a_bytes + b_bytes);
+          const uint32_t sa = base + s * stage_bytes;
+          tma_load_5d(sa, &tmA, full_bar(s), c0, w0 + tkw - p.kw / 2, h0 + tkh - p.kh / 2, d0 + tkd - p.kd / 2, n0);
+          tma_load_3d(sa + a_bytes, &tmB, full_bar(s), c0, co0, tap);
+        }
+        __syncwarp();
+        if (++chunk == kchunks) { chunk = 0; ++tap; }
+        if (++sg == p.cg) { sg = 0; ++g; }
+        if (++s == p.stages) { s = 0; g = 0; ph ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((128u >> 4) << 24);
+    const uint32_t row_bytes = BK * 4u;
+    const uint32_t layout = row_bytes == 128 ? 2u : (row_bytes == 64 ? 4u : 6u);
+    const uint32_t sbo = 8u * row_bytes;
+    const int tail_ks = (p.Cin % BK) ? (p.Cin % BK) / 8 : BK / 8;
+    int s = 0, g = 0, sg = 0; uint32_t ph = 0, it = 0;
+    for (int64_t t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+      const int bsel = it & 1; const uint32_t phacc = (it >> 1) & 1u;
+      mbar_wait(tmem_empty(bsel), phacc ^ 1u);       // the epilogue has drained this accumulator buffer
+      tc_fence_after();
+      const uint32_t tacc = tmem_base + (uint32_t)(bsel * p.BN);
+      int chunk_i = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(full_bar(s), ph);
+        tc_fence_after();
+        const uint32_t sa = base + s * stage_bytes;
+        const uint64_t adesc = make_desc(sa, sbo, layout);
+        const uint64_t bdesc = make_desc(sa + a_bytes, sbo, layout);
+        const bool last_chunk = (++chunk_i == kchunks);
+        if (last_chunk) chunk_i = 0;
+        const bool last_kb = (kb + 1 == num_kb);
+        const bool rel = (sg + 1 == p.cg) || (last_kb && t + gridDim.x >= total_tiles);   // group full, or the very last K block
+        if (elect_one()) {
+          umma_tf32(tacc, adesc, bdesc, idesc, kb != 0 ? 1u : 0u);
+          if (last_chunk) {
+#pragma unroll
+            for (int k = 1; k < BK / 8; ++k)
+              if (k < tail_ks) umma_tf32(tacc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, 1u);
+          } else {
+#pragma unroll
+            for (int k = 1; k < BK / 8; ++k) umma_tf32(tacc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, 1u);
+          }
+          if (rel) umma_commit(empty_bar(g));
+          if (last_kb) umma_commit(tmem_full(bsel));
+        }
+        __syncwarp();
+        if (++sg == p.cg) { sg = 0; ++g; }
+        if (++s == p.stages) { s = 0; g = 0; ph ^= 1u; }
+      }
+    }
+  } else {
+    // ===== epilogue (4 warps): warp w may only touch TMEM lanes [32*(w%4), +32); coalesced through a 2 KB staging tile per warp
+    const int q = warp & 3;
+    const uint32_t stg = epi_base + (uint32_t)q * 2048u;
+    const int lr = lane >> 2, lc = lane & 3;
+    const uint32_t st_row = stg + (uint32_t)lane * 64u, st_sw = (uint32_t)((lane >> 1) & 3);
+    uint32_t it = 0;
+    for (int64_t t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+      int n0, d0, h0, w0, co0; decode(t, n0, d0, h0, w0, co0);
+      const int bsel = it & 1; const uint32_t phacc = (it >> 1) & 1u;
+      int64_t mrow[4]; bool vrow[4]; const float* srow[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int rj = q * 32 + lr + 8 * j;
+        const int wj = w0 + rj % p.bw, hj = h0 + (rj / p.bw) % p.bh, nj = n0 + rj / (p.bw * p.bh);
+        vrow[j] = (nj < p.N) && (hj < p.H) && (wj < p.W);
+        mrow[j] = ((((int64_t)nj * p.D + d0) * p.H + hj) * p.W + wj) * p.Cout + co0 + 4 * lc;
+        srow[j] = (p.scale && vrow[j]) ? p.scale + (int64_t)(nj / (p.N / p.G)) * p.Cout : nullptr;
+      }
+      float4 rr[4];
+      auto load_res = [&](int c, float4* dst) {
+        if (p.res == nullptr || c >= p.BN || co0 + c + 4 * lc >= p.Cout) return;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (vrow[j]) dst[j] = __ldg(reinterpret_cast<const float4*>(p.res + mrow[j] + c));
+      };
+      load_res(0, rr);
+      mbar_wait(tmem_full(bsel), phacc);
+      tc_fence_after();
+      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(bsel * p.BN);
+      for (int c = 0; c < p.BN; c += 16) {
+        if (co0 + c >= p.Cout) break;
+        float4 rn[4];
+        load_res(c + 16, rn);
+        float v[16];
+        tmem_ld16(trow + (uint32_t)c, v);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(st_row + (((uint32_t)k ^ st_sw) << 4)), "f"(v[4 * k]), "f"(v[4 * k + 1]),
+                       "f"(v[4 * k + 2]), "f"(v[4 * k + 3]) : "memory");
+        __syncwarp();
+        const int co = co0 + c + 4 * lc;
+        const bool cok = co < p.Cout;
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (cok && p.bias) b4 = make_float4(__ldg(p.bias + co), __ldg(p.bias + co + 1), __ldg(p.bias + co + 2), __ldg(p.bias + co + 3));
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int row = lr + 8 * j;
+          float4 o;
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(o.x), "=f"(o.y), "=f"(o.z), "=f"(o.w)
+                       : "r"(stg + (uint32_t)row * 64u + (((uint32_t)lc ^ (uint32_t)((row >> 1) & 3)) << 4)) : "memory");
+          if (vrow[j] && cok) {
+            if (srow[j]) { o.x *= __ldg(srow[j] + co); o.y *= __ldg(srow[j] + co + 1); o.z *= __ldg(srow[j] + co + 2); o.w *= __ldg(srow[j] + co + 3); }
+            o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
+            if (p.res) { o.x += rr[j].x; o.y += rr[j].y; o.z += rr[j].z; o.w += rr[j].w; }
+            if (p.act == DGMR_ACT_RELU) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+            *reinterpret_cast<float4*>(p.y + mrow[j] + c) = o;
+          }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) rr[j] = rn[j];
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tmem_empty(bsel)) : "memory");
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { __syncwarp(); tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols); }
 }
 
 // ------------------------------------------------------------------ 3x3 convolution, halo-patch variant
@@ -1155,7 +1343,7 @@ static bool umma_fwd_ok(int N, int D, int H, int W, int Cin, int Cout, int kd, i
 int launch_conv_umma_fwd(const float* x, const float* wp, const float* bias, const float* scale, const float* res, float* y, int N, int D, int H, int W, int Cin,
                          int Cout, int kd, int kh, int kw, int G, int act, cudaStream_t st, int accumulate = 0) {
   UmmaConvParams p;
-  p.split_taps = accumulate;
+  p.split_taps = accumulate; p.n_tiles = 1;
   p.N = N; p.D = D; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.kd = kd; p.kh = kh; p.kw = kw; p.G = G;
   if (!pick_box(N, H, W, &p.bw, &p.bh, &p.bn)) { set_error("conv_umma_fwd: no 128-pixel box for N=%d H=%d W=%d", N, H, W); return 1; }
   p.tiles_w = W / p.bw; p.tiles_h = H / p.bh;
@@ -1213,6 +1401,51 @@ int launch_conv_umma_fwd(const float* x, const float* wp, const float* bias, con
     attr_set = true;
   }
   int64_t mtiles = ceil_div(N, p.bn) * D * p.tiles_h * p.tiles_w;
+  // many tiles: persistent CTAs (setup / pipeline fill once per CTA, double-buffered accumulators).  R CTAs per SM, bounded by the
+  // 512 TMEM columns (2*BN each, power of two) -- the shared-memory request is padded so that no (R+1)-th CTA becomes resident
+  // and blocks forever in tcgen05.alloc.
+  // Measured (tests/time_conv1x1.py, time_conv3d.py): +15..35 % on 1x1 convs and other short K loops (<= 12 K blocks per tile, where
+  // the per-tile fixed cost dominates), neutral to slightly negative on long K loops (fewer CTAs per SM in flight) -> only the former.
+  const int num_kb_tile = taps * (int)ceil_div(Cin, p.BK);
+  bool persist = !accumulate && (Cout % 4 == 0) && 2 * p.BN <= 512 && mtiles * ntiles >= 4 * (int64_t)sm_count() && num_kb_tile <= 12;
+  if (const char* e = getenv("DGMR_UMMA_PERSIST")) {   // tuning / test knob: 0 = never, 2 = whenever eligible (small test shapes)
+    const int v = atoi(e);
+    if (v == 0) persist = false;
+    else if (v == 2) persist = !accumulate && (Cout % 4 == 0) && 2 * p.BN <= 512;
+  }
+  if (persist) {
+    int cols = 32; while (cols < 2 * p.BN) cols <<= 1;
+    int R = 512 / cols; if (R > 2) R = 2;
+    if (const char* e = getenv("DGMR_UMMA_PERSIST_R")) { const int v = atoi(e); if (v >= 1 && v <= 3 && v <= 512 / cols) R = v; }   // tuning knob
+    const uint32_t budget = R == 3 ? 64u * 1024u : R == 2 ? 100u * 1024u : 196u * 1024u;
+    int pst = (int)(budget / stage_bytes);
+    if (pst < 2) { persist = false; }
+    else {
+      if (pst > 8) pst = 8;
+      p.cg = 1;
+      if (p.BN <= 160) { if (pst >= 6) { pst = pst / 3 * 3; p.cg = 3; } else if (pst >= 4) { pst = pst / 2 * 2; p.cg = 2; } }
+      p.stages = pst; p.tmem_cols = cols; p.n_tiles = ntiles;
+      size_t psmem = (size_t)pst * stage_bytes + 1024 + 8 * (2 * pst + 6) + 128 + 4 * 2048;
+      const size_t floor_smem = (size_t)232448 / (R + 1) + 1024;
+      if (psmem < floor_smem) psmem = floor_smem;
+      static bool pattr = false;
+      if (!pattr) {
+        if (cudaFuncSetAttribute(conv_umma_fwd_persist_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)) != cudaSuccess ||
+            cudaFuncSetAttribute(conv_umma_fwd_persist_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)) != cudaSuccess ||
+            cudaFuncSetAttribute(conv_umma_fwd_persist_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)) != cudaSuccess) {
+          set_error("conv_umma_fwd: cannot raise dynamic smem limit"); return 2;
+        }
+        pattr = true;
+      }
+      int64_t g = (int64_t)sm_count() * R;
+      if (g > mtiles * ntiles) g = mtiles * ntiles;
+      if (p.BK == 32) conv_umma_fwd_persist_kernel<32><<<(unsigned)g, kUmmaThreads, psmem, st>>>(tmA, tmB, p);
+      else if (p.BK == 16) conv_umma_fwd_persist_kernel<16><<<(unsigned)g, kUmmaThreads, psmem, st>>>(tmA, tmB, p);
+      else conv_umma_fwd_persist_kernel<8><<<(unsigned)g, kUmmaThreads, psmem, st>>>(tmA, tmB, p);
+      DGMR_CHECK_LAUNCH("conv_umma_fwd_persist");
+      return 0;
+    }
+  }
   dim3 grid((unsigned)mtiles, (unsigned)ntiles, (unsigned)(accumulate ? taps : 1));
   if (p.BK == 32) conv_umma_fwd_kernel<32><<<grid, kUmmaThreads, smem, st>>>(tmA, tmB, p);
   else if (p.BK == 16) conv_umma_fwd_kernel<16><<<grid, kUmmaThreads, smem, st>>>(tmA, tmB, p);
