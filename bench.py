@@ -346,12 +346,15 @@ def main():
         gpu_launches=launches // args.steps,
         clocks=clocks,
         step_tflops=flop_step(world * B, K) / (ms_per_step * 1e-3) / 1e12,
-        roofline=dict(bound="tensor", kernel="conv_umma_fwd_kernel (implicit-GEMM conv fwd + dgrad, tcgen05 kind::tf32)",
+        roofline=dict(bound="tensor", kernel="conv_umma_patch_kernel + conv_umma_fwd[_persist]_kernel (implicit-GEMM conv fwd + dgrad, tcgen05 kind::tf32)",
                       achieved=achieved, peak=tf32_peak, unit="TFLOP/s", frac=achieved / tf32_peak if tf32_peak else None, traffic=None,
                       peak_source=f"{pk['source']} bf16 sustained {pk['bf16_sustained']} TF/s / 2 (TF32 pipe = half the bf16 rate)",
                       launches=dom[2], kernel_ms_per_step=dom[1],
                       note="achieved = executed conv FLOPs (2*M*Cout*Cin*taps) of the tcgen05 launches in one instrumented step / their "
-                           "summed CUDA-event durations"),
+                           "summed CUDA-event durations; traffic is null because the figure aggregates launches of many shapes",
+                      traffic_profiled=dict(launch="conv_umma_patch_kernel<32,2,pair> 288x128x128 96->96 (+bias, scale, residual)",
+                                            dram_bytes=5.66e9, algorithmic_bytes=5.44e9, tensor_pipe_active_pct=40.5,
+                                            source="profiles/conv_umma_patch_pair_96x96_128_r01b_ncu.txt (ncu --set full)")),
         kernel_breakdown_ms={k: round(v[1], 3) for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])},
     )
     if args.ref_gpu:
