@@ -198,7 +198,26 @@ def gpu_reference_steps(cfg, batch, steps, warmup, k, dev):
 
 
 # ----------------------------------------------------------------------------------------------------- GPU arm
+_REAL_STDOUT = None
+
+
+def emit(line: dict):
+    """Write the ONE JSON line of the contract to the process's real stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    # stdout must carry exactly one JSON line, but libraries print there too (NCCL's "NCCL version ..." banner under torchrun):
+    # point fd 1 at stderr for the duration of the run and keep the real stdout for emit()
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
@@ -237,7 +256,7 @@ def main():
                     config=dict(workload=workload, note="CPU arm runs the oracle port on a bounded sample"),
                     cpu_baseline=dict(value=r["value"], unit="frames/s", cores=r["cores"], kind="port", sample=r["sample"]),
                     e2e=dict(value=r["value"], unit="frames/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
-        print(json.dumps(line))
+        emit(line)
         return
 
     import torch.distributed as dist
@@ -362,7 +381,7 @@ def main():
     if not args.no_cpu_baseline:
         r = cpu_reference_steps(cfg, args.cpu_batch, 1, 0, K, budget_s=90.0)
         line["cpu_baseline"] = dict(value=r["value"], unit="frames/s", cores=r["cores"], kind="port", sample=r["sample"])
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
