@@ -32,10 +32,12 @@ class ConvGRUCell(nn.Module):
         self.output_conv = SNConv(input_channels, output_channels, k, eps=sn_eps)
 
     # ---- channels-last multi-step engine -------------------------------------------------
-    def run_sequence(self, xs: torch.Tensor, h0: torch.Tensor, T: int, shared_input: bool = False) -> torch.Tensor:
+    def run_sequence(self, xs: torch.Tensor, h0: torch.Tensor, T: int, shared_input: bool = False,
+                     rounded_out: bool = False) -> torch.Tensor:
         """xs: [T*B,1,H,W,Cx] timestep-major (or [1,1,H,W,Cx] with shared_input=True: the same input at every
         step and for every batch element, as at the sampler's first level, ref: generators.py:146-149);
-        h0: [B,1,H,W,Ch].  Returns [T*B,1,H,W,Ch]."""
+        h0: [B,1,H,W,Ch].  Returns [T*B,1,H,W,Ch].  rounded_out: the caller feeds the result to convolutions only and
+        accepts the tf32-rounded copy the recurrence writes anyway (fused path on the tensor cores)."""
         ch = self.output_channels
         cx = self.input_channels - ch
         B = h0.shape[0]
@@ -43,7 +45,7 @@ class ConvGRUCell(nn.Module):
         # one launch per weight: the T power iterations of this forward (ref: per-call parametrization)
         scales = [g.scale_of(g.inv_sigma(T)) for g in gates]  # [T, Ch] each
         if ops.config.gru_sequence:
-            return self._run_fused(xs, h0, T, shared_input, scales)
+            return self._run_fused(xs, h0, T, shared_input, scales, rounded_out)
         xparts = []
         for g, sc in zip(gates, scales):
             xparts.append(self._x_part(xs, g.weight_orig, g.bias, sc, T, B, cx, shared_input).unbind(0))
@@ -73,7 +75,7 @@ class ConvGRUCell(nn.Module):
         xp = ops.conv(xs, w, bias, sc, None, 0, cx, T, ACT_NONE)
         return xp.reshape((T, B) + tuple(xp.shape[1:]))
 
-    def _run_fused(self, xs, h0, T, shared_input, scales):
+    def _run_fused(self, xs, h0, T, shared_input, scales, rounded_out=False):
         """Read and update gates as ONE convolution (their weights, biases and per-step sigmas side by side along Cout), and the
         whole recurrence as one autograd node (ops.gru_sequence): 2 serial convs per step instead of 3, weight gradients of all
         steps in one launch."""
@@ -88,7 +90,7 @@ class ConvGRUCell(nn.Module):
         xc = self._x_part(xs, gc.weight_orig, gc.bias, scales[2], T, B, cx, shared_input)
         xru = xru.reshape((T * B,) + tuple(xru.shape[2:]))
         xc = xc.reshape((T * B,) + tuple(xc.shape[2:]))
-        return ops.gru_sequence(xru, xc, h0, w_ru, gc.weight_orig, s_ru, scales[2], T, cx)
+        return ops.gru_sequence(xru, xc, h0, w_ru, gc.weight_orig, s_ru, scales[2], T, cx, rounded_out)
 
     def forward(self, x: torch.Tensor, prev_state: torch.Tensor):
         """NCHW in/out: (x [B,Cx,H,W], prev_state [B,Ch,H,W]) -> (out, new_state)."""

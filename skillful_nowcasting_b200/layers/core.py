@@ -89,7 +89,9 @@ class SNConv(nn.Module):
         """1/sigma for the next G reference calls (power iteration advances G times in training).  If the enclosing module
         prefetched it (all of its spectral norms in one launch, see `prefetch_sigmas`), that result is consumed here."""
         pending = self.__dict__.pop("_pending_sigma", None)
-        if pending is not None:
+        # a prefetched value is only valid for the weights and mode it was computed for (a forward that raised between the
+        # prefetch and this call may have left a stale one behind)
+        if pending is not None and pending[2] == (self.weight_orig._version, self.training, torch.is_grad_enabled()):
             assert pending[0] == G, f"prefetched spectral norm for G={pending[0]} but used with G={G}"
             return pending[1]
         u, v = self._uv
@@ -122,11 +124,11 @@ def prefetch_sigmas(calls):
     assert all(l.training == training for l, _ in calls)
     entries = []
     for l, g in calls:
-        assert "_pending_sigma" not in l.__dict__, "a prefetched spectral norm was never consumed"
+        l.__dict__.pop("_pending_sigma", None)   # left behind by a forward that did not finish: drop it
         u, v = l._uv
         entries.append((l.weight_orig, u, v, g, l.eps))
     for (l, g), s in zip(calls, ops.spectral_inv_sigma_multi(entries, training)):
-        l.__dict__["_pending_sigma"] = (g, s)
+        l.__dict__["_pending_sigma"] = (g, s, (l.weight_orig._version, training, torch.is_grad_enabled()))
 
 
 class PlainConv(nn.Module):

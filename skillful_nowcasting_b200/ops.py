@@ -397,7 +397,9 @@ def spectral_inv_sigma_multi(entries, training):
 
 
 # ----------------------------------------------------------------------------- convolution
-_pack_cache = {}
+import weakref  # noqa: E402
+
+_packed_params = {}   # id(Parameter) -> weakref: the Parameters that carry a pack cache (only so that clear_pack_cache can find them)
 
 
 def mark_conv_only(t: torch.Tensor) -> torch.Tensor:
@@ -457,36 +459,61 @@ def _use_split_taps(n, d, h, w, cin, cout, taps, has_bias, act) -> bool:
     return tiles <= 32 and cin >= 32 and _be().conv_umma_supported(n, d, h, w, cin, cout, 1, 3, 3)   # measured crossover (tests/time_gru_conv.py)
 
 
+def _pack_slot(w: torch.Tensor):
+    """The per-Parameter cache of packed copies.  It lives ON the Parameter object (so it dies with it: a new model whose
+    storage lands on a freed model's addresses can never see the old packs) and each entry remembers the storage it was
+    packed from (data pointer, device) and the parameter's version counter (moved by the optimiser step)."""
+    if not isinstance(w, torch.nn.Parameter):
+        # temporaries (e.g. the concatenated gate weights of a ConvGRU) are not cached: they can die and hand their
+        # address + version 0 to the next temporary
+        return None
+    slot = w.__dict__.get("_dgmr_packs")
+    if slot is None:
+        slot = w.__dict__["_dgmr_packs"] = {}
+        k = id(w)
+        _packed_params[k] = weakref.ref(w, lambda _r, k=k: _packed_params.pop(k, None))
+    return slot
+
+
+def _pack_lookup(slot, w, key):
+    if slot is None:
+        return None
+    hit = slot.get(key)
+    if hit is not None and hit[0] == (w._version, w.data_ptr(), str(w.device)):
+        return hit[1]
+    return None
+
+
+def _pack_store(slot, w, key, p):
+    if slot is not None:
+        slot[key] = ((w._version, w.data_ptr(), str(w.device)), p)
+
+
 def packed_weight(w: torch.Tensor, ci0: int, cin: int, mode: int) -> torch.Tensor:
     """[tap][Cout][Cin] (mode 0) / flipped-transposed dgrad pack (mode 1) of the OIHW weight slice
-    [:, ci0:ci0+cin]; cached until the parameter's version counter moves.  mode | FLAG_ROUND_TF32: tf32-rounded.
-    Only nn.Parameters are cached: a temporary (e.g. the concatenated gate weights of a ConvGRU) can die and hand its
-    address + version 0 to the next temporary, which a (data_ptr, version) key cannot tell apart."""
-    cacheable = isinstance(w, torch.nn.Parameter)
-    key = (w.data_ptr(), tuple(w.shape), ci0, cin, mode, str(w.device))
-    ver = w._version
-    if cacheable:
-        hit = _pack_cache.get(key)
-        if hit is not None and hit[0] == ver:
-            return hit[1]
+    [:, ci0:ci0+cin]; cached on the Parameter until its version counter (or storage) moves.
+    mode | FLAG_ROUND_TF32: tf32-rounded."""
+    slot = _pack_slot(w)
+    key = (ci0, cin, mode)
+    hit = _pack_lookup(slot, w, key)
+    if hit is not None:
+        return hit
     cout, cintot = w.shape[0], w.shape[1]
     taps = w.numel() // (cout * cintot)
     p = _new((taps * cout * cin,), w)
     _be().pack_weight(_c(w.detach()), p, cout, cintot, ci0, cin, taps, mode)
-    if cacheable:
-        _pack_cache[key] = (ver, p)
+    _pack_store(slot, w, key, p)
     return p
 
 
 def packed_weight_padded(w: torch.Tensor, ci0: int, cin: int, cin_p: int, mode: int) -> torch.Tensor:
     """Like packed_weight but with the input-channel axis zero-padded to cin_p (the 4-channel space-to-depth inputs
     are carried as 8 channels so that the tensor-core path, whose K step is 8 tf32, can serve them)."""
-    cacheable = isinstance(w, torch.nn.Parameter)
-    key = (w.data_ptr(), tuple(w.shape), ci0, cin, ("pad", cin_p, mode), str(w.device))
-    ver = w._version
-    hit = _pack_cache.get(key) if cacheable else None
-    if hit is not None and hit[0] == ver:
-        return hit[1]
+    slot = _pack_slot(w)
+    key = (ci0, cin, ("pad", cin_p, mode))
+    hit = _pack_lookup(slot, w, key)
+    if hit is not None:
+        return hit
     cout, cintot = w.shape[0], w.shape[1]
     taps = w.numel() // (cout * cintot)
     p = _zeros((taps * cout * cin_p,), w)
@@ -496,13 +523,16 @@ def packed_weight_padded(w: torch.Tensor, ci0: int, cin: int, cin_p: int, mode: 
         _be().permute(dense, p, (taps * cout, cin), (cin, 1), (cin_p, 1), False, 0, 0)
     else:           # p[taps-1-tap][ci][co]: ci rows spread to cin_p per tap (extra rows stay zero)
         _be().permute(dense, p, (taps, cin, cout), (cin * cout, cout, 1), (cin_p * cout, cout, 1), False, 0, 0)
-    if cacheable:
-        _pack_cache[key] = (ver, p)
+    _pack_store(slot, w, key, p)
     return p
 
 
 def clear_pack_cache():
-    _pack_cache.clear()
+    for r in list(_packed_params.values()):
+        w = r()
+        if w is not None:
+            w.__dict__.pop("_dgmr_packs", None)
+    _packed_params.clear()
 
 
 def _conv_launch(x, wp, bias, scale, res, y, n, d, h, wd, c, cout, kd, kh, kw, G, act):
@@ -752,7 +782,9 @@ class _GruSequence(Function):
         rh = _new((T * B, 1, H, W, ch), h0)
         # conv operand of step t = h_{t-1}; when the tensor-core path rounds operands it reads a rounded private copy (the gate
         # arithmetic must see the unrounded state), written by the previous step's blend kernel
-        hop = _new((T * B, 1, H, W, ch), h0) if rnd_ru else None
+        # (T+1 slots: slot t+1 = tf32(h_t), so hop[B:] is also the rounded copy of ALL outputs that the next layer's conv consumes --
+        # `out` itself stays unrounded: the gate backward reads it as h_prev)
+        hop = _new(((T + 1) * B, 1, H, W, ch), h0) if rnd_ru else None
         if rnd_ru:
             be.round_tf32(h0, hop[0:B])
         pru_flat = pru.view(-1)
@@ -763,14 +795,18 @@ class _GruSequence(Function):
             _conv_launch(a, wp_ru, None, s_ru[t:t + 1], xru[sl], pru[sl], B, 1, H, W, ch, 2 * ch, 1, 3, 3, 1, ACT_NONE)
             be.gru_gate_fwd(pru[sl], 2 * ch, h_prev, rh[sl], rows, ch, rnd_c)
             _conv_launch(rh[sl], wp_c, None, s_c[t:t + 1], xc[sl], cp[sl], B, 1, H, W, ch, ch, 1, 3, 3, 1, ACT_NONE)
-            nxt = hop[(t + 1) * B:(t + 2) * B] if (rnd_ru and t + 1 < T) else None
+            nxt = hop[(t + 1) * B:(t + 2) * B] if rnd_ru else None
             be.gru_blend_fwd(pru_flat[t * rows * 2 * ch + ch:], 2 * ch, h_prev, cp[sl], out[sl], nxt, rows, ch, True)
         ctx.save_for_backward(xru, xc, h0, w_ru, w_c, s_ru, s_c, out, pru, cp, rh, hop)
         ctx.meta = (T, cx, bool(rnd_c))
-        return out
+        if rnd_ru:
+            out_r = hop[B:]
+            out_r._dgmr_tf32 = True
+            return out, out_r
+        return out, out.view_as(out)
 
     @staticmethod
-    def backward(ctx, dout):
+    def backward(ctx, dout, dout_r):
         xru, xc, h0, w_ru, w_c, s_ru, s_c, out, pru, cp, rh, hop = ctx.saved_tensors
         T, cx, rh_rounded = ctx.meta
         be = _be()
@@ -782,7 +818,13 @@ class _GruSequence(Function):
         tc_wg_c = _tc_wgrad(T * B, 1, H, W, ch, ch, 1, 3, 3)
         wpt_ru = packed_weight(w_ru, cx, ch, 1 | (FLAG_ROUND_TF32 if tc_dg_ru else 0))
         wpt_c = packed_weight(w_c, cx, ch, 1 | (FLAG_ROUND_TF32 if tc_dg_c else 0))
-        gh = _c(dout).clone()                        # running dL/dh_t: starts as the output gradient, steps add their carry
+        # running dL/dh_t: starts as the output gradient (of both views of the output), steps add their carry
+        if dout is None:
+            gh = _c(dout_r).clone()
+        else:
+            gh = _c(dout).clone()
+            if dout_r is not None:
+                be.axpby(1.0, gh, 1.0, _c(dout_r), gh)
         dh0 = _new(h0.shape, h0)
         dxru, dzru = torch.empty_like(pru), torch.empty_like(pru)
         dxc, dzc = torch.empty_like(cp), torch.empty_like(cp)
@@ -805,7 +847,7 @@ class _GruSequence(Function):
             be.conv_bwd_prep(dxru[sl], pru[sl], xru[sl], None, s_ru[t:t + 1], dzru[sl], None, None, ds_ru[t:t + 1], rows, 1, 2 * ch, f_ru)
             _conv_launch(dzru[sl], wpt_ru, None, None, tgt, tgt, B, 1, H, W, 2 * ch, ch, 1, 3, 3, 1, ACT_NONE)
         # weight gradients: one launch per weight over all T*B images
-        xop = hop if hop is not None else torch.cat([h0, out[:(T - 1) * B]], dim=0)
+        xop = hop[:T * B] if hop is not None else torch.cat([h0, out[:(T - 1) * B]], dim=0)
         dws = []
         for wt, x_all, dz_all, co in ((w_ru, xop, dzru, 2 * ch), (w_c, rh, dzc, ch)):
             dwp = _new((9 * co * ch,), h0)
@@ -816,8 +858,10 @@ class _GruSequence(Function):
         return dxru, dxc, dh0, dws[0], dws[1], ds_ru, ds_c, None, None
 
 
-def gru_sequence(xru, xc, h0, w_ru, w_c, s_ru, s_c, T, cx):
-    return _GruSequence.apply(xru, xc, h0, w_ru, w_c, s_ru, s_c, T, cx)
+def gru_sequence(xru, xc, h0, w_ru, w_c, s_ru, s_c, T, cx, rounded_out=False):
+    """rounded_out: return the tf32-rounded copy of the outputs (what a convolution-only consumer wants) instead of the outputs."""
+    out, out_r = _GruSequence.apply(xru, xc, h0, w_ru, w_c, s_ru, s_c, T, cx)
+    return out_r if rounded_out else out
 
 
 # ----------------------------------------------------------------------------- discriminator head

@@ -46,17 +46,43 @@ class Adam(torch.optim.Optimizer):
         self.steps = 0
         self.process_group = process_group
 
-    def zero_grad(self, set_to_none: bool = False):  # grads stay views of the flat buffer
-        self.flat_g.zero_()
+    def _offsets(self):
         off = 0
         for p in self._params:
-            k = p.numel()
-            if p.grad is None or p.grad.data_ptr() != self.flat_g.data_ptr() + 4 * off:
+            yield p, off, p.numel()
+            off += self._al(p.numel())
+
+    def zero_grad(self, set_to_none: bool = False):  # grads stay views of the flat buffer
+        self.flat_g.zero_()
+        self._reattach(copy=False)
+
+    def _reattach(self, copy: bool):
+        """Parameters and their gradients must alias the flat buffers, or the fused update silently works on stale data:
+        `module.zero_grad()` (set_to_none) makes autograd write the next gradient into a fresh tensor, `module.to()/.cuda()`
+        re-points `p.data`.  Re-point them; with `copy` the detached values are copied in first (they are the live ones)."""
+        gbase, pbase = self.flat_g.data_ptr(), self.flat_p.data_ptr()
+        for p, off, k in self._offsets():
+            if p.data_ptr() != pbase + 4 * off:
+                if p.device != self.flat_p.device:
+                    raise RuntimeError("dgmr Adam: a parameter was moved to another device after the optimiser was built; "
+                                       "build the optimiser after .to()/.cuda()")
+                if copy:
+                    self.flat_p[off:off + k].copy_(p.detach().reshape(-1))
+                p.data = self.flat_p[off:off + k].view(p.shape)
+            if p.grad is None:
+                if copy:
+                    self.flat_g[off:off + k].zero_()
                 p.grad = self.flat_g[off:off + k].view(p.shape)
-            off += self._al(k)
+            elif p.grad.data_ptr() != gbase + 4 * off:
+                if copy:
+                    self.flat_g[off:off + k].copy_(p.grad.detach().reshape(-1))
+                p.grad = self.flat_g[off:off + k].view(p.shape)
 
     @torch.no_grad()
     def step(self, closure=None):
+        if len(self.param_groups) != 1:
+            raise RuntimeError("dgmr Adam: exactly one parameter group is supported (one flat buffer, one fused launch)")
+        self._reattach(copy=True)
         world = 1
         if dist.is_available() and dist.is_initialized():
             world = dist.get_world_size(self.process_group)
@@ -68,6 +94,39 @@ class Adam(torch.optim.Optimizer):
                             self.steps, 1.0 / world)
         torch.autograd.graph.increment_version(self._params)  # invalidates the packed-weight cache
         return None
+
+    # ---- checkpointing: the layout of torch.optim.Adam's state dict (exp_avg / exp_avg_sq / step per parameter index),
+    # so Lightning checkpoints carry the moments and reference (torch.optim.Adam) checkpoints load here and vice versa
+    def state_dict(self):
+        sd = super().state_dict()
+        state = {}
+        if self.steps > 0:
+            for i, (p, off, k) in enumerate(self._offsets()):
+                state[i] = dict(step=torch.tensor(float(self.steps)), exp_avg=self.m[off:off + k].view(p.shape).clone(),
+                                exp_avg_sq=self.v[off:off + k].view(p.shape).clone())
+        sd["state"] = state
+        return sd
+
+    @torch.no_grad()
+    def load_state_dict(self, state_dict):
+        state = state_dict.get("state", {})
+        groups = state_dict.get("param_groups")
+        if groups:
+            if len(groups) != 1:
+                raise RuntimeError("dgmr Adam: exactly one parameter group is supported")
+            for key in ("lr", "betas", "eps"):
+                if key in groups[0]:
+                    self.param_groups[0][key] = groups[0][key]
+        self.m.zero_(); self.v.zero_()
+        steps = 0
+        for i, (p, off, k) in enumerate(self._offsets()):
+            st = state.get(i, state.get(str(i)))
+            if st is None:
+                continue
+            self.m[off:off + k].copy_(st["exp_avg"].reshape(-1))
+            self.v[off:off + k].copy_(st["exp_avg_sq"].reshape(-1))
+            steps = max(steps, int(float(st["step"])))
+        self.steps = steps
 
 
 def gan_step(generator, discriminator, g_opt, d_opt, images: torch.Tensor, future: torch.Tensor,
