@@ -55,6 +55,12 @@ int dgmr_abi_version(void);
 int dgmr_conv_umma_supported(int N, int D, int H, int W, int Cin, int Cout, int kd, int kh, int kw);
 int dgmr_wgrad_umma_supported(int N, int D, int H, int W, int Cin, int Cout, int kd, int kh, int kw);
 
+/* Process-wide tuning / test options of the tensor-core launchers (-1 restores the heuristic default): "umma_cg", "umma_persist",
+ * "umma_persist_r", "patch_pair", "patch_mt", "patch_tg", "prefer_patch" (1: AUTO dispatch uses the halo-patch kernel for every
+ * shape it supports -- lets small parity cases exercise the kernels the benchmark shapes use).  Not a per-launch argument on
+ * purpose: results never depend on them, only which kernel variant computes them. */
+int dgmr_set_option(const char* name, int value);
+
 /* debug probe (tests only): C[128][N] = A[r0:r0+128, 0:32] . B[N, 0:32]^T through TMA + tcgen05 with the A descriptor
  * starting r0 rows into a swizzled 256-row tile; mode bit0 sets the descriptor base_offset field */
 int dgmr_debug_umma_shift(const float* A, const float* B, float* C, int N, int r0, int mode, dgmr_stream_t stream);
@@ -167,8 +173,9 @@ int dgmr_unpack_wgrad(const float* packed, float* gw, int Cout, int CinTot, int 
                       int accumulate, dgmr_stream_t stream);
 /* y = act( conv(x, wp) * scale[g][co] + bias[co] + res )   (scale, bias, res optional = NULL)
  * x:[N,D,H,W,Cin]  y,res:[N,D,H,W,Cout]  scale:[G][Cout]  g = n / (N/G) */
-/* precision DGMR_PREC_3XTF32 (tensor-core path): x/wp hold the hi parts, x_lo/wp_lo the lo parts
- * (dgmr_split_tf32); otherwise x_lo/wp_lo are NULL. */
+/* precision DGMR_PREC_3XTF32 ("parity mode"): on the tensor-core path x/wp hold the hi parts and x_lo/wp_lo the lo parts
+ * (dgmr_split_tf32) and every k-step issues lo*hi + hi*lo + hi*hi into the fp32 accumulator; with x_lo == wp_lo == NULL the
+ * operands are full fp32 and the fp32-FMA kernel serves the call.  DGMR_PREC_TF32: x_lo/wp_lo are NULL. */
 int dgmr_conv_fwd(const float* x, const float* x_lo, const float* wp, const float* wp_lo, const float* bias,
                   const float* scale, const float* res, float* y, int N, int D, int H, int W, int Cin, int Cout,
                   int kd, int kh, int kw, int G, int act, int algo, int precision, dgmr_stream_t stream);
@@ -178,12 +185,10 @@ int dgmr_conv_fwd(const float* x, const float* x_lo, const float* wp, const floa
 int dgmr_conv_bwd_prep(const float* dy, const float* y, const float* res, const float* bias, const float* scale,
                        float* dz, float* dpre /*optional: unscaled dpre, = grad of res*/, float* dbias, float* dscale,
                        int64_t rows, int G, int Cout, int act, int accumulate_dbias, dgmr_stream_t stream);
-/* dwp[tap][co][ci] = sum_pixels dz[p][co] * x[p+tap][ci]   (dwp fully overwritten)
- * xT/dzT: channel-major transposed copies [N][C][D][H][W] needed by the tensor-core path only
- * (NULL for SIMT). */
-int dgmr_conv_wgrad(const float* x, const float* dz, const float* xT, const float* dzT, const float* xT_lo,
-                    const float* dzT_lo, float* dwp, int N, int D, int H, int W, int Cin, int Cout,
-                    int kd, int kh, int kw, int algo, int precision, dgmr_stream_t stream);
+/* dwp[tap][co][ci] = sum_pixels dz[p][co] * x[p+tap][ci]   (dwp fully overwritten).  Both operands are read straight from the
+ * channels-last tensors (MN-major tensor-core tiles).  x_lo/dz_lo: lo parts for DGMR_PREC_3XTF32 (as in dgmr_conv_fwd), else NULL. */
+int dgmr_conv_wgrad(const float* x, const float* x_lo, const float* dz, const float* dz_lo, float* dwp, int N, int D, int H, int W,
+                    int Cin, int Cout, int kd, int kh, int kw, int algo, int precision, dgmr_stream_t stream);
 
 /* ---- discriminator head (ref: dgmr/discriminators.py:129,209: sum(relu(x)) over H,W) */
 int dgmr_sumpool_relu_fwd(const float* x, float* y, int N, int HW, int C, dgmr_stream_t stream);
@@ -220,7 +225,7 @@ int dgmr_adam(float* p, const float* g, float* m, float* v, int64_t n, float lr,
  * they enter a tensor-core convolution: in place when the tensor feeds convolutions only, into a copy otherwise */
 int dgmr_round_tf32(const float* x, float* y, int64_t n, dgmr_stream_t stream);
 
-/* ---- 3xTF32 support: hi = x & ~0x1fff, lo = x - hi */
+/* ---- 3xTF32 support: hi = nearest TF32 of x, lo = nearest TF32 of (x - hi); hi + lo reproduces x to 2^-22 relative */
 int dgmr_split_tf32(const float* x, float* hi, float* lo, int64_t n, dgmr_stream_t stream);
 
 #ifdef __cplusplus

@@ -21,7 +21,7 @@ HEADER = os.path.join(os.path.dirname(_HERE), "include", "dgmr_b200.h")
 LIB_PATH = os.path.join(_HERE, "libdgmr_b200.so")
 
 ACT_NONE, ACT_RELU = 0, 1
-ALGO_AUTO, ALGO_SIMT, ALGO_UMMA = 0, 1, 2
+ALGO_AUTO, ALGO_SIMT, ALGO_UMMA, ALGO_UMMA_PATCH = 0, 1, 2, 3
 PREC_TF32, PREC_3XTF32 = 0, 1
 FLAG_ROUND_TF32 = 256
 FLAG_ACCUMULATE = 512
@@ -31,6 +31,7 @@ _CTYPES = {
     "int64_t": ctypes.c_int64,
     "float": ctypes.c_float,
     "dgmr_stream_t": ctypes.c_void_p,
+    "char*": ctypes.c_char_p,
 }
 
 
@@ -53,6 +54,8 @@ def parse_header(path: str = HEADER) -> Dict[str, Tuple[str, List[Tuple[str, str
 
 def _to_ctype(t: str):
     t = t.replace("const ", "").strip()
+    if t == "char*":
+        return ctypes.c_char_p
     if t.endswith("*"):
         return ctypes.c_void_p
     return _CTYPES[t]
@@ -144,7 +147,12 @@ class CudaBackend:
     def _query(self, name, *args) -> int:
         return int(getattr(self.lib, name)(*args))
 
-    # -- queries
+    # -- queries / options
+    def set_option(self, name: str, value: int):
+        """Tuning / test option of the tensor-core launchers (include/dgmr_b200.h: dgmr_set_option); -1 = heuristic default."""
+        if self.lib.dgmr_set_option(name.encode(), int(value)) != 0:
+            raise RuntimeError(self.lib.dgmr_last_error().decode())
+
     def conv_umma_supported(self, N, D, H, W, Cin, Cout, kd, kh, kw) -> bool:
         return bool(self._query("dgmr_conv_umma_supported", N, D, H, W, Cin, Cout, kd, kh, kw))
 
@@ -269,14 +277,13 @@ class CudaBackend:
                    _f32(dz, "dz"), _f32(dpre, "dpre"), _f32(dbias, "dbias"), _f32(dscale, "dscale"), rows, G, Cout, act,
                    int(accumulate_dbias), _flops=nb, _info=f"rows{rows} G{G} C{Cout} (GB/s)")
 
-    def conv_wgrad(self, x, dz, dwp, N, D, H, W, Cin, Cout, kd, kh, kw, algo=ALGO_AUTO, precision=PREC_TF32, xT=None, dzT=None,
-                   xT_lo=None, dzT_lo=None):
+    def conv_wgrad(self, x, dz, dwp, N, D, H, W, Cin, Cout, kd, kh, kw, algo=ALGO_AUTO, precision=PREC_TF32, x_lo=None, dz_lo=None):
         tag = None
         if self.profile is not None:
             umma = algo == ALGO_UMMA or (algo == ALGO_AUTO and self.wgrad_umma_supported(N, D, H, W, Cin, Cout, kd, kh, kw))
             tag = "wgrad_umma" if umma else "wgrad_simt"
-        self._call("dgmr_conv_wgrad", _f32(x, "x"), _f32(dz, "dz"), _f32(xT, "xT"), _f32(dzT, "dzT"), _f32(xT_lo, "xT_lo"),
-                   _f32(dzT_lo, "dzT_lo"), _f32(dwp, "dwp"), N, D, H, W, Cin, Cout, kd, kh, kw, algo, precision,
+        self._call("dgmr_conv_wgrad", _f32(x, "x"), _f32(x_lo, "x_lo"), _f32(dz, "dz"), _f32(dz_lo, "dz_lo"), _f32(dwp, "dwp"),
+                   N, D, H, W, Cin, Cout, kd, kh, kw, algo, precision,
                    _tag=tag, _flops=2.0 * N * D * H * W * Cin * Cout * kd * kh * kw,
                    _info=f"{N}x{D}x{H}x{W} {Cin}->{Cout} k{kd}{kh}{kw}")
 

@@ -16,6 +16,7 @@
 #include "common.cuh"
 #include <cuda.h>
 #include <stdlib.h>
+#include <string.h>
 
 namespace dgmr {
 
@@ -197,16 +198,21 @@ struct UmmaConvParams {
 
 constexpr int kUmmaThreads = 192;  // warp0 TMA, warp1 MMA, warps 2..5 epilogue
 
-template <int BK>
+// X3: 3xTF32 error-compensated operands (DGMR_PREC_3XTF32).  Every stage carries the hi and the lo part of both tiles (tmA/tmB describe
+// the hi tensors, tmAlo/tmBlo the lo tensors) and every k-step issues lo*hi, hi*lo, hi*hi into the same fp32 accumulator (small terms
+// first); the dropped lo*lo term is ~2^-22 relative.
+template <int BK, bool X3>
 __global__ void __launch_bounds__(kUmmaThreads, 1)
-conv_umma_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const UmmaConvParams p) {
+conv_umma_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmAlo,
+                     const __grid_constant__ CUtensorMap tmBlo, const UmmaConvParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024-B alignment
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t a_bytes = 128u * BK * 4u, b_bytes = (uint32_t)p.BN * BK * 4u;
   const uint32_t b_bytes_al = (b_bytes + 1023u) & ~1023u;
-  const uint32_t stage_bytes = a_bytes + b_bytes_al;
+  const uint32_t half_bytes = a_bytes + b_bytes_al;          // X3: [A hi][B hi][A lo][B lo]
+  const uint32_t stage_bytes = X3 ? 2u * half_bytes : half_bytes;
   const uint32_t bar_base = base + p.stages * stage_bytes;  // full[stages], empty[stages], tmem_full, tmem_ptr
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (p.stages + s); };
@@ -230,6 +236,10 @@ conv_umma_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    if (X3) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmAlo) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmBlo) : "memory");
+    }
     for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     mbar_init(tmem_full_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -257,10 +267,14 @@ conv_umma_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         const int tkw = tap % p.kw, tkh = (tap / p.kw) % p.kh, tkd = tap / (p.kw * p.kh);
         if (sg == 0) mbar_wait(empty_bar(g), ph ^ 1u);
         if (elect_one()) {
-          mbar_expect_tx(full_bar(s), a_bytes + b_bytes);
+          mbar_expect_tx(full_bar(s), (X3 ? 2u : 1u) * (a_bytes + b_bytes));
           const uint32_t sa = base + s * stage_bytes;
           tma_load_5d(sa, &tmA, full_bar(s), c0, w0 + tkw - p.kw / 2, h0 + tkh - p.kh / 2, d0 + tkd - p.kd / 2, n0);
           tma_load_3d(sa + a_bytes, &tmB, full_bar(s), c0, co0, tap);
+          if (X3) {
+            tma_load_5d(sa + half_bytes, &tmAlo, full_bar(s), c0, w0 + tkw - p.kw / 2, h0 + tkh - p.kh / 2, d0 + tkd - p.kd / 2, n0);
+            tma_load_3d(sa + half_bytes + a_bytes, &tmBlo, full_bar(s), c0, co0, tap);
+          }
         }
         __syncwarp();
         if (++chunk == kchunks) { chunk = 0; ++tapl; }
@@ -287,16 +301,26 @@ conv_umma_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         const bool last_chunk = (++chunk_i == kchunks);   // last chunk of a tap: possibly a channel tail with fewer valid k-steps
         if (last_chunk) chunk_i = 0;
         const bool rel = (sg + 1 == p.cg) || (kb + 1 == num_kb);   // release this group (the final, possibly partial, one too)
+        const uint64_t lo_off = (uint64_t)(half_bytes >> 4);     // X3: the lo tiles sit half a stage further on
+        auto mma = [&](uint64_t ad, uint64_t bd, uint32_t acc) {
+          if (X3) {
+            umma_tf32(tmem_base, ad + lo_off, bd, idesc, acc);
+            umma_tf32(tmem_base, ad, bd + lo_off, idesc, 1u);
+            umma_tf32(tmem_base, ad, bd, idesc, 1u);
+          } else {
+            umma_tf32(tmem_base, ad, bd, idesc, acc);
+          }
+        };
         if (elect_one()) {
           // advance 8 tf32 = 32 bytes along K inside the swizzle row: +2 in the (addr>>4) field
-          umma_tf32(tmem_base, adesc, bdesc, idesc, kb != 0 ? 1u : 0u);
+          mma(adesc, bdesc, kb != 0 ? 1u : 0u);
           if (last_chunk) {
 #pragma unroll
             for (int k = 1; k < BK / 8; ++k)
-              if (k < tail_ks) umma_tf32(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, 1u);
+              if (k < tail_ks) mma(adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), 1u);
           } else {
 #pragma unroll
-            for (int k = 1; k < BK / 8; ++k) umma_tf32(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, 1u);
+            for (int k = 1; k < BK / 8; ++k) mma(adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), 1u);
           }
           if (rel) umma_commit(empty_bar(g));
         }
@@ -955,8 +979,11 @@ struct UmmaWgradParams {
   float* dwp;
 };
 
+// X3: 3xTF32 operands, as in conv_umma_fwd_kernel (stage = [dz hi][x hi][dz lo][x lo], three MMAs per k-step).
+template <bool X3>
 __global__ void __launch_bounds__(kUmmaThreads, 1)
-conv_umma_wgrad_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_constant__ CUtensorMap tmX, const UmmaWgradParams p) {
+conv_umma_wgrad_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDzLo,
+                       const __grid_constant__ CUtensorMap tmXLo, const UmmaWgradParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -965,7 +992,8 @@ conv_umma_wgrad_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_co
   const uint32_t blk_bytes = (uint32_t)KP * p.aw * 4u;     // one channel-block [32 pixels][aw channels]
   const int a_blocks = 128 / p.aw, b_blocks = p.BN / p.aw;
   const uint32_t a_bytes = a_blocks * blk_bytes, b_bytes = b_blocks * blk_bytes;
-  const uint32_t stage_bytes = a_bytes + b_bytes;          // multiples of 1024 (KP*aw*4 >= 1024)
+  const uint32_t half_bytes = a_bytes + b_bytes;           // multiples of 1024 (KP*aw*4 >= 1024)
+  const uint32_t stage_bytes = X3 ? 2u * half_bytes : half_bytes;
   const uint32_t bar_base = base + p.stages * stage_bytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (p.stages + s); };
@@ -1004,11 +1032,17 @@ conv_umma_wgrad_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_co
         const int n0 = t * p.bn, w0 = wi * p.bw, h0 = hi * p.bh;
         if (sg == 0) mbar_wait(empty_bar(g), ph ^ 1u);
         if (elect_one()) {
-          mbar_expect_tx(full_bar(s), a_bytes + b_bytes);
+          mbar_expect_tx(full_bar(s), (X3 ? 2u : 1u) * (a_bytes + b_bytes));
           const uint32_t sa = base + s * stage_bytes;
           for (int j = 0; j < a_blocks; ++j) tma_load_5d(sa + j * blk_bytes, &tmDz, full_bar(s), co0 + j * p.aw, w0, h0, d0, n0);
           for (int j = 0; j < b_blocks; ++j)
             tma_load_5d(sa + a_bytes + j * blk_bytes, &tmX, full_bar(s), ci0 + j * p.aw, w0 + tkw - p.kw / 2, h0 + tkh - p.kh / 2, d0 + tkd - p.kd / 2, n0);
+          if (X3) {
+            for (int j = 0; j < a_blocks; ++j) tma_load_5d(sa + half_bytes + j * blk_bytes, &tmDzLo, full_bar(s), co0 + j * p.aw, w0, h0, d0, n0);
+            for (int j = 0; j < b_blocks; ++j)
+              tma_load_5d(sa + half_bytes + a_bytes + j * blk_bytes, &tmXLo, full_bar(s), ci0 + j * p.aw, w0 + tkw - p.kw / 2, h0 + tkh - p.kh / 2,
+                          d0 + tkd - p.kd / 2, n0);
+          }
         }
         __syncwarp();
         if (++sg == p.cg) { sg = 0; ++g; }
@@ -1046,7 +1080,13 @@ conv_umma_wgrad_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_co
           for (int k = 0; k < KP / 8; ++k) {
             const uint64_t adesc = mn_desc(sa + k * kstep);
             const uint64_t bdesc = mn_desc(sa + a_bytes + k * kstep);
-            umma_tf32(tmem_base, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+            if (X3) {
+              umma_tf32(tmem_base, mn_desc(sa + half_bytes + k * kstep), bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+              umma_tf32(tmem_base, adesc, mn_desc(sa + half_bytes + a_bytes + k * kstep), idesc, 1u);
+              umma_tf32(tmem_base, adesc, bdesc, idesc, 1u);
+            } else {
+              umma_tf32(tmem_base, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
           }
           if (rel) umma_commit(empty_bar(g));
         }
@@ -1297,6 +1337,20 @@ __global__ void __launch_bounds__(128, 1) umma_rate_probe_kernel(float* out, int
 }
 
 // ------------------------------------------------------------------ host side
+// Tuning / test options (dgmr_set_option): plain process-wide ints read by the launchers -- no getenv on the launch path.
+// -1 = heuristic default.
+struct UmmaOptions {
+  int umma_cg = -1;          // 1: one tcgen05.commit per pipeline stage (no release groups)
+  int umma_persist = -1;     // 0: never the persistent plain kernel, 2: whenever eligible (small test shapes)
+  int umma_persist_r = -1;   // CTAs per SM of the persistent plain kernel (1..3)
+  int patch_pair = -1;       // 0: no CTA pairs in the halo-patch kernel
+  int patch_mt = -1;         // 128-row sub-tiles per halo-patch work item (1 or 2)
+  int patch_tg = -1;         // 1: release halo-patch weight tiles per tap instead of per filter row
+  int prefer_patch = -1;     // 1: AUTO dispatch takes the halo-patch kernel whenever it supports the shape (parity tests on small shapes)
+  int patch_dbg = 0;         // DGMR_TUNING builds only: make the halo-patch kernel skip work
+};
+static UmmaOptions g_opt;
+
 // channels per K block: 32 (128-byte rows) whenever Cin >= 32 -- a channel tail (Cin % 32 in {8,16,24}) is a last block whose
 // missing channels are TMA out-of-bounds zero fill and whose MMAs stop after the valid k-steps (64-byte-row TMA boxes move
 // half the bytes per row at the same per-row cost); 16 / 8 only for genuinely narrow inputs
@@ -1341,7 +1395,9 @@ static bool umma_fwd_ok(int N, int D, int H, int W, int Cin, int Cout, int kd, i
 }
 
 int launch_conv_umma_fwd(const float* x, const float* wp, const float* bias, const float* scale, const float* res, float* y, int N, int D, int H, int W, int Cin,
-                         int Cout, int kd, int kh, int kw, int G, int act, cudaStream_t st, int accumulate = 0) {
+                         int Cout, int kd, int kh, int kw, int G, int act, cudaStream_t st, int accumulate = 0, const float* x_lo = nullptr,
+                         const float* wp_lo = nullptr) {
+  const bool x3 = x_lo != nullptr && wp_lo != nullptr;
   UmmaConvParams p;
   p.split_taps = accumulate; p.n_tiles = 1;
   p.N = N; p.D = D; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.kd = kd; p.kh = kh; p.kw = kw; p.G = G;
@@ -1354,7 +1410,7 @@ int launch_conv_umma_fwd(const float* x, const float* wp, const float* bias, con
   p.act = act; p.bias = bias; p.scale = scale; p.res = res; p.y = y;
   p.tmem_cols = 32; while (p.tmem_cols < p.BN) p.tmem_cols <<= 1;
   const uint32_t a_bytes = 128u * p.BK * 4u, b_bytes = ((uint32_t)p.BN * p.BK * 4u + 1023u) & ~1023u;
-  const uint32_t stage_bytes = a_bytes + b_bytes;
+  const uint32_t stage_bytes = (a_bytes + b_bytes) * (x3 ? 2u : 1u);
   // several CTAs per SM so one tile's epilogue / prologue overlaps another tile's main loop: aim at <= ~72 KB of
   // pipeline per CTA (3 resident CTAs) but never fewer than 3 stages; big tiles fall back to 1-2 CTAs per SM
   // ... unless the whole grid fits in one or two CTAs per SM anyway (ConvGRU steps, latent stack): those launches are pure
@@ -1372,17 +1428,18 @@ int launch_conv_umma_fwd(const float* x, const float* wp, const float* bias, con
     if (stages >= 6) { stages = stages / 3 * 3; p.cg = 3; }
     else if (stages >= 4) { stages = 4; p.cg = 2; }
   }
-  if (const char* e = getenv("DGMR_UMMA_CG")) { if (atoi(e) == 1) p.cg = 1; }   // tuning knob
+  if (g_opt.umma_cg == 1) p.cg = 1;
   p.stages = stages;
   size_t smem = (size_t)stages * stage_bytes + 1024 /*align slack*/ + 8 * (2 * stages + 2);
   const int taps = kd * kh * kw;
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmAlo, tmBlo;
   {
     uint64_t dims[5] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)D, (uint64_t)N};
     uint64_t str[4] = {(uint64_t)Cin * 4, (uint64_t)W * Cin * 4, (uint64_t)H * W * Cin * 4, (uint64_t)D * H * W * Cin * 4};
     uint32_t box[5] = {(uint32_t)p.BK, (uint32_t)p.bw, (uint32_t)p.bh, 1u, (uint32_t)p.bn};
     int e = make_tmap(&tmA, x, 5, dims, str, box, p.BK * 4);
     if (e) return e;
+    if (x3) { e = make_tmap(&tmAlo, x_lo, 5, dims, str, box, p.BK * 4); if (e) return e; } else tmAlo = tmA;
   }
   {
     uint64_t dims[3] = {(uint64_t)Cin, (uint64_t)Cout, (uint64_t)taps};
@@ -1390,12 +1447,17 @@ int launch_conv_umma_fwd(const float* x, const float* wp, const float* bias, con
     uint32_t box[3] = {(uint32_t)p.BK, (uint32_t)p.BN, 1u};
     int e = make_tmap(&tmB, wp, 3, dims, str, box, p.BK * 4);
     if (e) return e;
+    if (x3) { e = make_tmap(&tmBlo, wp_lo, 3, dims, str, box, p.BK * 4); if (e) return e; } else tmBlo = tmB;
   }
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(conv_umma_fwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)) != cudaSuccess ||
-        cudaFuncSetAttribute(conv_umma_fwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)) != cudaSuccess ||
-        cudaFuncSetAttribute(conv_umma_fwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)) != cudaSuccess) {
+    const int lim = 220 * 1024;
+    if (cudaFuncSetAttribute(conv_umma_fwd_kernel<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim) != cudaSuccess ||
+        cudaFuncSetAttribute(conv_umma_fwd_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim) != cudaSuccess ||
+        cudaFuncSetAttribute(conv_umma_fwd_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim) != cudaSuccess ||
+        cudaFuncSetAttribute(conv_umma_fwd_kernel<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim) != cudaSuccess ||
+        cudaFuncSetAttribute(conv_umma_fwd_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim) != cudaSuccess ||
+        cudaFuncSetAttribute(conv_umma_fwd_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim) != cudaSuccess) {
       set_error("conv_umma_fwd: cannot raise dynamic smem limit"); return 2;
     }
     attr_set = true;
@@ -1407,16 +1469,16 @@ int launch_conv_umma_fwd(const float* x, const float* wp, const float* bias, con
   // Measured (tests/time_conv1x1.py, time_conv3d.py): +15..35 % on 1x1 convs and other short K loops (<= 12 K blocks per tile, where
   // the per-tile fixed cost dominates), neutral to slightly negative on long K loops (fewer CTAs per SM in flight) -> only the former.
   const int num_kb_tile = taps * (int)ceil_div(Cin, p.BK);
-  bool persist = !accumulate && (Cout % 4 == 0) && 2 * p.BN <= 512 && mtiles * ntiles >= 4 * (int64_t)sm_count() && num_kb_tile <= 12;
-  if (const char* e = getenv("DGMR_UMMA_PERSIST")) {   // tuning / test knob: 0 = never, 2 = whenever eligible (small test shapes)
-    const int v = atoi(e);
+  bool persist = !x3 && !accumulate && (Cout % 4 == 0) && 2 * p.BN <= 512 && mtiles * ntiles >= 4 * (int64_t)sm_count() && num_kb_tile <= 12;
+  if (g_opt.umma_persist >= 0) {   // tuning / test option: 0 = never, 2 = whenever eligible (small test shapes)
+    const int v = g_opt.umma_persist;
     if (v == 0) persist = false;
-    else if (v == 2) persist = !accumulate && (Cout % 4 == 0) && 2 * p.BN <= 512;
+    else if (v == 2) persist = !x3 && !accumulate && (Cout % 4 == 0) && 2 * p.BN <= 512;
   }
   if (persist) {
     int cols = 32; while (cols < 2 * p.BN) cols <<= 1;
     int R = 512 / cols; if (R > 2) R = 2;
-    if (const char* e = getenv("DGMR_UMMA_PERSIST_R")) { const int v = atoi(e); if (v >= 1 && v <= 3 && v <= 512 / cols) R = v; }   // tuning knob
+    if (g_opt.umma_persist_r >= 1 && g_opt.umma_persist_r <= 3 && g_opt.umma_persist_r <= 512 / cols) R = g_opt.umma_persist_r;
     const uint32_t budget = R == 3 ? 64u * 1024u : R == 2 ? 100u * 1024u : 196u * 1024u;
     int pst = (int)(budget / stage_bytes);
     if (pst < 2) { persist = false; }
@@ -1447,9 +1509,13 @@ int launch_conv_umma_fwd(const float* x, const float* wp, const float* bias, con
     }
   }
   dim3 grid((unsigned)mtiles, (unsigned)ntiles, (unsigned)(accumulate ? taps : 1));
-  if (p.BK == 32) conv_umma_fwd_kernel<32><<<grid, kUmmaThreads, smem, st>>>(tmA, tmB, p);
-  else if (p.BK == 16) conv_umma_fwd_kernel<16><<<grid, kUmmaThreads, smem, st>>>(tmA, tmB, p);
-  else conv_umma_fwd_kernel<8><<<grid, kUmmaThreads, smem, st>>>(tmA, tmB, p);
+  if (x3) {
+    if (p.BK == 32) conv_umma_fwd_kernel<32, true><<<grid, kUmmaThreads, smem, st>>>(tmA, tmB, tmAlo, tmBlo, p);
+    else if (p.BK == 16) conv_umma_fwd_kernel<16, true><<<grid, kUmmaThreads, smem, st>>>(tmA, tmB, tmAlo, tmBlo, p);
+    else conv_umma_fwd_kernel<8, true><<<grid, kUmmaThreads, smem, st>>>(tmA, tmB, tmAlo, tmBlo, p);
+  } else if (p.BK == 32) conv_umma_fwd_kernel<32, false><<<grid, kUmmaThreads, smem, st>>>(tmA, tmB, tmAlo, tmBlo, p);
+  else if (p.BK == 16) conv_umma_fwd_kernel<16, false><<<grid, kUmmaThreads, smem, st>>>(tmA, tmB, tmAlo, tmBlo, p);
+  else conv_umma_fwd_kernel<8, false><<<grid, kUmmaThreads, smem, st>>>(tmA, tmB, tmAlo, tmBlo, p);
   DGMR_CHECK_LAUNCH("conv_umma_fwd");
   return 0;
 }
@@ -1484,7 +1550,9 @@ static bool umma_wgrad_ok(int N, int D, int H, int W, int Cin, int Cout, int kd,
   return true;
 }
 
-int launch_conv_umma_wgrad(const float* x, const float* dz, float* dwp, int N, int D, int H, int W, int Cin, int Cout, int kd, int kh, int kw, cudaStream_t st) {
+int launch_conv_umma_wgrad(const float* x, const float* dz, float* dwp, int N, int D, int H, int W, int Cin, int Cout, int kd, int kh, int kw, cudaStream_t st,
+                           const float* x_lo = nullptr, const float* dz_lo = nullptr) {
+  const bool x3 = x_lo != nullptr && dz_lo != nullptr;
   UmmaWgradParams p;
   p.N = N; p.D = D; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.kd = kd; p.kh = kh; p.kw = kw;
   if (!pick_box32(N, H, W, &p.bw, &p.bh, &p.bn)) { set_error("conv_umma_wgrad: no 32-pixel box"); return 1; }
@@ -1496,7 +1564,7 @@ int launch_conv_umma_wgrad(const float* x, const float* dz, float* dwp, int N, i
   p.BN = (int)(ceil_div(bn_ci, p.aw) * p.aw);
   p.tmem_cols = 32; while (p.tmem_cols < p.BN) p.tmem_cols <<= 1;
   const uint32_t blk_bytes = 32u * p.aw * 4u;
-  const uint32_t stage_bytes = (128 / p.aw + p.BN / p.aw) * blk_bytes;
+  const uint32_t stage_bytes = (128 / p.aw + p.BN / p.aw) * blk_bytes * (x3 ? 2u : 1u);
   // one CTA per SM (launch bounds): use the shared memory for stages, handed back in groups so that a tcgen05.commit (which costs
   // the pipe ~780 cycles) follows >= 8 MMAs (4 per stage, 128..512 cycles each group otherwise)
   int stages = (int)((200u * 1024u) / stage_bytes);
@@ -1517,13 +1585,14 @@ int launch_conv_umma_wgrad(const float* x, const float* dz, float* dwp, int N, i
   p.kb_chunk = (int)ceil_div(p.kb_total, ksplit);
   ksplit = ceil_div(p.kb_total, p.kb_chunk);
   p.dwp = dwp;
-  CUtensorMap tmDz, tmX;
+  CUtensorMap tmDz, tmX, tmDzLo, tmXLo;
   {
     uint64_t dims[5] = {(uint64_t)Cout, (uint64_t)W, (uint64_t)H, (uint64_t)D, (uint64_t)N};
     uint64_t str[4] = {(uint64_t)Cout * 4, (uint64_t)W * Cout * 4, (uint64_t)H * W * Cout * 4, (uint64_t)D * H * W * Cout * 4};
     uint32_t box[5] = {(uint32_t)p.aw, (uint32_t)p.bw, (uint32_t)p.bh, 1u, (uint32_t)p.bn};
     int e = make_tmap(&tmDz, dz, 5, dims, str, box, p.aw * 4, true);
     if (e) return e;
+    if (x3) { e = make_tmap(&tmDzLo, dz_lo, 5, dims, str, box, p.aw * 4, true); if (e) return e; } else tmDzLo = tmDz;
   }
   {
     uint64_t dims[5] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)D, (uint64_t)N};
@@ -1531,17 +1600,20 @@ int launch_conv_umma_wgrad(const float* x, const float* dz, float* dwp, int N, i
     uint32_t box[5] = {(uint32_t)p.aw, (uint32_t)p.bw, (uint32_t)p.bh, 1u, (uint32_t)p.bn};
     int e = make_tmap(&tmX, x, 5, dims, str, box, p.aw * 4, true);
     if (e) return e;
+    if (x3) { e = make_tmap(&tmXLo, x_lo, 5, dims, str, box, p.aw * 4, true); if (e) return e; } else tmXLo = tmX;
   }
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(conv_umma_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)) != cudaSuccess) {
+    if (cudaFuncSetAttribute(conv_umma_wgrad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)) != cudaSuccess ||
+        cudaFuncSetAttribute(conv_umma_wgrad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)) != cudaSuccess) {
       set_error("conv_umma_wgrad: cannot raise dynamic smem limit"); return 2;
     }
     attr_set = true;
   }
   if (cudaMemsetAsync(dwp, 0, sizeof(float) * (size_t)taps * Cout * Cin, st) != cudaSuccess) { set_error("conv_umma_wgrad: memset failed"); return 2; }
   dim3 grid((unsigned)taps, (unsigned)ksplit, (unsigned)(co_tiles * p.ci_tiles));
-  conv_umma_wgrad_kernel<<<grid, kUmmaThreads, smem, st>>>(tmDz, tmX, p);
+  if (x3) conv_umma_wgrad_kernel<true><<<grid, kUmmaThreads, smem, st>>>(tmDz, tmX, tmDzLo, tmXLo, p);
+  else conv_umma_wgrad_kernel<false><<<grid, kUmmaThreads, smem, st>>>(tmDz, tmX, tmDzLo, tmXLo, p);
   DGMR_CHECK_LAUNCH("conv_umma_wgrad");
   return 0;
 }
@@ -1560,6 +1632,7 @@ static bool umma_patch_ok(int N, int D, int H, int W, int Cin, int Cout, int kd,
 // and narrow outputs (Cout < 64) make every MMA so short that the per-tap barrier round trips dominate (measured: 96->48 at
 // 128^2 runs 289 TF/s on the plain kernel, 178 TF/s here).
 static bool umma_patch_profitable(int N, int D, int H, int W, int Cin, int Cout) {
+  if (g_opt.prefer_patch == 1) return true;
   return Cin % 32 == 0 && Cout >= 64 && (int64_t)H * W >= 1024 && (int64_t)N * D * H * W >= (int64_t)128 * 4 * sm_count();
 }
 
@@ -1584,7 +1657,7 @@ int launch_conv_umma_patch(const float* x, const float* wp, const float* bias, c
   // CTA pairs (cta_group::2): each CTA stages half of every weight tile, so the weight ring is twice as deep in the same shared
   // memory and the weight bytes per SM halve -- the ring depth is what starves the MMAs at 96..192 channels
   int pair = (p.BK == 32 && (int64_t)N * D >= 2 && p.BN % 16 == 0 && sm_count() % 2 == 0) ? 1 : 0;
-  if (const char* e = getenv("DGMR_PATCH_PAIR")) pair = pair && atoi(e) != 0;   // tuning knob
+  if (g_opt.patch_pair == 0) pair = 0;
   // two sub-tiles per weight stage when accumulators and shared memory allow; double-buffer the accumulators when they still fit
   const uint32_t budget = 208u * 1024u;   // + 16 KB epilogue staging + barriers + alignment slack <= 226 KB
   const uint32_t b_al = (((uint32_t)(pair ? p.BN / 2 : p.BN) * row_bytes) + 1023u) & ~1023u;
@@ -1593,7 +1666,7 @@ int launch_conv_umma_patch(const float* x, const float* wp, const float* bias, c
   bool fits = false;
   const int64_t tiles_total = (int64_t)p.n_tiles * N * D * ceil_div((int64_t)H * p.P - 2, 128);
   int mt_start = (2 * p.BN <= 512 && tiles_total >= 2 * (int64_t)sm_count()) ? 2 : 1;
-  if (const char* e = getenv("DGMR_PATCH_MT")) { int v = atoi(e); if (v == 1 || (v == 2 && 2 * p.BN <= 512)) mt_start = v; }   // tuning knob
+  if (g_opt.patch_mt == 1 || (g_opt.patch_mt == 2 && 2 * p.BN <= 512)) mt_start = g_opt.patch_mt;
   for (p.MT = mt_start; p.MT >= 1; --p.MT) {
     const int span = 128 * p.MT + 2 * p.P + 2;
     p.Rb = (int)ceil_div(p.P - 1 + span, p.P);
@@ -1610,7 +1683,7 @@ int launch_conv_umma_patch(const float* x, const float* wp, const float* bias, c
   p.sb_vec = (((reinterpret_cast<uintptr_t>(bias) | reinterpret_cast<uintptr_t>(scale)) & 15u) == 0) ? 1 : 0;
   p.dbg = 0;
 #ifdef DGMR_TUNING      // the knob makes the kernel skip work (wrong results): only in tuning builds
-  if (const char* e = getenv("DGMR_PATCH_DBG")) p.dbg = atoi(e);
+  p.dbg = g_opt.patch_dbg;
 #endif
   if (((reinterpret_cast<uintptr_t>(res) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(wp)) & 15u) != 0) {
     set_error("conv_umma_patch: x / wp / res / y must be 16-byte aligned"); return 1;
@@ -1621,7 +1694,7 @@ int launch_conv_umma_patch(const float* x, const float* wp, const float* bias, c
   if (p.b_stages > 9) p.b_stages = 9;
   p.tg = 1;
   if (p.b_stages >= 6) { p.tg = 3; p.b_stages = p.b_stages / 3 * 3; }   // one release (commit) per filter row of 3 taps, >= 2 rows in flight
-  if (const char* e = getenv("DGMR_PATCH_TG")) { if (atoi(e) == 1) p.tg = 1; }   // tuning knob
+  if (g_opt.patch_tg == 1) p.tg = 1;
   size_t smem = (size_t)p.a_stages * patch_al + (size_t)p.b_stages * b_al + 1024 + 8 * (2 * p.a_stages + 2 * p.b_stages + 6) + 128 + 8 * 2048;
   CUtensorMap tmA, tmB;
   {
@@ -1765,6 +1838,16 @@ int dgmr_debug_umma_rate(float* out /*[blocks]*/, int blocks, int N, int iters, 
   DGMR_CHECK_LAUNCH("umma_rate_probe");
   return 0;
 }
+int dgmr_set_option(const char* name, int value) {
+  if (name == nullptr) { set_error("dgmr_set_option: null name"); return 1; }
+  struct { const char* n; int* v; } tab[] = {{"umma_cg", &g_opt.umma_cg}, {"umma_persist", &g_opt.umma_persist}, {"umma_persist_r", &g_opt.umma_persist_r},
+                                             {"patch_pair", &g_opt.patch_pair}, {"patch_mt", &g_opt.patch_mt}, {"patch_tg", &g_opt.patch_tg},
+                                             {"prefer_patch", &g_opt.prefer_patch}, {"patch_dbg", &g_opt.patch_dbg}};
+  for (auto& t : tab)
+    if (strcmp(t.n, name) == 0) { *t.v = value; return 0; }
+  set_error("dgmr_set_option: unknown option '%s'", name);
+  return 1;
+}
 int dgmr_conv_umma_supported(int N, int D, int H, int W, int Cin, int Cout, int kd, int kh, int kw) {
   return umma_fwd_ok(N, D, H, W, Cin, Cout, kd, kh, kw, 1) ? 1 : 0;
 }
@@ -1780,15 +1863,25 @@ int dgmr_conv_fwd(const float* x, const float* x_lo, const float* wp, const floa
   const int accumulate = (act & DGMR_FLAG_ACCUMULATE) ? 1 : 0;
   act &= ~DGMR_FLAG_ACCUMULATE;
   DGMR_REQUIRE(act == DGMR_ACT_NONE || act == DGMR_ACT_RELU, "dgmr_conv_fwd: bad act");
-  (void)x_lo; (void)wp_lo;
+  DGMR_REQUIRE(precision == DGMR_PREC_TF32 || precision == DGMR_PREC_3XTF32, "dgmr_conv_fwd: bad precision");
   bool ok = umma_fwd_ok(N, D, H, W, Cin, Cout, kd, kh, kw, G);
+  // 3xTF32 ("parity mode"): the caller hands over the hi and lo parts of both operands (dgmr_split_tf32); served by the plain tcgen05
+  // kernel only (three MMAs per k-step).  Without lo parts the call is an ordinary 1xTF32 / fp32-SIMT call on `x`, `wp`.
+  const bool x3 = precision == DGMR_PREC_3XTF32 && x_lo != nullptr && wp_lo != nullptr;
+  if (precision == DGMR_PREC_3XTF32 && !x3)
+    DGMR_REQUIRE(x_lo == nullptr && wp_lo == nullptr, "dgmr_conv_fwd: 3xTF32 needs both x_lo and wp_lo (or neither: full-precision operands for the SIMT kernel)");
+  if (x3) {
+    DGMR_REQUIRE(ok && algo != DGMR_ALGO_SIMT, "dgmr_conv_fwd: 3xTF32 operand pairs were passed but the shape is not served by the tcgen05 path");
+    if (accumulate) DGMR_REQUIRE(bias == nullptr && res == nullptr && act == DGMR_ACT_NONE, "dgmr_conv_fwd: ACCUMULATE excludes bias/res/act");
+    return launch_conv_umma_fwd(x, wp, bias, scale, res, y, N, D, H, W, Cin, Cout, kd, kh, kw, G, act, S(stream), accumulate, x_lo, wp_lo);
+  }
+  if (precision == DGMR_PREC_3XTF32) algo = DGMR_ALGO_SIMT;   // full-precision operands: fp32 FMA kernel
   if (accumulate) {
     DGMR_REQUIRE(bias == nullptr && res == nullptr && act == DGMR_ACT_NONE, "dgmr_conv_fwd: ACCUMULATE excludes bias/res/act");
     DGMR_REQUIRE(ok && algo != DGMR_ALGO_SIMT, "dgmr_conv_fwd: ACCUMULATE is a tensor-core-path mode");
     return launch_conv_umma_fwd(x, wp, nullptr, scale, nullptr, y, N, D, H, W, Cin, Cout, kd, kh, kw, G, DGMR_ACT_NONE, S(stream), 1);
   }
   if (algo == DGMR_ALGO_UMMA || algo == DGMR_ALGO_UMMA_PATCH) DGMR_REQUIRE(ok, "dgmr_conv_fwd: shape not supported by the tcgen05 path");
-  DGMR_REQUIRE(precision == DGMR_PREC_TF32 || algo == DGMR_ALGO_SIMT || !ok, "dgmr_conv_fwd: 3xTF32 not implemented on the tcgen05 path yet");
   if (algo == DGMR_ALGO_UMMA || algo == DGMR_ALGO_UMMA_PATCH || (algo == DGMR_ALGO_AUTO && ok)) {
     if (algo != DGMR_ALGO_UMMA && umma_patch_ok(N, D, H, W, Cin, Cout, kd, kh, kw, G) &&
         (algo == DGMR_ALGO_UMMA_PATCH || umma_patch_profitable(N, D, H, W, Cin, Cout))) {
@@ -1801,11 +1894,19 @@ int dgmr_conv_fwd(const float* x, const float* x_lo, const float* wp, const floa
   return launch_conv_simt_fwd(x, wp, bias, scale, res, y, N, D, H, W, Cin, Cout, kd, kh, kw, G, act, S(stream));
 }
 
-int dgmr_conv_wgrad(const float* x, const float* dz, const float* xT, const float* dzT, const float* xT_lo, const float* dzT_lo, float* dwp, int N, int D,
-                    int H, int W, int Cin, int Cout, int kd, int kh, int kw, int algo, int precision, dgmr_stream_t stream) {
-  (void)xT; (void)dzT; (void)xT_lo; (void)dzT_lo; (void)precision;  // MN-major tiles come straight from x / dz: no transposed copies needed
+int dgmr_conv_wgrad(const float* x, const float* x_lo, const float* dz, const float* dz_lo, float* dwp, int N, int D, int H, int W, int Cin, int Cout,
+                    int kd, int kh, int kw, int algo, int precision, dgmr_stream_t stream) {
   DGMR_REQUIRE(N > 0 && D > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, "dgmr_conv_wgrad: bad dims");
+  DGMR_REQUIRE(precision == DGMR_PREC_TF32 || precision == DGMR_PREC_3XTF32, "dgmr_conv_wgrad: bad precision");
   bool ok = umma_wgrad_ok(N, D, H, W, Cin, Cout, kd, kh, kw) && (reinterpret_cast<uintptr_t>(dwp) & 15u) == 0;   // 16-byte vector reductions into dwp
+  const bool x3 = precision == DGMR_PREC_3XTF32 && x_lo != nullptr && dz_lo != nullptr;
+  if (precision == DGMR_PREC_3XTF32 && !x3)
+    DGMR_REQUIRE(x_lo == nullptr && dz_lo == nullptr, "dgmr_conv_wgrad: 3xTF32 needs both x_lo and dz_lo (or neither: full-precision operands for the SIMT kernel)");
+  if (x3) {
+    DGMR_REQUIRE(ok && algo != DGMR_ALGO_SIMT, "dgmr_conv_wgrad: 3xTF32 operand pairs were passed but the shape is not served by the tcgen05 path");
+    return launch_conv_umma_wgrad(x, dz, dwp, N, D, H, W, Cin, Cout, kd, kh, kw, S(stream), x_lo, dz_lo);
+  }
+  if (precision == DGMR_PREC_3XTF32) algo = DGMR_ALGO_SIMT;
   if (algo == DGMR_ALGO_UMMA || algo == DGMR_ALGO_UMMA_PATCH) DGMR_REQUIRE(ok, "dgmr_conv_wgrad: shape not supported by the tcgen05 path (or dwp not 16-byte aligned)");
   if (algo == DGMR_ALGO_UMMA_PATCH) DGMR_REQUIRE(umma_wgrad_row_ok(N, D, H, W, Cin, Cout, kd, kh, kw), "dgmr_conv_wgrad: shape not supported by the row kernel");
   if (algo == DGMR_ALGO_UMMA_PATCH || (algo == DGMR_ALGO_AUTO && ok && umma_wgrad_row_ok(N, D, H, W, Cin, Cout, kd, kh, kw) && (int64_t)N * D * H * W >= 16384))

@@ -93,12 +93,14 @@ __global__ void relu_fwd_kernel(const float* __restrict__ x, float* __restrict__
 __global__ void relu_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, float* __restrict__ dx, int64_t n) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) dx[i] = x[i] > 0.f ? dy[i] : 0.f;
 }
+// 3xTF32 operand split: hi = nearest tf32 of x, lo = nearest tf32 of (x - hi).  x - hi is exact in fp32, |lo| <= 2^-11 |x| and what
+// the pair drops is <= 2^-22 |x|, unbiased (round-to-nearest both times: the MMA itself would truncate).
 __global__ void split_tf32_kernel(const float* __restrict__ x, float* __restrict__ hi, float* __restrict__ lo, int64_t n) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     float v = x[i];
-    float h = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+    float h = rna_tf32_pw(v);
     hi[i] = h;
-    lo[i] = v - h;
+    lo[i] = rna_tf32_pw(v - h);
   }
 }
 

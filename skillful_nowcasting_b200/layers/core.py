@@ -91,8 +91,7 @@ class SNConv(nn.Module):
         pending = self.__dict__.pop("_pending_sigma", None)
         # a prefetched value is only valid for the weights and mode it was computed for (a forward that raised between the
         # prefetch and this call may have left a stale one behind)
-        if pending is not None and pending[2] == (self.weight_orig._version, self.training, torch.is_grad_enabled()):
-            assert pending[0] == G, f"prefetched spectral norm for G={pending[0]} but used with G={G}"
+        if pending is not None and pending[0] == G and pending[2] == (self.weight_orig._version, self.training, torch.is_grad_enabled()):
             return pending[1]
         u, v = self._uv
         return ops.spectral_inv_sigma(self.weight_orig, u, v, G, self.eps, self.training)

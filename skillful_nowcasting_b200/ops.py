@@ -12,13 +12,18 @@ import torch
 from torch.autograd import Function
 
 from . import _lib
-from ._lib import ACT_NONE, ACT_RELU, ALGO_AUTO, ALGO_SIMT, ALGO_UMMA, FLAG_ACCUMULATE, FLAG_ROUND_TF32, PREC_TF32
+from ._lib import ACT_NONE, ACT_RELU, ALGO_AUTO, ALGO_SIMT, ALGO_UMMA, FLAG_ACCUMULATE, FLAG_ROUND_TF32, PREC_3XTF32, PREC_TF32
+
+FLAG_SPLIT = 1024   # packed_weight(): return the [hi | lo] 3xTF32 pair (host-side flag, never crosses the ABI)
 
 
 class config:
     """Runtime knobs (tests flip these to cross-check the tensor-core path against the SIMT kernels)."""
     conv_algo = ALGO_AUTO
     wgrad_algo = ALGO_AUTO
+    # PREC_TF32: 1xTF32 operands (what cuDNN does by default for the reference's convolutions) -- the fast mode every benchmark
+    # number comes from.  PREC_3XTF32: "parity mode": error-compensated operand pairs (hi*hi + hi*lo + lo*hi, ~fp32 accuracy) on
+    # the plain tcgen05 kernels; nothing is rounded to tf32 anywhere.
     precision = PREC_TF32
     # operands of tensor-core convs are rounded to the NEAREST tf32 value first (the MMA itself truncates, which is
     # biased): weights while packing, activations in place (idempotent), dz in the backward prologue
@@ -431,7 +436,7 @@ class _ConvOperand(Function):
 
     @staticmethod
     def forward(ctx, x):
-        return _round_(_c(x).detach()) if config.round_tf32 and config.conv_algo != ALGO_SIMT and _be().name == "cuda" else x.view_as(x)
+        return _round_(_c(x).detach()) if _rounding_on() else x.view_as(x)
 
     @staticmethod
     def backward(ctx, g):
@@ -442,13 +447,37 @@ def conv_operand(x):
     return _ConvOperand.apply(x)
 
 
+def _rounding_on() -> bool:
+    """Are conv operands rounded to tf32 at all (1xTF32 tensor-core mode on the CUDA library)?"""
+    return config.round_tf32 and config.conv_algo != ALGO_SIMT and config.precision == PREC_TF32 and _be().name == "cuda"
+
+
 def _tc_fwd(n, d, h, w, cin, cout, kd, kh, kw) -> bool:
-    """Will dgmr_conv_fwd serve this shape on the tensor cores (and should operands therefore be tf32-rounded)?"""
-    return (config.round_tf32 and config.conv_algo != ALGO_SIMT and _be().conv_umma_supported(n, d, h, w, cin, cout, kd, kh, kw))
+    """Will dgmr_conv_fwd serve this shape on the tensor cores in 1xTF32 mode (and should operands therefore be tf32-rounded)?"""
+    return (config.round_tf32 and config.precision == PREC_TF32 and config.conv_algo != ALGO_SIMT
+            and _be().conv_umma_supported(n, d, h, w, cin, cout, kd, kh, kw))
 
 
 def _tc_wgrad(n, d, h, w, cin, cout, kd, kh, kw) -> bool:
-    return (config.round_tf32 and config.wgrad_algo != ALGO_SIMT and _be().wgrad_umma_supported(n, d, h, w, cin, cout, kd, kh, kw))
+    return (config.round_tf32 and config.precision == PREC_TF32 and config.wgrad_algo != ALGO_SIMT
+            and _be().wgrad_umma_supported(n, d, h, w, cin, cout, kd, kh, kw))
+
+
+def _x3_fwd(n, d, h, w, cin, cout, kd, kh, kw) -> bool:
+    """Parity mode and the tcgen05 path serves the shape: operands go in as 3xTF32 (hi, lo) pairs."""
+    return (config.precision == PREC_3XTF32 and config.conv_algo != ALGO_SIMT and _be().name == "cuda"
+            and _be().conv_umma_supported(n, d, h, w, cin, cout, kd, kh, kw))
+
+
+def _x3_wgrad(n, d, h, w, cin, cout, kd, kh, kw) -> bool:
+    return (config.precision == PREC_3XTF32 and config.wgrad_algo != ALGO_SIMT and _be().name == "cuda"
+            and _be().wgrad_umma_supported(n, d, h, w, cin, cout, kd, kh, kw))
+
+
+def _split(t: torch.Tensor):
+    hl = _new((2,) + tuple(t.shape), t)
+    _be().split_tf32(t, hl[0], hl[1])
+    return hl[0], hl[1]
 
 
 def _use_split_taps(n, d, h, w, cin, cout, taps, has_bias, act) -> bool:
@@ -456,7 +485,7 @@ def _use_split_taps(n, d, h, w, cin, cout, taps, has_bias, act) -> bool:
     if not config.split_taps or taps == 1 or has_bias or act != ACT_NONE or config.conv_algo == ALGO_SIMT:
         return False
     tiles = ((n * d * h * w + 127) // 128) * ((cout + 255) // 256)
-    return tiles <= 32 and cin >= 32 and _be().conv_umma_supported(n, d, h, w, cin, cout, 1, 3, 3)   # measured crossover (tests/time_gru_conv.py)
+    return tiles <= 32 and cin >= 32 and _be().name == "cuda" and _be().conv_umma_supported(n, d, h, w, cin, cout, 1, 3, 3)   # measured crossover (tests/time_gru_conv.py)
 
 
 def _pack_slot(w: torch.Tensor):
@@ -501,7 +530,9 @@ def packed_weight(w: torch.Tensor, ci0: int, cin: int, mode: int) -> torch.Tenso
     cout, cintot = w.shape[0], w.shape[1]
     taps = w.numel() // (cout * cintot)
     p = _new((taps * cout * cin,), w)
-    _be().pack_weight(_c(w.detach()), p, cout, cintot, ci0, cin, taps, mode)
+    _be().pack_weight(_c(w.detach()), p, cout, cintot, ci0, cin, taps, mode & ~(FLAG_SPLIT | (FLAG_ROUND_TF32 if mode & FLAG_SPLIT else 0)))
+    if mode & FLAG_SPLIT:   # parity mode: [2, n] = (hi, lo) of the unrounded pack
+        p = torch.stack(_split(p))
     _pack_store(slot, w, key, p)
     return p
 
@@ -517,12 +548,15 @@ def packed_weight_padded(w: torch.Tensor, ci0: int, cin: int, cin_p: int, mode: 
     cout, cintot = w.shape[0], w.shape[1]
     taps = w.numel() // (cout * cintot)
     p = _zeros((taps * cout * cin_p,), w)
-    rnd, mode = mode & FLAG_ROUND_TF32, mode & ~FLAG_ROUND_TF32
+    split, mode = mode & FLAG_SPLIT, mode & ~FLAG_SPLIT
+    rnd, mode = (0 if split else mode & FLAG_ROUND_TF32), mode & ~FLAG_ROUND_TF32
     dense = packed_weight(w, ci0, cin, mode | rnd)
     if mode == 0:   # p[tap][co][ci] with row pitch cin_p
         _be().permute(dense, p, (taps * cout, cin), (cin, 1), (cin_p, 1), False, 0, 0)
     else:           # p[taps-1-tap][ci][co]: ci rows spread to cin_p per tap (extra rows stay zero)
         _be().permute(dense, p, (taps, cin, cout), (cin * cout, cout, 1), (cin_p * cout, cout, 1), False, 0, 0)
+    if split:
+        p = torch.stack(_split(p))
     _pack_store(slot, w, key, p)
     return p
 
@@ -537,17 +571,35 @@ def clear_pack_cache():
 
 def _conv_launch(x, wp, bias, scale, res, y, n, d, h, wd, c, cout, kd, kh, kw, G, act):
     """y = act(conv(x, wp) * scale + bias + res) through the C ABI; picks the tap-split accumulate mode for launches that
-    would otherwise leave most SMs idle.  `res` may alias `y` (each element is read, then written, by the same thread)."""
+    would otherwise leave most SMs idle.  `res` may alias `y` (each element is read, then written, by the same thread).
+    wp of shape [2, n] is a 3xTF32 (hi, lo) pair (parity mode): x is split the same way here."""
     be = _be()
-    if _use_split_taps(n, d, h, wd, c, cout, kd * kh * kw, bias is not None, act) and be.conv_umma_supported(n, d, h, wd, c, cout, kd, kh, kw):
+    x_lo = wp_lo = None
+    if wp.dim() == 2:
+        wp, wp_lo = wp[0], wp[1]
+        x, x_lo = _split(x)
+    if _use_split_taps(n, d, h, wd, c, cout, kd * kh * kw, bias is not None, act) and be.conv_umma_supported(n, d, h, wd, c, cout, kd, kh, kw) \
+            and (config.precision == PREC_TF32 or x_lo is not None):
         if res is None:
             be.fill(y, 0.0)
         elif res.data_ptr() != y.data_ptr():
             be.axpby(1.0, res, 0.0, None, y)   # y starts as the residual, the taps accumulate on top
         be.conv_fwd(x, wp, None, scale, None, y, n, d, h, wd, c, cout, kd, kh, kw, G, ACT_NONE | FLAG_ACCUMULATE,
-                    config.conv_algo, config.precision)
+                    config.conv_algo, config.precision, x_lo=x_lo, wp_lo=wp_lo)
     else:
-        be.conv_fwd(x, wp, bias, scale, res, y, n, d, h, wd, c, cout, kd, kh, kw, G, act, config.conv_algo, config.precision)
+        be.conv_fwd(x, wp, bias, scale, res, y, n, d, h, wd, c, cout, kd, kh, kw, G, act, config.conv_algo, config.precision,
+                    x_lo=x_lo, wp_lo=wp_lo)
+
+
+def _wgrad_launch(x, dz, dwp, n, d, h, wd, cin, cout, kd, kh, kw):
+    """dwp = wgrad(x, dz) through the C ABI; parity mode splits both operands into 3xTF32 pairs when the tcgen05 path takes the shape."""
+    be = _be()
+    if _x3_wgrad(n, d, h, wd, cin, cout, kd, kh, kw) and (dwp.data_ptr() & 15) == 0:
+        xh, xl = _split(x)
+        zh, zl = _split(dz)
+        be.conv_wgrad(xh, zh, dwp, n, d, h, wd, cin, cout, kd, kh, kw, config.wgrad_algo, config.precision, x_lo=xl, dz_lo=zl)
+    else:
+        be.conv_wgrad(x, dz, dwp, n, d, h, wd, cin, cout, kd, kh, kw, config.wgrad_algo, config.precision)
 
 
 class _Conv(Function):
@@ -566,6 +618,8 @@ class _Conv(Function):
             x = _round_(x)
         if not config._dbg_round_w:
             rnd = 0
+        if _x3_fwd(n, d, h, wd, c, cout, kd, kh, kw):
+            rnd = FLAG_SPLIT
         wp = packed_weight(w, ci0, cin, rnd) if c == cin else packed_weight_padded(w, ci0, cin, c, rnd)
         y = _new((n, d, h, wd, cout), x)
         res_c, scale_c, bias_c = _c(res), _c(scale), _c(bias)
@@ -604,8 +658,8 @@ class _Conv(Function):
                 # ref: dgmr/layers/Attention.py:69): recompute the raw conv output and reduce <dpre, z> directly
                 assert act == ACT_NONE
                 z = _new(dy.shape, dy)
-                be.conv_fwd(x, packed_weight(w, ci0, cin, 0), None, None, None, z, n, d, h, wd, cin, cout, kd, kh, kw, 1, ACT_NONE,
-                            config.conv_algo, config.precision)
+                _conv_launch(x, packed_weight(w, ci0, cin, FLAG_SPLIT if _x3_fwd(n, d, h, wd, cin, cout, kd, kh, kw) else 0), None, None, None, z,
+                             n, d, h, wd, cin, cout, kd, kh, kw, 1, ACT_NONE)
                 ones = torch.ones((G, cout), device=dy.device, dtype=dy.dtype)
                 be.conv_bwd_prep(dy, z, None, None, ones, None, None, None, dscale, rows, G, cout, ACT_NONE)
             if dz is None:
@@ -621,13 +675,15 @@ class _Conv(Function):
                 dz = _round_(dz)
         if need_x:
             rnd = FLAG_ROUND_TF32 if (_tc_fwd(n, d, h, wd, cout, cp, kd, kh, kw) and config._dbg_round_w) else 0
+            if _x3_fwd(n, d, h, wd, cout, cp, kd, kh, kw):
+                rnd = FLAG_SPLIT
             wpt = packed_weight(w, ci0, cin, 1 | rnd) if cp == cin else packed_weight_padded(w, ci0, cin, cp, 1 | rnd)
             dx = _new(x.shape, x)
             _conv_launch(dz, wpt, None, None, None, dx, n, d, h, wd, cout, cp, kd, kh, kw, 1, ACT_NONE)
         if need_w:
             taps = kd * kh * kw
             dwp = _new((taps * cout * cp,), x)
-            be.conv_wgrad(x, dz, dwp, n, d, h, wd, cp, cout, kd, kh, kw, config.wgrad_algo, config.precision)
+            _wgrad_launch(x, dz, dwp, n, d, h, wd, cp, cout, kd, kh, kw)
             cintot = w.shape[1]
             dw = _new(w.shape, x) if cin == cintot else _zeros(w.shape, x)
             if cp == cin:
@@ -664,7 +720,7 @@ class _BatchNorm(Function):
         mean, invstd, a, b = (_new((G, c), x) for _ in range(4))
         be.bn_finalize(sums, gamma, beta, rmean, rvar, rows, G, c, eps, momentum, training, mean, invstd, a, b)
         y = _new((n, d, 2 * h, 2 * w, c) if up2 else (n, d, h, w, c), x)
-        rnd = conv_only and config.round_tf32 and config.conv_algo != ALGO_SIMT and be.name == "cuda"
+        rnd = conv_only and _rounding_on()
         be.bn_apply(x, a, b, y, rows, G, c, int(relu_) | (FLAG_ROUND_TF32 if rnd else 0), up2, h, w)
         if rnd:
             y._dgmr_tf32 = True
@@ -774,8 +830,9 @@ class _GruSequence(Function):
         rows = B * H * W
         rnd_ru = FLAG_ROUND_TF32 if _tc_fwd(B, 1, H, W, ch, 2 * ch, 1, 3, 3) else 0
         rnd_c = FLAG_ROUND_TF32 if _tc_fwd(B, 1, H, W, ch, ch, 1, 3, 3) else 0
-        wp_ru = packed_weight(w_ru, cx, ch, rnd_ru)
-        wp_c = packed_weight(w_c, cx, ch, rnd_c)
+        x3 = _x3_fwd(B, 1, H, W, ch, 2 * ch, 1, 3, 3) and _x3_fwd(B, 1, H, W, ch, ch, 1, 3, 3)
+        wp_ru = packed_weight(w_ru, cx, ch, FLAG_SPLIT if x3 else rnd_ru)
+        wp_c = packed_weight(w_c, cx, ch, FLAG_SPLIT if x3 else rnd_c)
         out = _new((T * B, 1, H, W, ch), h0)
         pru = _new((T * B, 1, H, W, 2 * ch), h0)
         cp = _new((T * B, 1, H, W, ch), h0)
@@ -816,8 +873,9 @@ class _GruSequence(Function):
         tc_dg_c = _tc_fwd(B, 1, H, W, ch, ch, 1, 3, 3)
         tc_wg_ru = _tc_wgrad(T * B, 1, H, W, ch, 2 * ch, 1, 3, 3)
         tc_wg_c = _tc_wgrad(T * B, 1, H, W, ch, ch, 1, 3, 3)
-        wpt_ru = packed_weight(w_ru, cx, ch, 1 | (FLAG_ROUND_TF32 if tc_dg_ru else 0))
-        wpt_c = packed_weight(w_c, cx, ch, 1 | (FLAG_ROUND_TF32 if tc_dg_c else 0))
+        x3 = _x3_fwd(B, 1, H, W, 2 * ch, ch, 1, 3, 3) and _x3_fwd(B, 1, H, W, ch, ch, 1, 3, 3)
+        wpt_ru = packed_weight(w_ru, cx, ch, 1 | (FLAG_SPLIT if x3 else FLAG_ROUND_TF32 if tc_dg_ru else 0))
+        wpt_c = packed_weight(w_c, cx, ch, 1 | (FLAG_SPLIT if x3 else FLAG_ROUND_TF32 if tc_dg_c else 0))
         # running dL/dh_t: starts as the output gradient (of both views of the output), steps add their carry
         if dout is None:
             gh = _c(dout_r).clone()
@@ -851,7 +909,7 @@ class _GruSequence(Function):
         dws = []
         for wt, x_all, dz_all, co in ((w_ru, xop, dzru, 2 * ch), (w_c, rh, dzc, ch)):
             dwp = _new((9 * co * ch,), h0)
-            be.conv_wgrad(x_all, dz_all, dwp, T * B, 1, H, W, ch, co, 1, 3, 3, config.wgrad_algo, config.precision)
+            _wgrad_launch(x_all, dz_all, dwp, T * B, 1, H, W, ch, co, 1, 3, 3)
             dw = _zeros(wt.shape, h0)
             be.unpack_wgrad(dwp, dw, co, wt.shape[1], cx, ch, 9, False)
             dws.append(dw)

@@ -10,11 +10,14 @@ for p in (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "tests", "golden
         sys.path.insert(0, p)
 
 HAVE_REFERENCE = os.path.isdir(os.environ.get("DGMR_REFERENCE", "/root/reference"))
+# the unmodified reference package: /root/reference in the build container, baseline/_ref (pip --target install, travels with gpurun) elsewhere
+HAVE_REFERENCE_PKG = HAVE_REFERENCE or os.path.isfile(os.path.join(ROOT, "baseline", "_ref", "dgmr", "dgmr.py"))
 
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
     config.addinivalue_line("markers", "reference: needs /root/reference (build container only)")
+    config.addinivalue_line("markers", "refpkg: needs the reference package (/root/reference or baseline/_ref)")
 
 
 def pytest_collection_modifyitems(config, items):
@@ -24,6 +27,8 @@ def pytest_collection_modifyitems(config, items):
             item.add_marker(pytest.mark.skip(reason="no CUDA device"))
         if "reference" in item.keywords and not HAVE_REFERENCE:
             item.add_marker(pytest.mark.skip(reason="/root/reference not present"))
+        if "refpkg" in item.keywords and not HAVE_REFERENCE_PKG:
+            item.add_marker(pytest.mark.skip(reason="reference package not present (baseline/_ref)"))
 
 
 @pytest.fixture
@@ -39,12 +44,20 @@ def emu():
     ops.clear_pack_cache()
 
 
+OPTIONS = ("umma_cg", "umma_persist", "umma_persist_r", "patch_pair", "patch_mt", "patch_tg", "prefer_patch")
+
+
 @pytest.fixture
 def cuda_backend():
     from skillful_nowcasting_b200 import _lib, ops
 
     old = _lib.set_backend(None)
     ops.clear_pack_cache()
-    yield _lib.backend()
+    be = _lib.backend()
+    yield be
+    for o in OPTIONS:       # tests may flip launcher options: back to the heuristics
+        be.set_option(o, -1)
+    ops.config.precision = 0
+    ops.config.conv_algo = ops.config.wgrad_algo = 0
     _lib.set_backend(old)
     ops.clear_pack_cache()

@@ -77,9 +77,9 @@ class EmuBackend:
         (x if y is None else y).copy_(self._rna_tf32(x))
 
     def split_tf32(self, x, hi, lo):
-        h = (x.view(torch.int32) & -8192).view(torch.float32)
+        h = self._rna_tf32(x)
         hi.copy_(h)
-        lo.copy_(x - h)
+        lo.copy_(self._rna_tf32(x - h))
 
     def pool_sum(self, x, y, N, D, H, W, C, pd, ph, pw, scale):
         v = x.reshape(N, D, H, W, C)[:, :D // pd * pd, :H // ph * ph, :W // pw * pw]
@@ -281,7 +281,7 @@ class EmuBackend:
                 zs = zs - res.reshape(G, rows, Cout)
             dscale.copy_((d * zs).sum(1) / scale.reshape(G, Cout))
 
-    def conv_wgrad(self, x, dz, dwp, N, D, H, W, Cin, Cout, kd, kh, kw, algo=0, precision=0, xT=None, dzT=None, xT_lo=None, dzT_lo=None):
+    def conv_wgrad(self, x, dz, dwp, N, D, H, W, Cin, Cout, kd, kh, kw, algo=0, precision=0, x_lo=None, dz_lo=None):
         xi = x.reshape(N, D, H, W, Cin).permute(0, 4, 1, 2, 3)
         g = dz.reshape(N, D, H, W, Cout).permute(0, 4, 1, 2, 3)
         with torch.enable_grad():

@@ -157,3 +157,150 @@ def global_grad_error(got, ref):
         num += float(((g - r) ** 2).sum())
         den += float((r ** 2).sum())
     return (num / max(den, 1e-300)) ** 0.5
+
+
+# ------------------------------------------------------------------------------------------------ one full GAN step
+def oracle_gan_step(g_state, d_state, x, y, cfg, seed, generation_steps=1):
+    """oracle.gan_step on cloned state: returns losses, post-step parameters / buffers and the Adam moments."""
+    gs = O.clone_state(g_state, requires_grad=True)
+    ds = O.clone_state(d_state, requires_grad=True)
+    gn, dn = O._trainable(gs), O._trainable(ds)
+    g_opt = O.AdamState([gs[k] for k in gn], lr=5e-5)
+    d_opt = O.AdamState([ds[k] for k in dn], lr=2e-4)
+    s = cfg["output_shape"]
+    torch.manual_seed(seed)
+    losses = O.gan_step(gs, ds, g_opt, d_opt, x, y, cfg["forecast_steps"], (8, s // 32, s // 32), generation_steps=generation_steps)
+    return dict(losses=losses, g_state=gs, d_state=ds, g_names=gn, d_names=dn,
+                g_m=dict(zip(gn, g_opt.m)), g_v=dict(zip(gn, g_opt.v)), d_m=dict(zip(dn, d_opt.m)), d_v=dict(zip(dn, d_opt.v)),
+                g_t=g_opt.t, d_t=d_opt.t)
+
+
+def module_gan_step(gen, disc, x, y, seed, device, generation_steps=1):
+    """training.gan_step through the B200 modules and the fused Adam: the same quantities as oracle_gan_step."""
+    from skillful_nowcasting_b200.training import Adam, gan_step
+
+    gen.train(); disc.train()
+    g_opt = Adam(gen.parameters(), lr=5e-5, betas=(0.0, 0.999))
+    d_opt = Adam(disc.parameters(), lr=2e-4, betas=(0.0, 0.999))
+    torch.manual_seed(seed)
+    losses = gan_step(gen, disc, g_opt, d_opt, x.to(device), y.to(device), generation_steps=generation_steps)
+
+    def moments(opt, module):
+        names = [n for n, _ in module.named_parameters()]
+        sd = opt.state_dict()["state"]
+        return ({n: sd[i]["exp_avg"] for i, n in enumerate(names)}, {n: sd[i]["exp_avg_sq"] for i, n in enumerate(names)})
+
+    g_m, g_v = moments(g_opt, gen)
+    d_m, d_v = moments(d_opt, disc)
+    return dict(losses=losses, g_state=gen.state_dict(), d_state=disc.state_dict(), g_m=g_m, g_v=g_v, d_m=d_m, d_v=d_v,
+                g_t=g_opt.steps, d_t=d_opt.steps, requires_grad_after=all(p.requires_grad for p in disc.parameters()))
+
+
+def _l2(got, ref, names):
+    num = den = 0.0
+    for k in names:
+        a, b = got[k].detach().double().cpu(), ref[k].detach().double()
+        num += float(((a - b) ** 2).sum())
+        den += float((b ** 2).sum())
+    return (num / den) ** 0.5 if den > 0 else num ** 0.5   # all-zero reference (saturated hinge: zero gradient): absolute
+
+
+# bounds for compare_gan_step.  FP32: fp32 arithmetic on both sides (SIMT kernels, 3xTF32 parity mode, the host emulator) -- set from
+# the noise floor "oracle with 8 threads vs oracle with 3 threads" (g_m 5e-3, g_update 3.5e-3, d_uv 2.6e-4, d_bn 7.7e-3) times ~10;
+# TF32: 1xTF32 operands end to end through batch-stat BatchNorm at fresh init (chaotic, SURVEY.md section 7).
+GAN_STEP_TOL_FP32 = dict(d_loss=2e-3, g_loss=2e-3, grid_loss=2e-3, g_m=5e-2, g_v=1e-1, g_update=5e-2, g_uv=2e-4, g_bn=2e-3,
+                         d_m=5e-2, d_v=1e-1, d_update=5e-2, d_uv=2e-2, d_bn=5e-2)
+GAN_STEP_TOL_TF32 = dict(d_loss=5e-2, g_loss=5e-2, grid_loss=5e-2, g_m=0.3, g_v=0.6, g_update=0.35, g_uv=2e-4, g_bn=5e-2,
+                         d_m=0.3, d_v=0.6, d_update=0.35, d_uv=0.1, d_bn=0.2)
+
+
+def gan_step_report(got, ref, g0, d0):
+    """Everything one GAN step leaves behind, as error numbers (see compare_gan_step for how they are judged)."""
+    rep = {}
+    for k in ("d_loss", "g_loss", "grid_loss"):
+        rep[k] = rel_err(got["losses"][k], ref["losses"][k])
+    for net, names, s0 in (("g", ref["g_names"], g0), ("d", ref["d_names"], d0)):
+        rep[f"{net}_m"] = _l2(got[f"{net}_m"], ref[f"{net}_m"], names)
+        rep[f"{net}_v"] = _l2(got[f"{net}_v"], ref[f"{net}_v"], names)
+        num = den = 0.0
+        for k in names:
+            p, pr, p0 = got[f"{net}_state"][k].detach().double().cpu(), ref[f"{net}_state"][k].detach().double(), s0[k].double()
+            num += float((p - pr).abs().sum())
+            den += float((pr - p0).abs().sum())
+        rep[f"{net}_update"] = num / max(den, 1e-300)
+        rep[f"{net}_uv"] = rep[f"{net}_bn"] = 0.0
+        for k, v in ref[f"{net}_state"].items():
+            g = got[f"{net}_state"][k]
+            if k.endswith("._u") or k.endswith("._v"):
+                rep[f"{net}_uv"] = max(rep[f"{net}_uv"], rel_err(g, v))
+            elif "running_" in k:
+                rep[f"{net}_bn"] = max(rep[f"{net}_bn"], rel_err(g, v))
+            elif "num_batches" in k:
+                assert int(g) == int(v), k
+    return rep
+
+
+def compare_gan_step(got, ref, g0, d0, tol):
+    """Judge one GAN step against oracle.gan_step.  `tol` maps the report's keys to bounds:
+      d_loss / g_loss / grid_loss  relative error of the three logged losses;
+      g_m, d_m / g_v, d_v          Adam exp_avg (= the last gradient, beta1 = 0) / exp_avg_sq, global relative L2 over all parameters;
+      g_update, d_update           parameters, through the update they received: with beta1 = 0 the first Adam step moves every element
+                                   by lr * sign(g) (|g| >> eps), so they are compared by  sum|p - p_ref| / sum|p_ref - p_0|  (a flipped sign
+                                   of a ~0 gradient element costs 2 units of lr there);
+      g_uv, d_uv / g_bn, d_bn      mutated buffers: spectral-norm u, v / BatchNorm running statistics (max rel err over the buffers);
+                                   num_batches_tracked, the Adam step counts and the discriminator's requires_grad flags must be exact.
+    The discriminator takes TWO updates per step: everything after the first one (second forward, its gradient, the buffers) runs
+    on weights that moved by lr * sign(g), so sign flips of near-zero gradient elements are amplified there -- the d_* bounds are
+    looser than the g_* ones even for fp32 arithmetic (the fp32 emulator-vs-oracle numbers are recorded in tests/test_host_logic.py)."""
+    rep = gan_step_report(got, ref, g0, d0)
+    assert got["g_t"] == ref["g_t"] == 1 and got["d_t"] == ref["d_t"] == 2
+    assert got["requires_grad_after"], "gan_step left discriminator parameters frozen"
+    bad = {k: (v, tol[k]) for k, v in rep.items() if v >= tol[k]}
+    assert not bad, f"GAN step mismatch (value, bound): {bad}\nfull report: {rep}"
+    return rep
+
+
+# ------------------------------------------------------------------------------------------------ discriminators, separately
+def run_discriminator_case(which, training, device, tol_fwd, tol_grad_l2=None, cfg=C1, seed=3):
+    """SpatialDiscriminator / TemporalDiscriminator alone against the oracle (ref: dgmr/discriminators.py:104-138, 196-232) on a
+    [2B, T_in + T, 1, S, S] batch of real || "generated" sequences; forward scores and (training) the global gradient error."""
+    import skillful_nowcasting_b200 as B
+
+    torch.manual_seed(seed)
+    mod = B.SpatialDiscriminator(input_channels=1) if which == "spatial" else B.TemporalDiscriminator(input_channels=1)
+    pfx = "spatial_discriminator." if which == "spatial" else "temporal_discriminator."
+    st = O.clone_state({pfx + k: v for k, v in mod.state_dict().items()}, requires_grad=training)
+    s, b, t = cfg["output_shape"], cfg["batch"], 4 + cfg["forecast_steps"]
+    x = torch.rand(2 * b, t, 1, s, s)
+    mod.train(training)
+    torch.manual_seed(seed + 1)
+    if which == "spatial":
+        ref = O.spatial_discriminator(st, pfx[:-1], x, training)
+    else:
+        ref = O.temporal_discriminator(st, pfx[:-1], x, training)
+    mod.to(device)
+    torch.manual_seed(seed + 1)
+    got = mod(x.to(device))
+    e = rel_err(got, ref)
+    out = dict(fwd=e, ref=ref.detach().flatten().tolist(), got=got.detach().flatten().cpu().tolist())
+    assert got.shape == ref.shape
+    assert e < tol_fwd, (which, "scores", e, out["ref"], out["got"])
+    if training:
+        w = torch.randn_like(ref)
+        names = [k for k in st if st[k].requires_grad]
+        rg = torch.autograd.grad((ref * w).sum(), [st[k] for k in names], allow_unused=True)
+        params = dict(mod.named_parameters())
+        mg = torch.autograd.grad((got * w.to(device)).sum(), [params[k[len(pfx):]] for k in names], allow_unused=True)
+        keep = [k for k, g in zip(names, rg) if g is not None]
+        gd = {k: g for k, g in zip(names, mg) if g is not None}
+        rd = {k: g for k, g in zip(names, rg) if g is not None}
+        assert set(gd) == set(rd)
+        out["grad_l2"] = _l2(gd, rd, keep)
+        assert out["grad_l2"] < tol_grad_l2, (which, "gradients", out["grad_l2"])
+        for k, v in mod.state_dict().items():
+            r = st[pfx + k]
+            if k.endswith("._u") or k.endswith("._v"):
+                assert rel_err(v, r) < 2e-4, k
+            elif "running_" in k:
+                assert rel_err(v, r) < max(tol_fwd, 1e-3), k
+    return out

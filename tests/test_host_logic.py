@@ -116,3 +116,120 @@ def test_dgmr_training_step_runs_reference_schedule(emu):
     # parameters that never receive gradients stay put (g*.conv_1x1 w+b; attention q/k/v/out while gamma == 0)
     assert g_changed >= len(g_before) - 12 and d_changed >= 30, (g_changed, len(g_before), d_changed, len(d_before))
     assert model(x).shape == (2, 2, 1, 128, 128)
+
+
+def test_gan_step_matches_oracle_step(emu):
+    """training.gan_step (minimal schedule, fused Adam on flat buffers, requires_grad toggling) against oracle.gan_step from the same
+    state and seeds: losses, all parameters, Adam moments and step counts, mutated buffers.  Recorded fp32 numbers (emulator vs oracle):
+    g_m 6.7e-3, g_update 4.2e-3, d_uv 3.3e-3, d_bn 8.0e-3; oracle vs itself with another thread count: 5.3e-3, 3.5e-3, 2.6e-4, 7.7e-3."""
+    from parity_util import GAN_STEP_TOL_FP32, compare_gan_step, module_gan_step, oracle_gan_step
+
+    gen, disc = build_gan(C1, seed=0, gamma=0.5)
+    g0 = {k: v.clone() for k, v in gen.state_dict().items()}
+    d0 = {k: v.clone() for k, v in disc.state_dict().items()}
+    x, y = c1_inputs()
+    ref = oracle_gan_step(g0, d0, x, y, C1, seed=4)
+    got = module_gan_step(gen, disc, x, y, seed=4, device="cpu")
+    compare_gan_step(got, ref, g0, d0, GAN_STEP_TOL_FP32)
+
+
+@pytest.mark.parametrize("which", ["spatial", "temporal"])
+@pytest.mark.parametrize("training", [False, True], ids=["eval", "train"])
+def test_discriminators_separately(emu, which, training):
+    from parity_util import run_discriminator_case
+
+    run_discriminator_case(which, training, "cpu", 2e-4 if not training else 1e-3, tol_grad_l2=1e-2)
+
+
+def test_packed_weights_die_with_their_parameter(emu):
+    """Regression (advisor, round 1): the packed-weight cache was keyed on (data_ptr, version); a new layer whose storage landed on a
+    freed layer's address silently ran with the old layer's packed weights.  No clear_pack_cache() between the builds here."""
+    from skillful_nowcasting_b200.layers.core import PlainConv
+
+    for i in range(12):
+        torch.manual_seed(i)
+        m = PlainConv(8, 8, (3, 3))
+        x = torch.randn(1, 8, 6, 6)
+        ref = torch.nn.functional.conv2d(x, m.weight, m.bias, padding=1)
+        assert rel_err(m(x), ref) < 1e-5, i
+        with torch.no_grad():          # in-place update without a version bump through autograd is still seen (version counter moves)
+            m.weight.mul_(2.0)
+        assert rel_err(m(x), torch.nn.functional.conv2d(x, m.weight, m.bias, padding=1)) < 1e-5, i
+        del m
+
+
+def test_adam_checkpoints_like_torch_and_survives_detached_grads(emu):
+    """Regression (advisor): Optimizer.state_dict() carried no moments; module.zero_grad() detached the gradients from the flat buffer."""
+    from skillful_nowcasting_b200.training import Adam
+
+    torch.manual_seed(0)
+    lin, ref = torch.nn.Linear(5, 3), torch.nn.Linear(5, 3)
+    ref.load_state_dict(lin.state_dict())
+    o, ro = Adam(lin.parameters(), lr=1e-2, betas=(0.0, 0.999)), torch.optim.Adam(ref.parameters(), lr=1e-2, betas=(0.0, 0.999))
+    x = torch.randn(4, 5)
+    for _ in range(3):
+        o.zero_grad(); ro.zero_grad()
+        lin(x).pow(2).sum().backward(); ref(x).pow(2).sum().backward()
+        o.step(); ro.step()
+    assert torch.allclose(lin.weight, ref.weight, atol=1e-7)
+    sd, rsd = o.state_dict(), ro.state_dict()
+    assert float(sd["state"][0]["step"]) == 3
+    for i in (0, 1):
+        for k in ("exp_avg", "exp_avg_sq"):
+            assert torch.allclose(sd["state"][i][k], rsd["state"][i][k], atol=1e-8), (i, k)
+    lin2 = torch.nn.Linear(5, 3)
+    lin2.load_state_dict(ref.state_dict())
+    o2 = Adam(lin2.parameters(), lr=1e-2, betas=(0.0, 0.999))
+    o2.load_state_dict(rsd)                       # a torch.optim.Adam checkpoint resumes here
+    lin2.zero_grad(); ref.zero_grad()             # set_to_none: autograd will create fresh .grad tensors
+    lin2(x).pow(2).sum().backward(); ref(x).pow(2).sum().backward()
+    o2.step(); ro.step()
+    assert torch.allclose(lin2.weight, ref.weight, atol=1e-7)
+    torch.optim.Adam(ref.parameters(), lr=1e-2).load_state_dict(o2.state_dict())   # and the other way round
+    with pytest.raises(RuntimeError):
+        o2.add_param_group({"params": [torch.nn.Parameter(torch.zeros(2))]})
+        o2.step()
+
+
+def test_stale_prefetched_sigma_is_dropped(emu):
+    """Regression (advisor): a forward that raised between prefetch_sigmas and the consuming conv left a pending 1/sigma behind."""
+    from skillful_nowcasting_b200.common import GBlock
+    from skillful_nowcasting_b200.layers.core import prefetch_sigmas
+
+    torch.manual_seed(0)
+    blk = GBlock(8, 8)
+    prefetch_sigmas(blk.sn_calls(1))              # ... and the forward never happens
+    with torch.no_grad():
+        blk.first_conv_3x3.weight_orig.mul_(3.0)  # weights move on
+    y = blk(torch.rand(2, 8, 4, 4))               # must neither assert nor use the stale sigma
+    st = O.clone_state({"m." + k: v for k, v in blk.state_dict().items()})
+    assert torch.isfinite(y).all()
+    prefetch_sigmas(blk.sn_calls(2))              # a stale entry for another G is simply replaced
+    blk.run(torch.rand(2, 1, 4, 4, 8), 1)
+
+
+@pytest.mark.refpkg
+def test_unmodified_reference_wrapper_runs_on_these_modules(emu):
+    """SURVEY 8b / 8d mode (i): the reference's OWN dgmr/dgmr.py (unmodified, from /root/reference or baseline/_ref) constructs and trains
+    these modules through the import swap of INTEGRATION.md, and logs the losses the reference itself logs from the same seeds."""
+    import os
+    import sys
+
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from baseline import reference_arm as R
+
+    cfg = dict(forecast_steps=2, output_shape=128, latent_channels=288, context_channels=48)
+    torch.manual_seed(1)
+    x, y = torch.rand(2, 4, 1, 128, 128), torch.rand(2, 2, 1, 128, 128)
+    logs = {}
+    for dropin in (False, True):
+        model = R.build_dgmr(cfg, generation_steps=1, dropin=dropin, anomaly=False, seed=0)
+        assert type(model).__module__ == "dgmr.dgmr"
+        assert type(model.generator).__module__.startswith("skillful_nowcasting_b200" if dropin else "dgmr.")
+        torch.manual_seed(2)
+        logs[dropin] = {k: float(v) for k, v in R.training_step_fn(model, x, y)().items()}
+    for k in ("train/d_loss", "train/g_loss", "train/grid_loss"):
+        a, b = logs[True][k], logs[False][k]
+        assert abs(a - b) <= 2e-3 * max(abs(b), 1e-6), (k, a, b)
+    for k in [k for k in sys.modules if k == "dgmr" or k.startswith("dgmr.")]:
+        del sys.modules[k]

@@ -126,3 +126,127 @@ def test_conv_gru_simt_and_tensor_core(cuda_backend, fused):
     finally:
         ops.config.conv_algo = ops.config.wgrad_algo = 0
         ops.config.gru_sequence = old
+
+
+# ------------------------------------------------------------------------------------------------ modes
+# "simt": fp32 FMA kernels; "tf32": AUTO dispatch, 1xTF32 operands (the benchmark's mode); "tf32-patch": AUTO dispatch preferring the
+# halo-patch / CTA-pair kernels the benchmark shapes run on (they are not profitable, hence not chosen, at C1's sizes);
+# "3xtf32": parity mode, error-compensated operand pairs on the plain tcgen05 kernels.
+def _set_mode(be, mode):
+    from skillful_nowcasting_b200 import ops
+
+    ops.clear_pack_cache()
+    ops.config.conv_algo = ops.config.wgrad_algo = 1 if mode == "simt" else 0
+    ops.config.precision = 1 if mode == "3xtf32" else 0
+    be.set_option("prefer_patch", 1 if mode == "tf32-patch" else -1)
+
+
+@pytest.mark.parametrize("mode", ["tf32-patch", "3xtf32"])
+@pytest.mark.parametrize("training", [False, True], ids=["eval", "train"])
+def test_c1_gan_patch_kernels_and_parity_mode(cuda_backend, c1_state, mode, training):
+    """The C1 GAN forward / losses / gradients against the oracle (a) with the halo-patch + CTA-pair kernels forced into AUTO
+    dispatch, so the kernels the benchmark relies on see oracle data, and (b) in 3xTF32 parity mode, whose tolerances are the
+    fp32 ones: eval 1e-4 (north star: 1e-3), train-mode output 2e-3, gradients as for the fp32 SIMT path."""
+    gen, disc, g0, d0 = c1_state
+    x, y = c1_inputs()
+    ref = oracle_gan_forward(g0, d0, x, y, C1, training, seed=2)
+    gen.load_state_dict(g0); disc.load_state_dict(d0)
+    gen.cuda(); disc.cuda()
+    _set_mode(cuda_backend, mode)
+    got = module_gan_forward(gen, disc, x, y, training, seed=2, device="cuda")
+    x3 = mode == "3xtf32"
+    tol_out = (2e-3 if x3 else 5e-2) if training else (1e-4 if x3 else 1e-3)
+    e_out, e_sc = rel_err(got["out"], ref["out"]), rel_err(got["scores"], ref["scores"])
+    print(f"\nC1 {mode} {'train' if training else 'eval'}: out {e_out:.2e} scores {e_sc:.2e}")
+    assert e_out < tol_out, e_out
+    assert e_sc < tol_out * (1 if x3 else 5), e_sc
+    for k in ("d_loss", "grid", "g_loss"):
+        assert rel_err(got[k], ref[k]) < tol_out, (k, float(got[k]), float(ref[k]))
+    if training:
+        gd, gg = global_grad_error(got["d_grads"], ref["d_grads"]), global_grad_error(got["g_grads"], ref["g_grads"])
+        print(f"   global gradient error D {gd:.2e} G {gg:.2e}")
+        if x3:
+            compare_grads(got["d_grads"], ref["d_grads"], 2e-3, 5e-2, zero_floor=1e-6)
+            compare_grads(got["g_grads"], ref["g_grads"], 5e-2, 2e-1, zero_floor=1e-5)
+            assert gd < 2e-3 and gg < 5e-2, (gd, gg)
+        else:
+            assert gd < 0.25 and gg < 0.3, (gd, gg)
+    gen.cpu(); disc.cpu()
+
+
+@pytest.mark.parametrize("mode", ["simt", "tf32", "3xtf32"])
+def test_gan_step_against_oracle(cuda_backend, c1_state, mode):
+    """ONE full training.gan_step on C1 (2 discriminator updates + 1 generator update through the fused Adam) against
+    oracle.gan_step from the same state, seeds and RNG order: losses, every parameter, Adam exp_avg / exp_avg_sq / step, all
+    mutated buffers, and the requires_grad toggling of the discriminator (ref: dgmr/dgmr.py:137-218, :292-300)."""
+    from parity_util import GAN_STEP_TOL_FP32, GAN_STEP_TOL_TF32, compare_gan_step, module_gan_step, oracle_gan_step
+
+    gen, disc, g0, d0 = c1_state
+    x, y = c1_inputs()
+    ref = oracle_gan_step(g0, d0, x, y, C1, seed=4)
+    gen.load_state_dict(g0); disc.load_state_dict(d0)
+    gen.cuda(); disc.cuda()
+    _set_mode(cuda_backend, mode)
+    got = module_gan_step(gen, disc, x, y, seed=4, device="cuda")
+    # 1xTF32 end to end through batch-stat BatchNorm at fresh init is chaotic (see module docstring): loose there, tight elsewhere
+    rep = compare_gan_step(got, ref, g0, d0, GAN_STEP_TOL_TF32 if mode == "tf32" else GAN_STEP_TOL_FP32)
+    print(f"\nGAN STEP {mode}: " + " ".join(f"{k} {v:.2e}" for k, v in rep.items()))
+    gen.cpu(); disc.cpu()
+    gen.load_state_dict(g0); disc.load_state_dict(d0)
+
+
+@pytest.mark.parametrize("mode", ["simt", "tf32", "tf32-patch", "3xtf32"])
+@pytest.mark.parametrize("which", ["spatial", "temporal"])
+@pytest.mark.parametrize("training", [False, True], ids=["eval", "train"])
+def test_discriminators_separately(cuda_backend, which, training, mode):
+    """Spatial and temporal discriminator each on its own, so a score error is attributable.
+    Tolerances: north-star 1e-3 on the scores in eval mode for every tensor-core mode; fp32-level for SIMT and 3xTF32."""
+    from parity_util import run_discriminator_case
+
+    _set_mode(cuda_backend, mode)
+    fp = mode in ("simt", "3xtf32")
+    tol = (2e-4 if fp else 1e-3) if not training else (1e-3 if fp else 2e-2)
+    # (gradients: fp32 restatements of the temporal discriminator already differ by 3e-3 from each other through BatchNorm1d over 4 rows)
+    out = run_discriminator_case(which, training, "cuda", tol, tol_grad_l2=(1e-2 if fp else 0.2))
+    print(f"\nDISC {which} {mode} {'train' if training else 'eval'}: scores rel err {out['fwd']:.2e}" +
+          (f" grad L2 {out['grad_l2']:.2e}" if training else ""))
+
+
+@pytest.mark.parametrize("case", block_cases(True), ids=lambda c: c[0])
+def test_block_parity_mode(cuda_backend, case):
+    """Wide blocks in 3xTF32 parity mode: forward and gradients at fp32-level tolerances (per-block gradients <= 1e-3 rel)."""
+    _set_mode(cuda_backend, "3xtf32")
+    run_block_case(case, True, "cuda", 2e-5, 1e-3, tol_buf=1e-4, tol_l2=3e-4)
+
+
+def test_conv_gru_parity_mode(cuda_backend):
+    _set_mode(cuda_backend, "3xtf32")
+    run_conv_gru_case("cuda", 2e-5, 1e-3, cx=64, ch=32, s=16, T=4, tol_l2=3e-4)
+
+
+def test_pretrained_round_trip_on_gpu(cuda_backend, c1_state, tmp_path):
+    """save_pretrained / from_pretrained (ref: README.md:57-69, tests/test_model.py:341-399) with the model on the GPU: same keys,
+    same tensors, same eval forward afterwards."""
+    import skillful_nowcasting_b200 as B
+
+    gen, disc, g0, d0 = c1_state
+    gen.load_state_dict(g0)
+    gen.cuda().eval()
+    x, _ = c1_inputs()
+    torch.manual_seed(9)
+    a = gen(x.cuda())
+    for name, mod, cls in (("sampler", gen.sampler, B.Sampler), ("ctx", gen.conditioning_stack, B.ContextConditioningStack),
+                           ("lat", gen.latent_stack, B.LatentConditioningStack)):
+        mod.save_pretrained(tmp_path / name)
+        new = cls.from_pretrained(tmp_path / name)
+        assert not new.training
+        sd_a, sd_b = mod.state_dict(), new.state_dict()
+        assert list(sd_a) == list(sd_b)
+        for k in sd_a:
+            assert torch.equal(sd_a[k].cpu(), sd_b[k].cpu()), k
+    g2 = B.Generator(B.ContextConditioningStack.from_pretrained(tmp_path / "ctx"), B.LatentConditioningStack.from_pretrained(tmp_path / "lat"),
+                     B.Sampler.from_pretrained(tmp_path / "sampler")).cuda().eval()
+    torch.manual_seed(9)
+    b = g2(x.cuda())
+    assert torch.equal(a, b)
+    gen.cpu()

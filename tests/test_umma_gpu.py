@@ -38,10 +38,10 @@ UMMA_SHAPES = [
 
 @pytest.mark.parametrize("shape", UMMA_SHAPES)
 @pytest.mark.parametrize("variant", ["plain", "fused", "fused-persistent"])
-def test_conv_umma(cuda_backend, shape, variant, monkeypatch):
+def test_conv_umma(cuda_backend, shape, variant):
     n, d, h, w, cin, cout, kd, kh, kw, g = shape
     # "persistent": force the many-tile persistent kernel (double-buffered TMEM, continuous K stream) on these small shapes
-    monkeypatch.setenv("DGMR_UMMA_PERSIST", "2" if variant.endswith("persistent") else "0")
+    cuda_backend.set_option("umma_persist", 2 if variant.endswith("persistent") else 0)
     variant = variant.split("-")[0]
     assert cuda_backend.conv_umma_supported(n, d, h, w, cin, cout, kd, kh, kw), "shape should be served by tcgen05 path"
     torch.manual_seed(11)
