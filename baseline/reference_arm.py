@@ -123,3 +123,42 @@ def training_step_fn(model, x, y):
         model.training_step((x, y), 0)
         return model.logged
     return step
+
+
+def minimal_step_fn(model, x, y):
+    """The parity-preserving minimal schedule on the REFERENCE's modules: what this repository's native step driver runs
+    (skillful_nowcasting_b200.training.gan_step), restated with the reference's own generator / discriminator / losses / torch.optim.Adam
+    -- so that the native arm can be compared with the reference arithmetic under the same schedule, not only under the wrapper's
+    literal one (which back-propagates the generator in the D phase, recomputes it under checkpoint and runs a trailing forward)."""
+    import dgmr.dgmr as wrapper
+
+    g_opt, d_opt = model.optimizers()
+    b = x.shape[0]
+
+    def step():
+        real = torch.cat([x, y], dim=1)
+        for _ in range(2):
+            d_opt.zero_grad()
+            with torch.no_grad():
+                pred = model.generator(x)
+            out = model.discriminator(torch.cat([real, torch.cat([x, pred], dim=1)], dim=0))
+            sr, sg = out[:b], out[b:]
+            d_loss = wrapper.loss_hinge_disc(sg[:, 0:1], sr[:, 0:1]) + wrapper.loss_hinge_disc(sg[:, 1:2], sr[:, 1:2])
+            d_loss.backward()
+            d_opt.step()
+        g_opt.zero_grad()
+        d_params = [p for p in model.discriminator.parameters()]
+        for p in d_params:
+            p.requires_grad_(False)
+        try:
+            preds = [model.generator(x) for _ in range(model.generation_steps)]
+            grid = model.grid_regularizer(torch.stack(preds, dim=0).mean(dim=0), y)
+            scores = [model.discriminator(torch.cat([real, torch.cat([x, p_], dim=1)], dim=0))[b:] for p_ in preds]
+            g_loss = wrapper.loss_hinge_gen(torch.cat(scores, dim=0)) + model.grid_lambda * grid
+            g_loss.backward()
+        finally:
+            for p in d_params:
+                p.requires_grad_(True)
+        g_opt.step()
+        return {"train/d_loss": d_loss.detach(), "train/g_loss": g_loss.detach(), "train/grid_loss": grid.detach()}
+    return step

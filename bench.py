@@ -1,12 +1,21 @@
 #!/usr/bin/env python
 """Benchmark of the DGMR GAN training step on the B200-native path.
 
-    python bench.py --gpus N --steps K --warmup W          (N > 1: launched under torch.distributed.run)
-    python bench.py --impl reference ...                    (CPU arm: the oracle port of the reference on host cores)
+    python bench.py --gpus N --steps K --warmup W            (N > 1: launched under torch.distributed.run)
+    python bench.py --impl reference --steps K --warmup W    (reference arm: the UNMODIFIED reference on the host cores)
+    python bench.py --config c2|c3|c5  --mode native|dropin  --precision tf32|3xtf32   (other BASELINE.json configs / modes)
 
-One "step" = one full GAN step (2 discriminator updates + 1 generator update, hinge + grid-cell losses, Adam) on a
-synthetic batch of 4->18-frame 256x256 radar sequences: BASELINE.json configs[2] per GPU (configs[3] when N > 1:
-batch 16 per GPU, weak scaling, NCCL all-reduce of the flat G/D gradient buffers).  Prints ONE JSON line on rank 0.
+One "step" (default config c3, BASELINE.json configs[2]; configs[3] when N > 1) = one full GAN step: 2 discriminator updates + 1
+generator update, hinge + grid-cell losses, Adam, on a synthetic batch of 16 4->18-frame 256x256 radar sequences per GPU (weak
+scaling, NCCL all-reduce of the flat G/D gradient buffers).  Prints ONE JSON line on rank 0.
+
+What the line carries besides the contract's keys:
+  roofline             the dominant tcgen05 launch (largest share of the instrumented step), per launch, plus the aggregate over all
+                       tensor-core launches (conv fwd/dgrad, tap-split, wgrad)
+  cpu_baseline         the reference's own `DGMR.training_step` (baseline/_ref; oracle port if absent) on the host cores, bounded sample
+  reference_gpu_eager  the reference's own GPU path on the same B200: unmodified modules `.cuda()`, PyTorch eager + cuDNN, the wrapper's
+                       literal schedule as shipped (autograd anomaly mode on) and with anomaly mode off, and the minimal schedule the
+                       native arm runs -- the denominators of the ">= 5x the cuDNN-backed step" target
 """
 import argparse
 import json
@@ -23,6 +32,15 @@ sys.path.insert(0, ROOT)
 
 F_G = 521.4e9   # forward FLOPs (2*MAC) of the generator per sample, paper config
 F_D = 35.7e9    # forward FLOPs of both discriminators per 22-frame sequence
+METRIC = "radar frames/sec (G+D step, 256x256, 4->18)"
+
+# BASELINE.json configs.  c3 is the headline (c4 = c3 per GPU under torchrun); c1 is the reference's CPU smoke case.
+CONFIGS = {
+    "c1": dict(size=128, forecast_steps=4, latent=384, context=192, batch=2, k=1, kind="step"),
+    "c2": dict(size=256, forecast_steps=18, latent=768, context=384, batch=8, k=1, kind="inference"),
+    "c3": dict(size=256, forecast_steps=18, latent=768, context=384, batch=16, k=1, kind="step"),
+    "c5": dict(size=256, forecast_steps=18, latent=768, context=384, batch=16, k=6, kind="step"),
+}
 
 
 def flop_step(batch, k):
@@ -37,6 +55,17 @@ def peaks():
         return dict(bf16=d.get("bf16_tflops", 1590.0), bf16_sustained=d.get("bf16_tflops_sustained", 1400.0),
                     hbm=d.get("hbm_gbs", 6650.0), source="measured")
     return dict(bf16=1590.0, bf16_sustained=1400.0, hbm=6650.0, source="fallback")
+
+
+def workload_config(args, world):
+    """The `config` object of the JSON line -- built the same way for both arms so that the driver can compare them."""
+    c = CONFIGS[args.config]
+    what = ("DGMR generator-only eval inference" if c["kind"] == "inference" else
+            "DGMR full GAN step (G + spatial+temporal D, hinge + grid-cell, 2 D updates + 1 G update, Adam)")
+    return dict(workload=f"{what}, 4->{c['forecast_steps']} frames 1x{c['size']}x{c['size']}, latent {c['latent']} / context {c['context']}, "
+                         f"batch {args.batch}/GPU, generation_steps={args.generation_steps}",
+                name=args.config + ("/c4" if (args.config == "c3" and world > 1) else ""),
+                global_batch=world * args.batch, parallelism=f"dp{world}")
 
 
 class ClockSampler(threading.Thread):
@@ -74,7 +103,7 @@ class ClockSampler(threading.Thread):
 
 # ----------------------------------------------------------------------------------------------------- CPU arm
 def build_oracle_state(cfg, seed=0):
-    """Seeded construction through the package's parameter containers (CPU, no kernels), as a flat state dict."""
+    """Seeded construction through the package's parameter containers (CPU, no kernels)."""
     import skillful_nowcasting_b200 as B
 
     torch.manual_seed(seed)
@@ -89,7 +118,7 @@ def build_oracle_state(cfg, seed=0):
 
 def usable_cores() -> int:
     """Host cores this process may really use: affinity mask and cgroup quota, not os.cpu_count() (on a box with a CPU quota,
-    one thread per visible core oversubscribes the quota and the oracle crawls)."""
+    one thread per visible core oversubscribes the quota and torch crawls)."""
     n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     try:
         quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
@@ -97,104 +126,139 @@ def usable_cores() -> int:
             n = min(n, max(1, int(int(quota) / int(period))))
     except (OSError, ValueError):
         pass
-    return max(1, min(n, 32))     # the oracle's many small ops do not scale past a few tens of threads
+    return max(1, min(n, 32))     # the many small ops of this model do not scale past a few tens of threads
 
 
 # bounded samples of the workload, largest first: (image side, forecast steps).  The discriminator needs side >= 128.
 CPU_SAMPLES = ((128, 18), (128, 6), (128, 2))
 
 
-def _cpu_sample_child(argv):
-    """Child process: time `steps` oracle GAN steps of one bounded sample and print one JSON line."""
-    side, t, batch, steps, k, lat, ctx, threads = (int(v) for v in argv)
-    from oracle import dgmr_oracle as O
-
+def _cpu_child(argv):
+    """Child process: time GAN steps of one bounded sample on the host cores, one JSON line per finished step (partial results
+    survive a timeout).  kind 'reference': the UNMODIFIED reference's `DGMR.training_step` (literal schedule, anomaly mode off);
+    kind 'port': the oracle port's minimal-schedule step."""
+    kind = argv[0]
+    side, t, batch, steps, k, lat, ctx, threads = (int(v) for v in argv[1:])
     torch.set_num_threads(threads)
-    cfg = dict(output_shape=side, forecast_steps=t, latent_channels=lat, context_channels=ctx)
-    gen, disc = build_oracle_state(cfg)
-    gs = O.clone_state(gen.state_dict(), requires_grad=True)
-    ds = O.clone_state(disc.state_dict(), requires_grad=True)
-    g_opt = O.AdamState([gs[n] for n in O._trainable(gs)], lr=5e-5)
-    d_opt = O.AdamState([ds[n] for n in O._trainable(ds)], lr=2e-4)
     torch.manual_seed(1234)
     x, y = torch.rand(batch, 4, 1, side, side), torch.rand(batch, t, 1, side, side)
+    cfg = dict(output_shape=side, forecast_steps=t, latent_channels=lat, context_channels=ctx)
+    if kind == "reference":
+        from baseline import reference_arm as R
+
+        model = R.build_dgmr(cfg, generation_steps=k, anomaly=False)
+        step = R.training_step_fn(model, x, y)
+    else:
+        from oracle import dgmr_oracle as O
+
+        gen, disc = build_oracle_state(cfg)
+        gs = O.clone_state(gen.state_dict(), requires_grad=True)
+        ds = O.clone_state(disc.state_dict(), requires_grad=True)
+        g_opt = O.AdamState([gs[n] for n in O._trainable(gs)], lr=5e-5)
+        d_opt = O.AdamState([ds[n] for n in O._trainable(ds)], lr=2e-4)
+        step = lambda: O.gan_step(gs, ds, g_opt, d_opt, x, y, t, (8, side // 32, side // 32), generation_steps=k)  # noqa: E731
     times = []
     for _ in range(steps):
         t0 = time.perf_counter()
-        O.gan_step(gs, ds, g_opt, d_opt, x, y, t, (8, side // 32, side // 32), generation_steps=k)
+        step()
         times.append(time.perf_counter() - t0)
-        print(json.dumps(dict(times=times)), flush=True)      # partial results survive a timeout
+        print(json.dumps(dict(times=times)), flush=True)
 
 
-def cpu_reference_steps(cfg, batch, steps, warmup, k, budget_s=150.0):
-    """The reference's own CPU implementation of the path = the oracle port (oracle/dgmr_oracle.py: torch fp32 on the host
-    cores), timed on a BOUNDED sample and scaled to the metric's unit.  A sample is the same GAN step (same widths, same
-    schedule) on smaller frames / fewer lead times; its time is scaled by the pixel-and-frame ratio to the full
-    256x256 4->18 step (the step is convolution-dominated, cost ~ pixels x frames).  Runs in a child process under a wall-clock
-    budget so that a slow host can never stall the benchmark: on timeout the next smaller sample is tried."""
-    import subprocess
+def cpu_reference_steps(cfg, batch, steps, warmup, k, budget_s=150.0, samples=CPU_SAMPLES):
+    """The reference's own CPU implementation of the path, timed on a BOUNDED sample of the workload and scaled to the metric's unit.
 
+    What runs: the unmodified reference package (baseline/_ref, installed by `__graft_entry__.build()` where /root/reference exists)
+    through its public `DGMR.training_step` -- kind "reference"; if that package is absent, the oracle port's step -- kind "port".
+    A sample is the same step (same widths, same code) on smaller frames / fewer lead times / batch 1; its time is scaled by the
+    pixel-and-frame ratio to the full-size step (convolution-dominated: cost ~ pixels x frames) and `value` = batch x frames / that.
+    Exactly `warmup` untimed + `steps` timed steps run in a child process under a wall-clock budget; if the budget would be exceeded
+    the next smaller sample is tried (a quota-limited host can be 10x slower than the build container)."""
+    from baseline import reference_arm as R
+
+    kind = "reference" if R.reference_root() else "port"
     threads = usable_cores()
     full_side, full_t = cfg["output_shape"], cfg["forecast_steps"]
     n_steps = max(1, steps + warmup)
     last_err = "no sample finished"
-    for side, t in CPU_SAMPLES:
+    for side, t in samples:
         side, t = min(side, full_side), min(t, full_t)
-        cmd = [sys.executable, os.path.abspath(__file__), "--cpu-sample-child", str(side), str(t), str(batch), str(n_steps), str(k),
+        cmd = [sys.executable, os.path.abspath(__file__), "--cpu-child", kind, str(side), str(t), str(batch), str(n_steps), str(k),
                str(cfg["latent_channels"]), str(cfg["context_channels"]), str(threads)]
         t_start = time.perf_counter()
         out = ""
         try:
-            out = subprocess.run(cmd, capture_output=True, text=True, timeout=budget_s).stdout
+            out = subprocess.run(cmd, capture_output=True, text=True, timeout=budget_s, cwd=ROOT).stdout
         except subprocess.TimeoutExpired as e:
             out = e.stdout.decode() if isinstance(e.stdout, bytes) else (e.stdout or "")
             last_err = f"sample {side}x{side} 4->{t} exceeded {budget_s:.0f} s"
         lines = [ln for ln in out.splitlines() if ln.startswith("{")]
         times = json.loads(lines[-1])["times"] if lines else []
         budget_s = max(30.0, budget_s - (time.perf_counter() - t_start))
-        if len(times) > warmup or (times and len(times) == n_steps):
+        if len(times) == n_steps:
             timed = times[warmup:] if len(times) > warmup else times
             mean = sum(timed) / len(timed)
             scale = (full_side * full_side * full_t) / float(side * side * t)
             full_step_s = mean * scale
-            return dict(value=batch * full_t / full_step_s, unit="frames/s", cores=threads, kind="port", s_per_step=full_step_s,
-                        sample=f"oracle port, full GAN step (same widths and schedule) on {side}x{side} frames, 4->{t} lead times, batch {batch}: "
-                               f"{len(timed)} timed step(s) of {mean:.2f} s, scaled x{scale:.1f} (pixels x frames) to the 256x256 4->18 step")
-    return dict(value=None, unit="frames/s", cores=threads, kind="port", s_per_step=float("nan"), sample=f"unavailable: {last_err}")
+            what = ("UNMODIFIED reference package (dgmr 1.4.4, baseline/_ref): DGMR.training_step, its literal schedule, autograd anomaly mode off"
+                    if kind == "reference" else "oracle port (oracle/dgmr_oracle.py), minimal schedule")
+            return dict(value=batch * full_t / full_step_s, unit="frames/s", cores=threads, kind=kind, s_per_step=full_step_s,
+                        steps_timed=len(timed), warmup_run=min(warmup, len(times) - len(timed)),
+                        sample=f"{what}; same widths (latent {cfg['latent_channels']} / context {cfg['context_channels']}), generation_steps={k}, "
+                               f"on {side}x{side} frames, 4->{t} lead times, batch {batch}: {len(timed)} timed step(s) of {mean:.2f} s after "
+                               f"{len(times) - len(timed)} warm-up, " + (f"scaled x{scale:.1f} (pixels x frames) to the {full_side}x{full_side} 4->{full_t} step"
+                                                                           if scale != 1.0 else "un-scaled (this IS the configuration)"))
+        elif not out:
+            last_err = last_err if "exceeded" in last_err else f"sample {side}x{side} 4->{t} produced no output"
+    return dict(value=None, unit="frames/s", cores=threads, kind=kind, s_per_step=float("nan"), steps_timed=0, warmup_run=0,
+                sample=f"unavailable: {last_err}")
 
 
-def gpu_reference_steps(cfg, batch, steps, warmup, k, dev):
-    """The reference's GPU path for the '>= 5x cuDNN-backed step' target: the same oracle port, tensors on cuda
-    (PyTorch eager, cuDNN convs with torch's default allow_tf32=True), minimal schedule like the B200 arm."""
-    from oracle import dgmr_oracle as O
+def gpu_reference_eager(cfg, batch, k, dev):
+    """The reference's own GPU path on this B200: the UNMODIFIED modules `.cuda()`, PyTorch eager + cuDNN with torch's
+    defaults (cudnn.allow_tf32 = True).  Three measurements, each 1 warm-up + 2 timed steps with CUDA events:
+      as_shipped        DGMR.training_step, autograd anomaly mode ON (the constructor switches it on globally, ref: dgmr/dgmr.py:130)
+      anomaly_off       the same literal schedule with anomaly mode off
+      minimal_schedule  the parity-preserving minimal schedule the native arm runs, on the reference's modules (apples to apples)
+    A batch that does not fit is halved and the result says so."""
+    from baseline import reference_arm as R
 
-    gen, disc = build_oracle_state(cfg)
-    gs = {k_: v.to(dev) for k_, v in O.clone_state(gen.state_dict()).items()}
-    ds = {k_: v.to(dev) for k_, v in O.clone_state(disc.state_dict()).items()}
-    for st in (gs, ds):
-        for k_, v in st.items():
-            if v.is_floating_point() and not (k_.endswith("._u") or k_.endswith("._v") or "running_" in k_):
-                v.requires_grad_(True)
-    g_opt = O.AdamState([gs[n] for n in O._trainable(gs)], lr=5e-5)
-    d_opt = O.AdamState([ds[n] for n in O._trainable(ds)], lr=2e-4)
-    s = cfg["output_shape"]
-    x = torch.rand(batch, 4, 1, s, s, device=dev)
-    y = torch.rand(batch, cfg["forecast_steps"], 1, s, s, device=dev)
-    try:
-        for _ in range(warmup):
-            O.gan_step(gs, ds, g_opt, d_opt, x, y, cfg["forecast_steps"], (8, s // 32, s // 32), generation_steps=k)
+    if R.reference_root() is None:
+        return dict(unavailable="reference package not found (baseline/_ref)")
+    s, t = cfg["output_shape"], cfg["forecast_steps"]
+    out = dict(what="unmodified reference modules on cuda:0, PyTorch eager + cuDNN (allow_tf32 default), fp32 storage", batch_requested=batch)
+
+    def measure(fn_builder, b):
+        torch.manual_seed(1234)
+        x, y = torch.rand(b, 4, 1, s, s, device=dev), torch.rand(b, t, 1, s, s, device=dev)
+        step = fn_builder(x, y)
+        step()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(steps):
-            O.gan_step(gs, ds, g_opt, d_opt, x, y, cfg["forecast_steps"], (8, s // 32, s // 32), generation_steps=k)
+        for _ in range(2):
+            step()
         e1.record()
         torch.cuda.synchronize()
-    except torch.cuda.OutOfMemoryError:
-        return dict(batch=batch, error="out of memory")
-    ms = e0.elapsed_time(e1) / steps
-    return dict(batch=batch, ms_per_step=ms, value=batch * cfg["forecast_steps"] / (ms * 1e-3), unit="frames/s",
-                what="oracle port on cuda (PyTorch eager + cuDNN, allow_tf32 default), minimal schedule")
+        ms = e0.elapsed_time(e1) / 2
+        return dict(batch=b, ms_per_step=ms, value=b * t / (ms * 1e-3), unit="frames/s")
+
+    for name, anomaly, minimal in (("anomaly_off", False, False), ("as_shipped", True, False), ("minimal_schedule", False, True)):
+        b = batch
+        while b >= 1:
+            try:
+                model = R.build_dgmr(cfg, generation_steps=k, anomaly=anomaly).to(dev)
+                builder = (lambda x, y: R.minimal_step_fn(model, x, y)) if minimal else (lambda x, y: R.training_step_fn(model, x, y))
+                out[name] = measure(builder, b)
+                break
+            except torch.cuda.OutOfMemoryError:
+                out[name] = dict(batch=b, error="out of memory")
+                b //= 2
+            finally:
+                model = None
+                torch.cuda.empty_cache()
+    torch.autograd.set_detect_anomaly(False)
+    return out
 
 
 # ----------------------------------------------------------------------------------------------------- GPU arm
@@ -223,38 +287,38 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=16, help="per-GPU batch (BASELINE configs[2]/[3]: 16)")
-    ap.add_argument("--generation-steps", type=int, default=1)
-    ap.add_argument("--size", type=int, default=256)
-    ap.add_argument("--forecast-steps", type=int, default=18)
-    ap.add_argument("--latent-channels", type=int, default=768)
-    ap.add_argument("--context-channels", type=int, default=384)
+    ap.add_argument("--config", default="c3", choices=sorted(CONFIGS), help="BASELINE.json configuration (c3 = headline; c4 = c3 under torchrun)")
+    ap.add_argument("--mode", default="native", choices=["native", "dropin"],
+                    help="native: this repo's step driver (minimal schedule); dropin: the reference's unmodified dgmr/dgmr.py wrapper "
+                         "(literal schedule, torch.optim.Adam) over this repo's modules (SURVEY.md 8d mode (i))")
+    ap.add_argument("--precision", default="tf32", choices=["tf32", "3xtf32"], help="tensor-core operand mode: fast (1xTF32) or parity (3xTF32)")
+    ap.add_argument("--batch", type=int, default=None, help="per-GPU batch (default: the configuration's)")
+    ap.add_argument("--generation-steps", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ref-gpu", action="store_true", help="skip the reference's own GPU path (reference_gpu_eager)")
     ap.add_argument("--cpu-batch", type=int, default=1)
-    ap.add_argument("--ref-gpu", type=int, default=0, metavar="BATCH",
-                    help="also time the reference's own GPU path (the oracle port on cuda: PyTorch eager + cuDNN, TF32 convs "
-                         "allowed as in torch's default) at this batch; reported as `reference_gpu_eager`")
     args = ap.parse_args()
-    cfg = dict(output_shape=args.size, forecast_steps=args.forecast_steps, latent_channels=args.latent_channels,
-               context_channels=args.context_channels)
+    c = CONFIGS[args.config]
+    args.batch = args.batch or c["batch"]
+    args.generation_steps = args.generation_steps or c["k"]
+    cfg = dict(output_shape=c["size"], forecast_steps=c["forecast_steps"], latent_channels=c["latent"], context_channels=c["context"])
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     K = args.generation_steps
-    workload = (f"DGMR full GAN step (G + spatial+temporal D, hinge + grid-cell, 2 D updates + 1 G update, Adam), 4->{args.forecast_steps} "
-                f"frames 1x{args.size}x{args.size}, latent {args.latent_channels} / context {args.context_channels}, batch {args.batch}/GPU, "
-                f"generation_steps={K}")
+    config = workload_config(args, world)
 
     if args.impl == "reference":
         if rank != 0:
             return
-        warm = min(args.warmup, 1)
-        r = cpu_reference_steps(cfg, args.cpu_batch, max(1, min(args.steps, 3)), warm, K, budget_s=240.0)
-        line = dict(impl="reference", metric="radar frames/sec (G+D step, 256x256, 4->18)", value=r["value"], unit="frames/s",
-                    n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=(r["s_per_step"] * 1e3 if r["value"] else None), higher_is_better=True,
-                    scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
-                    config=dict(workload=workload, note="CPU arm runs the oracle port on a bounded sample"),
-                    cpu_baseline=dict(value=r["value"], unit="frames/s", cores=r["cores"], kind="port", sample=r["sample"]),
+        samples = ((c["size"], c["forecast_steps"]),) if args.config == "c1" else CPU_SAMPLES
+        batch = c["batch"] if args.config == "c1" else args.cpu_batch
+        r = cpu_reference_steps(cfg, batch, args.steps, args.warmup, K, budget_s=420.0, samples=samples)
+        line = dict(impl="reference", metric=METRIC, value=r["value"], unit="frames/s", n_gpus=args.gpus,
+                    steps=r["steps_timed"], warmup=r["warmup_run"], steps_requested=args.steps, warmup_requested=args.warmup,
+                    ms_per_step=(r["s_per_step"] * 1e3 if r["value"] else None), higher_is_better=True, scaling="weak", vs_baseline=None,
+                    dtype="f32", data="synthetic", config=config,
+                    cpu_baseline=dict(value=r["value"], unit="frames/s", cores=r["cores"], kind=r["kind"], sample=r["sample"]),
                     e2e=dict(value=r["value"], unit="frames/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
         emit(line)
         return
@@ -269,16 +333,42 @@ def main():
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout to the one JSON line (NCCL prints its version banner there)
         dist.init_process_group("nccl", device_id=dev)
     be = _lib.backend()  # raises if libdgmr_b200.so is missing: no fallback
-    gen, disc = build_oracle_state(cfg, seed=0)  # identical replicas on every rank
-    gen.to(dev).train()
-    disc.to(dev).train()
-    g_opt = Adam(gen.parameters(), lr=5e-5, betas=(0.0, 0.999))
-    d_opt = Adam(disc.parameters(), lr=2e-4, betas=(0.0, 0.999))
-    B, T, S = args.batch, args.forecast_steps, args.size
+    ops.config.precision = 1 if args.precision == "3xtf32" else 0
+    B, T, S = args.batch, c["forecast_steps"], c["size"]
+    inference = c["kind"] == "inference"
     torch.manual_seed(1234 + rank)
     host_x = torch.rand(B, 4, 1, S, S).pin_memory()
     host_y = torch.rand(B, T, 1, S, S).pin_memory()
     x, y = host_x.to(dev), host_y.to(dev)
+
+    if args.mode == "dropin":
+        from baseline import reference_arm as R
+
+        model = R.build_dgmr(cfg, generation_steps=K, dropin=True, anomaly=False, seed=0).to(dev)   # reference wrapper, our modules
+        gen, disc = model.generator, model.discriminator
+
+        def run_step(xi, yi):
+            model.training_step((xi, yi), 0)
+            lg = model.logged
+            return {"d_loss": lg["train/d_loss"], "g_loss": lg["train/g_loss"], "grid_loss": lg["train/grid_loss"]}
+    else:
+        gen, disc = build_oracle_state(cfg, seed=0)  # identical replicas on every rank
+        gen.to(dev)
+        disc.to(dev)
+        if inference:
+            gen.eval()
+
+            def run_step(xi, yi):
+                with torch.no_grad():
+                    return {"out": gen(xi)}
+        else:
+            gen.train()
+            disc.train()
+            g_opt = Adam(gen.parameters(), lr=5e-5, betas=(0.0, 0.999))
+            d_opt = Adam(disc.parameters(), lr=2e-4, betas=(0.0, 0.999))
+
+            def run_step(xi, yi):
+                return gan_step(gen, disc, g_opt, d_opt, xi, yi, generation_steps=K)
 
     def barrier():
         if world > 1:
@@ -286,12 +376,14 @@ def main():
         torch.cuda.synchronize()
 
     def step_resident():
-        return gan_step(gen, disc, g_opt, d_opt, x, y, generation_steps=K)
+        return run_step(x, y)
 
     def step_e2e():
         xi = host_x.to(dev, non_blocking=True)
         yi = host_y.to(dev, non_blocking=True)
-        out = gan_step(gen, disc, g_opt, d_opt, xi, yi, generation_steps=K)
+        out = run_step(xi, yi)
+        if inference:
+            return out["out"].to("cpu", non_blocking=False)   # device->host read of the forecast itself
         return torch.stack([out["d_loss"], out["g_loss"], out["grid_loss"]]).cpu()  # device->host read of the step's result
 
     def timed(fn, steps):
@@ -309,7 +401,8 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item()), be.launches - l0
 
-    for _ in range(max(args.warmup, 3)):
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
         step_resident()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -319,23 +412,18 @@ def main():
     step_e2e()
     ms_e2e, _ = timed(step_e2e, args.steps)
 
-    # ---- dominant-kernel roofline: one extra instrumented step, CUDA events around every conv launch
+    # ---- roofline: one extra instrumented step, CUDA events (on the launch stream) around every C-ABI launch
     be.profile = []
     step_resident()
     torch.cuda.synchronize()
     prof, be.profile = be.profile, None
-    agg = {}
-    shapes = {}
+    agg, shapes = {}, {}
     for name, flops, ev0, ev1, tag, info in prof:
         ms_ = ev0.elapsed_time(ev1)
         a = agg.setdefault(tag, [0.0, 0.0, 0])
-        a[0] += flops
-        a[1] += ms_
-        a[2] += 1
+        a[0] += flops; a[1] += ms_; a[2] += 1
         b_ = shapes.setdefault((tag, info), [0.0, 0.0, 0])
-        b_[0] += flops
-        b_[1] += ms_
-        b_[2] += 1
+        b_[0] += flops; b_[1] += ms_; b_[2] += 1
     dump = os.environ.get("DGMR_BENCH_DUMP")
     if dump and rank == 0:
         with open(dump, "w") as f:
@@ -352,42 +440,65 @@ def main():
     value = frames / (ms_per_step * 1e-3)
     e2e_value = frames / (ms_e2e / args.steps * 1e-3)
     tf32_peak = pk["bf16_sustained"] / 2.0
-    dom = agg.get("conv_umma", [0.0, 0.0, 0])
-    achieved = dom[0] / (dom[1] * 1e-3) / 1e12 if dom[1] > 0 else 0.0
+    TC_TAGS = ("conv_umma", "conv_umma_splitk", "wgrad_umma")
+    tc = [sum(agg.get(t, [0.0, 0.0, 0])[i] for t in TC_TAGS) for i in range(3)]
+    instr_ms = sum(v[1] for v in agg.values())
+    # the dominant launch = the (kernel family, shape) with the largest summed duration among the tensor-core launches
+    top = max(((k_, v) for k_, v in shapes.items() if k_[0] in TC_TAGS), key=lambda kv: kv[1][1], default=(("none", ""), [0.0, 0.0, 1]))
+    (top_tag, top_info), (top_fl, top_ms, top_n) = top
+    top_ach = top_fl / (top_ms * 1e-3) / 1e12 if top_ms > 0 else 0.0
+    agg_ach = tc[0] / (tc[1] * 1e-3) / 1e12 if tc[1] > 0 else 0.0
+    if inference:
+        h2d, d2h = int(host_x.numel()) * 4, int(B * T * S * S) * 4
+        step_flops = world * B * F_G
+    else:
+        h2d, d2h = int(host_x.numel() + host_y.numel()) * 4, 12
+        step_flops = flop_step(world * B, K)
     line = dict(
-        metric="radar frames/sec (G+D step, 256x256, 4->18)", value=value, unit="frames/s", n_gpus=world, steps=args.steps,
-        warmup=max(args.warmup, 3), ms_per_step=ms_per_step, higher_is_better=True, scaling="weak", vs_baseline=None,
-        dtype="tf32 (fp32 storage, tcgen05 kind::tf32 operands, fp32 accumulate)", data="synthetic",
-        config=dict(workload=workload, global_batch=world * B, parallelism=f"dp{world}",
+        metric=METRIC if not inference else "generated radar frames/sec (generator-only eval inference, 256x256, 4->18)",
+        value=value, unit="frames/s", n_gpus=world, steps=args.steps, warmup=warm, ms_per_step=ms_per_step, higher_is_better=True,
+        scaling="weak", vs_baseline=None,
+        dtype=("tf32 (fp32 storage, tcgen05 kind::tf32 operands, fp32 accumulate)" if args.precision == "tf32" else
+               "3xtf32 (fp32 storage, error-compensated tf32 operand pairs on tcgen05, fp32 accumulate)"), data="synthetic",
+        config=dict(config, mode=args.mode, precision=args.precision,
                     l2="inputs+activations per step (>10 GB) exceed the 126 MB L2; no explicit flush needed",
-                    schedule="parity-preserving minimal schedule (SURVEY.md 8d)"),
-        e2e=dict(value=e2e_value, unit="frames/s", h2d_bytes_per_step=int(host_x.numel() + host_y.numel()) * 4, d2h_bytes_per_step=12),
+                    schedule=("reference wrapper's literal schedule (checkpoint recompute, trailing forward), torch.optim.Adam" if args.mode == "dropin"
+                              else "generator forward only, eval mode" if inference else "parity-preserving minimal schedule (SURVEY.md 8d)")),
+        e2e=dict(value=e2e_value, unit="frames/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h),
         gpu_launches=launches // args.steps,
         clocks=clocks,
-        step_tflops=flop_step(world * B, K) / (ms_per_step * 1e-3) / 1e12,
-        roofline=dict(bound="tensor", kernel="conv_umma_patch_kernel + conv_umma_fwd[_persist]_kernel (implicit-GEMM conv fwd + dgrad, tcgen05 kind::tf32)",
-                      achieved=achieved, peak=tf32_peak, unit="TFLOP/s", frac=achieved / tf32_peak if tf32_peak else None, traffic=None,
+        step_tflops=step_flops / (ms_per_step * 1e-3) / 1e12,
+        roofline=dict(bound="tensor", kernel=f"{top_tag} {top_info} (tcgen05 kind::tf32 implicit GEMM; the tensor-core launch with the largest share of the step)",
+                      achieved=top_ach, peak=tf32_peak, unit="TFLOP/s", frac=top_ach / tf32_peak if tf32_peak else None, traffic=None,
+                      launches_per_step=top_n, ms_per_launch=top_ms / max(top_n, 1), share_of_step=top_ms / instr_ms if instr_ms else None,
                       peak_source=f"{pk['source']} bf16 sustained {pk['bf16_sustained']} TF/s / 2 (TF32 pipe = half the bf16 rate)",
-                      launches=dom[2], kernel_ms_per_step=dom[1],
-                      note="achieved = executed conv FLOPs (2*M*Cout*Cin*taps) of the tcgen05 launches in one instrumented step / their "
-                           "summed CUDA-event durations; traffic is null because the figure aggregates launches of many shapes",
-                      traffic_profiled=dict(launch="conv_umma_patch_kernel<32,2,pair> 288x128x128 96->96 (+bias, scale, residual)",
-                                            dram_bytes=5.66e9, algorithmic_bytes=5.44e9, tensor_pipe_active_pct=40.5,
-                                            source="profiles/conv_umma_patch_pair_96x96_128_r01b_ncu.txt (ncu --set full)")),
-        kernel_breakdown_ms={k: round(v[1], 3) for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])},
+                      note="achieved = executed FLOPs of one launch (2*pixels*Cin*Cout*taps) / its mean CUDA-event duration inside the instrumented step; "
+                           "traffic (ncu dram bytes per launch) is recorded in profiles/ for the launches that were captured",
+                      aggregate=dict(what="all tensor-core launches of the step: conv fwd + dgrad, tap-split, wgrad", achieved=agg_ach,
+                                     frac=agg_ach / tf32_peak if tf32_peak else None, launches=tc[2], kernel_ms_per_step=tc[1],
+                                     share_of_step=tc[1] / instr_ms if instr_ms else None)),
+        kernel_breakdown_ms={k_: round(v[1], 3) for k_, v in sorted(agg.items(), key=lambda kv: -kv[1][1])},
     )
-    if args.ref_gpu:
-        line["reference_gpu_eager"] = gpu_reference_steps(cfg, args.ref_gpu, 2, 1, K, dev)
-    if not args.no_cpu_baseline:
+    # free the benchmark's own state before the reference's eager path needs the memory
+    del prof
+    if not args.no_ref_gpu and world == 1 and not inference and args.mode == "native":
+        gen = disc = g_opt = d_opt = None
+        ops.clear_pack_cache()
+        torch.cuda.empty_cache()
+        try:
+            line["reference_gpu_eager"] = gpu_reference_eager(cfg, B, K, dev)
+        except Exception as e:  # noqa: BLE001  (the headline number must survive a failure of the comparison arm)
+            line["reference_gpu_eager"] = dict(error=f"{type(e).__name__}: {e}"[:400])
+    if not args.no_cpu_baseline and world == 1:
         r = cpu_reference_steps(cfg, args.cpu_batch, 1, 0, K, budget_s=90.0)
-        line["cpu_baseline"] = dict(value=r["value"], unit="frames/s", cores=r["cores"], kind="port", sample=r["sample"])
+        line["cpu_baseline"] = dict(value=r["value"], unit="frames/s", cores=r["cores"], kind=r["kind"], sample=r["sample"])
     emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "--cpu-sample-child":
-        _cpu_sample_child(sys.argv[2:])
+    if len(sys.argv) > 1 and sys.argv[1] == "--cpu-child":
+        _cpu_child(sys.argv[2:])
     else:
         main()
