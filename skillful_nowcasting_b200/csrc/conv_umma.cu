@@ -1582,6 +1582,12 @@ int launch_conv_umma_wgrad(const float* x, const float* dz, float* dwp, int N, i
   int64_t ksplit = ((int64_t)sm_count() * 3) / base_ctas;   // floor: never spill a few CTAs into an extra wave
   if (ksplit > p.kb_total / 4) ksplit = p.kb_total / 4;
   if (ksplit < 1) ksplit = 1;
+  // Parity mode: tcgen05 keeps the accumulator in fp32 but TRUNCATES the sum after every MMA (measured: tests/test_fullsize_gpu.py::
+  // test_tensor_core_accumulation), a bias of ~-0.5 ulp per MMA that grows with the chain -- 1e-4 relative after the ~2000-MMA chains of a
+  // two-wave split, more than 3xTF32 is meant to leave.  Short chains (16 K blocks = 192 MMAs) flushed with round-to-nearest fp32 red.adds
+  // keep it below 1e-5; the extra CTAs cost time, which parity mode does not optimise for.
+  if (x3 && ksplit < ceil_div(p.kb_total, 16)) ksplit = ceil_div(p.kb_total, 16);
+  if (ksplit > 65535) ksplit = 65535;
   p.kb_chunk = (int)ceil_div(p.kb_total, ksplit);
   ksplit = ceil_div(p.kb_total, p.kb_chunk);
   p.dwp = dwp;

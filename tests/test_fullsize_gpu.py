@@ -9,9 +9,14 @@ run in seconds.  Two arms per shape, both through the C ABI with AUTO dispatch -
   (2) the adjoint identities of a linear map,  <conv(x,w), dy> == <x, dgrad(dy,w)> == <w, wgrad(x,dy)>,  which tie the three kernels
       to each other without any reference.
 
-Tolerances are DERIVED from the measured accumulation behaviour of tcgen05 kind::tf32 (test_tensor_core_accumulation below and
-profiles/accum_probe_r02.txt): the tensor core keeps the running sum in fp32 but ALIGNS-AND-TRUNCATES addends (no round-to-nearest), so a
-K-term sum loses up to ~1 ulp per MMA, always towards -infinity in magnitude... see DESIGN.md section 5 for the numbers.
+Tolerances are DERIVED from the measured accumulation behaviour of tcgen05 kind::tf32 (test_tensor_core_accumulation below,
+profiles/accum_probe_r02.txt): inside one MMA chain every addend down to 2^-23 of the running sum survives (the accumulator is a
+genuine fp32), but the sum is TRUNCATED -- not rounded -- to fp32 after each MMA: a bias of about -0.5 ulp (3e-8 relative) per MMA in the
+chain, towards zero.  A forward / dgrad output accumulates K/8 MMAs (K = Cin*taps), so its relative error against an exactly rounded
+fp32 sum is ~ (K/8) * 2^-25: 3e-6 at K = 864 and 2.6e-5 at K = 6912 -- what round 2 measured (2.6e-6 and 1.96e-5).  A wgrad element
+accumulates (pixels / 8 / split-K CTAs) MMAs per CTA, ~2000 with the two-wave split of the big layers: -1.0e-4 .. -2.2e-4 relative,
+coherent -- that, not a dropped tap, is the 1.03e-4 adjoint mismatch round 1 left open (<w,dw> is low by exactly that bias while
+<y,dy> and <x,dx> agree to 4e-8).  Parity mode (3xTF32) issues three MMAs per k-step and caps wgrad chains at 192 MMAs.
 """
 import math
 
@@ -33,9 +38,28 @@ FULL_SHAPES = [
 ]
 IDS = ["patchpair_96x96_128", "plain_96x48_128", "conv3d_48x48", "first_d_8x48", "conv1x1_48x96", "wide_768_16", "gru_l1"]
 
-# max |y - ref| / max |ref| for one conv with TF32-exact operands: accumulation only (see module docstring)
-TOL_FP32 = 2e-5
-TOL_ADJ = 2e-4
+ULP_BIAS = 2.0 ** -25   # mean truncation loss per MMA, relative to the running sum
+
+
+def tol_chain(mmas: float, floor: float = 1e-5) -> float:
+    """max |y - ref| / max |ref| allowed for an accumulation chain of `mmas` truncating MMAs: 3x the mean bias (elements whose running sum
+    stayed near its final magnitude for the whole chain lose the full 1 ulp per MMA, and max|err|/max|ref| picks the worst), plus the
+    fp32 noise of the checker itself."""
+    return max(floor, 3.0 * mmas * ULP_BIAS)
+
+
+def wgrad_chain(n, d, h, w, cin, cout, kd, k, x3=False):
+    """MMAs in one CTA's wgrad accumulation chain (mirrors the split-K rules of launch_conv_umma_wgrad[_row]; 148 SMs)."""
+    pixels = n * d * h * w
+    if x3:
+        return 3 * 16 * 4
+    if k == 3 and w % 32 == 0 and pixels >= 16384:            # row kernel: two waves of CTAs
+        base = kd * 3 * -(-cout // 128) * -(-cin // 160)
+        ksplit = max(1, min((148 * 2) // base, pixels // 32 // 8))
+    else:                                                     # tap-wise kernel: three waves
+        base = kd * k * k * -(-cout // 128) * -(-cin // 256)
+        ksplit = max(1, min((148 * 3) // base, pixels // 32 // 4))
+    return pixels / 8.0 / ksplit
 
 
 def _dot(a, b):
@@ -107,17 +131,20 @@ def test_full_size_layer_against_fp32_torch_and_adjoints(cuda_backend, true_fp32
     e_ab, e_ac = abs(a - b) / a, abs(a - c) / a
     print(f"\nFULLSIZE {shape}: fwd {e_fwd:.2e} dgrad {e_dx:.2e} wgrad {e_dw:.2e} | <y,dy> {a:.9e} <x,dx> {b:.9e} <w,dw> {c:.9e} "
           f"adj {e_ab:.2e} {e_ac:.2e}")
-    assert e_fwd < TOL_FP32, f"forward vs fp32 torch: {e_fwd:.3e}"
-    assert e_dx < TOL_FP32, f"dgrad vs fp32 torch: {e_dx:.3e}"
-    # wgrad sums N*D*H*W (up to 4.7 M) products per element: fp32 accumulation noise grows with sqrt(K)
-    assert e_dw < TOL_FP32 * max(1.0, math.sqrt(n * d * h * w / 65536.0)), f"wgrad vs fp32 torch: {e_dw:.3e}"
-    assert a > 0 and e_ab < TOL_ADJ and e_ac < TOL_ADJ, f"adjoint identities: {e_ab:.3e} {e_ac:.3e}"
+    t_f, t_d, t_w = tol_chain(cin * taps / 8), tol_chain(cout * taps / 8), tol_chain(wgrad_chain(*shape))
+    print(f"   bounds: fwd {t_f:.1e} dgrad {t_d:.1e} wgrad {t_w:.1e}")
+    assert e_fwd < t_f, f"forward vs fp32 torch: {e_fwd:.3e} (bound {t_f:.1e})"
+    assert e_dx < t_d, f"dgrad vs fp32 torch: {e_dx:.3e} (bound {t_d:.1e})"
+    assert e_dw < t_w, f"wgrad vs fp32 torch: {e_dw:.3e} (bound {t_w:.1e})"
+    # <y,dy> and <x,dx> carry the (tiny) forward / dgrad bias, <w,dw> the wgrad chain bias
+    assert a > 0 and e_ab < t_f + t_d and e_ac < t_f + t_w, f"adjoint identities: {e_ab:.3e} {e_ac:.3e}"
 
 
 @pytest.mark.parametrize("shape", [FULL_SHAPES[0], FULL_SHAPES[2], FULL_SHAPES[5]], ids=[IDS[0], IDS[2], IDS[5]])
 def test_full_size_layer_3xtf32_matches_fp32_on_unrounded_operands(cuda_backend, true_fp32, shape):
     """Parity mode (DGMR_PREC_3XTF32): arbitrary fp32 operands split into (hi, lo) pairs; forward, dgrad and wgrad must agree with
-    torch's fp32 convolution to fp32-accumulation level, i.e. ~100x tighter than the 1xTF32 operand rounding (2^-11)."""
+    torch's fp32 convolution to the accumulation bound (three truncating MMAs per k-step) -- 10-100x tighter than the 2^-11 operand
+    rounding of 1xTF32.  Round 2 measured fwd 7e-6 / 1.1e-5 / 5.1e-5 at K = 864 / 1296 / 6912."""
     be = cuda_backend
     n, d, h, w, cin, cout, kd, k = shape
     taps = kd * k * k
@@ -156,9 +183,10 @@ def test_full_size_layer_3xtf32_matches_fp32_on_unrounded_operands(cuda_backend,
     gwp = torch.empty_like(dwp)
     be.pack_weight(gw.contiguous(), gwp, cout, cin, 0, cin, taps, 0)
     e_dw = float((dwp - gwp).abs().max() / gwp.abs().max())
-    print(f"\nFULLSIZE-3X {shape}: fwd {e_fwd:.2e} dgrad {e_dx:.2e} wgrad {e_dw:.2e}")
-    assert e_fwd < TOL_FP32 and e_dx < TOL_FP32, (e_fwd, e_dx)
-    assert e_dw < TOL_FP32 * max(1.0, math.sqrt(n * d * h * w / 65536.0)), e_dw
+    t_f, t_d, t_w = tol_chain(3 * cin * taps / 8), tol_chain(3 * cout * taps / 8), tol_chain(wgrad_chain(*shape, x3=True), floor=3e-5)
+    print(f"\nFULLSIZE-3X {shape}: fwd {e_fwd:.2e} dgrad {e_dx:.2e} wgrad {e_dw:.2e}   bounds {t_f:.1e} {t_d:.1e} {t_w:.1e}")
+    assert e_fwd < t_f and e_dx < t_d, (e_fwd, e_dx)
+    assert e_dw < t_w, e_dw
 
 
 def test_tensor_core_accumulation(cuda_backend):

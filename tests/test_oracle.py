@@ -105,3 +105,40 @@ def test_seeded_construction_equals_reference_bitwise(c1):
         assert list(ref_sd.keys()) == list(mine.keys())
         for k in ref_sd:
             assert torch.equal(ref_sd[k], mine[k]), k
+
+
+def test_tf32_operand_rounding_alone_moves_spatial_scores():
+    """Documents the conditioning of the discriminator scores ('D scores exceed the stated tolerance').  Rounding the
+    convolution operands of the fp32 CPU ORACLE to TF32 (round-to-nearest, fp32 accumulate -- what cuDNN does by default for the
+    reference's convolutions and what the 1xTF32 tcgen05 kernels do) moves the eval-mode SPATIAL score by ~1e-2 relative: the score is
+    a cancelling sum (8 frames x 768 normalised features, result 4e-3).  The temporal score moves by < 1e-3.  No GPU involved."""
+    import torch.nn.functional as F
+
+    import skillful_nowcasting_b200 as B
+    from oracle import dgmr_oracle as O
+
+    def rna(x):
+        i = x.contiguous().view(torch.int32)
+        return ((i + 0x1000) & ~0x1fff).view(torch.float32).view_as(x)
+
+    res = {}
+    orig2, orig3 = F.conv2d, F.conv3d
+    for which in ("spatial", "temporal"):
+        torch.manual_seed(3)
+        mod = B.SpatialDiscriminator(input_channels=1) if which == "spatial" else B.TemporalDiscriminator(input_channels=1)
+        pfx = which + "_discriminator"
+        st = O.clone_state({pfx + "." + k: v for k, v in mod.state_dict().items()})
+        x = torch.rand(4, 8, 1, 128, 128)
+        fn = O.spatial_discriminator if which == "spatial" else O.temporal_discriminator
+        torch.manual_seed(4)
+        ref = fn(st, pfx, x, False)
+        try:
+            F.conv2d = lambda a, w, b=None, *r, **k: orig2(rna(a), rna(w), b, *r, **k)
+            F.conv3d = lambda a, w, b=None, *r, **k: orig3(rna(a), rna(w), b, *r, **k)
+            torch.manual_seed(4)
+            got = fn(st, pfx, x, False)
+        finally:
+            F.conv2d, F.conv3d = orig2, orig3
+        res[which] = float((got - ref).abs().max() / ref.abs().max())
+    assert 3e-3 < res["spatial"] < 4e-2, res       # measured 1.27e-2: inherent to 2^-11 operands, not to the kernels
+    assert res["temporal"] < 1e-3, res             # measured 4.9e-4

