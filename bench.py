@@ -294,6 +294,7 @@ def main():
     ap.add_argument("--precision", default="tf32", choices=["tf32", "3xtf32"], help="tensor-core operand mode: fast (1xTF32) or parity (3xTF32)")
     ap.add_argument("--batch", type=int, default=None, help="per-GPU batch (default: the configuration's)")
     ap.add_argument("--generation-steps", type=int, default=None)
+    ap.add_argument("--cuda-graph", action="store_true", help="c2 only: replay the eval forward from a CUDA graph (skillful_nowcasting_b200.inference)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-gpu", action="store_true", help="skip the reference's own GPU path (reference_gpu_eager)")
     ap.add_argument("--cpu-batch", type=int, default=1)
@@ -357,10 +358,17 @@ def main():
         disc.to(dev)
         if inference:
             gen.eval()
+            if args.cuda_graph:
+                from skillful_nowcasting_b200.inference import GraphedGenerator
 
-            def run_step(xi, yi):
-                with torch.no_grad():
-                    return {"out": gen(xi)}
+                runner = GraphedGenerator(gen, x)
+
+                def run_step(xi, yi):
+                    return {"out": runner(xi)}
+            else:
+                def run_step(xi, yi):
+                    with torch.no_grad():
+                        return {"out": gen(xi)}
         else:
             gen.train()
             disc.train()
@@ -460,7 +468,7 @@ def main():
         scaling="weak", vs_baseline=None,
         dtype=("tf32 (fp32 storage, tcgen05 kind::tf32 operands, fp32 accumulate)" if args.precision == "tf32" else
                "3xtf32 (fp32 storage, error-compensated tf32 operand pairs on tcgen05, fp32 accumulate)"), data="synthetic",
-        config=dict(config, mode=args.mode, precision=args.precision,
+        config=dict(config, mode=args.mode + ("+cuda-graph" if args.cuda_graph else ""), precision=args.precision,
                     l2="inputs+activations per step (>10 GB) exceed the 126 MB L2; no explicit flush needed",
                     schedule=("reference wrapper's literal schedule (checkpoint recompute, trailing forward), torch.optim.Adam" if args.mode == "dropin"
                               else "generator forward only, eval mode" if inference else "parity-preserving minimal schedule (SURVEY.md 8d)")),

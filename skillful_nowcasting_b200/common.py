@@ -31,6 +31,17 @@ def _kernel(conv_type: str, k: int):
     raise ValueError(f"{conv_type} is not a recognized Conv method")
 
 
+def _conv_bn_relu_eval(conv: SNConv, bn: BatchNorm, x, G: int):
+    """Eval mode: relu(bn(conv(x))) as ONE convolution launch.  With running statistics BatchNorm is a per-channel affine map
+    y = a*z + b (a = gamma / sqrt(running_var + eps), b = beta - a * running_mean), so it folds into the conv epilogue's per-group scale
+    and bias -- scale'[g, co] = a[co] / sigma_g, bias'[co] = a[co] * bias[co] + b[co] -- followed by the fused ReLU: no BatchNorm pass over
+    the activation at all.  The [G, C]-sized folding arithmetic is plain differentiable tensor algebra on parameters."""
+    a = bn.weight * torch.rsqrt(bn.running_var + bn.eps)
+    b = bn.bias - a * bn.running_mean
+    scale = conv.inv_sigma(G).view(G, 1) * a.view(1, -1)
+    return ops.conv(x, conv.weight_orig, conv.bias * a + b, scale.contiguous(), None, 0, conv.in_channels, G, ACT_RELU)
+
+
 class GBlock(nn.Module):
     """Residual generator block without upsampling (ref: dgmr/common.py:17-84)."""
 
@@ -53,8 +64,11 @@ class GBlock(nn.Module):
     def run(self, x, G: int = 1):
         sc = x if x.shape[-1] == self.output_channels else self.conv_1x1.run(x, G)
         y = ops.mark_conv_only(self.bn1.run(x, G, relu=True, conv_only=True))
-        y = self.first_conv_3x3.run(y, G)
-        y = ops.mark_conv_only(self.bn2.run(y, G, relu=True, conv_only=True))
+        if self.training:
+            y = self.first_conv_3x3.run(y, G)
+            y = ops.mark_conv_only(self.bn2.run(y, G, relu=True, conv_only=True))
+        else:
+            y = ops.mark_conv_only(_conv_bn_relu_eval(self.first_conv_3x3, self.bn2, y, G))
         return self.last_conv_3x3.run(y, G, res=sc)  # residual add fused in the conv epilogue
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
@@ -82,8 +96,11 @@ class UpsampleGBlock(nn.Module):
         # conv1x1(up2(x)) == up2(conv1x1(x)) bit-for-bit (pointwise conv commutes with replication): 4x fewer MACs
         sc = ops.upsample2(self.conv_1x1.run(x, G))  # x also feeds BatchNorm: the conv rounds a private copy
         y = ops.mark_conv_only(self.bn1.run(x, G, relu=True, up2=True, conv_only=True))  # BN -> ReLU -> nearest x2 in one pass
-        y = self.first_conv_3x3.run(y, G)
-        y = ops.mark_conv_only(self.bn2.run(y, G, relu=True, conv_only=True))
+        if self.training:
+            y = self.first_conv_3x3.run(y, G)
+            y = ops.mark_conv_only(self.bn2.run(y, G, relu=True, conv_only=True))
+        else:
+            y = ops.mark_conv_only(_conv_bn_relu_eval(self.first_conv_3x3, self.bn2, y, G))
         return self.last_conv_3x3.run(y, G, res=sc)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
