@@ -43,6 +43,13 @@ enum { DGMR_FLAG_ROUND_TF32 = 256 };
  * caller, e.g. with the residual).  The tensor-core path then splits the K loop over filter taps across CTAs (fp32 red.add
  * into y), which is what fills the SMs for the small-M, large-K convolutions of the ConvGRU steps. */
 enum { DGMR_FLAG_ACCUMULATE = 512 };
+/* OR-able into dgmr_conv_fwd's `act`: y is written TF32-rounded (round-to-nearest) -- for outputs that feed tensor-core convolutions
+ * only, instead of a separate dgmr_round_tf32 pass over them. */
+enum { DGMR_FLAG_ROUND_OUT = 1024 };
+/* OR-able into dgmr_conv_fwd's `act`: `res` is a HALF-resolution tensor [N, D, H/2, W/2, Cout] and is added nearest-upsampled, i.e. read
+ * at (h/2, w/2): the shortcut of UpsampleGBlock, conv1x1(up2(x)) = up2(conv1x1(x)) (ref: dgmr/common.py:141-143), without ever
+ * materialising the upsampled tensor.  H and W must be even. */
+enum { DGMR_FLAG_RES_UP2 = 2048 };
 /* conv algorithm selector */
 enum { DGMR_ALGO_AUTO = 0, DGMR_ALGO_SIMT = 1, DGMR_ALGO_UMMA = 2 /* plain tcgen05 kernel */, DGMR_ALGO_UMMA_PATCH = 3 /* halo-patch tcgen05 kernel */ };
 /* tensor-core operand precision: 1xTF32 (what cuDNN does by default for the reference) or
@@ -168,6 +175,16 @@ int dgmr_sn_bwd(const float* d_inv_sigma, const float* inv_sigma, const float* u
  * mode 0: forward pack  packed[tap][co][ci];  mode 1: dgrad pack  packed[taps-1-tap][ci][co]. */
 int dgmr_pack_weight(const float* w, float* packed, int Cout, int CinTot, int ci0, int Cin, int taps, int mode,
                      dgmr_stream_t stream);
+/* Many packs in ONE launch (all the weights of a network right after its optimiser step).  `items` is a HOST array.  Compared with
+ * dgmr_pack_weight the destination may be wider than the slice: CinPad >= Cin input channels per row (the pad is not written: the
+ * caller zeroes the buffer once) and rows [co0, co0 + Cout) of CoutTot (several weights side by side along Cout: the read|update gate
+ * convolution of a ConvGRU, ref: dgmr/layers/ConvGRU.py:72-75).  mode as in dgmr_pack_weight (| DGMR_FLAG_ROUND_TF32). */
+typedef struct {
+  const float* w; float* packed;
+  int Cout, CinTot, ci0, Cin, taps, mode;
+  int CinPad, co0, CoutTot;
+} dgmr_pack_item;
+int dgmr_pack_weight_multi(const dgmr_pack_item* items, int n, dgmr_stream_t stream);
 /* inverse of mode 0 for gradients: gw[co][ci0+ci][tap] (+)= packed[tap][co][ci] */
 int dgmr_unpack_wgrad(const float* packed, float* gw, int Cout, int CinTot, int ci0, int Cin, int taps,
                       int accumulate, dgmr_stream_t stream);
@@ -181,10 +198,11 @@ int dgmr_conv_fwd(const float* x, const float* x_lo, const float* wp, const floa
                   int kd, int kh, int kw, int G, int act, int algo, int precision, dgmr_stream_t stream);
 /* backward prologue: dpre = dy*act'(y); dz = dpre*scale; dbias[co] (+)= sum dpre;
  * dscale[g][co] = sum dpre*(y - bias - res)/scale  (the <dY, Y-b> identity of SURVEY.md 8a/a13).
- * rows = pixels per group.  Any of dbias/dscale may be NULL. */
+ * rows = pixels per group.  Any of dbias/dscale may be NULL.  up_h, up_w > 0: the forward ran with DGMR_FLAG_RES_UP2 on up_h x up_w
+ * images, i.e. `res` is the half-resolution tensor and is read at (h/2, w/2); 0, 0 otherwise. */
 int dgmr_conv_bwd_prep(const float* dy, const float* y, const float* res, const float* bias, const float* scale,
                        float* dz, float* dpre /*optional: unscaled dpre, = grad of res*/, float* dbias, float* dscale,
-                       int64_t rows, int G, int Cout, int act, int accumulate_dbias, dgmr_stream_t stream);
+                       int64_t rows, int G, int Cout, int act, int accumulate_dbias, int up_h, int up_w, dgmr_stream_t stream);
 /* dwp[tap][co][ci] = sum_pixels dz[p][co] * x[p+tap][ci]   (dwp fully overwritten).  Both operands are read straight from the
  * channels-last tensors (MN-major tensor-core tiles).  x_lo/dz_lo: lo parts for DGMR_PREC_3XTF32 (as in dgmr_conv_fwd), else NULL. */
 int dgmr_conv_wgrad(const float* x, const float* x_lo, const float* dz, const float* dz_lo, float* dwp, int N, int D, int H, int W,

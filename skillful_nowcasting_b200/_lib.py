@@ -25,6 +25,8 @@ ALGO_AUTO, ALGO_SIMT, ALGO_UMMA, ALGO_UMMA_PATCH = 0, 1, 2, 3
 PREC_TF32, PREC_3XTF32 = 0, 1
 FLAG_ROUND_TF32 = 256
 FLAG_ACCUMULATE = 512
+FLAG_ROUND_OUT = 1024
+FLAG_RES_UP2 = 2048
 
 _CTYPES = {
     "int": ctypes.c_int,
@@ -266,16 +268,18 @@ class CudaBackend:
         if self.profile is not None:
             umma = algo == ALGO_UMMA or (algo == ALGO_AUTO and self.conv_umma_supported(N, D, H, W, Cin, Cout, kd, kh, kw))
             tag = ("conv_umma_splitk" if act & FLAG_ACCUMULATE else "conv_umma") if umma else "conv_simt"
+        if x_lo is not None:
+            tag = "conv_umma_3x"
         self._call("dgmr_conv_fwd", _f32(x, "x"), _f32(x_lo, "x_lo"), _f32(wp, "wp"), _f32(wp_lo, "wp_lo"), _f32(bias, "bias"),
                    _f32(scale, "scale"), _f32(res, "res"), _f32(y, "y"), N, D, H, W, Cin, Cout, kd, kh, kw, G, act, algo, precision,
                    _tag=tag, _flops=2.0 * N * D * H * W * Cin * Cout * kd * kh * kw,
                    _info=f"{N}x{D}x{H}x{W} {Cin}->{Cout} k{kd}{kh}{kw} G{G}")
 
-    def conv_bwd_prep(self, dy, y, res, bias, scale, dz, dpre, dbias, dscale, rows, G, Cout, act, accumulate_dbias=False):
+    def conv_bwd_prep(self, dy, y, res, bias, scale, dz, dpre, dbias, dscale, rows, G, Cout, act, accumulate_dbias=False, up_hw=(0, 0)):
         nb = sum(t is not None for t in (dy, y, res, dz, dpre)) * 4.0 * rows * G * Cout   # bytes moved (profile only)
         self._call("dgmr_conv_bwd_prep", _f32(dy, "dy"), _f32(y, "y"), _f32(res, "res"), _f32(bias, "bias"), _f32(scale, "scale"),
                    _f32(dz, "dz"), _f32(dpre, "dpre"), _f32(dbias, "dbias"), _f32(dscale, "dscale"), rows, G, Cout, act,
-                   int(accumulate_dbias), _flops=nb, _info=f"rows{rows} G{G} C{Cout} (GB/s)")
+                   int(accumulate_dbias), int(up_hw[0]), int(up_hw[1]), _flops=nb, _info=f"rows{rows} G{G} C{Cout} (GB/s)")
 
     def conv_wgrad(self, x, dz, dwp, N, D, H, W, Cin, Cout, kd, kh, kw, algo=ALGO_AUTO, precision=PREC_TF32, x_lo=None, dz_lo=None):
         tag = None

@@ -93,15 +93,16 @@ class UpsampleGBlock(nn.Module):
         return [(self.conv_1x1, G), (self.first_conv_3x3, G), (self.last_conv_3x3, G)]
 
     def run(self, x, G: int = 1):
-        # conv1x1(up2(x)) == up2(conv1x1(x)) bit-for-bit (pointwise conv commutes with replication): 4x fewer MACs
-        sc = ops.upsample2(self.conv_1x1.run(x, G))  # x also feeds BatchNorm: the conv rounds a private copy
+        # conv1x1(up2(x)) == up2(conv1x1(x)) bit-for-bit (pointwise conv commutes with replication): 4x fewer MACs, and the
+        # upsampled shortcut is never materialised: last_conv_3x3's epilogue reads it at (h/2, w/2)
+        sc = self.conv_1x1.run(x, G)  # x also feeds BatchNorm: the conv rounds a private copy
         y = ops.mark_conv_only(self.bn1.run(x, G, relu=True, up2=True, conv_only=True))  # BN -> ReLU -> nearest x2 in one pass
         if self.training:
             y = self.first_conv_3x3.run(y, G)
             y = ops.mark_conv_only(self.bn2.run(y, G, relu=True, conv_only=True))
         else:
             y = ops.mark_conv_only(_conv_bn_relu_eval(self.first_conv_3x3, self.bn2, y, G))
-        return self.last_conv_3x3.run(y, G, res=sc)
+        return self.last_conv_3x3.run(y, G, res=sc, res_up2=True)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         return ops.cl_to_nchw(self.run(ops.nchw_to_cl(x)))
@@ -136,7 +137,8 @@ class DBlock(nn.Module):
         else:
             x1 = x
         y = ops.mark_conv_only(ops.relu(x)) if self.first_relu else x
-        y = ops.mark_conv_only(self.first_conv_3x3.run(y, G, act=ACT_RELU))  # the ReLU between the convs is fused
+        # the ReLU between the convs is fused, and the result (read by last_conv_3x3 only) leaves the epilogue tf32-rounded
+        y = ops.mark_conv_only(self.first_conv_3x3.run(y, G, act=ACT_RELU, round_out=True))
         if self.keep_same_output:
             return self.last_conv_3x3.run(y, G, res=x1)
         y = self._pool(self.last_conv_3x3.run(y, G))
@@ -161,7 +163,7 @@ class LBlock(nn.Module):
             sc = ops.concat_channels(x, self.conv_1x1.run(x))
         else:
             sc = x
-        y = ops.mark_conv_only(self.first_conv_3x3.run(ops.mark_conv_only(ops.relu(x)), act=ACT_RELU))
+        y = ops.mark_conv_only(self.first_conv_3x3.run(ops.mark_conv_only(ops.relu(x)), act=ACT_RELU, round_out=True))
         return self.last_conv_3x3.run(y, res=sc)
 
     def forward(self, x) -> torch.Tensor:
@@ -208,7 +210,7 @@ class ContextConditioningStack(nn.Module, PyTorchModelHubMixin):
             # "b t c h w -> b (c t) h w" (:423): mixed[b, h, w, c*T + t] = s[t, b, h, w, c]
             mixed = ops.permute(s, (b, 1, hh, ww, cc * t), (t, b, hh * ww, cc),
                                 (b * hh * ww * cc, hh * ww * cc, cc, 1), (1, hh * ww * cc * t, cc * t, t))
-            outs.append(mix.run(ops.mark_conv_only(mixed), 1, act=ACT_RELU))
+            outs.append(mix.run(ops.mark_conv_only(mixed), 1, act=ACT_RELU))   # (feeds the ConvGRU as h0: gate arithmetic reads it unrounded)
         return tuple(outs)
 
     def forward(self, x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:

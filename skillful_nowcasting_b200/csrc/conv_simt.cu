@@ -11,6 +11,12 @@ struct ConvDims {
   int N, D, H, W, Cin, Cout, kd, kh, kw, G;
 };
 
+__device__ __forceinline__ float rna_tf32(float x) {  // round to nearest tf32 (10 explicit mantissa bits), low 13 bits zero
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
+
 // ------------------------------------------------------------------ forward / dgrad
 // y[m][co] = act( sum_{tap,ci} x[pix(m)+tap][ci] * wp[tap][co][ci] * scale + bias + res )
 template <int BM, int BN, int BK>
@@ -88,11 +94,20 @@ __global__ void __launch_bounds__(256) conv_simt_fwd_kernel(const float* __restr
   }
   const int64_t per_img = (int64_t)d.D * d.H * d.W;
   const int imgs_per_group = d.N / d.G;
+  const bool round_out = (act & DGMR_FLAG_ROUND_OUT) != 0, res_up2 = (act & DGMR_FLAG_RES_UP2) != 0;
+  act &= 3;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     int64_t m = m0 + ty * 4 + i;
     if (m >= M) continue;
     int g = (int)((m / per_img) / imgs_per_group);
+    int64_t mr = m;     // row of the residual: the same pixel, or (h/2, w/2) of a half-resolution tensor
+    if (res_up2) {
+      int64_t r = m;
+      const int w_ = (int)(r % d.W); r /= d.W;
+      const int h_ = (int)(r % d.H); r /= d.H;    // r = n*D + dd
+      mr = (r * (d.H >> 1) + (h_ >> 1)) * (d.W >> 1) + (w_ >> 1);
+    }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       int co = n0 + tx * 4 + j;
@@ -100,9 +115,9 @@ __global__ void __launch_bounds__(256) conv_simt_fwd_kernel(const float* __restr
       float v = acc[i][j];
       if (scale) v *= scale[(int64_t)g * d.Cout + co];
       if (bias) v += bias[co];
-      if (res) v += res[m * d.Cout + co];
+      if (res) v += res[mr * d.Cout + co];
       if (act == DGMR_ACT_RELU) v = fmaxf(v, 0.f);
-      y[m * d.Cout + co] = v;
+      y[m * d.Cout + co] = round_out ? rna_tf32(v) : v;
     }
   }
 }
@@ -188,11 +203,7 @@ __global__ void __launch_bounds__(256) conv_simt_wgrad_kernel(const float* __res
 }
 
 // ------------------------------------------------------------------ pack / unpack
-__device__ __forceinline__ float rna_tf32(float x) {  // round to nearest tf32 (10 explicit mantissa bits), low 13 bits zero
-  uint32_t u;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
-  return __uint_as_float(u);
-}
+
 __global__ void pack_weight_kernel(const float* __restrict__ w, float* __restrict__ packed, int Cout, int CinTot, int ci0, int Cin, int taps, int mode, int rnd) {
   int64_t total = (int64_t)taps * Cout * Cin;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -207,6 +218,29 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, float* __restric
       v = w[((int64_t)co * CinTot + ci0 + ci) * taps + tap];
     }
     packed[i] = rnd ? rna_tf32(v) : v;
+  }
+}
+// All the packs a network needs after an optimiser step in ONE launch: blockIdx.y = item, blockIdx.x strides over its elements.
+// Destination may be wider than the packed slice: CinPad >= Cin (zero-padded input channels: the pad stays as the caller zeroed it) and a
+// [co0, co0+Cout) window of CoutTot rows (two gate weights of a ConvGRU side by side along Cout).
+constexpr int kPackMaxItems = 64;
+struct PackMultiArgs { dgmr_pack_item it[kPackMaxItems]; };
+__global__ void pack_weight_multi_kernel(const __grid_constant__ PackMultiArgs a) {
+  const dgmr_pack_item& t = a.it[blockIdx.y];
+  const int rnd = (t.mode & DGMR_FLAG_ROUND_TF32) ? 1 : 0, mode = t.mode & ~DGMR_FLAG_ROUND_TF32;
+  const int64_t total = (int64_t)t.taps * t.Cout * t.Cin;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    float v; int64_t o;
+    if (mode == 0) {
+      int ci = i % t.Cin; int64_t r = i / t.Cin; int co = r % t.Cout; int tap = r / t.Cout;
+      v = t.w[((int64_t)co * t.CinTot + t.ci0 + ci) * t.taps + tap];
+      o = ((int64_t)tap * t.CoutTot + t.co0 + co) * t.CinPad + ci;
+    } else {
+      int co = i % t.Cout; int64_t r = i / t.Cout; int ci = r % t.Cin; int tapf = r / t.Cin;
+      v = t.w[((int64_t)co * t.CinTot + t.ci0 + ci) * t.taps + (t.taps - 1 - tapf)];
+      o = ((int64_t)tapf * t.CinPad + ci) * t.CoutTot + t.co0 + co;
+    }
+    t.packed[o] = rnd ? rna_tf32(v) : v;
   }
 }
 __global__ void round_tf32_kernel(const float4* x, float4* y, int64_t n4) {   // y may alias x
@@ -238,7 +272,8 @@ template <int V>
 __global__ void __launch_bounds__(256) conv_bwd_prep_kernel(const float* __restrict__ dy, const float* __restrict__ y, const float* __restrict__ res,
                                                             const float* __restrict__ bias, const float* __restrict__ scale, float* __restrict__ dz,
                                                             float* __restrict__ dpre, float* __restrict__ dbias, float* __restrict__ dscale,
-                                                            int64_t rows, int C, int64_t chunk, int act, int rnd) {
+                                                            int64_t rows, int C, int64_t chunk, int act, int rnd, int up_h, int up_w) {
+  // up_h, up_w > 0: `res` is the HALF-resolution tensor of DGMR_FLAG_RES_UP2 (full-resolution image up_h x up_w): read at (h/2, w/2)
   extern __shared__ double sh[];  // [rp][cpl][2*V]
   const int g = blockIdx.y;
   const int CV = C / V;
@@ -260,15 +295,23 @@ __global__ void __launch_bounds__(256) conv_bwd_prep_kernel(const float* __restr
       // one row: loads are issued by `load`, consumed by `finish`, so that two rows' loads are in flight together below
       struct Row { float d[V], yv[V], rv[V]; int64_t o; };
       auto load = [&](int64_t r, Row& w) {
-        w.o = ((int64_t)g * rows + r) * C + c;
+        const int64_t R = (int64_t)g * rows + r;
+        w.o = R * C + c;
+        int64_t ro = w.o;
+        if (up_w > 0 && res && dscale) {
+          const int64_t img = R / ((int64_t)up_h * up_w);
+          const int rem = (int)(R - img * up_h * up_w);
+          const int hh = rem / up_w, ww = rem - hh * up_w;
+          ro = ((img * (up_h >> 1) + (hh >> 1)) * (up_w >> 1) + (ww >> 1)) * C + c;
+        }
         if (V == 4) {
           float4 t = *reinterpret_cast<const float4*>(dy + w.o); w.d[0] = t.x; w.d[1] = t.y; w.d[2] = t.z; w.d[3] = t.w;
           if (y) { float4 u = *reinterpret_cast<const float4*>(y + w.o); w.yv[0] = u.x; w.yv[1] = u.y; w.yv[2] = u.z; w.yv[3] = u.w; }
-          if (res && dscale) { float4 u = *reinterpret_cast<const float4*>(res + w.o); w.rv[0] = u.x; w.rv[1] = u.y; w.rv[2] = u.z; w.rv[3] = u.w; }
+          if (res && dscale) { float4 u = *reinterpret_cast<const float4*>(res + ro); w.rv[0] = u.x; w.rv[1] = u.y; w.rv[2] = u.z; w.rv[3] = u.w; }
         } else {
           w.d[0] = dy[w.o];
           if (y) w.yv[0] = y[w.o];
-          if (res && dscale) w.rv[0] = res[w.o];
+          if (res && dscale) w.rv[0] = res[ro];
         }
       };
       auto finish = [&](Row& w) {
@@ -594,6 +637,30 @@ int dgmr_pack_weight(const float* w, float* packed, int Cout, int CinTot, int ci
   DGMR_CHECK_LAUNCH("dgmr_pack_weight");
   return 0;
 }
+int dgmr_pack_weight_multi(const dgmr_pack_item* items, int n, dgmr_stream_t stream) {
+  DGMR_REQUIRE(n >= 1 && items != nullptr, "dgmr_pack_weight_multi: empty");
+  for (int base = 0; base < n; base += kPackMaxItems) {
+    const int m = n - base < kPackMaxItems ? n - base : kPackMaxItems;
+    PackMultiArgs args;
+    int64_t biggest = 0;
+    for (int i = 0; i < m; ++i) {
+      const dgmr_pack_item& t = items[base + i];
+      const int mode = t.mode & ~DGMR_FLAG_ROUND_TF32;
+      DGMR_REQUIRE(t.w && t.packed && t.Cout > 0 && t.Cin > 0 && t.taps > 0 && t.ci0 >= 0 && t.ci0 + t.Cin <= t.CinTot && t.CinPad >= t.Cin && t.co0 >= 0 &&
+                   t.co0 + t.Cout <= t.CoutTot && (mode == 0 || mode == 1), "dgmr_pack_weight_multi: bad item %d", base + i);
+      args.it[i] = t;
+      const int64_t tot = (int64_t)t.taps * t.Cout * t.Cin;
+      if (tot > biggest) biggest = tot;
+    }
+    for (int i = m; i < kPackMaxItems; ++i) args.it[i] = args.it[0];
+    int gx = (int)ceil_div(biggest, (int64_t)256 * 8);
+    if (gx < 1) gx = 1;
+    if (gx > 4 * sm_count()) gx = 4 * sm_count();
+    pack_weight_multi_kernel<<<dim3((unsigned)gx, (unsigned)m), 256, 0, S(stream)>>>(args);
+    DGMR_CHECK_LAUNCH("dgmr_pack_weight_multi");
+  }
+  return 0;
+}
 int dgmr_round_tf32(const float* x, float* y, int64_t n, dgmr_stream_t stream) {
   if (n == 0) return 0;
   DGMR_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15u) == 0, "dgmr_round_tf32: pointers must be 16-byte aligned");
@@ -614,9 +681,11 @@ int dgmr_unpack_wgrad(const float* packed, float* gw, int Cout, int CinTot, int 
   return 0;
 }
 int dgmr_conv_bwd_prep(const float* dy, const float* y, const float* res, const float* bias, const float* scale, float* dz, float* dpre, float* dbias,
-                       float* dscale, int64_t rows, int G, int Cout, int act, int accumulate_dbias, dgmr_stream_t stream) {
+                       float* dscale, int64_t rows, int G, int Cout, int act, int accumulate_dbias, int up_h, int up_w, dgmr_stream_t stream) {
   const int rnd = (act & DGMR_FLAG_ROUND_TF32) ? 1 : 0;
   act &= ~DGMR_FLAG_ROUND_TF32;
+  DGMR_REQUIRE((up_h == 0 && up_w == 0) || (up_h > 0 && up_w > 0 && up_h % 2 == 0 && up_w % 2 == 0 && (rows * G) % ((int64_t)up_h * up_w) == 0),
+               "dgmr_conv_bwd_prep: bad half-resolution residual geometry %d x %d", up_h, up_w);
   DGMR_REQUIRE(rows > 0 && G > 0 && Cout > 0, "dgmr_conv_bwd_prep: bad dims");
   DGMR_REQUIRE(!(dscale && !scale), "dgmr_conv_bwd_prep: dscale requested without scale");
   DGMR_REQUIRE(!((act == DGMR_ACT_RELU || dscale) && !y), "dgmr_conv_bwd_prep: y required");
@@ -627,9 +696,9 @@ int dgmr_conv_bwd_prep(const float* dy, const float* y, const float* res, const 
   if (ceil_div(rows, chunk) * G < sm_count()) { chunk = ceil_div(rows * G, (int64_t)sm_count()); if (chunk < 8) chunk = 8; }   // small tensors (ConvGRU steps): fill the SMs
   dim3 grid((unsigned)ceil_div(rows, chunk), G);
   if (Cout % 4 == 0)
-    conv_bwd_prep_kernel<4><<<grid, 256, 256 * 8 * sizeof(double), S(stream)>>>(dy, y, res, bias, scale, dz, dpre, dbias, dscale, rows, Cout, chunk, act, rnd);
+    conv_bwd_prep_kernel<4><<<grid, 256, 256 * 8 * sizeof(double), S(stream)>>>(dy, y, res, bias, scale, dz, dpre, dbias, dscale, rows, Cout, chunk, act, rnd, up_h, up_w);
   else
-    conv_bwd_prep_kernel<1><<<grid, 256, 256 * 2 * sizeof(double), S(stream)>>>(dy, y, res, bias, scale, dz, dpre, dbias, dscale, rows, Cout, chunk, act, rnd);
+    conv_bwd_prep_kernel<1><<<grid, 256, 256 * 2 * sizeof(double), S(stream)>>>(dy, y, res, bias, scale, dz, dpre, dbias, dscale, rows, Cout, chunk, act, rnd, up_h, up_w);
   DGMR_CHECK_LAUNCH("dgmr_conv_bwd_prep");
   return 0;
 }

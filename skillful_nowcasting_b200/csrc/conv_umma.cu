@@ -181,6 +181,13 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t sbo_bytes
   return d;
 }
 
+__device__ __forceinline__ float rna_tf32_e(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
+__device__ __forceinline__ float4 rna_tf32_e4(float4 v) { return make_float4(rna_tf32_e(v.x), rna_tf32_e(v.y), rna_tf32_e(v.z), rna_tf32_e(v.w)); }
+
 struct UmmaConvParams {
   int N, D, H, W, Cin, Cout, kd, kh, kw, G;
   int bw, bh, bn;        // spatial box: bw*bh*bn == 128
@@ -193,6 +200,8 @@ struct UmmaConvParams {
   int act;
   int split_taps;        // 1: blockIdx.z = filter tap, epilogue red.adds acc*scale into y
   int n_tiles;           // persistent variant: Cout tiles
+  int round_out;         // DGMR_FLAG_ROUND_OUT: y written tf32-rounded
+  int res_up2;           // DGMR_FLAG_RES_UP2: res is [N,D,H/2,W/2,Cout], read at (h/2, w/2)
   const float* bias; const float* scale; const float* res; float* y;
 };
 
@@ -350,13 +359,14 @@ conv_umma_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       const uint32_t stg = base + (uint32_t)q * 2048u;
       const int lr = lane >> 2, lc = lane & 3;
       const uint32_t st_row = stg + (uint32_t)lane * 64u, st_sw = (uint32_t)((lane >> 1) & 3);
-      int64_t mrow[4]; bool vrow[4]; const float* srow[4];
+      int64_t mrow[4], rrow[4]; bool vrow[4]; const float* srow[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int rj = q * 32 + lr + 8 * j;
         const int wj = w0 + rj % p.bw, hj = h0 + (rj / p.bw) % p.bh, nj = n0 + rj / (p.bw * p.bh);
         vrow[j] = (nj < p.N) && (hj < p.H) && (wj < p.W);
         mrow[j] = ((((int64_t)nj * p.D + d0) * p.H + hj) * p.W + wj) * p.Cout + co0 + 4 * lc;
+        rrow[j] = p.res_up2 ? ((((int64_t)nj * p.D + d0) * (p.H >> 1) + (hj >> 1)) * (p.W >> 1) + (wj >> 1)) * p.Cout + co0 + 4 * lc : mrow[j];
         srow[j] = (p.scale && vrow[j]) ? p.scale + (int64_t)(nj / (p.N / p.G)) * p.Cout : nullptr;
       }
       float4 rr[4];
@@ -364,7 +374,7 @@ conv_umma_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         if (p.res == nullptr || c >= p.BN || co0 + c + 4 * lc >= p.Cout) return;
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-          if (vrow[j]) dst[j] = __ldg(reinterpret_cast<const float4*>(p.res + mrow[j] + c));
+          if (vrow[j]) dst[j] = __ldg(reinterpret_cast<const float4*>(p.res + rrow[j] + c));
       };
       load_res(0, rr);
       for (int c = 0; c < p.BN; c += 16) {
@@ -397,6 +407,7 @@ conv_umma_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
             if (p.res) { o.x += rr[j].x; o.y += rr[j].y; o.z += rr[j].z; o.w += rr[j].w; }
             if (p.act == DGMR_ACT_RELU) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+            if (p.round_out) o = rna_tf32_e4(o);
             *reinterpret_cast<float4*>(p.y + mrow[j] + c) = o;
           }
         }
@@ -421,7 +432,8 @@ conv_umma_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         }
       }
       float* yp = p.y + m * p.Cout + co0 + c;
-      const float* rp = p.res ? p.res + m * p.Cout + co0 + c : nullptr;
+      const int64_t mres = p.res_up2 ? (((int64_t)n * p.D + d0) * (p.H >> 1) + (h >> 1)) * (p.W >> 1) + (w >> 1) : m;
+      const float* rp = p.res ? p.res + mres * p.Cout + co0 + c : nullptr;
       if (p.split_taps) {
 #pragma unroll
         for (int j = 0; j < 16; ++j)
@@ -435,6 +447,7 @@ conv_umma_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
             if (rp) { float4 rr = *reinterpret_cast<const float4*>(rp + j); o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w; }
             if (p.act == DGMR_ACT_RELU) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+            if (p.round_out) o = rna_tf32_e4(o);
             *reinterpret_cast<float4*>(yp + j) = o;
           }
         }
@@ -445,7 +458,7 @@ conv_umma_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             float o = v[j];
             if (rp) o += rp[j];
             if (p.act == DGMR_ACT_RELU) o = fmaxf(o, 0.f);
-            yp[j] = o;
+            yp[j] = p.round_out ? rna_tf32_e(o) : o;
           }
         }
       }
@@ -583,13 +596,14 @@ conv_umma_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __gr
     for (int64_t t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
       int n0, d0, h0, w0, co0; decode(t, n0, d0, h0, w0, co0);
       const int bsel = it & 1; const uint32_t phacc = (it >> 1) & 1u;
-      int64_t mrow[4]; bool vrow[4]; const float* srow[4];
+      int64_t mrow[4], rrow[4]; bool vrow[4]; const float* srow[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int rj = q * 32 + lr + 8 * j;
         const int wj = w0 + rj % p.bw, hj = h0 + (rj / p.bw) % p.bh, nj = n0 + rj / (p.bw * p.bh);
         vrow[j] = (nj < p.N) && (hj < p.H) && (wj < p.W);
         mrow[j] = ((((int64_t)nj * p.D + d0) * p.H + hj) * p.W + wj) * p.Cout + co0 + 4 * lc;
+        rrow[j] = p.res_up2 ? ((((int64_t)nj * p.D + d0) * (p.H >> 1) + (hj >> 1)) * (p.W >> 1) + (wj >> 1)) * p.Cout + co0 + 4 * lc : mrow[j];
         srow[j] = (p.scale && vrow[j]) ? p.scale + (int64_t)(nj / (p.N / p.G)) * p.Cout : nullptr;
       }
       float4 rr[4];
@@ -597,7 +611,7 @@ conv_umma_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __gr
         if (p.res == nullptr || c >= p.BN || co0 + c + 4 * lc >= p.Cout) return;
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-          if (vrow[j]) dst[j] = __ldg(reinterpret_cast<const float4*>(p.res + mrow[j] + c));
+          if (vrow[j]) dst[j] = __ldg(reinterpret_cast<const float4*>(p.res + rrow[j] + c));
       };
       load_res(0, rr);
       mbar_wait(tmem_full(bsel), phacc);
@@ -629,6 +643,7 @@ conv_umma_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __gr
             o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
             if (p.res) { o.x += rr[j].x; o.y += rr[j].y; o.z += rr[j].z; o.w += rr[j].w; }
             if (p.act == DGMR_ACT_RELU) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+            if (p.round_out) o = rna_tf32_e4(o);
             *reinterpret_cast<float4*>(p.y + mrow[j] + c) = o;
           }
         }
@@ -669,6 +684,7 @@ struct PatchConvParams {
   int tmem_cols;
   int act;
   int sb_vec;            // scale / bias pointers are 16-byte aligned (they may be views into a flat parameter buffer)
+  int round_out, res_up2;   // as in UmmaConvParams
   int dbg;               // tuning only (DGMR_PATCH_DBG): 1 = epilogue skips global traffic, 2 = issuer skips the MMAs, 4 = no TMA loads
   int64_t total_items;   // n_tiles * N * D * items_per_img (pair: n_tiles * qpairs * items_per_img)
   int64_t qpairs;        // pair mode: ceil(N*D / 2) image-depth slice pairs
@@ -885,13 +901,14 @@ conv_umma_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       const int mt = (MT == 2) ? eg : 0;
       const int cbeg = (MT == 2) ? 0 : eg * ((p.BN / 2 + 15) / 16 * 16);
       const int cend = (MT == 2) ? p.BN : (eg == 0 ? (p.BN / 2 + 15) / 16 * 16 : p.BN);
-      int64_t mrow[4]; bool vrow[4];
+      int64_t mrow[4], rrow[4]; bool vrow[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int f = fs + 128 * mt + q * 32 + lr + 8 * j;
         const int hp = f / p.P, wp = f - hp * p.P;
         vrow[j] = (wp >= 1) && (wp <= p.W) && (hp >= 1) && (hp <= p.H) && (n < p.N) && !(p.dbg & 1);
         mrow[j] = ((((int64_t)n * p.D + d) * p.H + (hp - 1)) * p.W + (wp - 1)) * p.Cout + co0 + 4 * lc;
+        rrow[j] = p.res_up2 ? ((((int64_t)n * p.D + d) * (p.H >> 1) + ((hp - 1) >> 1)) * (p.W >> 1) + ((wp - 1) >> 1)) * p.Cout + co0 + 4 * lc : mrow[j];
       }
       const int g = n / (p.N / p.G);
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((buf * MT + mt) * p.BN);
@@ -901,7 +918,7 @@ conv_umma_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         if (p.res == nullptr || c >= cend || co0 + c + 4 * lc >= p.Cout) return;
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-          if (vrow[j]) dst[j] = __ldg(reinterpret_cast<const float4*>(p.res + mrow[j] + c));
+          if (vrow[j]) dst[j] = __ldg(reinterpret_cast<const float4*>(p.res + rrow[j] + c));
       };
       load_res(cbeg, rr);
       mbar_wait(acc_full(buf), phacc);
@@ -939,6 +956,7 @@ conv_umma_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             o.x = fmaf(o.x, s4.x, b4.x); o.y = fmaf(o.y, s4.y, b4.y); o.z = fmaf(o.z, s4.z, b4.z); o.w = fmaf(o.w, s4.w, b4.w);
             if (p.res) { o.x += rr[j].x; o.y += rr[j].y; o.z += rr[j].z; o.w += rr[j].w; }
             if (p.act == DGMR_ACT_RELU) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+            if (p.round_out) o = rna_tf32_e4(o);
             *reinterpret_cast<float4*>(p.y + mrow[j] + c) = o;
           }
         }
@@ -1399,6 +1417,8 @@ int launch_conv_umma_fwd(const float* x, const float* wp, const float* bias, con
                          const float* wp_lo = nullptr) {
   const bool x3 = x_lo != nullptr && wp_lo != nullptr;
   UmmaConvParams p;
+  p.round_out = (act & DGMR_FLAG_ROUND_OUT) ? 1 : 0; p.res_up2 = (act & DGMR_FLAG_RES_UP2) ? 1 : 0;
+  act &= 3;
   p.split_taps = accumulate; p.n_tiles = 1;
   p.N = N; p.D = D; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.kd = kd; p.kh = kh; p.kw = kw; p.G = G;
   if (!pick_box(N, H, W, &p.bw, &p.bh, &p.bn)) { set_error("conv_umma_fwd: no 128-pixel box for N=%d H=%d W=%d", N, H, W); return 1; }
@@ -1645,6 +1665,8 @@ static bool umma_patch_profitable(int N, int D, int H, int W, int Cin, int Cout)
 int launch_conv_umma_patch(const float* x, const float* wp, const float* bias, const float* scale, const float* res, float* y, int N, int D, int H, int W,
                            int Cin, int Cout, int kd, int G, int act, cudaStream_t st) {
   PatchConvParams p;
+  p.round_out = (act & DGMR_FLAG_ROUND_OUT) ? 1 : 0; p.res_up2 = (act & DGMR_FLAG_RES_UP2) ? 1 : 0;
+  act &= 3;
   p.N = N; p.D = D; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.kd = kd; p.G = G;
   p.P = W + 2;
   p.BK = (Cin >= 32) ? 32 : 16;
@@ -1868,7 +1890,10 @@ int dgmr_conv_fwd(const float* x, const float* x_lo, const float* wp, const floa
   DGMR_REQUIRE(G >= 1 && N % G == 0, "dgmr_conv_fwd: N=%d not divisible by G=%d", N, G);
   const int accumulate = (act & DGMR_FLAG_ACCUMULATE) ? 1 : 0;
   act &= ~DGMR_FLAG_ACCUMULATE;
-  DGMR_REQUIRE(act == DGMR_ACT_NONE || act == DGMR_ACT_RELU, "dgmr_conv_fwd: bad act");
+  const int eflags = act & (DGMR_FLAG_ROUND_OUT | DGMR_FLAG_RES_UP2);     // epilogue flags travel on with `act`
+  DGMR_REQUIRE((act & ~eflags) == DGMR_ACT_NONE || (act & ~eflags) == DGMR_ACT_RELU, "dgmr_conv_fwd: bad act");
+  DGMR_REQUIRE(!(eflags && accumulate), "dgmr_conv_fwd: ACCUMULATE excludes ROUND_OUT / RES_UP2");
+  DGMR_REQUIRE(!(eflags & DGMR_FLAG_RES_UP2) || (res != nullptr && H % 2 == 0 && W % 2 == 0), "dgmr_conv_fwd: RES_UP2 needs res and even H, W");
   DGMR_REQUIRE(precision == DGMR_PREC_TF32 || precision == DGMR_PREC_3XTF32, "dgmr_conv_fwd: bad precision");
   bool ok = umma_fwd_ok(N, D, H, W, Cin, Cout, kd, kh, kw, G);
   // 3xTF32 ("parity mode"): the caller hands over the hi and lo parts of both operands (dgmr_split_tf32); served by the plain tcgen05
@@ -1879,6 +1904,7 @@ int dgmr_conv_fwd(const float* x, const float* x_lo, const float* wp, const floa
   if (x3) {
     DGMR_REQUIRE(ok && algo != DGMR_ALGO_SIMT, "dgmr_conv_fwd: 3xTF32 operand pairs were passed but the shape is not served by the tcgen05 path");
     if (accumulate) DGMR_REQUIRE(bias == nullptr && res == nullptr && act == DGMR_ACT_NONE, "dgmr_conv_fwd: ACCUMULATE excludes bias/res/act");
+    DGMR_REQUIRE(!(eflags & DGMR_FLAG_ROUND_OUT), "dgmr_conv_fwd: ROUND_OUT makes no sense in 3xTF32 mode");
     return launch_conv_umma_fwd(x, wp, bias, scale, res, y, N, D, H, W, Cin, Cout, kd, kh, kw, G, act, S(stream), accumulate, x_lo, wp_lo);
   }
   if (precision == DGMR_PREC_3XTF32) algo = DGMR_ALGO_SIMT;   // full-precision operands: fp32 FMA kernel

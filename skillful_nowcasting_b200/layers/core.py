@@ -100,10 +100,10 @@ class SNConv(nn.Module):
         g = inv_sigma.shape[0]
         return inv_sigma.view(g, 1).expand(g, self.out_channels).contiguous()
 
-    def run(self, x, G: int = 1, act: int = ACT_NONE, res=None):
-        """x channels-last [N,D,H,W,Cin] -> [N,D,H,W,Cout], one spectral-norm call per group."""
+    def run(self, x, G: int = 1, act: int = ACT_NONE, res=None, res_up2: bool = False, round_out: bool = False):
+        """x channels-last [N,D,H,W,Cin] -> [N,D,H,W,Cout], one spectral-norm call per group.  res_up2 / round_out: see ops._Conv."""
         scale = self.scale_of(self.inv_sigma(G))
-        return ops.conv(x, self.weight_orig, self.bias, scale, res, 0, self.in_channels, G, act)
+        return ops.conv(x, self.weight_orig, self.bias, scale, res, 0, self.in_channels, G, act, res_up2=res_up2, round_out=round_out)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:  # NCHW in / out (drop-in use)
         if len(self.kernel) == 0:  # linear: [N, Cin]
@@ -145,8 +145,8 @@ class PlainConv(nn.Module):
         else:
             self.register_parameter("bias", None)
 
-    def run(self, x, act: int = ACT_NONE, res=None, scale=None, exact_dscale=False):
-        return ops.conv(x, self.weight, self.bias, scale, res, 0, self.in_channels, 1, act, exact_dscale)
+    def run(self, x, act: int = ACT_NONE, res=None, scale=None, exact_dscale=False, round_out: bool = False):
+        return ops.conv(x, self.weight, self.bias, scale, res, 0, self.in_channels, 1, act, exact_dscale, round_out=round_out)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         return ops.cl_to_nchw(self.run(ops.nchw_to_cl(x)))

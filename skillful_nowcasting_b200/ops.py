@@ -12,7 +12,8 @@ import torch
 from torch.autograd import Function
 
 from . import _lib
-from ._lib import ACT_NONE, ACT_RELU, ALGO_AUTO, ALGO_SIMT, ALGO_UMMA, FLAG_ACCUMULATE, FLAG_ROUND_TF32, PREC_3XTF32, PREC_TF32
+from ._lib import (ACT_NONE, ACT_RELU, ALGO_AUTO, ALGO_SIMT, ALGO_UMMA, FLAG_ACCUMULATE, FLAG_RES_UP2, FLAG_ROUND_OUT, FLAG_ROUND_TF32,
+                   PREC_3XTF32, PREC_TF32)
 
 FLAG_SPLIT = 1024   # packed_weight(): return the [hi | lo] 3xTF32 pair (host-side flag, never crosses the ABI)
 
@@ -579,7 +580,7 @@ def _conv_launch(x, wp, bias, scale, res, y, n, d, h, wd, c, cout, kd, kh, kw, G
         wp, wp_lo = wp[0], wp[1]
         x, x_lo = _split(x)
     if _use_split_taps(n, d, h, wd, c, cout, kd * kh * kw, bias is not None, act) and be.conv_umma_supported(n, d, h, wd, c, cout, kd, kh, kw) \
-            and (config.precision == PREC_TF32 or x_lo is not None):
+            and (config.precision == PREC_TF32 or x_lo is not None):   # (any epilogue flag in `act` makes act != ACT_NONE: no tap split)
         if res is None:
             be.fill(y, 0.0)
         elif res.data_ptr() != y.data_ptr():
@@ -603,10 +604,13 @@ def _wgrad_launch(x, dz, dwp, n, d, h, wd, cin, cout, kd, kh, kw):
 
 
 class _Conv(Function):
-    """y = act( conv(x, w[:, ci0:ci0+cin]) * scale[g, co] + bias + res ).  Kernel extents 1 or 3, same padding."""
+    """y = act( conv(x, w[:, ci0:ci0+cin]) * scale[g, co] + bias + res ).  Kernel extents 1 or 3, same padding.
+    res_up2: `res` is a half-resolution tensor added nearest-upsampled (read at (h/2, w/2) in the conv epilogue; its gradient is the
+    2x2 sum-pool of the full-resolution one).  round_out: the output feeds tensor-core convolutions only and is written tf32-rounded
+    by the epilogue (no separate rounding pass); ignored unless the 1xTF32 tensor-core mode is on."""
 
     @staticmethod
-    def forward(ctx, x, w, bias, scale, res, ci0, cin, G, act, exact_dscale=False):
+    def forward(ctx, x, w, bias, scale, res, ci0, cin, G, act, exact_dscale=False, res_up2=False, round_out=False):
         x = _c(x)
         n, d, h, wd, c = x.shape
         assert c == cin or (c > cin and c == (cin + 7) // 8 * 8), (c, cin)   # c > cin: zero-padded input channels
@@ -623,17 +627,22 @@ class _Conv(Function):
         wp = packed_weight(w, ci0, cin, rnd) if c == cin else packed_weight_padded(w, ci0, cin, c, rnd)
         y = _new((n, d, h, wd, cout), x)
         res_c, scale_c, bias_c = _c(res), _c(scale), _c(bias)
-        _conv_launch(x, wp, bias_c, scale_c, res_c, y, n, d, h, wd, c, cout, kd, kh, kw, G, act)
+        res_up2 = bool(res_up2 and res is not None)
+        round_out = bool(round_out and _rounding_on())
+        _conv_launch(x, wp, bias_c, scale_c, res_c, y, n, d, h, wd, c, cout, kd, kh, kw, G,
+                     act | (FLAG_RES_UP2 if res_up2 else 0) | (FLAG_ROUND_OUT if round_out else 0))
+        if round_out:
+            y._dgmr_tf32 = True
         need_s = scale is not None and scale.requires_grad
         need_y = act == ACT_RELU or need_s
         ctx.save_for_backward(x, w, bias_c, scale_c, res_c if need_s else None, y if need_y else None)
-        ctx.meta = (ci0, cin, G, act, (kd, kh, kw), res is not None, exact_dscale)
+        ctx.meta = (ci0, cin, G, act, (kd, kh, kw), res is not None, exact_dscale, res_up2)
         return y
 
     @staticmethod
     def backward(ctx, dy):
         x, w, bias, scale, res, y = ctx.saved_tensors
-        ci0, cin, G, act, (kd, kh, kw), has_res, exact_dscale = ctx.meta
+        ci0, cin, G, act, (kd, kh, kw), has_res, exact_dscale, res_up2 = ctx.meta
         be = _be()
         dy = _c(dy)
         n, d, h, wd, cp = x.shape   # cp > cin: zero-padded input channels
@@ -652,7 +661,8 @@ class _Conv(Function):
             dscale = _new((G, cout), dy) if need_s else None
             tc_bwd = (need_x and _tc_fwd(n, d, h, wd, cout, cp, kd, kh, kw)) or (need_w and _tc_wgrad(n, d, h, wd, cp, cout, kd, kh, kw))
             be.conv_bwd_prep(dy, y, res if need_s else None, bias, scale, dz, dpre, dbias, dscale, rows, G, cout,
-                             act | (FLAG_ROUND_TF32 if (tc_bwd and dz is not None and config._dbg_round_dz) else 0))
+                             act | (FLAG_ROUND_TF32 if (tc_bwd and dz is not None and config._dbg_round_dz) else 0),
+                             up_hw=((h, wd) if (res_up2 and need_s and res is not None) else (0, 0)))
             if need_s and exact_dscale:
                 # the <dY, Y-b-res>/scale identity divides by the scale, which may be exactly 0 (attention gamma starts at 0,
                 # ref: dgmr/layers/Attention.py:69): recompute the raw conv output and reduce <dpre, z> directly
@@ -690,13 +700,19 @@ class _Conv(Function):
                 be.unpack_wgrad(dwp, dw, cout, cintot, ci0, cin, taps, False)
             else:  # drop the padded channels: dw[co][ci0+ci][tap] = dwp[tap][co][ci], ci < cin
                 be.permute(dwp, dw, (taps, cout, cin), (cout * cp, cp, 1), (1, cintot * taps, taps), False, 0, ci0 * taps)
-        return dx, dw, dbias, dscale, (dpre if need_r else None), None, None, None, None, None
+        dres = None
+        if need_r:
+            dres = dpre
+            if res_up2:   # gradient of the half-resolution residual: 2x2 sum-pool of the full-resolution one
+                dres = _new((n, d, h // 2, wd // 2, cout), dy)
+                be.pool_sum(_c(dpre), dres, n, d, h, wd, cout, 1, 2, 2, 1.0)
+        return dx, dw, dbias, dscale, dres, None, None, None, None, None, None, None
 
 
-def conv(x, w, bias=None, scale=None, res=None, ci0=0, cin=None, G=1, act=ACT_NONE, exact_dscale=False):
+def conv(x, w, bias=None, scale=None, res=None, ci0=0, cin=None, G=1, act=ACT_NONE, exact_dscale=False, res_up2=False, round_out=False):
     if cin is None:
         cin = w.shape[1]
-    return _Conv.apply(x, w, bias, scale, res, ci0, cin, G, act, exact_dscale)
+    return _Conv.apply(x, w, bias, scale, res, ci0, cin, G, act, exact_dscale, res_up2, round_out)
 
 
 # ----------------------------------------------------------------------------- BatchNorm

@@ -251,16 +251,28 @@ class EmuBackend:
         if act & 512:  # DGMR_FLAG_ACCUMULATE
             y.add_(z.reshape(y.shape))
             return
+        round_out, res_up2, act = bool(act & 1024), bool(act & 2048), act & 3
         if bias is not None:
             z = z + bias
         if res is not None:
-            z = z + res.reshape(z.shape)
+            if res_up2:   # half-resolution residual, added nearest-upsampled
+                r = res.reshape(N, D, H // 2, W // 2, Cout)
+                r = r.repeat_interleave(2, dim=2).repeat_interleave(2, dim=3)
+                z = z + r
+            else:
+                z = z + res.reshape(z.shape)
         if act == 1:
             z = torch.relu(z)
+        if round_out:
+            z = self._rna_tf32(z.contiguous())
         y.copy_(z.reshape(y.shape))
 
-    def conv_bwd_prep(self, dy, y, res, bias, scale, dz, dpre, dbias, dscale, rows, G, Cout, act, accumulate_dbias=False):
+    def conv_bwd_prep(self, dy, y, res, bias, scale, dz, dpre, dbias, dscale, rows, G, Cout, act, accumulate_dbias=False, up_hw=(0, 0)):
         rnd, act = bool(act & 256), act & ~256
+        if res is not None and up_hw[0]:
+            uh, uw = up_hw
+            r = res.reshape(-1, uh // 2, uw // 2, Cout)
+            res = r.repeat_interleave(2, dim=1).repeat_interleave(2, dim=2).contiguous()
         d = dy.reshape(G, rows, Cout)
         if act == 1:
             d = d * (y.reshape(G, rows, Cout) > 0)

@@ -168,7 +168,10 @@ def test_full_size_layer_3xtf32_matches_fp32_on_unrounded_operands(cuda_backend,
     be.conv_fwd(xh, wh, None, None, None, y, n, d, h, w, cin, cout, kd, k, k, 1, 0, precision=1, x_lo=xl, wp_lo=wl)
     ref = _torch_conv(x, wt, kd, k)
     e_fwd = float((y - ref).abs().max() / ref.abs().max())
-    dy = torch.randn_like(y)
+    # dy = y: every gradient element is then a COHERENT sum (~ ||y||^2-like), which is what makes a relative comparison meaningful --
+    # with an uncorrelated dy a weight-gradient element is a zero-mean sum of up to 4.7 M terms and any fp32 accumulation (torch's own
+    # included) is only good to ~1e-4 of it (round 2 measured 3.5e-4 between this path and cuDNN's fp32 wgrad that way).
+    dy = y.clone()
     dyh, dyl = split(dy)
     wth, wtl = split(wpt)
     dx = torch.full((n, d, h, w, cin), float("nan"), device="cuda")
@@ -183,10 +186,13 @@ def test_full_size_layer_3xtf32_matches_fp32_on_unrounded_operands(cuda_backend,
     gwp = torch.empty_like(dwp)
     be.pack_weight(gw.contiguous(), gwp, cout, cin, 0, cin, taps, 0)
     e_dw = float((dwp - gwp).abs().max() / gwp.abs().max())
+    a, b, c = _dot(y, dy), _dot(x, dx), _dot(wp, dwp)
+    e_ab, e_ac = abs(a - b) / a, abs(a - c) / a
     t_f, t_d, t_w = tol_chain(3 * cin * taps / 8), tol_chain(3 * cout * taps / 8), tol_chain(wgrad_chain(*shape, x3=True), floor=3e-5)
-    print(f"\nFULLSIZE-3X {shape}: fwd {e_fwd:.2e} dgrad {e_dx:.2e} wgrad {e_dw:.2e}   bounds {t_f:.1e} {t_d:.1e} {t_w:.1e}")
+    print(f"\nFULLSIZE-3X {shape}: fwd {e_fwd:.2e} dgrad {e_dx:.2e} wgrad {e_dw:.2e} adj {e_ab:.2e} {e_ac:.2e}  bounds {t_f:.1e} {t_d:.1e} {t_w:.1e}")
     assert e_fwd < t_f and e_dx < t_d, (e_fwd, e_dx)
-    assert e_dw < t_w, e_dw
+    assert e_dw < max(t_w, 1e-4), e_dw          # (the checker's own fp32 wgrad is not better than that over millions of pixels)
+    assert e_ab < t_f + t_d and e_ac < t_f + t_w, (e_ab, e_ac)   # our three kernels against each other, no checker involved
 
 
 def test_tensor_core_accumulation(cuda_backend):

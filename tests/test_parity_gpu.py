@@ -258,8 +258,10 @@ def test_pretrained_round_trip_on_gpu(cuda_backend, c1_state, tmp_path):
                      B.Sampler.from_pretrained(tmp_path / "sampler")).cuda().eval()
     torch.manual_seed(9)
     b = g2(x.cuda())
-    # identical weights and latent draw; the tap-split ConvGRU convolutions accumulate with fp32 atomics (order not fixed): not bit-equal
-    assert rel_err(b, a) < 1e-4
+    # Identical weights and latent draw, yet not bit-equal: the tap-split ConvGRU convolutions accumulate with fp32 atomics whose order is
+    # not fixed, and a 1e-7 difference that lands on a tf32 rounding boundary of a conv operand becomes a 2^-11 (4.9e-4) difference of
+    # that element.  Round 2 measured 6.0e-4 between two runs -- this is the run-to-run noise floor of the 1xTF32 path.
+    assert rel_err(b, a) < 3e-3
     gen.cpu()
 
 
@@ -281,7 +283,7 @@ def test_graphed_generator_matches_eager_and_oracle(cuda_backend, c1_state):
     torch.manual_seed(2)
     with torch.no_grad():
         out_e = gen(xc)
-    assert rel_err(out_g, out_e) < 1e-4
+    assert rel_err(out_g, out_e) < 3e-3          # run-to-run noise floor of the 1xTF32 path (see test_pretrained_round_trip_on_gpu): 5.4e-4
     ref = oracle_gan_forward(g0, d0, x, y, C1, False, seed=2)
     assert rel_err(out_g, ref["out"]) < 1e-3
     torch.manual_seed(3)                      # a second replay with another latent draw really changes the forecast
