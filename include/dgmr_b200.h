@@ -167,6 +167,14 @@ int dgmr_sn_power_iter_multi(const dgmr_sn_item* items, int n, dgmr_stream_t str
 int dgmr_sn_bwd(const float* d_inv_sigma, const float* inv_sigma, const float* u_hist, const float* v_hist,
                 float* dw, int R, int K, int G, int accumulate, dgmr_stream_t stream);
 
+/* dgmr_sn_bwd for all the spectrally normalised weights of a module in one launch (`items`: HOST array) */
+typedef struct {
+  const float* d_inv_sigma; const float* inv_sigma; const float* u_hist; const float* v_hist;
+  float* dw;
+  int R, K, G, accumulate;
+} dgmr_sn_bwd_item;
+int dgmr_sn_bwd_multi(const dgmr_sn_bwd_item* items, int n, dgmr_stream_t stream);
+
 /* ---- convolution (ref: every Conv2d/Conv3d call site: dgmr/layers/ConvGRU.py:72-81,
  * common.py:71-83,141-154,222-236,290-300,413-424,486, generators.py:153,176-177,
  * discriminators.py:113-133,203-211; F.linear heads as 1x1).  Stride 1, "same" zero padding,

@@ -118,6 +118,19 @@ class SnItem(ctypes.Structure):
                 ("K", ctypes.c_int), ("G", ctypes.c_int), ("training", ctypes.c_int), ("eps", ctypes.c_float)]
 
 
+class PackItem(ctypes.Structure):
+    """dgmr_pack_item of include/dgmr_b200.h."""
+    _fields_ = [("w", ctypes.c_void_p), ("packed", ctypes.c_void_p), ("Cout", ctypes.c_int), ("CinTot", ctypes.c_int), ("ci0", ctypes.c_int),
+                ("Cin", ctypes.c_int), ("taps", ctypes.c_int), ("mode", ctypes.c_int), ("CinPad", ctypes.c_int), ("co0", ctypes.c_int),
+                ("CoutTot", ctypes.c_int)]
+
+
+class SnBwdItem(ctypes.Structure):
+    """dgmr_sn_bwd_item of include/dgmr_b200.h."""
+    _fields_ = [("d_inv_sigma", ctypes.c_void_p), ("inv_sigma", ctypes.c_void_p), ("u_hist", ctypes.c_void_p), ("v_hist", ctypes.c_void_p),
+                ("dw", ctypes.c_void_p), ("R", ctypes.c_int), ("K", ctypes.c_int), ("G", ctypes.c_int), ("accumulate", ctypes.c_int)]
+
+
 class CudaBackend:
     """Thin tensor-level view of the C ABI.  Method names/arguments mirror include/dgmr_b200.h.
     `launches` counts kernel-launching entry-point calls (reported by bench.py as gpu_launches)."""
@@ -255,9 +268,28 @@ class CudaBackend:
         self._call("dgmr_sn_bwd", _f32(d_inv_sigma, "d_inv_sigma"), _f32(inv_sigma, "inv_sigma"), _f32(u_hist, "u_hist"),
                    _f32(v_hist, "v_hist"), _f32(dw, "dw"), R, K, G, int(accumulate))
 
+    def sn_bwd_multi(self, items):
+        """items: list of dicts(d_inv_sigma, inv_sigma, u_hist, v_hist, dw, R, K, G, accumulate): one launch per 48 weights."""
+        arr = (SnBwdItem * len(items))()
+        for a, it in zip(arr, items):
+            for k in ("d_inv_sigma", "inv_sigma", "u_hist", "v_hist", "dw"):
+                setattr(a, k, _f32(it[k], k))
+            a.R, a.K, a.G, a.accumulate = it["R"], it["K"], it["G"], int(it["accumulate"])
+        self._call("dgmr_sn_bwd_multi", arr, len(items), _info=f"{len(items)} weights")
+
     # -- conv
     def pack_weight(self, w, packed, Cout, CinTot, ci0, Cin, taps, mode):
         self._call("dgmr_pack_weight", _f32(w, "w"), _f32(packed, "packed"), Cout, CinTot, ci0, Cin, taps, mode)
+
+    def pack_weight_multi(self, items):
+        """items: list of dicts(w, packed, Cout, CinTot, ci0, Cin, taps, mode, CinPad, co0, CoutTot): all of them in one launch
+        (per 64 items)."""
+        arr = (PackItem * len(items))()
+        for a, it in zip(arr, items):
+            a.w, a.packed = _f32(it["w"], "w"), _f32(it["packed"], "packed")
+            for k in ("Cout", "CinTot", "ci0", "Cin", "taps", "mode", "CinPad", "co0", "CoutTot"):
+                setattr(a, k, int(it[k]))
+        self._call("dgmr_pack_weight_multi", arr, len(items), _info=f"{len(items)} packs")
 
     def unpack_wgrad(self, packed, gw, Cout, CinTot, ci0, Cin, taps, accumulate):
         self._call("dgmr_unpack_wgrad", _f32(packed, "packed"), _f32(gw, "gw"), Cout, CinTot, ci0, Cin, taps, int(accumulate))

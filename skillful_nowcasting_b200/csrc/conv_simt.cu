@@ -589,6 +589,22 @@ __global__ void sn_bwd_kernel(const float* __restrict__ dis, const float* __rest
     if (acc) dw[i] += s; else dw[i] = s;
   }
 }
+constexpr int kSnBwdMaxItems = 48;
+struct SnBwdMultiArgs { dgmr_sn_bwd_item it[kSnBwdMaxItems]; };
+// the rank-G corrections of many weights in one launch: blockIdx.y = weight
+__global__ void sn_bwd_multi_kernel(const __grid_constant__ SnBwdMultiArgs a) {
+  const dgmr_sn_bwd_item& t = a.it[blockIdx.y];
+  const int64_t total = (int64_t)t.R * t.K;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int k = (int)(i % t.K), r = (int)(i / t.K);
+    float s = 0.f;
+    for (int g = 0; g < t.G; ++g) {
+      const float is = t.inv_sigma[g];
+      s += (-t.d_inv_sigma[g] * is * is) * t.u_hist[(int64_t)g * t.R + r] * t.v_hist[(int64_t)g * t.K + k];
+    }
+    if (t.accumulate) t.dw[i] += s; else t.dw[i] = s;
+  }
+}
 
 // exposed to conv_umma.cu / api
 int launch_conv_simt_fwd(const float* x, const float* wp, const float* bias, const float* scale, const float* res, float* y,
@@ -798,6 +814,27 @@ int dgmr_sn_bwd(const float* d_inv_sigma, const float* inv_sigma, const float* u
   int64_t total = (int64_t)R * K;
   sn_bwd_kernel<<<ew_grid(total, 256, 2), 256, 0, S(stream)>>>(d_inv_sigma, inv_sigma, u_hist, v_hist, dw, R, K, G, accumulate);
   DGMR_CHECK_LAUNCH("dgmr_sn_bwd");
+  return 0;
+}
+int dgmr_sn_bwd_multi(const dgmr_sn_bwd_item* items, int n, dgmr_stream_t stream) {
+  DGMR_REQUIRE(n >= 1 && items != nullptr, "dgmr_sn_bwd_multi: empty");
+  for (int base = 0; base < n; base += kSnBwdMaxItems) {
+    const int m = n - base < kSnBwdMaxItems ? n - base : kSnBwdMaxItems;
+    SnBwdMultiArgs args;
+    int64_t biggest = 0;
+    for (int i = 0; i < m; ++i) {
+      const dgmr_sn_bwd_item& t = items[base + i];
+      DGMR_REQUIRE(t.d_inv_sigma && t.inv_sigma && t.u_hist && t.v_hist && t.dw && t.R > 0 && t.K > 0 && t.G > 0, "dgmr_sn_bwd_multi: bad item %d", base + i);
+      args.it[i] = t;
+      if ((int64_t)t.R * t.K > biggest) biggest = (int64_t)t.R * t.K;
+    }
+    for (int i = m; i < kSnBwdMaxItems; ++i) args.it[i] = args.it[0];
+    int gx = (int)ceil_div(biggest, (int64_t)256 * 8);
+    if (gx < 1) gx = 1;
+    if (gx > 4 * sm_count()) gx = 4 * sm_count();
+    sn_bwd_multi_kernel<<<dim3((unsigned)gx, (unsigned)m), 256, 0, S(stream)>>>(args);
+    DGMR_CHECK_LAUNCH("dgmr_sn_bwd_multi");
+  }
   return 0;
 }
 

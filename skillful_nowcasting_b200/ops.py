@@ -385,14 +385,17 @@ class _SpectralSigmaMulti(Function):
     @staticmethod
     def backward(ctx, *gs):
         inv = ctx.saved_tensors
-        outs = []
-        for g, inv_sigma, (u_hist, v_hist), (R, K, G), shape, need in zip(gs, inv, ctx.hist, ctx.sizes, ctx.shapes, ctx.needs_input_grad[2:]):
-            if g is None or not need:
-                outs.append(None)
-                continue
-            dw = _new(shape, inv_sigma)
-            _be().sn_bwd(_c(g), _c(inv_sigma), u_hist, v_hist, dw, R, K, G, False)
-            outs.append(dw)
+        todo = [(i, g, inv_sigma, hist, size, shape) for i, (g, inv_sigma, hist, size, shape, need) in
+                enumerate(zip(gs, inv, ctx.hist, ctx.sizes, ctx.shapes, ctx.needs_input_grad[2:])) if g is not None and need]
+        outs = [None] * len(gs)
+        if todo:   # the rank-G corrections of all the weights in ONE launch, into views of one allocation
+            flat = _new((sum(R * K for _, _, _, _, (R, K, G), _ in todo),), inv[0])
+            o, items = 0, []
+            for i, g, inv_sigma, (u_hist, v_hist), (R, K, G), shape in todo:
+                dw = flat[o:o + R * K].view(shape); o += R * K
+                items.append(dict(d_inv_sigma=_c(g), inv_sigma=_c(inv_sigma), u_hist=u_hist, v_hist=v_hist, dw=dw, R=R, K=K, G=G, accumulate=False))
+                outs[i] = dw
+            _be().sn_bwd_multi(items)
         return (None, None) + tuple(outs)
 
 
@@ -548,18 +551,47 @@ def packed_weight_padded(w: torch.Tensor, ci0: int, cin: int, cin_p: int, mode: 
         return hit
     cout, cintot = w.shape[0], w.shape[1]
     taps = w.numel() // (cout * cintot)
-    p = _zeros((taps * cout * cin_p,), w)
-    split, mode = mode & FLAG_SPLIT, mode & ~FLAG_SPLIT
-    rnd, mode = (0 if split else mode & FLAG_ROUND_TF32), mode & ~FLAG_ROUND_TF32
-    dense = packed_weight(w, ci0, cin, mode | rnd)
-    if mode == 0:   # p[tap][co][ci] with row pitch cin_p
-        _be().permute(dense, p, (taps * cout, cin), (cin, 1), (cin_p, 1), False, 0, 0)
-    else:           # p[taps-1-tap][ci][co]: ci rows spread to cin_p per tap (extra rows stay zero)
-        _be().permute(dense, p, (taps, cin, cout), (cin * cout, cout, 1), (cin_p * cout, cout, 1), False, 0, 0)
+    p = _zeros((taps * cout * cin_p,), w)     # the pad rows / columns stay zero: the pack kernel writes the [cin] window only
+    split = mode & FLAG_SPLIT
+    kmode = mode & ~(FLAG_SPLIT | (FLAG_ROUND_TF32 if split else 0))
+    _be().pack_weight_multi([dict(w=_c(w.detach()), packed=p, Cout=cout, CinTot=cintot, ci0=ci0, Cin=cin, taps=taps, mode=kmode,
+                                  CinPad=cin_p, co0=0, CoutTot=cout)])
     if split:
         p = torch.stack(_split(p))
     _pack_store(slot, w, key, p)
     return p
+
+
+def refresh_packs(params) -> int:
+    """Re-pack, IN PLACE and in one launch per 64 packs, every cached packed copy of `params` that an optimiser step made stale
+    (the optimiser calls this right after its update): from the second step on a network's ~100-200 packs cost a couple of
+    launches instead of one launch each at first use.  Parity-mode (hi, lo) pairs are simply dropped and rebuilt on demand."""
+    items, touched = [], []
+    for w in params:
+        slot = w.__dict__.get("_dgmr_packs")
+        if not slot:
+            continue
+        tag = (w._version, w.data_ptr(), str(w.device))
+        cout, cintot = w.shape[0], w.shape[1]
+        taps = w.numel() // (cout * cintot)
+        for key in list(slot):
+            if slot[key][0] == tag:
+                continue
+            ci0, cin, m = key
+            pad = cin
+            if isinstance(m, tuple):
+                _, pad, m = m
+            if m & FLAG_SPLIT:
+                del slot[key]
+                continue
+            items.append(dict(w=_c(w.detach()), packed=slot[key][1], Cout=cout, CinTot=cintot, ci0=ci0, Cin=cin, taps=taps, mode=m,
+                              CinPad=pad, co0=0, CoutTot=cout))
+            touched.append((slot, key, tag))
+    if items:
+        _be().pack_weight_multi(items)
+        for slot, key, tag in touched:
+            slot[key] = (tag, slot[key][1])
+    return len(items)
 
 
 def clear_pack_cache():

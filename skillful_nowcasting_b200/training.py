@@ -92,7 +92,8 @@ class Adam(torch.optim.Optimizer):
         g = self.param_groups[0]
         _lib.backend().adam(self.flat_p, self.flat_g, self.m, self.v, g["lr"], g["betas"][0], g["betas"][1], g["eps"],
                             self.steps, 1.0 / world)
-        torch.autograd.graph.increment_version(self._params)  # invalidates the packed-weight cache
+        torch.autograd.graph.increment_version(self._params)  # invalidates the packed-weight cache ...
+        ops.refresh_packs(self._params)                       # ... which is refreshed in place, all weights in one launch
         return None
 
     # ---- checkpointing: the layout of torch.optim.Adam's state dict (exp_avg / exp_avg_sq / step per parameter index),

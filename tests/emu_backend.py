@@ -221,6 +221,10 @@ class EmuBackend:
         g = torch.einsum("g,gr,gk->rk", coef, u_hist, v_hist).reshape(dw.shape)
         dw.add_(g) if accumulate else dw.copy_(g)
 
+    def sn_bwd_multi(self, items):
+        for it in items:
+            self.sn_bwd(it["d_inv_sigma"], it["inv_sigma"], it["u_hist"], it["v_hist"], it["dw"], it["R"], it["K"], it["G"], it["accumulate"])
+
     # ---- conv
     def pack_weight(self, w, packed, Cout, CinTot, ci0, Cin, taps, mode):
         rnd, mode = bool(mode & 256), mode & ~256
@@ -231,6 +235,16 @@ class EmuBackend:
             packed.copy_(wv.flip(2).permute(2, 1, 0).reshape(-1))
         if rnd:
             packed.copy_(self._rna_tf32(packed))
+
+    def pack_weight_multi(self, items):
+        for it in items:
+            cout, cin, taps, pad, cot, co0 = it["Cout"], it["Cin"], it["taps"], it["CinPad"], it["CoutTot"], it["co0"]
+            dense = torch.empty(taps * cout * cin)
+            self.pack_weight(it["w"], dense, cout, it["CinTot"], it["ci0"], cin, taps, it["mode"])
+            if (it["mode"] & ~256) == 0:
+                it["packed"].view(taps, cot, pad)[:, co0:co0 + cout, :cin] = dense.view(taps, cout, cin)
+            else:
+                it["packed"].view(taps, pad, cot)[:, :cin, co0:co0 + cout] = dense.view(taps, cin, cout)
 
     def unpack_wgrad(self, packed, gw, Cout, CinTot, ci0, Cin, taps, accumulate):
         g = packed.reshape(taps, Cout, Cin).permute(1, 2, 0)

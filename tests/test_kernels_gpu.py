@@ -178,6 +178,75 @@ def test_conv_bwd_prep(cuda_backend, G, rows, C, act):
     _both("conv_bwd_prep", args, cuda_backend, rtol=1e-4, atol=1e-4)
 
 
+@pytest.mark.parametrize("G,n_img,hw,C,act", [(2, 4, (8, 12), 24, 0), (1, 3, (4, 4), 7, 1)])
+def test_conv_bwd_prep_half_resolution_residual(cuda_backend, G, n_img, hw, C, act):
+    """Backward prologue of a conv that ran with DGMR_FLAG_RES_UP2: the residual in the <dY, Y - b - res> reduction is the
+    half-resolution tensor read at (h/2, w/2)."""
+    torch.manual_seed(18)
+    uh, uw = hw
+    rows = (n_img // G) * uh * uw if n_img % G == 0 else None
+    assert rows is not None or G == 1
+    rows = (n_img * uh * uw) // G
+    dy, y = torch.randn(G * rows, C), torch.randn(G * rows, C)
+    res = torch.randn(n_img * (uh // 2) * (uw // 2), C)
+    bias, scale = torch.randn(C), torch.rand(G, C) + 0.5
+    args = [dy, y, res, bias, scale, torch.empty(G * rows, C), torch.empty(G * rows, C), torch.zeros(C), torch.zeros(G, C), rows, G, C, act]
+    _both("conv_bwd_prep", args, cuda_backend, rtol=1e-4, atol=1e-4, kwargs=dict(up_hw=(uh, uw)))
+
+
+def test_pack_weight_multi(cuda_backend):
+    """dgmr_pack_weight_multi: several packs in one launch, padded input channels and a Cout window of a wider destination,
+    against dgmr_pack_weight (bit-exact: pure index maps + the same cvt.rna rounding)."""
+    import ctypes
+
+    from skillful_nowcasting_b200._lib import PackItem
+
+    be = cuda_backend
+    torch.manual_seed(19)
+    specs = [(24, 16, 0, 16, 9, 0), (24, 16, 4, 8, 9, 1 | 256), (48, 4, 0, 4, 27, 0 | 256), (40, 40, 8, 32, 1, 1)]
+    items, checks = [], []
+    for cout, cintot, ci0, cin, taps, mode in specs:
+        w = torch.randn(cout, cintot, taps, device="cuda")
+        pad = 8 if cin == 4 else cin
+        cot, co0 = cout + 16, 8
+        dst = torch.zeros(taps * cot * pad, device="cuda")
+        items.append(dict(w=w, packed=dst, Cout=cout, CinTot=cintot, ci0=ci0, Cin=cin, taps=taps, mode=mode, CinPad=pad, co0=co0, CoutTot=cot))
+        single = torch.empty(taps * cout * cin, device="cuda")
+        be.pack_weight(w, single, cout, cintot, ci0, cin, taps, mode)
+        checks.append((dst, single, cout, cin, taps, mode & 1, pad, co0, cot))
+    be.pack_weight_multi(items)
+    torch.cuda.synchronize()
+    for dst, single, cout, cin, taps, mode, pad, co0, cot in checks:
+        if mode == 0:
+            got = dst.view(taps, cot, pad)[:, co0:co0 + cout, :cin]
+            ref = single.view(taps, cout, cin)
+            rest = dst.view(taps, cot, pad).clone(); rest[:, co0:co0 + cout, :cin] = 0
+        else:
+            got = dst.view(taps, pad, cot)[:, :cin, co0:co0 + cout]
+            ref = single.view(taps, cin, cout)
+            rest = dst.view(taps, pad, cot).clone(); rest[:, :cin, co0:co0 + cout] = 0
+        assert torch.equal(got, ref)
+        assert float(rest.abs().max()) == 0.0     # nothing outside the window was written
+
+
+def test_sn_bwd_multi(cuda_backend):
+    """dgmr_sn_bwd_multi against dgmr_sn_bwd weight by weight (same arithmetic order per element: bit-exact)."""
+    be = cuda_backend
+    torch.manual_seed(20)
+    items, refs = [], []
+    for R, K, G, acc in ((24, 72, 3, False), (8, 9, 1, True), (96, 864, 18, False)):
+        t = [torch.randn(G, device="cuda"), torch.rand(G, device="cuda") + 0.5, torch.randn(G, R, device="cuda"), torch.randn(G, K, device="cuda")]
+        dw0 = torch.randn(R, K, device="cuda")
+        ref, dw = dw0.clone(), dw0.clone()
+        be.sn_bwd(t[0], t[1], t[2], t[3], ref, R, K, G, acc)
+        items.append(dict(d_inv_sigma=t[0], inv_sigma=t[1], u_hist=t[2], v_hist=t[3], dw=dw, R=R, K=K, G=G, accumulate=acc))
+        refs.append(ref)
+    be.sn_bwd_multi(items)
+    torch.cuda.synchronize()
+    for it, ref in zip(items, refs):
+        assert torch.equal(it["dw"], ref)
+
+
 def test_head_attention_losses_adam(cuda_backend):
     torch.manual_seed(9)
     x = torch.randn(6, 4, 40)

@@ -37,7 +37,7 @@ UMMA_SHAPES = [
 
 
 @pytest.mark.parametrize("shape", UMMA_SHAPES)
-@pytest.mark.parametrize("variant", ["plain", "fused", "fused-persistent"])
+@pytest.mark.parametrize("variant", ["plain", "fused", "fused-persistent", "fusedup2", "fusedup2-persistent"])
 def test_conv_umma(cuda_backend, shape, variant):
     n, d, h, w, cin, cout, kd, kh, kw, g = shape
     # "persistent": force the many-tile persistent kernel (double-buffered TMEM, continuous K stream) on these small shapes
@@ -48,11 +48,14 @@ def test_conv_umma(cuda_backend, shape, variant):
     taps = kd * kh * kw
     x = torch.randn(n, d, h, w, cin)
     wp = torch.randn(taps * cout * cin) / (taps * cin) ** 0.5
-    fused = variant == "fused"
+    fused = variant.startswith("fused")
+    up2 = variant == "fusedup2"     # epilogue flags: half-resolution residual read at (h/2, w/2) + tf32-rounded output
+    if up2 and (h % 2 or w % 2):
+        pytest.skip("RES_UP2 needs even H, W")
     bias = torch.randn(cout) if fused else None
     scale = (torch.rand(g, cout) + 0.5) if fused else None
-    res = torch.randn(n, d, h, w, cout) if fused else None
-    act = 1 if fused else 0
+    res = (torch.randn(n, d, h // 2, w // 2, cout) if up2 else torch.randn(n, d, h, w, cout)) if fused else None
+    act = (1 if fused else 0) | ((1024 | 2048) if up2 else 0)
     y_ref = torch.empty(n, d, h, w, cout)
     EmuBackend().conv_fwd(x, wp, bias, scale, res, y_ref, n, d, h, w, cin, cout, kd, kh, kw, g, act)
     dev = lambda t: None if t is None else t.cuda()
@@ -67,6 +70,9 @@ def test_conv_umma(cuda_backend, shape, variant):
     assert e_simt <= 2e-5 * max(ref_max, 1), f"SIMT err {e_simt:.3e}"
     assert not torch.isnan(y_umma).any(), "tcgen05 path left outputs unwritten"
     assert e_umma <= 4e-3 * max(ref_max, 1), f"tcgen05 err {e_umma:.3e} (ref max {ref_max:.3e}, simt err {e_simt:.3e})"
+    if up2:   # ROUND_OUT: every output is a tf32 value (low 13 mantissa bits zero)
+        for t in (y_umma, y_simt):
+            assert int((t.view(torch.int32) & 0x1fff).abs().max()) == 0
 
 
 # N, D, H, W, Cin, Cout, kd, kh, kw
@@ -145,7 +151,7 @@ PATCH_SHAPES = [
 
 
 @pytest.mark.parametrize("shape", PATCH_SHAPES)
-@pytest.mark.parametrize("variant", ["plain", "fused"])
+@pytest.mark.parametrize("variant", ["plain", "fused", "fusedup2"])
 def test_conv_umma_patch(cuda_backend, shape, variant):
     """Halo-patch persistent kernel (one activation patch feeds all 9 taps) vs fp32 emulator and the plain tcgen05 kernel."""
     n, d, h, w, cin, cout, kd, g = shape
@@ -153,11 +159,12 @@ def test_conv_umma_patch(cuda_backend, shape, variant):
     taps = kd * 9
     x = torch.randn(n, d, h, w, cin)
     wp = torch.randn(taps * cout * cin) / (taps * cin) ** 0.5
-    fused = variant == "fused"
+    fused = variant.startswith("fused")
+    up2 = variant == "fusedup2"
     bias = torch.randn(cout) if fused else None
     scale = (torch.rand(g, cout) + 0.5) if fused else None
-    res = torch.randn(n, d, h, w, cout) if fused else None
-    act = 1 if fused else 0
+    res = (torch.randn(n, d, h // 2, w // 2, cout) if up2 else torch.randn(n, d, h, w, cout)) if fused else None
+    act = (1 if fused else 0) | ((1024 | 2048) if up2 else 0)
     y_ref = torch.empty(n, d, h, w, cout)
     EmuBackend().conv_fwd(x, wp, bias, scale, res, y_ref, n, d, h, w, cin, cout, kd, 3, 3, g, act)
     dev = lambda t: None if t is None else t.cuda()
