@@ -138,9 +138,12 @@ int dgmr_bn_apply(const float* x, const float* a, const float* b, float* y, int6
 int dgmr_bn_bwd_reduce(const float* dy, const float* x, const float* a, const float* b, const float* mean,
                        const float* invstd, double* red /*[G][C][2], zeroed inside*/, int64_t rows, int G, int C,
                        int relu, int up2, int H, int W, dgmr_stream_t stream);
-/* dx (training: full batch-stat backward; eval: a*dpre); dgamma/dbeta [C] (+= if accumulate) */
+/* dx (training: full batch-stat backward; eval: a*dpre); dgamma/dbeta [C] (+= if accumulate).
+ * out_scale (nullable, [G][C]): dx is multiplied by it, and with relu | DGMR_FLAG_ROUND_TF32 written tf32-rounded -- when the BatchNorm
+ * input is the output of a spectrally normalised convolution y = z/sigma_g + b, this IS that convolution's scaled, rounded output
+ * gradient dz (its bias / scale gradients vanish identically under train-mode BatchNorm), so no separate dgmr_conv_bwd_prep pass runs. */
 int dgmr_bn_bwd_apply(const float* dy, const float* x, const float* a, const float* b, const float* mean,
-                      const float* invstd, const float* gamma, const double* red, float* dx, float* dgamma,
+                      const float* invstd, const float* out_scale, const double* red, float* dx, float* dgamma,
                       float* dbeta, int accumulate, int64_t rows, int G, int C, int relu, int up2, int H, int W,
                       int training, dgmr_stream_t stream);
 

@@ -42,6 +42,15 @@ def _conv_bn_relu_eval(conv: SNConv, bn: BatchNorm, x, G: int):
     return ops.conv(x, conv.weight_orig, conv.bias * a + b, scale.contiguous(), None, 0, conv.in_channels, G, ACT_RELU)
 
 
+def _conv_bn_relu_train(conv: SNConv, bn: BatchNorm, x, G: int):
+    """Train mode: relu(bn(conv(x))) as one autograd node (ops._ConvBNRelu): the BatchNorm backward hands the convolution its scaled,
+    rounded output gradient directly."""
+    bn.num_batches_tracked += G
+    scale = conv.scale_of(conv.inv_sigma(G))
+    return ops.conv_bn_relu(x, conv.weight_orig, conv.bias, scale, bn.weight, bn.bias, bn.running_mean, bn.running_var, G,
+                            bn.eps, bn.momentum, conv_only=True)
+
+
 class GBlock(nn.Module):
     """Residual generator block without upsampling (ref: dgmr/common.py:17-84)."""
 
@@ -65,8 +74,7 @@ class GBlock(nn.Module):
         sc = x if x.shape[-1] == self.output_channels else self.conv_1x1.run(x, G)
         y = ops.mark_conv_only(self.bn1.run(x, G, relu=True, conv_only=True))
         if self.training:
-            y = self.first_conv_3x3.run(y, G)
-            y = ops.mark_conv_only(self.bn2.run(y, G, relu=True, conv_only=True))
+            y = ops.mark_conv_only(_conv_bn_relu_train(self.first_conv_3x3, self.bn2, y, G))
         else:
             y = ops.mark_conv_only(_conv_bn_relu_eval(self.first_conv_3x3, self.bn2, y, G))
         return self.last_conv_3x3.run(y, G, res=sc)  # residual add fused in the conv epilogue
@@ -98,8 +106,7 @@ class UpsampleGBlock(nn.Module):
         sc = self.conv_1x1.run(x, G)  # x also feeds BatchNorm: the conv rounds a private copy
         y = ops.mark_conv_only(self.bn1.run(x, G, relu=True, up2=True, conv_only=True))  # BN -> ReLU -> nearest x2 in one pass
         if self.training:
-            y = self.first_conv_3x3.run(y, G)
-            y = ops.mark_conv_only(self.bn2.run(y, G, relu=True, conv_only=True))
+            y = ops.mark_conv_only(_conv_bn_relu_train(self.first_conv_3x3, self.bn2, y, G))
         else:
             y = ops.mark_conv_only(_conv_bn_relu_eval(self.first_conv_3x3, self.bn2, y, G))
         return self.last_conv_3x3.run(y, G, res=sc, res_up2=True)

@@ -544,7 +544,7 @@ __global__ void bn_bwd_reduce4_kernel(const float* __restrict__ dy, const float4
 }
 __global__ void bn_bwd_apply_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ a, const float* __restrict__ b,
                                     const float* __restrict__ mean, const float* __restrict__ invstd, const double* __restrict__ red, float* __restrict__ dx,
-                                    int64_t rows, int G, int C, int relu, int up2, int H, int W, int training) {
+                                    int64_t rows, int G, int C, int relu, int up2, int H, int W, int training, const float* __restrict__ oscale, int rnd) {
   int64_t total = (int64_t)G * rows * C;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     int c = i % C; int64_t r = i / C; int g = r / rows;
@@ -559,7 +559,8 @@ __global__ void bn_bwd_apply_kernel(const float* __restrict__ dy, const float* _
     } else {
       v = aa * d;
     }
-    dx[i] = v;
+    if (oscale) v *= oscale[o];
+    dx[i] = rnd ? rna_tf32_pw(v) : v;
   }
 }
 // float4 variant (C % 4 == 0): one thread per 4 channels of one low-res row
@@ -567,7 +568,7 @@ __global__ void bn_bwd_apply_kernel(const float* __restrict__ dy, const float* _
 template <typename I>
 __global__ void bn_bwd_apply4_kernel(const float* __restrict__ dy, const float4* __restrict__ x, const float4* __restrict__ a, const float4* __restrict__ b,
                                      const float4* __restrict__ mean, const float4* __restrict__ invstd, const double* __restrict__ red, float4* __restrict__ dx,
-                                     int64_t rows, int G, int C4, int relu, int up2, int H, int W, int training) {
+                                     int64_t rows, int G, int C4, int relu, int up2, int H, int W, int training, const float4* __restrict__ oscale, int rnd) {
   const int C = C4 * 4;
   const I total = (I)G * (I)rows * C4;
   for (I i = blockIdx.x * (I)blockDim.x + threadIdx.x; i < total; i += (I)gridDim.x * blockDim.x) {
@@ -604,6 +605,8 @@ __global__ void bn_bwd_apply4_kernel(const float* __restrict__ dy, const float4*
     } else {
       v = make_float4(aa.x * d.x, aa.y * d.y, aa.z * d.z, aa.w * d.w);
     }
+    if (oscale) { const float4 os = oscale[o4]; v.x *= os.x; v.y *= os.y; v.z *= os.z; v.w *= os.w; }
+    if (rnd) v = make_float4(rna_tf32_pw(v.x), rna_tf32_pw(v.y), rna_tf32_pw(v.z), rna_tf32_pw(v.w));
     dx[i] = v;
   }
 }
@@ -970,21 +973,23 @@ int dgmr_bn_bwd_reduce(const float* dy, const float* x, const float* a, const fl
   DGMR_CHECK_LAUNCH("dgmr_bn_bwd_reduce");
   return 0;
 }
-int dgmr_bn_bwd_apply(const float* dy, const float* x, const float* a, const float* b, const float* mean, const float* invstd, const float* gamma,
+int dgmr_bn_bwd_apply(const float* dy, const float* x, const float* a, const float* b, const float* mean, const float* invstd, const float* out_scale,
                       const double* red, float* dx, float* dgamma, float* dbeta, int accumulate, int64_t rows, int G, int C, int relu, int up2,
                       int H, int W, int training, dgmr_stream_t stream) {
-  (void)gamma;
+  const int rnd = (relu & DGMR_FLAG_ROUND_TF32) ? 1 : 0;
+  relu &= ~DGMR_FLAG_ROUND_TF32;
+  const float* oscale = out_scale;
   int64_t total = (int64_t)G * rows * C;
   if (dx && total) {
-    if (C % 4 == 0 && al16(dy) && al16(x) && al16(dx) && al16(a) && al16(b) && al16(mean) && al16(invstd))
+    if (C % 4 == 0 && al16(dy) && al16(x) && al16(dx) && al16(a) && al16(b) && al16(mean) && al16(invstd) && al16(oscale))
       if (total * (up2 ? 4 : 1) < (int64_t)1 << 31)
         bn_bwd_apply4_kernel<uint32_t><<<ew_grid(total / 4, 256, 1), 256, 0, S(stream)>>>(dy, (const float4*)x, (const float4*)a, (const float4*)b, (const float4*)mean,
-                                                                                         (const float4*)invstd, red, (float4*)dx, rows, G, C / 4, relu, up2, H, W, training);
+                                                                                         (const float4*)invstd, red, (float4*)dx, rows, G, C / 4, relu, up2, H, W, training, (const float4*)oscale, rnd);
       else
         bn_bwd_apply4_kernel<int64_t><<<ew_grid(total / 4, 256, 1), 256, 0, S(stream)>>>(dy, (const float4*)x, (const float4*)a, (const float4*)b, (const float4*)mean,
-                                                                                        (const float4*)invstd, red, (float4*)dx, rows, G, C / 4, relu, up2, H, W, training);
+                                                                                        (const float4*)invstd, red, (float4*)dx, rows, G, C / 4, relu, up2, H, W, training, (const float4*)oscale, rnd);
     else
-      bn_bwd_apply_kernel<<<ew_grid(total, 256, 2), 256, 0, S(stream)>>>(dy, x, a, b, mean, invstd, red, dx, rows, G, C, relu, up2, H, W, training);
+      bn_bwd_apply_kernel<<<ew_grid(total, 256, 2), 256, 0, S(stream)>>>(dy, x, a, b, mean, invstd, red, dx, rows, G, C, relu, up2, H, W, training, oscale, rnd);
     DGMR_CHECK_LAUNCH("dgmr_bn_bwd_apply");
   }
   if (dgamma || dbeta) {

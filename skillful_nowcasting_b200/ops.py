@@ -789,13 +789,96 @@ class _BatchNorm(Function):
         dx = _new(x.shape, x) if ctx.needs_input_grad[0] else None
         dgamma = _new((c,), x) if (gamma is not None and ctx.needs_input_grad[1]) else None
         dbeta = _new((c,), x) if (gamma is not None and ctx.needs_input_grad[2]) else None
-        be.bn_bwd_apply(dy, x, a, b, mean, invstd, gamma, red, dx, dgamma, dbeta, False, rows, G, c, relu_, up2, h, w, training)
+        be.bn_bwd_apply(dy, x, a, b, mean, invstd, None, red, dx, dgamma, dbeta, False, rows, G, c, relu_, up2, h, w, training)
         return dx, dgamma, dbeta, None, None, None, None, None, None, None, None, None
 
 
 def batch_norm(x, gamma, beta, rmean, rvar, G, training, relu_=False, up2=False, eps=1e-5, momentum=0.1, conv_only=False):
     """conv_only: the result is consumed by convolutions only, so it may be emitted tf32-rounded straight away."""
     return _BatchNorm.apply(x, gamma, beta, rmean, rvar, G, training, relu_, up2, eps, momentum, conv_only)
+
+
+class _ConvBNRelu(Function):
+    """relu(BN_train(conv(x, w) * scale[g] + bias)) as ONE autograd node (GBlock / UpsampleGBlock: first_conv_3x3 -> bn2 -> ReLU,
+    ref: dgmr/common.py:76-80, 146-151), train mode only.
+
+    Fusing the two nodes is what makes the backward cheap: under batch-statistics BatchNorm the loss cannot depend on a per-channel
+    scale or shift of the BatchNorm input, so the convolution's bias and spectral-norm-scale gradients are IDENTICALLY zero (the
+    reference computes rounding noise there) and its output gradient is the BatchNorm input gradient -- which dgmr_bn_bwd_apply
+    writes already multiplied by scale[g] and tf32-rounded, i.e. as the operand of dgrad / wgrad.  No conv_bwd_prep pass, no
+    <dY, Y - b> reduction, and the conv output is saved once (as the BatchNorm input) instead of twice."""
+
+    @staticmethod
+    def forward(ctx, x, w, bias, scale, gamma, beta, rmean, rvar, cin, G, eps, momentum, conv_only):
+        be = _be()
+        x = _c(x)
+        n, d, h, wd, c = x.shape
+        assert c == cin
+        cout = w.shape[0]
+        ks = tuple(w.shape[2:])
+        kd, kh, kw = (1,) * (3 - len(ks)) + ks
+        rnd = FLAG_ROUND_TF32 if _tc_fwd(n, d, h, wd, c, cout, kd, kh, kw) else 0
+        if rnd and config._dbg_round_act:
+            x = _round_(x)
+        if _x3_fwd(n, d, h, wd, c, cout, kd, kh, kw):
+            rnd = FLAG_SPLIT
+        wp = packed_weight(w, 0, cin, rnd)
+        z = _new((n, d, h, wd, cout), x)
+        scale_c, bias_c = _c(scale), _c(bias)
+        _conv_launch(x, wp, bias_c, scale_c, None, z, n, d, h, wd, c, cout, kd, kh, kw, G, ACT_NONE)
+        rows = (n // G) * d * h * wd
+        if rows <= 1:
+            raise ValueError("Expected more than 1 value per channel when training")
+        sums = _new((G, cout, 2), x, torch.float64)
+        be.bn_stats(z, sums, rows, G, cout)
+        mean, invstd, a, b = (_new((G, cout), x) for _ in range(4))
+        be.bn_finalize(sums, gamma, beta, rmean, rvar, rows, G, cout, eps, momentum, True, mean, invstd, a, b)
+        y = _new(z.shape, x)
+        out_rnd = conv_only and _rounding_on()
+        be.bn_apply(z, a, b, y, rows, G, cout, 1 | (FLAG_ROUND_TF32 if out_rnd else 0), False, h, wd)
+        if out_rnd:
+            y._dgmr_tf32 = True
+        ctx.save_for_backward(x, w, scale_c, z, gamma, a, b, mean, invstd)
+        ctx.meta = (cin, G, (kd, kh, kw))
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w, scale, z, gamma, a, b, mean, invstd = ctx.saved_tensors
+        cin, G, (kd, kh, kw) = ctx.meta
+        be = _be()
+        dy = _c(dy)
+        n, d, h, wd, c = x.shape
+        cout = w.shape[0]
+        rows = (n // G) * d * h * wd
+        need_x, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        red = _new((G, cout, 2), x, torch.float64)
+        be.bn_bwd_reduce(dy, z, a, b, mean, invstd, red, rows, G, cout, True, False, h, wd)
+        tc_bwd = (need_x and _tc_fwd(n, d, h, wd, cout, c, kd, kh, kw)) or (need_w and _tc_wgrad(n, d, h, wd, c, cout, kd, kh, kw))
+        dz = _new(z.shape, x) if (need_x or need_w) else None       # = dL/dz * scale[g], tf32-rounded: the dgrad / wgrad operand
+        dgamma = _new((cout,), x) if ctx.needs_input_grad[4] else None
+        dbeta = _new((cout,), x) if ctx.needs_input_grad[5] else None
+        be.bn_bwd_apply(dy, z, a, b, mean, invstd, scale, red, dz, dgamma, dbeta, False, rows, G, cout,
+                        1 | (FLAG_ROUND_TF32 if (tc_bwd and config._dbg_round_dz) else 0), False, h, wd, True)
+        dx = dw = None
+        if need_x:
+            rnd = FLAG_ROUND_TF32 if (_tc_fwd(n, d, h, wd, cout, c, kd, kh, kw) and config._dbg_round_w) else 0
+            if _x3_fwd(n, d, h, wd, cout, c, kd, kh, kw):
+                rnd = FLAG_SPLIT
+            dx = _new(x.shape, x)
+            _conv_launch(dz, packed_weight(w, 0, cin, 1 | rnd), None, None, None, dx, n, d, h, wd, cout, c, kd, kh, kw, 1, ACT_NONE)
+        if need_w:
+            taps = kd * kh * kw
+            dwp = _new((taps * cout * c,), x)
+            _wgrad_launch(x, dz, dwp, n, d, h, wd, c, cout, kd, kh, kw)
+            dw = _new(w.shape, x)
+            be.unpack_wgrad(dwp, dw, cout, w.shape[1], 0, cin, taps, False)
+        # bias and scale gradients: identically zero (None = zero for autograd; the flat gradient buffers keep their zeros)
+        return dx, dw, None, None, dgamma, dbeta, None, None, None, None, None, None, None
+
+
+def conv_bn_relu(x, w, bias, scale, gamma, beta, rmean, rvar, G, eps=1e-5, momentum=0.1, conv_only=False):
+    return _ConvBNRelu.apply(x, w, bias, scale, gamma, beta, rmean, rvar, w.shape[1], G, eps, momentum, conv_only)
 
 
 # ----------------------------------------------------------------------------- ConvGRU gate arithmetic

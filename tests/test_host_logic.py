@@ -113,8 +113,10 @@ def test_dgmr_training_step_runs_reference_schedule(emu):
     assert all(torch.isfinite(v) and v.dim() == 0 for v in model.logged.values())
     g_changed = sum(not torch.equal(a, b) for a, b in zip(g_before, model.generator.parameters()))
     d_changed = sum(not torch.equal(a, b) for a, b in zip(d_before, model.discriminator.parameters()))
-    # parameters that never receive gradients stay put (g*.conv_1x1 w+b; attention q/k/v/out while gamma == 0)
-    assert g_changed >= len(g_before) - 12 and d_changed >= 30, (g_changed, len(g_before), d_changed, len(d_before))
+    # parameters that never receive gradients stay put (g*.conv_1x1 w+b; attention q/k/v/out while gamma == 0),
+    # and so do the 8 first_conv_3x3 biases in front of a train-mode BatchNorm: their gradient is identically zero and is not
+    # produced at all here (ops._ConvBNRelu), while the reference random-walks them on rounding noise
+    assert g_changed >= len(g_before) - 20 and d_changed >= 30, (g_changed, len(g_before), d_changed, len(d_before))
     assert model(x).shape == (2, 2, 1, 128, 128)
 
 
