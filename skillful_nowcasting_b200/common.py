@@ -134,6 +134,18 @@ class DBlock(nn.Module):
         proj = [(self.conv_1x1, G)] if self.input_channels != self.output_channels else []
         return proj + [(self.first_conv_3x3, G), (self.last_conv_3x3, G)]
 
+    def _first_conv_depth_folded(self, x, G):
+        """3x3x3 convolution over a few-channel input (first temporal-discriminator block, 4 channels carried as 8) with its three
+        depth taps folded into the channel axis: x' = [x(d-1) | x(d) | x(d+1)] (12 real channels in 16), weight [Cout, kd*Cin + ci, kh, kw],
+        a 1x3x3 convolution with K = 9*16 instead of 27*8 half-empty -- same products, same sums; 1.5x fewer forward MMAs and 3x
+        fewer weight-gradient MMAs (its weight gradient ran at 24 TF/s)."""
+        conv, cin = self.first_conv_3x3, self.input_channels
+        w = conv.weight_orig                                               # [Cout, Cin, 3, 3, 3]
+        wf = w.permute(0, 2, 1, 3, 4).reshape(w.shape[0], 3 * cin, 3, 3)   # [Cout, kd*Cin + ci, kh, kw] (differentiable view algebra)
+        xf = ops.mark_conv_only(ops.fold_depth3(x, cin))
+        scale = conv.scale_of(conv.inv_sigma(G))
+        return ops.conv(xf, wf, conv.bias, scale, None, 0, 3 * cin, G, ACT_RELU, round_out=True)
+
     def run(self, x, G: int = 1):
         if self.input_channels != self.output_channels:
             # x is read by convolutions and by ReLU only (ReLU commutes with tf32 rounding): rounding in place is exact
@@ -145,7 +157,10 @@ class DBlock(nn.Module):
             x1 = x
         y = ops.mark_conv_only(ops.relu(x)) if self.first_relu else x
         # the ReLU between the convs is fused, and the result (read by last_conv_3x3 only) leaves the epilogue tf32-rounded
-        y = ops.mark_conv_only(self.first_conv_3x3.run(y, G, act=ACT_RELU, round_out=True))
+        if self.conv_type == "3d" and self.input_channels <= 8 and x.shape[-1] == ops.pad8(self.input_channels) and x.shape[1] >= 3:
+            y = ops.mark_conv_only(self._first_conv_depth_folded(y, G))
+        else:
+            y = ops.mark_conv_only(self.first_conv_3x3.run(y, G, act=ACT_RELU, round_out=True))
         if self.keep_same_output:
             return self.last_conv_3x3.run(y, G, res=x1)
         y = self._pool(self.last_conv_3x3.run(y, G))

@@ -210,7 +210,9 @@ constexpr int kUmmaThreads = 192;  // warp0 TMA, warp1 MMA, warps 2..5 epilogue
 // X3: 3xTF32 error-compensated operands (DGMR_PREC_3XTF32).  Every stage carries the hi and the lo part of both tiles (tmA/tmB describe
 // the hi tensors, tmAlo/tmBlo the lo tensors) and every k-step issues lo*hi, hi*lo, hi*hi into the same fp32 accumulator (small terms
 // first); the dropped lo*lo term is ~2^-22 relative.
-template <int BK, bool X3>
+// EF: the epilogue flags (DGMR_FLAG_ROUND_OUT / DGMR_FLAG_RES_UP2) are compiled in.  They cost 8 registers and, measured, 10-28 % on the
+// launches that are all epilogue (Cout <= 48, many tiles), so the common instantiation does not carry them.
+template <int BK, bool X3, bool EF>
 __global__ void __launch_bounds__(kUmmaThreads, 1)
 conv_umma_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmAlo,
                      const __grid_constant__ CUtensorMap tmBlo, const UmmaConvParams p) {
@@ -366,7 +368,7 @@ conv_umma_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         const int wj = w0 + rj % p.bw, hj = h0 + (rj / p.bw) % p.bh, nj = n0 + rj / (p.bw * p.bh);
         vrow[j] = (nj < p.N) && (hj < p.H) && (wj < p.W);
         mrow[j] = ((((int64_t)nj * p.D + d0) * p.H + hj) * p.W + wj) * p.Cout + co0 + 4 * lc;
-        rrow[j] = p.res_up2 ? ((((int64_t)nj * p.D + d0) * (p.H >> 1) + (hj >> 1)) * (p.W >> 1) + (wj >> 1)) * p.Cout + co0 + 4 * lc : mrow[j];
+        rrow[j] = (EF && p.res_up2) ? ((((int64_t)nj * p.D + d0) * (p.H >> 1) + (hj >> 1)) * (p.W >> 1) + (wj >> 1)) * p.Cout + co0 + 4 * lc : mrow[j];
         srow[j] = (p.scale && vrow[j]) ? p.scale + (int64_t)(nj / (p.N / p.G)) * p.Cout : nullptr;
       }
       float4 rr[4];
@@ -407,7 +409,7 @@ conv_umma_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
             if (p.res) { o.x += rr[j].x; o.y += rr[j].y; o.z += rr[j].z; o.w += rr[j].w; }
             if (p.act == DGMR_ACT_RELU) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-            if (p.round_out) o = rna_tf32_e4(o);
+            if (EF && p.round_out) o = rna_tf32_e4(o);
             *reinterpret_cast<float4*>(p.y + mrow[j] + c) = o;
           }
         }
@@ -432,7 +434,7 @@ conv_umma_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         }
       }
       float* yp = p.y + m * p.Cout + co0 + c;
-      const int64_t mres = p.res_up2 ? (((int64_t)n * p.D + d0) * (p.H >> 1) + (h >> 1)) * (p.W >> 1) + (w >> 1) : m;
+      const int64_t mres = (EF && p.res_up2) ? (((int64_t)n * p.D + d0) * (p.H >> 1) + (h >> 1)) * (p.W >> 1) + (w >> 1) : m;
       const float* rp = p.res ? p.res + mres * p.Cout + co0 + c : nullptr;
       if (p.split_taps) {
 #pragma unroll
@@ -447,7 +449,7 @@ conv_umma_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
             if (rp) { float4 rr = *reinterpret_cast<const float4*>(rp + j); o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w; }
             if (p.act == DGMR_ACT_RELU) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-            if (p.round_out) o = rna_tf32_e4(o);
+            if (EF && p.round_out) o = rna_tf32_e4(o);
             *reinterpret_cast<float4*>(yp + j) = o;
           }
         }
@@ -458,7 +460,7 @@ conv_umma_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             float o = v[j];
             if (rp) o += rp[j];
             if (p.act == DGMR_ACT_RELU) o = fmaxf(o, 0.f);
-            yp[j] = p.round_out ? rna_tf32_e(o) : o;
+            yp[j] = (EF && p.round_out) ? rna_tf32_e(o) : o;
           }
         }
       }
@@ -477,7 +479,7 @@ conv_umma_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 // pipeline fill are paid once per CTA instead of once per 128-pixel tile, the K-block stream of consecutive tiles is continuous
 // and the accumulator is double-buffered in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.  For launches with
 // many tiles and a short K loop (1x1 convs, narrow layers) the per-tile fixed cost was most of the time.
-template <int BK>
+template <int BK, bool EF>
 __global__ void __launch_bounds__(kUmmaThreads, 1)
 conv_umma_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const UmmaConvParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -603,7 +605,7 @@ conv_umma_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __gr
         const int wj = w0 + rj % p.bw, hj = h0 + (rj / p.bw) % p.bh, nj = n0 + rj / (p.bw * p.bh);
         vrow[j] = (nj < p.N) && (hj < p.H) && (wj < p.W);
         mrow[j] = ((((int64_t)nj * p.D + d0) * p.H + hj) * p.W + wj) * p.Cout + co0 + 4 * lc;
-        rrow[j] = p.res_up2 ? ((((int64_t)nj * p.D + d0) * (p.H >> 1) + (hj >> 1)) * (p.W >> 1) + (wj >> 1)) * p.Cout + co0 + 4 * lc : mrow[j];
+        rrow[j] = (EF && p.res_up2) ? ((((int64_t)nj * p.D + d0) * (p.H >> 1) + (hj >> 1)) * (p.W >> 1) + (wj >> 1)) * p.Cout + co0 + 4 * lc : mrow[j];
         srow[j] = (p.scale && vrow[j]) ? p.scale + (int64_t)(nj / (p.N / p.G)) * p.Cout : nullptr;
       }
       float4 rr[4];
@@ -643,7 +645,7 @@ conv_umma_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __gr
             o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
             if (p.res) { o.x += rr[j].x; o.y += rr[j].y; o.z += rr[j].z; o.w += rr[j].w; }
             if (p.act == DGMR_ACT_RELU) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-            if (p.round_out) o = rna_tf32_e4(o);
+            if (EF && p.round_out) o = rna_tf32_e4(o);
             *reinterpret_cast<float4*>(p.y + mrow[j] + c) = o;
           }
         }
@@ -1472,14 +1474,13 @@ int launch_conv_umma_fwd(const float* x, const float* wp, const float* bias, con
   static bool attr_set = false;
   if (!attr_set) {
     const int lim = 220 * 1024;
-    if (cudaFuncSetAttribute(conv_umma_fwd_kernel<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim) != cudaSuccess ||
-        cudaFuncSetAttribute(conv_umma_fwd_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim) != cudaSuccess ||
-        cudaFuncSetAttribute(conv_umma_fwd_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim) != cudaSuccess ||
-        cudaFuncSetAttribute(conv_umma_fwd_kernel<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim) != cudaSuccess ||
-        cudaFuncSetAttribute(conv_umma_fwd_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim) != cudaSuccess ||
-        cudaFuncSetAttribute(conv_umma_fwd_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim) != cudaSuccess) {
-      set_error("conv_umma_fwd: cannot raise dynamic smem limit"); return 2;
-    }
+    bool ok = true;
+#define DGMR_SET(K) ok = ok && cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, lim) == cudaSuccess
+    DGMR_SET((conv_umma_fwd_kernel<32, false, false>)); DGMR_SET((conv_umma_fwd_kernel<16, false, false>)); DGMR_SET((conv_umma_fwd_kernel<8, false, false>));
+    DGMR_SET((conv_umma_fwd_kernel<32, false, true>)); DGMR_SET((conv_umma_fwd_kernel<16, false, true>)); DGMR_SET((conv_umma_fwd_kernel<8, false, true>));
+    DGMR_SET((conv_umma_fwd_kernel<32, true, false>)); DGMR_SET((conv_umma_fwd_kernel<16, true, false>)); DGMR_SET((conv_umma_fwd_kernel<8, true, false>));
+#undef DGMR_SET
+    if (!ok) { set_error("conv_umma_fwd: cannot raise dynamic smem limit"); return 2; }
     attr_set = true;
   }
   int64_t mtiles = ceil_div(N, p.bn) * D * p.tiles_h * p.tiles_w;
@@ -1512,30 +1513,36 @@ int launch_conv_umma_fwd(const float* x, const float* wp, const float* bias, con
       if (psmem < floor_smem) psmem = floor_smem;
       static bool pattr = false;
       if (!pattr) {
-        if (cudaFuncSetAttribute(conv_umma_fwd_persist_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)) != cudaSuccess ||
-            cudaFuncSetAttribute(conv_umma_fwd_persist_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)) != cudaSuccess ||
-            cudaFuncSetAttribute(conv_umma_fwd_persist_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)) != cudaSuccess) {
-          set_error("conv_umma_fwd: cannot raise dynamic smem limit"); return 2;
-        }
+        bool ok = true;
+#define DGMR_SET(K) ok = ok && cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)) == cudaSuccess
+        DGMR_SET((conv_umma_fwd_persist_kernel<32, false>)); DGMR_SET((conv_umma_fwd_persist_kernel<16, false>)); DGMR_SET((conv_umma_fwd_persist_kernel<8, false>));
+        DGMR_SET((conv_umma_fwd_persist_kernel<32, true>)); DGMR_SET((conv_umma_fwd_persist_kernel<16, true>)); DGMR_SET((conv_umma_fwd_persist_kernel<8, true>));
+#undef DGMR_SET
+        if (!ok) { set_error("conv_umma_fwd: cannot raise dynamic smem limit"); return 2; }
         pattr = true;
       }
       int64_t g = (int64_t)sm_count() * R;
       if (g > mtiles * ntiles) g = mtiles * ntiles;
-      if (p.BK == 32) conv_umma_fwd_persist_kernel<32><<<(unsigned)g, kUmmaThreads, psmem, st>>>(tmA, tmB, p);
-      else if (p.BK == 16) conv_umma_fwd_persist_kernel<16><<<(unsigned)g, kUmmaThreads, psmem, st>>>(tmA, tmB, p);
-      else conv_umma_fwd_persist_kernel<8><<<(unsigned)g, kUmmaThreads, psmem, st>>>(tmA, tmB, p);
+      const bool pef = p.round_out || p.res_up2;
+#define DGMR_GO(BKV, EFV) conv_umma_fwd_persist_kernel<BKV, EFV><<<(unsigned)g, kUmmaThreads, psmem, st>>>(tmA, tmB, p)
+      if (pef) { if (p.BK == 32) DGMR_GO(32, true); else if (p.BK == 16) DGMR_GO(16, true); else DGMR_GO(8, true); }
+      else { if (p.BK == 32) DGMR_GO(32, false); else if (p.BK == 16) DGMR_GO(16, false); else DGMR_GO(8, false); }
+#undef DGMR_GO
       DGMR_CHECK_LAUNCH("conv_umma_fwd_persist");
       return 0;
     }
   }
   dim3 grid((unsigned)mtiles, (unsigned)ntiles, (unsigned)(accumulate ? taps : 1));
-  if (x3) {
-    if (p.BK == 32) conv_umma_fwd_kernel<32, true><<<grid, kUmmaThreads, smem, st>>>(tmA, tmB, tmAlo, tmBlo, p);
-    else if (p.BK == 16) conv_umma_fwd_kernel<16, true><<<grid, kUmmaThreads, smem, st>>>(tmA, tmB, tmAlo, tmBlo, p);
-    else conv_umma_fwd_kernel<8, true><<<grid, kUmmaThreads, smem, st>>>(tmA, tmB, tmAlo, tmBlo, p);
-  } else if (p.BK == 32) conv_umma_fwd_kernel<32, false><<<grid, kUmmaThreads, smem, st>>>(tmA, tmB, tmAlo, tmBlo, p);
-  else if (p.BK == 16) conv_umma_fwd_kernel<16, false><<<grid, kUmmaThreads, smem, st>>>(tmA, tmB, tmAlo, tmBlo, p);
-  else conv_umma_fwd_kernel<8, false><<<grid, kUmmaThreads, smem, st>>>(tmA, tmB, tmAlo, tmBlo, p);
+  const bool ef = p.round_out || p.res_up2;
+#define DGMR_GO(BKV, X3V, EFV) conv_umma_fwd_kernel<BKV, X3V, EFV><<<grid, kUmmaThreads, smem, st>>>(tmA, tmB, tmAlo, tmBlo, p)
+  if (x3) {   // (ROUND_OUT is refused in 3xTF32 mode; RES_UP2 falls back to the unfused upsample there: see dgmr_conv_fwd)
+    if (p.BK == 32) DGMR_GO(32, true, false); else if (p.BK == 16) DGMR_GO(16, true, false); else DGMR_GO(8, true, false);
+  } else if (ef) {
+    if (p.BK == 32) DGMR_GO(32, false, true); else if (p.BK == 16) DGMR_GO(16, false, true); else DGMR_GO(8, false, true);
+  } else {
+    if (p.BK == 32) DGMR_GO(32, false, false); else if (p.BK == 16) DGMR_GO(16, false, false); else DGMR_GO(8, false, false);
+  }
+#undef DGMR_GO
   DGMR_CHECK_LAUNCH("conv_umma_fwd");
   return 0;
 }

@@ -137,6 +137,48 @@ def space_to_depth(x: torch.Tensor, pad: bool = True) -> torch.Tensor:
                    (ss[0], ss[1], 2 * ss[2], 2 * ss[3], 1, ss[2], ss[3]), (ds[0], ds[1], ds[2], ds[3], 4, 2, 1))
 
 
+class _FoldDepth3(Function):
+    """x [N,D,H,W,Cp] (first `c` channels real) -> [N,D,H,W,pad8(3c)] with channel kd*c + i = x[d + kd - 1][i] (zero outside the depth
+    range): the depth taps of a 3x3x3 convolution over a FEW-channel input folded into the channel axis, so that the convolution becomes
+    a 1x3x3 one with 3c input channels (first temporal-discriminator block: 4 -> 12 real channels in 16 instead of 27 taps x 8 half-empty
+    channels; ref: dgmr/discriminators.py:113, common.py:187-191).  Pure index map: bit-exact."""
+
+    @staticmethod
+    def forward(ctx, x, c):
+        x = _c(x)
+        n, d, h, w, cp = x.shape
+        co = pad8(3 * c)
+        out = _zeros((n, d, h, w, co), x)
+        hw = h * w
+        for kd in range(3):
+            sh = kd - 1                                   # out[d] <- x[d + sh]
+            d0, d1 = max(0, -sh), min(d, d - sh)          # valid output depths
+            if d1 > d0:
+                _be().permute(x, out, (n, d1 - d0, hw, c), (d * hw * cp, hw * cp, cp, 1), (d * hw * co, hw * co, co, 1), False,
+                              (d0 + sh) * hw * cp, d0 * hw * co + kd * c)
+        ctx.meta = (tuple(x.shape), c)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (n, d, h, w, cp), c = ctx.meta
+        g = _c(g)
+        co = g.shape[-1]
+        gx = _zeros((n, d, h, w, cp), g)
+        hw = h * w
+        for kd in range(3):
+            sh = kd - 1
+            d0, d1 = max(0, -sh), min(d, d - sh)
+            if d1 > d0:
+                _be().permute(g, gx, (n, d1 - d0, hw, c), (d * hw * co, hw * co, co, 1), (d * hw * cp, hw * cp, cp, 1), True,
+                              d0 * hw * co + kd * c, (d0 + sh) * hw * cp)
+        return gx, None
+
+
+def fold_depth3(x, c):
+    return _FoldDepth3.apply(x, c)
+
+
 class _ConcatC(Function):
     @staticmethod
     def forward(ctx, a, b):

@@ -286,7 +286,8 @@ def test_graphed_generator_matches_eager_and_oracle(cuda_backend, c1_state):
     assert rel_err(out_g, out_e) < 3e-3          # run-to-run noise floor of the 1xTF32 path (see test_pretrained_round_trip_on_gpu): 5.4e-4
     ref = oracle_gan_forward(g0, d0, x, y, C1, False, seed=2)
     assert rel_err(out_g, ref["out"]) < 1e-3
-    torch.manual_seed(3)                      # a second replay with another latent draw really changes the forecast
-    out_g2 = runner(xc)
-    assert rel_err(out_g2, out_e) > 1e-3
+    torch.manual_seed(3)                      # a second replay takes a fresh latent draw (the reference's CPU RNG order) into the static buffer
+    runner(xc)
+    torch.manual_seed(3)
+    assert torch.equal(runner.z, gen.latent_stack.sample_z(xc))
     gen.cpu()
