@@ -141,11 +141,13 @@ int dgmr_bn_bwd_reduce(const float* dy, const float* x, const float* a, const fl
 /* dx (training: full batch-stat backward; eval: a*dpre); dgamma/dbeta [C] (+= if accumulate).
  * out_scale (nullable, [G][C]): dx is multiplied by it, and with relu | DGMR_FLAG_ROUND_TF32 written tf32-rounded -- when the BatchNorm
  * input is the output of a spectrally normalised convolution y = z/sigma_g + b, this IS that convolution's scaled, rounded output
- * gradient dz (its bias / scale gradients vanish identically under train-mode BatchNorm), so no separate dgmr_conv_bwd_prep pass runs. */
+ * gradient dz (its bias / scale gradients vanish identically under train-mode BatchNorm), so no separate dgmr_conv_bwd_prep pass runs.
+ * dx_add (nullable, same shape as dx): added to dx before the optional rounding -- the gradient that reaches the BatchNorm input through its
+ * OTHER consumer (the residual shortcut of GBlock / UpsampleGBlock, ref: dgmr/common.py:70-84), instead of a separate accumulation pass. */
 int dgmr_bn_bwd_apply(const float* dy, const float* x, const float* a, const float* b, const float* mean,
-                      const float* invstd, const float* out_scale, const double* red, float* dx, float* dgamma,
-                      float* dbeta, int accumulate, int64_t rows, int G, int C, int relu, int up2, int H, int W,
-                      int training, dgmr_stream_t stream);
+                      const float* invstd, const float* out_scale, const double* red, float* dx, const float* dx_add,
+                      float* dgamma, float* dbeta, int accumulate, int64_t rows, int G, int C, int relu, int up2, int H,
+                      int W, int training, dgmr_stream_t stream);
 
 /* ---- spectral norm (ref: torch/nn/utils/parametrizations.py:495-527, applied at
  * dgmr/layers/ConvGRU.py:29-55, common.py:43-66,113-137,192-215,350-384,451-455,

@@ -244,10 +244,11 @@ class CudaBackend:
         self._call("dgmr_bn_bwd_reduce", _f32(dy, "dy"), _f32(x, "x"), _f32(a, "a"), _f32(b, "b"), _f32(mean, "mean"),
                    _f32(invstd, "invstd"), _f64(red, "red"), rows, G, C, int(relu), int(up2), H, W)
 
-    def bn_bwd_apply(self, dy, x, a, b, mean, invstd, out_scale, red, dx, dgamma, dbeta, accumulate, rows, G, C, relu, up2, H, W, training):
-        """relu may carry FLAG_ROUND_TF32 (dx written tf32-rounded); out_scale [G, C] (nullable) multiplies dx."""
+    def bn_bwd_apply(self, dy, x, a, b, mean, invstd, out_scale, red, dx, dgamma, dbeta, accumulate, rows, G, C, relu, up2, H, W, training,
+                     dx_add=None):
+        """relu may carry FLAG_ROUND_TF32 (dx written tf32-rounded); out_scale [G, C] (nullable) multiplies dx; dx_add (nullable) is added."""
         self._call("dgmr_bn_bwd_apply", _f32(dy, "dy"), _f32(x, "x"), _f32(a, "a"), _f32(b, "b"), _f32(mean, "mean"),
-                   _f32(invstd, "invstd"), _f32(out_scale, "out_scale"), _f64(red, "red"), _f32(dx, "dx"), _f32(dgamma, "dgamma"),
+                   _f32(invstd, "invstd"), _f32(out_scale, "out_scale"), _f64(red, "red"), _f32(dx, "dx"), _f32(dx_add, "dx_add"), _f32(dgamma, "dgamma"),
                    _f32(dbeta, "dbeta"), int(accumulate), rows, G, C, int(relu), int(up2), H, W, int(training), _info=f"rows{rows} G{G} C{C} up{int(up2)}")
 
     # -- spectral norm

@@ -71,8 +71,9 @@ class GBlock(nn.Module):
         return proj + [(self.first_conv_3x3, G), (self.last_conv_3x3, G)]
 
     def run(self, x, G: int = 1):
-        sc = x if x.shape[-1] == self.output_channels else self.conv_1x1.run(x, G)
-        y = ops.mark_conv_only(self.bn1.run(x, G, relu=True, conv_only=True))
+        y, xs = self.bn1.run(x, G, relu=True, conv_only=True, branch=True)   # xs: x again, for the shortcut (gradients meet in the BN backward)
+        y = ops.mark_conv_only(y)
+        sc = xs if x.shape[-1] == self.output_channels else self.conv_1x1.run(xs, G)
         if self.training:
             y = ops.mark_conv_only(_conv_bn_relu_train(self.first_conv_3x3, self.bn2, y, G))
         else:
@@ -103,8 +104,9 @@ class UpsampleGBlock(nn.Module):
     def run(self, x, G: int = 1):
         # conv1x1(up2(x)) == up2(conv1x1(x)) bit-for-bit (pointwise conv commutes with replication): 4x fewer MACs, and the
         # upsampled shortcut is never materialised: last_conv_3x3's epilogue reads it at (h/2, w/2)
-        sc = self.conv_1x1.run(x, G)  # x also feeds BatchNorm: the conv rounds a private copy
-        y = ops.mark_conv_only(self.bn1.run(x, G, relu=True, up2=True, conv_only=True))  # BN -> ReLU -> nearest x2 in one pass
+        y, xs = self.bn1.run(x, G, relu=True, up2=True, conv_only=True, branch=True)  # BN -> ReLU -> nearest x2 in one pass; xs: x for the shortcut
+        y = ops.mark_conv_only(y)
+        sc = self.conv_1x1.run(xs, G)  # x also feeds BatchNorm: the conv rounds a private copy
         if self.training:
             y = ops.mark_conv_only(_conv_bn_relu_train(self.first_conv_3x3, self.bn2, y, G))
         else:

@@ -1491,6 +1491,12 @@ int launch_conv_umma_fwd(const float* x, const float* wp, const float* bias, con
   // the per-tile fixed cost dominates), neutral to slightly negative on long K loops (fewer CTAs per SM in flight) -> only the former.
   const int num_kb_tile = taps * (int)ceil_div(Cin, p.BK);
   bool persist = !x3 && !accumulate && (Cout % 4 == 0) && 2 * p.BN <= 512 && mtiles * ntiles >= 4 * (int64_t)sm_count() && num_kb_tile <= 12;
+  // ... and small launches of one to eight waves whatever their K loop (the per-step ConvGRU convolutions at 32x32 / 64x64): there the
+  // per-CTA setup is a large part of a 20-40 us kernel.  Measured (tests/time_gru_conv.py, 16 images): 48->96 @64^2 38.7 -> 31.8 us,
+  // 48->48 @64^2 29.5 -> 24.7 us, 96->192 @32^2 26.8 -> 24.8 us, never slower.
+  if (!persist && !x3 && !accumulate && (Cout % 4 == 0) && 2 * p.BN <= 512 && mtiles * ntiles >= (int64_t)sm_count() &&
+      mtiles * ntiles <= 8 * (int64_t)sm_count() && (int64_t)N * D * H * W <= 131072)
+    persist = true;
   if (g_opt.umma_persist >= 0) {   // tuning / test option: 0 = never, 2 = whenever eligible (small test shapes)
     const int v = g_opt.umma_persist;
     if (v == 0) persist = false;

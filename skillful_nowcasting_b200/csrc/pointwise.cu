@@ -544,7 +544,8 @@ __global__ void bn_bwd_reduce4_kernel(const float* __restrict__ dy, const float4
 }
 __global__ void bn_bwd_apply_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ a, const float* __restrict__ b,
                                     const float* __restrict__ mean, const float* __restrict__ invstd, const double* __restrict__ red, float* __restrict__ dx,
-                                    int64_t rows, int G, int C, int relu, int up2, int H, int W, int training, const float* __restrict__ oscale, int rnd) {
+                                    int64_t rows, int G, int C, int relu, int up2, int H, int W, int training, const float* __restrict__ oscale, int rnd,
+                                    const float* __restrict__ dx_add) {
   int64_t total = (int64_t)G * rows * C;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     int c = i % C; int64_t r = i / C; int g = r / rows;
@@ -560,6 +561,7 @@ __global__ void bn_bwd_apply_kernel(const float* __restrict__ dy, const float* _
       v = aa * d;
     }
     if (oscale) v *= oscale[o];
+    if (dx_add) v += dx_add[i];
     dx[i] = rnd ? rna_tf32_pw(v) : v;
   }
 }
@@ -568,7 +570,8 @@ __global__ void bn_bwd_apply_kernel(const float* __restrict__ dy, const float* _
 template <typename I>
 __global__ void bn_bwd_apply4_kernel(const float* __restrict__ dy, const float4* __restrict__ x, const float4* __restrict__ a, const float4* __restrict__ b,
                                      const float4* __restrict__ mean, const float4* __restrict__ invstd, const double* __restrict__ red, float4* __restrict__ dx,
-                                     int64_t rows, int G, int C4, int relu, int up2, int H, int W, int training, const float4* __restrict__ oscale, int rnd) {
+                                     int64_t rows, int G, int C4, int relu, int up2, int H, int W, int training, const float4* __restrict__ oscale, int rnd,
+                                     const float4* __restrict__ dx_add) {
   const int C = C4 * 4;
   const I total = (I)G * (I)rows * C4;
   for (I i = blockIdx.x * (I)blockDim.x + threadIdx.x; i < total; i += (I)gridDim.x * blockDim.x) {
@@ -606,6 +609,7 @@ __global__ void bn_bwd_apply4_kernel(const float* __restrict__ dy, const float4*
       v = make_float4(aa.x * d.x, aa.y * d.y, aa.z * d.z, aa.w * d.w);
     }
     if (oscale) { const float4 os = oscale[o4]; v.x *= os.x; v.y *= os.y; v.z *= os.z; v.w *= os.w; }
+    if (dx_add) { const float4 ad = dx_add[i]; v.x += ad.x; v.y += ad.y; v.z += ad.z; v.w += ad.w; }
     if (rnd) v = make_float4(rna_tf32_pw(v.x), rna_tf32_pw(v.y), rna_tf32_pw(v.z), rna_tf32_pw(v.w));
     dx[i] = v;
   }
@@ -974,22 +978,22 @@ int dgmr_bn_bwd_reduce(const float* dy, const float* x, const float* a, const fl
   return 0;
 }
 int dgmr_bn_bwd_apply(const float* dy, const float* x, const float* a, const float* b, const float* mean, const float* invstd, const float* out_scale,
-                      const double* red, float* dx, float* dgamma, float* dbeta, int accumulate, int64_t rows, int G, int C, int relu, int up2,
-                      int H, int W, int training, dgmr_stream_t stream) {
+                      const double* red, float* dx, const float* dx_add, float* dgamma, float* dbeta, int accumulate, int64_t rows, int G, int C,
+                      int relu, int up2, int H, int W, int training, dgmr_stream_t stream) {
   const int rnd = (relu & DGMR_FLAG_ROUND_TF32) ? 1 : 0;
   relu &= ~DGMR_FLAG_ROUND_TF32;
   const float* oscale = out_scale;
   int64_t total = (int64_t)G * rows * C;
   if (dx && total) {
-    if (C % 4 == 0 && al16(dy) && al16(x) && al16(dx) && al16(a) && al16(b) && al16(mean) && al16(invstd) && al16(oscale))
+    if (C % 4 == 0 && al16(dy) && al16(x) && al16(dx) && al16(a) && al16(b) && al16(mean) && al16(invstd) && al16(oscale) && al16(dx_add))
       if (total * (up2 ? 4 : 1) < (int64_t)1 << 31)
         bn_bwd_apply4_kernel<uint32_t><<<ew_grid(total / 4, 256, 1), 256, 0, S(stream)>>>(dy, (const float4*)x, (const float4*)a, (const float4*)b, (const float4*)mean,
-                                                                                         (const float4*)invstd, red, (float4*)dx, rows, G, C / 4, relu, up2, H, W, training, (const float4*)oscale, rnd);
+                                                                                         (const float4*)invstd, red, (float4*)dx, rows, G, C / 4, relu, up2, H, W, training, (const float4*)oscale, rnd, (const float4*)dx_add);
       else
         bn_bwd_apply4_kernel<int64_t><<<ew_grid(total / 4, 256, 1), 256, 0, S(stream)>>>(dy, (const float4*)x, (const float4*)a, (const float4*)b, (const float4*)mean,
-                                                                                        (const float4*)invstd, red, (float4*)dx, rows, G, C / 4, relu, up2, H, W, training, (const float4*)oscale, rnd);
+                                                                                        (const float4*)invstd, red, (float4*)dx, rows, G, C / 4, relu, up2, H, W, training, (const float4*)oscale, rnd, (const float4*)dx_add);
     else
-      bn_bwd_apply_kernel<<<ew_grid(total, 256, 2), 256, 0, S(stream)>>>(dy, x, a, b, mean, invstd, red, dx, rows, G, C, relu, up2, H, W, training, oscale, rnd);
+      bn_bwd_apply_kernel<<<ew_grid(total, 256, 2), 256, 0, S(stream)>>>(dy, x, a, b, mean, invstd, red, dx, rows, G, C, relu, up2, H, W, training, oscale, rnd, dx_add);
     DGMR_CHECK_LAUNCH("dgmr_bn_bwd_apply");
   }
   if (dgamma || dbeta) {

@@ -164,11 +164,12 @@ class BatchNorm(nn.Module):
         self.register_buffer("running_var", torch.ones(num_features))
         self.register_buffer("num_batches_tracked", torch.tensor(0, dtype=torch.long))
 
-    def run(self, x, G: int = 1, relu: bool = False, up2: bool = False, conv_only: bool = False):
+    def run(self, x, G: int = 1, relu: bool = False, up2: bool = False, conv_only: bool = False, branch: bool = False):
+        """branch: returns (y, x_skip), x_skip being the input for its other consumer (residual shortcut): see ops._BatchNorm."""
         if self.training:
             self.num_batches_tracked += G
         return ops.batch_norm(x, self.weight, self.bias, self.running_mean, self.running_var, G, self.training,
-                              relu, up2, self.eps, self.momentum, conv_only)
+                              relu, up2, self.eps, self.momentum, conv_only, branch)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         if x.dim() == 2:

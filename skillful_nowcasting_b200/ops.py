@@ -797,7 +797,7 @@ class _BatchNorm(Function):
     (ref: dgmr/common.py:74-82,145-153; generators.py:176)."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, rmean, rvar, G, training, relu_, up2, eps, momentum, conv_only=False):
+    def forward(ctx, x, gamma, beta, rmean, rvar, G, training, relu_, up2, eps, momentum, conv_only=False, branch=False):
         be = _be()
         x = _c(x)
         n, d, h, w, c = x.shape
@@ -816,10 +816,15 @@ class _BatchNorm(Function):
             y._dgmr_tf32 = True
         ctx.save_for_backward(x, gamma, a, b, mean, invstd)
         ctx.meta = (G, training, relu_, up2)
+        if branch:
+            # second output: the input itself, for its OTHER consumer (the residual shortcut).  Routing that use through this node means
+            # the two gradients of x meet in backward(), where dgmr_bn_bwd_apply adds the shortcut's while it writes dx -- instead of
+            # autograd accumulating them in a separate read-read-write pass over the activation.
+            return y, x.view_as(x)
         return y
 
     @staticmethod
-    def backward(ctx, dy):
+    def backward(ctx, dy, dskip=None):
         x, gamma, a, b, mean, invstd = ctx.saved_tensors
         G, training, relu_, up2 = ctx.meta
         be = _be()
@@ -831,13 +836,17 @@ class _BatchNorm(Function):
         dx = _new(x.shape, x) if ctx.needs_input_grad[0] else None
         dgamma = _new((c,), x) if (gamma is not None and ctx.needs_input_grad[1]) else None
         dbeta = _new((c,), x) if (gamma is not None and ctx.needs_input_grad[2]) else None
-        be.bn_bwd_apply(dy, x, a, b, mean, invstd, None, red, dx, dgamma, dbeta, False, rows, G, c, relu_, up2, h, w, training)
-        return dx, dgamma, dbeta, None, None, None, None, None, None, None, None, None
+        if dy is None:      # only the shortcut carried a gradient
+            return (_c(dskip) if ctx.needs_input_grad[0] else None), None, None, None, None, None, None, None, None, None, None, None, None
+        be.bn_bwd_apply(dy, x, a, b, mean, invstd, None, red, dx, dgamma, dbeta, False, rows, G, c, relu_, up2, h, w, training,
+                        dx_add=(_c(dskip) if (dskip is not None and dx is not None) else None))
+        return dx, dgamma, dbeta, None, None, None, None, None, None, None, None, None, None
 
 
-def batch_norm(x, gamma, beta, rmean, rvar, G, training, relu_=False, up2=False, eps=1e-5, momentum=0.1, conv_only=False):
-    """conv_only: the result is consumed by convolutions only, so it may be emitted tf32-rounded straight away."""
-    return _BatchNorm.apply(x, gamma, beta, rmean, rvar, G, training, relu_, up2, eps, momentum, conv_only)
+def batch_norm(x, gamma, beta, rmean, rvar, G, training, relu_=False, up2=False, eps=1e-5, momentum=0.1, conv_only=False, branch=False):
+    """conv_only: the result is consumed by convolutions only, so it may be emitted tf32-rounded straight away.
+    branch: returns (y, x_skip) -- x_skip is the input, to be handed to its other consumer (see _BatchNorm.forward)."""
+    return _BatchNorm.apply(x, gamma, beta, rmean, rvar, G, training, relu_, up2, eps, momentum, conv_only, branch)
 
 
 class _ConvBNRelu(Function):

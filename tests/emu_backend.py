@@ -180,7 +180,8 @@ class EmuBackend:
         xh = (x.reshape(G, rows, C) - mean.reshape(G, 1, C)) * invstd.reshape(G, 1, C)
         red.copy_(torch.stack([d.double().sum(1), (d * xh).double().sum(1)], dim=-1))
 
-    def bn_bwd_apply(self, dy, x, a, b, mean, invstd, out_scale, red, dx, dgamma, dbeta, accumulate, rows, G, C, relu, up2, H, W, training):
+    def bn_bwd_apply(self, dy, x, a, b, mean, invstd, out_scale, red, dx, dgamma, dbeta, accumulate, rows, G, C, relu, up2, H, W, training,
+                     dx_add=None):
         rnd, relu = bool(relu & 256), relu & ~256
         d = self._dpre(dy, x, a, b, rows, G, C, relu, up2, H, W)
         if dx is not None:
@@ -193,6 +194,8 @@ class EmuBackend:
                 v = a.reshape(G, 1, C) * d
             if out_scale is not None:
                 v = v * out_scale.reshape(G, 1, C)
+            if dx_add is not None:
+                v = v + dx_add.reshape(v.shape)
             if rnd:
                 v = self._rna_tf32(v.contiguous())
             dx.copy_(v.reshape(dx.shape))
