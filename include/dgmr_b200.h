@@ -221,6 +221,25 @@ int dgmr_conv_bwd_prep(const float* dy, const float* y, const float* res, const 
 int dgmr_conv_wgrad(const float* x, const float* x_lo, const float* dz, const float* dz_lo, float* dwp, int N, int D, int H, int W,
                     int Cin, int Cout, int kd, int kh, int kw, int algo, int precision, dgmr_stream_t stream);
 
+/* ---- "nearest x2 upsample -> 3x3 convolution" in sub-pixel form (ref: UpsampleGBlock.first_conv_3x3 on the upsampled input,
+ * dgmr/common.py:146-149): every output phase (2h+i, 2w+j) is a 2x2-tap convolution of the LOW-resolution input with pre-summed taps --
+ * 16 instead of 36 MACs per low-resolution pixel, and the upsampled activation is never materialised (csrc/conv_subpix.cu).
+ * x: [N,H,W,Cin] low resolution; y, res, dz: [N,2H,2W,Cout]; scale: [G][Cout].  All tensor-core only (no SIMT form): check
+ * dgmr_upconv_supported first and use dgmr_upsample + dgmr_conv_fwd otherwise. */
+int dgmr_upconv_supported(int N, int H, int W, int Cin, int Cout);
+/* w: OIHW [Cout][CinTot][3][3] -> packed[16][Cout][Cin] (mode 0, forward) or packed[16][Cin][Cout] (mode 1, dgrad); tile z = ((i*2+j)*2+a)*2+b holds
+ * sum_{kh in S(i,a), kw in S(j,b)} w[:, :, kh, kw], S(0,0) = {0}, S(0,1) = {1,2}, S(1,0) = {0,1}, S(1,1) = {2}; mode | DGMR_FLAG_ROUND_TF32 rounds the sums. */
+int dgmr_pack_weight_subpix(const float* w, float* packed, int Cout, int CinTot, int ci0, int Cin, int mode, dgmr_stream_t stream);
+/* gw[co][ci0+ci][kh][kw] (+)= sum of the tiles dwsp[z][co][ci] whose tap sets contain (kh, kw) */
+int dgmr_unpack_wgrad_subpix(const float* dwsp, float* gw, int Cout, int CinTot, int ci0, int Cin, int accumulate, dgmr_stream_t stream);
+/* y = act( upconv(x, wsp) * scale[g][co] + bias + res );  act may carry DGMR_FLAG_ROUND_OUT */
+int dgmr_upconv_fwd(const float* x, const float* wsp, const float* bias, const float* scale, const float* res, float* y, int N, int H, int W,
+                    int Cin, int Cout, int G, int act, dgmr_stream_t stream);
+/* dx[N,H,W,Cin] = transpose of the above applied to dz (already scaled, tf32-rounded); wspt: the mode-1 pack */
+int dgmr_upconv_dgrad(const float* dz, const float* wspt, float* dx, int N, int H, int W, int Cin, int Cout, dgmr_stream_t stream);
+/* dwsp[16][Cout][Cin] = weight gradient of the pre-summed tiles (fold with dgmr_unpack_wgrad_subpix) */
+int dgmr_upconv_wgrad(const float* x, const float* dz, float* dwsp, int N, int H, int W, int Cin, int Cout, dgmr_stream_t stream);
+
 /* ---- discriminator head (ref: dgmr/discriminators.py:129,209: sum(relu(x)) over H,W) */
 int dgmr_sumpool_relu_fwd(const float* x, float* y, int N, int HW, int C, dgmr_stream_t stream);
 int dgmr_sumpool_relu_bwd(const float* dy, const float* x, float* dx, int N, int HW, int C, dgmr_stream_t stream);

@@ -309,6 +309,29 @@ class CudaBackend:
                    _tag=tag, _flops=2.0 * N * D * H * W * Cin * Cout * kd * kh * kw,
                    _info=f"{N}x{D}x{H}x{W} {Cin}->{Cout} k{kd}{kh}{kw} G{G}")
 
+    # -- sub-pixel up-convolution (nearest x2 -> 3x3 conv on the low-resolution input; csrc/conv_subpix.cu)
+    def upconv_supported(self, N, H, W, Cin, Cout) -> bool:
+        return bool(self._query("dgmr_upconv_supported", N, H, W, Cin, Cout))
+
+    def pack_weight_subpix(self, w, packed, Cout, CinTot, ci0, Cin, mode):
+        self._call("dgmr_pack_weight_subpix", _f32(w, "w"), _f32(packed, "packed"), Cout, CinTot, ci0, Cin, mode, _tag="pack_weight")
+
+    def unpack_wgrad_subpix(self, dwsp, gw, Cout, CinTot, ci0, Cin, accumulate):
+        self._call("dgmr_unpack_wgrad_subpix", _f32(dwsp, "dwsp"), _f32(gw, "gw"), Cout, CinTot, ci0, Cin, int(accumulate), _tag="unpack_wgrad")
+
+    def upconv_fwd(self, x, wsp, bias, scale, res, y, N, H, W, Cin, Cout, G, act):
+        self._call("dgmr_upconv_fwd", _f32(x, "x"), _f32(wsp, "wsp"), _f32(bias, "bias"), _f32(scale, "scale"), _f32(res, "res"), _f32(y, "y"),
+                   N, H, W, Cin, Cout, G, act, _tag="conv_umma", _flops=2.0 * N * H * W * 16 * Cin * Cout,
+                   _info=f"{N}x1x{H}x{W} {Cin}->{Cout} up2+k133 (sub-pixel: 16 taps) G{G}")
+
+    def upconv_dgrad(self, dz, wspt, dx, N, H, W, Cin, Cout):
+        self._call("dgmr_upconv_dgrad", _f32(dz, "dz"), _f32(wspt, "wspt"), _f32(dx, "dx"), N, H, W, Cin, Cout, _tag="conv_umma",
+                   _flops=2.0 * N * H * W * 16 * Cin * Cout, _info=f"{N}x1x{H}x{W} {Cout}->{Cin} up2+k133 dgrad (sub-pixel: 16 taps)")
+
+    def upconv_wgrad(self, x, dz, dwsp, N, H, W, Cin, Cout):
+        self._call("dgmr_upconv_wgrad", _f32(x, "x"), _f32(dz, "dz"), _f32(dwsp, "dwsp"), N, H, W, Cin, Cout, _tag="wgrad_umma",
+                   _flops=2.0 * N * H * W * 16 * Cin * Cout, _info=f"{N}x1x{H}x{W} {Cin}->{Cout} up2+k133 (sub-pixel: 16 taps)")
+
     def conv_bwd_prep(self, dy, y, res, bias, scale, dz, dpre, dbias, dscale, rows, G, Cout, act, accumulate_dbias=False, up_hw=(0, 0)):
         nb = sum(t is not None for t in (dy, y, res, dz, dpre)) * 4.0 * rows * G * Cout   # bytes moved (profile only)
         self._call("dgmr_conv_bwd_prep", _f32(dy, "dy"), _f32(y, "y"), _f32(res, "res"), _f32(bias, "bias"), _f32(scale, "scale"),

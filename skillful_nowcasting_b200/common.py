@@ -31,7 +31,7 @@ def _kernel(conv_type: str, k: int):
     raise ValueError(f"{conv_type} is not a recognized Conv method")
 
 
-def _conv_bn_relu_eval(conv: SNConv, bn: BatchNorm, x, G: int):
+def _conv_bn_relu_eval(conv: SNConv, bn: BatchNorm, x, G: int, up2: bool = False):
     """Eval mode: relu(bn(conv(x))) as ONE convolution launch.  With running statistics BatchNorm is a per-channel affine map
     y = a*z + b (a = gamma / sqrt(running_var + eps), b = beta - a * running_mean), so it folds into the conv epilogue's per-group scale
     and bias -- scale'[g, co] = a[co] / sigma_g, bias'[co] = a[co] * bias[co] + b[co] -- followed by the fused ReLU: no BatchNorm pass over
@@ -39,16 +39,18 @@ def _conv_bn_relu_eval(conv: SNConv, bn: BatchNorm, x, G: int):
     a = bn.weight * torch.rsqrt(bn.running_var + bn.eps)
     b = bn.bias - a * bn.running_mean
     scale = conv.inv_sigma(G).view(G, 1) * a.view(1, -1)
+    if up2:   # the convolution runs on the nearest x2 upsampling of x (sub-pixel form where available)
+        return ops.upconv(x, conv.weight_orig, conv.bias * a + b, scale.contiguous(), G, ACT_RELU, round_out=True)
     return ops.conv(x, conv.weight_orig, conv.bias * a + b, scale.contiguous(), None, 0, conv.in_channels, G, ACT_RELU)
 
 
-def _conv_bn_relu_train(conv: SNConv, bn: BatchNorm, x, G: int):
+def _conv_bn_relu_train(conv: SNConv, bn: BatchNorm, x, G: int, up2: bool = False):
     """Train mode: relu(bn(conv(x))) as one autograd node (ops._ConvBNRelu): the BatchNorm backward hands the convolution its scaled,
     rounded output gradient directly."""
     bn.num_batches_tracked += G
     scale = conv.scale_of(conv.inv_sigma(G))
     return ops.conv_bn_relu(x, conv.weight_orig, conv.bias, scale, bn.weight, bn.bias, bn.running_mean, bn.running_var, G,
-                            bn.eps, bn.momentum, conv_only=True)
+                            bn.eps, bn.momentum, conv_only=True, up2=up2)
 
 
 class GBlock(nn.Module):
@@ -104,13 +106,15 @@ class UpsampleGBlock(nn.Module):
     def run(self, x, G: int = 1):
         # conv1x1(up2(x)) == up2(conv1x1(x)) bit-for-bit (pointwise conv commutes with replication): 4x fewer MACs, and the
         # upsampled shortcut is never materialised: last_conv_3x3's epilogue reads it at (h/2, w/2)
-        y, xs = self.bn1.run(x, G, relu=True, up2=True, conv_only=True, branch=True)  # BN -> ReLU -> nearest x2 in one pass; xs: x for the shortcut
+        # BN -> ReLU at LOW resolution; the nearest x2 upsampling (ref :148) is folded into first_conv_3x3's sub-pixel form (ops.upconv:
+        # 2.25x fewer MACs, the upsampled activation is never written); xs: x again, for the shortcut
+        y, xs = self.bn1.run(x, G, relu=True, conv_only=True, branch=True)
         y = ops.mark_conv_only(y)
         sc = self.conv_1x1.run(xs, G)  # x also feeds BatchNorm: the conv rounds a private copy
         if self.training:
-            y = ops.mark_conv_only(_conv_bn_relu_train(self.first_conv_3x3, self.bn2, y, G))
+            y = ops.mark_conv_only(_conv_bn_relu_train(self.first_conv_3x3, self.bn2, y, G, up2=True))
         else:
-            y = ops.mark_conv_only(_conv_bn_relu_eval(self.first_conv_3x3, self.bn2, y, G))
+            y = ops.mark_conv_only(_conv_bn_relu_eval(self.first_conv_3x3, self.bn2, y, G, up2=True))
         return self.last_conv_3x3.run(y, G, res=sc, res_up2=True)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:

@@ -13,8 +13,7 @@
 //   * warp roles: warp0 = TMA producer, warp1 = MMA issuer (single elected thread),
 //     warps 2-5 = epilogue (tcgen05.ld 32x32b, fused scale/bias/residual/ReLU, NHWC float4 stores).
 //   * mbarrier full/empty ring between TMA and MMA; tcgen05.commit frees stages and signals the epilogue.
-#include "common.cuh"
-#include <cuda.h>
+#include "umma_common.cuh"
 #include <stdlib.h>
 #include <string.h>
 
@@ -22,171 +21,6 @@ namespace dgmr {
 
 int launch_conv_simt_fwd(const float*, const float*, const float*, const float*, const float*, float*, int, int, int, int, int, int, int, int, int, int, int, cudaStream_t);
 int launch_conv_simt_wgrad(const float*, const float*, float*, int, int, int, int, int, int, int, int, int, cudaStream_t);
-
-// ------------------------------------------------------------------ driver entry point for tensor maps
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
-                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static EncodeTiledFn get_encode() {
-  static EncodeTiledFn fn = nullptr;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(p);
-  }
-  return fn;
-}
-static CUtensorMapSwizzle swizzle_for(int row_bytes) {
-  return row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
-}
-static int make_tmap(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box, int row_bytes,
-                     bool atom32 = false) {
-  EncodeTiledFn enc = get_encode();
-  if (!enc) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return 2; }
-  cuuint64_t gd[5]; cuuint64_t gs[4]; cuuint32_t bx[5]; cuuint32_t es[5];
-  for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
-  for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
-  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : swizzle_for(row_bytes), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    set_error("cuTensorMapEncodeTiled failed (%d): rank %d dims [%llu %llu %llu %llu %llu] box [%u %u %u %u %u] row_bytes %d", (int)r, rank,
-              (unsigned long long)gd[0], (unsigned long long)(rank > 1 ? gd[1] : 0), (unsigned long long)(rank > 2 ? gd[2] : 0),
-              (unsigned long long)(rank > 3 ? gd[3] : 0), (unsigned long long)(rank > 4 ? gd[4] : 0), bx[0], rank > 1 ? bx[1] : 0, rank > 2 ? bx[2] : 0,
-              rank > 3 ? bx[3] : 0, rank > 4 ? bx[4] : 0, row_bytes);
-    return 2;
-  }
-  return 0;
-}
-
-// ------------------------------------------------------------------ PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done;
-  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-  return done != 0;
-}
-// bounded wait: a wedged pipeline traps (host sees a launch failure) instead of hanging the GPU
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  long long t0 = 0;
-  uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if (++spins == 1024u) t0 = clock64();
-    if (spins > 1024u && (spins & 1023u) == 0 && clock64() - t0 > 4000000000LL) {
-      printf("dgmr umma: mbarrier wait timeout (block %d,%d thread %d bar %u parity %u)\n", blockIdx.x, blockIdx.y, threadIdx.x, bar, parity);
-      __trap();
-    }
-  }
-}
-__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
-  asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(dst), "l"(tm),
-               "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
-               : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2) {
-  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst), "l"(tm), "r"(bar),
-               "r"(c0), "r"(c1), "r"(c2)
-               : "memory");
-}
-__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t cols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(cols) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
-}
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc),
-               "r"(idesc), "r"(accumulate)
-               : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-// ---- CTA-pair (cta_group::2) variants: two CTAs of a cluster on the two SMs of a TPC share one MMA stream.  Each CTA stages its own
-// 128 x K activation rows and HALF of the N x K weight tile; the leader (cluster rank 0) issues M = 256 MMAs that read both shared
-// memories and write both tensor memories.
-__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ uint32_t mapa_rank(uint32_t addr, uint32_t rank) {
-  uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank)); return r;
-}
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-__device__ __forceinline__ void tma_load_5d_2sm(uint32_t dst, const CUtensorMap* tm, uint32_t bar_cluster, int c0, int c1, int c2, int c3, int c4) {
-  asm volatile("cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(dst),
-               "l"(tm), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
-               : "memory");
-}
-__device__ __forceinline__ void tma_load_3d_2sm(uint32_t dst, const CUtensorMap* tm, uint32_t bar_cluster, int c0, int c1, int c2) {
-  asm volatile("cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst), "l"(tm),
-               "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2)
-               : "memory");
-}
-__device__ __forceinline__ void tmem_alloc2(uint32_t smem_dst, uint32_t cols) {
-  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(cols) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t cols) {
-  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
-}
-__device__ __forceinline__ void umma_tf32_2cta(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc),
-               "r"(idesc), "r"(accumulate)
-               : "memory");
-}
-__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {   // arrives on the barrier at this offset in BOTH CTAs
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"((uint16_t)3) : "memory");
-}
-// One lane of a converged warp.  The role loops run WARP-UNIFORM (all 32 lanes execute the control flow and the address / descriptor
-// arithmetic, which the compiler can then keep in uniform registers) and only the async instructions are predicated on the elected
-// lane: inside an `if (lane == 0)` region every descriptor handed to UTCHMMA / UTMALDG went through an ELECT + R2UR.BROADCAST waterfall
-// loop (~140 cycles of dependent latency per MMA, measured 2.5x the tensor pipe's own 60-cycle minimum).
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
-  return pred != 0;
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
-  uint32_t r[16];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]),
-        "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-// K-major swizzled shared-memory matrix descriptor (sm_100 "version 1" format, see
-// cute/arch/mma_sm100_desc.hpp SmemDescriptor): start>>4 | LBO>>4 <<16 | SBO>>4 <<32 | 1<<46 | layout<<61
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t sbo_bytes, uint32_t layout_type) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr >> 4) & 0x3FFFu);
-  d |= (uint64_t)1u << 16;                         // LBO (unused for swizzled K-major; canonical value 1)
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
-  d |= (uint64_t)1u << 46;                         // descriptor version (Blackwell)
-  d |= (uint64_t)layout_type << 61;
-  return d;
-}
-
-__device__ __forceinline__ float rna_tf32_e(float x) {
-  uint32_t u;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
-  return __uint_as_float(u);
-}
-__device__ __forceinline__ float4 rna_tf32_e4(float4 v) { return make_float4(rna_tf32_e(v.x), rna_tf32_e(v.y), rna_tf32_e(v.z), rna_tf32_e(v.w)); }
 
 struct UmmaConvParams {
   int N, D, H, W, Cin, Cout, kd, kh, kw, G;
@@ -996,6 +830,8 @@ struct UmmaWgradParams {
   int stages, tmem_cols;
   int cg;                 // stages per release group (one tcgen05.commit hands cg stages back); stages % cg == 0
   int kb_total, kb_chunk;
+  int subpix;             // 1: the 16 pre-summed sub-pixel tiles of conv_subpix.cu: "tap" z = ((i*2+j)*2+a)*2+b reads the phase-(i,j) view of dz
+                          //    (tmDz / tmV1 / tmV2 / tmV3) and x shifted by (a+i-1, b+j-1); N, H, W are the LOW-resolution geometry
   float* dwp;
 };
 
@@ -1003,7 +839,8 @@ struct UmmaWgradParams {
 template <bool X3>
 __global__ void __launch_bounds__(kUmmaThreads, 1)
 conv_umma_wgrad_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDzLo,
-                       const __grid_constant__ CUtensorMap tmXLo, const UmmaWgradParams p) {
+                       const __grid_constant__ CUtensorMap tmXLo, const __grid_constant__ CUtensorMap tmV1, const __grid_constant__ CUtensorMap tmV2,
+                       const __grid_constant__ CUtensorMap tmV3, const UmmaWgradParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -1022,7 +859,16 @@ conv_umma_wgrad_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_co
   volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_addr - raw));
 
   const int tap = blockIdx.x;
-  const int tkw = tap % p.kw, tkh = (tap / p.kw) % p.kh, tkd = tap / (p.kw * p.kh);
+  int tkw = tap % p.kw, tkh = (tap / p.kw) % p.kh, tkd = tap / (p.kw * p.kh);
+  int sh_w = tkw - p.kw / 2, sh_h = tkh - p.kh / 2;
+  const CUtensorMap* dzmap = &tmDz;
+  if (p.subpix) {
+    const int i = tap >> 3, j = (tap >> 2) & 1, a = (tap >> 1) & 1, b = tap & 1;
+    sh_h = a + i - 1; sh_w = b + j - 1; tkd = 0;
+    const int v = i * 2 + j;
+    dzmap = (v == 0) ? &tmDz : (v == 1) ? &tmV1 : (v == 2) ? &tmV2 : &tmV3;
+  }
+  const int sh_d = p.subpix ? 0 : tkd - p.kd / 2;
   const int co0 = (blockIdx.z / p.ci_tiles) * 128, ci0 = (blockIdx.z % p.ci_tiles) * p.BN;
   const int kb0 = blockIdx.y * p.kb_chunk;
   const int kb1 = min(kb0 + p.kb_chunk, p.kb_total);
@@ -1054,14 +900,13 @@ conv_umma_wgrad_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_co
         if (elect_one()) {
           mbar_expect_tx(full_bar(s), (X3 ? 2u : 1u) * (a_bytes + b_bytes));
           const uint32_t sa = base + s * stage_bytes;
-          for (int j = 0; j < a_blocks; ++j) tma_load_5d(sa + j * blk_bytes, &tmDz, full_bar(s), co0 + j * p.aw, w0, h0, d0, n0);
+          for (int j = 0; j < a_blocks; ++j) tma_load_5d(sa + j * blk_bytes, dzmap, full_bar(s), co0 + j * p.aw, w0, h0, d0, n0);
           for (int j = 0; j < b_blocks; ++j)
-            tma_load_5d(sa + a_bytes + j * blk_bytes, &tmX, full_bar(s), ci0 + j * p.aw, w0 + tkw - p.kw / 2, h0 + tkh - p.kh / 2, d0 + tkd - p.kd / 2, n0);
+            tma_load_5d(sa + a_bytes + j * blk_bytes, &tmX, full_bar(s), ci0 + j * p.aw, w0 + sh_w, h0 + sh_h, d0 + sh_d, n0);
           if (X3) {
             for (int j = 0; j < a_blocks; ++j) tma_load_5d(sa + half_bytes + j * blk_bytes, &tmDzLo, full_bar(s), co0 + j * p.aw, w0, h0, d0, n0);
             for (int j = 0; j < b_blocks; ++j)
-              tma_load_5d(sa + half_bytes + a_bytes + j * blk_bytes, &tmXLo, full_bar(s), ci0 + j * p.aw, w0 + tkw - p.kw / 2, h0 + tkh - p.kh / 2,
-                          d0 + tkd - p.kd / 2, n0);
+              tma_load_5d(sa + half_bytes + a_bytes + j * blk_bytes, &tmXLo, full_bar(s), ci0 + j * p.aw, w0 + sh_w, h0 + sh_h, d0 + sh_d, n0);
           }
         }
         __syncwarp();
@@ -1587,6 +1432,7 @@ int launch_conv_umma_wgrad(const float* x, const float* dz, float* dwp, int N, i
                            const float* x_lo = nullptr, const float* dz_lo = nullptr) {
   const bool x3 = x_lo != nullptr && dz_lo != nullptr;
   UmmaWgradParams p;
+  p.subpix = 0;
   p.N = N; p.D = D; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.kd = kd; p.kh = kh; p.kw = kw;
   if (!pick_box32(N, H, W, &p.bw, &p.bh, &p.bn)) { set_error("conv_umma_wgrad: no 32-pixel box"); return 1; }
   p.tiles_w = W / p.bw; p.tiles_h = H / p.bh;
@@ -1651,9 +1497,69 @@ int launch_conv_umma_wgrad(const float* x, const float* dz, float* dwp, int N, i
   }
   if (cudaMemsetAsync(dwp, 0, sizeof(float) * (size_t)taps * Cout * Cin, st) != cudaSuccess) { set_error("conv_umma_wgrad: memset failed"); return 2; }
   dim3 grid((unsigned)taps, (unsigned)ksplit, (unsigned)(co_tiles * p.ci_tiles));
-  if (x3) conv_umma_wgrad_kernel<true><<<grid, kUmmaThreads, smem, st>>>(tmDz, tmX, tmDzLo, tmXLo, p);
-  else conv_umma_wgrad_kernel<false><<<grid, kUmmaThreads, smem, st>>>(tmDz, tmX, tmDzLo, tmXLo, p);
+  if (x3) conv_umma_wgrad_kernel<true><<<grid, kUmmaThreads, smem, st>>>(tmDz, tmX, tmDzLo, tmXLo, tmDz, tmDz, tmDz, p);
+  else conv_umma_wgrad_kernel<false><<<grid, kUmmaThreads, smem, st>>>(tmDz, tmX, tmDzLo, tmXLo, tmDz, tmDz, tmDz, p);
   DGMR_CHECK_LAUNCH("conv_umma_wgrad");
+  return 0;
+}
+
+// Weight gradient of the 16 pre-summed sub-pixel tiles (conv_subpix.cu): dwp[z][co][ci] = sum_{n,h,w} dz[n, 2h+i, 2w+j, co] * x[n, h+a+i-1, w+b+j-1, ci],
+// z = ((i*2+j)*2+a)*2+b.  x: [N,H,W,Cin] (low resolution), dz: [N,2H,2W,Cout]; each "tap" is one tap-wise wgrad over the low-resolution pixel
+// grid whose dz operand is a strided phase view of the high-resolution tensor.  16 instead of 36 MACs per low-res pixel and channel pair.
+int launch_conv_umma_wgrad_subpix(const float* x, const float* dz, float* dwp, int N, int H, int W, int Cin, int Cout, cudaStream_t st) {
+  UmmaWgradParams p;
+  p.subpix = 1;
+  p.N = N; p.D = 1; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.kd = 1; p.kh = 1; p.kw = 1;
+  if (!pick_box32(N, H, W, &p.bw, &p.bh, &p.bn)) { set_error("conv_umma_wgrad_subpix: no 32-pixel box"); return 1; }
+  p.tiles_w = W / p.bw; p.tiles_h = H / p.bh;
+  p.aw = pick_aw(Cin, Cout);
+  if (p.aw == 0) { set_error("conv_umma_wgrad_subpix: channels not multiples of 4"); return 1; }
+  p.ci_tiles = (int)ceil_div(Cin, 256);
+  p.BN = (int)(ceil_div(ceil_div(Cin, p.ci_tiles), p.aw) * p.aw);
+  p.tmem_cols = 32; while (p.tmem_cols < p.BN) p.tmem_cols <<= 1;
+  const uint32_t blk_bytes = 32u * p.aw * 4u;
+  const uint32_t stage_bytes = (128 / p.aw + p.BN / p.aw) * blk_bytes;
+  int stages = (int)((200u * 1024u) / stage_bytes);
+  if (stages > 8) stages = 8;
+  if (stages < 2) { set_error("conv_umma_wgrad_subpix: stage too large"); return 1; }
+  p.cg = 1;
+  if (stages >= 6 && p.BN <= 128) { stages = stages / 3 * 3; p.cg = 3; }
+  else if (stages >= 4) { stages = stages / 2 * 2; p.cg = 2; }
+  p.stages = stages;
+  const size_t smem = (size_t)stages * stage_bytes + 1024 + 8 * (2 * stages + 2);
+  const int taps = 16;
+  const int co_tiles = (int)ceil_div(Cout, 128);
+  p.kb_total = (N / p.bn) * p.tiles_h * p.tiles_w;
+  const int64_t base_ctas = (int64_t)taps * co_tiles * p.ci_tiles;
+  int64_t ksplit = ((int64_t)sm_count() * 3) / base_ctas;
+  if (ksplit > p.kb_total / 4) ksplit = p.kb_total / 4;
+  if (ksplit < 1) ksplit = 1;
+  p.kb_chunk = (int)ceil_div(p.kb_total, ksplit);
+  ksplit = ceil_div(p.kb_total, p.kb_chunk);
+  p.dwp = dwp;
+  CUtensorMap tmV[4], tmX;
+  for (int v = 0; v < 4; ++v) {
+    const int i = v >> 1, j = v & 1;
+    uint64_t dims[5] = {(uint64_t)Cout, (uint64_t)W, (uint64_t)H, 1u, (uint64_t)N};
+    uint64_t str[4] = {(uint64_t)2 * Cout * 4, (uint64_t)2 * (2 * W) * Cout * 4, (uint64_t)(2 * H) * (2 * W) * Cout * 4, (uint64_t)(2 * H) * (2 * W) * Cout * 4};
+    uint32_t box[5] = {(uint32_t)p.aw, (uint32_t)p.bw, (uint32_t)p.bh, 1u, (uint32_t)p.bn};
+    int e = make_tmap(&tmV[v], dz + ((int64_t)i * 2 * W + j) * Cout, 5, dims, str, box, p.aw * 4, true);
+    if (e) return e;
+  }
+  {
+    uint64_t dims[5] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, 1u, (uint64_t)N};
+    uint64_t str[4] = {(uint64_t)Cin * 4, (uint64_t)W * Cin * 4, (uint64_t)H * W * Cin * 4, (uint64_t)H * W * Cin * 4};
+    uint32_t box[5] = {(uint32_t)p.aw, (uint32_t)p.bw, (uint32_t)p.bh, 1u, (uint32_t)p.bn};
+    int e = make_tmap(&tmX, x, 5, dims, str, box, p.aw * 4, true);
+    if (e) return e;
+  }
+  if (cudaFuncSetAttribute(conv_umma_wgrad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)) != cudaSuccess) {
+    set_error("conv_umma_wgrad_subpix: cannot raise dynamic smem limit"); return 2;
+  }
+  if (cudaMemsetAsync(dwp, 0, sizeof(float) * (size_t)taps * Cout * Cin, st) != cudaSuccess) { set_error("conv_umma_wgrad_subpix: memset failed"); return 2; }
+  dim3 grid((unsigned)taps, (unsigned)ksplit, (unsigned)(co_tiles * p.ci_tiles));
+  conv_umma_wgrad_kernel<false><<<grid, kUmmaThreads, smem, st>>>(tmV[0], tmX, tmV[0], tmX, tmV[1], tmV[2], tmV[3], p);
+  DGMR_CHECK_LAUNCH("conv_umma_wgrad_subpix");
   return 0;
 }
 

@@ -36,6 +36,9 @@ class config:
     split_taps = True
     # ConvGRU: fused read|update gate conv + whole recurrence as one autograd node (False: the per-step reference wiring)
     gru_sequence = True
+    # "nearest x2 -> 3x3 conv" in sub-pixel form (csrc/conv_subpix.cu) wherever the tensor-core kernels serve the shape (1xTF32 mode)
+    upconv = True
+    _force_upconv = False   # tests: take the sub-pixel path on the host emulator too
 
 
 def _be():
@@ -621,6 +624,9 @@ def refresh_packs(params) -> int:
                 continue
             ci0, cin, m = key
             pad = cin
+            if isinstance(m, tuple) and m[0] == "sub":   # pre-summed sub-pixel tiles: rebuilt on demand (8 small launches per step)
+                del slot[key]
+                continue
             if isinstance(m, tuple):
                 _, pad, m = m
             if m & FLAG_SPLIT:
@@ -849,6 +855,108 @@ def batch_norm(x, gamma, beta, rmean, rvar, G, training, relu_=False, up2=False,
     return _BatchNorm.apply(x, gamma, beta, rmean, rvar, G, training, relu_, up2, eps, momentum, conv_only, branch)
 
 
+# ----------------------------------------------------------------------------- nearest x2 -> 3x3 conv, sub-pixel form
+def upconv_available(n, h, w, cin, cout) -> bool:
+    """Do the sub-pixel tensor-core kernels (forward, dgrad, wgrad) serve this up-convolution in the current mode?"""
+    if not config.upconv:
+        return False
+    if config._force_upconv:
+        return True
+    return _rounding_on() and _be().upconv_supported(n, h, w, cin, cout)
+
+
+def packed_weight_subpix(w: torch.Tensor, cin: int, mode: int) -> torch.Tensor:
+    """The 16 pre-summed [Cout][Cin] tiles (mode 0) / their transposes (mode 1) of a 3x3 weight (dgmr_pack_weight_subpix), cached on the
+    Parameter like the ordinary packs."""
+    slot = _pack_slot(w)
+    key = (0, cin, ("sub", mode))
+    hit = _pack_lookup(slot, w, key)
+    if hit is not None:
+        return hit
+    cout = w.shape[0]
+    p = _new((16 * cout * cin,), w)
+    _be().pack_weight_subpix(_c(w.detach()), p, cout, w.shape[1], 0, cin, mode)
+    _pack_store(slot, w, key, p)
+    return p
+
+
+def _upconv_fwd(x, w, bias, scale, res, G, act):
+    """x: [N,1,H,W,Cin] LOW resolution (tf32-rounded if rounding is on) -> y [N,1,2H,2W,Cout] = act(conv3x3(up2(x), w) * scale + bias + res)."""
+    n, d, h, wd, c = x.shape
+    assert d == 1 and tuple(w.shape[2:]) == (3, 3) and w.shape[1] == c, (x.shape, w.shape)
+    cout = w.shape[0]
+    wsp = packed_weight_subpix(w, c, FLAG_ROUND_TF32 if _rounding_on() else 0)
+    y = _new((n, 1, 2 * h, 2 * wd, cout), x)
+    _be().upconv_fwd(x, wsp, bias, scale, res, y, n, h, wd, c, cout, G, act)
+    return y
+
+
+def _upconv_bwd(x, w, dz, need_x, need_w):
+    """dz: [N,1,2H,2W,Cout] (scaled, rounded) -> (dx [N,1,H,W,Cin], dw like w)."""
+    be = _be()
+    n, d, h, wd, c = x.shape
+    cout = w.shape[0]
+    dx = dw = None
+    if need_x:
+        wspt = packed_weight_subpix(w, c, 1 | (FLAG_ROUND_TF32 if _rounding_on() else 0))
+        dx = _new(x.shape, x)
+        be.upconv_dgrad(dz, wspt, dx, n, h, wd, c, cout)
+    if need_w:
+        dwsp = _new((16 * cout * c,), x)
+        be.upconv_wgrad(x, dz, dwsp, n, h, wd, c, cout)
+        dw = _new(w.shape, x)
+        be.unpack_wgrad_subpix(dwsp, dw, cout, w.shape[1], 0, c, False)
+    return dx, dw
+
+
+class _UpConv(Function):
+    """y = act(conv3x3(nearest_up2(x), w) * scale[g, co] + bias) computed on the LOW-resolution x in sub-pixel form (ref: UpsampleGBlock,
+    dgmr/common.py:146-149): 2.25x fewer MACs, no upsampled tensor.  Caller checks upconv_available()."""
+
+    @staticmethod
+    def forward(ctx, x, w, bias, scale, G, act, round_out):
+        x = _c(x)
+        if _rounding_on() and config._dbg_round_act:
+            x = _round_(x)
+        scale_c, bias_c = _c(scale), _c(bias)
+        round_out = bool(round_out and _rounding_on())
+        y = _upconv_fwd(x, w, bias_c, scale_c, None, G, act | (FLAG_ROUND_OUT if round_out else 0))
+        if round_out:
+            y._dgmr_tf32 = True
+        need_s = scale is not None and scale.requires_grad
+        ctx.save_for_backward(x, w, bias_c, scale_c, y if (act == ACT_RELU or need_s) else None)
+        ctx.meta = (G, act)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w, bias, scale, y = ctx.saved_tensors
+        G, act = ctx.meta
+        be = _be()
+        dy = _c(dy)
+        n, d, h, wd, c = x.shape
+        cout = w.shape[0]
+        rows = (n // G) * 4 * h * wd
+        need_x, need_w, need_b, need_s = (ctx.needs_input_grad[i] for i in range(4))
+        need_b = need_b and bias is not None
+        need_s = need_s and scale is not None
+        dz = _new(dy.shape, dy)
+        dbias = _new((cout,), dy) if need_b else None
+        dscale = _new((G, cout), dy) if need_s else None
+        be.conv_bwd_prep(dy, y, None, bias, scale, dz, None, dbias, dscale, rows, G, cout,
+                         act | (FLAG_ROUND_TF32 if (_rounding_on() and config._dbg_round_dz) else 0))
+        dx, dw = _upconv_bwd(x, w, dz, need_x, need_w)
+        return dx, dw, dbias, dscale, None, None, None
+
+
+def upconv(x, w, bias=None, scale=None, G=1, act=ACT_NONE, round_out=False):
+    """conv3x3(nearest_up2(x)): sub-pixel kernels where available, else the materialised upsample + ordinary convolution."""
+    n, d, h, wd, c = x.shape
+    if d == 1 and tuple(w.shape[2:]) == (3, 3) and upconv_available(n, h, wd, c, w.shape[0]):
+        return _UpConv.apply(x, w, bias, scale, G, act, round_out)
+    return conv(mark_conv_only(upsample2(x)), w, bias, scale, None, 0, c, G, act, round_out=round_out)
+
+
 class _ConvBNRelu(Function):
     """relu(BN_train(conv(x, w) * scale[g] + bias)) as ONE autograd node (GBlock / UpsampleGBlock: first_conv_3x3 -> bn2 -> ReLU,
     ref: dgmr/common.py:76-80, 146-151), train mode only.
@@ -860,7 +968,9 @@ class _ConvBNRelu(Function):
     <dY, Y - b> reduction, and the conv output is saved once (as the BatchNorm input) instead of twice."""
 
     @staticmethod
-    def forward(ctx, x, w, bias, scale, gamma, beta, rmean, rvar, cin, G, eps, momentum, conv_only):
+    def forward(ctx, x, w, bias, scale, gamma, beta, rmean, rvar, cin, G, eps, momentum, conv_only, up2=False):
+        """up2: x is the LOW-resolution tensor and the convolution runs on its nearest x2 upsampling, in sub-pixel form (the caller
+        checked upconv_available)."""
         be = _be()
         x = _c(x)
         n, d, h, wd, c = x.shape
@@ -868,15 +978,21 @@ class _ConvBNRelu(Function):
         cout = w.shape[0]
         ks = tuple(w.shape[2:])
         kd, kh, kw = (1,) * (3 - len(ks)) + ks
-        rnd = FLAG_ROUND_TF32 if _tc_fwd(n, d, h, wd, c, cout, kd, kh, kw) else 0
-        if rnd and config._dbg_round_act:
-            x = _round_(x)
-        if _x3_fwd(n, d, h, wd, c, cout, kd, kh, kw):
-            rnd = FLAG_SPLIT
-        wp = packed_weight(w, 0, cin, rnd)
-        z = _new((n, d, h, wd, cout), x)
         scale_c, bias_c = _c(scale), _c(bias)
-        _conv_launch(x, wp, bias_c, scale_c, None, z, n, d, h, wd, c, cout, kd, kh, kw, G, ACT_NONE)
+        if up2:
+            if _rounding_on() and config._dbg_round_act:
+                x = _round_(x)
+            z = _upconv_fwd(x, w, bias_c, scale_c, None, G, ACT_NONE)
+            h, wd = 2 * h, 2 * wd           # BatchNorm geometry = the convolution's output
+        else:
+            rnd = FLAG_ROUND_TF32 if _tc_fwd(n, d, h, wd, c, cout, kd, kh, kw) else 0
+            if rnd and config._dbg_round_act:
+                x = _round_(x)
+            if _x3_fwd(n, d, h, wd, c, cout, kd, kh, kw):
+                rnd = FLAG_SPLIT
+            wp = packed_weight(w, 0, cin, rnd)
+            z = _new((n, d, h, wd, cout), x)
+            _conv_launch(x, wp, bias_c, scale_c, None, z, n, d, h, wd, c, cout, kd, kh, kw, G, ACT_NONE)
         rows = (n // G) * d * h * wd
         if rows <= 1:
             raise ValueError("Expected more than 1 value per channel when training")
@@ -890,28 +1006,34 @@ class _ConvBNRelu(Function):
         if out_rnd:
             y._dgmr_tf32 = True
         ctx.save_for_backward(x, w, scale_c, z, gamma, a, b, mean, invstd)
-        ctx.meta = (cin, G, (kd, kh, kw))
+        ctx.meta = (cin, G, (kd, kh, kw), bool(up2))
         return y
 
     @staticmethod
     def backward(ctx, dy):
         x, w, scale, z, gamma, a, b, mean, invstd = ctx.saved_tensors
-        cin, G, (kd, kh, kw) = ctx.meta
+        cin, G, (kd, kh, kw), up2 = ctx.meta
         be = _be()
         dy = _c(dy)
         n, d, h, wd, c = x.shape
         cout = w.shape[0]
+        if up2:
+            h, wd = 2 * h, 2 * wd
         rows = (n // G) * d * h * wd
         need_x, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         red = _new((G, cout, 2), x, torch.float64)
         be.bn_bwd_reduce(dy, z, a, b, mean, invstd, red, rows, G, cout, True, False, h, wd)
-        tc_bwd = (need_x and _tc_fwd(n, d, h, wd, cout, c, kd, kh, kw)) or (need_w and _tc_wgrad(n, d, h, wd, c, cout, kd, kh, kw))
+        tc_bwd = up2 and _rounding_on() or \
+            (need_x and _tc_fwd(n, d, h, wd, cout, c, kd, kh, kw)) or (need_w and _tc_wgrad(n, d, h, wd, c, cout, kd, kh, kw))
         dz = _new(z.shape, x) if (need_x or need_w) else None       # = dL/dz * scale[g], tf32-rounded: the dgrad / wgrad operand
         dgamma = _new((cout,), x) if ctx.needs_input_grad[4] else None
         dbeta = _new((cout,), x) if ctx.needs_input_grad[5] else None
         be.bn_bwd_apply(dy, z, a, b, mean, invstd, scale, red, dz, dgamma, dbeta, False, rows, G, cout,
                         1 | (FLAG_ROUND_TF32 if (tc_bwd and config._dbg_round_dz) else 0), False, h, wd, True)
         dx = dw = None
+        if up2:
+            dx, dw = _upconv_bwd(x, w, dz, need_x, need_w)
+            return dx, dw, None, None, dgamma, dbeta, None, None, None, None, None, None, None, None
         if need_x:
             rnd = FLAG_ROUND_TF32 if (_tc_fwd(n, d, h, wd, cout, c, kd, kh, kw) and config._dbg_round_w) else 0
             if _x3_fwd(n, d, h, wd, cout, c, kd, kh, kw):
@@ -925,11 +1047,16 @@ class _ConvBNRelu(Function):
             dw = _new(w.shape, x)
             be.unpack_wgrad(dwp, dw, cout, w.shape[1], 0, cin, taps, False)
         # bias and scale gradients: identically zero (None = zero for autograd; the flat gradient buffers keep their zeros)
-        return dx, dw, None, None, dgamma, dbeta, None, None, None, None, None, None, None
+        return dx, dw, None, None, dgamma, dbeta, None, None, None, None, None, None, None, None
 
 
-def conv_bn_relu(x, w, bias, scale, gamma, beta, rmean, rvar, G, eps=1e-5, momentum=0.1, conv_only=False):
-    return _ConvBNRelu.apply(x, w, bias, scale, gamma, beta, rmean, rvar, w.shape[1], G, eps, momentum, conv_only)
+def conv_bn_relu(x, w, bias, scale, gamma, beta, rmean, rvar, G, eps=1e-5, momentum=0.1, conv_only=False, up2=False):
+    """up2: the convolution runs on the nearest x2 upsampling of x -- in sub-pixel form when available, else on the materialised upsample."""
+    if up2:
+        n, d, h, wd, c = x.shape
+        if not (d == 1 and tuple(w.shape[2:]) == (3, 3) and upconv_available(n, h, wd, c, w.shape[0])):
+            x, up2 = mark_conv_only(upsample2(x)), False
+    return _ConvBNRelu.apply(x, w, bias, scale, gamma, beta, rmean, rvar, w.shape[1], G, eps, momentum, conv_only, up2)
 
 
 # ----------------------------------------------------------------------------- ConvGRU gate arithmetic

@@ -289,6 +289,82 @@ class EmuBackend:
             z = self._rna_tf32(z.contiguous())
         y.copy_(z.reshape(y.shape))
 
+    # ---- sub-pixel up-convolution (plain restatement of the phase formula of csrc/conv_subpix.cu)
+    def upconv_supported(self, *a):
+        return False
+
+    @staticmethod
+    def _tap_set(i, a):
+        return ((0,), (1, 2))[a] if i == 0 else ((0, 1), (2,))[a]
+
+    def pack_weight_subpix(self, w, packed, Cout, CinTot, ci0, Cin, mode):
+        rnd, mode = bool(mode & 256), mode & ~256
+        wv = w.reshape(Cout, CinTot, 3, 3)[:, ci0:ci0 + Cin]
+        tiles = []
+        for i in range(2):
+            for j in range(2):
+                for a in range(2):
+                    for b in range(2):
+                        t = sum(wv[:, :, kh, kw] for kh in self._tap_set(i, a) for kw in self._tap_set(j, b))
+                        tiles.append(t if mode == 0 else t.t())
+        p = torch.stack(tiles).reshape(-1)
+        packed.copy_(self._rna_tf32(p.contiguous()) if rnd else p)
+
+    def unpack_wgrad_subpix(self, dwsp, gw, Cout, CinTot, ci0, Cin, accumulate):
+        t = dwsp.reshape(2, 2, 2, 2, Cout, Cin)
+        g = torch.zeros(Cout, Cin, 3, 3)
+        for i in range(2):
+            for j in range(2):
+                for a in range(2):
+                    for b in range(2):
+                        for kh in self._tap_set(i, a):
+                            for kw in self._tap_set(j, b):
+                                g[:, :, kh, kw] += t[i, j, a, b]
+        tgt = gw.reshape(Cout, CinTot, 3, 3)[:, ci0:ci0 + Cin]
+        tgt.add_(g) if accumulate else tgt.copy_(g)
+
+    def _upconv_raw(self, x, wsp, N, H, W, Cin, Cout):
+        xl = F.pad(x.reshape(N, H, W, Cin), (0, 0, 1, 1, 1, 1))     # zero halo
+        t = wsp.reshape(2, 2, 2, 2, Cout, Cin)
+        y = torch.zeros(N, 2 * H, 2 * W, Cout)
+        for i in range(2):
+            for j in range(2):
+                acc = 0
+                for a in range(2):
+                    for b in range(2):
+                        sl = xl[:, a + i:a + i + H, b + j:b + j + W]      # xl_unpadded[h + a + i - 1, w + b + j - 1]
+                        acc = acc + torch.einsum("nhwc,oc->nhwo", sl, t[i, j, a, b])
+                y[:, i::2, j::2] = acc
+        return y
+
+    def upconv_fwd(self, x, wsp, bias, scale, res, y, N, H, W, Cin, Cout, G, act):
+        z = self._upconv_raw(x, wsp, N, H, W, Cin, Cout)
+        if scale is not None:
+            z = (z.reshape(G, -1, Cout) * scale.reshape(G, 1, Cout)).reshape(N, 2 * H, 2 * W, Cout)
+        round_out, act = bool(act & 1024), act & 3
+        if bias is not None:
+            z = z + bias
+        if res is not None:
+            z = z + res.reshape(z.shape)
+        if act == 1:
+            z = torch.relu(z)
+        if round_out:
+            z = self._rna_tf32(z.contiguous())
+        y.copy_(z.reshape(y.shape))
+
+    def upconv_dgrad(self, dz, wspt, dx, N, H, W, Cin, Cout):
+        wsp = wspt.reshape(16, Cin, Cout).transpose(1, 2).contiguous()
+        with torch.enable_grad():
+            x = torch.zeros(N, H, W, Cin, requires_grad=True)
+            (g,) = torch.autograd.grad(self._upconv_raw(x, wsp, N, H, W, Cin, Cout), x, dz.reshape(N, 2 * H, 2 * W, Cout))
+        dx.copy_(g.reshape(dx.shape))
+
+    def upconv_wgrad(self, x, dz, dwsp, N, H, W, Cin, Cout):
+        with torch.enable_grad():
+            w = torch.zeros(16 * Cout * Cin, requires_grad=True)
+            (g,) = torch.autograd.grad(self._upconv_raw(x.detach(), w, N, H, W, Cin, Cout), w, dz.reshape(N, 2 * H, 2 * W, Cout))
+        dwsp.copy_(g)
+
     def conv_bwd_prep(self, dy, y, res, bias, scale, dz, dpre, dbias, dscale, rows, G, Cout, act, accumulate_dbias=False, up_hw=(0, 0)):
         rnd, act = bool(act & 256), act & ~256
         if res is not None and up_hw[0]:

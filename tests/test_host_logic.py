@@ -235,3 +235,19 @@ def test_unmodified_reference_wrapper_runs_on_these_modules(emu):
         assert abs(a - b) <= 2e-3 * max(abs(b), 1e-6), (k, a, b)
     for k in [k for k in sys.modules if k == "dgmr" or k.startswith("dgmr.")]:
         del sys.modules[k]
+
+
+@pytest.mark.parametrize("training", [True, False], ids=["train", "eval"])
+def test_upsample_gblock_subpixel_form(emu, training):
+    """UpsampleGBlock with first_conv_3x3 in sub-pixel form (ops.upconv / ops._ConvBNRelu(up2): the four output phases as 2x2-tap
+    convolutions of the low-resolution input with pre-summed taps) against the oracle's upsample -> 3x3 conv: values,
+    buffers and every gradient.  The emulator restates the phase formula, so this pins the host logic (tap sets, weight-gradient
+    folding, BatchNorm geometry); the tcgen05 kernels are checked against the same emulator in tests/test_umma_gpu.py."""
+    from skillful_nowcasting_b200 import ops
+
+    ops.config._force_upconv = True
+    try:
+        case = [c for c in block_cases(False) if c[0] == "upg"][0]
+        run_block_case(case, training, "cpu", 2e-5, 3e-4)
+    finally:
+        ops.config._force_upconv = False

@@ -203,3 +203,86 @@ def test_wgrad_umma_row(cuda_backend, shape):
     assert not torch.isnan(g).any()
     e = (g.cpu() - ref).abs().max().item()
     assert e <= 4e-3 * ref.abs().max().item(), f"row wgrad err {e:.3e} (ref max {ref.abs().max().item():.3e})"
+
+
+# N, H, W (low resolution), Cin, Cout, G
+UPCONV_SHAPES = [
+    (4, 16, 16, 64, 64, 2),       # smallest supported image (H*W = 256), CTA pairs, groups
+    (3, 32, 32, 96, 96, 3),       # odd batch: the pair's second image is past the end for the last item
+    (2, 64, 64, 96, 96, 1),       # P = 66
+    (2, 32, 32, 384, 192, 1),     # two Cout tiles of 96, 12 channel chunks
+    (1, 32, 32, 64, 160, 1),      # single image: no CTA pairs; Cout = 160 -> two tiles of 80
+    (2, 16, 16, 768, 256, 1),     # widest K
+    (2, 128, 128, 32, 48, 2),     # P = 130, narrow output
+]
+
+
+@pytest.mark.parametrize("shape", UPCONV_SHAPES)
+def test_upconv_subpixel_kernels(cuda_backend, shape):
+    """csrc/conv_subpix.cu: forward (plain and fused epilogue), dgrad (four strided phase views of dz) and the 16-tile weight gradient of the
+    sub-pixel up-convolution against the host emulator's restatement of the phase formula; pre-summed packs bit-exact."""
+    be = cuda_backend
+    n, h, w, cin, cout, g = shape
+    assert be.upconv_supported(n, h, w, cin, cout)
+    emu = EmuBackend()
+    torch.manual_seed(21)
+    x = torch.randn(n, 1, h, w, cin)
+    wt = torch.randn(cout, cin, 3, 3) / (9 * cin) ** 0.5
+    # packs: pure sums + the same rounding instruction -> equal up to the order of the <= 4-term fp32 sums
+    for mode in (0, 1, 0 | 256, 1 | 256):
+        ref = torch.empty(16 * cout * cin)
+        emu.pack_weight_subpix(wt, ref, cout, cin, 0, cin, mode)
+        got = torch.empty(16 * cout * cin, device="cuda")
+        be.pack_weight_subpix(wt.cuda(), got, cout, cin, 0, cin, mode)
+        assert (got.cpu() - ref).abs().max().item() <= (1e-6 if not mode & 256 else 1e-3) * ref.abs().max().item(), mode
+    wsp = torch.empty(16 * cout * cin)
+    emu.pack_weight_subpix(wt, wsp, cout, cin, 0, cin, 0)
+    wspt = torch.empty(16 * cout * cin)
+    emu.pack_weight_subpix(wt, wspt, cout, cin, 0, cin, 1)
+    for fused in (False, True):
+        bias = torch.randn(cout) if fused else None
+        scale = (torch.rand(g, cout) + 0.5) if fused else None
+        res = torch.randn(n, 1, 2 * h, 2 * w, cout) if fused else None
+        act = (1 | 1024) if fused else 0
+        y_ref = torch.empty(n, 1, 2 * h, 2 * w, cout)
+        emu.upconv_fwd(x, wsp, bias, scale, res, y_ref, n, h, w, cin, cout, g, act)
+        dev = lambda t: None if t is None else t.cuda()
+        y = torch.full((n, 1, 2 * h, 2 * w, cout), float("nan"), device="cuda")
+        be.upconv_fwd(x.cuda(), wsp.cuda(), dev(bias), dev(scale), dev(res), y, n, h, w, cin, cout, g, act)
+        torch.cuda.synchronize()
+        assert not torch.isnan(y).any(), "sub-pixel forward left outputs unwritten"
+        e = (y.cpu() - y_ref).abs().max().item()
+        assert e <= 4e-3 * max(y_ref.abs().max().item(), 1), f"sub-pixel forward err {e:.3e} (fused={fused})"
+    dz = torch.randn(n, 1, 2 * h, 2 * w, cout)
+    dx_ref = torch.empty(n, 1, h, w, cin)
+    emu.upconv_dgrad(dz, wspt, dx_ref, n, h, w, cin, cout)
+    dx = torch.full((n, 1, h, w, cin), float("nan"), device="cuda")
+    be.upconv_dgrad(dz.cuda(), wspt.cuda(), dx, n, h, w, cin, cout)
+    dw_ref = torch.empty(16 * cout * cin)
+    emu.upconv_wgrad(x, dz, dw_ref, n, h, w, cin, cout)
+    dw = torch.full((16 * cout * cin,), float("nan"), device="cuda")
+    be.upconv_wgrad(x.cuda(), dz.cuda(), dw, n, h, w, cin, cout)
+    torch.cuda.synchronize()
+    assert not torch.isnan(dx).any() and not torch.isnan(dw).any()
+    e = (dx.cpu() - dx_ref).abs().max().item()
+    assert e <= 4e-3 * dx_ref.abs().max().item(), f"sub-pixel dgrad err {e:.3e}"
+    e = (dw.cpu() - dw_ref).abs().max().item()
+    assert e <= 4e-3 * dw_ref.abs().max().item(), f"sub-pixel wgrad err {e:.3e}"
+    # folding the 16 tile gradients back onto the 3x3 taps
+    gw_ref = torch.zeros(cout, cin, 3, 3)
+    emu.unpack_wgrad_subpix(dw_ref, gw_ref, cout, cin, 0, cin, False)
+    gw = torch.empty(cout, cin, 3, 3, device="cuda")
+    be.unpack_wgrad_subpix(dw_ref.cuda(), gw, cout, cin, 0, cin, False)
+    assert (gw.cpu() - gw_ref).abs().max().item() <= 1e-5 * gw_ref.abs().max().item()
+
+
+def test_upsample_gblock_subpixel_on_gpu(cuda_backend):
+    """The wide UpsampleGBlock case takes the sub-pixel kernels in AUTO mode (S = 16: H*W = 256): block output and gradients vs the oracle."""
+    from block_cases import block_cases, run_block_case
+    from skillful_nowcasting_b200 import ops
+
+    case = [c for c in block_cases(True) if c[0] == "upg"][0]
+    n0 = cuda_backend.launches
+    assert ops.upconv_available(2, 16, 16, 64, 64)
+    run_block_case(case, True, "cuda", 1e-3, 1.5e-1, tol_buf=1e-3, tol_l2=5e-2)
+    run_block_case(case, False, "cuda", 1e-3, 1.5e-1, tol_buf=1e-3, tol_l2=5e-2)
