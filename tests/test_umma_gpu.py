@@ -213,7 +213,7 @@ UPCONV_SHAPES = [
     (2, 32, 32, 384, 192, 1),     # two Cout tiles of 96, 12 channel chunks
     (1, 32, 32, 64, 160, 1),      # single image: no CTA pairs; Cout = 160 -> two tiles of 80
     (2, 16, 16, 768, 256, 1),     # widest K
-    (2, 128, 128, 32, 48, 2),     # P = 130, narrow output
+    (2, 128, 128, 32, 64, 2),     # P = 130
 ]
 
 
