@@ -13,7 +13,7 @@ from typing import Tuple
 
 import torch
 import torch.nn as nn
-from huggingface_hub import PyTorchModelHubMixin
+from .hub import HubMixin as PyTorchModelHubMixin   # same API; saves compact copies (see hub.py)
 
 from . import ops
 from .layers.Attention import AttentionLayer

@@ -195,15 +195,18 @@ conv_umma_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       const uint32_t stg = base + (uint32_t)q * 2048u;
       const int lr = lane >> 2, lc = lane & 3;
       const uint32_t st_row = stg + (uint32_t)lane * 64u, st_sw = (uint32_t)((lane >> 1) & 3);
-      int64_t mrow[4], rrow[4]; bool vrow[4]; const float* srow[4];
+      // element offsets are 32-bit (host check: the output tensor has < 2^32 elements): half the registers of 64-bit offsets / pointers,
+      // which is what keeps this kernel at 3 CTAs per SM with the epilogue flags compiled in
+      uint32_t mrow[4], rrow[4], soff[4]; bool vrow[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int rj = q * 32 + lr + 8 * j;
         const int wj = w0 + rj % p.bw, hj = h0 + (rj / p.bw) % p.bh, nj = n0 + rj / (p.bw * p.bh);
         vrow[j] = (nj < p.N) && (hj < p.H) && (wj < p.W);
-        mrow[j] = ((((int64_t)nj * p.D + d0) * p.H + hj) * p.W + wj) * p.Cout + co0 + 4 * lc;
-        rrow[j] = (EF && p.res_up2) ? ((((int64_t)nj * p.D + d0) * (p.H >> 1) + (hj >> 1)) * (p.W >> 1) + (wj >> 1)) * p.Cout + co0 + 4 * lc : mrow[j];
-        srow[j] = (p.scale && vrow[j]) ? p.scale + (int64_t)(nj / (p.N / p.G)) * p.Cout : nullptr;
+        mrow[j] = (uint32_t)((((nj * p.D + d0) * p.H + hj) * p.W + wj)) * (uint32_t)p.Cout + (uint32_t)(co0 + 4 * lc);
+        rrow[j] = (EF && p.res_up2) ? (uint32_t)((((nj * p.D + d0) * (p.H >> 1) + (hj >> 1)) * (p.W >> 1) + (wj >> 1))) * (uint32_t)p.Cout + (uint32_t)(co0 + 4 * lc)
+                                    : mrow[j];
+        soff[j] = vrow[j] ? (uint32_t)(nj / (p.N / p.G)) * (uint32_t)p.Cout : 0u;
       }
       float4 rr[4];
       auto load_res = [&](int c, float4* dst) {
@@ -235,7 +238,7 @@ conv_umma_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(o.x), "=f"(o.y), "=f"(o.z), "=f"(o.w)
                        : "r"(stg + (uint32_t)row * 64u + (((uint32_t)lc ^ (uint32_t)((row >> 1) & 3)) << 4)) : "memory");
           if (vrow[j] && cok) {
-            if (srow[j]) { o.x *= __ldg(srow[j] + co); o.y *= __ldg(srow[j] + co + 1); o.z *= __ldg(srow[j] + co + 2); o.w *= __ldg(srow[j] + co + 3); }
+            if (p.scale) { const float* sr = p.scale + soff[j] + co; o.x *= __ldg(sr); o.y *= __ldg(sr + 1); o.z *= __ldg(sr + 2); o.w *= __ldg(sr + 3); }
             if (p.split_taps) {   // one filter tap per CTA: accumulate into y (pre-filled with the residual or zero)
               asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p.y + mrow[j] + c), "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w) : "memory");
               continue;
@@ -1263,6 +1266,9 @@ int launch_conv_umma_fwd(const float* x, const float* wp, const float* bias, con
                          int Cout, int kd, int kh, int kw, int G, int act, cudaStream_t st, int accumulate = 0, const float* x_lo = nullptr,
                          const float* wp_lo = nullptr) {
   const bool x3 = x_lo != nullptr && wp_lo != nullptr;
+  if ((int64_t)N * D * H * W * Cout >= ((int64_t)1 << 32) || (int64_t)N * D * H * W >= ((int64_t)1 << 31)) {
+    set_error("conv_umma_fwd: output tensor too large for 32-bit element offsets"); return 1;
+  }
   UmmaConvParams p;
   p.round_out = (act & DGMR_FLAG_ROUND_OUT) ? 1 : 0; p.res_up2 = (act & DGMR_FLAG_RES_UP2) ? 1 : 0;
   act &= 3;
@@ -1323,7 +1329,7 @@ int launch_conv_umma_fwd(const float* x, const float* wp, const float* bias, con
 #define DGMR_SET(K) ok = ok && cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, lim) == cudaSuccess
     DGMR_SET((conv_umma_fwd_kernel<32, false, false>)); DGMR_SET((conv_umma_fwd_kernel<16, false, false>)); DGMR_SET((conv_umma_fwd_kernel<8, false, false>));
     DGMR_SET((conv_umma_fwd_kernel<32, false, true>)); DGMR_SET((conv_umma_fwd_kernel<16, false, true>)); DGMR_SET((conv_umma_fwd_kernel<8, false, true>));
-    DGMR_SET((conv_umma_fwd_kernel<32, true, false>)); DGMR_SET((conv_umma_fwd_kernel<16, true, false>)); DGMR_SET((conv_umma_fwd_kernel<8, true, false>));
+    DGMR_SET((conv_umma_fwd_kernel<32, true, true>)); DGMR_SET((conv_umma_fwd_kernel<16, true, true>)); DGMR_SET((conv_umma_fwd_kernel<8, true, true>));
 #undef DGMR_SET
     if (!ok) { set_error("conv_umma_fwd: cannot raise dynamic smem limit"); return 2; }
     attr_set = true;
@@ -1386,8 +1392,8 @@ int launch_conv_umma_fwd(const float* x, const float* wp, const float* bias, con
   dim3 grid((unsigned)mtiles, (unsigned)ntiles, (unsigned)(accumulate ? taps : 1));
   const bool ef = p.round_out || p.res_up2;
 #define DGMR_GO(BKV, X3V, EFV) conv_umma_fwd_kernel<BKV, X3V, EFV><<<grid, kUmmaThreads, smem, st>>>(tmA, tmB, tmAlo, tmBlo, p)
-  if (x3) {   // (ROUND_OUT is refused in 3xTF32 mode; RES_UP2 falls back to the unfused upsample there: see dgmr_conv_fwd)
-    if (p.BK == 32) DGMR_GO(32, true, false); else if (p.BK == 16) DGMR_GO(16, true, false); else DGMR_GO(8, true, false);
+  if (x3) {   // (parity mode does not optimise for time: one instantiation, epilogue flags compiled in; ROUND_OUT is refused there)
+    if (p.BK == 32) DGMR_GO(32, true, true); else if (p.BK == 16) DGMR_GO(16, true, true); else DGMR_GO(8, true, true);
   } else if (ef) {
     if (p.BK == 32) DGMR_GO(32, false, true); else if (p.BK == 16) DGMR_GO(16, false, true); else DGMR_GO(8, false, true);
   } else {

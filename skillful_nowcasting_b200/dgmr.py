@@ -10,7 +10,7 @@ the headline benchmark lives in `skillful_nowcasting_b200.training.gan_step`.
 from __future__ import annotations
 
 import torch
-from huggingface_hub import PyTorchModelHubMixin
+from .hub import HubMixin as PyTorchModelHubMixin   # same API; saves compact copies (see hub.py)
 from torch.utils.checkpoint import checkpoint
 
 from .common import ContextConditioningStack, LatentConditioningStack

@@ -251,3 +251,19 @@ def test_upsample_gblock_subpixel_form(emu, training):
         run_block_case(case, training, "cpu", 2e-5, 3e-4)
     finally:
         ops.config._force_upconv = False
+
+
+def test_save_pretrained_while_parameters_live_in_the_flat_optimiser_buffer(emu, tmp_path):
+    """training.Adam turns every parameter into a view of one flat tensor; the stock hub mixin's safetensors writer refuses such views
+    ('None is covering the entire storage').  hub.HubMixin saves compact copies: same file format, same keys, same values."""
+    import skillful_nowcasting_b200 as B
+    from skillful_nowcasting_b200.training import Adam
+
+    torch.manual_seed(0)
+    ctx = B.ContextConditioningStack(input_channels=1, output_channels=96)
+    Adam(ctx.parameters(), lr=1e-3)          # parameters are now slices of the optimiser's flat buffer
+    assert ctx.d1.conv_1x1.bias.untyped_storage().nbytes() > ctx.d1.conv_1x1.bias.numel() * 4
+    ctx.save_pretrained(tmp_path / "ctx")
+    new = B.ContextConditioningStack.from_pretrained(tmp_path / "ctx")
+    for (ka, va), (kb, vb) in zip(ctx.state_dict().items(), new.state_dict().items()):
+        assert ka == kb and torch.equal(va, vb)

@@ -103,8 +103,19 @@ def test_batchnorm(cuda_backend, G, rows, C, relu, up2):
     _both("bn_bwd_reduce", [dy, x, a, b, mean, invstd, red, rows, G, C, relu, up2, H, W], cuda_backend, rtol=1e-4, atol=1e-4)
     EmuBackend().bn_bwd_reduce(dy, x, a, b, mean, invstd, red, rows, G, C, relu, up2, H, W)
     for training in (True, False):
-        _both("bn_bwd_apply", [dy, x, a, b, mean, invstd, gamma, red, torch.empty(G * rows, C), torch.empty(C), torch.empty(C), False,
+        _both("bn_bwd_apply", [dy, x, a, b, mean, invstd, None, red, torch.empty(G * rows, C), torch.empty(C), torch.empty(C), False,
                                rows, G, C, relu, up2, H, W, training], cuda_backend, rtol=1e-4, atol=1e-5)
+    # fused forms: dx * out_scale[g, c] (+ dx_add), tf32-rounded (ops._ConvBNRelu / the BatchNorm branch node)
+    osc, add = torch.rand(G, C) + 0.5, torch.randn(G * rows, C)
+    _both("bn_bwd_apply", [dy, x, a, b, mean, invstd, osc, red, torch.empty(G * rows, C), torch.empty(C), torch.empty(C), False,
+                           rows, G, C, relu, up2, H, W, True], cuda_backend, rtol=1e-4, atol=1e-5, kwargs=dict(dx_add=None))
+    emu_dx, gpu_dx = torch.empty(G * rows, C), torch.empty(G * rows, C, device="cuda")
+    EmuBackend().bn_bwd_apply(dy, x, a, b, mean, invstd, osc, red, emu_dx, None, None, False, rows, G, C, int(relu) | 256, up2, H, W, True, dx_add=add)
+    dev = lambda t: t.cuda()
+    cuda_backend.bn_bwd_apply(dev(dy), dev(x), dev(a), dev(b), dev(mean), dev(invstd), dev(osc), dev(red), gpu_dx, None, None, False, rows, G, C,
+                              int(relu) | 256, up2, H, W, True, dx_add=dev(add))
+    assert (gpu_dx.cpu() - emu_dx).abs().max().item() <= 1.1e-3 * emu_dx.abs().max().item()   # one tf32 ulp at rounding boundaries
+    assert int((gpu_dx.view(torch.int32) & 0x1fff).abs().max()) == 0
 
 
 @pytest.mark.parametrize("R,K,G", [(24, 36, 1), (48, 432, 4), (1, 768, 8), (384, 3456, 18), (768, 6912, 3), (96, 2592, 2)])

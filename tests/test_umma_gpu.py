@@ -67,7 +67,8 @@ def test_conv_umma(cuda_backend, shape, variant):
     ref_max = y_ref.abs().max().item()
     e_simt = (y_simt.cpu() - y_ref).abs().max().item()
     e_umma = (y_umma.cpu() - y_ref).abs().max().item()
-    assert e_simt <= 2e-5 * max(ref_max, 1), f"SIMT err {e_simt:.3e}"
+    # (ROUND_OUT: an fp32 difference of 1e-7 that straddles a tf32 rounding boundary becomes one tf32 ulp, 2^-10 of the value)
+    assert e_simt <= (1.1e-3 if up2 else 2e-5) * max(ref_max, 1), f"SIMT err {e_simt:.3e}"
     assert not torch.isnan(y_umma).any(), "tcgen05 path left outputs unwritten"
     assert e_umma <= 4e-3 * max(ref_max, 1), f"tcgen05 err {e_umma:.3e} (ref max {ref_max:.3e}, simt err {e_simt:.3e})"
     if up2:   # ROUND_OUT: every output is a tf32 value (low 13 mantissa bits zero)
