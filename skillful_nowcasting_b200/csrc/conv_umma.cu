@@ -998,12 +998,15 @@ struct WgradRowParams {
   int BN, ci_tiles, b_blocks;
   int stages, tmem_cols;
   int kb_total, kb_chunk, wsegs;
+  int subpix;             // 1: sub-pixel up-convolution tiles (conv_subpix.cu): blockIdx.x = (i, j, a); the two column taps b = 0, 1 share one dz tile
+                          //    (phase-(i,j) view of the high-resolution dz: tmDz / tmV1 / tmV2 / tmV3) and one 34-pixel x patch of row h+a+i-1
   float* dwp;
 };
 constexpr uint32_t kRowPatchPitch = 36u * 128u;   // 34 patch rows, padded to a multiple of the 512-byte swizzle period
 
 __global__ void __launch_bounds__(kUmmaThreads, 1)
-conv_umma_wgrad_row_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_constant__ CUtensorMap tmX, const WgradRowParams p) {
+conv_umma_wgrad_row_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmV1,
+                           const __grid_constant__ CUtensorMap tmV2, const __grid_constant__ CUtensorMap tmV3, const WgradRowParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -1020,7 +1023,16 @@ conv_umma_wgrad_row_kernel(const __grid_constant__ CUtensorMap tmDz, const __gri
   volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_addr - raw));
 
   const int trow_i = blockIdx.x;                 // (kd, kh) filter row: fastest index, so the CTAs sharing a pixel range are co-scheduled (L2 reuse)
-  const int tkh = trow_i % p.kh, tkd = trow_i / p.kh;
+  int tkh = trow_i % p.kh, tkd = trow_i / p.kh;
+  int sh_h = tkh - p.kh / 2, sh_d = tkd - p.kd / 2;
+  int ndw = 3, dw0 = 0;                          // column taps per CTA and the patch row of the first one
+  const CUtensorMap* dzmap = &tmDz;
+  if (p.subpix) {
+    const int i = trow_i >> 2, j = (trow_i >> 1) & 1, a = trow_i & 1;
+    sh_h = a + i - 1; sh_d = 0; ndw = 2; dw0 = j;       // tap b reads x column w + b + j - 1 = patch row (b + j)
+    const int v = i * 2 + j;
+    dzmap = (v == 0) ? &tmDz : (v == 1) ? &tmV1 : (v == 2) ? &tmV2 : &tmV3;
+  }
   const int co0 = (blockIdx.z / p.ci_tiles) * 128, ci0 = (blockIdx.z % p.ci_tiles) * p.BN;
   const int kb0 = blockIdx.y * p.kb_chunk;
   const int kb1 = min(kb0 + p.kb_chunk, p.kb_total);
@@ -1051,9 +1063,9 @@ conv_umma_wgrad_row_kernel(const __grid_constant__ CUtensorMap tmDz, const __gri
           mbar_expect_tx(full_bar(s), tx_bytes);
           const uint32_t sa = base + s * stage_bytes;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) tma_load_5d(sa + j * 4096u, &tmDz, full_bar(s), co0 + j * 32, w0, h, d, n);
+          for (int j = 0; j < 4; ++j) tma_load_5d(sa + j * 4096u, dzmap, full_bar(s), co0 + j * 32, w0, h, d, n);
           for (int j = 0; j < p.b_blocks; ++j)
-            tma_load_5d(sa + a_bytes + j * kRowPatchPitch, &tmX, full_bar(s), ci0 + j * 32, w0 - 1, h + tkh - p.kh / 2, d + tkd - p.kd / 2, n);
+            tma_load_5d(sa + a_bytes + j * kRowPatchPitch, &tmX, full_bar(s), ci0 + j * 32, w0 - 1, h + sh_h, d + sh_d, n);
         }
         __syncwarp();
         if (++ws == p.wsegs) { ws = 0; if (++h == p.H) { h = 0; if (++d == p.D) { d = 0; ++n; } } }
@@ -1079,11 +1091,14 @@ conv_umma_wgrad_row_kernel(const __grid_constant__ CUtensorMap tmDz, const __gri
         const uint32_t sa = base + s * stage_bytes;
         if (elect_one()) {
 #pragma unroll
-          for (int dw = 0; dw < 3; ++dw)
+          for (int dw = 0; dw < 3; ++dw) {
+            if (dw < ndw) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_tf32(tmem_base + (uint32_t)(dw * p.BN), mn_desc(sa + k * 1024u, 4096u), mn_desc(sa + a_bytes + (uint32_t)(dw + 8 * k) * 128u, kRowPatchPitch),
-                        idesc, (kb | k) != 0 ? 1u : 0u);
+              for (int k = 0; k < 4; ++k)
+                umma_tf32(tmem_base + (uint32_t)(dw * p.BN), mn_desc(sa + k * 1024u, 4096u),
+                          mn_desc(sa + a_bytes + (uint32_t)(dw0 + dw + 8 * k) * 128u, kRowPatchPitch), idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+          }
           umma_commit(empty_bar(s));
         }
         __syncwarp();
@@ -1097,8 +1112,8 @@ conv_umma_wgrad_row_kernel(const __grid_constant__ CUtensorMap tmDz, const __gri
     const int co = co0 + q * 32 + lane;
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
-    for (int dw = 0; dw < 3; ++dw) {
-      const int tap = trow_i * 3 + dw;
+    for (int dw = 0; dw < ndw; ++dw) {
+      const int tap = p.subpix ? trow_i * 2 + dw : trow_i * 3 + dw;
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(dw * p.BN);
       for (int c = 0; c < p.BN; c += 16) {
         if (ci0 + c >= p.Cin) break;
@@ -1215,6 +1230,7 @@ struct UmmaOptions {
   int patch_mt = -1;         // 128-row sub-tiles per halo-patch work item (1 or 2)
   int patch_tg = -1;         // 1: release halo-patch weight tiles per tap instead of per filter row
   int prefer_patch = -1;     // 1: AUTO dispatch takes the halo-patch kernel whenever it supports the shape (parity tests on small shapes)
+  int subpix_wgrad_row = -1; // sub-pixel weight gradient: 0 = always the tap-wise kernel, 1 = the row kernel whenever W % 32 == 0 (tests)
   int patch_dbg = 0;         // DGMR_TUNING builds only: make the halo-patch kernel skip work
 };
 static UmmaOptions g_opt;
@@ -1512,7 +1528,10 @@ int launch_conv_umma_wgrad(const float* x, const float* dz, float* dwp, int N, i
 // Weight gradient of the 16 pre-summed sub-pixel tiles (conv_subpix.cu): dwp[z][co][ci] = sum_{n,h,w} dz[n, 2h+i, 2w+j, co] * x[n, h+a+i-1, w+b+j-1, ci],
 // z = ((i*2+j)*2+a)*2+b.  x: [N,H,W,Cin] (low resolution), dz: [N,2H,2W,Cout]; each "tap" is one tap-wise wgrad over the low-resolution pixel
 // grid whose dz operand is a strided phase view of the high-resolution tensor.  16 instead of 36 MACs per low-res pixel and channel pair.
+int launch_conv_umma_wgrad_row_subpix(const float* x, const float* dz, float* dwp, int N, int H, int W, int Cin, int Cout, cudaStream_t st);
 int launch_conv_umma_wgrad_subpix(const float* x, const float* dz, float* dwp, int N, int H, int W, int Cin, int Cout, cudaStream_t st) {
+  if (W % 32 == 0 && Cin % 4 == 0 && Cout % 4 == 0 && (g_opt.subpix_wgrad_row == 1 || (g_opt.subpix_wgrad_row != 0 && (int64_t)N * H * W >= 16384)))
+    return launch_conv_umma_wgrad_row_subpix(x, dz, dwp, N, H, W, Cin, Cout, st);   // (measured 2.4 ms tap-wise vs the row form on 96->96 at 64^2)
   UmmaWgradParams p;
   p.subpix = 1;
   p.N = N; p.D = 1; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.kd = 1; p.kh = 1; p.kw = 1;
@@ -1713,6 +1732,7 @@ static bool umma_wgrad_row_ok(int N, int D, int H, int W, int Cin, int Cout, int
 
 int launch_conv_umma_wgrad_row(const float* x, const float* dz, float* dwp, int N, int D, int H, int W, int Cin, int Cout, int kd, int kh, cudaStream_t st) {
   WgradRowParams p;
+  p.subpix = 0;
   p.N = N; p.D = D; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.kd = kd; p.kh = kh;
   p.ci_tiles = (int)ceil_div(Cin, 160);
   p.BN = (int)(ceil_div(ceil_div(Cin, p.ci_tiles), 32) * 32);
@@ -1760,8 +1780,59 @@ int launch_conv_umma_wgrad_row(const float* x, const float* dz, float* dwp, int 
   }
   if (cudaMemsetAsync(dwp, 0, sizeof(float) * (size_t)taps * Cout * Cin, st) != cudaSuccess) { set_error("conv_umma_wgrad_row: memset failed"); return 2; }
   dim3 grid((unsigned)(kd * kh), (unsigned)ksplit, (unsigned)(co_tiles * p.ci_tiles));
-  conv_umma_wgrad_row_kernel<<<grid, kUmmaThreads, smem, st>>>(tmDz, tmX, p);
+  conv_umma_wgrad_row_kernel<<<grid, kUmmaThreads, smem, st>>>(tmDz, tmX, tmDz, tmDz, tmDz, p);
   DGMR_CHECK_LAUNCH("conv_umma_wgrad_row");
+  return 0;
+}
+
+// Sub-pixel weight gradient, row variant (low-resolution W % 32 == 0): one CTA per (phase i, j; row tap a), its two column taps as two accumulators.
+int launch_conv_umma_wgrad_row_subpix(const float* x, const float* dz, float* dwp, int N, int H, int W, int Cin, int Cout, cudaStream_t st) {
+  WgradRowParams p;
+  p.subpix = 1;
+  p.N = N; p.D = 1; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.kd = 1; p.kh = 1;
+  p.ci_tiles = (int)ceil_div(Cin, 160);
+  p.BN = (int)(ceil_div(ceil_div(Cin, p.ci_tiles), 32) * 32);
+  p.b_blocks = p.BN / 32;
+  p.tmem_cols = 32; while (p.tmem_cols < 3 * p.BN) p.tmem_cols <<= 1;
+  const uint32_t stage_bytes = 4u * 4096u + (((uint32_t)p.b_blocks * kRowPatchPitch + 1023u) & ~1023u);
+  int stages = (int)((200u * 1024u) / stage_bytes);
+  if (stages > 6) stages = 6;
+  if (stages < 2) { set_error("conv_umma_wgrad_row_subpix: stage too large"); return 1; }
+  p.stages = stages;
+  const size_t smem = (size_t)stages * stage_bytes + 1024 + 8 * (2 * stages + 2);
+  const int co_tiles = (int)ceil_div(Cout, 128);
+  p.wsegs = W / 32;
+  p.kb_total = N * H * p.wsegs;
+  const int64_t base_ctas = (int64_t)8 * co_tiles * p.ci_tiles;
+  int64_t ksplit = ((int64_t)sm_count() * 2) / base_ctas;
+  if (ksplit > p.kb_total / 8) ksplit = p.kb_total / 8;
+  if (ksplit < 1) ksplit = 1;
+  p.kb_chunk = (int)ceil_div(p.kb_total, ksplit);
+  ksplit = ceil_div(p.kb_total, p.kb_chunk);
+  p.dwp = dwp;
+  CUtensorMap tmV[4], tmX;
+  for (int v = 0; v < 4; ++v) {
+    const int i = v >> 1, j = v & 1;
+    uint64_t dims[5] = {(uint64_t)Cout, (uint64_t)W, (uint64_t)H, 1u, (uint64_t)N};
+    uint64_t str[4] = {(uint64_t)2 * Cout * 4, (uint64_t)2 * (2 * W) * Cout * 4, (uint64_t)(2 * H) * (2 * W) * Cout * 4, (uint64_t)(2 * H) * (2 * W) * Cout * 4};
+    uint32_t box[5] = {32u, 32u, 1u, 1u, 1u};
+    int e = make_tmap(&tmV[v], dz + ((int64_t)i * 2 * W + j) * Cout, 5, dims, str, box, 128, true);
+    if (e) return e;
+  }
+  {
+    uint64_t dims[5] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, 1u, (uint64_t)N};
+    uint64_t str[4] = {(uint64_t)Cin * 4, (uint64_t)W * Cin * 4, (uint64_t)H * W * Cin * 4, (uint64_t)H * W * Cin * 4};
+    uint32_t box[5] = {32u, 34u, 1u, 1u, 1u};
+    int e = make_tmap(&tmX, x, 5, dims, str, box, 128, true);
+    if (e) return e;
+  }
+  if (cudaFuncSetAttribute(conv_umma_wgrad_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)) != cudaSuccess) {
+    set_error("conv_umma_wgrad_row_subpix: cannot raise dynamic smem limit"); return 2;
+  }
+  if (cudaMemsetAsync(dwp, 0, sizeof(float) * (size_t)16 * Cout * Cin, st) != cudaSuccess) { set_error("conv_umma_wgrad_row_subpix: memset failed"); return 2; }
+  dim3 grid(8u, (unsigned)ksplit, (unsigned)(co_tiles * p.ci_tiles));
+  conv_umma_wgrad_row_kernel<<<grid, kUmmaThreads, smem, st>>>(tmV[0], tmX, tmV[1], tmV[2], tmV[3], p);
+  DGMR_CHECK_LAUNCH("conv_umma_wgrad_row_subpix");
   return 0;
 }
 
@@ -1795,7 +1866,8 @@ int dgmr_set_option(const char* name, int value) {
   if (name == nullptr) { set_error("dgmr_set_option: null name"); return 1; }
   struct { const char* n; int* v; } tab[] = {{"umma_cg", &g_opt.umma_cg}, {"umma_persist", &g_opt.umma_persist}, {"umma_persist_r", &g_opt.umma_persist_r},
                                              {"patch_pair", &g_opt.patch_pair}, {"patch_mt", &g_opt.patch_mt}, {"patch_tg", &g_opt.patch_tg},
-                                             {"prefer_patch", &g_opt.prefer_patch}, {"patch_dbg", &g_opt.patch_dbg}};
+                                             {"prefer_patch", &g_opt.prefer_patch}, {"patch_dbg", &g_opt.patch_dbg},
+                                             {"subpix_wgrad_row", &g_opt.subpix_wgrad_row}};
   for (auto& t : tab)
     if (strcmp(t.n, name) == 0) { *t.v = value; return 0; }
   set_error("dgmr_set_option: unknown option '%s'", name);
