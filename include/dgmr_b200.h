@@ -212,10 +212,14 @@ int dgmr_conv_fwd(const float* x, const float* x_lo, const float* wp, const floa
 /* backward prologue: dpre = dy*act'(y); dz = dpre*scale; dbias[co] (+)= sum dpre;
  * dscale[g][co] = sum dpre*(y - bias - res)/scale  (the <dY, Y-b> identity of SURVEY.md 8a/a13).
  * rows = pixels per group.  Any of dbias/dscale may be NULL.  up_h, up_w > 0: the forward ran with DGMR_FLAG_RES_UP2 on up_h x up_w
- * images, i.e. `res` is the half-resolution tensor and is read at (h/2, w/2); 0, 0 otherwise. */
+ * images, i.e. `res` is the half-resolution tensor and is read at (h/2, w/2); 0, 0 otherwise.
+ * pool_d, pool_h, pool_w > 0 (with the convolution's output geometry D, H, W): the convolution output went through AvgPool (window
+ * pool_d x pool_h x pool_w, floor; ref: DBlock, dgmr/common.py:234-236) and `dy` is the gradient of the POOLED tensor [N, D/pd, H/ph, W/pw, Cout]:
+ * it is read at (d/pd, h/ph, w/pw) and divided by the window size here, instead of a separate upsample pass. */
 int dgmr_conv_bwd_prep(const float* dy, const float* y, const float* res, const float* bias, const float* scale,
                        float* dz, float* dpre /*optional: unscaled dpre, = grad of res*/, float* dbias, float* dscale,
-                       int64_t rows, int G, int Cout, int act, int accumulate_dbias, int up_h, int up_w, dgmr_stream_t stream);
+                       int64_t rows, int G, int Cout, int act, int accumulate_dbias, int up_h, int up_w,
+                       int pool_d, int pool_h, int pool_w, int D, int H, int W, dgmr_stream_t stream);
 /* dwp[tap][co][ci] = sum_pixels dz[p][co] * x[p+tap][ci]   (dwp fully overwritten).  Both operands are read straight from the
  * channels-last tensors (MN-major tensor-core tiles).  x_lo/dz_lo: lo parts for DGMR_PREC_3XTF32 (as in dgmr_conv_fwd), else NULL. */
 int dgmr_conv_wgrad(const float* x, const float* x_lo, const float* dz, const float* dz_lo, float* dwp, int N, int D, int H, int W,

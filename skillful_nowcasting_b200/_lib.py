@@ -332,11 +332,14 @@ class CudaBackend:
         self._call("dgmr_upconv_wgrad", _f32(x, "x"), _f32(dz, "dz"), _f32(dwsp, "dwsp"), N, H, W, Cin, Cout, _tag="wgrad_umma",
                    _flops=2.0 * N * H * W * 16 * Cin * Cout, _info=f"{N}x1x{H}x{W} {Cin}->{Cout} up2+k133 (sub-pixel: 16 taps)")
 
-    def conv_bwd_prep(self, dy, y, res, bias, scale, dz, dpre, dbias, dscale, rows, G, Cout, act, accumulate_dbias=False, up_hw=(0, 0)):
+    def conv_bwd_prep(self, dy, y, res, bias, scale, dz, dpre, dbias, dscale, rows, G, Cout, act, accumulate_dbias=False, up_hw=(0, 0),
+                      pool=None):
+        """pool: (pd, ph, pw, D, H, W): dy is the gradient of the average-pooled conv output (see the header)."""
+        pool = tuple(int(v) for v in pool) if pool else (0, 0, 0, 0, 0, 0)
         nb = sum(t is not None for t in (dy, y, res, dz, dpre)) * 4.0 * rows * G * Cout   # bytes moved (profile only)
         self._call("dgmr_conv_bwd_prep", _f32(dy, "dy"), _f32(y, "y"), _f32(res, "res"), _f32(bias, "bias"), _f32(scale, "scale"),
                    _f32(dz, "dz"), _f32(dpre, "dpre"), _f32(dbias, "dbias"), _f32(dscale, "dscale"), rows, G, Cout, act,
-                   int(accumulate_dbias), int(up_hw[0]), int(up_hw[1]), _flops=nb, _info=f"rows{rows} G{G} C{Cout} (GB/s)")
+                   int(accumulate_dbias), int(up_hw[0]), int(up_hw[1]), *pool, _flops=nb, _info=f"rows{rows} G{G} C{Cout} (GB/s)")
 
     def conv_wgrad(self, x, dz, dwp, N, D, H, W, Cin, Cout, kd, kh, kw, algo=ALGO_AUTO, precision=PREC_TF32, x_lo=None, dz_lo=None):
         tag = None

@@ -154,11 +154,15 @@ class DBlock(nn.Module):
 
     def run(self, x, G: int = 1):
         if self.input_channels != self.output_channels:
-            # x is read by convolutions and by ReLU only (ReLU commutes with tf32 rounding): rounding in place is exact
+            if self.keep_same_output:
+                x1 = self.conv_1x1.run(x, G)
+            else:
+                # avgpool(conv1x1(x)) == conv1x1(avgpool(x)) (both linear, the bias passes through the mean; SURVEY.md section 7, diff 6e-7):
+                # 4x (2-D) / 8x (3-D) fewer MACs and no full-resolution shortcut tensor.  The pool is launched before anything rounds x
+                # in place, so it averages the unrounded values.
+                x1 = self.conv_1x1.run(ops.mark_conv_only(self._pool(x)), G)
+            # x is otherwise read by convolutions and by ReLU only (ReLU commutes with tf32 rounding): rounding in place is exact
             ops.mark_conv_only(x)
-            x1 = self.conv_1x1.run(x, G)
-            if not self.keep_same_output:
-                x1 = self._pool(x1)
         else:
             x1 = x
         y = ops.mark_conv_only(ops.relu(x)) if self.first_relu else x
@@ -169,7 +173,8 @@ class DBlock(nn.Module):
             y = ops.mark_conv_only(self.first_conv_3x3.run(y, G, act=ACT_RELU, round_out=True))
         if self.keep_same_output:
             return self.last_conv_3x3.run(y, G, res=x1)
-        y = self._pool(self.last_conv_3x3.run(y, G))
+        # conv -> AvgPool as one node: the backward prologue reads the pooled gradient directly (no upsample pass)
+        y = self.last_conv_3x3.run(y, G, pool=((2, 2, 2) if self.conv_type == "3d" else (1, 2, 2)))
         return ops.add(x1, y)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:

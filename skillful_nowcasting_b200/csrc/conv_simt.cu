@@ -268,11 +268,14 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ packed, float* __r
 // rows = pixels per group; grid (row chunks, G); 256 threads as (cpl channel-vector lanes x rp row lanes).
 // V = 4: float4 path (Cout % 4 == 0), V = 1: scalar fallback.  One pass: reads dy (+y, +res), writes dz (+dpre),
 // and reduces dbias / dscale per channel -> HBM-bound, ~3 reads + 1-2 writes per element.
+struct PoolGeom { int pd, ph, pw, D, H, W; float inv; };
 template <int V>
 __global__ void __launch_bounds__(256) conv_bwd_prep_kernel(const float* __restrict__ dy, const float* __restrict__ y, const float* __restrict__ res,
                                                             const float* __restrict__ bias, const float* __restrict__ scale, float* __restrict__ dz,
                                                             float* __restrict__ dpre, float* __restrict__ dbias, float* __restrict__ dscale,
-                                                            int64_t rows, int C, int64_t chunk, int act, int rnd, int up_h, int up_w) {
+                                                            int64_t rows, int C, int64_t chunk, int act, int rnd, int up_h, int up_w, PoolGeom pg) {
+  // pg.pd > 0: `dy` is the gradient of the AVERAGE-POOLED output (window pd x ph x pw, floor) of this convolution: read at (d/pd, h/ph, w/pw) and
+  // divided by the window size -- the pooling backward (a nearest upsample pass) happens inside this load
   // up_h, up_w > 0: `res` is the HALF-resolution tensor of DGMR_FLAG_RES_UP2 (full-resolution image up_h x up_w): read at (h/2, w/2)
   extern __shared__ double sh[];  // [rp][cpl][2*V]
   const int g = blockIdx.y;
@@ -304,12 +307,23 @@ __global__ void __launch_bounds__(256) conv_bwd_prep_kernel(const float* __restr
           const int hh = rem / up_w, ww = rem - hh * up_w;
           ro = ((img * (up_h >> 1) + (hh >> 1)) * (up_w >> 1) + (ww >> 1)) * C + c;
         }
+        int64_t dyo = w.o; float dsc = 1.f;
+        if (pg.pd > 0) {
+          int64_t t = R;
+          const int ww = (int)(t % pg.W); t /= pg.W;
+          const int hh = (int)(t % pg.H); t /= pg.H;
+          const int dd = (int)(t % pg.D); const int64_t nn = t / pg.D;
+          const int Dp = pg.D / pg.pd, Hp = pg.H / pg.ph, Wp = pg.W / pg.pw;
+          const int dq = dd / pg.pd, hq = hh / pg.ph, wq = ww / pg.pw;
+          if (dq < Dp && hq < Hp && wq < Wp) { dyo = ((((nn * Dp + dq) * Hp + hq) * Wp + wq)) * C + c; dsc = pg.inv; }
+          else { dyo = 0; dsc = 0.f; }     // rim dropped by the floor: no gradient
+        }
         if (V == 4) {
-          float4 t = *reinterpret_cast<const float4*>(dy + w.o); w.d[0] = t.x; w.d[1] = t.y; w.d[2] = t.z; w.d[3] = t.w;
+          float4 t = *reinterpret_cast<const float4*>(dy + dyo); w.d[0] = t.x * dsc; w.d[1] = t.y * dsc; w.d[2] = t.z * dsc; w.d[3] = t.w * dsc;
           if (y) { float4 u = *reinterpret_cast<const float4*>(y + w.o); w.yv[0] = u.x; w.yv[1] = u.y; w.yv[2] = u.z; w.yv[3] = u.w; }
           if (res && dscale) { float4 u = *reinterpret_cast<const float4*>(res + ro); w.rv[0] = u.x; w.rv[1] = u.y; w.rv[2] = u.z; w.rv[3] = u.w; }
         } else {
-          w.d[0] = dy[w.o];
+          w.d[0] = dy[dyo] * dsc;
           if (y) w.yv[0] = y[w.o];
           if (res && dscale) w.rv[0] = res[ro];
         }
@@ -697,9 +711,16 @@ int dgmr_unpack_wgrad(const float* packed, float* gw, int Cout, int CinTot, int 
   return 0;
 }
 int dgmr_conv_bwd_prep(const float* dy, const float* y, const float* res, const float* bias, const float* scale, float* dz, float* dpre, float* dbias,
-                       float* dscale, int64_t rows, int G, int Cout, int act, int accumulate_dbias, int up_h, int up_w, dgmr_stream_t stream) {
+                       float* dscale, int64_t rows, int G, int Cout, int act, int accumulate_dbias, int up_h, int up_w, int pool_d, int pool_h, int pool_w,
+                       int D, int H, int W, dgmr_stream_t stream) {
   const int rnd = (act & DGMR_FLAG_ROUND_TF32) ? 1 : 0;
   act &= ~DGMR_FLAG_ROUND_TF32;
+  PoolGeom pg{pool_d, pool_h, pool_w, D, H, W, 0.f};
+  if (pool_d > 0) {
+    DGMR_REQUIRE(pool_h > 0 && pool_w > 0 && pool_d <= 2 && pool_h <= 2 && pool_w <= 2 && D > 0 && H > 0 && W > 0 && (rows * G) % ((int64_t)D * H * W) == 0,
+                 "dgmr_conv_bwd_prep: bad pooled-gradient geometry");
+    pg.inv = 1.0f / (float)(pool_d * pool_h * pool_w);
+  }
   DGMR_REQUIRE((up_h == 0 && up_w == 0) || (up_h > 0 && up_w > 0 && up_h % 2 == 0 && up_w % 2 == 0 && (rows * G) % ((int64_t)up_h * up_w) == 0),
                "dgmr_conv_bwd_prep: bad half-resolution residual geometry %d x %d", up_h, up_w);
   DGMR_REQUIRE(rows > 0 && G > 0 && Cout > 0, "dgmr_conv_bwd_prep: bad dims");
@@ -712,9 +733,9 @@ int dgmr_conv_bwd_prep(const float* dy, const float* y, const float* res, const 
   if (ceil_div(rows, chunk) * G < sm_count()) { chunk = ceil_div(rows * G, (int64_t)sm_count()); if (chunk < 8) chunk = 8; }   // small tensors (ConvGRU steps): fill the SMs
   dim3 grid((unsigned)ceil_div(rows, chunk), G);
   if (Cout % 4 == 0)
-    conv_bwd_prep_kernel<4><<<grid, 256, 256 * 8 * sizeof(double), S(stream)>>>(dy, y, res, bias, scale, dz, dpre, dbias, dscale, rows, Cout, chunk, act, rnd, up_h, up_w);
+    conv_bwd_prep_kernel<4><<<grid, 256, 256 * 8 * sizeof(double), S(stream)>>>(dy, y, res, bias, scale, dz, dpre, dbias, dscale, rows, Cout, chunk, act, rnd, up_h, up_w, pg);
   else
-    conv_bwd_prep_kernel<1><<<grid, 256, 256 * 2 * sizeof(double), S(stream)>>>(dy, y, res, bias, scale, dz, dpre, dbias, dscale, rows, Cout, chunk, act, rnd, up_h, up_w);
+    conv_bwd_prep_kernel<1><<<grid, 256, 256 * 2 * sizeof(double), S(stream)>>>(dy, y, res, bias, scale, dz, dpre, dbias, dscale, rows, Cout, chunk, act, rnd, up_h, up_w, pg);
   DGMR_CHECK_LAUNCH("dgmr_conv_bwd_prep");
   return 0;
 }

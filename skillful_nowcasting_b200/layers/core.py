@@ -100,10 +100,11 @@ class SNConv(nn.Module):
         g = inv_sigma.shape[0]
         return inv_sigma.view(g, 1).expand(g, self.out_channels).contiguous()
 
-    def run(self, x, G: int = 1, act: int = ACT_NONE, res=None, res_up2: bool = False, round_out: bool = False):
-        """x channels-last [N,D,H,W,Cin] -> [N,D,H,W,Cout], one spectral-norm call per group.  res_up2 / round_out: see ops._Conv."""
+    def run(self, x, G: int = 1, act: int = ACT_NONE, res=None, res_up2: bool = False, round_out: bool = False, pool=None):
+        """x channels-last [N,D,H,W,Cin] -> [N,D,H,W,Cout], one spectral-norm call per group.  res_up2 / round_out / pool: see ops._Conv."""
         scale = self.scale_of(self.inv_sigma(G))
-        return ops.conv(x, self.weight_orig, self.bias, scale, res, 0, self.in_channels, G, act, res_up2=res_up2, round_out=round_out)
+        return ops.conv(x, self.weight_orig, self.bias, scale, res, 0, self.in_channels, G, act, res_up2=res_up2, round_out=round_out,
+                        pool=pool)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:  # NCHW in / out (drop-in use)
         if len(self.kernel) == 0:  # linear: [N, Cin]

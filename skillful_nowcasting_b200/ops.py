@@ -690,7 +690,9 @@ class _Conv(Function):
     by the epilogue (no separate rounding pass); ignored unless the 1xTF32 tensor-core mode is on."""
 
     @staticmethod
-    def forward(ctx, x, w, bias, scale, res, ci0, cin, G, act, exact_dscale=False, res_up2=False, round_out=False):
+    def forward(ctx, x, w, bias, scale, res, ci0, cin, G, act, exact_dscale=False, res_up2=False, round_out=False, pool=None):
+        """pool = (pd, ph, pw): the result is average-pooled (floor) and the POOLED tensor is returned (DBlock: conv -> AvgPool, ref:
+        dgmr/common.py:234-236); fusing the two nodes lets the backward prologue read the pooled gradient directly (no upsample pass)."""
         x = _c(x)
         n, d, h, wd, c = x.shape
         assert c == cin or (c > cin and c == (cin + 7) // 8 * 8), (c, cin)   # c > cin: zero-padded input channels
@@ -716,18 +718,29 @@ class _Conv(Function):
         need_s = scale is not None and scale.requires_grad
         need_y = act == ACT_RELU or need_s
         ctx.save_for_backward(x, w, bias_c, scale_c, res_c if need_s else None, y if need_y else None)
-        ctx.meta = (ci0, cin, G, act, (kd, kh, kw), res is not None, exact_dscale, res_up2)
+        ctx.meta = (ci0, cin, G, act, (kd, kh, kw), res is not None, exact_dscale, res_up2, pool)
+        if pool:
+            pd, ph, pw = pool
+            yp = _new((n, d // pd, h // ph, wd // pw, cout), x)
+            _be().pool_sum(y, yp, n, d, h, wd, cout, pd, ph, pw, 1.0 / (pd * ph * pw))
+            return yp
         return y
 
     @staticmethod
     def backward(ctx, dy):
         x, w, bias, scale, res, y = ctx.saved_tensors
-        ci0, cin, G, act, (kd, kh, kw), has_res, exact_dscale, res_up2 = ctx.meta
+        ci0, cin, G, act, (kd, kh, kw), has_res, exact_dscale, res_up2, pool = ctx.meta
         be = _be()
         dy = _c(dy)
         n, d, h, wd, cp = x.shape   # cp > cin: zero-padded input channels
         cout = w.shape[0]
         rows = (n // G) * d * h * wd
+        full_shape = (n, d, h, wd, cout)
+        if pool and not (act == ACT_RELU or scale is not None or (ctx.needs_input_grad[2] and bias is not None)):
+            # no prologue will run: undo the pooling explicitly
+            g_full = _new(full_shape, dy)
+            be.upsample(dy, g_full, n, d // pool[0], h // pool[1], wd // pool[2], cout, pool[0], pool[1], pool[2], d, h, wd, 1.0 / (pool[0] * pool[1] * pool[2]))
+            dy, pool = g_full, None
         need_x, need_w, need_b, need_s, need_r = (ctx.needs_input_grad[i] for i in range(5))
         need_b = need_b and bias is not None
         need_s = need_s and scale is not None
@@ -735,14 +748,15 @@ class _Conv(Function):
         dz, dpre, dbias, dscale = dy, dy, None, None
         if act == ACT_RELU or scale is not None or need_b:
             need_dz = need_x or need_w
-            dz = _new(dy.shape, dy) if (need_dz and (act == ACT_RELU or scale is not None)) else None
-            dpre = _new(dy.shape, dy) if (need_r and act == ACT_RELU) else None
+            dz = _new(full_shape, dy) if (need_dz and (act == ACT_RELU or scale is not None or pool)) else None
+            dpre = _new(full_shape, dy) if (need_r and (act == ACT_RELU or pool)) else None
             dbias = _new((cout,), dy) if need_b else None
             dscale = _new((G, cout), dy) if need_s else None
             tc_bwd = (need_x and _tc_fwd(n, d, h, wd, cout, cp, kd, kh, kw)) or (need_w and _tc_wgrad(n, d, h, wd, cp, cout, kd, kh, kw))
             be.conv_bwd_prep(dy, y, res if need_s else None, bias, scale, dz, dpre, dbias, dscale, rows, G, cout,
                              act | (FLAG_ROUND_TF32 if (tc_bwd and dz is not None and config._dbg_round_dz) else 0),
-                             up_hw=((h, wd) if (res_up2 and need_s and res is not None) else (0, 0)))
+                             up_hw=((h, wd) if (res_up2 and need_s and res is not None) else (0, 0)),
+                             pool=((pool[0], pool[1], pool[2], d, h, wd) if pool else None))
             if need_s and exact_dscale:
                 # the <dY, Y-b-res>/scale identity divides by the scale, which may be exactly 0 (attention gamma starts at 0,
                 # ref: dgmr/layers/Attention.py:69): recompute the raw conv output and reduce <dpre, z> directly
@@ -751,7 +765,8 @@ class _Conv(Function):
                 _conv_launch(x, packed_weight(w, ci0, cin, FLAG_SPLIT if _x3_fwd(n, d, h, wd, cin, cout, kd, kh, kw) else 0), None, None, None, z,
                              n, d, h, wd, cin, cout, kd, kh, kw, 1, ACT_NONE)
                 ones = torch.ones((G, cout), device=dy.device, dtype=dy.dtype)
-                be.conv_bwd_prep(dy, z, None, None, ones, None, None, None, dscale, rows, G, cout, ACT_NONE)
+                be.conv_bwd_prep(dy, z, None, None, ones, None, None, None, dscale, rows, G, cout, ACT_NONE,
+                                 pool=((pool[0], pool[1], pool[2], d, h, wd) if pool else None))
             if dz is None:
                 dz = dy
             elif tc_bwd:
@@ -786,13 +801,14 @@ class _Conv(Function):
             if res_up2:   # gradient of the half-resolution residual: 2x2 sum-pool of the full-resolution one
                 dres = _new((n, d, h // 2, wd // 2, cout), dy)
                 be.pool_sum(_c(dpre), dres, n, d, h, wd, cout, 1, 2, 2, 1.0)
-        return dx, dw, dbias, dscale, dres, None, None, None, None, None, None, None
+        return dx, dw, dbias, dscale, dres, None, None, None, None, None, None, None, None
 
 
-def conv(x, w, bias=None, scale=None, res=None, ci0=0, cin=None, G=1, act=ACT_NONE, exact_dscale=False, res_up2=False, round_out=False):
+def conv(x, w, bias=None, scale=None, res=None, ci0=0, cin=None, G=1, act=ACT_NONE, exact_dscale=False, res_up2=False, round_out=False,
+         pool=None):
     if cin is None:
         cin = w.shape[1]
-    return _Conv.apply(x, w, bias, scale, res, ci0, cin, G, act, exact_dscale, res_up2, round_out)
+    return _Conv.apply(x, w, bias, scale, res, ci0, cin, G, act, exact_dscale, res_up2, round_out, pool)
 
 
 # ----------------------------------------------------------------------------- BatchNorm

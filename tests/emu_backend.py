@@ -365,8 +365,16 @@ class EmuBackend:
             (g,) = torch.autograd.grad(self._upconv_raw(x.detach(), w, N, H, W, Cin, Cout), w, dz.reshape(N, 2 * H, 2 * W, Cout))
         dwsp.copy_(g)
 
-    def conv_bwd_prep(self, dy, y, res, bias, scale, dz, dpre, dbias, dscale, rows, G, Cout, act, accumulate_dbias=False, up_hw=(0, 0)):
+    def conv_bwd_prep(self, dy, y, res, bias, scale, dz, dpre, dbias, dscale, rows, G, Cout, act, accumulate_dbias=False, up_hw=(0, 0), pool=None):
         rnd, act = bool(act & 256), act & ~256
+        if pool:   # dy is the gradient of the average-pooled output: nearest-upsample it (zero on the floor-dropped rim), divide by the window
+            pd, ph, pw, D, H, W = pool
+            N = (rows * G) // (D * H * W)
+            g = dy.reshape(N, D // pd, H // ph, W // pw, Cout) / float(pd * ph * pw)
+            g = g.repeat_interleave(pd, 1).repeat_interleave(ph, 2).repeat_interleave(pw, 3)
+            full = torch.zeros(N, D, H, W, Cout)
+            full[:, :g.shape[1], :g.shape[2], :g.shape[3]] = g
+            dy = full.reshape(G * rows, Cout)
         if res is not None and up_hw[0]:
             uh, uw = up_hw
             r = res.reshape(-1, uh // 2, uw // 2, Cout)

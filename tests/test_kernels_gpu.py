@@ -205,6 +205,21 @@ def test_conv_bwd_prep_half_resolution_residual(cuda_backend, G, n_img, hw, C, a
     _both("conv_bwd_prep", args, cuda_backend, rtol=1e-4, atol=1e-4, kwargs=dict(up_hw=(uh, uw)))
 
 
+@pytest.mark.parametrize("geom,C,act", [((1, 2, 2, 1, 8, 12), 24, 0), ((2, 2, 2, 5, 6, 6), 8, 1), ((2, 2, 2, 11, 4, 4), 7, 1)])
+def test_conv_bwd_prep_pooled_gradient(cuda_backend, geom, C, act):
+    """Backward prologue of a conv whose output was average-pooled (DBlock): dy is the POOLED gradient, read at (d/pd, h/ph, w/pw) and divided
+    by the window; odd depths leave a floor-dropped rim with zero gradient."""
+    torch.manual_seed(22)
+    pd, ph, pw, D, H, W = geom
+    N, G = 4, 2
+    rows = (N // G) * D * H * W
+    dyp = torch.randn(N * (D // pd) * (H // ph) * (W // pw), C)
+    y = torch.randn(G * rows, C)
+    bias, scale = torch.randn(C), torch.rand(G, C) + 0.5
+    args = [dyp, y, None, bias, scale, torch.empty(G * rows, C), torch.empty(G * rows, C), torch.zeros(C), torch.zeros(G, C), rows, G, C, act]
+    _both("conv_bwd_prep", args, cuda_backend, rtol=1e-4, atol=1e-4, kwargs=dict(pool=geom))
+
+
 def test_pack_weight_multi(cuda_backend):
     """dgmr_pack_weight_multi: several packs in one launch, padded input channels and a Cout window of a wider destination,
     against dgmr_pack_weight (bit-exact: pure index maps + the same cvt.rna rounding)."""
