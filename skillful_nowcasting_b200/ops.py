@@ -38,6 +38,8 @@ class config:
     gru_sequence = True
     # "nearest x2 -> 3x3 conv" in sub-pixel form (csrc/conv_subpix.cu) wherever the tensor-core kernels serve the shape (1xTF32 mode)
     upconv = True
+    # 3x3x3 weight gradients of narrow layers with the depth taps folded into the channel axis (see _Conv.backward)
+    fold_depth_wgrad = True
     _force_upconv = False   # tests: take the sub-pixel path on the host emulator too
 
 
@@ -787,14 +789,27 @@ class _Conv(Function):
             _conv_launch(dz, wpt, None, None, None, dx, n, d, h, wd, cout, cp, kd, kh, kw, 1, ACT_NONE)
         if need_w:
             taps = kd * kh * kw
-            dwp = _new((taps * cout * cp,), x)
-            _wgrad_launch(x, dz, dwp, n, d, h, wd, cp, cout, kd, kh, kw)
             cintot = w.shape[1]
             dw = _new(w.shape, x) if cin == cintot else _zeros(w.shape, x)
-            if cp == cin:
-                be.unpack_wgrad(dwp, dw, cout, cintot, ci0, cin, taps, False)
-            else:  # drop the padded channels: dw[co][ci0+ci][tap] = dwp[tap][co][ci], ci < cin
-                be.permute(dwp, dw, (taps, cout, cin), (cout * cp, cp, 1), (1, cintot * taps, taps), False, 0, ci0 * taps)
+            if kd == 3 and kh == 3 and kw == 3 and cp == cin and 3 * cin <= 160 and cout <= 128 and d >= 3 and _tc_wgrad(n, d, h, wd, 3 * cin, cout, 1, 3, 3) \
+                    and wd % 32 == 0 and config.fold_depth_wgrad:
+                # 3x3x3 weight gradient of a narrow layer (temporal discriminator, 48 -> 48): with M = Cout and N = Cin both far below the
+                # 128-row tensor-core tile every MMA sits at the pipe's ~60-cycle floor, so the count of MMAs is what costs.  Folding the three
+                # depth taps into the channel axis (x' = [x(d-1) | x(d) | x(d+1)], 3*Cin channels) turns 9 (kd, kh) filter rows of N = Cin
+                # into 3 rows of N = 3*Cin: 2.25x fewer MMAs for the same products.  dW'[(kh,kw)][co][kd*Cin + ci] scatters back onto dW.
+                xf = _FoldDepth3.apply(x.detach(), cin)                     # [N, D, H, W, 3*Cin] (pad8(3*cin) == 3*cin: cin % 8 == 0)
+                cf = xf.shape[-1]
+                dwp = _new((9 * cout * cf,), x)
+                _wgrad_launch(xf, dz, dwp, n, d, h, wd, cf, cout, 1, 3, 3)
+                # dw[co][ci0 + ci][kd][kh][kw] = dwp[kh*3 + kw][co][kd*cin + ci]
+                be.permute(dwp, dw, (9, cout, 3, cin), (cout * cf, cf, cin, 1), (1, cintot * 27, 9, 27), False, 0, ci0 * 27)
+            else:
+                dwp = _new((taps * cout * cp,), x)
+                _wgrad_launch(x, dz, dwp, n, d, h, wd, cp, cout, kd, kh, kw)
+                if cp == cin:
+                    be.unpack_wgrad(dwp, dw, cout, cintot, ci0, cin, taps, False)
+                else:  # drop the padded channels: dw[co][ci0+ci][tap] = dwp[tap][co][ci], ci < cin
+                    be.permute(dwp, dw, (taps, cout, cin), (cout * cp, cp, 1), (1, cintot * taps, taps), False, 0, ci0 * taps)
         dres = None
         if need_r:
             dres = dpre

@@ -267,3 +267,24 @@ def test_save_pretrained_while_parameters_live_in_the_flat_optimiser_buffer(emu,
     new = B.ContextConditioningStack.from_pretrained(tmp_path / "ctx")
     for (ka, va), (kb, vb) in zip(ctx.state_dict().items(), new.state_dict().items()):
         assert ka == kb and torch.equal(va, vb)
+
+
+def test_depth_folded_weight_gradient_matches_direct(emu, monkeypatch):
+    """3x3x3 weight gradient with the depth taps folded into the channel axis (ops._Conv.backward: x' = [x(d-1)|x(d)|x(d+1)], a 1x3x3 weight
+    gradient with 3*Cin channels, scattered back onto [Cout, Cin, kd, kh, kw]) against the direct form -- same products, same sums."""
+    from skillful_nowcasting_b200 import ops
+
+    monkeypatch.setattr(ops, "_tc_wgrad", lambda *a: True)      # take the tensor-core-only branch on the host emulator
+    torch.manual_seed(0)
+    n, d, h, w, cin, cout = 2, 5, 4, 32, 8, 16
+    x, wt, b = torch.randn(n, d, h, w, cin), torch.randn(cout, cin, 3, 3, 3), torch.randn(cout)
+    g = None
+    res = {}
+    for fold in (True, False):
+        monkeypatch.setattr(ops.config, "fold_depth_wgrad", fold)
+        xs, ws, bs = (t.clone().requires_grad_(True) for t in (x, wt, b))
+        y = ops.conv(xs, ws, bs)
+        g = torch.randn_like(y) if g is None else g
+        res[fold] = torch.autograd.grad(y, [xs, ws, bs], g)
+    for a, c in zip(res[True], res[False]):
+        assert rel_err(a, c) < 1e-5
