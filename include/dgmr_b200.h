@@ -172,6 +172,13 @@ int dgmr_sn_power_iter_multi(const dgmr_sn_item* items, int n, dgmr_stream_t str
 int dgmr_sn_bwd(const float* d_inv_sigma, const float* inv_sigma, const float* u_hist, const float* v_hist,
                 float* dw, int R, int K, int G, int accumulate, dgmr_stream_t stream);
 
+/* out[r] = <a[r][offset : offset+cols], b[r][offset : offset+cols]> / denom[r]   (a, b: [rows][ld]; denom nullable)
+ * The gradient of a G = 1 spectrally normalised convolution's output scale s = 1/sigma from its weight gradient:
+ * dL/ds[co] = <dW[co], W[co]> / s[co]  (replaces the activation-side reduction of dgmr_conv_bwd_prep where one sigma serves the whole
+ * batch; ref: torch.nn.utils.parametrizations.spectral_norm as used in dgmr/common.py:174-201, dgmr/layers/ConvGRU.py:37-52) */
+int dgmr_rowdot_div(const float* a, const float* b, const float* denom, float* out, int rows, int64_t cols, int64_t ld, int64_t offset,
+                    dgmr_stream_t stream);
+
 /* dgmr_sn_bwd for all the spectrally normalised weights of a module in one launch (`items`: HOST array) */
 typedef struct {
   const float* d_inv_sigma; const float* inv_sigma; const float* u_hist; const float* v_hist;

@@ -270,6 +270,9 @@ class CudaBackend:
         self._call("dgmr_sn_bwd", _f32(d_inv_sigma, "d_inv_sigma"), _f32(inv_sigma, "inv_sigma"), _f32(u_hist, "u_hist"),
                    _f32(v_hist, "v_hist"), _f32(dw, "dw"), R, K, G, int(accumulate))
 
+    def rowdot_div(self, a, b, denom, out, rows, cols, ld, offset=0):
+        self._call("dgmr_rowdot_div", _f32(a, "a"), _f32(b, "b"), _f32(denom, "denom"), _f32(out, "out"), int(rows), int(cols), int(ld), int(offset))
+
     def sn_bwd_multi(self, items):
         """items: list of dicts(d_inv_sigma, inv_sigma, u_hist, v_hist, dw, R, K, G, accumulate): one launch per 48 weights."""
         arr = (SnBwdItem * len(items))()

@@ -267,17 +267,20 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ packed, float* __r
 // ------------------------------------------------------------------ backward prologue
 // rows = pixels per group; grid (row chunks, G); 256 threads as (cpl channel-vector lanes x rp row lanes).
 // V = 4: float4 path (Cout % 4 == 0), V = 1: scalar fallback.  One pass: reads dy (+y, +res), writes dz (+dpre),
-// and reduces dbias / dscale per channel -> HBM-bound, ~3 reads + 1-2 writes per element.
+// and reduces dbias / dscale per channel -> HBM-bound, 8-20 B per element.  The template flags only REMOVE paths (HASY: y may be
+// read, DSR: dscale with a residual, GEO: pooled-gradient / half-resolution-residual index maps), so that the common variants stay
+// small enough for 3-4 CTAs per SM with four rows of loads in flight per thread; the fp64 partial sums live in shared memory
+// (touched once per 32 iterations), not in registers.
 struct PoolGeom { int pd, ph, pw, D, H, W; float inv; };
-template <int V>
-__global__ void __launch_bounds__(256) conv_bwd_prep_kernel(const float* __restrict__ dy, const float* __restrict__ y, const float* __restrict__ res,
-                                                            const float* __restrict__ bias, const float* __restrict__ scale, float* __restrict__ dz,
-                                                            float* __restrict__ dpre, float* __restrict__ dbias, float* __restrict__ dscale,
-                                                            int64_t rows, int C, int64_t chunk, int act, int rnd, int up_h, int up_w, PoolGeom pg) {
+template <int V, bool HASY, bool DSR, bool GEO>
+__global__ void __launch_bounds__(256, 3) conv_bwd_prep_kernel(const float* __restrict__ dy, const float* __restrict__ y, const float* __restrict__ res,
+                                                               const float* __restrict__ bias, const float* __restrict__ scale, float* __restrict__ dz,
+                                                               float* __restrict__ dpre, float* __restrict__ dbias, float* __restrict__ dscale,
+                                                               int64_t rows, int C, int64_t chunk, int act, int rnd, int up_h, int up_w, PoolGeom pg) {
   // pg.pd > 0: `dy` is the gradient of the AVERAGE-POOLED output (window pd x ph x pw, floor) of this convolution: read at (d/pd, h/ph, w/pw) and
   // divided by the window size -- the pooling backward (a nearest upsample pass) happens inside this load
   // up_h, up_w > 0: `res` is the HALF-resolution tensor of DGMR_FLAG_RES_UP2 (full-resolution image up_h x up_w): read at (h/2, w/2)
-  extern __shared__ double sh[];  // [rp][cpl][2*V]
+  extern __shared__ double sh[];  // [256][2*V]: (sum dpre, sum dpre*(y-b-res)) per thread
   const int g = blockIdx.y;
   const int CV = C / V;
   const int cpl = CV < 256 ? CV : 256;
@@ -285,59 +288,67 @@ __global__ void __launch_bounds__(256) conv_bwd_prep_kernel(const float* __restr
   const int cl = threadIdx.x % cpl, rl = threadIdx.x / cpl;
   const int64_t r0 = (int64_t)blockIdx.x * chunk;
   const int64_t r1 = r0 + chunk < rows ? r0 + chunk : rows;
-  for (int cv = cl; cv < CV; cv += cpl) {
+  const bool reduce = dbias != nullptr || dscale != nullptr;
+  const bool use_y = HASY && y != nullptr;
+  const bool use_res = DSR && res != nullptr && dscale != nullptr;
+  const bool relu = HASY && act == DGMR_ACT_RELU;
+  double* my = sh + (size_t)threadIdx.x * 2 * V;
+  for (int cb = 0; cb < CV; cb += cpl) {     // block-uniform trip count (barriers inside)
+    const int cv = cb + cl;
     const int c = cv * V;
-    double s[V], q[V];
+    if (reduce) {
 #pragma unroll
-    for (int i = 0; i < V; ++i) { s[i] = 0.0; q[i] = 0.0; }
-    if (rl < rp) {
+      for (int i = 0; i < 2 * V; ++i) my[i] = 0.0;
+    }
+    if (rl < rp && cv < CV) {
       float sc[V], bi[V], fs[V], fq[V];
 #pragma unroll
       for (int i = 0; i < V; ++i) { sc[i] = scale ? scale[(int64_t)g * C + c + i] : 1.f; bi[i] = bias ? bias[c + i] : 0.f; fs[i] = 0.f; fq[i] = 0.f; }
-      int cnt = 0;
-      // one row: loads are issued by `load`, consumed by `finish`, so that two rows' loads are in flight together below
       struct Row { float d[V], yv[V], rv[V]; int64_t o; };
       auto load = [&](int64_t r, Row& w) {
         const int64_t R = (int64_t)g * rows + r;
         w.o = R * C + c;
-        int64_t ro = w.o;
-        if (up_w > 0 && res && dscale) {
-          const int64_t img = R / ((int64_t)up_h * up_w);
-          const int rem = (int)(R - img * up_h * up_w);
-          const int hh = rem / up_w, ww = rem - hh * up_w;
-          ro = ((img * (up_h >> 1) + (hh >> 1)) * (up_w >> 1) + (ww >> 1)) * C + c;
-        }
-        int64_t dyo = w.o; float dsc = 1.f;
-        if (pg.pd > 0) {
-          int64_t t = R;
-          const int ww = (int)(t % pg.W); t /= pg.W;
-          const int hh = (int)(t % pg.H); t /= pg.H;
-          const int dd = (int)(t % pg.D); const int64_t nn = t / pg.D;
-          const int Dp = pg.D / pg.pd, Hp = pg.H / pg.ph, Wp = pg.W / pg.pw;
-          const int dq = dd / pg.pd, hq = hh / pg.ph, wq = ww / pg.pw;
-          if (dq < Dp && hq < Hp && wq < Wp) { dyo = ((((nn * Dp + dq) * Hp + hq) * Wp + wq)) * C + c; dsc = pg.inv; }
-          else { dyo = 0; dsc = 0.f; }     // rim dropped by the floor: no gradient
+        int64_t ro = w.o, dyo = w.o;
+        float dsc = 1.f;
+        if (GEO) {
+          const uint32_t Ru = (uint32_t)R;                         // host checks G*rows < 2^31 for these maps
+          if (up_w > 0 && use_res) {
+            const uint32_t hw = (uint32_t)up_h * (uint32_t)up_w;
+            const uint32_t img = Ru / hw, rem = Ru - img * hw;
+            const uint32_t hh = rem / (uint32_t)up_w, ww = rem - hh * (uint32_t)up_w;
+            ro = ((int64_t)(img * (uint32_t)(up_h >> 1) + (hh >> 1)) * (up_w >> 1) + (ww >> 1)) * C + c;
+          }
+          if (pg.pd > 0) {
+            uint32_t t = Ru;
+            const uint32_t ww = t % (uint32_t)pg.W; t /= (uint32_t)pg.W;
+            const uint32_t hh = t % (uint32_t)pg.H; t /= (uint32_t)pg.H;
+            const uint32_t dd = t % (uint32_t)pg.D; const uint32_t nn = t / (uint32_t)pg.D;
+            const uint32_t Dp = pg.D / pg.pd, Hp = pg.H / pg.ph, Wp = pg.W / pg.pw;
+            const uint32_t dq = dd / (uint32_t)pg.pd, hq = hh / (uint32_t)pg.ph, wq = ww / (uint32_t)pg.pw;
+            if (dq < Dp && hq < Hp && wq < Wp) { dyo = ((((int64_t)nn * Dp + dq) * Hp + hq) * Wp + wq) * C + c; dsc = pg.inv; }
+            else { dyo = 0; dsc = 0.f; }     // rim dropped by the floor: no gradient
+          }
         }
         if (V == 4) {
           float4 t = *reinterpret_cast<const float4*>(dy + dyo); w.d[0] = t.x * dsc; w.d[1] = t.y * dsc; w.d[2] = t.z * dsc; w.d[3] = t.w * dsc;
-          if (y) { float4 u = *reinterpret_cast<const float4*>(y + w.o); w.yv[0] = u.x; w.yv[1] = u.y; w.yv[2] = u.z; w.yv[3] = u.w; }
-          if (res && dscale) { float4 u = *reinterpret_cast<const float4*>(res + ro); w.rv[0] = u.x; w.rv[1] = u.y; w.rv[2] = u.z; w.rv[3] = u.w; }
+          if (use_y) { float4 u = *reinterpret_cast<const float4*>(y + w.o); w.yv[0] = u.x; w.yv[1] = u.y; w.yv[2] = u.z; w.yv[3] = u.w; }
+          if (use_res) { float4 u = *reinterpret_cast<const float4*>(res + ro); w.rv[0] = u.x; w.rv[1] = u.y; w.rv[2] = u.z; w.rv[3] = u.w; }
         } else {
           w.d[0] = dy[dyo] * dsc;
-          if (y) w.yv[0] = y[w.o];
-          if (res && dscale) w.rv[0] = res[ro];
+          if (use_y) w.yv[0] = y[w.o];
+          if (use_res) w.rv[0] = res[ro];
         }
       };
       auto finish = [&](Row& w) {
         float zo[V];
 #pragma unroll
         for (int i = 0; i < V; ++i) {
-          float yy = y ? w.yv[i] : 0.f;
-          if (act == DGMR_ACT_RELU && !(yy > 0.f)) w.d[i] = 0.f;
+          const float yy = use_y ? w.yv[i] : 0.f;
+          if (relu && !(yy > 0.f)) w.d[i] = 0.f;
           zo[i] = w.d[i] * sc[i];
           if (rnd) zo[i] = rna_tf32(zo[i]);
           fs[i] += w.d[i];
-          if (dscale) fq[i] += w.d[i] * (yy - bi[i] - ((res) ? w.rv[i] : 0.f));
+          if (HASY && dscale) fq[i] += w.d[i] * (yy - bi[i] - (use_res ? w.rv[i] : 0.f));
         }
         if (V == 4) {
           if (dz) *reinterpret_cast<float4*>(dz + w.o) = make_float4(zo[0], zo[1], zo[2], zo[3]);
@@ -348,41 +359,62 @@ __global__ void __launch_bounds__(256) conv_bwd_prep_kernel(const float* __restr
         }
       };
       auto flush = [&]() {
-        if (++cnt == 32) {
+        if (reduce) {
 #pragma unroll
-          for (int i = 0; i < V; ++i) { s[i] += fs[i]; q[i] += fq[i]; fs[i] = 0.f; fq[i] = 0.f; }
-          cnt = 0;
+          for (int i = 0; i < V; ++i) { my[2 * i] += (double)fs[i]; my[2 * i + 1] += (double)fq[i]; fs[i] = 0.f; fq[i] = 0.f; }
         }
       };
+      constexpr int U = (DSR || V == 1) ? 2 : 4;     // rows of loads in flight per thread
+      int cnt = 0;
       int64_t r = r0 + rl;
-      for (; r + rp < r1; r += 2 * (int64_t)rp) {
-        Row a, b;
-        load(r, a); load(r + rp, b);
-        finish(a); finish(b);
-        flush();
-      }
-      for (; r < r1; r += rp) { Row a; load(r, a); finish(a); flush(); }
+      for (; r + (int64_t)(U - 1) * rp < r1; r += (int64_t)U * rp) {
+        Row w[U];
 #pragma unroll
-      for (int i = 0; i < V; ++i) { s[i] += fs[i]; q[i] += fq[i]; }
-      if (dbias || dscale) {
+        for (int u = 0; u < U; ++u) load(r + (int64_t)u * rp, w[u]);
 #pragma unroll
-        for (int i = 0; i < V; ++i) { sh[((rl * cpl + cl) * V + i) * 2] = s[i]; sh[((rl * cpl + cl) * V + i) * 2 + 1] = q[i]; }
+        for (int u = 0; u < U; ++u) finish(w[u]);
+        if (++cnt == 64 / U) { flush(); cnt = 0; }
       }
+      for (; r < r1; r += rp) { Row a; load(r, a); finish(a); }
+      flush();
     }
-    if (dbias || dscale) {
+    if (reduce) {
       __syncthreads();
-      if (rl == 0) {
-        for (int j = 1; j < rp; ++j)
-#pragma unroll
-          for (int i = 0; i < V; ++i) { s[i] += sh[((j * cpl + cl) * V + i) * 2]; q[i] += sh[((j * cpl + cl) * V + i) * 2 + 1]; }
-#pragma unroll
-        for (int i = 0; i < V; ++i) {
-          if (dbias) atomicAdd(&dbias[c + i], (float)s[i]);
-          if (dscale) atomicAdd(&dscale[(int64_t)g * C + c + i], (float)(q[i] / (double)scale[(int64_t)g * C + c + i]));
+      // 2V partial sums per channel lane and row lane: spread the cross-row-lane reduction over cpl * 2V threads
+      for (int t = threadIdx.x; t < cpl * 2 * V; t += 256) {
+        const int lane = t / (2 * V), k = t - lane * (2 * V);
+        if (cb + lane < CV) {
+          double v = 0.0;
+          for (int j = 0; j < rp; ++j) v += sh[(size_t)(j * cpl + lane) * 2 * V + k];
+          const int ch = (cb + lane) * V + (k >> 1);
+          if ((k & 1) == 0) { if (dbias) atomicAdd(&dbias[ch], (float)v); }
+          else if (dscale) atomicAdd(&dscale[(int64_t)g * C + ch], (float)(v / (double)scale[(int64_t)g * C + ch]));
         }
       }
       __syncthreads();
     }
+  }
+}
+
+// out[r] = <a[r, off:off+cols], b[r, off:off+cols]> / denom[r]: the spectral-norm scale gradient of a G = 1 convolution from its WEIGHT gradient
+// (with Y = s conv(X, W) + b and dW = wgrad(s dY, X): dL/ds[co] = <dY[co], conv(X, W)[co]> = <dW[co], W[co]> / s[co]) -- a few KB of weights
+// instead of a pass over the activations.  One CTA per output channel, fp64 accumulation.
+__global__ void __launch_bounds__(256) rowdot_div_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ denom,
+                                                         float* __restrict__ out, int64_t cols, int64_t ld, int64_t offset) {
+  __shared__ double sh[8];
+  const int r = blockIdx.x;
+  const float* ar = a + (int64_t)r * ld + offset;
+  const float* br = b + (int64_t)r * ld + offset;
+  double acc = 0.0;
+  for (int64_t j = threadIdx.x; j < cols; j += 256) acc += (double)ar[j] * (double)br[j];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double v = 0.0;
+    for (int w = 0; w < 8; ++w) v += sh[w];
+    out[r] = (float)(denom ? v / (double)denom[r] : v);
   }
 }
 
@@ -710,6 +742,12 @@ int dgmr_unpack_wgrad(const float* packed, float* gw, int Cout, int CinTot, int 
   DGMR_CHECK_LAUNCH("dgmr_unpack_wgrad");
   return 0;
 }
+int dgmr_rowdot_div(const float* a, const float* b, const float* denom, float* out, int rows, int64_t cols, int64_t ld, int64_t offset, dgmr_stream_t stream) {
+  DGMR_REQUIRE(rows > 0 && cols > 0 && ld >= cols && offset >= 0 && offset + cols <= ld, "dgmr_rowdot_div: bad geometry");
+  rowdot_div_kernel<<<rows, 256, 0, S(stream)>>>(a, b, denom, out, cols, ld, offset);
+  DGMR_CHECK_LAUNCH("dgmr_rowdot_div");
+  return 0;
+}
 int dgmr_conv_bwd_prep(const float* dy, const float* y, const float* res, const float* bias, const float* scale, float* dz, float* dpre, float* dbias,
                        float* dscale, int64_t rows, int G, int Cout, int act, int accumulate_dbias, int up_h, int up_w, int pool_d, int pool_h, int pool_w,
                        int D, int H, int W, dgmr_stream_t stream) {
@@ -732,10 +770,15 @@ int dgmr_conv_bwd_prep(const float* dy, const float* y, const float* res, const 
   int64_t chunk = ceil_div(rows, bpg); if (chunk < 64) chunk = 64;
   if (ceil_div(rows, chunk) * G < sm_count()) { chunk = ceil_div(rows * G, (int64_t)sm_count()); if (chunk < 8) chunk = 8; }   // small tensors (ConvGRU steps): fill the SMs
   dim3 grid((unsigned)ceil_div(rows, chunk), G);
-  if (Cout % 4 == 0)
-    conv_bwd_prep_kernel<4><<<grid, 256, 256 * 8 * sizeof(double), S(stream)>>>(dy, y, res, bias, scale, dz, dpre, dbias, dscale, rows, Cout, chunk, act, rnd, up_h, up_w, pg);
-  else
-    conv_bwd_prep_kernel<1><<<grid, 256, 256 * 2 * sizeof(double), S(stream)>>>(dy, y, res, bias, scale, dz, dpre, dbias, dscale, rows, Cout, chunk, act, rnd, up_h, up_w, pg);
+  const bool hasy = y != nullptr, dsr = res != nullptr && dscale != nullptr, geo = pool_d > 0 || (up_w > 0 && dsr);
+  DGMR_REQUIRE(!geo || rows * G < ((int64_t)1 << 31), "dgmr_conv_bwd_prep: pooled / half-resolution maps need G*rows < 2^31");
+#define DGMR_PREP(V_, Y_, R_, G_) conv_bwd_prep_kernel<V_, Y_, R_, G_><<<grid, 256, 256 * 2 * V_ * sizeof(double), S(stream)>>>( \
+      dy, y, res, bias, scale, dz, dpre, dbias, dscale, rows, Cout, chunk, act, rnd, up_h, up_w, pg)
+  if (Cout % 4 != 0) DGMR_PREP(1, true, true, true);
+  else if (!hasy) { if (geo) DGMR_PREP(4, false, false, true); else DGMR_PREP(4, false, false, false); }
+  else if (!dsr) { if (geo) DGMR_PREP(4, true, false, true); else DGMR_PREP(4, true, false, false); }
+  else { if (geo) DGMR_PREP(4, true, true, true); else DGMR_PREP(4, true, true, false); }
+#undef DGMR_PREP
   DGMR_CHECK_LAUNCH("dgmr_conv_bwd_prep");
   return 0;
 }

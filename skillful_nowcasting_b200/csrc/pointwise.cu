@@ -32,14 +32,22 @@ __device__ __forceinline__ float rna_tf32_pw(float x) {
   return __uint_as_float(u);
 }
 
+static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
 // ------------------------------------------------------------------ permute
 struct PermuteArgs {
   int ndim;
   int64_t shape[8], sstr[8], dstr[8];
 };
 // I = uint32_t when all offsets fit 32 bits (up to 8 div/mod pairs per element: 64-bit ones dominate the kernel otherwise)
-template <typename I>
-__global__ void permute_kernel(const float* __restrict__ src, float* __restrict__ dst, PermuteArgs a, int64_t total_, int acc) {
+// T = float4 when the innermost dimension is contiguous on both sides and everything is 16-byte aligned (shape / strides then count float4s)
+__device__ __forceinline__ void permute_store(float* d, float v, int acc) { if (acc) *d += v; else *d = v; }
+__device__ __forceinline__ void permute_store(float4* d, float4 v, int acc) {
+  if (acc) { float4 o = *d; v = make_float4(o.x + v.x, o.y + v.y, o.z + v.z, o.w + v.w); }
+  *d = v;
+}
+template <typename I, typename T>
+__global__ void permute_kernel(const T* __restrict__ src, T* __restrict__ dst, PermuteArgs a, int64_t total_, int acc) {
   const I total = (I)total_;
   for (I i = blockIdx.x * (I)blockDim.x + threadIdx.x; i < total; i += (I)gridDim.x * blockDim.x) {
     I rem = i, so = 0, dof = 0;
@@ -54,8 +62,7 @@ __global__ void permute_kernel(const float* __restrict__ src, float* __restrict_
         dof += r * (I)a.dstr[d];
       }
     }
-    float v = src[so];
-    if (acc) dst[dof] += v; else dst[dof] = v;
+    permute_store(dst + dof, src[so], acc);
   }
 }
 
@@ -472,10 +479,13 @@ __global__ void bn_bwd_reduce_kernel(const float* __restrict__ dy, const float* 
     __syncthreads();
   }
 }
-__global__ void bn_bwd_reduce4_kernel(const float* __restrict__ dy, const float4* __restrict__ x, const float4* __restrict__ a, const float4* __restrict__ b,
-                                      const float4* __restrict__ mean, const float4* __restrict__ invstd, double* __restrict__ red,
-                                      int64_t rows, int C4, int64_t chunk, int relu, int up2, int H, int W) {
-  extern __shared__ double sh[];  // [rp][cpl][8]
+// float4 variant.  Thread = (row lane, 4-channel lane) with its per-channel constants in registers; U rows of loads in flight per thread;
+// fp32 partials are flushed into fp64 slots in SHARED memory every 64 rows (keeps the register count at 3-4 CTAs per SM).
+template <bool UP2>
+__global__ void __launch_bounds__(256, 2) bn_bwd_reduce4_kernel(const float* __restrict__ dy, const float4* __restrict__ x, const float4* __restrict__ a,
+                                                                const float4* __restrict__ b, const float4* __restrict__ mean, const float4* __restrict__ invstd,
+                                                                double* __restrict__ red, int64_t rows, int C4, int64_t chunk, int relu, int H, int W) {
+  extern __shared__ double sh[];  // [256][8]
   const int g = blockIdx.y;
   const int C = C4 * 4;
   const int cpl = C4 < 256 ? C4 : 256;
@@ -483,27 +493,32 @@ __global__ void bn_bwd_reduce4_kernel(const float* __restrict__ dy, const float4
   const int cl = threadIdx.x % cpl, rl = threadIdx.x / cpl;
   const int64_t r0 = (int64_t)blockIdx.x * chunk;
   const int64_t r1 = r0 + chunk < rows ? r0 + chunk : rows;
+  double* my = sh + (size_t)threadIdx.x * 8;
   for (int cb = 0; cb < C4; cb += cpl) {   // block-uniform trip count (barriers inside)
     const int c = cb + cl;
-    double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) my[k] = 0.0;
     if (rl < rp && c < C4) {
       const int64_t o4 = (int64_t)g * C4 + c;
       const float4 aa = a[o4], bb = b[o4], m = mean[o4], is = invstd[o4];
       float fs[4] = {0.f, 0.f, 0.f, 0.f}, fq[4] = {0.f, 0.f, 0.f, 0.f};
-      int cnt = 0;
-      auto one = [&](int64_t r) {
+      struct Row { float4 xv, d; };
+      auto load = [&](int64_t r, Row& w) {
         const int64_t gr = (int64_t)g * rows + r;
-        const float4 xv = x[gr * C4 + c];
-        float4 d;
-        if (up2) {
-          int w = gr % W; int64_t t = gr / W; int h = t % H; int64_t n = t / H;
-          const float4* p0 = reinterpret_cast<const float4*>(dy + ((n * 2 * H + 2 * h) * (2 * (int64_t)W) + 2 * w) * C) + c;
+        w.xv = x[gr * C4 + c];
+        if (UP2) {
+          const uint32_t gu = (uint32_t)gr;               // host checks G*rows < 2^31 for the upsampled form
+          const uint32_t wq = gu % (uint32_t)W, t = gu / (uint32_t)W, hq = t % (uint32_t)H, n = t / (uint32_t)H;
+          const float4* p0 = reinterpret_cast<const float4*>(dy + (((int64_t)n * 2 * H + 2 * hq) * (2 * (int64_t)W) + 2 * wq) * C) + c;
           const float4* p1 = p0 + (int64_t)2 * W * C4;
-          float4 q0 = p0[0], q1 = p0[C4], q2 = p1[0], q3 = p1[C4];
-          d = make_float4(q0.x + q1.x + q2.x + q3.x, q0.y + q1.y + q2.y + q3.y, q0.z + q1.z + q2.z + q3.z, q0.w + q1.w + q2.w + q3.w);
+          const float4 q0 = p0[0], q1 = p0[C4], q2 = p1[0], q3 = p1[C4];
+          w.d = make_float4(q0.x + q1.x + q2.x + q3.x, q0.y + q1.y + q2.y + q3.y, q0.z + q1.z + q2.z + q3.z, q0.w + q1.w + q2.w + q3.w);
         } else {
-          d = reinterpret_cast<const float4*>(dy)[gr * C4 + c];
+          w.d = reinterpret_cast<const float4*>(dy)[gr * C4 + c];
         }
+      };
+      auto finish = [&](Row& w) {
+        float4 d = w.d; const float4 xv = w.xv;
         if (relu) {
           if (!(aa.x * xv.x + bb.x > 0.f)) d.x = 0.f;
           if (!(aa.y * xv.y + bb.y > 0.f)) d.y = 0.f;
@@ -515,27 +530,46 @@ __global__ void bn_bwd_reduce4_kernel(const float* __restrict__ dy, const float4
         fs[2] += d.z; fq[2] += d.z * (xv.z - m.z) * is.z;
         fs[3] += d.w; fq[3] += d.w * (xv.w - m.w) * is.w;
       };
-      int64_t r = r0 + rl;
-      for (; r + (int64_t)rp < r1; r += 2 * (int64_t)rp) {
-        one(r); one(r + rp);
-        if (++cnt == 32) {
+      auto flush = [&]() {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) { acc[2 * k] += fs[k]; acc[2 * k + 1] += fq[k]; fs[k] = fq[k] = 0.f; }
-          cnt = 0;
+        for (int k = 0; k < 4; ++k) { my[2 * k] += (double)fs[k]; my[2 * k + 1] += (double)fq[k]; fs[k] = fq[k] = 0.f; }
+      };
+      constexpr int U = UP2 ? 2 : 4;
+      int cnt = 0;
+      int64_t r = r0 + rl;
+      if (!UP2) {
+        // pointer-bumped main loop: one 64-bit pointer pair and a 32-bit stride instead of per-row 64-bit index arithmetic
+        const float4* xp = x + ((int64_t)g * rows + r) * C4 + c;
+        const float4* dp = reinterpret_cast<const float4*>(dy) + ((int64_t)g * rows + r) * C4 + c;
+        const int step = rp * C4;
+        for (; r + (int64_t)(U - 1) * rp < r1; r += (int64_t)U * rp, xp += (int64_t)U * step, dp += (int64_t)U * step) {
+          Row w[U];
+#pragma unroll
+          for (int u = 0; u < U; ++u) { w[u].xv = xp[u * step]; w[u].d = dp[u * step]; }
+#pragma unroll
+          for (int u = 0; u < U; ++u) finish(w[u]);
+          if (++cnt == 64 / U) { flush(); cnt = 0; }
         }
       }
-      for (; r < r1; r += rp) one(r);
+      if (UP2) {
+        for (; r + (int64_t)(U - 1) * rp < r1; r += (int64_t)U * rp) {
+          Row w[U];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) { acc[2 * k] += fs[k]; acc[2 * k + 1] += fq[k]; }
+          for (int u = 0; u < U; ++u) load(r + (int64_t)u * rp, w[u]);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) sh[(rl * cpl + cl) * 8 + k] = acc[k];
+          for (int u = 0; u < U; ++u) finish(w[u]);
+          if (++cnt == 64 / U) { flush(); cnt = 0; }
+        }
+      }
+      for (; r < r1; r += rp) { Row w; load(r, w); finish(w); }
+      flush();
     }
     __syncthreads();
     for (int t = threadIdx.x; t < cpl * 8; t += blockDim.x) {
       const int lane4 = t >> 3, k = t & 7;
       if (lane4 + cb < C4) {
         double v = 0.0;
-        for (int j = 0; j < rp; ++j) v += sh[(j * cpl + lane4) * 8 + k];
+        for (int j = 0; j < rp; ++j) v += sh[(size_t)(j * cpl + lane4) * 8 + k];
         atomicAdd(&red[((int64_t)g * C + (int64_t)(cb + lane4) * 4 + (k >> 1)) * 2 + (k & 1)], v);
       }
     }
@@ -565,53 +599,84 @@ __global__ void bn_bwd_apply_kernel(const float* __restrict__ dy, const float* _
     dx[i] = rnd ? rna_tf32_pw(v) : v;
   }
 }
-// float4 variant (C % 4 == 0): one thread per 4 channels of one low-res row
-// I = uint32_t when every index fits 32 bits (a 64-bit div/mod costs ~4x a 32-bit one and these kernels do several per element)
-template <typename I>
-__global__ void bn_bwd_apply4_kernel(const float* __restrict__ dy, const float4* __restrict__ x, const float4* __restrict__ a, const float4* __restrict__ b,
-                                     const float4* __restrict__ mean, const float4* __restrict__ invstd, const double* __restrict__ red, float4* __restrict__ dx,
-                                     int64_t rows, int G, int C4, int relu, int up2, int H, int W, int training, const float4* __restrict__ oscale, int rnd,
-                                     const float4* __restrict__ dx_add) {
+// float4 variant (C % 4 == 0): same thread map as the reduce kernel (grid = row chunks x G, thread = row lane x 4-channel lane), so the per-channel
+// constants (a, b, mean, invstd, the two means of the reduce pass, the output scale) are loaded ONCE per thread instead of once per element, and
+// U rows of loads are in flight per thread.
+template <bool UP2, bool ADD>
+__global__ void __launch_bounds__(256, 3) bn_bwd_apply4_kernel(const float* __restrict__ dy, const float4* __restrict__ x, const float4* __restrict__ a,
+                                                               const float4* __restrict__ b, const float4* __restrict__ mean, const float4* __restrict__ invstd,
+                                                               const double* __restrict__ red, float4* __restrict__ dx, int64_t rows, int C4, int64_t chunk,
+                                                               int relu, int H, int W, int training, const float4* __restrict__ oscale, int rnd,
+                                                               const float4* __restrict__ dx_add) {
+  const int g = blockIdx.y;
   const int C = C4 * 4;
-  const I total = (I)G * (I)rows * C4;
-  for (I i = blockIdx.x * (I)blockDim.x + threadIdx.x; i < total; i += (I)gridDim.x * blockDim.x) {
-    int c4 = i % C4; I r = i / C4; int g = r / (I)rows;
-    int64_t o4 = (int64_t)g * C4 + c4;
-    float4 aa = a[o4], bb = b[o4], xv = x[i];
-    float4 d;
-    if (up2) {
-      int w = r % W; I t = r / W; int h = t % H; int64_t n = t / H;
-      const float4* p0 = reinterpret_cast<const float4*>(dy + ((n * 2 * H + 2 * h) * (2 * (int64_t)W) + 2 * w) * C) + c4;
-      const float4* p1 = p0 + (int64_t)2 * W * C4;
-      float4 q0 = p0[0], q1 = p0[C4], q2 = p1[0], q3 = p1[C4];
-      d = make_float4(q0.x + q1.x + q2.x + q3.x, q0.y + q1.y + q2.y + q3.y, q0.z + q1.z + q2.z + q3.z, q0.w + q1.w + q2.w + q3.w);
-    } else {
-      d = reinterpret_cast<const float4*>(dy)[i];
-    }
-    if (relu) {
-      if (!(aa.x * xv.x + bb.x > 0.f)) d.x = 0.f;
-      if (!(aa.y * xv.y + bb.y > 0.f)) d.y = 0.f;
-      if (!(aa.z * xv.z + bb.z > 0.f)) d.z = 0.f;
-      if (!(aa.w * xv.w + bb.w > 0.f)) d.w = 0.f;
-    }
-    float4 v;
+  const int cpl = C4 < 256 ? C4 : 256;
+  const int rp = 256 / cpl;
+  const int cl = threadIdx.x % cpl, rl = threadIdx.x / cpl;
+  if (rl >= rp) return;
+  const int64_t r0 = (int64_t)blockIdx.x * chunk;
+  const int64_t r1 = r0 + chunk < rows ? r0 + chunk : rows;
+  for (int c = cl; c < C4; c += cpl) {
+    const int64_t o4 = (int64_t)g * C4 + c;
+    const float4 aa = a[o4], bb = b[o4];
+    float4 m = make_float4(0.f, 0.f, 0.f, 0.f), is = m, m1 = m, m2 = m, os = make_float4(1.f, 1.f, 1.f, 1.f);
     if (training) {
-      float4 m = mean[o4], is = invstd[o4];
+      m = mean[o4]; is = invstd[o4];
       const double inv = 1.0 / (double)rows;
-      const double* rp = red + o4 * 8;
-      float m1x = (float)(rp[0] * inv), m2x = (float)(rp[1] * inv), m1y = (float)(rp[2] * inv), m2y = (float)(rp[3] * inv);
-      float m1z = (float)(rp[4] * inv), m2z = (float)(rp[5] * inv), m1w = (float)(rp[6] * inv), m2w = (float)(rp[7] * inv);
-      v.x = aa.x * (d.x - m1x - (xv.x - m.x) * is.x * m2x);
-      v.y = aa.y * (d.y - m1y - (xv.y - m.y) * is.y * m2y);
-      v.z = aa.z * (d.z - m1z - (xv.z - m.z) * is.z * m2z);
-      v.w = aa.w * (d.w - m1w - (xv.w - m.w) * is.w * m2w);
-    } else {
-      v = make_float4(aa.x * d.x, aa.y * d.y, aa.z * d.z, aa.w * d.w);
+      const double* rq = red + o4 * 8;
+      m1 = make_float4((float)(rq[0] * inv), (float)(rq[2] * inv), (float)(rq[4] * inv), (float)(rq[6] * inv));
+      m2 = make_float4((float)(rq[1] * inv), (float)(rq[3] * inv), (float)(rq[5] * inv), (float)(rq[7] * inv));
     }
-    if (oscale) { const float4 os = oscale[o4]; v.x *= os.x; v.y *= os.y; v.z *= os.z; v.w *= os.w; }
-    if (dx_add) { const float4 ad = dx_add[i]; v.x += ad.x; v.y += ad.y; v.z += ad.z; v.w += ad.w; }
-    if (rnd) v = make_float4(rna_tf32_pw(v.x), rna_tf32_pw(v.y), rna_tf32_pw(v.z), rna_tf32_pw(v.w));
-    dx[i] = v;
+    if (oscale) os = oscale[o4];
+    struct Row { float4 xv, d, ad; int64_t i; };
+    auto load = [&](int64_t r, Row& w) {
+      const int64_t gr = (int64_t)g * rows + r;
+      w.i = gr * C4 + c;
+      w.xv = x[w.i];
+      if (UP2) {
+        const uint32_t gu = (uint32_t)gr;               // host checks G*rows < 2^31 for the upsampled form
+        const uint32_t wq = gu % (uint32_t)W, t = gu / (uint32_t)W, hq = t % (uint32_t)H, n = t / (uint32_t)H;
+        const float4* p0 = reinterpret_cast<const float4*>(dy + (((int64_t)n * 2 * H + 2 * hq) * (2 * (int64_t)W) + 2 * wq) * C) + c;
+        const float4* p1 = p0 + (int64_t)2 * W * C4;
+        const float4 q0 = p0[0], q1 = p0[C4], q2 = p1[0], q3 = p1[C4];
+        w.d = make_float4(q0.x + q1.x + q2.x + q3.x, q0.y + q1.y + q2.y + q3.y, q0.z + q1.z + q2.z + q3.z, q0.w + q1.w + q2.w + q3.w);
+      } else {
+        w.d = reinterpret_cast<const float4*>(dy)[w.i];
+      }
+      if (ADD) w.ad = dx_add[w.i];
+    };
+    auto finish = [&](Row& w) {
+      float4 d = w.d; const float4 xv = w.xv;
+      if (relu) {
+        if (!(aa.x * xv.x + bb.x > 0.f)) d.x = 0.f;
+        if (!(aa.y * xv.y + bb.y > 0.f)) d.y = 0.f;
+        if (!(aa.z * xv.z + bb.z > 0.f)) d.z = 0.f;
+        if (!(aa.w * xv.w + bb.w > 0.f)) d.w = 0.f;
+      }
+      float4 v;
+      if (training) {
+        v.x = aa.x * (d.x - m1.x - (xv.x - m.x) * is.x * m2.x);
+        v.y = aa.y * (d.y - m1.y - (xv.y - m.y) * is.y * m2.y);
+        v.z = aa.z * (d.z - m1.z - (xv.z - m.z) * is.z * m2.z);
+        v.w = aa.w * (d.w - m1.w - (xv.w - m.w) * is.w * m2.w);
+      } else {
+        v = make_float4(aa.x * d.x, aa.y * d.y, aa.z * d.z, aa.w * d.w);
+      }
+      if (oscale) { v.x *= os.x; v.y *= os.y; v.z *= os.z; v.w *= os.w; }
+      if (ADD) { v.x += w.ad.x; v.y += w.ad.y; v.z += w.ad.z; v.w += w.ad.w; }
+      if (rnd) v = make_float4(rna_tf32_pw(v.x), rna_tf32_pw(v.y), rna_tf32_pw(v.z), rna_tf32_pw(v.w));
+      dx[w.i] = v;
+    };
+    constexpr int U = (UP2 || ADD) ? 2 : 4;
+    int64_t r = r0 + rl;
+    for (; r + (int64_t)(U - 1) * rp < r1; r += (int64_t)U * rp) {
+      Row w[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) load(r + (int64_t)u * rp, w[u]);
+#pragma unroll
+      for (int u = 0; u < U; ++u) finish(w[u]);
+    }
+    for (; r < r1; r += rp) { Row w; load(r, w); finish(w); }
   }
 }
 __global__ void bn_bwd_params_kernel(const double* __restrict__ red, float* __restrict__ dgamma, float* __restrict__ dbeta, int G, int C, int acc) {
@@ -809,8 +874,19 @@ int dgmr_permute(const float* src, float* dst, int ndim, const int64_t* shape, c
   int64_t max_s = 0, max_d = 0; bool nonneg = true;
   for (int d = 0; d < ndim; ++d) { max_s += (shape[d] - 1) * sstr[d]; max_d += (shape[d] - 1) * dstr[d]; nonneg = nonneg && sstr[d] >= 0 && dstr[d] >= 0; }
   const int64_t lim = (int64_t)1 << 31;
-  if (nonneg && total < lim && max_s < lim && max_d < lim) permute_kernel<uint32_t><<<ew_grid(total, 256, 2), 256, 0, S(stream)>>>(src, dst, a, total, accumulate);
-  else permute_kernel<int64_t><<<ew_grid(total, 256, 2), 256, 0, S(stream)>>>(src, dst, a, total, accumulate);
+  // float4 form: innermost dimension contiguous on both sides, a multiple of 4 long, every other stride and both base pointers 16-byte aligned
+  bool vec = ndim >= 1 && sstr[ndim - 1] == 1 && dstr[ndim - 1] == 1 && shape[ndim - 1] % 4 == 0 && al16(src) && al16(dst);
+  for (int d = 0; d + 1 < ndim && vec; ++d) vec = sstr[d] % 4 == 0 && dstr[d] % 4 == 0;
+  if (vec) {
+    a.shape[ndim - 1] /= 4;
+    for (int d = 0; d + 1 < ndim; ++d) { a.sstr[d] /= 4; a.dstr[d] /= 4; }
+    total /= 4;
+    if (nonneg && max_s < lim && max_d < lim)
+      permute_kernel<uint32_t, float4><<<ew_grid(total, 256, 1), 256, 0, S(stream)>>>((const float4*)src, (float4*)dst, a, total, accumulate);
+    else
+      permute_kernel<int64_t, float4><<<ew_grid(total, 256, 1), 256, 0, S(stream)>>>((const float4*)src, (float4*)dst, a, total, accumulate);
+  } else if (nonneg && total < lim && max_s < lim && max_d < lim) permute_kernel<uint32_t, float><<<ew_grid(total, 256, 2), 256, 0, S(stream)>>>(src, dst, a, total, accumulate);
+  else permute_kernel<int64_t, float><<<ew_grid(total, 256, 2), 256, 0, S(stream)>>>(src, dst, a, total, accumulate);
   DGMR_CHECK_LAUNCH("dgmr_permute");
   return 0;
 }
@@ -828,7 +904,6 @@ int dgmr_reduce_mid(const float* x, float* y, int64_t A, int64_t R, int64_t C, i
   DGMR_CHECK_LAUNCH("dgmr_reduce_mid");
   return 0;
 }
-static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 int dgmr_axpby(float a, const float* x, float b, const float* y, float* out, int64_t n, dgmr_stream_t stream) {
   if (n == 0) return 0;
   if (n % 4 == 0 && al16(x) && al16(out) && (!y || al16(y)))
@@ -969,9 +1044,14 @@ int dgmr_bn_bwd_reduce(const float* dy, const float* x, const float* a, const fl
   DGMR_CUDA(cudaMemsetAsync(red, 0, sizeof(double) * 2 * G * C, S(stream)));
   int64_t chunk = bn_chunk(rows, G);
   dim3 grid((unsigned)ceil_div(rows, chunk), G);
-  if (C % 4 == 0 && al16(dy) && al16(x) && al16(a) && al16(b) && al16(mean) && al16(invstd))
-    bn_bwd_reduce4_kernel<<<grid, 256, 256 * 8 * sizeof(double), S(stream)>>>(dy, (const float4*)x, (const float4*)a, (const float4*)b, (const float4*)mean,
-                                                                              (const float4*)invstd, red, rows, C / 4, chunk, relu, up2, H, W);
+  if (C % 4 == 0 && al16(dy) && al16(x) && al16(a) && al16(b) && al16(mean) && al16(invstd) && (!up2 || rows * G < ((int64_t)1 << 31))) {
+    if (up2)
+      bn_bwd_reduce4_kernel<true><<<grid, 256, 256 * 8 * sizeof(double), S(stream)>>>(dy, (const float4*)x, (const float4*)a, (const float4*)b, (const float4*)mean,
+                                                                                      (const float4*)invstd, red, rows, C / 4, chunk, relu, H, W);
+    else
+      bn_bwd_reduce4_kernel<false><<<grid, 256, 256 * 8 * sizeof(double), S(stream)>>>(dy, (const float4*)x, (const float4*)a, (const float4*)b, (const float4*)mean,
+                                                                                       (const float4*)invstd, red, rows, C / 4, chunk, relu, H, W);
+  }
   else
     bn_bwd_reduce_kernel<<<grid, 256, 256 * 2 * sizeof(double), S(stream)>>>(dy, x, a, b, mean, invstd, red, rows, C, chunk, relu, up2, H, W);
   DGMR_CHECK_LAUNCH("dgmr_bn_bwd_reduce");
@@ -985,13 +1065,16 @@ int dgmr_bn_bwd_apply(const float* dy, const float* x, const float* a, const flo
   const float* oscale = out_scale;
   int64_t total = (int64_t)G * rows * C;
   if (dx && total) {
-    if (C % 4 == 0 && al16(dy) && al16(x) && al16(dx) && al16(a) && al16(b) && al16(mean) && al16(invstd) && al16(oscale) && al16(dx_add))
-      if (total * (up2 ? 4 : 1) < (int64_t)1 << 31)
-        bn_bwd_apply4_kernel<uint32_t><<<ew_grid(total / 4, 256, 1), 256, 0, S(stream)>>>(dy, (const float4*)x, (const float4*)a, (const float4*)b, (const float4*)mean,
-                                                                                         (const float4*)invstd, red, (float4*)dx, rows, G, C / 4, relu, up2, H, W, training, (const float4*)oscale, rnd, (const float4*)dx_add);
-      else
-        bn_bwd_apply4_kernel<int64_t><<<ew_grid(total / 4, 256, 1), 256, 0, S(stream)>>>(dy, (const float4*)x, (const float4*)a, (const float4*)b, (const float4*)mean,
-                                                                                        (const float4*)invstd, red, (float4*)dx, rows, G, C / 4, relu, up2, H, W, training, (const float4*)oscale, rnd, (const float4*)dx_add);
+    if (C % 4 == 0 && al16(dy) && al16(x) && al16(dx) && al16(a) && al16(b) && al16(mean) && al16(invstd) && al16(oscale) && al16(dx_add) &&
+        (!up2 || rows * G < ((int64_t)1 << 31))) {
+      const int64_t chunk = bn_chunk(rows, G);
+      dim3 grid((unsigned)ceil_div(rows, chunk), G);
+#define DGMR_BNA(U_, A_) bn_bwd_apply4_kernel<U_, A_><<<grid, 256, 0, S(stream)>>>(dy, (const float4*)x, (const float4*)a, (const float4*)b, (const float4*)mean, \
+        (const float4*)invstd, red, (float4*)dx, rows, C / 4, chunk, relu, H, W, training, (const float4*)oscale, rnd, (const float4*)dx_add)
+      if (up2) { if (dx_add) DGMR_BNA(true, true); else DGMR_BNA(true, false); }
+      else { if (dx_add) DGMR_BNA(false, true); else DGMR_BNA(false, false); }
+#undef DGMR_BNA
+    }
     else
       bn_bwd_apply_kernel<<<ew_grid(total, 256, 2), 256, 0, S(stream)>>>(dy, x, a, b, mean, invstd, red, dx, rows, G, C, relu, up2, H, W, training, oscale, rnd, dx_add);
     DGMR_CHECK_LAUNCH("dgmr_bn_bwd_apply");

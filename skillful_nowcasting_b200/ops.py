@@ -40,6 +40,9 @@ class config:
     upconv = True
     # 3x3x3 weight gradients of narrow layers with the depth taps folded into the channel axis (see _Conv.backward)
     fold_depth_wgrad = True
+    # G = 1 spectrally normalised convolutions: scale gradient from the weight gradient (<dW, W>/s per output channel) instead of an
+    # activation-side reduction in the backward prologue (see _Conv.forward)
+    dscale_from_wgrad = True
     _force_upconv = False   # tests: take the sub-pixel path on the host emulator too
 
 
@@ -153,8 +156,18 @@ class _FoldDepth3(Function):
         x = _c(x)
         n, d, h, w, cp = x.shape
         co = pad8(3 * c)
-        out = _zeros((n, d, h, w, co), x)
         hw = h * w
+        if c % 4 == 0 and d >= 2:
+            # every element is written exactly once (float4 permutes): the three shifted copies, the two out-of-range depth slices and
+            # the padding channels from a zero row -- no full-tensor memset
+            out = _new((n, d, h, w, co), x)
+            zrow = _zeros((max(c, co - 3 * c, 4),), x)
+            _be().permute(zrow, out, (n, hw, c), (0, 0, 1), (d * hw * co, co, 1), False, 0, 0)                               # kd = 0 at d = 0
+            _be().permute(zrow, out, (n, hw, c), (0, 0, 1), (d * hw * co, co, 1), False, 0, (d - 1) * hw * co + 2 * c)       # kd = 2 at d = D-1
+            if co > 3 * c:
+                _be().permute(zrow, out, (n * d * hw, co - 3 * c), (0, 1), (co, 1), False, 0, 3 * c)
+        else:
+            out = _zeros((n, d, h, w, co), x)
         for kd in range(3):
             sh = kd - 1                                   # out[d] <- x[d + sh]
             d0, d1 = max(0, -sh), min(d, d - sh)          # valid output depths
@@ -718,9 +731,12 @@ class _Conv(Function):
         if round_out:
             y._dgmr_tf32 = True
         need_s = scale is not None and scale.requires_grad
-        need_y = act == ACT_RELU or need_s
-        ctx.save_for_backward(x, w, bias_c, scale_c, res_c if need_s else None, y if need_y else None)
-        ctx.meta = (ci0, cin, G, act, (kd, kh, kw), res is not None, exact_dscale, res_up2, pool)
+        # one sigma for the whole batch (G = 1): the scale gradient comes from the weight gradient, <dW[co], W[co]> / s[co], instead of a
+        # reduction over the activations -- y (and the residual) need not be kept or re-read for it
+        wdot = bool(need_s and G == 1 and w.requires_grad and not exact_dscale and config.dscale_from_wgrad)
+        need_y = act == ACT_RELU or (need_s and not wdot)
+        ctx.save_for_backward(x, w, bias_c, scale_c, res_c if (need_s and not wdot) else None, y if need_y else None)
+        ctx.meta = (ci0, cin, G, act, (kd, kh, kw), res is not None, exact_dscale, res_up2, pool, wdot)
         if pool:
             pd, ph, pw = pool
             yp = _new((n, d // pd, h // ph, wd // pw, cout), x)
@@ -731,7 +747,7 @@ class _Conv(Function):
     @staticmethod
     def backward(ctx, dy):
         x, w, bias, scale, res, y = ctx.saved_tensors
-        ci0, cin, G, act, (kd, kh, kw), has_res, exact_dscale, res_up2, pool = ctx.meta
+        ci0, cin, G, act, (kd, kh, kw), has_res, exact_dscale, res_up2, pool, wdot = ctx.meta
         be = _be()
         dy = _c(dy)
         n, d, h, wd, cp = x.shape   # cp > cin: zero-padded input channels
@@ -747,6 +763,8 @@ class _Conv(Function):
         need_b = need_b and bias is not None
         need_s = need_s and scale is not None
         need_r = need_r and has_res
+        wdot = wdot and need_s
+        need_w = need_w or wdot
         dz, dpre, dbias, dscale = dy, dy, None, None
         if act == ACT_RELU or scale is not None or need_b:
             need_dz = need_x or need_w
@@ -755,9 +773,9 @@ class _Conv(Function):
             dbias = _new((cout,), dy) if need_b else None
             dscale = _new((G, cout), dy) if need_s else None
             tc_bwd = (need_x and _tc_fwd(n, d, h, wd, cout, cp, kd, kh, kw)) or (need_w and _tc_wgrad(n, d, h, wd, cp, cout, kd, kh, kw))
-            be.conv_bwd_prep(dy, y, res if need_s else None, bias, scale, dz, dpre, dbias, dscale, rows, G, cout,
+            be.conv_bwd_prep(dy, y, res if (need_s and not wdot) else None, bias, scale, dz, dpre, dbias, None if wdot else dscale, rows, G, cout,
                              act | (FLAG_ROUND_TF32 if (tc_bwd and dz is not None and config._dbg_round_dz) else 0),
-                             up_hw=((h, wd) if (res_up2 and need_s and res is not None) else (0, 0)),
+                             up_hw=((h, wd) if (res_up2 and need_s and not wdot and res is not None) else (0, 0)),
                              pool=((pool[0], pool[1], pool[2], d, h, wd) if pool else None))
             if need_s and exact_dscale:
                 # the <dY, Y-b-res>/scale identity divides by the scale, which may be exactly 0 (attention gamma starts at 0,
@@ -810,6 +828,11 @@ class _Conv(Function):
                     be.unpack_wgrad(dwp, dw, cout, cintot, ci0, cin, taps, False)
                 else:  # drop the padded channels: dw[co][ci0+ci][tap] = dwp[tap][co][ci], ci < cin
                     be.permute(dwp, dw, (taps, cout, cin), (cout * cp, cp, 1), (1, cintot * taps, taps), False, 0, ci0 * taps)
+        if wdot:
+            taps = kd * kh * kw
+            be.rowdot_div(dw, w, scale, dscale, cout, cin * taps, w.shape[1] * taps, ci0 * taps)
+            if not ctx.needs_input_grad[1]:
+                dw = None
         dres = None
         if need_r:
             dres = dpre

@@ -229,6 +229,14 @@ class EmuBackend:
         g = torch.einsum("g,gr,gk->rk", coef, u_hist, v_hist).reshape(dw.shape)
         dw.add_(g) if accumulate else dw.copy_(g)
 
+    def rowdot_div(self, a, b, denom, out, rows, cols, ld, offset=0):
+        av = a.reshape(rows, ld)[:, offset:offset + cols].double()
+        bv = b.reshape(rows, ld)[:, offset:offset + cols].double()
+        v = (av * bv).sum(1)
+        if denom is not None:
+            v = v / denom.reshape(-1)[:rows].double()
+        out.reshape(-1)[:rows].copy_(v.float())
+
     def sn_bwd_multi(self, items):
         for it in items:
             self.sn_bwd(it["d_inv_sigma"], it["inv_sigma"], it["u_hist"], it["v_hist"], it["dw"], it["R"], it["K"], it["G"], it["accumulate"])

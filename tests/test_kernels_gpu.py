@@ -38,6 +38,24 @@ def test_permute_and_reduce(cuda_backend):
     _both("permute", [src, dst, (4, 5), (5, 1), (10, 1), True, 7, 3], cuda_backend, rtol=0, atol=1e-7)
     x = torch.randn(3 * 37 * 50)
     _both("reduce_mid", [x, torch.zeros(150), 3, 37, 50], cuda_backend)
+    # float4 form (contiguous innermost dimension, 16-byte aligned offsets): the depth-fold copy, a zero-stride broadcast, accumulate
+    src = torch.randn(2 * 5 * 6 * 8)
+    dst = torch.zeros(2 * 5 * 6 * 24)
+    _both("permute", [src, dst, (2, 4, 6, 8), (240, 48, 8, 1), (720, 144, 24, 1), False, 48, 8], cuda_backend, rtol=0, atol=0)
+    _both("permute", [torch.zeros(8), torch.randn(2 * 5 * 6 * 24), (2, 6, 8), (0, 0, 1), (720, 24, 1), False, 0, 16], cuda_backend, rtol=0, atol=0)
+    _both("permute", [src, torch.randn(2 * 5 * 6 * 24), (2, 5, 6, 8), (240, 48, 8, 1), (720, 144, 24, 1), True, 0, 16], cuda_backend, rtol=0, atol=1e-7)
+    # misaligned offset: must take the scalar path
+    _both("permute", [src, torch.randn(2 * 5 * 6 * 24), (2, 5, 6, 8), (240, 48, 8, 1), (720, 144, 24, 1), False, 0, 3], cuda_backend, rtol=0, atol=0)
+
+
+def test_rowdot_div(cuda_backend):
+    """dL/ds[co] = <dW[co], W[co]> / s[co] over a channel slice of an OIHW weight (dgmr_rowdot_div)."""
+    torch.manual_seed(3)
+    cout, cintot, taps, ci0, cin = 37, 24, 9, 8, 12
+    a, b = torch.randn(cout, cintot, taps), torch.randn(cout, cintot, taps)
+    den = torch.rand(cout) + 0.5
+    _both("rowdot_div", [a, b, den, torch.empty(1, cout), cout, cin * taps, cintot * taps, ci0 * taps], cuda_backend, rtol=1e-5, atol=1e-5)
+    _both("rowdot_div", [a, b, None, torch.empty(cout), cout, cintot * taps, cintot * taps, 0], cuda_backend, rtol=1e-5, atol=1e-5)
 
 
 def test_pointwise(cuda_backend):
@@ -79,7 +97,8 @@ def test_gru_pointwise(cuda_backend):
     _both("gru_gate_bwd", [g, pre, ch, h, torch.empty(rows, ch), ch, torch.empty(rows, ch), False, rows, ch], cuda_backend, atol=1e-6)
 
 
-@pytest.mark.parametrize("G,rows,C,relu,up2", [(1, 500, 24, True, False), (3, 2 * 8 * 8, 96, True, True), (4, 6, 768, False, False), (2, 4 * 4, 4, True, True)])
+@pytest.mark.parametrize("G,rows,C,relu,up2", [(1, 500, 24, True, False), (3, 2 * 8 * 8, 96, True, True), (4, 6, 768, False, False), (2, 4 * 4, 4, True, True),
+                                               (2, 700000, 8, True, False), (1, 2 * 512 * 512, 8, True, True)])   # long chunks: the multi-row main loops
 def test_batchnorm(cuda_backend, G, rows, C, relu, up2):
     torch.manual_seed(4)
     H = W = int((rows // 2) ** 0.5) if up2 else 1
@@ -187,6 +206,28 @@ def test_conv_bwd_prep(cuda_backend, G, rows, C, act):
     bias, scale = torch.randn(C), torch.rand(G, C) + 0.5
     args = [dy, y, res, bias, scale, torch.empty(G * rows, C), torch.empty(G * rows, C), torch.zeros(C), torch.zeros(G, C), rows, G, C, act]
     _both("conv_bwd_prep", args, cuda_backend, rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("G,rows,C", [(1, 1000, 48), (2, 333, 96), (1, 45, 7)])
+@pytest.mark.parametrize("variant", ["no_y", "y_no_dscale", "dscale_no_res", "many_rows"])
+def test_conv_bwd_prep_variants(cuda_backend, G, rows, C, variant):
+    """The template variants of the prologue: no y at all (scale / bias only: the G = 1 form whose scale gradient comes from dgmr_rowdot_div),
+    ReLU mask without a scale gradient, scale gradient without a residual; long row chunks (several 4-row groups + tail, fp64 flushes)."""
+    torch.manual_seed(28)
+    if variant == "many_rows":
+        rows = rows * 37
+    dy, y, res = (torch.randn(G * rows, C) for _ in range(3))
+    bias, scale = torch.randn(C), torch.rand(G, C) + 0.5
+    dz, dpre, dbias, dscale = torch.empty(G * rows, C), torch.empty(G * rows, C), torch.zeros(C), torch.zeros(G, C)
+    if variant == "no_y":
+        args = [dy, None, None, bias, scale, dz, None, dbias, None, rows, G, C, 256]
+    elif variant == "y_no_dscale":
+        args = [dy, y, None, bias, scale, dz, dpre, dbias, None, rows, G, C, 1]
+    elif variant == "dscale_no_res":
+        args = [dy, y, None, bias, scale, dz, None, None, dscale, rows, G, C, 257]
+    else:
+        args = [dy, y, res, bias, scale, dz, dpre, dbias, dscale, rows, G, C, 1]
+    _both("conv_bwd_prep", args, cuda_backend, rtol=1e-4, atol=2e-4)
 
 
 @pytest.mark.parametrize("G,n_img,hw,C,act", [(2, 4, (8, 12), 24, 0), (1, 3, (4, 4), 7, 1)])
