@@ -51,7 +51,8 @@ enum { DGMR_FLAG_ROUND_OUT = 1024 };
  * materialising the upsampled tensor.  H and W must be even. */
 enum { DGMR_FLAG_RES_UP2 = 2048 };
 /* conv algorithm selector */
-enum { DGMR_ALGO_AUTO = 0, DGMR_ALGO_SIMT = 1, DGMR_ALGO_UMMA = 2 /* plain tcgen05 kernel */, DGMR_ALGO_UMMA_PATCH = 3 /* halo-patch tcgen05 kernel */ };
+enum { DGMR_ALGO_AUTO = 0, DGMR_ALGO_SIMT = 1, DGMR_ALGO_UMMA = 2 /* plain tcgen05 kernel */, DGMR_ALGO_UMMA_PATCH = 3 /* halo-patch tcgen05 kernel */,
+       DGMR_ALGO_UMMA_KWSTACK = 4 /* narrow outputs: column taps stacked along N (conv_kwstack.cu) */ };
 /* tensor-core operand precision: 1xTF32 (what cuDNN does by default for the reference) or
  * 3xTF32 error-compensated (hi*hi + hi*lo + lo*hi), ~fp32 accuracy */
 enum { DGMR_PREC_TF32 = 0, DGMR_PREC_3XTF32 = 1 };

@@ -1,0 +1,310 @@
+// Narrow-output 3x3(x3) convolutions on tcgen05 with the three COLUMN taps stacked along the MMA's N dimension.
+//
+// A layer with few output channels (Cout = 48: the first temporal-discriminator block, the last sampler block, their dgrads) is the worst case of
+// the plain implicit-GEMM kernel (conv_umma.cu): a kind::tf32 MMA of M = 128, N = 48 still occupies the tensor pipe for its ~60-cycle minimum (40 % of
+// peak at best), and every filter tap re-reads its 128-pixel activation tile from L2 (27 re-reads for a 3x3x3 filter), which is what actually bounds
+// those launches (~45 B/clk/SM of L2->SM traffic).  Here a tile is 128 consecutive pixels of WHOLE image rows (W in {32, 64, 128}) and one MMA multiplies
+// the activation tile of filter row (kd, kh) -- unshifted in w -- with the weights of its three column taps side by side,
+//
+//     T[p][kw*Cout + co] += sum_ci x[p + (kd-1, kh-1, 0)][ci] * W[kd][kh][kw][co][ci]            N = 3*Cout (144: 72 cycles for three taps),
+//
+// which is a contiguous [3*Cout][Cin] slab of the ordinary packed weights ([tap][Cout][Cin], taps ordered (kd, kh, kw)): no new packing.  The
+// column shift moves to the epilogue:   y[p] = T[p-1][kw=0] + T[p][kw=1] + T[p+1][kw=2],   with the first / last pixel of an image row dropping the term
+// that would come from the zero padding -- because tiles are whole rows, every p +- 1 that is needed lies inside the tile.  Rows live in TMEM lanes, so
+// the shift is a warp shuffle plus a 16-float exchange between neighbouring epilogue warps.  Per tile that is 3x fewer activation bytes through
+// L2->SM and 2.5x fewer tensor-pipe cycles than the tap-by-tap form.  Same persistent structure as conv_umma_fwd_persist_kernel: one TMA warp, one MMA
+// warp, four epilogue warps, double-buffered accumulators (2 x 3*Cout TMEM columns), stages released in groups.
+#include "umma_common.cuh"
+
+namespace dgmr {
+
+struct KwStackParams {
+  int N, D, H, W, Cin, Cout, kd, kh, G;
+  int bh;                // image rows per tile: 128 / W
+  int BN;                // 3 * Cout
+  int stages, cg, tmem_cols, act, round_out, res_up2;
+  const float* bias; const float* scale; const float* res; float* y;
+};
+
+constexpr int kKwThreads = 192;  // warp0 TMA, warp1 MMA, warps 2..5 epilogue
+
+template <int BK>
+__global__ void __launch_bounds__(kKwThreads, 1)
+conv_umma_kwstack_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const KwStackParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t a_bytes = 128u * BK * 4u, b_bytes = (uint32_t)p.BN * BK * 4u;
+  const uint32_t b_bytes_al = (b_bytes + 1023u) & ~1023u;
+  const uint32_t stage_bytes = a_bytes + b_bytes_al;
+  const uint32_t bar_base = base + p.stages * stage_bytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (p.stages + s); };
+  auto tmem_full = [&](int bsel) { return bar_base + 8u * (2 * p.stages + bsel); };
+  auto tmem_empty = [&](int bsel) { return bar_base + 8u * (2 * p.stages + 2 + bsel); };
+  const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * p.stages + 4);
+  volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_addr - raw));
+  const uint32_t epi_base = (tmem_ptr_addr + 8u + 127u) & ~127u;     // 4 epilogue warps x 2 KB transpose staging
+  const uint32_t xchg_base = epi_base + 4u * 2048u;                  // [2 parities][4 warps][2: T0 of lane 31 | T2 of lane 0][16 floats]
+
+  const int tiles_h = p.H / p.bh;
+  const int64_t total_tiles = (int64_t)p.N * p.D * tiles_h;
+  auto decode = [&](int64_t t, int& n0, int& d0, int& h0) {
+    h0 = (int)(t % tiles_h) * p.bh; t /= tiles_h;
+    d0 = (int)(t % p.D); n0 = (int)(t / p.D);
+  };
+  const int rtaps = p.kd * p.kh;                 // filter rows: (kd, kh)
+  const int kchunks = (p.Cin + BK - 1) / BK;
+  const int num_kb = rtaps * kchunks;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int bsel = 0; bsel < 2; ++bsel) { mbar_init(tmem_full(bsel), 1); mbar_init(tmem_empty(bsel), 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) { __syncwarp(); tmem_alloc(tmem_ptr_addr, (uint32_t)p.tmem_cols); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_gen;
+
+  if (warp == 0) {
+    // ===== TMA producer: one continuous stream of K blocks over all of this CTA's tiles
+    int s = 0, g = 0, sg = 0; uint32_t ph = 0;
+    for (int64_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      int n0, d0, h0; decode(t, n0, d0, h0);
+      int rt = 0, chunk = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int c0 = chunk * BK;
+        const int tkh = rt % p.kh, tkd = rt / p.kh;
+        if (sg == 0) mbar_wait(empty_bar(g), ph ^ 1u);
+        if (elect_one()) {
+          mbar_expect_tx(full_bar(s), a_bytes + b_bytes);
+          const uint32_t sa = base + s * stage_bytes;
+          tma_load_5d(sa, &tmA, full_bar(s), c0, 0, h0 + tkh - p.kh / 2, d0 + tkd - p.kd / 2, n0);
+          tma_load_3d(sa + a_bytes, &tmB, full_bar(s), c0, 0, rt);
+        }
+        __syncwarp();
+        if (++chunk == kchunks) { chunk = 0; ++rt; }
+        if (++sg == p.cg) { sg = 0; ++g; }
+        if (++s == p.stages) { s = 0; g = 0; ph ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((128u >> 4) << 24);
+    constexpr uint32_t row_bytes = BK * 4u;
+    constexpr uint32_t layout = row_bytes == 128 ? 2u : (row_bytes == 64 ? 4u : 6u);
+    constexpr uint32_t sbo = 8u * row_bytes;
+    const int tail_ks = (p.Cin % BK) ? (p.Cin % BK) / 8 : BK / 8;
+    int s = 0, g = 0, sg = 0; uint32_t ph = 0, it = 0;
+    for (int64_t t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+      const int bsel = it & 1; const uint32_t phacc = (it >> 1) & 1u;
+      mbar_wait(tmem_empty(bsel), phacc ^ 1u);       // the epilogue has drained this accumulator buffer
+      tc_fence_after();
+      const uint32_t tacc = tmem_base + (uint32_t)(bsel * p.BN);
+      int chunk_i = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(full_bar(s), ph);
+        tc_fence_after();
+        const uint32_t sa = base + s * stage_bytes;
+        const uint64_t adesc = make_desc(sa, sbo, layout);
+        const uint64_t bdesc = make_desc(sa + a_bytes, sbo, layout);
+        const bool last_chunk = (++chunk_i == kchunks);
+        if (last_chunk) chunk_i = 0;
+        const bool last_kb = (kb + 1 == num_kb);
+        const bool rel = (sg + 1 == p.cg) || (last_kb && t + gridDim.x >= total_tiles);   // group full, or the very last K block
+        if (elect_one()) {
+          umma_tf32(tacc, adesc, bdesc, idesc, kb != 0 ? 1u : 0u);
+          if (last_chunk) {
+#pragma unroll
+            for (int k = 1; k < BK / 8; ++k)
+              if (k < tail_ks) umma_tf32(tacc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, 1u);
+          } else {
+#pragma unroll
+            for (int k = 1; k < BK / 8; ++k) umma_tf32(tacc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, 1u);
+          }
+          if (rel) umma_commit(empty_bar(g));
+          if (last_kb) umma_commit(tmem_full(bsel));
+        }
+        __syncwarp();
+        if (++sg == p.cg) { sg = 0; ++g; }
+        if (++s == p.stages) { s = 0; g = 0; ph ^= 1u; }
+      }
+    }
+  } else {
+    // ===== epilogue (4 warps): warp w may only touch TMEM lanes [32*(w%4), +32).  Lane = tile row r = 32q + lane = pixel (h0 + r / W, r % W).
+    const int q = warp & 3;
+    const uint32_t stg = epi_base + (uint32_t)q * 2048u;
+    const int lr = lane >> 2, lc = lane & 3;
+    const uint32_t st_row = stg + (uint32_t)lane * 64u, st_sw = (uint32_t)((lane >> 1) & 3);
+    const int my_w = (q * 32 + lane) % p.W;
+    const bool has_prev = my_w != 0, has_next = my_w != p.W - 1;     // neighbours inside the image row (else: zero padding, term dropped)
+    const bool cross = p.W > 32;                                     // rows continue across epilogue-warp boundaries
+    uint32_t it = 0, par = 0;
+    for (int64_t t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+      int n0, d0, h0; decode(t, n0, d0, h0);
+      const int bsel = it & 1; const uint32_t phacc = (it >> 1) & 1u;
+      uint32_t mrow[4], rrow[4]; const float* srow[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int rj = q * 32 + lr + 8 * j;
+        const int wj = rj % p.W, hj = h0 + rj / p.W;
+        mrow[j] = (uint32_t)(((n0 * p.D + d0) * p.H + hj) * p.W + wj) * (uint32_t)p.Cout + 4u * lc;
+        rrow[j] = p.res_up2 ? (uint32_t)(((n0 * p.D + d0) * (p.H >> 1) + (hj >> 1)) * (p.W >> 1) + (wj >> 1)) * (uint32_t)p.Cout + 4u * lc : mrow[j];
+        srow[j] = p.scale ? p.scale + (int64_t)(n0 / (p.N / p.G)) * p.Cout : nullptr;
+      }
+      mbar_wait(tmem_full(bsel), phacc);
+      tc_fence_after();
+      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(bsel * p.BN);
+      for (int c = 0; c < p.Cout; c += 16, par ^= 1u) {
+        float4 rr[4];
+        if (p.res) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) rr[j] = __ldg(reinterpret_cast<const float4*>(p.res + rrow[j] + c));
+        }
+        float t0[16], v[16], t2[16];
+        tmem_ld16(trow + (uint32_t)c, t0);
+        tmem_ld16(trow + (uint32_t)(p.Cout + c), v);
+        tmem_ld16(trow + (uint32_t)(2 * p.Cout + c), t2);
+        if (cross) {
+          const uint32_t xb = xchg_base + par * 512u + (uint32_t)q * 128u;
+          if (lane == 31) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(xb + 16u * k), "f"(t0[4 * k]), "f"(t0[4 * k + 1]), "f"(t0[4 * k + 2]), "f"(t0[4 * k + 3]) : "memory");
+          }
+          if (lane == 0) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(xb + 64u + 16u * k), "f"(t2[4 * k]), "f"(t2[4 * k + 1]), "f"(t2[4 * k + 2]), "f"(t2[4 * k + 3]) : "memory");
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");    // the four epilogue warps
+        }
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          const float a = __shfl_up_sync(0xffffffffu, t0[k], 1);      // T[r-1][kw=0]
+          const float b = __shfl_down_sync(0xffffffffu, t2[k], 1);    // T[r+1][kw=2]
+          t0[k] = a; t2[k] = b;
+        }
+        if (cross) {
+          if (lane == 0 && has_prev) {        // r-1 is lane 31 of the previous warp (has_prev => q > 0)
+            const uint32_t xa = xchg_base + par * 512u + (uint32_t)(q - 1) * 128u;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(t0[4 * k]), "=f"(t0[4 * k + 1]), "=f"(t0[4 * k + 2]), "=f"(t0[4 * k + 3]) : "r"(xa + 16u * k) : "memory");
+          }
+          if (lane == 31 && has_next) {       // r+1 is lane 0 of the next warp (has_next => q < 3)
+            const uint32_t xa = xchg_base + par * 512u + (uint32_t)(q + 1) * 128u + 64u;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(t2[4 * k]), "=f"(t2[4 * k + 1]), "=f"(t2[4 * k + 2]), "=f"(t2[4 * k + 3]) : "r"(xa + 16u * k) : "memory");
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < 16; ++k) v[k] += (has_prev ? t0[k] : 0.f) + (has_next ? t2[k] : 0.f);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(st_row + (((uint32_t)k ^ st_sw) << 4)), "f"(v[4 * k]), "f"(v[4 * k + 1]),
+                       "f"(v[4 * k + 2]), "f"(v[4 * k + 3]) : "memory");
+        __syncwarp();
+        const int co = c + 4 * lc;
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.bias) b4 = make_float4(__ldg(p.bias + co), __ldg(p.bias + co + 1), __ldg(p.bias + co + 2), __ldg(p.bias + co + 3));
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int row = lr + 8 * j;
+          float4 o;
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(o.x), "=f"(o.y), "=f"(o.z), "=f"(o.w)
+                       : "r"(stg + (uint32_t)row * 64u + (((uint32_t)lc ^ (uint32_t)((row >> 1) & 3)) << 4)) : "memory");
+          if (srow[j]) { o.x *= __ldg(srow[j] + co); o.y *= __ldg(srow[j] + co + 1); o.z *= __ldg(srow[j] + co + 2); o.w *= __ldg(srow[j] + co + 3); }
+          o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
+          if (p.res) { o.x += rr[j].x; o.y += rr[j].y; o.z += rr[j].z; o.w += rr[j].w; }
+          if (p.act == DGMR_ACT_RELU) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+          if (p.round_out) o = rna_tf32_e4(o);
+          *reinterpret_cast<float4*>(p.y + mrow[j] + c) = o;
+        }
+        __syncwarp();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tmem_empty(bsel)) : "memory");
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { __syncwarp(); tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols); }
+}
+
+static int kw_bk(int Cin) { return (Cin % 8 != 0) ? 0 : (Cin >= 32) ? 32 : (Cin == 16 || Cin == 24) ? 16 : 0; }
+
+bool umma_kwstack_ok(int N, int D, int H, int W, int Cin, int Cout, int kd, int kh, int kw, int G) {
+  if (kw != 3 || kh != 3 || !(kd == 1 || kd == 3)) return false;
+  if (!(W == 32 || W == 64 || W == 128) || H % (128 / W) != 0) return false;
+  if (Cout % 16 != 0 || Cout < 16 || 3 * Cout > 256) return false;
+  if (kw_bk(Cin) == 0 || (Cin < 32 && Cin != 16)) return false;
+  if (G < 1 || N % G) return false;
+  if ((int64_t)N * D * H * W * Cout >= ((int64_t)1 << 32) || (int64_t)N * D * H * W >= ((int64_t)1 << 31)) return false;   // 32-bit epilogue offsets
+  return true;
+}
+
+int launch_conv_umma_kwstack(const float* x, const float* wp, const float* bias, const float* scale, const float* res, float* y, int N, int D, int H, int W,
+                             int Cin, int Cout, int kd, int G, int act, cudaStream_t st) {
+  KwStackParams p;
+  p.round_out = (act & DGMR_FLAG_ROUND_OUT) ? 1 : 0; p.res_up2 = (act & DGMR_FLAG_RES_UP2) ? 1 : 0;
+  act &= 3;
+  p.N = N; p.D = D; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.kd = kd; p.kh = 3; p.G = G;
+  p.bh = 128 / W; p.BN = 3 * Cout;
+  p.act = act; p.bias = bias; p.scale = scale; p.res = res; p.y = y;
+  const int BK = kw_bk(Cin);
+  if (BK == 0) { set_error("conv_umma_kwstack: Cin=%d not served", Cin); return 1; }
+  p.tmem_cols = 32; while (p.tmem_cols < 2 * p.BN) p.tmem_cols <<= 1;
+  const uint32_t a_bytes = 128u * BK * 4u, b_bytes = ((uint32_t)p.BN * BK * 4u + 1023u) & ~1023u;
+  const uint32_t stage_bytes = a_bytes + b_bytes;
+  int stages = (int)((196u * 1024u) / stage_bytes);
+  if (stages > 9) stages = 9;
+  if (stages < 2) { set_error("conv_umma_kwstack: stage too large"); return 1; }
+  p.cg = 1;
+  if (stages >= 6) { stages = stages / 3 * 3; p.cg = 3; } else if (stages >= 4) { stages = stages / 2 * 2; p.cg = 2; }
+  p.stages = stages;
+  const size_t smem = (size_t)stages * stage_bytes + 1024 + 8 * (2 * stages + 6) + 128 + 4 * 2048 + 1024;
+  CUtensorMap tmA, tmB;
+  {
+    uint64_t dims[5] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)D, (uint64_t)N};
+    uint64_t str[4] = {(uint64_t)Cin * 4, (uint64_t)W * Cin * 4, (uint64_t)H * W * Cin * 4, (uint64_t)D * H * W * Cin * 4};
+    uint32_t box[5] = {(uint32_t)BK, (uint32_t)W, (uint32_t)p.bh, 1u, 1u};
+    int e = make_tmap(&tmA, x, 5, dims, str, box, BK * 4);
+    if (e) return e;
+  }
+  {
+    // packed weights [tap = (kd, kh, kw)][Cout][Cin] seen as [(kd, kh)][kw*Cout + co][Cin]
+    uint64_t dims[3] = {(uint64_t)Cin, (uint64_t)(3 * Cout), (uint64_t)(kd * 3)};
+    uint64_t str[2] = {(uint64_t)Cin * 4, (uint64_t)3 * Cout * Cin * 4};
+    uint32_t box[3] = {(uint32_t)BK, (uint32_t)p.BN, 1u};
+    int e = make_tmap(&tmB, wp, 3, dims, str, box, BK * 4);
+    if (e) return e;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(conv_umma_kwstack_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(224 * 1024)) != cudaSuccess ||
+        cudaFuncSetAttribute(conv_umma_kwstack_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(224 * 1024)) != cudaSuccess) {
+      set_error("conv_umma_kwstack: cannot raise dynamic smem limit"); return 2;
+    }
+    attr_set = true;
+  }
+  const int64_t total_tiles = (int64_t)N * D * (H / p.bh);
+  int64_t g = sm_count();
+  if (g > total_tiles) g = total_tiles;
+  // one CTA per SM (2 x 3*Cout TMEM columns each): pad the shared-memory request so that a second CTA can never become resident and block in tcgen05.alloc
+  size_t req = smem;
+  if (req < (size_t)232448 / 2 + 1024) req = (size_t)232448 / 2 + 1024;
+  if (BK == 32) conv_umma_kwstack_kernel<32><<<(unsigned)g, kKwThreads, req, st>>>(tmA, tmB, p);
+  else conv_umma_kwstack_kernel<16><<<(unsigned)g, kKwThreads, req, st>>>(tmA, tmB, p);
+  DGMR_CHECK_LAUNCH("conv_umma_kwstack");
+  return 0;
+}
+
+}  // namespace dgmr

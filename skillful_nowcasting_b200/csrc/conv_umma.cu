@@ -21,6 +21,9 @@ namespace dgmr {
 
 int launch_conv_simt_fwd(const float*, const float*, const float*, const float*, const float*, float*, int, int, int, int, int, int, int, int, int, int, int, cudaStream_t);
 int launch_conv_simt_wgrad(const float*, const float*, float*, int, int, int, int, int, int, int, int, int, cudaStream_t);
+bool umma_kwstack_ok(int N, int D, int H, int W, int Cin, int Cout, int kd, int kh, int kw, int G);   // conv_kwstack.cu
+int launch_conv_umma_kwstack(const float* x, const float* wp, const float* bias, const float* scale, const float* res, float* y, int N, int D, int H, int W,
+                             int Cin, int Cout, int kd, int G, int act, cudaStream_t st);
 
 struct UmmaConvParams {
   int N, D, H, W, Cin, Cout, kd, kh, kw, G;
@@ -1231,6 +1234,7 @@ struct UmmaOptions {
   int patch_tg = -1;         // 1: release halo-patch weight tiles per tap instead of per filter row
   int prefer_patch = -1;     // 1: AUTO dispatch takes the halo-patch kernel whenever it supports the shape (parity tests on small shapes)
   int subpix_wgrad_row = -1; // sub-pixel weight gradient: 0 = always the tap-wise kernel, 1 = the row kernel whenever W % 32 == 0 (tests)
+  int kwstack = -1;          // 0: never the column-stacked kernel (conv_kwstack.cu), 1: whenever it supports the shape (small test shapes)
   int patch_dbg = 0;         // DGMR_TUNING builds only: make the halo-patch kernel skip work
 };
 static UmmaOptions g_opt;
@@ -1867,7 +1871,7 @@ int dgmr_set_option(const char* name, int value) {
   struct { const char* n; int* v; } tab[] = {{"umma_cg", &g_opt.umma_cg}, {"umma_persist", &g_opt.umma_persist}, {"umma_persist_r", &g_opt.umma_persist_r},
                                              {"patch_pair", &g_opt.patch_pair}, {"patch_mt", &g_opt.patch_mt}, {"patch_tg", &g_opt.patch_tg},
                                              {"prefer_patch", &g_opt.prefer_patch}, {"patch_dbg", &g_opt.patch_dbg},
-                                             {"subpix_wgrad_row", &g_opt.subpix_wgrad_row}};
+                                             {"subpix_wgrad_row", &g_opt.subpix_wgrad_row}, {"kwstack", &g_opt.kwstack}};
   for (auto& t : tab)
     if (strcmp(t.n, name) == 0) { *t.v = value; return 0; }
   set_error("dgmr_set_option: unknown option '%s'", name);
@@ -1911,6 +1915,11 @@ int dgmr_conv_fwd(const float* x, const float* x_lo, const float* wp, const floa
     return launch_conv_umma_fwd(x, wp, nullptr, scale, nullptr, y, N, D, H, W, Cin, Cout, kd, kh, kw, G, DGMR_ACT_NONE, S(stream), 1);
   }
   if (algo == DGMR_ALGO_UMMA || algo == DGMR_ALGO_UMMA_PATCH) DGMR_REQUIRE(ok, "dgmr_conv_fwd: shape not supported by the tcgen05 path");
+  if (algo == DGMR_ALGO_UMMA_KWSTACK) DGMR_REQUIRE(umma_kwstack_ok(N, D, H, W, Cin, Cout, kd, kh, kw, G), "dgmr_conv_fwd: shape not supported by the column-stacked kernel");
+  // narrow outputs (Cout < 64) of at least a few waves of tiles: column taps stacked along N, the shift done in the epilogue (conv_kwstack.cu)
+  if (algo == DGMR_ALGO_UMMA_KWSTACK || (algo == DGMR_ALGO_AUTO && g_opt.kwstack != 0 && Cout < 64 && umma_kwstack_ok(N, D, H, W, Cin, Cout, kd, kh, kw, G) &&
+                                         ((int64_t)N * D * H * W >= (int64_t)128 * 2 * sm_count() || g_opt.kwstack == 1)))
+    return launch_conv_umma_kwstack(x, wp, bias, scale, res, y, N, D, H, W, Cin, Cout, kd, G, act, S(stream));
   if (algo == DGMR_ALGO_UMMA || algo == DGMR_ALGO_UMMA_PATCH || (algo == DGMR_ALGO_AUTO && ok)) {
     if (algo != DGMR_ALGO_UMMA && umma_patch_ok(N, D, H, W, Cin, Cout, kd, kh, kw, G) &&
         (algo == DGMR_ALGO_UMMA_PATCH || umma_patch_profitable(N, D, H, W, Cin, Cout))) {

@@ -177,6 +177,52 @@ def test_conv_umma_patch(cuda_backend, shape, variant):
     assert e <= 4e-3 * max(y_ref.abs().max().item(), 1), f"halo-patch kernel err {e:.3e}"
 
 
+# N, D, H, W, Cin, Cout, kd, G
+KWSTACK_SHAPES = [
+    (3, 1, 64, 64, 48, 48, 1, 1),      # W = 64: two image rows per tile, warp-boundary exchange; 32-channel chunk + 16-channel tail
+    (4, 1, 128, 128, 96, 48, 1, 2),    # W = 128: one row per tile, three warp boundaries; groups
+    (2, 5, 32, 32, 48, 48, 3, 1),      # W = 32: four rows per tile, no exchange; 3-D, odd depth
+    (2, 6, 64, 64, 48, 48, 3, 1),      # the temporal discriminator's 48 -> 48 (small)
+    (2, 1, 64, 64, 16, 48, 1, 1),      # 16-channel chunks (64-byte rows)
+    (2, 3, 32, 32, 96, 16, 3, 1),      # Cout = 16 (N = 48)
+    (5, 1, 64, 64, 96, 80, 1, 5),      # Cout = 80 (N = 240), odd tile count
+    (1, 1, 2, 64, 32, 32, 1, 1),       # a single tile
+]
+
+
+@pytest.mark.parametrize("shape", KWSTACK_SHAPES)
+@pytest.mark.parametrize("variant", ["plain", "fused", "fusedup2"])
+def test_conv_umma_kwstack(cuda_backend, shape, variant):
+    """Column-stacked kernel (three kw taps along the MMA's N, shift-add in the epilogue) vs fp32 emulator; same packed weights as every other kernel."""
+    n, d, h, w, cin, cout, kd, g = shape
+    torch.manual_seed(24)
+    taps = kd * 9
+    x = torch.randn(n, d, h, w, cin)
+    wp = torch.randn(taps * cout * cin) / (taps * cin) ** 0.5
+    fused = variant.startswith("fused")
+    up2 = variant == "fusedup2"
+    bias = torch.randn(cout) if fused else None
+    scale = (torch.rand(g, cout) + 0.5) if fused else None
+    res = (torch.randn(n, d, h // 2, w // 2, cout) if up2 else torch.randn(n, d, h, w, cout)) if fused else None
+    act = (1 if fused else 0) | ((1024 | 2048) if up2 else 0)
+    y_ref = torch.empty(n, d, h, w, cout)
+    EmuBackend().conv_fwd(x, wp, bias, scale, res, y_ref, n, d, h, w, cin, cout, kd, 3, 3, g, act)
+    dev = lambda t: None if t is None else t.cuda()
+    y = torch.full((n, d, h, w, cout), float("nan"), device="cuda")
+    cuda_backend.conv_fwd(dev(x), dev(wp), dev(bias), dev(scale), dev(res), y, n, d, h, w, cin, cout, kd, 3, 3, g, act, algo=4)
+    torch.cuda.synchronize()
+    assert not torch.isnan(y).any(), "column-stacked kernel left outputs unwritten"
+    e = (y.cpu() - y_ref).abs().max().item()
+    assert e <= 4e-3 * max(y_ref.abs().max().item(), 1), f"column-stacked kernel err {e:.3e}"
+    # the same call through AUTO with the option forced must take this kernel too (bit-identical result)
+    cuda_backend.set_option("kwstack", 1)
+    y2 = torch.empty_like(y)
+    cuda_backend.conv_fwd(dev(x), dev(wp), dev(bias), dev(scale), dev(res), y2, n, d, h, w, cin, cout, kd, 3, 3, g, act)
+    torch.cuda.synchronize()
+    if cout < 64:
+        assert torch.equal(y, y2)
+
+
 # N, D, H, W, Cin, Cout, kd, kh
 WGRAD_ROW_SHAPES = [
     (4, 1, 32, 32, 32, 64, 1, 3),
