@@ -1001,11 +1001,11 @@ struct WgradRowParams {
   int BN, ci_tiles, b_blocks;
   int stages, tmem_cols;
   int kb_total, kb_chunk, wsegs;
+  int rpk, hg, pitch;     // image rows per 32-pixel K block (1; 2 / 4 for W = 16 / 8), row groups per image (H / rpk), bytes between 32-channel patch blocks
   int subpix;             // 1: sub-pixel up-convolution tiles (conv_subpix.cu): blockIdx.x = (i, j, a); the two column taps b = 0, 1 share one dz tile
                           //    (phase-(i,j) view of the high-resolution dz: tmDz / tmV1 / tmV2 / tmV3) and one 34-pixel x patch of row h+a+i-1
   float* dwp;
 };
-constexpr uint32_t kRowPatchPitch = 36u * 128u;   // 34 patch rows, padded to a multiple of the 512-byte swizzle period
 
 __global__ void __launch_bounds__(kUmmaThreads, 1)
 conv_umma_wgrad_row_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmV1,
@@ -1015,9 +1015,11 @@ conv_umma_wgrad_row_kernel(const __grid_constant__ CUtensorMap tmDz, const __gri
   const uint32_t base = (raw + 1023u) & ~1023u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t a_bytes = 4u * 4096u;                                   // 4 co blocks x [32 px][32 co]
-  const uint32_t b_span = (uint32_t)p.b_blocks * kRowPatchPitch;
+  const uint32_t pitch = (uint32_t)p.pitch;
+  const uint32_t b_span = (uint32_t)p.b_blocks * pitch;
   const uint32_t stage_bytes = a_bytes + ((b_span + 1023u) & ~1023u);
-  const uint32_t tx_bytes = a_bytes + (uint32_t)p.b_blocks * 34u * 128u;
+  const int wt = p.W < 32 ? p.W : 32;                                    // pixels of one image row inside a K block
+  const uint32_t tx_bytes = a_bytes + (uint32_t)p.b_blocks * (uint32_t)(p.rpk * (wt + 2)) * 128u;
   const uint32_t bar_base = base + p.stages * stage_bytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (p.stages + s); };
@@ -1057,8 +1059,8 @@ conv_umma_wgrad_row_kernel(const __grid_constant__ CUtensorMap tmDz, const __gri
   if (warp == 0) {
     if (num_kb > 0) {      // warp-uniform loop, elected lane issues (see elect_one)
       int s = 0; uint32_t ph = 0;
-      int ws = kb0 % p.wsegs, h, d, n;
-      { int t = kb0 / p.wsegs; h = t % p.H; t /= p.H; d = t % p.D; n = t / p.D; }
+      int ws = kb0 % p.wsegs, h, d, n;          // h counts row groups of p.rpk image rows
+      { int t = kb0 / p.wsegs; h = t % p.hg; t /= p.hg; d = t % p.D; n = t / p.D; }
       for (int kb = kb0; kb < kb1; ++kb) {
         const int w0 = ws * 32;
         mbar_wait(empty_bar(s), ph ^ 1u);
@@ -1066,12 +1068,12 @@ conv_umma_wgrad_row_kernel(const __grid_constant__ CUtensorMap tmDz, const __gri
           mbar_expect_tx(full_bar(s), tx_bytes);
           const uint32_t sa = base + s * stage_bytes;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) tma_load_5d(sa + j * 4096u, dzmap, full_bar(s), co0 + j * 32, w0, h, d, n);
+          for (int j = 0; j < 4; ++j) tma_load_5d(sa + j * 4096u, dzmap, full_bar(s), co0 + j * 32, w0, h * p.rpk, d, n);
           for (int j = 0; j < p.b_blocks; ++j)
-            tma_load_5d(sa + a_bytes + j * kRowPatchPitch, &tmX, full_bar(s), ci0 + j * 32, w0 - 1, h + sh_h, d + sh_d, n);
+            tma_load_5d(sa + a_bytes + j * pitch, &tmX, full_bar(s), ci0 + j * 32, w0 - 1, h * p.rpk + sh_h, d + sh_d, n);
         }
         __syncwarp();
-        if (++ws == p.wsegs) { ws = 0; if (++h == p.H) { h = 0; if (++d == p.D) { d = 0; ++n; } } }
+        if (++ws == p.wsegs) { ws = 0; if (++h == p.hg) { h = 0; if (++d == p.D) { d = 0; ++n; } } }
         if (++s == p.stages) { s = 0; ph ^= 1u; }
       }
     }
@@ -1087,6 +1089,10 @@ conv_umma_wgrad_row_kernel(const __grid_constant__ CUtensorMap tmDz, const __gri
         d |= (uint64_t)1u << 61;                        // SWIZZLE_128B_BASE32B
         return d;
       };
+      // first patch row of k-step k (8 pixels): the K block is p.rpk image rows of wt pixels, each stored with its two halo pixels
+      uint32_t prow[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) prow[k] = (uint32_t)(((8 * k) / wt) * (wt + 2) + (8 * k) % wt);
       int s = 0; uint32_t ph = 0;
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(full_bar(s), ph);
@@ -1099,7 +1105,7 @@ conv_umma_wgrad_row_kernel(const __grid_constant__ CUtensorMap tmDz, const __gri
 #pragma unroll
               for (int k = 0; k < 4; ++k)
                 umma_tf32(tmem_base + (uint32_t)(dw * p.BN), mn_desc(sa + k * 1024u, 4096u),
-                          mn_desc(sa + a_bytes + (uint32_t)(dw0 + dw + 8 * k) * 128u, kRowPatchPitch), idesc, (kb | k) != 0 ? 1u : 0u);
+                          mn_desc(sa + a_bytes + (prow[k] + (uint32_t)(dw0 + dw)) * 128u, pitch), idesc, (kb | k) != 0 ? 1u : 0u);
             }
           }
           umma_commit(empty_bar(s));
@@ -1534,7 +1540,8 @@ int launch_conv_umma_wgrad(const float* x, const float* dz, float* dwp, int N, i
 // grid whose dz operand is a strided phase view of the high-resolution tensor.  16 instead of 36 MACs per low-res pixel and channel pair.
 int launch_conv_umma_wgrad_row_subpix(const float* x, const float* dz, float* dwp, int N, int H, int W, int Cin, int Cout, cudaStream_t st);
 int launch_conv_umma_wgrad_subpix(const float* x, const float* dz, float* dwp, int N, int H, int W, int Cin, int Cout, cudaStream_t st) {
-  if (W % 32 == 0 && Cin % 4 == 0 && Cout % 4 == 0 && (g_opt.subpix_wgrad_row == 1 || (g_opt.subpix_wgrad_row != 0 && (int64_t)N * H * W >= 16384)))
+  const bool row_geom = W % 32 == 0 || (W == 16 && H % 2 == 0) || (W == 8 && H % 4 == 0);
+  if (row_geom && Cin % 4 == 0 && Cout % 4 == 0 && (g_opt.subpix_wgrad_row == 1 || (g_opt.subpix_wgrad_row != 0 && (int64_t)N * H * W >= 16384)))
     return launch_conv_umma_wgrad_row_subpix(x, dz, dwp, N, H, W, Cin, Cout, st);   // (measured 2.4 ms tap-wise vs the row form on 96->96 at 64^2)
   UmmaWgradParams p;
   p.subpix = 1;
@@ -1728,10 +1735,11 @@ int launch_conv_umma_patch(const float* x, const float* wp, const float* bias, c
 
 
 static bool umma_wgrad_row_ok(int N, int D, int H, int W, int Cin, int Cout, int kd, int kh, int kw) {
-  (void)N; (void)D; (void)H;
+  (void)N; (void)D;
   if (kw != 3 || !(kh == 1 || kh == 3) || !(kd == 1 || kd == 3)) return false;
-  if (W % 32 != 0 || Cin % 4 != 0 || Cout % 4 != 0) return false;
-  return true;
+  if (Cin % 4 != 0 || Cout % 4 != 0) return false;
+  if (W % 32 == 0) return true;
+  return (W == 16 && H % 2 == 0) || (W == 8 && H % 4 == 0);     // narrow images: a K block is 2 / 4 whole image rows
 }
 
 int launch_conv_umma_wgrad_row(const float* x, const float* dz, float* dwp, int N, int D, int H, int W, int Cin, int Cout, int kd, int kh, cudaStream_t st) {
@@ -1742,7 +1750,10 @@ int launch_conv_umma_wgrad_row(const float* x, const float* dz, float* dwp, int 
   p.BN = (int)(ceil_div(ceil_div(Cin, p.ci_tiles), 32) * 32);
   p.b_blocks = p.BN / 32;
   p.tmem_cols = 32; while (p.tmem_cols < 3 * p.BN) p.tmem_cols <<= 1;
-  const uint32_t stage_bytes = 4u * 4096u + (((uint32_t)p.b_blocks * kRowPatchPitch + 1023u) & ~1023u);
+  const int wt = W < 32 ? W : 32;
+  p.rpk = 32 / wt; p.hg = H / p.rpk;
+  p.pitch = (int)((((uint32_t)(p.rpk * (wt + 2)) * 128u + 511u) / 512u) * 512u);     // a multiple of the 512-byte swizzle period
+  const uint32_t stage_bytes = 4u * 4096u + (((uint32_t)p.b_blocks * (uint32_t)p.pitch + 1023u) & ~1023u);
   int stages = (int)((200u * 1024u) / stage_bytes);
   if (stages > 6) stages = 6;
   if (stages < 2) { set_error("conv_umma_wgrad_row: stage too large"); return 1; }
@@ -1750,8 +1761,8 @@ int launch_conv_umma_wgrad_row(const float* x, const float* dz, float* dwp, int 
   size_t smem = (size_t)stages * stage_bytes + 1024 + 8 * (2 * stages + 2);
   const int taps = kd * kh * 3;
   const int co_tiles = (int)ceil_div(Cout, 128);
-  p.wsegs = W / 32;
-  p.kb_total = N * D * H * p.wsegs;
+  p.wsegs = W < 32 ? 1 : W / 32;
+  p.kb_total = N * D * p.hg * p.wsegs;
   int64_t base_ctas = (int64_t)kd * kh * co_tiles * p.ci_tiles;
   // one CTA per SM (shared memory): fill exactly two waves, never spill a few CTAs into a third
   int64_t ksplit = ((int64_t)sm_count() * 2) / base_ctas;
@@ -1764,14 +1775,14 @@ int launch_conv_umma_wgrad_row(const float* x, const float* dz, float* dwp, int 
   {
     uint64_t dims[5] = {(uint64_t)Cout, (uint64_t)W, (uint64_t)H, (uint64_t)D, (uint64_t)N};
     uint64_t str[4] = {(uint64_t)Cout * 4, (uint64_t)W * Cout * 4, (uint64_t)H * W * Cout * 4, (uint64_t)D * H * W * Cout * 4};
-    uint32_t box[5] = {32u, 32u, 1u, 1u, 1u};
+    uint32_t box[5] = {32u, (uint32_t)wt, (uint32_t)p.rpk, 1u, 1u};
     int e = make_tmap(&tmDz, dz, 5, dims, str, box, 128, true);
     if (e) return e;
   }
   {
     uint64_t dims[5] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)D, (uint64_t)N};
     uint64_t str[4] = {(uint64_t)Cin * 4, (uint64_t)W * Cin * 4, (uint64_t)H * W * Cin * 4, (uint64_t)D * H * W * Cin * 4};
-    uint32_t box[5] = {32u, 34u, 1u, 1u, 1u};
+    uint32_t box[5] = {32u, (uint32_t)(wt + 2), (uint32_t)p.rpk, 1u, 1u};
     int e = make_tmap(&tmX, x, 5, dims, str, box, 128, true);
     if (e) return e;
   }
@@ -1798,15 +1809,18 @@ int launch_conv_umma_wgrad_row_subpix(const float* x, const float* dz, float* dw
   p.BN = (int)(ceil_div(ceil_div(Cin, p.ci_tiles), 32) * 32);
   p.b_blocks = p.BN / 32;
   p.tmem_cols = 32; while (p.tmem_cols < 3 * p.BN) p.tmem_cols <<= 1;
-  const uint32_t stage_bytes = 4u * 4096u + (((uint32_t)p.b_blocks * kRowPatchPitch + 1023u) & ~1023u);
+  const int wt = W < 32 ? W : 32;
+  p.rpk = 32 / wt; p.hg = H / p.rpk;
+  p.pitch = (int)((((uint32_t)(p.rpk * (wt + 2)) * 128u + 511u) / 512u) * 512u);
+  const uint32_t stage_bytes = 4u * 4096u + (((uint32_t)p.b_blocks * (uint32_t)p.pitch + 1023u) & ~1023u);
   int stages = (int)((200u * 1024u) / stage_bytes);
   if (stages > 6) stages = 6;
   if (stages < 2) { set_error("conv_umma_wgrad_row_subpix: stage too large"); return 1; }
   p.stages = stages;
   const size_t smem = (size_t)stages * stage_bytes + 1024 + 8 * (2 * stages + 2);
   const int co_tiles = (int)ceil_div(Cout, 128);
-  p.wsegs = W / 32;
-  p.kb_total = N * H * p.wsegs;
+  p.wsegs = W < 32 ? 1 : W / 32;
+  p.kb_total = N * p.hg * p.wsegs;
   const int64_t base_ctas = (int64_t)8 * co_tiles * p.ci_tiles;
   int64_t ksplit = ((int64_t)sm_count() * 2) / base_ctas;
   if (ksplit > p.kb_total / 8) ksplit = p.kb_total / 8;
@@ -1819,14 +1833,14 @@ int launch_conv_umma_wgrad_row_subpix(const float* x, const float* dz, float* dw
     const int i = v >> 1, j = v & 1;
     uint64_t dims[5] = {(uint64_t)Cout, (uint64_t)W, (uint64_t)H, 1u, (uint64_t)N};
     uint64_t str[4] = {(uint64_t)2 * Cout * 4, (uint64_t)2 * (2 * W) * Cout * 4, (uint64_t)(2 * H) * (2 * W) * Cout * 4, (uint64_t)(2 * H) * (2 * W) * Cout * 4};
-    uint32_t box[5] = {32u, 32u, 1u, 1u, 1u};
+    uint32_t box[5] = {32u, (uint32_t)wt, (uint32_t)p.rpk, 1u, 1u};
     int e = make_tmap(&tmV[v], dz + ((int64_t)i * 2 * W + j) * Cout, 5, dims, str, box, 128, true);
     if (e) return e;
   }
   {
     uint64_t dims[5] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, 1u, (uint64_t)N};
     uint64_t str[4] = {(uint64_t)Cin * 4, (uint64_t)W * Cin * 4, (uint64_t)H * W * Cin * 4, (uint64_t)H * W * Cin * 4};
-    uint32_t box[5] = {32u, 34u, 1u, 1u, 1u};
+    uint32_t box[5] = {32u, (uint32_t)(wt + 2), (uint32_t)p.rpk, 1u, 1u};
     int e = make_tmap(&tmX, x, 5, dims, str, box, 128, true);
     if (e) return e;
   }
@@ -1916,8 +1930,9 @@ int dgmr_conv_fwd(const float* x, const float* x_lo, const float* wp, const floa
   }
   if (algo == DGMR_ALGO_UMMA || algo == DGMR_ALGO_UMMA_PATCH) DGMR_REQUIRE(ok, "dgmr_conv_fwd: shape not supported by the tcgen05 path");
   if (algo == DGMR_ALGO_UMMA_KWSTACK) DGMR_REQUIRE(umma_kwstack_ok(N, D, H, W, Cin, Cout, kd, kh, kw, G), "dgmr_conv_fwd: shape not supported by the column-stacked kernel");
-  // narrow outputs (Cout < 64) of at least a few waves of tiles: column taps stacked along N, the shift done in the epilogue (conv_kwstack.cu)
-  if (algo == DGMR_ALGO_UMMA_KWSTACK || (algo == DGMR_ALGO_AUTO && g_opt.kwstack != 0 && Cout < 64 && umma_kwstack_ok(N, D, H, W, Cin, Cout, kd, kh, kw, G) &&
+  // narrow outputs (Cout < 64) of at least a few waves of tiles: column taps stacked along N, the shift done in the epilogue (conv_kwstack.cu).
+  // Measured (profiles/time_kwstack_r02.txt): 3-D 48->48 1.76 -> 0.90 ms, 96->48 @128^2 1.37 -> 0.90 ms; 16-channel inputs are slower there (0.32 -> 0.40 ms).
+  if (algo == DGMR_ALGO_UMMA_KWSTACK || (algo == DGMR_ALGO_AUTO && g_opt.kwstack != 0 && Cout < 64 && Cin >= 32 && umma_kwstack_ok(N, D, H, W, Cin, Cout, kd, kh, kw, G) &&
                                          ((int64_t)N * D * H * W >= (int64_t)128 * 2 * sm_count() || g_opt.kwstack == 1)))
     return launch_conv_umma_kwstack(x, wp, bias, scale, res, y, N, D, H, W, Cin, Cout, kd, G, act, S(stream));
   if (algo == DGMR_ALGO_UMMA || algo == DGMR_ALGO_UMMA_PATCH || (algo == DGMR_ALGO_AUTO && ok)) {

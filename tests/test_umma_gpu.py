@@ -232,6 +232,10 @@ WGRAD_ROW_SHAPES = [
     (2, 4, 32, 32, 48, 96, 3, 3),      # 3-D
     (1, 1, 32, 32, 768, 384, 1, 3),    # 5 ci tiles of 160, 3 co tiles
     (2, 1, 32, 32, 8, 48, 1, 3),       # zero-padded 8-channel input
+    (4, 1, 16, 16, 96, 64, 1, 3),      # W = 16: a K block is two whole image rows (36-row patch)
+    (3, 1, 16, 16, 384, 192, 1, 3),    # same, three ci tiles
+    (6, 1, 8, 8, 64, 96, 1, 3),        # W = 8: four image rows per K block (40-row patch)
+    (2, 3, 8, 16, 48, 48, 3, 3),       # W = 16, 3-D, H = 8
 ]
 
 
@@ -311,7 +315,7 @@ def test_upconv_subpixel_kernels(cuda_backend, shape):
     assert not torch.isnan(dx).any()
     e = (dx.cpu() - dx_ref).abs().max().item()
     assert e <= 4e-3 * dx_ref.abs().max().item(), f"sub-pixel dgrad err {e:.3e}"
-    for row in ((0, 1) if w % 32 == 0 else (0,)):     # tap-wise kernel / row kernel (two column taps per CTA)
+    for row in ((0, 1) if (w % 32 == 0 or w == 16) else (0,)):     # tap-wise kernel / row kernel (two column taps per CTA; W = 16: two image rows per K block)
         be.set_option("subpix_wgrad_row", row)
         dw = torch.full((16 * cout * cin,), float("nan"), device="cuda")
         be.upconv_wgrad(x.cuda(), dz.cuda(), dw, n, h, w, cin, cout)
