@@ -28,14 +28,21 @@ struct KwStackParams {
 
 constexpr int kKwThreads = 192;  // warp0 TMA, warp1 MMA, warps 2..5 epilogue
 
-template <int BK>
+// PAIR: launched as clusters of 2 CTAs (one TPC), tcgen05.mma.cta_group::2 with M = 256: the two CTAs work on two different tiles (identical
+// shared-memory geometry, one A descriptor), each stages HALF of every stacked weight tile (cp.async.bulk.tensor...cta_group::2 signalling the
+// leader's mbarrier) -- the weight slab is ~half of this kernel's L2->SM traffic, which is what bounds it -- and the leader's MMA warp issues for
+// both; commits are multicast to both CTAs, the peer's epilogue warps release the accumulators on the leader's barrier.
+template <int BK, bool PAIR>
 __global__ void __launch_bounds__(kKwThreads, 1)
 conv_umma_kwstack_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const KwStackParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t a_bytes = 128u * BK * 4u, b_bytes = (uint32_t)p.BN * BK * 4u;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const int64_t wid = PAIR ? (int64_t)(blockIdx.x >> 1) : (int64_t)blockIdx.x;      // worker (CTA or CTA pair) index
+  const int64_t nworkers = PAIR ? (int64_t)(gridDim.x >> 1) : (int64_t)gridDim.x;
+  const uint32_t a_bytes = 128u * BK * 4u, b_bytes = (uint32_t)(PAIR ? p.BN / 2 : p.BN) * BK * 4u;   // pair: half of the weight rows per CTA
   const uint32_t b_bytes_al = (b_bytes + 1023u) & ~1023u;
   const uint32_t stage_bytes = a_bytes + b_bytes_al;
   const uint32_t bar_base = base + p.stages * stage_bytes;
@@ -50,6 +57,10 @@ conv_umma_kwstack_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 
   const int tiles_h = p.H / p.bh;
   const int64_t total_tiles = (int64_t)p.N * p.D * tiles_h;
+  // work items: single tiles, or (pair) two consecutive tiles 2i + rank; with an odd total the peer's last tile lies past the end
+  // (n0 = N: TMA zero fill, stores skipped)
+  const int64_t total_items = PAIR ? (total_tiles + 1) / 2 : total_tiles;
+  auto tile_of = [&](int64_t item) { return PAIR ? 2 * item + (int64_t)rank : item; };
   auto decode = [&](int64_t t, int& n0, int& d0, int& h0) {
     h0 = (int)(t % tiles_h) * p.bh; t /= tiles_h;
     d0 = (int)(t % p.D); n0 = (int)(t / p.D);
@@ -62,28 +73,37 @@ conv_umma_kwstack_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
     for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int bsel = 0; bsel < 2; ++bsel) { mbar_init(tmem_full(bsel), 1); mbar_init(tmem_empty(bsel), 4); }
+    for (int bsel = 0; bsel < 2; ++bsel) { mbar_init(tmem_full(bsel), 1); mbar_init(tmem_empty(bsel), PAIR ? 8 : 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 0) { __syncwarp(); tmem_alloc(tmem_ptr_addr, (uint32_t)p.tmem_cols); }
+  if (warp == 0) { __syncwarp(); if (PAIR) tmem_alloc2(tmem_ptr_addr, (uint32_t)p.tmem_cols); else tmem_alloc(tmem_ptr_addr, (uint32_t)p.tmem_cols); }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all(); else __syncthreads();     // pair: the peer's barriers must exist before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_gen;
 
   if (warp == 0) {
     // ===== TMA producer: one continuous stream of K blocks over all of this CTA's tiles
     int s = 0, g = 0, sg = 0; uint32_t ph = 0;
-    for (int64_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-      int n0, d0, h0; decode(t, n0, d0, h0);
+    for (int64_t item = wid; item < total_items; item += nworkers) {
+      int n0, d0, h0; decode(tile_of(item), n0, d0, h0);
       int rt = 0, chunk = 0;
       for (int kb = 0; kb < num_kb; ++kb) {
         const int c0 = chunk * BK;
         const int tkh = rt % p.kh, tkd = rt / p.kh;
         if (sg == 0) mbar_wait(empty_bar(g), ph ^ 1u);
-        if (elect_one()) {
+        const uint32_t sa = base + s * stage_bytes;
+        if (PAIR) {
+          // the leader's full barrier collects both CTAs' bytes (one arrival: its own expect_tx of the doubled count; the peer's bytes may
+          // land first, the phase cannot complete before that arrival)
+          const uint32_t lead = mapa_rank(full_bar(s), 0);
+          if (elect_one()) {
+            if (rank == 0) mbar_expect_tx(full_bar(s), 2u * (a_bytes + b_bytes));
+            tma_load_5d_2sm(sa, &tmA, lead, c0, 0, h0 + tkh - p.kh / 2, d0 + tkd - p.kd / 2, n0);
+            tma_load_3d_2sm(sa + a_bytes, &tmB, lead, c0, (int)rank * (p.BN / 2), rt);
+          }
+        } else if (elect_one()) {
           mbar_expect_tx(full_bar(s), a_bytes + b_bytes);
-          const uint32_t sa = base + s * stage_bytes;
           tma_load_5d(sa, &tmA, full_bar(s), c0, 0, h0 + tkh - p.kh / 2, d0 + tkd - p.kd / 2, n0);
           tma_load_3d(sa + a_bytes, &tmB, full_bar(s), c0, 0, rt);
         }
@@ -94,16 +114,21 @@ conv_umma_kwstack_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer
-    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((128u >> 4) << 24);
+   if (rank == 0) {
+    // ===== MMA issuer (pair: the leader alone, M = 256 instructions spanning both CTAs)
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.BN >> 3) << 17) | (((PAIR ? 256u : 128u) >> 4) << 24);
+    auto mma = [](uint32_t dcol, uint64_t ad, uint64_t bd, uint32_t id, uint32_t acc) {
+      if (PAIR) umma_tf32_2cta(dcol, ad, bd, id, acc); else umma_tf32(dcol, ad, bd, id, acc);
+    };
+    auto commit = [](uint32_t bar) { if (PAIR) umma_commit_pair(bar); else umma_commit(bar); };
     constexpr uint32_t row_bytes = BK * 4u;
     constexpr uint32_t layout = row_bytes == 128 ? 2u : (row_bytes == 64 ? 4u : 6u);
     constexpr uint32_t sbo = 8u * row_bytes;
     const int tail_ks = (p.Cin % BK) ? (p.Cin % BK) / 8 : BK / 8;
     int s = 0, g = 0, sg = 0; uint32_t ph = 0, it = 0;
-    for (int64_t t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+    for (int64_t item = wid; item < total_items; item += nworkers, ++it) {
       const int bsel = it & 1; const uint32_t phacc = (it >> 1) & 1u;
-      mbar_wait(tmem_empty(bsel), phacc ^ 1u);       // the epilogue has drained this accumulator buffer
+      mbar_wait(tmem_empty(bsel), phacc ^ 1u);       // the epilogue warps (of both CTAs) have drained this accumulator buffer
       tc_fence_after();
       const uint32_t tacc = tmem_base + (uint32_t)(bsel * p.BN);
       int chunk_i = 0;
@@ -116,25 +141,26 @@ conv_umma_kwstack_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         const bool last_chunk = (++chunk_i == kchunks);
         if (last_chunk) chunk_i = 0;
         const bool last_kb = (kb + 1 == num_kb);
-        const bool rel = (sg + 1 == p.cg) || (last_kb && t + gridDim.x >= total_tiles);   // group full, or the very last K block
+        const bool rel = (sg + 1 == p.cg) || (last_kb && item + nworkers >= total_items);   // group full, or the very last K block
         if (elect_one()) {
-          umma_tf32(tacc, adesc, bdesc, idesc, kb != 0 ? 1u : 0u);
+          mma(tacc, adesc, bdesc, idesc, kb != 0 ? 1u : 0u);
           if (last_chunk) {
 #pragma unroll
             for (int k = 1; k < BK / 8; ++k)
-              if (k < tail_ks) umma_tf32(tacc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, 1u);
+              if (k < tail_ks) mma(tacc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, 1u);
           } else {
 #pragma unroll
-            for (int k = 1; k < BK / 8; ++k) umma_tf32(tacc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, 1u);
+            for (int k = 1; k < BK / 8; ++k) mma(tacc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, 1u);
           }
-          if (rel) umma_commit(empty_bar(g));
-          if (last_kb) umma_commit(tmem_full(bsel));
+          if (rel) commit(empty_bar(g));
+          if (last_kb) commit(tmem_full(bsel));
         }
         __syncwarp();
         if (++sg == p.cg) { sg = 0; ++g; }
         if (++s == p.stages) { s = 0; g = 0; ph ^= 1u; }
       }
     }
+   }
   } else {
     // ===== epilogue (4 warps): warp w may only touch TMEM lanes [32*(w%4), +32).  Lane = tile row r = 32q + lane = pixel (h0 + r / W, r % W).
     const int q = warp & 3;
@@ -145,8 +171,10 @@ conv_umma_kwstack_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     const bool has_prev = my_w != 0, has_next = my_w != p.W - 1;     // neighbours inside the image row (else: zero padding, term dropped)
     const bool cross = p.W > 32;                                     // rows continue across epilogue-warp boundaries
     uint32_t it = 0, par = 0;
-    for (int64_t t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
-      int n0, d0, h0; decode(t, n0, d0, h0);
+    for (int64_t item = wid; item < total_items; item += nworkers, ++it) {
+      const int64_t t = tile_of(item);
+      const bool live = t < total_tiles;             // pair with an odd tile count: the peer's last tile does not exist
+      int n0, d0, h0; decode(live ? t : 0, n0, d0, h0);
       const int bsel = it & 1; const uint32_t phacc = (it >> 1) & 1u;
       uint32_t mrow[4], rrow[4]; const float* srow[4];
 #pragma unroll
@@ -225,19 +253,24 @@ conv_umma_kwstack_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           if (p.res) { o.x += rr[j].x; o.y += rr[j].y; o.z += rr[j].z; o.w += rr[j].w; }
           if (p.act == DGMR_ACT_RELU) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
           if (p.round_out) o = rna_tf32_e4(o);
-          *reinterpret_cast<float4*>(p.y + mrow[j] + c) = o;
+          if (live) *reinterpret_cast<float4*>(p.y + mrow[j] + c) = o;
         }
         __syncwarp();
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tmem_empty(bsel)) : "memory");
+      if (lane == 0) {
+        if (PAIR) mbar_arrive_cluster(mapa_rank(tmem_empty(bsel), 0));   // the leader's MMA warp waits for both CTAs' epilogues
+        else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tmem_empty(bsel)) : "memory");
+      }
     }
   }
   tc_fence_before();
-  __syncthreads();
-  if (warp == 0) { __syncwarp(); tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols); }
+  if (PAIR) cluster_sync_all(); else __syncthreads();
+  if (warp == 0) { __syncwarp(); if (PAIR) tmem_dealloc2(tmem_base, (uint32_t)p.tmem_cols); else tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols); }
 }
+
+int g_kwstack_pair = -1;     // dgmr_set_option("kwstack_pair"): 0 = never CTA pairs, 1 = pairs whenever there are at least two tiles (tests)
 
 static int kw_bk(int Cin) { return (Cin % 8 != 0) ? 0 : (Cin >= 32) ? 32 : (Cin == 16 || Cin == 24) ? 16 : 0; }
 
@@ -262,7 +295,11 @@ int launch_conv_umma_kwstack(const float* x, const float* wp, const float* bias,
   const int BK = kw_bk(Cin);
   if (BK == 0) { set_error("conv_umma_kwstack: Cin=%d not served", Cin); return 1; }
   p.tmem_cols = 32; while (p.tmem_cols < 2 * p.BN) p.tmem_cols <<= 1;
-  const uint32_t a_bytes = 128u * BK * 4u, b_bytes = ((uint32_t)p.BN * BK * 4u + 1023u) & ~1023u;
+  const int64_t total_tiles = (int64_t)N * D * (H / p.bh);
+  // CTA pairs (cta_group::2, half of every weight tile per CTA) whenever there are a few waves of tiles; the pair splits the N = 3*Cout rows
+  // in two halves of whole 8-row groups
+  const bool pair = g_kwstack_pair != 0 && sm_count() % 2 == 0 && (p.BN / 2) % 8 == 0 && (total_tiles >= 2 * (int64_t)sm_count() || (g_kwstack_pair == 1 && total_tiles >= 2));
+  const uint32_t a_bytes = 128u * BK * 4u, b_bytes = ((uint32_t)(pair ? p.BN / 2 : p.BN) * BK * 4u + 1023u) & ~1023u;
   const uint32_t stage_bytes = a_bytes + b_bytes;
   int stages = (int)((196u * 1024u) / stage_bytes);
   if (stages > 9) stages = 9;
@@ -283,26 +320,42 @@ int launch_conv_umma_kwstack(const float* x, const float* wp, const float* bias,
     // packed weights [tap = (kd, kh, kw)][Cout][Cin] seen as [(kd, kh)][kw*Cout + co][Cin]
     uint64_t dims[3] = {(uint64_t)Cin, (uint64_t)(3 * Cout), (uint64_t)(kd * 3)};
     uint64_t str[2] = {(uint64_t)Cin * 4, (uint64_t)3 * Cout * Cin * 4};
-    uint32_t box[3] = {(uint32_t)BK, (uint32_t)p.BN, 1u};
+    uint32_t box[3] = {(uint32_t)BK, (uint32_t)(pair ? p.BN / 2 : p.BN), 1u};
     int e = make_tmap(&tmB, wp, 3, dims, str, box, BK * 4);
     if (e) return e;
   }
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(conv_umma_kwstack_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(224 * 1024)) != cudaSuccess ||
-        cudaFuncSetAttribute(conv_umma_kwstack_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(224 * 1024)) != cudaSuccess) {
+    if (cudaFuncSetAttribute(conv_umma_kwstack_kernel<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(224 * 1024)) != cudaSuccess ||
+        cudaFuncSetAttribute(conv_umma_kwstack_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(224 * 1024)) != cudaSuccess ||
+        cudaFuncSetAttribute(conv_umma_kwstack_kernel<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(224 * 1024)) != cudaSuccess ||
+        cudaFuncSetAttribute(conv_umma_kwstack_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(224 * 1024)) != cudaSuccess) {
       set_error("conv_umma_kwstack: cannot raise dynamic smem limit"); return 2;
     }
     attr_set = true;
   }
-  const int64_t total_tiles = (int64_t)N * D * (H / p.bh);
-  int64_t g = sm_count();
-  if (g > total_tiles) g = total_tiles;
   // one CTA per SM (2 x 3*Cout TMEM columns each): pad the shared-memory request so that a second CTA can never become resident and block in tcgen05.alloc
   size_t req = smem;
   if (req < (size_t)232448 / 2 + 1024) req = (size_t)232448 / 2 + 1024;
-  if (BK == 32) conv_umma_kwstack_kernel<32><<<(unsigned)g, kKwThreads, req, st>>>(tmA, tmB, p);
-  else conv_umma_kwstack_kernel<16><<<(unsigned)g, kKwThreads, req, st>>>(tmA, tmB, p);
+  if (pair) {
+    int64_t g = sm_count();                                   // even (checked above): one CTA pair per TPC
+    const int64_t items = (total_tiles + 1) / 2;
+    if (g > 2 * items) g = 2 * items;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)g); cfg.blockDim = dim3(kKwThreads); cfg.dynamicSmemBytes = req; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaError_t e = (BK == 32) ? cudaLaunchKernelEx(&cfg, conv_umma_kwstack_kernel<32, true>, tmA, tmB, p)
+                               : cudaLaunchKernelEx(&cfg, conv_umma_kwstack_kernel<16, true>, tmA, tmB, p);
+    if (e != cudaSuccess) { set_error("conv_umma_kwstack: cluster launch failed: %s", cudaGetErrorString(e)); return 2; }
+    return 0;
+  }
+  int64_t g = sm_count();
+  if (g > total_tiles) g = total_tiles;
+  if (BK == 32) conv_umma_kwstack_kernel<32, false><<<(unsigned)g, kKwThreads, req, st>>>(tmA, tmB, p);
+  else conv_umma_kwstack_kernel<16, false><<<(unsigned)g, kKwThreads, req, st>>>(tmA, tmB, p);
   DGMR_CHECK_LAUNCH("conv_umma_kwstack");
   return 0;
 }

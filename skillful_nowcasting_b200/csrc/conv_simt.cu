@@ -271,7 +271,7 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ packed, float* __r
 // read, DSR: dscale with a residual, GEO: pooled-gradient / half-resolution-residual index maps), so that the common variants stay
 // small enough for 3-4 CTAs per SM with four rows of loads in flight per thread; the fp64 partial sums live in shared memory
 // (touched once per 32 iterations), not in registers.
-struct PoolGeom { int pd, ph, pw, D, H, W; float inv; };
+struct PoolGeom { int pd, ph, pw, D, H, W; float inv; int lw, lh; };   // lw / lh: log2 of W / H when they are powers of two (shift instead of divide), else -1
 template <int V, bool HASY, bool DSR, bool GEO>
 __global__ void __launch_bounds__(256, 3) conv_bwd_prep_kernel(const float* __restrict__ dy, const float* __restrict__ y, const float* __restrict__ res,
                                                                const float* __restrict__ bias, const float* __restrict__ scale, float* __restrict__ dz,
@@ -319,12 +319,12 @@ __global__ void __launch_bounds__(256, 3) conv_bwd_prep_kernel(const float* __re
             ro = ((int64_t)(img * (uint32_t)(up_h >> 1) + (hh >> 1)) * (up_w >> 1) + (ww >> 1)) * C + c;
           }
           if (pg.pd > 0) {
-            uint32_t t = Ru;
-            const uint32_t ww = t % (uint32_t)pg.W; t /= (uint32_t)pg.W;
-            const uint32_t hh = t % (uint32_t)pg.H; t /= (uint32_t)pg.H;
-            const uint32_t dd = t % (uint32_t)pg.D; const uint32_t nn = t / (uint32_t)pg.D;
+            uint32_t t = Ru, ww, hh;
+            if (pg.lw >= 0) { ww = t & (uint32_t)(pg.W - 1); t >>= pg.lw; } else { ww = t % (uint32_t)pg.W; t /= (uint32_t)pg.W; }
+            if (pg.lh >= 0) { hh = t & (uint32_t)(pg.H - 1); t >>= pg.lh; } else { hh = t % (uint32_t)pg.H; t /= (uint32_t)pg.H; }
+            const uint32_t nn = t / (uint32_t)pg.D, dd = t - nn * (uint32_t)pg.D;
             const uint32_t Dp = pg.D / pg.pd, Hp = pg.H / pg.ph, Wp = pg.W / pg.pw;
-            const uint32_t dq = dd / (uint32_t)pg.pd, hq = hh / (uint32_t)pg.ph, wq = ww / (uint32_t)pg.pw;
+            const uint32_t dq = dd >> (pg.pd - 1), hq = hh >> (pg.ph - 1), wq = ww >> (pg.pw - 1);       // windows are 1 or 2 wide (host-checked)
             if (dq < Dp && hq < Hp && wq < Wp) { dyo = ((((int64_t)nn * Dp + dq) * Hp + hq) * Wp + wq) * C + c; dsc = pg.inv; }
             else { dyo = 0; dsc = 0.f; }     // rim dropped by the floor: no gradient
           }
@@ -753,7 +753,9 @@ int dgmr_conv_bwd_prep(const float* dy, const float* y, const float* res, const 
                        int D, int H, int W, dgmr_stream_t stream) {
   const int rnd = (act & DGMR_FLAG_ROUND_TF32) ? 1 : 0;
   act &= ~DGMR_FLAG_ROUND_TF32;
-  PoolGeom pg{pool_d, pool_h, pool_w, D, H, W, 0.f};
+  PoolGeom pg{pool_d, pool_h, pool_w, D, H, W, 0.f, -1, -1};
+  if (W > 0 && (W & (W - 1)) == 0) { pg.lw = 0; while ((1 << pg.lw) < W) ++pg.lw; }
+  if (H > 0 && (H & (H - 1)) == 0) { pg.lh = 0; while ((1 << pg.lh) < H) ++pg.lh; }
   if (pool_d > 0) {
     DGMR_REQUIRE(pool_h > 0 && pool_w > 0 && pool_d <= 2 && pool_h <= 2 && pool_w <= 2 && D > 0 && H > 0 && W > 0 && (rows * G) % ((int64_t)D * H * W) == 0,
                  "dgmr_conv_bwd_prep: bad pooled-gradient geometry");

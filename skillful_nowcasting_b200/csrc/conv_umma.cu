@@ -22,6 +22,7 @@ namespace dgmr {
 int launch_conv_simt_fwd(const float*, const float*, const float*, const float*, const float*, float*, int, int, int, int, int, int, int, int, int, int, int, cudaStream_t);
 int launch_conv_simt_wgrad(const float*, const float*, float*, int, int, int, int, int, int, int, int, int, cudaStream_t);
 bool umma_kwstack_ok(int N, int D, int H, int W, int Cin, int Cout, int kd, int kh, int kw, int G);   // conv_kwstack.cu
+extern int g_kwstack_pair;
 int launch_conv_umma_kwstack(const float* x, const float* wp, const float* bias, const float* scale, const float* res, float* y, int N, int D, int H, int W,
                              int Cin, int Cout, int kd, int G, int act, cudaStream_t st);
 
@@ -1885,7 +1886,7 @@ int dgmr_set_option(const char* name, int value) {
   struct { const char* n; int* v; } tab[] = {{"umma_cg", &g_opt.umma_cg}, {"umma_persist", &g_opt.umma_persist}, {"umma_persist_r", &g_opt.umma_persist_r},
                                              {"patch_pair", &g_opt.patch_pair}, {"patch_mt", &g_opt.patch_mt}, {"patch_tg", &g_opt.patch_tg},
                                              {"prefer_patch", &g_opt.prefer_patch}, {"patch_dbg", &g_opt.patch_dbg},
-                                             {"subpix_wgrad_row", &g_opt.subpix_wgrad_row}, {"kwstack", &g_opt.kwstack}};
+                                             {"subpix_wgrad_row", &g_opt.subpix_wgrad_row}, {"kwstack", &g_opt.kwstack}, {"kwstack_pair", &g_kwstack_pair}};
   for (auto& t : tab)
     if (strcmp(t.n, name) == 0) { *t.v = value; return 0; }
   set_error("dgmr_set_option: unknown option '%s'", name);
@@ -1962,7 +1963,7 @@ int dgmr_conv_wgrad(const float* x, const float* x_lo, const float* dz, const fl
   if (precision == DGMR_PREC_3XTF32) algo = DGMR_ALGO_SIMT;
   if (algo == DGMR_ALGO_UMMA || algo == DGMR_ALGO_UMMA_PATCH) DGMR_REQUIRE(ok, "dgmr_conv_wgrad: shape not supported by the tcgen05 path (or dwp not 16-byte aligned)");
   if (algo == DGMR_ALGO_UMMA_PATCH) DGMR_REQUIRE(umma_wgrad_row_ok(N, D, H, W, Cin, Cout, kd, kh, kw), "dgmr_conv_wgrad: shape not supported by the row kernel");
-  if (algo == DGMR_ALGO_UMMA_PATCH || (algo == DGMR_ALGO_AUTO && ok && umma_wgrad_row_ok(N, D, H, W, Cin, Cout, kd, kh, kw) && (int64_t)N * D * H * W >= 16384))
+  if (algo == DGMR_ALGO_UMMA_PATCH || (algo == DGMR_ALGO_AUTO && ok && umma_wgrad_row_ok(N, D, H, W, Cin, Cout, kd, kh, kw) && (int64_t)N * D * H * W >= 8192))
     return launch_conv_umma_wgrad_row(x, dz, dwp, N, D, H, W, Cin, Cout, kd, kh, S(stream));
   if (algo == DGMR_ALGO_UMMA || (algo == DGMR_ALGO_AUTO && ok))
     return launch_conv_umma_wgrad(x, dz, dwp, N, D, H, W, Cin, Cout, kd, kh, kw, S(stream));

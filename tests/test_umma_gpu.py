@@ -192,9 +192,12 @@ KWSTACK_SHAPES = [
 
 @pytest.mark.parametrize("shape", KWSTACK_SHAPES)
 @pytest.mark.parametrize("variant", ["plain", "fused", "fusedup2"])
-def test_conv_umma_kwstack(cuda_backend, shape, variant):
-    """Column-stacked kernel (three kw taps along the MMA's N, shift-add in the epilogue) vs fp32 emulator; same packed weights as every other kernel."""
+@pytest.mark.parametrize("pair", [0, 1])
+def test_conv_umma_kwstack(cuda_backend, shape, variant, pair):
+    """Column-stacked kernel (three kw taps along the MMA's N, shift-add in the epilogue) vs fp32 emulator; same packed weights as every other kernel.
+    pair = 1: CTA pairs (cta_group::2, half of each weight tile per CTA) forced on these small shapes, odd tile counts included."""
     n, d, h, w, cin, cout, kd, g = shape
+    cuda_backend.set_option("kwstack_pair", pair)
     torch.manual_seed(24)
     taps = kd * 9
     x = torch.randn(n, d, h, w, cin)

@@ -17,7 +17,8 @@ for (n,d,h,w,cin,cout,kd,g) in [(32,22,64,64,48,48,3,1),(288,1,128,128,96,48,1,1
     bias = torch.randn(cout,device="cuda"); scale = torch.rand(g,cout,device="cuda")+0.5
     y = torch.empty(n,d,h,w,cout,device="cuda"); y2 = torch.empty_like(y)
     out=[]
-    for name, algo in (("plain",2),("kwstack",4)):
+    for name, algo, pair in (("plain",2,0),("kwstack",4,0),("kwstack-pair",4,-1)):
+        be.set_option("kwstack_pair", pair)
         ms = timeit(lambda: be.conv_fwd(x,wp,bias,scale,None,y if algo==2 else y2,n,d,h,w,cin,cout,kd,3,3,g,1,algo=algo))
         out.append(f"{name}: {ms:.3f} ms {2*n*d*h*w*cin*cout*taps/ms/1e9:.0f} TF/s")
     err = (y-y2).abs().max().item()/y.abs().max().item()
