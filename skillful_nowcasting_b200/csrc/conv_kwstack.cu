@@ -115,49 +115,54 @@ conv_umma_kwstack_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     }
   } else if (warp == 1) {
    if (rank == 0) {
-    // ===== MMA issuer (pair: the leader alone, M = 256 instructions spanning both CTAs)
+    // ===== MMA issuer (pair: the leader alone, M = 256 instructions spanning both CTAs).  This warp's instruction stream bounds the kernel
+    // (ncu source view: ~94 instructions per 4-MMA stage at ~4.4 cycles each against 288 cycles of MMA), so descriptors are advanced as 32-bit
+    // low words and the per-stage bookkeeping is kept to a handful of adds / selects.
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.BN >> 3) << 17) | (((PAIR ? 256u : 128u) >> 4) << 24);
-    auto mma = [](uint32_t dcol, uint64_t ad, uint64_t bd, uint32_t id, uint32_t acc) {
-      if (PAIR) umma_tf32_2cta(dcol, ad, bd, id, acc); else umma_tf32(dcol, ad, bd, id, acc);
-    };
-    auto commit = [](uint32_t bar) { if (PAIR) umma_commit_pair(bar); else umma_commit(bar); };
     constexpr uint32_t row_bytes = BK * 4u;
     constexpr uint32_t layout = row_bytes == 128 ? 2u : (row_bytes == 64 ? 4u : 6u);
-    constexpr uint32_t sbo = 8u * row_bytes;
+    constexpr uint32_t dhi = desc_hi(8u * row_bytes, layout);
+    auto mma = [](uint32_t dcol, uint32_t al, uint32_t bl, uint32_t id, uint32_t acc) {
+      if (PAIR) umma_tf32_2cta_lo(dcol, al, bl, dhi, id, acc); else umma_tf32_lo(dcol, al, bl, dhi, id, acc);
+    };
+    auto commit = [](uint32_t bar) { if (PAIR) umma_commit_pair(bar); else umma_commit(bar); };
     const int tail_ks = (p.Cin % BK) ? (p.Cin % BK) / 8 : BK / 8;
-    int s = 0, g = 0, sg = 0; uint32_t ph = 0, it = 0;
+    const uint32_t lo0 = desc_lo(base), st16 = stage_bytes >> 4, a16 = a_bytes >> 4;
+    // ring state as running values: descriptor low word, full / empty barrier addresses (no multiplications in the loop).  The last, possibly
+    // partial, release group is never committed: nothing refills those stages, and tmem_full covers the completion of their MMAs.
+    int s = 0, sg = 0; uint32_t ph = 0, it = 0;
+    uint32_t a_lo = lo0, fbar = full_bar(0), ebar = empty_bar(0);
     for (int64_t item = wid; item < total_items; item += nworkers, ++it) {
       const int bsel = it & 1; const uint32_t phacc = (it >> 1) & 1u;
       mbar_wait(tmem_empty(bsel), phacc ^ 1u);       // the epilogue warps (of both CTAs) have drained this accumulator buffer
       tc_fence_after();
       const uint32_t tacc = tmem_base + (uint32_t)(bsel * p.BN);
+      const uint32_t tfull = tmem_full(bsel);
       int chunk_i = 0;
       for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(full_bar(s), ph);
+        mbar_wait(fbar, ph);
         tc_fence_after();
-        const uint32_t sa = base + s * stage_bytes;
-        const uint64_t adesc = make_desc(sa, sbo, layout);
-        const uint64_t bdesc = make_desc(sa + a_bytes, sbo, layout);
+        const uint32_t b_lo = a_lo + a16;
         const bool last_chunk = (++chunk_i == kchunks);
         if (last_chunk) chunk_i = 0;
-        const bool last_kb = (kb + 1 == num_kb);
-        const bool rel = (sg + 1 == p.cg) || (last_kb && item + nworkers >= total_items);   // group full, or the very last K block
+        const bool rel = (++sg == p.cg);
         if (elect_one()) {
-          mma(tacc, adesc, bdesc, idesc, kb != 0 ? 1u : 0u);
-          if (last_chunk) {
+          mma(tacc, a_lo, b_lo, idesc, kb != 0 ? 1u : 0u);
+          if (last_chunk && tail_ks != BK / 8) {
 #pragma unroll
             for (int k = 1; k < BK / 8; ++k)
-              if (k < tail_ks) mma(tacc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, 1u);
+              if (k < tail_ks) mma(tacc, a_lo + (uint32_t)(2 * k), b_lo + (uint32_t)(2 * k), idesc, 1u);
           } else {
 #pragma unroll
-            for (int k = 1; k < BK / 8; ++k) mma(tacc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, 1u);
+            for (int k = 1; k < BK / 8; ++k) mma(tacc, a_lo + (uint32_t)(2 * k), b_lo + (uint32_t)(2 * k), idesc, 1u);
           }
-          if (rel) commit(empty_bar(g));
-          if (last_kb) commit(tmem_full(bsel));
+          if (rel) commit(ebar);
+          if (kb + 1 == num_kb) commit(tfull);
         }
         __syncwarp();
-        if (++sg == p.cg) { sg = 0; ++g; }
-        if (++s == p.stages) { s = 0; g = 0; ph ^= 1u; }
+        a_lo += st16; fbar += 8u;
+        if (rel) { sg = 0; ebar += 8u; }
+        if (++s == p.stages) { s = 0; ph ^= 1u; a_lo = lo0; fbar = full_bar(0); ebar = empty_bar(0); }
       }
     }
    }

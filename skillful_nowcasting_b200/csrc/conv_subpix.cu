@@ -35,7 +35,8 @@ struct SubpixParams {
 
 constexpr int kSubThreads = 320;  // warp0 TMA, warp1 MMA, warps 2..9 epilogue
 
-template <int MODE, int MT, bool PAIR>
+// TG: weight tiles per ring release (p.tg; p.b_stages % TG == 0): with the NT tiles of a patch unrolled, release points and the ring wrap test are static.
+template <int MODE, int MT, bool PAIR, int TG>
 __global__ void __launch_bounds__(kSubThreads, 1)
 conv_subpix_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
                    const __grid_constant__ CUtensorMap tmA3, const __grid_constant__ CUtensorMap tmB, const SubpixParams p) {
@@ -153,17 +154,22 @@ conv_subpix_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
     }
   } else if (warp == 1) {
     if (rank == 0) {
-      // ===== MMA issuer (pair: the leader alone, M = 256 instructions spanning both CTAs); warp-uniform loop, elected lane issues
+      // ===== MMA issuer (pair: the leader alone, M = 256 instructions spanning both CTAs); warp-uniform loop, elected lane issues.
+      // A weight tile feeds only 4 (forward) or 4*MT (dgrad) MMAs, so this warp's instruction count per tile is what bounds the kernel (ncu source
+      // view): descriptors are 32-bit low words (umma_tf32_lo), tap offsets are hoisted out of the unrolled tile loop, ring bookkeeping is static (TG).
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.BN >> 3) << 17) | (((PAIR ? 256u : 128u) >> 4) << 24);
       constexpr uint32_t layout = 2u;          // SWIZZLE_128B
       constexpr int ksteps = BK / 8;
-      const uint64_t adesc0 = make_desc(a_base, 8u * row_bytes, layout);
-      const uint64_t bdesc0 = make_desc(b_base, 8u * row_bytes, layout);
-      auto mma = [](uint32_t dcol, uint64_t ad, uint64_t bd, uint32_t id, uint32_t acc) {
-        if (PAIR) umma_tf32_2cta(dcol, ad, bd, id, acc); else umma_tf32(dcol, ad, bd, id, acc);
+      constexpr uint32_t rb16 = (uint32_t)BK * 4u / 16u;               // descriptor units (16 B) per patch row
+      constexpr uint32_t dhi = desc_hi(8u * (uint32_t)BK * 4u, layout);
+      const uint32_t a_lo0 = desc_lo(a_base), b_lo0 = desc_lo(b_base);
+      const uint32_t a_st16 = patch_al >> 4, b_st16 = b_al >> 4;
+      const int P16 = p.P * (int)rb16;
+      auto mma = [](uint32_t dcol, uint32_t al, uint32_t bl, uint32_t id, uint32_t acc) {
+        if (PAIR) umma_tf32_2cta_lo(dcol, al, bl, dhi, id, acc); else umma_tf32_lo(dcol, al, bl, dhi, id, acc);
       };
       auto commit = [](uint32_t bar) { if (PAIR) umma_commit_pair(bar); else umma_commit(bar); };
-      int sa = 0, sb = 0, gb = 0, tb = 0; uint32_t pha = 0, phb = 0, it = 0;
+      int sa = 0, sb = 0, gb = 0; uint32_t pha = 0, phb = 0, it = 0;
       for (int64_t item = wid; item < p.total_items; item += nworkers, ++it) {
         int nt, n, fs, ph; decode(item, nt, n, fs, ph);
         const int r_lo = (fs - p.P - 1) / p.P;
@@ -171,47 +177,52 @@ conv_subpix_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
         mbar_wait(acc_empty(buf), phacc ^ 1u);
         tc_fence_after();
         const uint32_t tacc = tmem_base + (uint32_t)(buf * NSLOT * p.BN);
+        const int fb16 = (fs - r_lo * p.P) * (int)rb16;      // patch row of the unshifted first pixel (in [P+1, 2P]), in descriptor units
         int view = 0, cin_view = 0;
         for (int pi = 0; pi < ppi; ++pi) {
           mbar_wait(a_full(sa), pha);
+          // row / column shift of tap (a, b) in descriptor units: forward (phase ph, j): (a + ph - 1) rows, (b + j - 1) columns;
+          // dgrad (view i, j): -(a + i - 1) rows, -(b + j - 1) columns
+          const int vi = view >> 1, vj = view & 1;
+          const int row0 = (MODE == 1) ? (ph - 1) * P16 : -(vi - 1) * P16;                    // a = 0; a = 1 adds (MODE 1) / subtracts (MODE 2) P16
+          const int col0 = (MODE == 1) ? -(int)rb16 : -(vj - 1) * (int)rb16;                  // MODE 1: b + j = 0; MODE 2: b = 0
+          const uint32_t a_lo = a_lo0 + (uint32_t)sa * a_st16 + (uint32_t)fb16;
 #pragma unroll
           for (int t = 0; t < NT; ++t) {
-            mbar_wait(b_full(sb), phb);
+            const int st = sb + t % TG;                               // weight-ring stage (sb = first stage of the release group)
+            mbar_wait(b_full(st), phb);
             tc_fence_after();
-            int sh, slot; uint32_t first;
+            int off, slot; uint32_t first;
             if (MODE == 1) {
               const int j = t >> 2, a = (t >> 1) & 1, b = t & 1;
-              sh = (a + ph - 1) * p.P + (b + j - 1);          // low-res input shift of this (phase, tap)
+              off = row0 + a * P16 + col0 + (b + j) * (int)rb16;      // low-res input shift of this (phase, tap)
               slot = j;
-              first = (pi == 0 && (t & 3) == 0) ? 0u : 1u;    // first MMA group into accumulator j of this item
+              first = (pi == 0 && (t & 3) == 0) ? 0u : 1u;            // first MMA group into accumulator j of this item
             } else {
-              const int a = t >> 1, b = t & 1, i = view >> 1, j = view & 1;
-              sh = -(a + i - 1) * p.P - (b + j - 1);          // the phase-(i,j) pixel of dy that tap (a,b) maps onto this input pixel
+              const int a = t >> 1, b = t & 1;
+              off = row0 - a * P16 + col0 - b * (int)rb16;            // the phase-(i,j) pixel of dy that tap (a,b) maps onto this input pixel
               slot = 0;
               first = (pi == 0 && t == 0) ? 0u : 1u;
             }
-            const int j0 = fs + sh - r_lo * p.P;             // first patch row this MMA group reads (>= 0)
-            const uint64_t bdesc = bdesc0 + (uint64_t)((sb * b_al) >> 4);
-            const uint64_t adesc = adesc0 + (uint64_t)((sa * patch_al + (uint32_t)j0 * row_bytes) >> 4);
+            const uint32_t bl = b_lo0 + (uint32_t)st * b_st16;
+            const uint32_t al = a_lo + (uint32_t)off;                 // first patch row this MMA group reads (>= 0)
             if (elect_one()) {
               if (MODE == 1) {
 #pragma unroll
                 for (int k = 0; k < ksteps; ++k)
-                  mma(tacc + (uint32_t)(slot * p.BN), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, k == 0 ? first : 1u);
+                  mma(tacc + (uint32_t)(slot * p.BN), al + (uint32_t)(2 * k), bl + (uint32_t)(2 * k), idesc, k == 0 ? first : 1u);
               } else {
 #pragma unroll
                 for (int mt = 0; mt < MT; ++mt) {
 #pragma unroll
                   for (int k = 0; k < ksteps; ++k)
-                    mma(tacc + (uint32_t)(mt * p.BN), adesc + (uint64_t)(mt * 128 * (BK * 4 / 16) + 2 * k), bdesc + (uint64_t)(2 * k), idesc,
-                        k == 0 ? first : 1u);
+                    mma(tacc + (uint32_t)(mt * p.BN), al + (uint32_t)(mt * 128 * (int)rb16 + 2 * k), bl + (uint32_t)(2 * k), idesc, k == 0 ? first : 1u);
                 }
               }
-              if (tb + 1 == p.tg) commit(b_empty(gb));
+              if (t % TG == TG - 1) commit(b_empty(gb));
             }
             __syncwarp();
-            if (++tb == p.tg) { tb = 0; ++gb; }
-            if (++sb == p.b_stages) { sb = 0; gb = 0; phb ^= 1u; }
+            if (t % TG == TG - 1) { sb += TG; ++gb; if (sb == p.b_stages) { sb = 0; gb = 0; phb ^= 1u; } }
           }
           if (elect_one()) commit(a_empty(sa));
           __syncwarp();
@@ -464,9 +475,10 @@ static int launch_subpix(int mode, const float* a_ptr, const float* wp, const fl
     const int lim = 226 * 1024;
     bool ok = true;
 #define DGMR_SET(K) ok = ok && cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, lim) == cudaSuccess
-    DGMR_SET((conv_subpix_kernel<1, 1, false>)); DGMR_SET((conv_subpix_kernel<1, 1, true>));
-    DGMR_SET((conv_subpix_kernel<2, 1, false>)); DGMR_SET((conv_subpix_kernel<2, 1, true>));
-    DGMR_SET((conv_subpix_kernel<2, 2, false>)); DGMR_SET((conv_subpix_kernel<2, 2, true>));
+    DGMR_SET((conv_subpix_kernel<1, 1, false, 2>)); DGMR_SET((conv_subpix_kernel<1, 1, true, 2>));
+    DGMR_SET((conv_subpix_kernel<1, 1, false, 4>)); DGMR_SET((conv_subpix_kernel<1, 1, true, 4>));
+    DGMR_SET((conv_subpix_kernel<2, 1, false, 2>)); DGMR_SET((conv_subpix_kernel<2, 1, true, 2>));
+    DGMR_SET((conv_subpix_kernel<2, 2, false, 2>)); DGMR_SET((conv_subpix_kernel<2, 2, true, 2>));
 #undef DGMR_SET
     if (!ok) { set_error("conv_subpix: cannot raise dynamic smem limit"); return 2; }
     attr_set = true;
@@ -482,12 +494,12 @@ static int launch_subpix(int mode, const float* a_ptr, const float* wp, const fl
   } else if (grid > p.total_items) grid = p.total_items;
   cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(kSubThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
   cudaError_t e;
-  if (mode == 1) e = pair ? cudaLaunchKernelEx(&cfg, conv_subpix_kernel<1, 1, true>, tmA[0], tmA[1], tmA[2], tmA[3], tmB, p)
-                          : cudaLaunchKernelEx(&cfg, conv_subpix_kernel<1, 1, false>, tmA[0], tmA[1], tmA[2], tmA[3], tmB, p);
-  else if (p.MT == 2) e = pair ? cudaLaunchKernelEx(&cfg, conv_subpix_kernel<2, 2, true>, tmA[0], tmA[1], tmA[2], tmA[3], tmB, p)
-                               : cudaLaunchKernelEx(&cfg, conv_subpix_kernel<2, 2, false>, tmA[0], tmA[1], tmA[2], tmA[3], tmB, p);
-  else e = pair ? cudaLaunchKernelEx(&cfg, conv_subpix_kernel<2, 1, true>, tmA[0], tmA[1], tmA[2], tmA[3], tmB, p)
-                : cudaLaunchKernelEx(&cfg, conv_subpix_kernel<2, 1, false>, tmA[0], tmA[1], tmA[2], tmA[3], tmB, p);
+#define DGMR_GO(...) cudaLaunchKernelEx(&cfg, conv_subpix_kernel<__VA_ARGS__>, tmA[0], tmA[1], tmA[2], tmA[3], tmB, p)
+  if (mode == 1 && p.tg == 4) e = pair ? DGMR_GO(1, 1, true, 4) : DGMR_GO(1, 1, false, 4);
+  else if (mode == 1) e = pair ? DGMR_GO(1, 1, true, 2) : DGMR_GO(1, 1, false, 2);
+  else if (p.MT == 2) e = pair ? DGMR_GO(2, 2, true, 2) : DGMR_GO(2, 2, false, 2);
+  else e = pair ? DGMR_GO(2, 1, true, 2) : DGMR_GO(2, 1, false, 2);
+#undef DGMR_GO
   if (e != cudaSuccess) { set_error("conv_subpix: launch failed: %s", cudaGetErrorString(e)); return 2; }
   return 0;
 }

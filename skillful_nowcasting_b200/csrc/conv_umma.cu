@@ -537,7 +537,9 @@ struct PatchConvParams {
 constexpr int kPatchThreads = 320;  // warp0 TMA, warp1 MMA, warps 2..9 epilogue
 // PAIR: launched as clusters of 2 CTAs (one TPC); see the cta_group::2 helpers above.  The two CTAs of a pair work on the SAME tile
 // position of two different images, so their activation patches have identical shared-memory geometry (one A descriptor serves both).
-template <int BK, int MT, bool PAIR>
+// TG3: the weight ring is released per filter row of three taps (p.tg == 3, p.b_stages % 3 == 0): with the nine taps unrolled the release points,
+// ring positions within a row and the ring wrap test become static (one test per row instead of three per tap).
+template <int BK, int MT, bool PAIR, bool TG3>
 __global__ void __launch_bounds__(kPatchThreads, 1)
 conv_umma_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const PatchConvParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -611,9 +613,12 @@ conv_umma_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         int nt, n, d, fs; decode(q.item, nt, n, d, fs);
         const int r_lo = (fs - p.P - 1) / p.P;            // first padded image row of the patch
         mbar_wait(a_empty(sa), pha ^ 1u);
+#ifdef DGMR_TUNING
         if (p.dbg & 4) {            // tuning: no loads, the MMAs run on whatever is in shared memory
           if (rank == 0 && elect_one()) mbar_expect_tx(a_full(sa), 0);
-        } else if (PAIR) {
+        } else
+#endif
+        if (PAIR) {
           const uint32_t lead = mapa_rank(a_full(sa), 0);
           if (elect_one()) {
             if (rank == 0) mbar_expect_tx(a_full(sa), 2u * patch_bytes);   // the leader arms for both CTAs' bytes; the peer only sends them
@@ -635,9 +640,12 @@ conv_umma_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           // weight tiles are released in groups of p.tg taps: a tcgen05.commit costs the tensor pipe ~780 cycles (measured,
           // dgmr_debug_umma_rate), more than the 8 MMAs of one tap at N <= 128, so one commit per tap would throttle the MMAs
           if (tb == 0) mbar_wait(b_empty(gb), phb ^ 1u);
+#ifdef DGMR_TUNING
           if (p.dbg & 4) {
             if (rank == 0 && elect_one()) mbar_expect_tx(b_full(sb), 0);
-          } else if (PAIR) {
+          } else
+#endif
+          if (PAIR) {
             const uint32_t lead = mapa_rank(b_full(sb), 0);
             if (elect_one()) {
               if (rank == 0) mbar_expect_tx(b_full(sb), 2u * b_bytes);
@@ -656,15 +664,21 @@ conv_umma_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     }
   } else if (warp == 1) {
     if (rank == 0) {
-      // ===== MMA issuer (pair: the leader alone, with M = 256 instructions spanning both CTAs); warp-uniform loop, elected lane issues
+      // ===== MMA issuer (pair: the leader alone, with M = 256 instructions spanning both CTAs); warp-uniform loop, elected lane issues.
+      // This warp's instruction stream is what bounds the kernel at N <= 128 (an MMA lasts ~60 cycles there, an instruction issues every ~4.4):
+      // descriptors are advanced as 32-bit low words (umma_tf32_lo), all per-tap bookkeeping that can be static is static (TG3), nothing is
+      // divided or multiplied in the tap loop.
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.BN >> 3) << 17) | (((PAIR ? 256u : 128u) >> 4) << 24);
       constexpr uint32_t layout = (BK == 32) ? 2u : 4u;
       constexpr int ksteps = BK / 8;
+      constexpr uint32_t rb16 = (uint32_t)BK * 4u / 16u;               // descriptor units (16 B) per patch row
+      constexpr uint32_t dhi = desc_hi(8u * (uint32_t)BK * 4u, layout);
       const int tail_ks = (p.Cin % BK) ? (p.Cin % BK) / 8 : ksteps;
-      const uint64_t adesc0 = make_desc(a_base, 8u * row_bytes, layout);
-      const uint64_t bdesc0 = make_desc(b_base, 8u * row_bytes, layout);
-      auto mma = [](uint32_t dcol, uint64_t ad, uint64_t bd, uint32_t id, uint32_t acc) {
-        if (PAIR) umma_tf32_2cta(dcol, ad, bd, id, acc); else umma_tf32(dcol, ad, bd, id, acc);
+      const uint32_t a_lo0 = desc_lo(a_base), b_lo0 = desc_lo(b_base);
+      const uint32_t a_st16 = patch_al >> 4, b_st16 = b_al >> 4;
+      const int P16 = p.P * (int)rb16;                                 // descriptor units per padded image row
+      auto mma = [](uint32_t dcol, uint32_t al, uint32_t bl, uint32_t id, uint32_t acc) {
+        if (PAIR) umma_tf32_2cta_lo(dcol, al, bl, dhi, id, acc); else umma_tf32_lo(dcol, al, bl, dhi, id, acc);
       };
       auto commit = [](uint32_t bar) { if (PAIR) umma_commit_pair(bar); else umma_commit(bar); };
       int sa = 0, sb = 0, gb = 0, tb = 0; uint32_t pha = 0, phb = 0, it = 0;   // ring positions advance incrementally: no divisions in the issue loop
@@ -675,46 +689,54 @@ conv_umma_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         mbar_wait(acc_empty(buf), phacc ^ 1u);
         tc_fence_after();
         const uint32_t tacc = tmem_base + (uint32_t)(buf * MT * p.BN);
+        const int fb16 = (fs - r_lo * p.P) * (int)rb16;      // patch row of the centre tap's first pixel (in [P+1, 2P]), in descriptor units
         int chunk_i = 0;
         for (int a = 0; a < a_per_item; ++a) {
           const bool tail_now = (++chunk_i == chunks) && tail_ks != ksteps;   // channel-tail chunk: fewer valid k-steps
           if (chunk_i == chunks) chunk_i = 0;
           mbar_wait(a_full(sa), pha);
+          const uint32_t a_lo = a_lo0 + (uint32_t)sa * a_st16 + (uint32_t)fb16;
 #pragma unroll
           for (int tap = 0; tap < 9; ++tap) {
-            mbar_wait(b_full(sb), phb);
+            const int st = TG3 ? sb + tap % 3 : sb;                 // weight-ring stage of this tap (TG3: sb = first stage of the filter row)
+            mbar_wait(b_full(st), phb);
             tc_fence_after();
             const int th = tap / 3, tw = tap - th * 3;
-            const int j0 = fs + (th - 1) * p.P + (tw - 1) - r_lo * p.P;     // first patch row this tap reads (>= 0)
-            // descriptors differ from the per-stage base only in their 14-bit start-address field: one add each.
-            // Fully unrolled: the single issuing thread must spend far fewer cycles per MMA than the MMA takes (N/2 cycles).
-            const uint64_t bdesc = bdesc0 + (uint64_t)((sb * b_al) >> 4);
-            const uint64_t adesc = adesc0 + (uint64_t)((sa * patch_al + (uint32_t)j0 * row_bytes) >> 4);
+            // descriptors differ from the per-stage base only in their 14-bit start-address field: one 32-bit add each
+            const uint32_t bl = b_lo0 + (uint32_t)st * b_st16;
+            const uint32_t al = a_lo + (uint32_t)((th - 1) * P16 + (tw - 1) * (int)rb16);      // first patch row this tap reads (>= 0)
             const uint32_t acc0 = (a | tap) != 0 ? 1u : 0u;
+            const bool grp_end = TG3 ? (tap % 3 == 2) : (tb + 1 == p.tg);
             if (elect_one()) {
-            if (p.dbg & 2) {
-            } else if (!tail_now) {
+#ifdef DGMR_TUNING
+              if (p.dbg & 2) {
+              } else
+#endif
+              if (!tail_now) {
 #pragma unroll
-              for (int mt = 0; mt < MT; ++mt) {
+                for (int mt = 0; mt < MT; ++mt) {
 #pragma unroll
-                for (int k = 0; k < ksteps; ++k)
-                  mma(tacc + (uint32_t)(mt * p.BN), adesc + (uint64_t)(mt * 128 * (BK * 4 / 16) + 2 * k), bdesc + (uint64_t)(2 * k), idesc,
-                      k == 0 ? acc0 : 1u);
+                  for (int k = 0; k < ksteps; ++k)
+                    mma(tacc + (uint32_t)(mt * p.BN), al + (uint32_t)(mt * 128 * (int)rb16 + 2 * k), bl + (uint32_t)(2 * k), idesc, k == 0 ? acc0 : 1u);
+                }
+              } else {
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+                  for (int k = 0; k < ksteps; ++k)
+                    if (k < tail_ks) mma(tacc + (uint32_t)(mt * p.BN), al + (uint32_t)(mt * 128 * (int)rb16 + 2 * k), bl + (uint32_t)(2 * k), idesc,
+                                         k == 0 ? acc0 : 1u);
+                }
               }
-            } else {
-#pragma unroll
-              for (int mt = 0; mt < MT; ++mt) {
-#pragma unroll
-                for (int k = 0; k < ksteps; ++k)
-                  if (k < tail_ks) mma(tacc + (uint32_t)(mt * p.BN), adesc + (uint64_t)(mt * 128 * (BK * 4 / 16) + 2 * k), bdesc + (uint64_t)(2 * k), idesc,
-                                       k == 0 ? acc0 : 1u);
-              }
-            }
-            if (tb + 1 == p.tg) commit(b_empty(gb));
+              if (grp_end) commit(b_empty(gb));
             }
             __syncwarp();
-            if (++tb == p.tg) { tb = 0; ++gb; }
-            if (++sb == p.b_stages) { sb = 0; gb = 0; phb ^= 1u; }
+            if (TG3) {
+              if (tap % 3 == 2) { sb += 3; ++gb; if (sb == p.b_stages) { sb = 0; gb = 0; phb ^= 1u; } }
+            } else {
+              if (++tb == p.tg) { tb = 0; ++gb; }
+              if (++sb == p.b_stages) { sb = 0; gb = 0; phb ^= 1u; }
+            }
           }
           if (elect_one()) commit(a_empty(sa));
           __syncwarp();
@@ -749,7 +771,11 @@ conv_umma_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       for (int j = 0; j < 4; ++j) {
         const int f = fs + 128 * mt + q * 32 + lr + 8 * j;
         const int hp = f / p.P, wp = f - hp * p.P;
-        vrow[j] = (wp >= 1) && (wp <= p.W) && (hp >= 1) && (hp <= p.H) && (n < p.N) && !(p.dbg & 1);
+        vrow[j] = (wp >= 1) && (wp <= p.W) && (hp >= 1) && (hp <= p.H) && (n < p.N)
+#ifdef DGMR_TUNING
+                  && !(p.dbg & 1)
+#endif
+            ;
         mrow[j] = ((((int64_t)n * p.D + d) * p.H + (hp - 1)) * p.W + (wp - 1)) * p.Cout + co0 + 4 * lc;
         rrow[j] = p.res_up2 ? ((((int64_t)n * p.D + d) * (p.H >> 1) + ((hp - 1) >> 1)) * (p.W >> 1) + ((wp - 1) >> 1)) * p.Cout + co0 + 4 * lc : mrow[j];
       }
@@ -1699,12 +1725,14 @@ int launch_conv_umma_patch(const float* x, const float* wp, const float* bias, c
   static bool attr_set = false;
   if (!attr_set) {
     const int lim = 226 * 1024;
-    if (cudaFuncSetAttribute(conv_umma_patch_kernel<32, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim) != cudaSuccess ||
-        cudaFuncSetAttribute(conv_umma_patch_kernel<32, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim) != cudaSuccess ||
-        cudaFuncSetAttribute(conv_umma_patch_kernel<16, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim) != cudaSuccess ||
-        cudaFuncSetAttribute(conv_umma_patch_kernel<16, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim) != cudaSuccess ||
-        cudaFuncSetAttribute(conv_umma_patch_kernel<32, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim) != cudaSuccess ||
-        cudaFuncSetAttribute(conv_umma_patch_kernel<32, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim) != cudaSuccess) {
+    bool ok = true;
+#define DGMR_SET(...) ok = ok && cudaFuncSetAttribute(conv_umma_patch_kernel<__VA_ARGS__>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim) == cudaSuccess
+    DGMR_SET(32, 1, false, false); DGMR_SET(32, 2, false, false); DGMR_SET(16, 1, false, false); DGMR_SET(16, 2, false, false);
+    DGMR_SET(32, 1, true, false); DGMR_SET(32, 2, true, false);
+    DGMR_SET(32, 1, false, true); DGMR_SET(32, 2, false, true); DGMR_SET(16, 1, false, true); DGMR_SET(16, 2, false, true);
+    DGMR_SET(32, 1, true, true); DGMR_SET(32, 2, true, true);
+#undef DGMR_SET
+    if (!ok) {
       set_error("conv_umma_patch: cannot raise dynamic smem limit"); return 2;
     }
     attr_set = true;
@@ -1718,18 +1746,24 @@ int launch_conv_umma_patch(const float* x, const float* wp, const float* bias, c
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    cudaError_t e = (p.MT == 2) ? cudaLaunchKernelEx(&cfg, conv_umma_patch_kernel<32, 2, true>, tmA, tmB, p)
-                                : cudaLaunchKernelEx(&cfg, conv_umma_patch_kernel<32, 1, true>, tmA, tmB, p);
+    const bool tg3 = p.tg == 3;
+    cudaError_t e = (p.MT == 2) ? (tg3 ? cudaLaunchKernelEx(&cfg, conv_umma_patch_kernel<32, 2, true, true>, tmA, tmB, p)
+                                       : cudaLaunchKernelEx(&cfg, conv_umma_patch_kernel<32, 2, true, false>, tmA, tmB, p))
+                                : (tg3 ? cudaLaunchKernelEx(&cfg, conv_umma_patch_kernel<32, 1, true, true>, tmA, tmB, p)
+                                       : cudaLaunchKernelEx(&cfg, conv_umma_patch_kernel<32, 1, true, false>, tmA, tmB, p));
     if (e != cudaSuccess) { set_error("conv_umma_patch: cluster launch failed: %s", cudaGetErrorString(e)); return 2; }
     return 0;
   }
   int64_t grid = sm_count();
   if (grid > p.total_items) grid = p.total_items;
   const dim3 g((unsigned)grid);
-  if (p.BK == 32 && p.MT == 2) conv_umma_patch_kernel<32, 2, false><<<g, kPatchThreads, smem, st>>>(tmA, tmB, p);
-  else if (p.BK == 32) conv_umma_patch_kernel<32, 1, false><<<g, kPatchThreads, smem, st>>>(tmA, tmB, p);
-  else if (p.MT == 2) conv_umma_patch_kernel<16, 2, false><<<g, kPatchThreads, smem, st>>>(tmA, tmB, p);
-  else conv_umma_patch_kernel<16, 1, false><<<g, kPatchThreads, smem, st>>>(tmA, tmB, p);
+#define DGMR_GO(BKV, MTV) do { if (p.tg == 3) conv_umma_patch_kernel<BKV, MTV, false, true><<<g, kPatchThreads, smem, st>>>(tmA, tmB, p); \
+                               else conv_umma_patch_kernel<BKV, MTV, false, false><<<g, kPatchThreads, smem, st>>>(tmA, tmB, p); } while (0)
+  if (p.BK == 32 && p.MT == 2) DGMR_GO(32, 2);
+  else if (p.BK == 32) DGMR_GO(32, 1);
+  else if (p.MT == 2) DGMR_GO(16, 2);
+  else DGMR_GO(16, 1);
+#undef DGMR_GO
   DGMR_CHECK_LAUNCH("conv_umma_patch");
   return 0;
 }

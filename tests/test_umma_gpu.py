@@ -222,7 +222,7 @@ def test_conv_umma_kwstack(cuda_backend, shape, variant, pair):
     y2 = torch.empty_like(y)
     cuda_backend.conv_fwd(dev(x), dev(wp), dev(bias), dev(scale), dev(res), y2, n, d, h, w, cin, cout, kd, 3, 3, g, act)
     torch.cuda.synchronize()
-    if cout < 64:
+    if cout < 64 and cin >= 32:     # (AUTO leaves 16-channel inputs to the plain kernel: measured slower here)
         assert torch.equal(y, y2)
 
 
