@@ -1,6 +1,2 @@
-TAILN=8 ./run_gpu_tests.sh umma
-echo "=== time_kwstack"; timeout 120 python tests/time_kwstack.py > gpurun_out/time_kwstack.log 2>&1; echo "exit $?"; head -5 gpurun_out/time_kwstack.log
-TAILN=6 ./run_gpu_tests.sh parity
-b() { name=$1; shift; echo "=== bench $name"; DGMR_BENCH_DUMP=gpurun_out/shapes_$name.tsv timeout 600 python bench.py "$@" > gpurun_out/bench_$name.json 2> gpurun_out/bench_$name.err; echo "exit $?"; python -c "
-import json; d=json.load(open('gpurun_out/bench_$name.json')); print(d['value'], d['ms_per_step'], d['e2e']['value'], d['gpu_launches']); print(d['kernel_breakdown_ms'])"; tail -n 3 gpurun_out/bench_$name.err; }
-b c3i --steps 5 --warmup 3 --no-ref-gpu --no-cpu-baseline
+TAILN=25 ./run_gpu_tests.sh allv
+grep -E "DISC" gpurun_out/allv.log | head -20

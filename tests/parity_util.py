@@ -268,9 +268,14 @@ def compare_gan_step(got, ref, g0, d0, tol):
 
 
 # ------------------------------------------------------------------------------------------------ discriminators, separately
-def run_discriminator_case(which, training, device, tol_fwd, tol_grad_l2=None, cfg=C1, seed=3):
+def run_discriminator_case(which, training, device, tol_fwd, tol_grad_l2=None, cfg=C1, seed=5):
     """SpatialDiscriminator / TemporalDiscriminator alone against the oracle (ref: dgmr/discriminators.py:104-138, 196-232) on a
-    [2B, T_in + T, 1, S, S] batch of real || "generated" sequences; forward scores and (training) the global gradient error."""
+    [2B, T_in + T, 1, S, S] batch of real || "generated" sequences; forward scores and (training) the global gradient error.
+
+    The seed matters: with seed 3 (used until round 2) the temporal case sits ON a ReLU kink of the head -- relative noise of 1e-7 injected into the
+    fp32 host emulator's convolution outputs flips the global gradient error between 2.9e-3 and 6.1e-2 (bimodal, nothing in between), which made the
+    device test depend on the summation order of unrelated kernels.  Seed 5 is a generic point: 2.4e-5 for the emulator, growing smoothly with
+    injected noise (6e-5 at 1e-6)."""
     import skillful_nowcasting_b200 as B
 
     torch.manual_seed(seed)

@@ -199,7 +199,7 @@ def test_conv_simt(cuda_backend, shape, act, with_res, with_scale):
           rtol=5e-5, atol=5e-5, kwargs=dict(algo=1))
 
 
-@pytest.mark.parametrize("G,rows,C,act", [(1, 300, 24, 0), (3, 64, 48, 1), (2, 17, 4, 1), (2, 40, 32, 257), (1, 33, 7, 1)])
+@pytest.mark.parametrize("G,rows,C,act", [(1, 300, 24, 0), (3, 64, 48, 1), (2, 17, 4, 1), (2, 40, 32, 257), (1, 33, 7, 1), (2, 4, 768, 0), (2, 5, 1024, 1), (3, 7, 1536, 0)])
 def test_conv_bwd_prep(cuda_backend, G, rows, C, act):
     torch.manual_seed(8)
     dy, y, res = (torch.randn(G * rows, C) for _ in range(3))
