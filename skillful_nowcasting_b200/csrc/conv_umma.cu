@@ -135,47 +135,48 @@ conv_umma_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     {
       // ===== MMA issuer
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((128u >> 4) << 24);
-      const uint32_t row_bytes = BK * 4u;
-      const uint32_t layout = row_bytes == 128 ? 2u : (row_bytes == 64 ? 4u : 6u);
-      const uint32_t sbo = 8u * row_bytes;
+      constexpr uint32_t row_bytes = BK * 4u;
+      constexpr uint32_t layout = row_bytes == 128 ? 2u : (row_bytes == 64 ? 4u : 6u);
+      constexpr uint32_t dhi = desc_hi(8u * row_bytes, layout);     // descriptors as (low word, common high word): see umma_tf32_lo
       const int tail_ks = (p.Cin % BK) ? (p.Cin % BK) / 8 : BK / 8;
+      const uint32_t lo0 = desc_lo(base), st16 = stage_bytes >> 4, a16 = a_bytes >> 4;
+      const uint32_t lo_off = half_bytes >> 4;     // X3: the lo tiles sit half a stage further on
       int chunk_i = 0;
       int s = 0, g = 0, sg = 0; uint32_t ph = 0;
+      uint32_t a_lo = lo0;
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(full_bar(s), ph);
         tc_fence_after();
-        const uint32_t sa = base + s * stage_bytes;
-        const uint64_t adesc = make_desc(sa, sbo, layout);
-        const uint64_t bdesc = make_desc(sa + a_bytes, sbo, layout);
+        const uint32_t b_lo = a_lo + a16;
         const bool last_chunk = (++chunk_i == kchunks);   // last chunk of a tap: possibly a channel tail with fewer valid k-steps
         if (last_chunk) chunk_i = 0;
         const bool rel = (sg + 1 == p.cg) || (kb + 1 == num_kb);   // release this group (the final, possibly partial, one too)
-        const uint64_t lo_off = (uint64_t)(half_bytes >> 4);     // X3: the lo tiles sit half a stage further on
-        auto mma = [&](uint64_t ad, uint64_t bd, uint32_t acc) {
+        auto mma = [&](uint32_t ad, uint32_t bd, uint32_t acc) {
           if (X3) {
-            umma_tf32(tmem_base, ad + lo_off, bd, idesc, acc);
-            umma_tf32(tmem_base, ad, bd + lo_off, idesc, 1u);
-            umma_tf32(tmem_base, ad, bd, idesc, 1u);
+            umma_tf32_lo(tmem_base, ad + lo_off, bd, dhi, idesc, acc);
+            umma_tf32_lo(tmem_base, ad, bd + lo_off, dhi, idesc, 1u);
+            umma_tf32_lo(tmem_base, ad, bd, dhi, idesc, 1u);
           } else {
-            umma_tf32(tmem_base, ad, bd, idesc, acc);
+            umma_tf32_lo(tmem_base, ad, bd, dhi, idesc, acc);
           }
         };
         if (elect_one()) {
           // advance 8 tf32 = 32 bytes along K inside the swizzle row: +2 in the (addr>>4) field
-          mma(adesc, bdesc, kb != 0 ? 1u : 0u);
+          mma(a_lo, b_lo, kb != 0 ? 1u : 0u);
           if (last_chunk) {
 #pragma unroll
             for (int k = 1; k < BK / 8; ++k)
-              if (k < tail_ks) mma(adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), 1u);
+              if (k < tail_ks) mma(a_lo + (uint32_t)(2 * k), b_lo + (uint32_t)(2 * k), 1u);
           } else {
 #pragma unroll
-            for (int k = 1; k < BK / 8; ++k) mma(adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), 1u);
+            for (int k = 1; k < BK / 8; ++k) mma(a_lo + (uint32_t)(2 * k), b_lo + (uint32_t)(2 * k), 1u);
           }
           if (rel) umma_commit(empty_bar(g));
         }
         __syncwarp();
+        a_lo += st16;
         if (++sg == p.cg) { sg = 0; ++g; }
-        if (++s == p.stages) { s = 0; g = 0; ph ^= 1u; }
+        if (++s == p.stages) { s = 0; g = 0; ph ^= 1u; a_lo = lo0; }
       }
       if (elect_one()) umma_commit(tmem_full_bar);
       __syncwarp();
@@ -390,13 +391,16 @@ conv_umma_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __gr
   } else if (warp == 1) {
     // ===== MMA issuer
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((128u >> 4) << 24);
-    const uint32_t row_bytes = BK * 4u;
-    const uint32_t layout = row_bytes == 128 ? 2u : (row_bytes == 64 ? 4u : 6u);
-    const uint32_t sbo = 8u * row_bytes;
+    constexpr uint32_t row_bytes = BK * 4u;
+    constexpr uint32_t layout = row_bytes == 128 ? 2u : (row_bytes == 64 ? 4u : 6u);
+    constexpr uint32_t dhi = desc_hi(8u * row_bytes, layout);     // descriptors as (low word, common high word): see umma_tf32_lo
     const int tail_ks = (p.Cin % BK) ? (p.Cin % BK) / 8 : BK / 8;
+    const uint32_t lo0 = desc_lo(base), st16 = stage_bytes >> 4, a16 = a_bytes >> 4;
     int s = 0, g = 0, sg = 0; uint32_t ph = 0, it = 0;
+    uint32_t a_lo = lo0;
     for (int64_t t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
       const int bsel = it & 1; const uint32_t phacc = (it >> 1) & 1u;
+      const bool last_tile = t + gridDim.x >= total_tiles;
       mbar_wait(tmem_empty(bsel), phacc ^ 1u);       // the epilogue has drained this accumulator buffer
       tc_fence_after();
       const uint32_t tacc = tmem_base + (uint32_t)(bsel * p.BN);
@@ -404,29 +408,28 @@ conv_umma_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __gr
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(full_bar(s), ph);
         tc_fence_after();
-        const uint32_t sa = base + s * stage_bytes;
-        const uint64_t adesc = make_desc(sa, sbo, layout);
-        const uint64_t bdesc = make_desc(sa + a_bytes, sbo, layout);
+        const uint32_t b_lo = a_lo + a16;
         const bool last_chunk = (++chunk_i == kchunks);
         if (last_chunk) chunk_i = 0;
         const bool last_kb = (kb + 1 == num_kb);
-        const bool rel = (sg + 1 == p.cg) || (last_kb && t + gridDim.x >= total_tiles);   // group full, or the very last K block
+        const bool rel = (sg + 1 == p.cg) || (last_kb && last_tile);   // group full, or the very last K block
         if (elect_one()) {
-          umma_tf32(tacc, adesc, bdesc, idesc, kb != 0 ? 1u : 0u);
+          umma_tf32_lo(tacc, a_lo, b_lo, dhi, idesc, kb != 0 ? 1u : 0u);
           if (last_chunk) {
 #pragma unroll
             for (int k = 1; k < BK / 8; ++k)
-              if (k < tail_ks) umma_tf32(tacc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, 1u);
+              if (k < tail_ks) umma_tf32_lo(tacc, a_lo + (uint32_t)(2 * k), b_lo + (uint32_t)(2 * k), dhi, idesc, 1u);
           } else {
 #pragma unroll
-            for (int k = 1; k < BK / 8; ++k) umma_tf32(tacc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, 1u);
+            for (int k = 1; k < BK / 8; ++k) umma_tf32_lo(tacc, a_lo + (uint32_t)(2 * k), b_lo + (uint32_t)(2 * k), dhi, idesc, 1u);
           }
           if (rel) umma_commit(empty_bar(g));
           if (last_kb) umma_commit(tmem_full(bsel));
         }
         __syncwarp();
+        a_lo += st16;
         if (++sg == p.cg) { sg = 0; ++g; }
-        if (++s == p.stages) { s = 0; g = 0; ph ^= 1u; }
+        if (++s == p.stages) { s = 0; g = 0; ph ^= 1u; a_lo = lo0; }
       }
     }
   } else {
@@ -1107,38 +1110,36 @@ conv_umma_wgrad_row_kernel(const __grid_constant__ CUtensorMap tmDz, const __gri
   } else if (warp == 1) {
     if (num_kb > 0) {
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(p.BN >> 3) << 17) | ((128u >> 4) << 24);
-      auto mn_desc = [&](uint32_t saddr, uint32_t lbo) {
-        uint64_t d = 0;
-        d |= (uint64_t)((saddr >> 4) & 0x3FFFu);
-        d |= (uint64_t)((lbo >> 4) & 0x3FFFu) << 16;
-        d |= (uint64_t)((512u >> 4) & 0x3FFFu) << 32;   // SBO: next 4-row K atom
-        d |= (uint64_t)1u << 46;
-        d |= (uint64_t)1u << 61;                        // SWIZZLE_128B_BASE32B
-        return d;
-      };
+      // MN-major descriptors as (low word, common high word): low = start address >> 4 | LBO >> 4 << 16 (LBO: 4096 between the 32-co blocks of
+      // the dz tile, `pitch` between the 32-ci blocks of the x patch); high = SBO (512: next 4-row K atom) | version | SWIZZLE_128B_BASE32B.
+      // One 32-bit add per descriptor in the issue loop (the issuing warp's instruction rate bounds the narrow layers).
+      constexpr uint32_t dhi = ((512u >> 4) & 0x3FFFu) | (1u << 14) | (1u << 29);
+      const uint32_t a_lbo = ((4096u >> 4) & 0x3FFFu) << 16, b_lbo = ((pitch >> 4) & 0x3FFFu) << 16;
       // first patch row of k-step k (8 pixels): the K block is p.rpk image rows of wt pixels, each stored with its two halo pixels
-      uint32_t prow[4];
+      uint32_t prow8[4];     // in descriptor units (a patch row is 128 B = 8 units)
 #pragma unroll
-      for (int k = 0; k < 4; ++k) prow[k] = (uint32_t)(((8 * k) / wt) * (wt + 2) + (8 * k) % wt);
+      for (int k = 0; k < 4; ++k) prow8[k] = (uint32_t)(((8 * k) / wt) * (wt + 2) + (8 * k) % wt + dw0) * 8u;
+      const uint32_t st16 = stage_bytes >> 4;
+      const uint32_t a_lo0 = ((base >> 4) & 0x3FFFu) | a_lbo, b_lo0 = (((base + a_bytes) >> 4) & 0x3FFFu) | b_lbo;
       int s = 0; uint32_t ph = 0;
+      uint32_t a_lo = a_lo0, b_lo = b_lo0;
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(full_bar(s), ph);
         tc_fence_after();
-        const uint32_t sa = base + s * stage_bytes;
         if (elect_one()) {
 #pragma unroll
           for (int dw = 0; dw < 3; ++dw) {
             if (dw < ndw) {
 #pragma unroll
               for (int k = 0; k < 4; ++k)
-                umma_tf32(tmem_base + (uint32_t)(dw * p.BN), mn_desc(sa + k * 1024u, 4096u),
-                          mn_desc(sa + a_bytes + (prow[k] + (uint32_t)(dw0 + dw)) * 128u, pitch), idesc, (kb | k) != 0 ? 1u : 0u);
+                umma_tf32_lo(tmem_base + (uint32_t)(dw * p.BN), a_lo + (uint32_t)(k * 64), b_lo + prow8[k] + (uint32_t)(dw * 8), dhi, idesc, (kb | k) != 0 ? 1u : 0u);
             }
           }
           umma_commit(empty_bar(s));
         }
         __syncwarp();
-        if (++s == p.stages) { s = 0; ph ^= 1u; }
+        a_lo += st16; b_lo += st16;
+        if (++s == p.stages) { s = 0; ph ^= 1u; a_lo = a_lo0; b_lo = b_lo0; }
       }
       if (elect_one()) umma_commit(tmem_full_bar);
       __syncwarp();
