@@ -100,8 +100,8 @@ conv_subpix_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
   };
 
   if (warp == 0) {
-    // ===== TMA producer: one activation patch per (phase view,) channel chunk, NT weight tiles per patch; the next patch is issued
-    // before the weight tiles of the current one so the large load overlaps a whole step of MMAs
+    // ===== TMA producer: one activation patch per (phase view,) channel chunk, NT weight tiles per patch; the patch of the NEXT step is issued
+    // right after the weight tiles of the current one, so the large load overlaps a whole step of MMAs
     struct Cur { int64_t item; int pi; };
     auto valid = [&](const Cur& q) { return q.item < p.total_items; };
     auto advance = [&](Cur& q) { if (++q.pi == ppi) { q.pi = 0; q.item += nworkers; } };
@@ -126,10 +126,10 @@ conv_subpix_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
       __syncwarp();
       if (++sa == p.a_stages) { sa = 0; pha ^= 1u; }
     };
+    // (weight tiles of step s first, THEN the patch of step s+1 whose slot step s-1 is still reading: see conv_umma_patch_kernel)
     Cur ca{wid, 0}, cb = ca;
     if (valid(ca)) { issue_patch(ca); advance(ca); }
     while (valid(cb)) {
-      if (valid(ca)) { issue_patch(ca); advance(ca); }
       int nt, n, fs, ph; decode(cb.item, nt, n, fs, ph);
       const int view = (MODE == 2) ? cb.pi / chunks : 0;
       const int c = (MODE == 2) ? cb.pi - view * chunks : cb.pi;
@@ -151,6 +151,7 @@ conv_subpix_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
         if (++sb == p.b_stages) { sb = 0; gb = 0; phb ^= 1u; }
       }
       advance(cb);
+      if (valid(ca)) { issue_patch(ca); advance(ca); }
     }
   } else if (warp == 1) {
     if (rank == 0) {

@@ -605,7 +605,7 @@ conv_umma_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   if (warp == 0) {
     {
       // ===== TMA producer (warp-uniform loop, elected lane issues): one activation patch per (kd, channel chunk), nine weight tiles per patch.  The patch of step s+1 is
-      // issued BEFORE the weight tiles of step s, so the (large) patch load overlaps a whole step of MMAs.
+      // issued right after the weight tiles of step s, so the (large) patch load overlaps a whole step of MMAs.
       struct Cur { int64_t item; int kdi, c; };
       auto valid = [&](const Cur& q) { return q.item < p.total_items; };
       auto advance = [&](Cur& q) {
@@ -634,10 +634,13 @@ conv_umma_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         __syncwarp();
         if (++sa == p.a_stages) { sa = 0; pha ^= 1u; }
       };
+      // Order matters: the weight tiles of step s go out BEFORE the patch of step s+1.  The patch slot of step s+1 is the one step s-1 is still
+      // reading, so waiting for it first (as this loop did until round 2) held back the weights of step s until step s-1 had completely
+      // finished -- every step then started with the MMA warp waiting a full TMA latency for its first weight tile (ncu source view: 21 % of
+      // that warp's samples on that one wait) although the weight ring holds a whole step.
       Cur ca{wid, 0, 0}, cb = ca;
       if (valid(ca)) { issue_patch(ca); advance(ca); }
       while (valid(cb)) {
-        if (valid(ca)) { issue_patch(ca); advance(ca); }
         int nt, n, d, fs; decode(cb.item, nt, n, d, fs);
         for (int tap = 0; tap < 9; ++tap) {
           // weight tiles are released in groups of p.tg taps: a tcgen05.commit costs the tensor pipe ~780 cycles (measured,
@@ -663,6 +666,7 @@ conv_umma_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           if (++sb == p.b_stages) { sb = 0; gb = 0; phb ^= 1u; }
         }
         advance(cb);
+        if (valid(ca)) { issue_patch(ca); advance(ca); }
       }
     }
   } else if (warp == 1) {
