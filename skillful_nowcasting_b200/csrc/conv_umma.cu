@@ -1646,7 +1646,9 @@ static bool umma_patch_ok(int N, int D, int H, int W, int Cin, int Cout, int kd,
 // 128^2 runs 289 TF/s on the plain kernel, 178 TF/s here).
 static bool umma_patch_profitable(int N, int D, int H, int W, int Cin, int Cout) {
   if (g_opt.prefer_patch == 1) return true;
-  return Cin % 32 == 0 && Cout >= 64 && (int64_t)H * W >= 1024 && (int64_t)N * D * H * W >= (int64_t)128 * 4 * sm_count();
+  // (a 16-channel tail -- Cin = 48 -- costs nothing special here: measured 48->96 at 128^2 432 TF/s against 201 on the plain kernel)
+  if (Cin == 16 && Cout >= 48 && (int64_t)N * D * H * W >= (int64_t)128 * 16 * sm_count()) return true;   // depth-folded first temporal conv: 0.31 -> 0.25 ms
+  return Cin >= 32 && Cout >= 64 && (int64_t)H * W >= 1024 && (int64_t)N * D * H * W >= (int64_t)128 * 4 * sm_count();
 }
 
 int launch_conv_umma_patch(const float* x, const float* wp, const float* bias, const float* scale, const float* res, float* y, int N, int D, int H, int W,
