@@ -1,4 +1,4 @@
-timeout 200 python tests/time_patch_cin48.py 2>&1 | head -4
+TAILN=10 ./run_gpu_tests.sh allv
 b() { name=$1; shift; echo "=== bench $name"; DGMR_BENCH_DUMP=gpurun_out/shapes_$name.tsv timeout 600 python bench.py "$@" > gpurun_out/bench_$name.json 2> gpurun_out/bench_$name.err; echo "exit $?"; python -c "
 import json; d=json.load(open('gpurun_out/bench_$name.json')); print(d['value'], d['ms_per_step'], d['e2e']['value'], d['gpu_launches']); print(d['kernel_breakdown_ms'])"; tail -n 3 gpurun_out/bench_$name.err; }
-b c3l --steps 5 --warmup 3 --no-ref-gpu --no-cpu-baseline
+b c3m --steps 5 --warmup 3 --no-ref-gpu --no-cpu-baseline

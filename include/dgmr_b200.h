@@ -52,7 +52,8 @@ enum { DGMR_FLAG_ROUND_OUT = 1024 };
 enum { DGMR_FLAG_RES_UP2 = 2048 };
 /* conv algorithm selector */
 enum { DGMR_ALGO_AUTO = 0, DGMR_ALGO_SIMT = 1, DGMR_ALGO_UMMA = 2 /* plain tcgen05 kernel */, DGMR_ALGO_UMMA_PATCH = 3 /* halo-patch tcgen05 kernel */,
-       DGMR_ALGO_UMMA_KWSTACK = 4 /* narrow outputs: column taps stacked along N (conv_kwstack.cu) */ };
+       DGMR_ALGO_UMMA_KWSTACK = 4 /* narrow outputs: column taps stacked along N (conv_kwstack.cu) */,
+       DGMR_ALGO_UMMA_PAIR = 5 /* persistent whole-row tiles, CTA pairs sharing each weight tile (conv_kwstack.cu, STACK = false) */ };
 /* tensor-core operand precision: 1xTF32 (what cuDNN does by default for the reference) or
  * 3xTF32 error-compensated (hi*hi + hi*lo + lo*hi), ~fp32 accuracy */
 enum { DGMR_PREC_TF32 = 0, DGMR_PREC_3XTF32 = 1 };

@@ -21,7 +21,7 @@ HEADER = os.path.join(os.path.dirname(_HERE), "include", "dgmr_b200.h")
 LIB_PATH = os.path.join(_HERE, "libdgmr_b200.so")
 
 ACT_NONE, ACT_RELU = 0, 1
-ALGO_AUTO, ALGO_SIMT, ALGO_UMMA, ALGO_UMMA_PATCH, ALGO_UMMA_KWSTACK = 0, 1, 2, 3, 4
+ALGO_AUTO, ALGO_SIMT, ALGO_UMMA, ALGO_UMMA_PATCH, ALGO_UMMA_KWSTACK, ALGO_UMMA_PAIR = 0, 1, 2, 3, 4, 5
 PREC_TF32, PREC_3XTF32 = 0, 1
 FLAG_ROUND_TF32 = 256
 FLAG_ACCUMULATE = 512

@@ -21,7 +21,8 @@ namespace dgmr {
 struct KwStackParams {
   int N, D, H, W, Cin, Cout, kd, kh, G;
   int bh;                // image rows per tile: 128 / W
-  int BN;                // 3 * Cout
+  int BN;                // STACK: 3 * Cout; else the Cout tile (<= 256)
+  int n_tiles;           // Cout tiles (STACK: 1)
   int stages, cg, tmem_cols, act, round_out, res_up2;
   const float* bias; const float* scale; const float* res; float* y;
 };
@@ -32,7 +33,11 @@ constexpr int kKwThreads = 192;  // warp0 TMA, warp1 MMA, warps 2..5 epilogue
 // shared-memory geometry, one A descriptor), each stages HALF of every stacked weight tile (cp.async.bulk.tensor...cta_group::2 signalling the
 // leader's mbarrier) -- the weight slab is ~half of this kernel's L2->SM traffic, which is what bounds it -- and the leader's MMA warp issues for
 // both; commits are multicast to both CTAs, the peer's epilogue warps release the accumulators on the leader's barrier.
-template <int BK, bool PAIR>
+// STACK = false: the same persistent (pair) structure with ORDINARY taps -- one K block per (kd, kh, kw, channel chunk), the activation tile shifted in w
+// by TMA, Cout in tiles of BN <= 256, plain epilogue.  That is the plain persistent kernel of conv_umma.cu plus CTA pairs: the wide 16x16 sampler
+// layers (768 -> 768, 384 -> 384: few pixels, large weights) are bound by the weight stream per 128-pixel tile there (~45 B/clk/SM at 557 TF/s);
+// a pair halves it.
+template <int BK, bool PAIR, bool STACK>
 __global__ void __launch_bounds__(kKwThreads, 1)
 conv_umma_kwstack_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const KwStackParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -59,13 +64,15 @@ conv_umma_kwstack_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   const int64_t total_tiles = (int64_t)p.N * p.D * tiles_h;
   // work items: single tiles, or (pair) two consecutive tiles 2i + rank; with an odd total the peer's last tile lies past the end
   // (n0 = N: TMA zero fill, stores skipped)
-  const int64_t total_items = PAIR ? (total_tiles + 1) / 2 : total_tiles;
-  auto tile_of = [&](int64_t item) { return PAIR ? 2 * item + (int64_t)rank : item; };
+  const int64_t m_items = PAIR ? (total_tiles + 1) / 2 : total_tiles;
+  const int64_t total_items = m_items * p.n_tiles;                 // item = (Cout tile, tile or tile pair): the Cout tile is the slow index
+  auto tile_of = [&](int64_t item) { const int64_t mi = item % m_items; return PAIR ? 2 * mi + (int64_t)rank : mi; };
+  auto co_of = [&](int64_t item) { return (int)(item / m_items) * p.BN; };
   auto decode = [&](int64_t t, int& n0, int& d0, int& h0) {
     h0 = (int)(t % tiles_h) * p.bh; t /= tiles_h;
     d0 = (int)(t % p.D); n0 = (int)(t / p.D);
   };
-  const int rtaps = p.kd * p.kh;                 // filter rows: (kd, kh)
+  const int rtaps = p.kd * p.kh * (STACK ? 1 : 3);   // K-block taps: filter rows (kd, kh), or single taps (kd, kh, kw)
   const int kchunks = (p.Cin + BK - 1) / BK;
   const int num_kb = rtaps * kchunks;
 
@@ -87,10 +94,13 @@ conv_umma_kwstack_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     int s = 0, g = 0, sg = 0; uint32_t ph = 0;
     for (int64_t item = wid; item < total_items; item += nworkers) {
       int n0, d0, h0; decode(tile_of(item), n0, d0, h0);
+      const int co0 = co_of(item);
       int rt = 0, chunk = 0;
       for (int kb = 0; kb < num_kb; ++kb) {
         const int c0 = chunk * BK;
-        const int tkh = rt % p.kh, tkd = rt / p.kh;
+        const int frow = STACK ? rt : rt / 3;                       // filter row (kd, kh)
+        const int tkh = frow % p.kh, tkd = frow / p.kh;
+        const int wsh = STACK ? 0 : rt % 3 - 1;                     // column shift of this K block's activation tile
         if (sg == 0) mbar_wait(empty_bar(g), ph ^ 1u);
         const uint32_t sa = base + s * stage_bytes;
         if (PAIR) {
@@ -99,13 +109,13 @@ conv_umma_kwstack_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           const uint32_t lead = mapa_rank(full_bar(s), 0);
           if (elect_one()) {
             if (rank == 0) mbar_expect_tx(full_bar(s), 2u * (a_bytes + b_bytes));
-            tma_load_5d_2sm(sa, &tmA, lead, c0, 0, h0 + tkh - p.kh / 2, d0 + tkd - p.kd / 2, n0);
-            tma_load_3d_2sm(sa + a_bytes, &tmB, lead, c0, (int)rank * (p.BN / 2), rt);
+            tma_load_5d_2sm(sa, &tmA, lead, c0, wsh, h0 + tkh - p.kh / 2, d0 + tkd - p.kd / 2, n0);
+            tma_load_3d_2sm(sa + a_bytes, &tmB, lead, c0, co0 + (int)rank * (p.BN / 2), rt);
           }
         } else if (elect_one()) {
           mbar_expect_tx(full_bar(s), a_bytes + b_bytes);
-          tma_load_5d(sa, &tmA, full_bar(s), c0, 0, h0 + tkh - p.kh / 2, d0 + tkd - p.kd / 2, n0);
-          tma_load_3d(sa + a_bytes, &tmB, full_bar(s), c0, 0, rt);
+          tma_load_5d(sa, &tmA, full_bar(s), c0, wsh, h0 + tkh - p.kh / 2, d0 + tkd - p.kd / 2, n0);
+          tma_load_3d(sa + a_bytes, &tmB, full_bar(s), c0, co0, rt);
         }
         __syncwarp();
         if (++chunk == kchunks) { chunk = 0; ++rt; }
@@ -180,26 +190,31 @@ conv_umma_kwstack_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       const int64_t t = tile_of(item);
       const bool live = t < total_tiles;             // pair with an odd tile count: the peer's last tile does not exist
       int n0, d0, h0; decode(live ? t : 0, n0, d0, h0);
+      const int co0 = co_of(item);
+      const int cend = STACK ? p.Cout : (p.Cout - co0 < p.BN ? p.Cout - co0 : p.BN);     // output channels of this item
       const int bsel = it & 1; const uint32_t phacc = (it >> 1) & 1u;
       uint32_t mrow[4], rrow[4]; const float* srow[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int rj = q * 32 + lr + 8 * j;
         const int wj = rj % p.W, hj = h0 + rj / p.W;
-        mrow[j] = (uint32_t)(((n0 * p.D + d0) * p.H + hj) * p.W + wj) * (uint32_t)p.Cout + 4u * lc;
-        rrow[j] = p.res_up2 ? (uint32_t)(((n0 * p.D + d0) * (p.H >> 1) + (hj >> 1)) * (p.W >> 1) + (wj >> 1)) * (uint32_t)p.Cout + 4u * lc : mrow[j];
-        srow[j] = p.scale ? p.scale + (int64_t)(n0 / (p.N / p.G)) * p.Cout : nullptr;
+        mrow[j] = (uint32_t)(((n0 * p.D + d0) * p.H + hj) * p.W + wj) * (uint32_t)p.Cout + (uint32_t)co0 + 4u * lc;
+        rrow[j] = p.res_up2 ? (uint32_t)(((n0 * p.D + d0) * (p.H >> 1) + (hj >> 1)) * (p.W >> 1) + (wj >> 1)) * (uint32_t)p.Cout + (uint32_t)co0 + 4u * lc : mrow[j];
+        srow[j] = p.scale ? p.scale + (int64_t)(n0 / (p.N / p.G)) * p.Cout + co0 : nullptr;
       }
       mbar_wait(tmem_full(bsel), phacc);
       tc_fence_after();
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(bsel * p.BN);
-      for (int c = 0; c < p.Cout; c += 16, par ^= 1u) {
+      for (int c = 0; c < cend; c += 16, par ^= 1u) {
         float4 rr[4];
         if (p.res) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) rr[j] = __ldg(reinterpret_cast<const float4*>(p.res + rrow[j] + c));
         }
         float t0[16], v[16], t2[16];
+        if (!STACK) {
+          tmem_ld16(trow + (uint32_t)c, v);
+        } else {
         tmem_ld16(trow + (uint32_t)c, t0);
         tmem_ld16(trow + (uint32_t)(p.Cout + c), v);
         tmem_ld16(trow + (uint32_t)(2 * p.Cout + c), t2);
@@ -239,14 +254,15 @@ conv_umma_kwstack_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         }
 #pragma unroll
         for (int k = 0; k < 16; ++k) v[k] += (has_prev ? t0[k] : 0.f) + (has_next ? t2[k] : 0.f);
+        }
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(st_row + (((uint32_t)k ^ st_sw) << 4)), "f"(v[4 * k]), "f"(v[4 * k + 1]),
                        "f"(v[4 * k + 2]), "f"(v[4 * k + 3]) : "memory");
         __syncwarp();
-        const int co = c + 4 * lc;
+        const int co = c + 4 * lc;             // relative to co0 (srow / mrow carry co0; the bias does not)
         float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (p.bias) b4 = make_float4(__ldg(p.bias + co), __ldg(p.bias + co + 1), __ldg(p.bias + co + 2), __ldg(p.bias + co + 3));
+        if (p.bias) b4 = make_float4(__ldg(p.bias + co0 + co), __ldg(p.bias + co0 + co + 1), __ldg(p.bias + co0 + co + 2), __ldg(p.bias + co0 + co + 3));
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int row = lr + 8 * j;
@@ -288,29 +304,42 @@ bool umma_kwstack_ok(int N, int D, int H, int W, int Cin, int Cout, int kd, int 
   if ((int64_t)N * D * H * W * Cout >= ((int64_t)1 << 32) || (int64_t)N * D * H * W >= ((int64_t)1 << 31)) return false;   // 32-bit epilogue offsets
   return true;
 }
+// the same kernel with ordinary taps (STACK = false): whole-row tiles of 16..128-pixel-wide images, any Cout that is a multiple of 16
+bool umma_pairconv_ok(int N, int D, int H, int W, int Cin, int Cout, int kd, int kh, int kw, int G) {
+  if (kw != 3 || kh != 3 || !(kd == 1 || kd == 3)) return false;
+  if (!(W == 16 || W == 32 || W == 64 || W == 128) || H % (128 / W) != 0) return false;
+  if (Cout % 16 != 0 || Cout < 16) return false;
+  if (Cin % 8 != 0 || Cin < 32) return false;
+  if (G < 1 || N % G) return false;
+  if ((int64_t)N * D * H * W * Cout >= ((int64_t)1 << 32) || (int64_t)N * D * H * W >= ((int64_t)1 << 31)) return false;
+  return true;
+}
 
-int launch_conv_umma_kwstack(const float* x, const float* wp, const float* bias, const float* scale, const float* res, float* y, int N, int D, int H, int W,
-                             int Cin, int Cout, int kd, int G, int act, cudaStream_t st) {
+static int launch_kw_impl(bool stack, const float* x, const float* wp, const float* bias, const float* scale, const float* res, float* y, int N, int D, int H,
+                          int W, int Cin, int Cout, int kd, int G, int act, cudaStream_t st) {
   KwStackParams p;
   p.round_out = (act & DGMR_FLAG_ROUND_OUT) ? 1 : 0; p.res_up2 = (act & DGMR_FLAG_RES_UP2) ? 1 : 0;
   act &= 3;
   p.N = N; p.D = D; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.kd = kd; p.kh = 3; p.G = G;
-  p.bh = 128 / W; p.BN = 3 * Cout;
+  p.bh = 128 / W;
+  if (stack) { p.n_tiles = 1; p.BN = 3 * Cout; }
+  else { p.n_tiles = (int)ceil_div(Cout, 256); p.BN = (int)(ceil_div(ceil_div(Cout, p.n_tiles), 16) * 16); p.n_tiles = (int)ceil_div(Cout, p.BN); }
   p.act = act; p.bias = bias; p.scale = scale; p.res = res; p.y = y;
   const int BK = kw_bk(Cin);
   if (BK == 0) { set_error("conv_umma_kwstack: Cin=%d not served", Cin); return 1; }
   p.tmem_cols = 32; while (p.tmem_cols < 2 * p.BN) p.tmem_cols <<= 1;
   const int64_t total_tiles = (int64_t)N * D * (H / p.bh);
-  // CTA pairs (cta_group::2, half of every weight tile per CTA) whenever there are a few waves of tiles; the pair splits the N = 3*Cout rows
-  // in two halves of whole 8-row groups
-  const bool pair = g_kwstack_pair != 0 && sm_count() % 2 == 0 && (p.BN / 2) % 8 == 0 && (total_tiles >= 2 * (int64_t)sm_count() || (g_kwstack_pair == 1 && total_tiles >= 2));
+  // CTA pairs (cta_group::2, half of every weight tile per CTA) whenever there are a few waves of tiles; the pair splits the N rows of the weight
+  // tile in two halves of whole 8-row groups
+  const bool pair = g_kwstack_pair != 0 && sm_count() % 2 == 0 && (p.BN / 2) % 8 == 0 &&
+                    (total_tiles * p.n_tiles >= 2 * (int64_t)sm_count() || (g_kwstack_pair == 1 && total_tiles >= 2));
   const uint32_t a_bytes = 128u * BK * 4u, b_bytes = ((uint32_t)(pair ? p.BN / 2 : p.BN) * BK * 4u + 1023u) & ~1023u;
   const uint32_t stage_bytes = a_bytes + b_bytes;
   int stages = (int)((196u * 1024u) / stage_bytes);
   if (stages > 9) stages = 9;
   if (stages < 2) { set_error("conv_umma_kwstack: stage too large"); return 1; }
   p.cg = 1;
-  if (stages >= 6) { stages = stages / 3 * 3; p.cg = 3; } else if (stages >= 4) { stages = stages / 2 * 2; p.cg = 2; }
+  if (stages >= 6 && p.BN <= 160) { stages = stages / 3 * 3; p.cg = 3; } else if (stages >= 4) { stages = stages / 2 * 2; p.cg = 2; }
   p.stages = stages;
   const size_t smem = (size_t)stages * stage_bytes + 1024 + 8 * (2 * stages + 6) + 128 + 4 * 2048 + 1024;
   CUtensorMap tmA, tmB;
@@ -321,30 +350,36 @@ int launch_conv_umma_kwstack(const float* x, const float* wp, const float* bias,
     int e = make_tmap(&tmA, x, 5, dims, str, box, BK * 4);
     if (e) return e;
   }
-  {
+  if (stack) {
     // packed weights [tap = (kd, kh, kw)][Cout][Cin] seen as [(kd, kh)][kw*Cout + co][Cin]
     uint64_t dims[3] = {(uint64_t)Cin, (uint64_t)(3 * Cout), (uint64_t)(kd * 3)};
     uint64_t str[2] = {(uint64_t)Cin * 4, (uint64_t)3 * Cout * Cin * 4};
     uint32_t box[3] = {(uint32_t)BK, (uint32_t)(pair ? p.BN / 2 : p.BN), 1u};
     int e = make_tmap(&tmB, wp, 3, dims, str, box, BK * 4);
     if (e) return e;
+  } else {
+    uint64_t dims[3] = {(uint64_t)Cin, (uint64_t)Cout, (uint64_t)(kd * 9)};
+    uint64_t str[2] = {(uint64_t)Cin * 4, (uint64_t)Cout * Cin * 4};
+    uint32_t box[3] = {(uint32_t)BK, (uint32_t)(pair ? p.BN / 2 : p.BN), 1u};
+    int e = make_tmap(&tmB, wp, 3, dims, str, box, BK * 4);
+    if (e) return e;
   }
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(conv_umma_kwstack_kernel<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(224 * 1024)) != cudaSuccess ||
-        cudaFuncSetAttribute(conv_umma_kwstack_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(224 * 1024)) != cudaSuccess ||
-        cudaFuncSetAttribute(conv_umma_kwstack_kernel<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(224 * 1024)) != cudaSuccess ||
-        cudaFuncSetAttribute(conv_umma_kwstack_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(224 * 1024)) != cudaSuccess) {
-      set_error("conv_umma_kwstack: cannot raise dynamic smem limit"); return 2;
-    }
+    bool ok = true;
+#define DGMR_SET(...) ok = ok && cudaFuncSetAttribute(conv_umma_kwstack_kernel<__VA_ARGS__>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(224 * 1024)) == cudaSuccess
+    DGMR_SET(32, false, true); DGMR_SET(16, false, true); DGMR_SET(32, true, true); DGMR_SET(16, true, true);
+    DGMR_SET(32, false, false); DGMR_SET(32, true, false);
+#undef DGMR_SET
+    if (!ok) { set_error("conv_umma_kwstack: cannot raise dynamic smem limit"); return 2; }
     attr_set = true;
   }
-  // one CTA per SM (2 x 3*Cout TMEM columns each): pad the shared-memory request so that a second CTA can never become resident and block in tcgen05.alloc
+  // one CTA per SM (2 x BN TMEM columns each): pad the shared-memory request so that a second CTA can never become resident and block in tcgen05.alloc
   size_t req = smem;
   if (req < (size_t)232448 / 2 + 1024) req = (size_t)232448 / 2 + 1024;
   if (pair) {
     int64_t g = sm_count();                                   // even (checked above): one CTA pair per TPC
-    const int64_t items = (total_tiles + 1) / 2;
+    const int64_t items = (total_tiles + 1) / 2 * p.n_tiles;
     if (g > 2 * items) g = 2 * items;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)g); cfg.blockDim = dim3(kKwThreads); cfg.dynamicSmemBytes = req; cfg.stream = st;
@@ -352,17 +387,28 @@ int launch_conv_umma_kwstack(const float* x, const float* wp, const float* bias,
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    cudaError_t e = (BK == 32) ? cudaLaunchKernelEx(&cfg, conv_umma_kwstack_kernel<32, true>, tmA, tmB, p)
-                               : cudaLaunchKernelEx(&cfg, conv_umma_kwstack_kernel<16, true>, tmA, tmB, p);
+    cudaError_t e = !stack ? cudaLaunchKernelEx(&cfg, conv_umma_kwstack_kernel<32, true, false>, tmA, tmB, p)
+                   : (BK == 32) ? cudaLaunchKernelEx(&cfg, conv_umma_kwstack_kernel<32, true, true>, tmA, tmB, p)
+                                : cudaLaunchKernelEx(&cfg, conv_umma_kwstack_kernel<16, true, true>, tmA, tmB, p);
     if (e != cudaSuccess) { set_error("conv_umma_kwstack: cluster launch failed: %s", cudaGetErrorString(e)); return 2; }
     return 0;
   }
   int64_t g = sm_count();
-  if (g > total_tiles) g = total_tiles;
-  if (BK == 32) conv_umma_kwstack_kernel<32, false><<<(unsigned)g, kKwThreads, req, st>>>(tmA, tmB, p);
-  else conv_umma_kwstack_kernel<16, false><<<(unsigned)g, kKwThreads, req, st>>>(tmA, tmB, p);
+  if (g > total_tiles * p.n_tiles) g = total_tiles * p.n_tiles;
+  if (!stack) conv_umma_kwstack_kernel<32, false, false><<<(unsigned)g, kKwThreads, req, st>>>(tmA, tmB, p);
+  else if (BK == 32) conv_umma_kwstack_kernel<32, false, true><<<(unsigned)g, kKwThreads, req, st>>>(tmA, tmB, p);
+  else conv_umma_kwstack_kernel<16, false, true><<<(unsigned)g, kKwThreads, req, st>>>(tmA, tmB, p);
   DGMR_CHECK_LAUNCH("conv_umma_kwstack");
   return 0;
+}
+
+int launch_conv_umma_kwstack(const float* x, const float* wp, const float* bias, const float* scale, const float* res, float* y, int N, int D, int H, int W,
+                             int Cin, int Cout, int kd, int G, int act, cudaStream_t st) {
+  return launch_kw_impl(true, x, wp, bias, scale, res, y, N, D, H, W, Cin, Cout, kd, G, act, st);
+}
+int launch_conv_umma_pairconv(const float* x, const float* wp, const float* bias, const float* scale, const float* res, float* y, int N, int D, int H, int W,
+                              int Cin, int Cout, int kd, int G, int act, cudaStream_t st) {
+  return launch_kw_impl(false, x, wp, bias, scale, res, y, N, D, H, W, Cin, Cout, kd, G, act, st);
 }
 
 }  // namespace dgmr

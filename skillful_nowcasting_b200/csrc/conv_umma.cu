@@ -23,6 +23,9 @@ int launch_conv_simt_fwd(const float*, const float*, const float*, const float*,
 int launch_conv_simt_wgrad(const float*, const float*, float*, int, int, int, int, int, int, int, int, int, cudaStream_t);
 bool umma_kwstack_ok(int N, int D, int H, int W, int Cin, int Cout, int kd, int kh, int kw, int G);   // conv_kwstack.cu
 extern int g_kwstack_pair;
+bool umma_pairconv_ok(int N, int D, int H, int W, int Cin, int Cout, int kd, int kh, int kw, int G);   // conv_kwstack.cu, STACK = false
+int launch_conv_umma_pairconv(const float* x, const float* wp, const float* bias, const float* scale, const float* res, float* y, int N, int D, int H, int W,
+                              int Cin, int Cout, int kd, int G, int act, cudaStream_t st);
 int launch_conv_umma_kwstack(const float* x, const float* wp, const float* bias, const float* scale, const float* res, float* y, int N, int D, int H, int W,
                              int Cin, int Cout, int kd, int G, int act, cudaStream_t st);
 
@@ -1272,6 +1275,7 @@ struct UmmaOptions {
   int patch_tg = -1;         // 1: release halo-patch weight tiles per tap instead of per filter row
   int prefer_patch = -1;     // 1: AUTO dispatch takes the halo-patch kernel whenever it supports the shape (parity tests on small shapes)
   int subpix_wgrad_row = -1; // sub-pixel weight gradient: 0 = always the tap-wise kernel, 1 = the row kernel whenever W % 32 == 0 (tests)
+  int pairconv = -1;         // 0: never the pair-persistent whole-row kernel (conv_kwstack.cu, STACK = false), 1: whenever it supports the shape
   int kwstack = -1;          // 0: never the column-stacked kernel (conv_kwstack.cu), 1: whenever it supports the shape (small test shapes)
   int patch_dbg = 0;         // DGMR_TUNING builds only: make the halo-patch kernel skip work
 };
@@ -1648,7 +1652,7 @@ static bool umma_patch_profitable(int N, int D, int H, int W, int Cin, int Cout)
   if (g_opt.prefer_patch == 1) return true;
   // (a 16-channel tail -- Cin = 48 -- costs nothing special here: measured 48->96 at 128^2 432 TF/s against 201 on the plain kernel)
   if (Cin == 16 && Cout >= 48 && (int64_t)N * D * H * W >= (int64_t)128 * 16 * sm_count()) return true;   // depth-folded first temporal conv: 0.31 -> 0.25 ms
-  return Cin >= 32 && Cout >= 64 && (int64_t)H * W >= 1024 && (int64_t)N * D * H * W >= (int64_t)128 * 4 * sm_count();
+  return Cin >= 32 && Cout >= 64 && (int64_t)H * W >= 1024 && (int64_t)N * D * H * W >= (int64_t)128 * 2 * sm_count();   // (16 x 64^2 48->96: 34 -> 26 us)
 }
 
 int launch_conv_umma_patch(const float* x, const float* wp, const float* bias, const float* scale, const float* res, float* y, int N, int D, int H, int W,
@@ -1927,7 +1931,7 @@ int dgmr_set_option(const char* name, int value) {
   struct { const char* n; int* v; } tab[] = {{"umma_cg", &g_opt.umma_cg}, {"umma_persist", &g_opt.umma_persist}, {"umma_persist_r", &g_opt.umma_persist_r},
                                              {"patch_pair", &g_opt.patch_pair}, {"patch_mt", &g_opt.patch_mt}, {"patch_tg", &g_opt.patch_tg},
                                              {"prefer_patch", &g_opt.prefer_patch}, {"patch_dbg", &g_opt.patch_dbg},
-                                             {"subpix_wgrad_row", &g_opt.subpix_wgrad_row}, {"kwstack", &g_opt.kwstack}, {"kwstack_pair", &g_kwstack_pair}};
+                                             {"subpix_wgrad_row", &g_opt.subpix_wgrad_row}, {"kwstack", &g_opt.kwstack}, {"kwstack_pair", &g_kwstack_pair}, {"pairconv", &g_opt.pairconv}};
   for (auto& t : tab)
     if (strcmp(t.n, name) == 0) { *t.v = value; return 0; }
   set_error("dgmr_set_option: unknown option '%s'", name);
@@ -1977,6 +1981,16 @@ int dgmr_conv_fwd(const float* x, const float* x_lo, const float* wp, const floa
   if (algo == DGMR_ALGO_UMMA_KWSTACK || (algo == DGMR_ALGO_AUTO && g_opt.kwstack != 0 && Cout < 64 && Cin >= 32 && umma_kwstack_ok(N, D, H, W, Cin, Cout, kd, kh, kw, G) &&
                                          ((int64_t)N * D * H * W >= (int64_t)128 * 2 * sm_count() || g_opt.kwstack == 1)))
     return launch_conv_umma_kwstack(x, wp, bias, scale, res, y, N, D, H, W, Cin, Cout, kd, G, act, S(stream));
+  if (algo == DGMR_ALGO_UMMA_PAIR) {
+    DGMR_REQUIRE(umma_pairconv_ok(N, D, H, W, Cin, Cout, kd, kh, kw, G), "dgmr_conv_fwd: shape not supported by the pair-persistent kernel");
+    return launch_conv_umma_pairconv(x, wp, bias, scale, res, y, N, D, H, W, Cin, Cout, kd, G, act, S(stream));
+  }
+  // wide channels on small images (the 16x16 / 32x32 sampler layers, the per-step ConvGRU convolutions): whole-row tiles, CTA pairs sharing each
+  // weight tile.  Measured (tests/time_patch16.py, time_pairconv.py): 768->768 @16^2 559 -> 834 TF/s, 192->192 @32^2 632 (patch) -> 679, ConvGRU
+  // 16 x 16^2 192->384 39 -> 31 us; the halo-patch kernel keeps N = 96 layers and everything at 64^2 and above (activation traffic dominates there).
+  if (algo == DGMR_ALGO_AUTO && g_opt.pairconv != 0 && W <= 32 && Cout >= 64 && umma_pairconv_ok(N, D, H, W, Cin, Cout, kd, kh, kw, G) &&
+      (Cin >= 192 || (int64_t)N * D * H * W <= 131072 || g_opt.pairconv == 1))
+    return launch_conv_umma_pairconv(x, wp, bias, scale, res, y, N, D, H, W, Cin, Cout, kd, G, act, S(stream));
   if (algo == DGMR_ALGO_UMMA || algo == DGMR_ALGO_UMMA_PATCH || (algo == DGMR_ALGO_AUTO && ok)) {
     if (algo != DGMR_ALGO_UMMA && umma_patch_ok(N, D, H, W, Cin, Cout, kd, kh, kw, G) &&
         (algo == DGMR_ALGO_UMMA_PATCH || umma_patch_profitable(N, D, H, W, Cin, Cout))) {

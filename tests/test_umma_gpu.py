@@ -226,6 +226,44 @@ def test_conv_umma_kwstack(cuda_backend, shape, variant, pair):
         assert torch.equal(y, y2)
 
 
+# N, D, H, W, Cin, Cout, kd, G
+PAIRCONV_SHAPES = [
+    (6, 1, 16, 16, 192, 384, 1, 3),    # W = 16: eight image rows per tile; two Cout tiles of 192
+    (4, 1, 16, 16, 768, 768, 1, 2),    # the weight-heavy sampler layer (small batch): three Cout tiles of 256
+    (3, 1, 32, 32, 96, 80, 1, 1),      # odd tile count (the pair's last tile past the end), Cout = 80
+    (2, 3, 16, 16, 64, 32, 3, 1),      # 3-D
+    (2, 1, 64, 64, 48, 96, 1, 2),      # channel tail (32 + 16), W = 64
+]
+
+
+@pytest.mark.parametrize("shape", PAIRCONV_SHAPES)
+@pytest.mark.parametrize("variant", ["plain", "fused", "fusedup2"])
+@pytest.mark.parametrize("pair", [0, 1])
+def test_conv_umma_pairconv(cuda_backend, shape, variant, pair):
+    """Persistent whole-row-tile kernel with ordinary taps (conv_kwstack.cu, STACK = false), single CTAs and CTA pairs sharing each weight tile."""
+    n, d, h, w, cin, cout, kd, g = shape
+    cuda_backend.set_option("kwstack_pair", pair)
+    torch.manual_seed(25)
+    taps = kd * 9
+    x = torch.randn(n, d, h, w, cin)
+    wp = torch.randn(taps * cout * cin) / (taps * cin) ** 0.5
+    fused = variant.startswith("fused")
+    up2 = variant == "fusedup2"
+    bias = torch.randn(cout) if fused else None
+    scale = (torch.rand(g, cout) + 0.5) if fused else None
+    res = (torch.randn(n, d, h // 2, w // 2, cout) if up2 else torch.randn(n, d, h, w, cout)) if fused else None
+    act = (1 if fused else 0) | ((1024 | 2048) if up2 else 0)
+    y_ref = torch.empty(n, d, h, w, cout)
+    EmuBackend().conv_fwd(x, wp, bias, scale, res, y_ref, n, d, h, w, cin, cout, kd, 3, 3, g, act)
+    dev = lambda t: None if t is None else t.cuda()
+    y = torch.full((n, d, h, w, cout), float("nan"), device="cuda")
+    cuda_backend.conv_fwd(dev(x), dev(wp), dev(bias), dev(scale), dev(res), y, n, d, h, w, cin, cout, kd, 3, 3, g, act, algo=5)
+    torch.cuda.synchronize()
+    assert not torch.isnan(y).any(), "pair-persistent kernel left outputs unwritten"
+    e = (y.cpu() - y_ref).abs().max().item()
+    assert e <= 4e-3 * max(y_ref.abs().max().item(), 1), f"pair-persistent kernel err {e:.3e}"
+
+
 # N, D, H, W, Cin, Cout, kd, kh
 WGRAD_ROW_SHAPES = [
     (4, 1, 32, 32, 32, 64, 1, 3),
