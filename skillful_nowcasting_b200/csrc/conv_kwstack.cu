@@ -23,6 +23,8 @@ struct KwStackParams {
   int bh;                // image rows per tile: 128 / W
   int BN;                // STACK: 3 * Cout; else the Cout tile (<= 256)
   int n_tiles;           // Cout tiles (STACK: 1)
+  int subpix;            // STACK = false only: sub-pixel up-convolution (conv_subpix.cu) -- items carry an output phase (i, j); its four taps (a, b) read the
+                         // low-resolution tile shifted by (a+i-1, b+j-1) with the pre-summed weight tile [i][j][a][b]; outputs go to pixel (2h+i, 2w+j)
   int stages, cg, tmem_cols, act, round_out, res_up2;
   const float* bias; const float* scale; const float* res; float* y;
 };
@@ -65,14 +67,16 @@ conv_umma_kwstack_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   // work items: single tiles, or (pair) two consecutive tiles 2i + rank; with an odd total the peer's last tile lies past the end
   // (n0 = N: TMA zero fill, stores skipped)
   const int64_t m_items = PAIR ? (total_tiles + 1) / 2 : total_tiles;
-  const int64_t total_items = m_items * p.n_tiles;                 // item = (Cout tile, tile or tile pair): the Cout tile is the slow index
+  const int nphase = (!STACK && p.subpix) ? 4 : 1;
+  const int64_t total_items = m_items * p.n_tiles * nphase;        // item = (phase, Cout tile, tile or tile pair): tiles are the fast index
   auto tile_of = [&](int64_t item) { const int64_t mi = item % m_items; return PAIR ? 2 * mi + (int64_t)rank : mi; };
-  auto co_of = [&](int64_t item) { return (int)(item / m_items) * p.BN; };
+  auto co_of = [&](int64_t item) { return (int)((item / m_items) % p.n_tiles) * p.BN; };
+  auto phase_of = [&](int64_t item) { return (int)(item / (m_items * p.n_tiles)); };
   auto decode = [&](int64_t t, int& n0, int& d0, int& h0) {
     h0 = (int)(t % tiles_h) * p.bh; t /= tiles_h;
     d0 = (int)(t % p.D); n0 = (int)(t / p.D);
   };
-  const int rtaps = p.kd * p.kh * (STACK ? 1 : 3);   // K-block taps: filter rows (kd, kh), or single taps (kd, kh, kw)
+  const int rtaps = (!STACK && p.subpix) ? 4 : p.kd * p.kh * (STACK ? 1 : 3);   // K-block taps: filter rows (kd, kh), single taps (kd, kh, kw), or (a, b)
   const int kchunks = (p.Cin + BK - 1) / BK;
   const int num_kb = rtaps * kchunks;
 
@@ -95,12 +99,19 @@ conv_umma_kwstack_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     for (int64_t item = wid; item < total_items; item += nworkers) {
       int n0, d0, h0; decode(tile_of(item), n0, d0, h0);
       const int co0 = co_of(item);
+      const int phs = phase_of(item), pi = phs >> 1, pj = phs & 1;
       int rt = 0, chunk = 0;
       for (int kb = 0; kb < num_kb; ++kb) {
         const int c0 = chunk * BK;
-        const int frow = STACK ? rt : rt / 3;                       // filter row (kd, kh)
-        const int tkh = frow % p.kh, tkd = frow / p.kh;
-        const int wsh = STACK ? 0 : rt % 3 - 1;                     // column shift of this K block's activation tile
+        int wsh, hsh, dsh, bz;           // shifts of this K block's activation tile, weight tile index
+        if (!STACK && p.subpix) {
+          const int a = rt >> 1, b = rt & 1;
+          hsh = a + pi - 1; wsh = b + pj - 1; dsh = 0; bz = phs * 4 + rt;
+        } else {
+          const int frow = STACK ? rt : rt / 3;                     // filter row (kd, kh)
+          hsh = frow % p.kh - p.kh / 2; dsh = frow / p.kh - p.kd / 2;
+          wsh = STACK ? 0 : rt % 3 - 1; bz = rt;
+        }
         if (sg == 0) mbar_wait(empty_bar(g), ph ^ 1u);
         const uint32_t sa = base + s * stage_bytes;
         if (PAIR) {
@@ -109,13 +120,13 @@ conv_umma_kwstack_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           const uint32_t lead = mapa_rank(full_bar(s), 0);
           if (elect_one()) {
             if (rank == 0) mbar_expect_tx(full_bar(s), 2u * (a_bytes + b_bytes));
-            tma_load_5d_2sm(sa, &tmA, lead, c0, wsh, h0 + tkh - p.kh / 2, d0 + tkd - p.kd / 2, n0);
-            tma_load_3d_2sm(sa + a_bytes, &tmB, lead, c0, co0 + (int)rank * (p.BN / 2), rt);
+            tma_load_5d_2sm(sa, &tmA, lead, c0, wsh, h0 + hsh, d0 + dsh, n0);
+            tma_load_3d_2sm(sa + a_bytes, &tmB, lead, c0, co0 + (int)rank * (p.BN / 2), bz);
           }
         } else if (elect_one()) {
           mbar_expect_tx(full_bar(s), a_bytes + b_bytes);
-          tma_load_5d(sa, &tmA, full_bar(s), c0, wsh, h0 + tkh - p.kh / 2, d0 + tkd - p.kd / 2, n0);
-          tma_load_3d(sa + a_bytes, &tmB, full_bar(s), c0, co0, rt);
+          tma_load_5d(sa, &tmA, full_bar(s), c0, wsh, h0 + hsh, d0 + dsh, n0);
+          tma_load_3d(sa + a_bytes, &tmB, full_bar(s), c0, co0, bz);
         }
         __syncwarp();
         if (++chunk == kchunks) { chunk = 0; ++rt; }
@@ -198,8 +209,14 @@ conv_umma_kwstack_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       for (int j = 0; j < 4; ++j) {
         const int rj = q * 32 + lr + 8 * j;
         const int wj = rj % p.W, hj = h0 + rj / p.W;
+        if (!STACK && p.subpix) {   // low-resolution pixel (hj, wj), phase (i, j) -> pixel (2h+i, 2w+j) of the [N, 2H, 2W, Cout] output
+          const int phs = phase_of(item);
+          mrow[j] = (uint32_t)((n0 * 2 * p.H + 2 * hj + (phs >> 1)) * (2 * p.W) + 2 * wj + (phs & 1)) * (uint32_t)p.Cout + (uint32_t)co0 + 4u * lc;
+          rrow[j] = mrow[j];
+        } else {
         mrow[j] = (uint32_t)(((n0 * p.D + d0) * p.H + hj) * p.W + wj) * (uint32_t)p.Cout + (uint32_t)co0 + 4u * lc;
         rrow[j] = p.res_up2 ? (uint32_t)(((n0 * p.D + d0) * (p.H >> 1) + (hj >> 1)) * (p.W >> 1) + (wj >> 1)) * (uint32_t)p.Cout + (uint32_t)co0 + 4u * lc : mrow[j];
+        }
         srow[j] = p.scale ? p.scale + (int64_t)(n0 / (p.N / p.G)) * p.Cout + co0 : nullptr;
       }
       mbar_wait(tmem_full(bsel), phacc);
@@ -315,9 +332,11 @@ bool umma_pairconv_ok(int N, int D, int H, int W, int Cin, int Cout, int kd, int
   return true;
 }
 
-static int launch_kw_impl(bool stack, const float* x, const float* wp, const float* bias, const float* scale, const float* res, float* y, int N, int D, int H,
+static int launch_kw_impl(int mode /* 1: column-stacked, 0: ordinary taps, 2: sub-pixel up-convolution tiles */, const float* x, const float* wp, const float* bias, const float* scale, const float* res, float* y, int N, int D, int H,
                           int W, int Cin, int Cout, int kd, int G, int act, cudaStream_t st) {
+  const bool stack = mode == 1;
   KwStackParams p;
+  p.subpix = mode == 2 ? 1 : 0;
   p.round_out = (act & DGMR_FLAG_ROUND_OUT) ? 1 : 0; p.res_up2 = (act & DGMR_FLAG_RES_UP2) ? 1 : 0;
   act &= 3;
   p.N = N; p.D = D; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.kd = kd; p.kh = 3; p.G = G;
@@ -332,7 +351,7 @@ static int launch_kw_impl(bool stack, const float* x, const float* wp, const flo
   // CTA pairs (cta_group::2, half of every weight tile per CTA) whenever there are a few waves of tiles; the pair splits the N rows of the weight
   // tile in two halves of whole 8-row groups
   const bool pair = g_kwstack_pair != 0 && sm_count() % 2 == 0 && (p.BN / 2) % 8 == 0 &&
-                    (total_tiles * p.n_tiles >= 2 * (int64_t)sm_count() || (g_kwstack_pair == 1 && total_tiles >= 2));
+                    (total_tiles * p.n_tiles * (mode == 2 ? 4 : 1) >= 2 * (int64_t)sm_count() || (g_kwstack_pair == 1 && total_tiles >= 2));
   const uint32_t a_bytes = 128u * BK * 4u, b_bytes = ((uint32_t)(pair ? p.BN / 2 : p.BN) * BK * 4u + 1023u) & ~1023u;
   const uint32_t stage_bytes = a_bytes + b_bytes;
   int stages = (int)((196u * 1024u) / stage_bytes);
@@ -358,7 +377,7 @@ static int launch_kw_impl(bool stack, const float* x, const float* wp, const flo
     int e = make_tmap(&tmB, wp, 3, dims, str, box, BK * 4);
     if (e) return e;
   } else {
-    uint64_t dims[3] = {(uint64_t)Cin, (uint64_t)Cout, (uint64_t)(kd * 9)};
+    uint64_t dims[3] = {(uint64_t)Cin, (uint64_t)Cout, (uint64_t)(mode == 2 ? 16 : kd * 9)};
     uint64_t str[2] = {(uint64_t)Cin * 4, (uint64_t)Cout * Cin * 4};
     uint32_t box[3] = {(uint32_t)BK, (uint32_t)(pair ? p.BN / 2 : p.BN), 1u};
     int e = make_tmap(&tmB, wp, 3, dims, str, box, BK * 4);
@@ -379,7 +398,7 @@ static int launch_kw_impl(bool stack, const float* x, const float* wp, const flo
   if (req < (size_t)232448 / 2 + 1024) req = (size_t)232448 / 2 + 1024;
   if (pair) {
     int64_t g = sm_count();                                   // even (checked above): one CTA pair per TPC
-    const int64_t items = (total_tiles + 1) / 2 * p.n_tiles;
+    const int64_t items = (total_tiles + 1) / 2 * p.n_tiles * (mode == 2 ? 4 : 1);
     if (g > 2 * items) g = 2 * items;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)g); cfg.blockDim = dim3(kKwThreads); cfg.dynamicSmemBytes = req; cfg.stream = st;
@@ -394,7 +413,7 @@ static int launch_kw_impl(bool stack, const float* x, const float* wp, const flo
     return 0;
   }
   int64_t g = sm_count();
-  if (g > total_tiles * p.n_tiles) g = total_tiles * p.n_tiles;
+  if (g > total_tiles * p.n_tiles * (mode == 2 ? 4 : 1)) g = total_tiles * p.n_tiles * (mode == 2 ? 4 : 1);
   if (!stack) conv_umma_kwstack_kernel<32, false, false><<<(unsigned)g, kKwThreads, req, st>>>(tmA, tmB, p);
   else if (BK == 32) conv_umma_kwstack_kernel<32, false, true><<<(unsigned)g, kKwThreads, req, st>>>(tmA, tmB, p);
   else conv_umma_kwstack_kernel<16, false, true><<<(unsigned)g, kKwThreads, req, st>>>(tmA, tmB, p);
@@ -404,11 +423,16 @@ static int launch_kw_impl(bool stack, const float* x, const float* wp, const flo
 
 int launch_conv_umma_kwstack(const float* x, const float* wp, const float* bias, const float* scale, const float* res, float* y, int N, int D, int H, int W,
                              int Cin, int Cout, int kd, int G, int act, cudaStream_t st) {
-  return launch_kw_impl(true, x, wp, bias, scale, res, y, N, D, H, W, Cin, Cout, kd, G, act, st);
+  return launch_kw_impl(1, x, wp, bias, scale, res, y, N, D, H, W, Cin, Cout, kd, G, act, st);
 }
 int launch_conv_umma_pairconv(const float* x, const float* wp, const float* bias, const float* scale, const float* res, float* y, int N, int D, int H, int W,
                               int Cin, int Cout, int kd, int G, int act, cudaStream_t st) {
-  return launch_kw_impl(false, x, wp, bias, scale, res, y, N, D, H, W, Cin, Cout, kd, G, act, st);
+  return launch_kw_impl(0, x, wp, bias, scale, res, y, N, D, H, W, Cin, Cout, kd, G, act, st);
+}
+// sub-pixel up-convolution forward on the same kernel: x [N,H,W,Cin] (low resolution), wsp [16][Cout][Cin], y / res [N,2H,2W,Cout]
+int launch_conv_umma_pairconv_subpix(const float* x, const float* wsp, const float* bias, const float* scale, const float* res, float* y, int N, int H, int W,
+                                     int Cin, int Cout, int G, int act, cudaStream_t st) {
+  return launch_kw_impl(2, x, wsp, bias, scale, res, y, N, 1, H, W, Cin, Cout, 1, G, act, st);
 }
 
 }  // namespace dgmr

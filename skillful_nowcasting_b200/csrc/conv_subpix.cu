@@ -22,6 +22,10 @@
 namespace dgmr {
 
 int launch_conv_umma_wgrad_subpix(const float* x, const float* dz, float* dwp, int N, int H, int W, int Cin, int Cout, cudaStream_t st);
+bool umma_pairconv_ok(int N, int D, int H, int W, int Cin, int Cout, int kd, int kh, int kw, int G);   // conv_kwstack.cu
+int launch_conv_umma_pairconv_subpix(const float* x, const float* wsp, const float* bias, const float* scale, const float* res, float* y, int N, int H, int W,
+                                     int Cin, int Cout, int G, int act, cudaStream_t st);
+int g_subpix_rows = -1;      // dgmr_set_option("subpix_rows"): 0 = never the whole-row pair kernel for the sub-pixel forward, 1 = whenever it supports the shape
 
 struct SubpixParams {
   int N, H, W;           // LOW-resolution geometry (the grid the patches live on); the other tensor is 2H x 2W
@@ -536,6 +540,10 @@ int dgmr_upconv_fwd(const float* x, const float* wsp, const float* bias, const f
                     int Cout, int G, int act, dgmr_stream_t stream) {
   DGMR_REQUIRE(subpix_ok(N, H, W, Cin, Cout, G), "dgmr_upconv_fwd: shape not supported (N=%d H=%d W=%d Cin=%d Cout=%d G=%d)", N, H, W, Cin, Cout, G);
   DGMR_REQUIRE((act & ~(3 | DGMR_FLAG_ROUND_OUT)) == 0 && (act & 3) <= 1, "dgmr_upconv_fwd: bad act");
+  // wide channels on small low-resolution images: whole-row tiles with CTA pairs sharing each pre-summed weight tile (conv_kwstack.cu); the
+  // weight stream per 128-position item is what bounds the patch form there
+  if (g_subpix_rows != 0 && W <= 32 && umma_pairconv_ok(N, 1, H, W, Cin, Cout, 1, 3, 3, G) && (Cin >= 192 || g_subpix_rows == 1))
+    return launch_conv_umma_pairconv_subpix(x, wsp, bias, scale, res, y, N, H, W, Cin, Cout, G, act, S(stream));
   return launch_subpix(1, x, wsp, bias, scale, res, y, N, H, W, Cin, Cout, G, act, S(stream));
 }
 

@@ -23,6 +23,7 @@ int launch_conv_simt_fwd(const float*, const float*, const float*, const float*,
 int launch_conv_simt_wgrad(const float*, const float*, float*, int, int, int, int, int, int, int, int, int, cudaStream_t);
 bool umma_kwstack_ok(int N, int D, int H, int W, int Cin, int Cout, int kd, int kh, int kw, int G);   // conv_kwstack.cu
 extern int g_kwstack_pair;
+extern int g_subpix_rows;
 bool umma_pairconv_ok(int N, int D, int H, int W, int Cin, int Cout, int kd, int kh, int kw, int G);   // conv_kwstack.cu, STACK = false
 int launch_conv_umma_pairconv(const float* x, const float* wp, const float* bias, const float* scale, const float* res, float* y, int N, int D, int H, int W,
                               int Cin, int Cout, int kd, int G, int act, cudaStream_t st);
@@ -1931,7 +1932,7 @@ int dgmr_set_option(const char* name, int value) {
   struct { const char* n; int* v; } tab[] = {{"umma_cg", &g_opt.umma_cg}, {"umma_persist", &g_opt.umma_persist}, {"umma_persist_r", &g_opt.umma_persist_r},
                                              {"patch_pair", &g_opt.patch_pair}, {"patch_mt", &g_opt.patch_mt}, {"patch_tg", &g_opt.patch_tg},
                                              {"prefer_patch", &g_opt.prefer_patch}, {"patch_dbg", &g_opt.patch_dbg},
-                                             {"subpix_wgrad_row", &g_opt.subpix_wgrad_row}, {"kwstack", &g_opt.kwstack}, {"kwstack_pair", &g_kwstack_pair}, {"pairconv", &g_opt.pairconv}};
+                                             {"subpix_wgrad_row", &g_opt.subpix_wgrad_row}, {"kwstack", &g_opt.kwstack}, {"kwstack_pair", &g_kwstack_pair}, {"pairconv", &g_opt.pairconv}, {"subpix_rows", &g_subpix_rows}};
   for (auto& t : tab)
     if (strcmp(t.n, name) == 0) { *t.v = value; return 0; }
   set_error("dgmr_set_option: unknown option '%s'", name);

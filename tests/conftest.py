@@ -44,7 +44,7 @@ def emu():
     ops.clear_pack_cache()
 
 
-OPTIONS = ("umma_cg", "umma_persist", "umma_persist_r", "patch_pair", "patch_mt", "patch_tg", "prefer_patch", "subpix_wgrad_row", "kwstack", "kwstack_pair", "pairconv")
+OPTIONS = ("umma_cg", "umma_persist", "umma_persist_r", "patch_pair", "patch_mt", "patch_tg", "prefer_patch", "subpix_wgrad_row", "kwstack", "kwstack_pair", "pairconv", "subpix_rows")
 
 
 @pytest.fixture

@@ -331,7 +331,11 @@ def test_upconv_subpixel_kernels(cuda_backend, shape):
     emu.pack_weight_subpix(wt, wsp, cout, cin, 0, cin, 0)
     wspt = torch.empty(16 * cout * cin)
     emu.pack_weight_subpix(wt, wspt, cout, cin, 0, cin, 1)
-    for fused in (False, True):
+    # forward: the halo-patch form (subpix_rows = 0) and, on narrow images, the whole-row CTA-pair form (1; single CTAs with kwstack_pair = 0)
+    for fused, rows, pair in [(f, r, pr) for f in (False, True) for (r, pr) in ((0, -1), (1, 1), (1, 0))]:
+        if rows and not (w <= 32 and cout % 16 == 0):
+            continue
+        be.set_option("subpix_rows", rows); be.set_option("kwstack_pair", pair)
         bias = torch.randn(cout) if fused else None
         scale = (torch.rand(g, cout) + 0.5) if fused else None
         res = torch.randn(n, 1, 2 * h, 2 * w, cout) if fused else None
@@ -344,7 +348,8 @@ def test_upconv_subpixel_kernels(cuda_backend, shape):
         torch.cuda.synchronize()
         assert not torch.isnan(y).any(), "sub-pixel forward left outputs unwritten"
         e = (y.cpu() - y_ref).abs().max().item()
-        assert e <= 4e-3 * max(y_ref.abs().max().item(), 1), f"sub-pixel forward err {e:.3e} (fused={fused})"
+        assert e <= 4e-3 * max(y_ref.abs().max().item(), 1), f"sub-pixel forward err {e:.3e} (fused={fused}, rows={rows}, pair={pair})"
+    be.set_option("subpix_rows", -1); be.set_option("kwstack_pair", -1)
     dz = torch.randn(n, 1, 2 * h, 2 * w, cout)
     dx_ref = torch.empty(n, 1, h, w, cin)
     emu.upconv_dgrad(dz, wspt, dx_ref, n, h, w, cin, cout)
