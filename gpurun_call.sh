@@ -1,2 +1,6 @@
-echo "=== upconv tests"; timeout 300 python -m pytest tests/test_umma_gpu.py -x -q -m gpu -k "upconv or subpix or pairconv" --timeout 120 > gpurun_out/upconv.log 2>&1; echo "exit $?"; tail -12 gpurun_out/upconv.log
-timeout 200 python tests/time_subpix_rows.py 2>&1 | tail -4
+TAILN=6 ./run_gpu_tests.sh kernels
+timeout 100 python tests/time_pairconv.py 2>&1 | head -2
+TAILN=6 ./run_gpu_tests.sh parity
+b() { name=$1; shift; echo "=== bench $name"; DGMR_BENCH_DUMP=gpurun_out/shapes_$name.tsv timeout 600 python bench.py "$@" > gpurun_out/bench_$name.json 2> gpurun_out/bench_$name.err; echo "exit $?"; python -c "
+import json; d=json.load(open('gpurun_out/bench_$name.json')); print(d['value'], d['ms_per_step'], d['e2e']['value'], d['gpu_launches']); print(d['kernel_breakdown_ms'])"; tail -n 3 gpurun_out/bench_$name.err; }
+b c3n --steps 5 --warmup 3 --no-ref-gpu --no-cpu-baseline

@@ -133,8 +133,10 @@ int dgmr_bn_finalize(const double* sums, const float* gamma, const float* beta, 
                      float* running_var, int64_t rows, int G, int C, float eps, float momentum, int training,
                      float* mean, float* invstd, float* a, float* b, dgmr_stream_t stream);
 /* y = act(a[g,c]*x + b[g,c]); if up2: x is [G*Ng, H, W, C] and y is [G*Ng, 2H, 2W, C] (nearest).
- * relu | DGMR_FLAG_ROUND_TF32: y is written tf32-rounded (it feeds tensor-core convolutions only). */
-int dgmr_bn_apply(const float* x, const float* a, const float* b, float* y, int64_t rows, int G, int C,
+ * relu | DGMR_FLAG_ROUND_TF32: y is written tf32-rounded (it feeds tensor-core convolutions only).
+ * x_rounded (nullable, not with up2): the tf32-rounded copy of x itself, for x's OTHER consumer in a residual block (the 1x1 shortcut
+ * convolution, ref: dgmr/common.py:71-74,140-143) -- written by the pass that reads x anyway instead of by a separate rounding pass. */
+int dgmr_bn_apply(const float* x, const float* a, const float* b, float* y, float* x_rounded, int64_t rows, int G, int C,
                   int relu, int up2, int H, int W, dgmr_stream_t stream);
 /* red[g][c] = (sum dpre, sum dpre*xhat), dpre = dy*(y>0 if relu), dy pooled over the 2x2 replicas if up2 */
 int dgmr_bn_bwd_reduce(const float* dy, const float* x, const float* a, const float* b, const float* mean,

@@ -236,9 +236,9 @@ class CudaBackend:
                    _f32(rvar, "running_var"), rows, G, C, float(eps), float(momentum), int(training), _f32(mean, "mean"),
                    _f32(invstd, "invstd"), _f32(a, "a"), _f32(b, "b"))
 
-    def bn_apply(self, x, a, b, y, rows, G, C, relu, up2, H, W):
-        self._call("dgmr_bn_apply", _f32(x, "x"), _f32(a, "a"), _f32(b, "b"), _f32(y, "y"), rows, G, C, int(relu), int(up2), H, W,  # relu may carry FLAG_ROUND_TF32
-                   _flops=4.0 * rows * G * C * (5 if up2 else 2), _info=f"rows{rows} G{G} C{C} up{int(up2)} (GB/s)")
+    def bn_apply(self, x, a, b, y, rows, G, C, relu, up2, H, W, x_rounded=None):
+        self._call("dgmr_bn_apply", _f32(x, "x"), _f32(a, "a"), _f32(b, "b"), _f32(y, "y"), _f32(x_rounded, "x_rounded"), rows, G, C, int(relu), int(up2), H, W,  # relu may carry FLAG_ROUND_TF32
+                   _flops=4.0 * rows * G * C * (5 if up2 else 2 + (x_rounded is not None)), _info=f"rows{rows} G{G} C{C} up{int(up2)}{' +xr' if x_rounded is not None else ''} (GB/s)")
 
     def bn_bwd_reduce(self, dy, x, a, b, mean, invstd, red, rows, G, C, relu, up2, H, W):
         self._call("dgmr_bn_bwd_reduce", _f32(dy, "dy"), _f32(x, "x"), _f32(a, "a"), _f32(b, "b"), _f32(mean, "mean"),

@@ -391,28 +391,30 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, const float*
 }
 // y = act(a*x+b), optional nearest x2 upsample on write.  One thread per output element.
 __global__ void bn_apply_kernel(const float* __restrict__ x, const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ y,
-                                int64_t rows, int G, int C, int relu, int up2, int H, int W, int rnd) {
+                                int64_t rows, int G, int C, int relu, int up2, int H, int W, int rnd, float* __restrict__ xr) {
   int64_t orows = up2 ? rows * 4 : rows;
   int64_t total = (int64_t)G * orows * C;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     int c = i % C; int64_t r = i / C;  // global output row
     int g = r / orows;
-    int64_t xr = r;
+    int64_t xrow = r;
     if (up2) {
       int Wo = 2 * W, Ho = 2 * H;
       int wo = r % Wo; int64_t t = r / Wo;
       int ho = t % Ho; int64_t n = t / Ho;
-      xr = (n * H + (ho >> 1)) * W + (wo >> 1);
+      xrow = (n * H + (ho >> 1)) * W + (wo >> 1);
     }
-    float v = a[(int64_t)g * C + c] * x[xr * C + c] + b[(int64_t)g * C + c];
+    const float u = x[xrow * C + c];
+    float v = a[(int64_t)g * C + c] * u + b[(int64_t)g * C + c];
     v = relu ? fmaxf(v, 0.f) : v;
     y[i] = rnd ? rna_tf32_pw(v) : v;
+    if (xr) xr[i] = rna_tf32_pw(u);      // (never with up2: host-checked)
   }
 }
 // I = uint32_t when every index fits 32 bits (a 64-bit div/mod costs ~4x a 32-bit one and these kernels do several per element)
 template <typename I>
 __global__ void bn_apply4_kernel(const float4* __restrict__ x, const float4* __restrict__ a, const float4* __restrict__ b, float4* __restrict__ y,
-                                 int64_t rows, int G, int C4, int relu, int up2, int H, int W, int rnd) {
+                                 int64_t rows, int G, int C4, int relu, int up2, int H, int W, int rnd, float4* __restrict__ xr4) {
   const I orows = (I)(up2 ? rows * 4 : rows);
   const I total = (I)G * orows * C4;
   for (I i = blockIdx.x * (I)blockDim.x + threadIdx.x; i < total; i += (I)gridDim.x * blockDim.x) {
@@ -430,6 +432,7 @@ __global__ void bn_apply4_kernel(const float4* __restrict__ x, const float4* __r
     if (relu) v = make_float4(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f), fmaxf(v.z, 0.f), fmaxf(v.w, 0.f));
     if (rnd) v = make_float4(rna_tf32_pw(v.x), rna_tf32_pw(v.y), rna_tf32_pw(v.z), rna_tf32_pw(v.w));
     y[i] = v;
+    if (xr4) xr4[i] = make_float4(rna_tf32_pw(u.x), rna_tf32_pw(u.y), rna_tf32_pw(u.z), rna_tf32_pw(u.w));      // (never with up2: host-checked)
   }
 }
 // dpre at low-res row r, channel c (sums the 4 replicas if up2, applies relu mask)
@@ -1025,17 +1028,19 @@ int dgmr_bn_finalize(const double* sums, const float* gamma, const float* beta, 
   DGMR_CHECK_LAUNCH("dgmr_bn_finalize");
   return 0;
 }
-int dgmr_bn_apply(const float* x, const float* a, const float* b, float* y, int64_t rows, int G, int C, int relu, int up2, int H, int W, dgmr_stream_t stream) {
+int dgmr_bn_apply(const float* x, const float* a, const float* b, float* y, float* x_rounded, int64_t rows, int G, int C, int relu, int up2, int H, int W,
+                  dgmr_stream_t stream) {
   const int rnd = (relu & DGMR_FLAG_ROUND_TF32) ? 1 : 0;   // output feeds tensor-core convs only: emit tf32-rounded values directly
   relu &= ~DGMR_FLAG_ROUND_TF32;
   int64_t total = (int64_t)G * rows * C * (up2 ? 4 : 1);
   if (total == 0) return 0;
   DGMR_REQUIRE(!up2 || (rows % ((int64_t)H * W) == 0), "dgmr_bn_apply: rows not a multiple of H*W");
-  if (C % 4 == 0 && al16(x) && al16(y) && al16(a) && al16(b))
-    if (total < (int64_t)1 << 31) bn_apply4_kernel<uint32_t><<<ew_grid(total / 4, 256, 1), 256, 0, S(stream)>>>((const float4*)x, (const float4*)a, (const float4*)b, (float4*)y, rows, G, C / 4, relu, up2, H, W, rnd);
-    else bn_apply4_kernel<int64_t><<<ew_grid(total / 4, 256, 1), 256, 0, S(stream)>>>((const float4*)x, (const float4*)a, (const float4*)b, (float4*)y, rows, G, C / 4, relu, up2, H, W, rnd);
+  DGMR_REQUIRE(!(up2 && x_rounded), "dgmr_bn_apply: x_rounded is not available together with up2");
+  if (C % 4 == 0 && al16(x) && al16(y) && al16(a) && al16(b) && al16(x_rounded))
+    if (total < (int64_t)1 << 31) bn_apply4_kernel<uint32_t><<<ew_grid(total / 4, 256, 1), 256, 0, S(stream)>>>((const float4*)x, (const float4*)a, (const float4*)b, (float4*)y, rows, G, C / 4, relu, up2, H, W, rnd, (float4*)x_rounded);
+    else bn_apply4_kernel<int64_t><<<ew_grid(total / 4, 256, 1), 256, 0, S(stream)>>>((const float4*)x, (const float4*)a, (const float4*)b, (float4*)y, rows, G, C / 4, relu, up2, H, W, rnd, (float4*)x_rounded);
   else
-    bn_apply_kernel<<<ew_grid(total, 256, 2), 256, 0, S(stream)>>>(x, a, b, y, rows, G, C, relu, up2, H, W, rnd);
+    bn_apply_kernel<<<ew_grid(total, 256, 2), 256, 0, S(stream)>>>(x, a, b, y, rows, G, C, relu, up2, H, W, rnd, x_rounded);
   DGMR_CHECK_LAUNCH("dgmr_bn_apply");
   return 0;
 }

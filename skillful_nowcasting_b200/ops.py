@@ -484,6 +484,9 @@ def _round_(t: torch.Tensor) -> torch.Tensor:
     (flag rides on the Python tensor object), else a rounded copy."""
     if getattr(t, "_dgmr_tf32", False):
         return t
+    r = getattr(t, "_dgmr_rounded", None)
+    if r is not None:                      # a producer already wrote the rounded copy (BatchNorm branch node)
+        return r
     if getattr(t, "_dgmr_conv_only", False):
         _be().round_tf32(t)
         t._dgmr_tf32 = True
@@ -871,7 +874,10 @@ class _BatchNorm(Function):
         be.bn_finalize(sums, gamma, beta, rmean, rvar, rows, G, c, eps, momentum, training, mean, invstd, a, b)
         y = _new((n, d, 2 * h, 2 * w, c) if up2 else (n, d, h, w, c), x)
         rnd = conv_only and _rounding_on()
-        be.bn_apply(x, a, b, y, rows, G, c, int(relu_) | (FLAG_ROUND_TF32 if rnd else 0), up2, h, w)
+        # branch: the shortcut convolution wants x tf32-rounded (a private copy: this BatchNorm must see the unrounded values) -- written by
+        # this pass, which reads x anyway, instead of by a rounding pass of its own
+        xr = _new(x.shape, x) if (branch and _rounding_on() and not up2 and not getattr(x, "_dgmr_tf32", False)) else None
+        be.bn_apply(x, a, b, y, rows, G, c, int(relu_) | (FLAG_ROUND_TF32 if rnd else 0), up2, h, w, x_rounded=xr)
         if rnd:
             y._dgmr_tf32 = True
         ctx.save_for_backward(x, gamma, a, b, mean, invstd)
@@ -880,11 +886,14 @@ class _BatchNorm(Function):
             # second output: the input itself, for its OTHER consumer (the residual shortcut).  Routing that use through this node means
             # the two gradients of x meet in backward(), where dgmr_bn_bwd_apply adds the shortcut's while it writes dx -- instead of
             # autograd accumulating them in a separate read-read-write pass over the activation.
+            if xr is not None:
+                ctx.mark_non_differentiable(xr)
+                return y, x.view_as(x), xr
             return y, x.view_as(x)
         return y
 
     @staticmethod
-    def backward(ctx, dy, dskip=None):
+    def backward(ctx, dy, dskip=None, _dxr=None):
         x, gamma, a, b, mean, invstd = ctx.saved_tensors
         G, training, relu_, up2 = ctx.meta
         be = _be()
@@ -906,7 +915,13 @@ class _BatchNorm(Function):
 def batch_norm(x, gamma, beta, rmean, rvar, G, training, relu_=False, up2=False, eps=1e-5, momentum=0.1, conv_only=False, branch=False):
     """conv_only: the result is consumed by convolutions only, so it may be emitted tf32-rounded straight away.
     branch: returns (y, x_skip) -- x_skip is the input, to be handed to its other consumer (see _BatchNorm.forward)."""
-    return _BatchNorm.apply(x, gamma, beta, rmean, rvar, G, training, relu_, up2, eps, momentum, conv_only, branch)
+    out = _BatchNorm.apply(x, gamma, beta, rmean, rvar, G, training, relu_, up2, eps, momentum, conv_only, branch)
+    if branch and len(out) == 3:
+        y, skip, xr = out
+        xr._dgmr_tf32 = True
+        skip._dgmr_rounded = xr          # picked up by _round_ when the shortcut convolution asks for its operand
+        return y, skip
+    return out
 
 
 # ----------------------------------------------------------------------------- nearest x2 -> 3x3 conv, sub-pixel form

@@ -154,8 +154,11 @@ class EmuBackend:
     def _bn_low(x, rows, G, C):
         return x.reshape(G, rows, C)
 
-    def bn_apply(self, x, a, b, y, rows, G, C, relu, up2, H, W):
+    def bn_apply(self, x, a, b, y, rows, G, C, relu, up2, H, W, x_rounded=None):
         rnd, relu = bool(int(relu) & 256), int(relu) & ~256
+        if x_rounded is not None:
+            assert not up2
+            x_rounded.copy_(self._rna_tf32(x.reshape(x_rounded.shape)))
         v = x.reshape(G, rows, C) * a.reshape(G, 1, C) + b.reshape(G, 1, C)
         if relu:
             v = torch.relu(v)

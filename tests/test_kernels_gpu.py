@@ -117,6 +117,13 @@ def test_batchnorm(cuda_backend, G, rows, C, relu, up2):
     y = torch.empty(G * rows * (4 if up2 else 1), C)
     _both("bn_apply", [x, a, b, y, rows, G, C, relu, up2, H, W], cuda_backend, atol=1e-6)
     _both("bn_apply", [x, a, b, y, rows, G, C, int(relu) | 256, up2, H, W], cuda_backend, rtol=6e-4, atol=1e-6)  # tf32-rounded output
+    if not up2:   # second output: the tf32-rounded copy of x itself (bit-exact: cvt.rna)
+        xr = torch.empty_like(x)
+        _both("bn_apply", [x, a, b, y, rows, G, C, int(relu) | 256, up2, H, W], cuda_backend, rtol=6e-4, atol=1e-6, kwargs=dict(x_rounded=None))
+        emu_y, gpu_y, gpu_xr = torch.empty_like(y), torch.empty_like(y).cuda(), torch.empty_like(x).cuda()
+        EmuBackend().bn_apply(x, a, b, emu_y, rows, G, C, int(relu), up2, H, W, x_rounded=xr)
+        cuda_backend.bn_apply(x.cuda(), a.cuda(), b.cuda(), gpu_y, rows, G, C, int(relu), up2, H, W, x_rounded=gpu_xr)
+        assert torch.equal(gpu_xr.cpu(), xr) and (gpu_y.cpu() - emu_y).abs().max().item() <= 1e-5 * max(emu_y.abs().max().item(), 1)
     dy = torch.randn_like(y)
     red = torch.zeros(G, C, 2, dtype=torch.float64)
     _both("bn_bwd_reduce", [dy, x, a, b, mean, invstd, red, rows, G, C, relu, up2, H, W], cuda_backend, rtol=1e-4, atol=1e-4)

@@ -10,7 +10,7 @@ def timeit(f, n=5):
     for _ in range(n): f()
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1)/n
-for (n,d,h,w,cin,cout,kd,g) in [(288,1,64,64,96,96,1,18),(288,1,64,64,192,96,1,18),(288,1,128,128,96,96,1,18),(32,11,32,32,96,96,3,1),(288,1,128,128,48,96,1,1),
+for (n,d,h,w,cin,cout,kd,g) in [(16,1,16,16,192,192,1,1),(16,1,16,16,384,192,1,1),(288,1,64,64,96,96,1,18),(288,1,64,64,192,96,1,18),(288,1,128,128,96,96,1,18),(32,11,32,32,96,96,3,1),(288,1,128,128,48,96,1,1),
                                 (256,1,32,32,96,96,1,8),(256,1,64,64,48,48,1,8),(16,1,32,32,96,192,1,1),(16,1,16,16,192,384,1,1),(16,1,64,64,48,96,1,1),(160,1,16,16,192,192,1,5)]:
     taps=kd*9
     x = torch.randn(n,d,h,w,cin,device="cuda"); wp = torch.randn(taps*cout*cin,device="cuda")/30
