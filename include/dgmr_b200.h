@@ -116,13 +116,15 @@ int dgmr_gru_gate_fwd(const float* pre_r, int ld, const float* h, float* rh, int
 /* hnew_tf32 (nullable): tf32-rounded copy of hnew = the next step's conv operand */
 int dgmr_gru_blend_fwd(const float* pre_u, int ld, const float* h, const float* c, float* hnew, float* hnew_tf32,
                        int64_t rows, int Ch, int relu_c, dgmr_stream_t stream);
-/* d_rh -> d_pre_r, dh (+= if accumulate) */
+/* d_rh -> d_pre_r, dh (+= if accumulate).  dz_scale [Ch] / dz (nullable, leading dimension ldd like d_pre_r): additionally dz = d_pre_r * dz_scale[c]
+ * (tf32-rounded if dz_round) -- the recurrent convolution's backward operand, so the walk over the steps needs no dgmr_conv_bwd_prep per step */
 int dgmr_gru_gate_bwd(const float* d_rh, const float* pre_r, int ld, const float* h, float* d_pre_r, int ldd,
-                      float* dh, int accumulate, int64_t rows, int Ch, dgmr_stream_t stream);
-/* d_hnew -> d_pre_u, dc, dh (+= if accumulate) */
+                      float* dh, int accumulate, int64_t rows, int Ch, const float* dz_scale, float* dz, int dz_round, dgmr_stream_t stream);
+/* d_hnew -> d_pre_u, dc, dh (+= if accumulate); dz_u (ldd) = d_pre_u * dz_u_scale[c], dz_c (contiguous) = dc * dz_c_scale[c] as above (nullable) */
 int dgmr_gru_blend_bwd(const float* d_hnew, const float* pre_u, int ld, const float* h, const float* c,
                        float* d_pre_u, int ldd, float* dc, float* dh, int accumulate,
-                       int64_t rows, int Ch, int relu_c, dgmr_stream_t stream);
+                       int64_t rows, int Ch, int relu_c, const float* dz_u_scale, float* dz_u, const float* dz_c_scale, float* dz_c, int dz_round,
+                       dgmr_stream_t stream);
 
 /* ---- BatchNorm (ref: BatchNorm2d dgmr/common.py:38-39,108-109, generators.py:113; BatchNorm1d
  * discriminators.py:102,194).  x: [G*rows, C]; batch statistics per (group, channel). */

@@ -219,13 +219,15 @@ class CudaBackend:
         self._call("dgmr_gru_blend_fwd", _f32(pre_u, "pre_u"), ld, _f32(h, "h"), _f32(c, "c"), _f32(hnew, "hnew"), _f32(hnew_tf32, "hnew_tf32"),
                    rows, Ch, int(relu_c))
 
-    def gru_gate_bwd(self, d_rh, pre_r, ld, h, d_pre_r, ldd, dh, accumulate, rows, Ch):
+    def gru_gate_bwd(self, d_rh, pre_r, ld, h, d_pre_r, ldd, dh, accumulate, rows, Ch, dz_scale=None, dz=None, dz_round=False):
         self._call("dgmr_gru_gate_bwd", _f32(d_rh, "d_rh"), _f32(pre_r, "pre_r"), ld, _f32(h, "h"), _f32(d_pre_r, "d_pre_r"), ldd,
-                   _f32(dh, "dh"), int(accumulate), rows, Ch)
+                   _f32(dh, "dh"), int(accumulate), rows, Ch, _f32(dz_scale, "dz_scale"), _f32(dz, "dz"), int(dz_round))
 
-    def gru_blend_bwd(self, d_hnew, pre_u, ld, h, c, d_pre_u, ldd, dc, dh, accumulate, rows, Ch, relu_c=False):
+    def gru_blend_bwd(self, d_hnew, pre_u, ld, h, c, d_pre_u, ldd, dc, dh, accumulate, rows, Ch, relu_c=False, dz_u_scale=None, dz_u=None,
+                      dz_c_scale=None, dz_c=None, dz_round=False):
         self._call("dgmr_gru_blend_bwd", _f32(d_hnew, "d_hnew"), _f32(pre_u, "pre_u"), ld, _f32(h, "h"), _f32(c, "c"),
-                   _f32(d_pre_u, "d_pre_u"), ldd, _f32(dc, "dc"), _f32(dh, "dh"), int(accumulate), rows, Ch, int(relu_c))
+                   _f32(d_pre_u, "d_pre_u"), ldd, _f32(dc, "dc"), _f32(dh, "dh"), int(accumulate), rows, Ch, int(relu_c),
+                   _f32(dz_u_scale, "dz_u_scale"), _f32(dz_u, "dz_u"), _f32(dz_c_scale, "dz_c_scale"), _f32(dz_c, "dz_c"), int(dz_round))
 
     # -- BatchNorm
     def bn_stats(self, x, sums, rows, G, C):

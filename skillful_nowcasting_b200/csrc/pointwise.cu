@@ -244,20 +244,26 @@ __global__ void gru_blend_fwd4_kernel(const float* __restrict__ pre_u, int ld, c
     if (hn_tf32) hn_tf32[i] = make_float4(rna_tf32_pw(v.x), rna_tf32_pw(v.y), rna_tf32_pw(v.z), rna_tf32_pw(v.w));
   }
 }
+// sc / dz (nullable): additionally write dz = d_pre * sc[c] (tf32-rounded if rnd) -- the operand of the recurrent convolution's dgrad / wgrad, so
+// that the backward walk needs no separate prologue pass per step (its per-step scale gradients are reduced in one grouped pass afterwards)
 __global__ void gru_gate_bwd_kernel(const float* __restrict__ d_rh, const float* __restrict__ pre_r, int ld, const float* __restrict__ h,
-                                    float* __restrict__ d_pre_r, int ldd, float* __restrict__ dh, int acc, int64_t rows, int Ch) {
+                                    float* __restrict__ d_pre_r, int ldd, float* __restrict__ dh, int acc, int64_t rows, int Ch,
+                                    const float* __restrict__ sc, float* __restrict__ dz, int rnd) {
   int64_t total = rows * Ch;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     int64_t r = i / Ch; int c = i - r * Ch;
     float g = 1.0f / (1.0f + expf(-pre_r[r * ld + c]));
     float d = d_rh[i];
-    d_pre_r[r * ldd + c] = d * h[i] * g * (1.0f - g);
+    const float dp = d * h[i] * g * (1.0f - g);
+    d_pre_r[r * ldd + c] = dp;
+    if (dz) { const float z = dp * sc[c]; dz[r * ldd + c] = rnd ? rna_tf32_pw(z) : z; }
     float v = d * g;
     if (acc) dh[i] += v; else dh[i] = v;
   }
 }
 __global__ void gru_blend_bwd_kernel(const float* __restrict__ d_hn, const float* __restrict__ pre_u, int ld, const float* __restrict__ h, const float* __restrict__ c_,
-                                     float* __restrict__ d_pre_u, int ldd, float* __restrict__ dc, float* __restrict__ dh, int acc, int64_t rows, int Ch, int relu_c) {
+                                     float* __restrict__ d_pre_u, int ldd, float* __restrict__ dc, float* __restrict__ dh, int acc, int64_t rows, int Ch, int relu_c,
+                                     const float* __restrict__ sc_u, float* __restrict__ dz_u, const float* __restrict__ sc_c, float* __restrict__ dz_c, int rnd) {
   int64_t total = rows * Ch;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     int64_t r = i / Ch; int c = i - r * Ch;
@@ -265,8 +271,12 @@ __global__ void gru_blend_bwd_kernel(const float* __restrict__ d_hn, const float
     float d = d_hn[i];
     float cp = c_[i];
     float cv = relu_c ? fmaxf(cp, 0.f) : cp;
-    d_pre_u[r * ldd + c] = d * (h[i] - cv) * u * (1.0f - u);
-    dc[i] = (relu_c && !(cp > 0.f)) ? 0.f : d * (1.0f - u);
+    const float dpu = d * (h[i] - cv) * u * (1.0f - u);
+    d_pre_u[r * ldd + c] = dpu;
+    if (dz_u) { const float z = dpu * sc_u[c]; dz_u[r * ldd + c] = rnd ? rna_tf32_pw(z) : z; }
+    const float dcv = (relu_c && !(cp > 0.f)) ? 0.f : d * (1.0f - u);
+    dc[i] = dcv;
+    if (dz_c) { const float z = dcv * sc_c[c]; dz_c[i] = rnd ? rna_tf32_pw(z) : z; }
     float v = d * u;
     if (acc) dh[i] += v; else dh[i] = v;
   }
@@ -990,15 +1000,21 @@ int dgmr_gru_blend_fwd(const float* pre_u, int ld, const float* h, const float* 
   DGMR_CHECK_LAUNCH("dgmr_gru_blend_fwd");
   return 0;
 }
-int dgmr_gru_gate_bwd(const float* d_rh, const float* pre_r, int ld, const float* h, float* d_pre_r, int ldd, float* dh, int accumulate, int64_t rows, int Ch, dgmr_stream_t stream) {
+int dgmr_gru_gate_bwd(const float* d_rh, const float* pre_r, int ld, const float* h, float* d_pre_r, int ldd, float* dh, int accumulate, int64_t rows, int Ch,
+                      const float* dz_scale, float* dz, int dz_round, dgmr_stream_t stream) {
   int64_t n = rows * Ch; if (n == 0) return 0;
-  gru_gate_bwd_kernel<<<ew_grid(n, 256, 2), 256, 0, S(stream)>>>(d_rh, pre_r, ld, h, d_pre_r, ldd, dh, accumulate, rows, Ch);
+  DGMR_REQUIRE((dz == nullptr) == (dz_scale == nullptr), "dgmr_gru_gate_bwd: dz and dz_scale go together");
+  gru_gate_bwd_kernel<<<ew_grid(n, 256, 2), 256, 0, S(stream)>>>(d_rh, pre_r, ld, h, d_pre_r, ldd, dh, accumulate, rows, Ch, dz_scale, dz, dz_round);
   DGMR_CHECK_LAUNCH("dgmr_gru_gate_bwd");
   return 0;
 }
-int dgmr_gru_blend_bwd(const float* d_hnew, const float* pre_u, int ld, const float* h, const float* c, float* d_pre_u, int ldd, float* dc, float* dh, int accumulate, int64_t rows, int Ch, int relu_c, dgmr_stream_t stream) {
+int dgmr_gru_blend_bwd(const float* d_hnew, const float* pre_u, int ld, const float* h, const float* c, float* d_pre_u, int ldd, float* dc, float* dh, int accumulate,
+                       int64_t rows, int Ch, int relu_c, const float* dz_u_scale, float* dz_u, const float* dz_c_scale, float* dz_c, int dz_round,
+                       dgmr_stream_t stream) {
   int64_t n = rows * Ch; if (n == 0) return 0;
-  gru_blend_bwd_kernel<<<ew_grid(n, 256, 2), 256, 0, S(stream)>>>(d_hnew, pre_u, ld, h, c, d_pre_u, ldd, dc, dh, accumulate, rows, Ch, relu_c);
+  DGMR_REQUIRE((dz_u == nullptr) == (dz_u_scale == nullptr) && (dz_c == nullptr) == (dz_c_scale == nullptr), "dgmr_gru_blend_bwd: dz and its scale go together");
+  gru_blend_bwd_kernel<<<ew_grid(n, 256, 2), 256, 0, S(stream)>>>(d_hnew, pre_u, ld, h, c, d_pre_u, ldd, dc, dh, accumulate, rows, Ch, relu_c, dz_u_scale, dz_u,
+                                                                   dz_c_scale, dz_c, dz_round);
   DGMR_CHECK_LAUNCH("dgmr_gru_blend_bwd");
   return 0;
 }

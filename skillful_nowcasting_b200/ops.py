@@ -1267,21 +1267,25 @@ class _GruSequence(Function):
         ds_ru, ds_c = _new((T, 2 * ch), h0), _new((T, ch), h0)
         drh = _new(h0.shape, h0)
         pru_flat, dxru_flat = pru.view(-1), dxru.view(-1)
-        f_ru = ACT_NONE | (FLAG_ROUND_TF32 if (tc_dg_ru or tc_wg_ru) else 0)
-        f_c = ACT_NONE | (FLAG_ROUND_TF32 if (tc_dg_c or tc_wg_c) else 0)
+        rnd_ru = rnd_c = bool(tc_dg_ru or tc_wg_ru or tc_dg_c or tc_wg_c)     # (both convolutions have Ch input channels: served alike)
+        dzru_flat = dzru.view(-1)
         for t in range(T - 1, -1, -1):
             sl = slice(t * B, (t + 1) * B)
             h_prev = h0 if t == 0 else out[(t - 1) * B:t * B]
             tgt = dh0 if t == 0 else gh[(t - 1) * B:t * B]
             off = t * rows * 2 * ch
-            # h_t = u h + (1-u) relu(c):  d pre_u -> dxru[:, ch:], d c_pre -> dxc, u * dh_t -> tgt
-            be.gru_blend_bwd(gh[sl], pru_flat[off + ch:], 2 * ch, h_prev, cp[sl], dxru_flat[off + ch:], 2 * ch, dxc[sl], tgt, t > 0, rows, ch, True)
-            be.conv_bwd_prep(dxc[sl], cp[sl], xc[sl], None, s_c[t:t + 1], dzc[sl], None, None, ds_c[t:t + 1], rows, 1, ch, f_c)
+            # h_t = u h + (1-u) relu(c):  d pre_u -> dxru[:, ch:], d c_pre -> dxc, u * dh_t -> tgt.  The gate kernels also emit the scaled (and
+            # rounded) operands dzru / dzc of the recurrent convolutions' backward: no prologue pass per step (the per-step scale gradients are
+            # reduced in ONE grouped pass per weight after the loop)
+            be.gru_blend_bwd(gh[sl], pru_flat[off + ch:], 2 * ch, h_prev, cp[sl], dxru_flat[off + ch:], 2 * ch, dxc[sl], tgt, t > 0, rows, ch, True,
+                             dz_u_scale=s_ru[t, ch:], dz_u=dzru_flat[off + ch:], dz_c_scale=s_c[t], dz_c=dzc[sl], dz_round=rnd_c)
             _conv_launch(dzc[sl], wpt_c, None, None, None, drh, B, 1, H, W, ch, ch, 1, 3, 3, 1, ACT_NONE)
             # rh = r h:  d pre_r -> dxru[:, :ch], r * drh added to tgt
-            be.gru_gate_bwd(drh, pru[sl], 2 * ch, h_prev, dxru[sl], 2 * ch, tgt, True, rows, ch)
-            be.conv_bwd_prep(dxru[sl], pru[sl], xru[sl], None, s_ru[t:t + 1], dzru[sl], None, None, ds_ru[t:t + 1], rows, 1, 2 * ch, f_ru)
+            be.gru_gate_bwd(drh, pru[sl], 2 * ch, h_prev, dxru[sl], 2 * ch, tgt, True, rows, ch, dz_scale=s_ru[t, :ch], dz=dzru[sl], dz_round=rnd_ru)
             _conv_launch(dzru[sl], wpt_ru, None, None, tgt, tgt, B, 1, H, W, 2 * ch, ch, 1, 3, 3, 1, ACT_NONE)
+        # d s[t, co] = <d pre_t[co], pre_t[co] - x_t[co]> / s[t, co]: one grouped reduction (G = T) per weight
+        be.conv_bwd_prep(dxc, cp, xc, None, s_c, None, None, None, ds_c, rows, T, ch, ACT_NONE)
+        be.conv_bwd_prep(dxru, pru, xru, None, s_ru, None, None, None, ds_ru, rows, T, 2 * ch, ACT_NONE)
         # weight gradients: one launch per weight over all T*B images
         xop = hop[:T * B] if hop is not None else torch.cat([h0, out[:(T - 1) * B]], dim=0)
         dws = []

@@ -108,23 +108,35 @@ class EmuBackend:
         if hnew_tf32 is not None:
             hnew_tf32.copy_(self._rna_tf32(v).reshape(hnew_tf32.shape))
 
-    def gru_gate_bwd(self, d_rh, pre_r, ld, h, d_pre_r, ldd, dh, accumulate, rows, Ch):
+    def gru_gate_bwd(self, d_rh, pre_r, ld, h, d_pre_r, ldd, dh, accumulate, rows, Ch, dz_scale=None, dz=None, dz_round=False):
         g = torch.sigmoid(_rows(pre_r, rows, ld, Ch))
         d = d_rh.reshape(rows, Ch)
-        _rows(d_pre_r, rows, ldd, Ch)[...] = d * h.reshape(rows, Ch) * g * (1 - g)
+        dp = d * h.reshape(rows, Ch) * g * (1 - g)
+        _rows(d_pre_r, rows, ldd, Ch)[...] = dp
+        if dz is not None:
+            z = dp * dz_scale.reshape(1, Ch)
+            _rows(dz, rows, ldd, Ch)[...] = self._rna_tf32(z) if dz_round else z
         v = (d * g).reshape(dh.shape)
         dh.add_(v) if accumulate else dh.copy_(v)
 
-    def gru_blend_bwd(self, d_hnew, pre_u, ld, h, c, d_pre_u, ldd, dc, dh, accumulate, rows, Ch, relu_c=False):
+    def gru_blend_bwd(self, d_hnew, pre_u, ld, h, c, d_pre_u, ldd, dc, dh, accumulate, rows, Ch, relu_c=False, dz_u_scale=None, dz_u=None,
+                      dz_c_scale=None, dz_c=None, dz_round=False):
         u = torch.sigmoid(_rows(pre_u, rows, ld, Ch))
         d = d_hnew.reshape(rows, Ch)
         cp = c.reshape(rows, Ch)
         cv = torch.relu(cp) if relu_c else cp
-        _rows(d_pre_u, rows, ldd, Ch)[...] = d * (h.reshape(rows, Ch) - cv) * u * (1 - u)
+        dpu = d * (h.reshape(rows, Ch) - cv) * u * (1 - u)
+        _rows(d_pre_u, rows, ldd, Ch)[...] = dpu
+        if dz_u is not None:
+            z = dpu * dz_u_scale.reshape(1, Ch)
+            _rows(dz_u, rows, ldd, Ch)[...] = self._rna_tf32(z) if dz_round else z
         g = d * (1 - u)
         if relu_c:
             g = g * (cp > 0)
         dc.copy_(g.reshape(dc.shape))
+        if dz_c is not None:
+            z = g * dz_c_scale.reshape(1, Ch)
+            dz_c.copy_((self._rna_tf32(z) if dz_round else z).reshape(dz_c.shape))
         v = (d * u).reshape(dh.shape)
         dh.add_(v) if accumulate else dh.copy_(v)
 

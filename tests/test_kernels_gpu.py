@@ -95,6 +95,13 @@ def test_gru_pointwise(cuda_backend):
         _both("gru_blend_bwd", [g, pre, ch, h, c, torch.empty(rows, ch), ch, torch.empty(rows, ch), torch.empty(rows, ch), False, rows, ch, relu_c],
               cuda_backend, atol=1e-6)
     _both("gru_gate_bwd", [g, pre, ch, h, torch.empty(rows, ch), ch, torch.empty(rows, ch), False, rows, ch], cuda_backend, atol=1e-6)
+    # fused backward operands: dz = d_pre * scale[c], fp32 and tf32-rounded
+    sc, sc2 = torch.rand(ch) + 0.5, torch.rand(ch) + 0.5
+    for rnd in (False, True):
+        tol = dict(rtol=6e-4, atol=1e-6) if rnd else dict(atol=1e-6)
+        _both("gru_gate_bwd", [g, pre, ch, h, torch.empty(rows, ch), ch, torch.empty(rows, ch), False, rows, ch, sc, torch.empty(rows, ch), rnd], cuda_backend, **tol)
+        _both("gru_blend_bwd", [g, pre, ch, h, c, torch.empty(rows, ch), ch, torch.empty(rows, ch), torch.empty(rows, ch), False, rows, ch, True,
+                                sc, torch.empty(rows, ch), sc2, torch.empty(rows, ch), rnd], cuda_backend, **tol)
 
 
 @pytest.mark.parametrize("G,rows,C,relu,up2", [(1, 500, 24, True, False), (3, 2 * 8 * 8, 96, True, True), (4, 6, 768, False, False), (2, 4 * 4, 4, True, True),
