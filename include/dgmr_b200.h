@@ -62,9 +62,6 @@ const char* dgmr_last_error(void);
 int dgmr_abi_version(void);
 /* 1 if the tcgen05/TMA implicit-GEMM path can serve this conv shape (else the SIMT kernel is used) */
 int dgmr_conv_umma_supported(int N, int D, int H, int W, int Cin, int Cout, int kd, int kh, int kw);
-/* 1 if AUTO dispatch serves the shape with the pair-persistent whole-row kernel (bias / residual / scale in its epilogue): the caller then has no
- * reason to split a small launch over the filter taps (DGMR_FLAG_ACCUMULATE) */
-int dgmr_conv_rows_supported(int N, int D, int H, int W, int Cin, int Cout, int kd, int kh, int kw);
 int dgmr_wgrad_umma_supported(int N, int D, int H, int W, int Cin, int Cout, int kd, int kh, int kw);
 
 /* Process-wide tuning / test options of the tensor-core launchers (-1 restores the heuristic default): "umma_cg", "umma_persist",

@@ -171,9 +171,6 @@ class CudaBackend:
     def conv_umma_supported(self, N, D, H, W, Cin, Cout, kd, kh, kw) -> bool:
         return bool(self._query("dgmr_conv_umma_supported", N, D, H, W, Cin, Cout, kd, kh, kw))
 
-    def conv_rows_supported(self, N, D, H, W, Cin, Cout, kd, kh, kw) -> bool:
-        return bool(self._query("dgmr_conv_rows_supported", N, D, H, W, Cin, Cout, kd, kh, kw))
-
     def wgrad_umma_supported(self, N, D, H, W, Cin, Cout, kd, kh, kw) -> bool:
         return bool(self._query("dgmr_wgrad_umma_supported", N, D, H, W, Cin, Cout, kd, kh, kw))
 

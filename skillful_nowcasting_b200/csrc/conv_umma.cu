@@ -1656,12 +1656,6 @@ static bool umma_patch_profitable(int N, int D, int H, int W, int Cin, int Cout)
   return Cin >= 32 && Cout >= 64 && (int64_t)H * W >= 1024 && (int64_t)N * D * H * W >= (int64_t)128 * 2 * sm_count();   // (16 x 64^2 48->96: 34 -> 26 us)
 }
 
-// AUTO dispatch: does this shape go to the pair-persistent whole-row kernel (conv_kwstack.cu, STACK = false)?
-static bool auto_takes_rows_kernel(int N, int D, int H, int W, int Cin, int Cout, int kd, int kh, int kw, int G) {
-  return g_opt.pairconv != 0 && W <= 32 && Cout >= 64 && umma_pairconv_ok(N, D, H, W, Cin, Cout, kd, kh, kw, G) &&
-         (Cin >= 192 || (int64_t)N * D * H * W <= 131072 || g_opt.pairconv == 1);
-}
-
 int launch_conv_umma_patch(const float* x, const float* wp, const float* bias, const float* scale, const float* res, float* y, int N, int D, int H, int W,
                            int Cin, int Cout, int kd, int G, int act, cudaStream_t st) {
   PatchConvParams p;
@@ -1944,9 +1938,6 @@ int dgmr_set_option(const char* name, int value) {
   set_error("dgmr_set_option: unknown option '%s'", name);
   return 1;
 }
-int dgmr_conv_rows_supported(int N, int D, int H, int W, int Cin, int Cout, int kd, int kh, int kw) {
-  return auto_takes_rows_kernel(N, D, H, W, Cin, Cout, kd, kh, kw, 1) ? 1 : 0;
-}
 int dgmr_conv_umma_supported(int N, int D, int H, int W, int Cin, int Cout, int kd, int kh, int kw) {
   return umma_fwd_ok(N, D, H, W, Cin, Cout, kd, kh, kw, 1) ? 1 : 0;
 }
@@ -1998,7 +1989,8 @@ int dgmr_conv_fwd(const float* x, const float* x_lo, const float* wp, const floa
   // wide channels on small images (the 16x16 / 32x32 sampler layers, the per-step ConvGRU convolutions): whole-row tiles, CTA pairs sharing each
   // weight tile.  Measured (tests/time_patch16.py, time_pairconv.py): 768->768 @16^2 559 -> 834 TF/s, 192->192 @32^2 632 (patch) -> 679, ConvGRU
   // 16 x 16^2 192->384 39 -> 31 us; the halo-patch kernel keeps N = 96 layers and everything at 64^2 and above (activation traffic dominates there).
-  if (algo == DGMR_ALGO_AUTO && auto_takes_rows_kernel(N, D, H, W, Cin, Cout, kd, kh, kw, G))
+  if (algo == DGMR_ALGO_AUTO && g_opt.pairconv != 0 && W <= 32 && Cout >= 64 && umma_pairconv_ok(N, D, H, W, Cin, Cout, kd, kh, kw, G) &&
+      (Cin >= 192 || (int64_t)N * D * H * W <= 131072 || g_opt.pairconv == 1))
     return launch_conv_umma_pairconv(x, wp, bias, scale, res, y, N, D, H, W, Cin, Cout, kd, G, act, S(stream));
   if (algo == DGMR_ALGO_UMMA || algo == DGMR_ALGO_UMMA_PATCH || (algo == DGMR_ALGO_AUTO && ok)) {
     if (algo != DGMR_ALGO_UMMA && umma_patch_ok(N, D, H, W, Cin, Cout, kd, kh, kw, G) &&

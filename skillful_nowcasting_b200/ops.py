@@ -552,11 +552,7 @@ def _use_split_taps(n, d, h, w, cin, cout, taps, has_bias, act) -> bool:
     if not config.split_taps or taps == 1 or has_bias or act != ACT_NONE or config.conv_algo == ALGO_SIMT:
         return False
     tiles = ((n * d * h * w + 127) // 128) * ((cout + 255) // 256)
-    if not (tiles <= 32 and cin >= 32 and _be().name == "cuda" and _be().conv_umma_supported(n, d, h, w, cin, cout, 1, 3, 3)):   # measured crossover (tests/time_gru_conv.py)
-        return False
-    # the whole-row kernel takes 16-pixel-wide images with everything in its epilogue: 16 x 16^2 192->192 27 us there vs 31 us tap-split + the
-    # launch that pre-loads the residual
-    return not (taps == 9 and _be().conv_rows_supported(n, d, h, w, cin, cout, 1, 3, 3))
+    return tiles <= 32 and cin >= 32 and _be().name == "cuda" and _be().conv_umma_supported(n, d, h, w, cin, cout, 1, 3, 3)   # measured crossover (tests/time_gru_conv.py)
 
 
 def _pack_slot(w: torch.Tensor):

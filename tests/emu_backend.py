@@ -33,9 +33,6 @@ class EmuBackend:
     def conv_umma_supported(self, *a):
         return False
 
-    def conv_rows_supported(self, *a):
-        return False
-
     def wgrad_umma_supported(self, *a):
         return False
 
