@@ -469,6 +469,12 @@ def main():
     else:
         h2d, d2h = int(host_x.numel() + host_y.numel()) * 4, 12
         step_flops = flop_step(world * B, K)
+    # DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the launches captured with `ncu --set full` and committed under
+    # profiles/ (kernels_r02b_ncu.txt): reported for the dominant launch when it is one of them, else null
+    NCU_TRAFFIC = {("conv_umma", "32x22x64x64 48->48 k333 G1"): (553955328 + 520765184, "profiles/kernels_r02b_ncu.txt (column-stacked CTA-pair kernel; algorithmic: 553.6 MB in + 553.6 MB out)"),
+                   ("conv_umma", "288x1x64x64 96->96 k133 G18"): (908325120 + 424768256, "profiles/kernels_r02b_ncu.txt (CTA-pair halo-patch kernel; algorithmic: 453 MB in + 453 MB out + 453 MB residual)"),
+                   ("wgrad_umma", "288x1x16x16 768->768 k133"): (739300352 + 15547904, "profiles/kernels_r02b_ncu.txt (row wgrad; algorithmic: 226 MB x + 226 MB dz, read once per filter row)")}
+    top_traffic = NCU_TRAFFIC.get((top_tag, top_info.split(" (")[0].strip()))
     line = dict(
         metric=METRIC if not inference else "generated radar frames/sec (generator-only eval inference, 256x256, 4->18)",
         value=value, unit="frames/s", n_gpus=world, steps=args.steps, warmup=warm, ms_per_step=ms_per_step, higher_is_better=True,
@@ -484,7 +490,8 @@ def main():
         clocks=clocks,
         step_tflops=step_flops / (ms_per_step * 1e-3) / 1e12,
         roofline=dict(bound="tensor", kernel=f"{top_tag} {top_info} (tcgen05 kind::tf32 implicit GEMM; the tensor-core launch with the largest share of the step)",
-                      achieved=top_ach, peak=tf32_peak, unit="TFLOP/s", frac=top_ach / tf32_peak if tf32_peak else None, traffic=None,
+                      achieved=top_ach, peak=tf32_peak, unit="TFLOP/s", frac=top_ach / tf32_peak if tf32_peak else None,
+                      traffic=(top_traffic[0] if top_traffic else None), traffic_source=(top_traffic[1] if top_traffic else None),
                       launches_per_step=top_n, ms_per_launch=top_ms / max(top_n, 1), share_of_step=top_ms / instr_ms if instr_ms else None,
                       peak_source=f"{pk['source']} bf16 sustained {pk['bf16_sustained']} TF/s / 2 (TF32 pipe = half the bf16 rate)",
                       note="achieved = executed FLOPs of one launch (2*pixels*Cin*Cout*taps) / its mean CUDA-event duration inside the instrumented step; "
