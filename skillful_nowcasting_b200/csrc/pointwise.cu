@@ -141,6 +141,30 @@ __global__ void pool_sum_kernel(const float* __restrict__ x, float* __restrict__
     y[i] = s * scale;
   }
 }
+// single-channel images (the radar frames both discriminators average-pool first, ref: dgmr/discriminators.py:108,199): window 1x2x2, rows = N*D*H.
+// One thread per TWO output pixels: two float4 loads (rows 2h, 2h+1), one float2 store -- the generic kernel's four scalar loads and three 64-bit
+// div/mod pairs per pixel ran at a quarter of the memory rate.
+__global__ void pool_sum_c1_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t rows_out, int W, float scale) {
+  const int Wq = W >> 2;                       // float4 groups per input row = output pixel pairs per output row
+  const int64_t total = rows_out * Wq;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / Wq; const int q = (int)(i - r * Wq);
+    const float4 a = reinterpret_cast<const float4*>(x + (2 * r) * W)[q], b = reinterpret_cast<const float4*>(x + (2 * r + 1) * W)[q];
+    reinterpret_cast<float2*>(y + r * (W >> 1))[q] = make_float2((a.x + a.y + b.x + b.y) * scale, (a.z + a.w + b.z + b.w) * scale);
+  }
+}
+// its backward: x [rows, W] -> y [2*rows, 2W], every input pixel replicated 2x2 (times scale)
+__global__ void upsample_c1_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t rows_in, int W, float scale) {
+  const int Wh = W >> 1;                       // float2 groups per input row
+  const int64_t total = rows_in * Wh;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / Wh; const int q = (int)(i - r * Wh);
+    const float2 v = reinterpret_cast<const float2*>(x + r * W)[q];
+    const float4 o = make_float4(v.x * scale, v.x * scale, v.y * scale, v.y * scale);
+    reinterpret_cast<float4*>(y + (2 * r) * (2 * W))[q] = o;
+    reinterpret_cast<float4*>(y + (2 * r + 1) * (2 * W))[q] = o;
+  }
+}
 // y[n,do,ho,wo,c] = scale * x[n,do/ud,ho/uh,wo/uw,c] if inside x's replicated extent else 0
 __global__ void upsample_kernel(const float* __restrict__ x, float* __restrict__ y, int N, int D, int H, int W, int C,
                                 int ud, int uh, int uw, int Do, int Ho, int Wo, float scale) {
@@ -960,6 +984,12 @@ int dgmr_pool_sum(const float* x, float* y, int N, int D, int H, int W, int C, i
   DGMR_REQUIRE(pd >= 1 && ph >= 1 && pw >= 1 && pd <= 2 && ph <= 2 && pw <= 2, "dgmr_pool_sum: window must be 1 or 2");
   int64_t total = (int64_t)N * (D / pd) * (H / ph) * (W / pw) * C;
   if (total == 0) return 0;
+  if (C == 1 && pd == 1 && ph == 2 && pw == 2 && H % 2 == 0 && W % 4 == 0 && al16(x) && al16(y)) {
+    const int64_t rows_out = (int64_t)N * D * (H / 2);
+    pool_sum_c1_kernel<<<ew_grid(rows_out * (W / 4), 256, 1), 256, 0, S(stream)>>>(x, y, rows_out, W, scale);
+    DGMR_CHECK_LAUNCH("dgmr_pool_sum");
+    return 0;
+  }
   if (C % 4 == 0 && al16(x) && al16(y))
     if ((int64_t)N * D * H * W * C < (int64_t)1 << 31) pool_sum4_kernel<uint32_t><<<ew_grid(total / 4, 256, 1), 256, 0, S(stream)>>>((const float4*)x, (float4*)y, N, D, H, W, C / 4, pd, ph, pw, scale);
     else pool_sum4_kernel<int64_t><<<ew_grid(total / 4, 256, 1), 256, 0, S(stream)>>>((const float4*)x, (float4*)y, N, D, H, W, C / 4, pd, ph, pw, scale);
@@ -972,6 +1002,12 @@ int dgmr_upsample(const float* x, float* y, int N, int D, int H, int W, int C, i
   DGMR_REQUIRE(Do >= D * ud && Ho >= H * uh && Wo >= W * uw, "dgmr_upsample: output smaller than replicated input");
   int64_t total = (int64_t)N * Do * Ho * Wo * C;
   if (total == 0) return 0;
+  if (C == 1 && ud == 1 && uh == 2 && uw == 2 && Do == D && Ho == 2 * H && Wo == 2 * W && W % 2 == 0 && al16(x) && al16(y)) {
+    const int64_t rows_in = (int64_t)N * D * H;
+    upsample_c1_kernel<<<ew_grid(rows_in * (W / 2), 256, 1), 256, 0, S(stream)>>>(x, y, rows_in, W, scale);
+    DGMR_CHECK_LAUNCH("dgmr_upsample");
+    return 0;
+  }
   if (C % 4 == 0 && al16(x) && al16(y))
     if (total < (int64_t)1 << 31) upsample4_kernel<uint32_t><<<ew_grid(total / 4, 256, 1), 256, 0, S(stream)>>>((const float4*)x, (float4*)y, N, D, H, W, C / 4, ud, uh, uw, Do, Ho, Wo, scale);
     else upsample4_kernel<int64_t><<<ew_grid(total / 4, 256, 1), 256, 0, S(stream)>>>((const float4*)x, (float4*)y, N, D, H, W, C / 4, ud, uh, uw, Do, Ho, Wo, scale);

@@ -71,7 +71,8 @@ def test_pointwise(cuda_backend):
     _both("round_tf32", [torch.randn(n) * 100], cuda_backend, rtol=0, atol=0)   # cvt.rna.tf32.f32, bit-exact
 
 
-@pytest.mark.parametrize("dims,win", [((2, 1, 8, 12, 5), (1, 2, 2)), ((2, 5, 6, 6, 3), (2, 2, 2)), ((1, 22, 4, 4, 1), (1, 2, 2))])
+@pytest.mark.parametrize("dims,win", [((2, 1, 8, 12, 5), (1, 2, 2)), ((2, 5, 6, 6, 3), (2, 2, 2)), ((1, 22, 4, 4, 1), (1, 2, 2)),
+                                      ((3, 5, 16, 24, 1), (1, 2, 2)), ((2, 3, 6, 6, 1), (1, 2, 2))])   # single channel: float4 form / W % 4 != 0 fallback
 def test_pool_upsample(cuda_backend, dims, win):
     torch.manual_seed(2)
     n, d, h, w, c = dims
