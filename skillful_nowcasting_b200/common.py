@@ -103,7 +103,10 @@ class UpsampleGBlock(nn.Module):
     def sn_calls(self, G: int = 1):
         return [(self.conv_1x1, G), (self.first_conv_3x3, G), (self.last_conv_3x3, G)]
 
-    def run(self, x, G: int = 1):
+    def run(self, x, G: int = 1, round_out: bool = False):
+        """round_out: the block output is read by tensor-core convolutions only (the next sampler level's gate convolutions) and is written tf32-rounded
+        by last_conv_3x3's epilogue -- no rounding pass into a private copy.  (Its own backward then reduces <dY, Y - b - res> over the rounded Y: 2^-12
+        relative noise on a sum of millions of terms, far below the 1xTF32 operand rounding of every product in that sum.)"""
         # conv1x1(up2(x)) == up2(conv1x1(x)) bit-for-bit (pointwise conv commutes with replication): 4x fewer MACs, and the
         # upsampled shortcut is never materialised: last_conv_3x3's epilogue reads it at (h/2, w/2)
         # BN -> ReLU at LOW resolution; the nearest x2 upsampling (ref :148) is folded into first_conv_3x3's sub-pixel form (ops.upconv:
@@ -115,7 +118,7 @@ class UpsampleGBlock(nn.Module):
             y = ops.mark_conv_only(_conv_bn_relu_train(self.first_conv_3x3, self.bn2, y, G, up2=True))
         else:
             y = ops.mark_conv_only(_conv_bn_relu_eval(self.first_conv_3x3, self.bn2, y, G, up2=True))
-        return self.last_conv_3x3.run(y, G, res=sc, res_up2=True)
+        return self.last_conv_3x3.run(y, G, res=sc, res_up2=True, round_out=round_out)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         return ops.cl_to_nchw(self.run(ops.nchw_to_cl(x)))

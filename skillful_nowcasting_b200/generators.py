@@ -66,14 +66,14 @@ class Sampler(nn.Module, PyTorchModelHubMixin):
         hs = latent
         for lvl, (gru, c11, g, ug) in enumerate(levels):
             # level 0: identical latent input at every step and for every sample (generators.py:146-149)
-            # The level input is read by convolutions only, but above level 0 it is the block output its producer SAVED for backward
-            # (spectral-norm scale gradient): it is rounded into one private copy that both gate convs share.  The recurrence
-            # hands back the tf32-rounded copy of its outputs, which the 1x1 conv consumes as is.
+            # The level input is read by convolutions only: above level 0 it is the previous up-block's output, written tf32-rounded by that
+            # block's last epilogue (conv_operand passes it through; unrounded tensors get one private rounded copy that both gate convs share).
+            # The recurrence hands back the tf32-rounded copy of its outputs, which the 1x1 conv consumes as is.
             xin = ops.mark_conv_only(hs) if lvl == 0 else ops.conv_operand(hs)
             hs = gru.cell.run_sequence(xin, init_states[3 - lvl], T, shared_input=(lvl == 0), rounded_out=True)
             hs = c11.run(hs if getattr(hs, "_dgmr_tf32", False) else ops.mark_conv_only(hs), T)
             hs = g.run(hs, T)
-            hs = ug.run(hs, T)
+            hs = ug.run(hs, T, round_out=(lvl < 3))      # levels 0-2: read by the next level's gate convolutions only
         hs = ops.mark_conv_only(self.bn.run(hs, T, relu=True, conv_only=True))
         hs = self.conv_1x1.run(hs, T)  # [T*B,1,h,w,4*Co]
         _, _, h, w, c4 = hs.shape

@@ -503,7 +503,9 @@ class _ConvOperand(Function):
 
     @staticmethod
     def forward(ctx, x):
-        return _round_(_c(x).detach()) if _rounding_on() else x.view_as(x)
+        if not _rounding_on() or getattr(x, "_dgmr_tf32", False):     # already rounded by its producer's epilogue: pass through
+            return x.view_as(x)
+        return _round_(_c(x).detach())
 
     @staticmethod
     def backward(ctx, g):
@@ -511,7 +513,10 @@ class _ConvOperand(Function):
 
 
 def conv_operand(x):
-    return _ConvOperand.apply(x)
+    y = _ConvOperand.apply(x)
+    if getattr(x, "_dgmr_tf32", False):
+        y._dgmr_tf32 = True
+    return y
 
 
 def _rounding_on() -> bool:
