@@ -1,4 +1,4 @@
-TAILN=6 ./run_gpu_tests.sh parity
-b() { name=$1; shift; echo "=== bench $name"; DGMR_BENCH_DUMP=gpurun_out/shapes_$name.tsv timeout 600 python bench.py "$@" > gpurun_out/bench_$name.json 2> gpurun_out/bench_$name.err; echo "exit $?"; python -c "
-import json; d=json.load(open('gpurun_out/bench_$name.json')); print(d['value'], d['ms_per_step'], d['e2e']['value'], d['gpu_launches']); print({k:v for k,v in d['kernel_breakdown_ms'].items() if k in ('round_tf32','conv_umma')})"; tail -n 3 gpurun_out/bench_$name.err; }
-b c3s --steps 5 --warmup 3 --no-ref-gpu --no-cpu-baseline
+TAILN=8 ./run_gpu_tests.sh allv smoke
+b() { name=$1; shift; echo "=== bench $name"; timeout 1200 python bench.py "$@" > gpurun_out/bench_$name.json 2> gpurun_out/bench_$name.err; echo "exit $?"; python -c "
+import json; d=json.load(open('gpurun_out/bench_$name.json')); print({k:d.get(k) for k in ('value','ms_per_step','e2e','gpu_launches','clocks')}); print(d.get('reference_gpu_eager')); print(d.get('cpu_baseline')); print(d['roofline']['kernel'], d['roofline']['achieved'], d['roofline']['frac'], d['roofline']['traffic'])"; tail -n 2 gpurun_out/bench_$name.err; }
+b final2_default
