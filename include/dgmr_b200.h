@@ -110,11 +110,14 @@ int dgmr_upsample(const float* x, float* y, int N, int D, int H, int W, int C, i
 
 /* ---- ConvGRU gate arithmetic (ref: dgmr/layers/ConvGRU.py:72-82); `ld` = row pitch (floats) of the
  * pre-activation tensors so that r|u can live side by side in one [rows, 2*Ch] conv output. */
-/* flags & DGMR_FLAG_ROUND_TF32: rh (a conv-only operand) is emitted tf32-rounded */
-int dgmr_gru_gate_fwd(const float* pre_r, int ld, const float* h, float* rh, int64_t rows, int Ch, int flags, dgmr_stream_t stream);
+/* flags & DGMR_FLAG_ROUND_TF32: rh (a conv-only operand) is emitted tf32-rounded.
+ * x_r (nullable, pitch ld): the input-dependent part of the pre-activation (ConvGRU.py:66-70: the conv over cat(x, h) split by input
+ * channels); when given, pre_r holds only the h part, the sum is formed here AND written back to pre_r (the backward reads it). */
+int dgmr_gru_gate_fwd(float* pre_r, int ld, const float* x_r, const float* h, float* rh, int64_t rows, int Ch, int flags, dgmr_stream_t stream);
 /* relu_c != 0: `c` holds the candidate pre-activation and relu is applied here (ref: ConvGRU.py:81) */
 /* hnew_tf32 (nullable): tf32-rounded copy of hnew = the next step's conv operand */
-int dgmr_gru_blend_fwd(const float* pre_u, int ld, const float* h, const float* c, float* hnew, float* hnew_tf32,
+/* x_u (pitch ld) / x_c (dense), nullable: as x_r above, for the update gate and the candidate; pre_u / c are completed in place */
+int dgmr_gru_blend_fwd(float* pre_u, int ld, const float* x_u, const float* h, float* c, const float* x_c, float* hnew, float* hnew_tf32,
                        int64_t rows, int Ch, int relu_c, dgmr_stream_t stream);
 /* d_rh -> d_pre_r, dh (+= if accumulate).  dz_scale [Ch] / dz (nullable, leading dimension ldd like d_pre_r): additionally dz = d_pre_r * dz_scale[c]
  * (tf32-rounded if dz_round) -- the recurrent convolution's backward operand, so the walk over the steps needs no dgmr_conv_bwd_prep per step */

@@ -212,12 +212,12 @@ class CudaBackend:
         self._call("dgmr_upsample", _f32(x, "x"), _f32(y, "y"), N, D, H, W, C, ud, uh, uw, Do, Ho, Wo, float(scale), _info=f"{N}x{D}x{H}x{W}x{C} *{ud}{uh}{uw}")
 
     # -- GRU
-    def gru_gate_fwd(self, pre_r, ld, h, rh, rows, Ch, flags=0):
-        self._call("dgmr_gru_gate_fwd", _f32(pre_r, "pre_r"), ld, _f32(h, "h"), _f32(rh, "rh"), rows, Ch, int(flags))
+    def gru_gate_fwd(self, pre_r, ld, h, rh, rows, Ch, flags=0, x_r=None):
+        self._call("dgmr_gru_gate_fwd", _f32(pre_r, "pre_r"), ld, _f32(x_r, "x_r"), _f32(h, "h"), _f32(rh, "rh"), rows, Ch, int(flags))
 
-    def gru_blend_fwd(self, pre_u, ld, h, c, hnew, hnew_tf32, rows, Ch, relu_c=False):
-        self._call("dgmr_gru_blend_fwd", _f32(pre_u, "pre_u"), ld, _f32(h, "h"), _f32(c, "c"), _f32(hnew, "hnew"), _f32(hnew_tf32, "hnew_tf32"),
-                   rows, Ch, int(relu_c))
+    def gru_blend_fwd(self, pre_u, ld, h, c, hnew, hnew_tf32, rows, Ch, relu_c=False, x_u=None, x_c=None):
+        self._call("dgmr_gru_blend_fwd", _f32(pre_u, "pre_u"), ld, _f32(x_u, "x_u"), _f32(h, "h"), _f32(c, "c"), _f32(x_c, "x_c"), _f32(hnew, "hnew"),
+                   _f32(hnew_tf32, "hnew_tf32"), rows, Ch, int(relu_c))
 
     def gru_gate_bwd(self, d_rh, pre_r, ld, h, d_pre_r, ldd, dh, accumulate, rows, Ch, dz_scale=None, dz=None, dz_round=False):
         self._call("dgmr_gru_gate_bwd", _f32(d_rh, "d_rh"), _f32(pre_r, "pre_r"), ld, _f32(h, "h"), _f32(d_pre_r, "d_pre_r"), ldd,

@@ -637,9 +637,33 @@ __global__ void sn_bwd_kernel(const float* __restrict__ dis, const float* __rest
 }
 constexpr int kSnBwdMaxItems = 48;
 struct SnBwdMultiArgs { dgmr_sn_bwd_item it[kSnBwdMaxItems]; };
-// the rank-G corrections of many weights in one launch: blockIdx.y = weight
-__global__ void sn_bwd_multi_kernel(const __grid_constant__ SnBwdMultiArgs a) {
+// the rank-G corrections of many weights in one launch: blockIdx.y = weight.  dw[r][k] (+)= sum_g coef[g] * u_g[r] * v_g[k]: the per-call
+// coefficients sit in shared memory and each thread owns four consecutive k (one 16-byte access of dw and of every v_g) -- the pass should cost
+// about one read + one write of dw
+constexpr int kSnBwdMaxG = 64;
+__global__ void __launch_bounds__(256) sn_bwd_multi_kernel(const __grid_constant__ SnBwdMultiArgs a) {
   const dgmr_sn_bwd_item& t = a.it[blockIdx.y];
+  __shared__ float coef[kSnBwdMaxG];
+  const bool fast = t.G <= kSnBwdMaxG && (t.K & 3) == 0 && ((reinterpret_cast<uintptr_t>(t.dw) | reinterpret_cast<uintptr_t>(t.v_hist)) & 15) == 0;
+  if (fast) {
+    for (int g = threadIdx.x; g < t.G; g += blockDim.x) { const float is = t.inv_sigma[g]; coef[g] = -t.d_inv_sigma[g] * is * is; }
+    __syncthreads();
+    const int K4 = t.K >> 2;
+    const int64_t total4 = (int64_t)t.R * K4;
+    float4* dw4 = reinterpret_cast<float4*>(t.dw);
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
+      const int r = (int)(i / K4), k4 = (int)(i - (int64_t)r * K4);
+      float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int g = 0; g < t.G; ++g) {
+        const float c = coef[g] * t.u_hist[(int64_t)g * t.R + r];
+        const float4 v = reinterpret_cast<const float4*>(t.v_hist + (int64_t)g * t.K)[k4];
+        s.x += c * v.x; s.y += c * v.y; s.z += c * v.z; s.w += c * v.w;
+      }
+      if (t.accumulate) { const float4 o = dw4[i]; s.x = o.x + s.x; s.y = o.y + s.y; s.z = o.z + s.z; s.w = o.w + s.w; }
+      dw4[i] = s;
+    }
+    return;
+  }
   const int64_t total = (int64_t)t.R * t.K;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int k = (int)(i % t.K), r = (int)(i / t.K);

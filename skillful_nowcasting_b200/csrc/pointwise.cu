@@ -224,43 +224,55 @@ __global__ void upsample4_kernel(const float4* __restrict__ x, float4* __restric
 
 // ------------------------------------------------------------------ ConvGRU gates (ref: dgmr/layers/ConvGRU.py:72-82)
 __device__ __forceinline__ float sigmoid_acc(float v) { return 1.0f / (1.0f + expf(-v)); }   // full-accuracy expf (parity with the oracle)
-__global__ void gru_gate_fwd_kernel(const float* __restrict__ pre_r, int ld, const float* __restrict__ h, float* __restrict__ rh, int64_t rows, int Ch, int rnd) {
+// xr / xu / xc (nullable, same pitch as the pre-activation they belong to): the input-dependent part of the pre-activation, added HERE and the sum
+// written back (the backward reads the complete pre-activation) -- the tap-split convolution then accumulates into a zeroed buffer and the
+// per-step copy of the x part (one launch per convolution and step) disappears
+__global__ void gru_gate_fwd_kernel(float* __restrict__ pre_r, int ld, const float* __restrict__ xr, const float* __restrict__ h, float* __restrict__ rh, int64_t rows, int Ch, int rnd) {
   int64_t total = rows * Ch;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     int64_t r = i / Ch; int c = i - r * Ch;
-    float v = sigmoid_acc(pre_r[r * ld + c]) * h[i];
+    float p = pre_r[r * ld + c];
+    if (xr) { p += xr[r * ld + c]; pre_r[r * ld + c] = p; }
+    float v = sigmoid_acc(p) * h[i];
     rh[i] = rnd ? rna_tf32_pw(v) : v;
   }
 }
-__global__ void gru_gate_fwd4_kernel(const float* __restrict__ pre_r, int ld, const float4* __restrict__ h, float4* __restrict__ rh, int64_t rows, int C4, int rnd) {
+__device__ __forceinline__ float4 add4(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+__global__ void gru_gate_fwd4_kernel(float* __restrict__ pre_r, int ld, const float* __restrict__ xr, const float4* __restrict__ h, float4* __restrict__ rh, int64_t rows, int C4, int rnd) {
   int64_t total = rows * C4;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     int64_t r = i / C4; int c = i - r * C4;
     float4 p = *reinterpret_cast<const float4*>(pre_r + r * ld + 4 * c), hv = h[i];
+    if (xr) { p = add4(p, *reinterpret_cast<const float4*>(xr + r * ld + 4 * c)); *reinterpret_cast<float4*>(pre_r + r * ld + 4 * c) = p; }
     float4 v = make_float4(sigmoid_acc(p.x) * hv.x, sigmoid_acc(p.y) * hv.y, sigmoid_acc(p.z) * hv.z, sigmoid_acc(p.w) * hv.w);
     if (rnd) v = make_float4(rna_tf32_pw(v.x), rna_tf32_pw(v.y), rna_tf32_pw(v.z), rna_tf32_pw(v.w));
     rh[i] = v;
   }
 }
-__global__ void gru_blend_fwd_kernel(const float* __restrict__ pre_u, int ld, const float* __restrict__ h, const float* __restrict__ c_, float* __restrict__ hn,
-                                     float* __restrict__ hn_tf32, int64_t rows, int Ch, int relu_c) {
+__global__ void gru_blend_fwd_kernel(float* __restrict__ pre_u, int ld, const float* __restrict__ xu, const float* __restrict__ h, float* __restrict__ c_,
+                                     const float* __restrict__ xc, float* __restrict__ hn, float* __restrict__ hn_tf32, int64_t rows, int Ch, int relu_c) {
   int64_t total = rows * Ch;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     int64_t r = i / Ch; int c = i - r * Ch;
-    float u = sigmoid_acc(pre_u[r * ld + c]);
+    float p = pre_u[r * ld + c];
+    if (xu) { p += xu[r * ld + c]; pre_u[r * ld + c] = p; }
+    float u = sigmoid_acc(p);
     float cv = c_[i];
+    if (xc) { cv += xc[i]; c_[i] = cv; }
     if (relu_c) cv = fmaxf(cv, 0.f);
     float v = u * h[i] + (1.0f - u) * cv;
     hn[i] = v;
     if (hn_tf32) hn_tf32[i] = rna_tf32_pw(v);
   }
 }
-__global__ void gru_blend_fwd4_kernel(const float* __restrict__ pre_u, int ld, const float4* __restrict__ h, const float4* __restrict__ c_, float4* __restrict__ hn,
-                                      float4* __restrict__ hn_tf32, int64_t rows, int C4, int relu_c) {
+__global__ void gru_blend_fwd4_kernel(float* __restrict__ pre_u, int ld, const float* __restrict__ xu, const float4* __restrict__ h, float4* __restrict__ c_,
+                                      const float4* __restrict__ xc, float4* __restrict__ hn, float4* __restrict__ hn_tf32, int64_t rows, int C4, int relu_c) {
   int64_t total = rows * C4;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     int64_t r = i / C4; int c = i - r * C4;
     float4 p = *reinterpret_cast<const float4*>(pre_u + r * ld + 4 * c), hv = h[i], cv = c_[i];
+    if (xu) { p = add4(p, *reinterpret_cast<const float4*>(xu + r * ld + 4 * c)); *reinterpret_cast<float4*>(pre_u + r * ld + 4 * c) = p; }
+    if (xc) { cv = add4(cv, xc[i]); c_[i] = cv; }
     if (relu_c) cv = make_float4(fmaxf(cv.x, 0.f), fmaxf(cv.y, 0.f), fmaxf(cv.z, 0.f), fmaxf(cv.w, 0.f));
     float ux = sigmoid_acc(p.x), uy = sigmoid_acc(p.y), uz = sigmoid_acc(p.z), uw = sigmoid_acc(p.w);
     float4 v = make_float4(ux * hv.x + (1.0f - ux) * cv.x, uy * hv.y + (1.0f - uy) * cv.y, uz * hv.z + (1.0f - uz) * cv.z, uw * hv.w + (1.0f - uw) * cv.w);
@@ -392,36 +404,50 @@ __global__ void bn_stats4_kernel(const float4* __restrict__ x, double* __restric
     __syncthreads();
   }
 }
-__global__ void bn_finalize_kernel(const double* __restrict__ sums, const float* __restrict__ gamma, const float* __restrict__ beta,
+// block = 32 channels x 8 group lanes: the per-(group, channel) statistics (fp64 divisions) of all G groups are formed in parallel, then one lane per
+// channel walks the running-statistics recurrence in group order (the reference's G successive module calls) over the values parked in shared memory
+__global__ void __launch_bounds__(256) bn_finalize_kernel(const double* __restrict__ sums, const float* __restrict__ gamma, const float* __restrict__ beta,
                                    float* __restrict__ rmean, float* __restrict__ rvar, int64_t rows, int G, int C, float eps, float mom, int training,
                                    float* __restrict__ mean, float* __restrict__ invstd, float* __restrict__ a, float* __restrict__ b) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  float ga = gamma ? gamma[c] : 1.f, be = beta ? beta[c] : 0.f;
-  float rm = rmean[c], rv = rvar[c];
-  for (int g = 0; g < G; ++g) {
-    float m, is;
-    if (training) {
-      double s = sums[((int64_t)g * C + c) * 2], q = sums[((int64_t)g * C + c) * 2 + 1];
-      double md = s / (double)rows;
-      double vd = q / (double)rows - md * md;
-      if (vd < 0) vd = 0;
-      m = (float)md;
-      float var = (float)vd;
-      is = 1.0f / sqrtf(var + eps);
-      float unb = rows > 1 ? (float)(vd * (double)rows / (double)(rows - 1)) : var;
-      rm = (1.f - mom) * rm + mom * m;
-      rv = (1.f - mom) * rv + mom * unb;
-    } else {
-      m = rm;
-      is = 1.0f / sqrtf(rv + eps);
+  extern __shared__ float fin_sh[];                      // [G][32] batch means, [G][32] unbiased variances
+  const int cl = threadIdx.x & 31, gl = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
+  const bool live = c < C;
+  const float ga = (live && gamma) ? gamma[c] : 1.f, be = (live && beta) ? beta[c] : 0.f;
+  const float rm0 = live ? rmean[c] : 0.f, rv0 = live ? rvar[c] : 1.f;
+  if (live) {
+    for (int g = gl; g < G; g += 8) {
+      float m, is;
+      if (training) {
+        const double s = sums[((int64_t)g * C + c) * 2], q = sums[((int64_t)g * C + c) * 2 + 1];
+        const double md = s / (double)rows;
+        double vd = q / (double)rows - md * md;
+        if (vd < 0) vd = 0;
+        m = (float)md;
+        const float var = (float)vd;
+        is = 1.0f / sqrtf(var + eps);
+        fin_sh[g * 32 + cl] = m;
+        fin_sh[(G + g) * 32 + cl] = rows > 1 ? (float)(vd * (double)rows / (double)(rows - 1)) : var;
+      } else {
+        m = rm0;
+        is = 1.0f / sqrtf(rv0 + eps);
+      }
+      const int64_t o = (int64_t)g * C + c;
+      mean[o] = m; invstd[o] = is;
+      const float aa = ga * is;
+      a[o] = aa; b[o] = be - m * aa;
     }
-    int64_t o = (int64_t)g * C + c;
-    mean[o] = m; invstd[o] = is;
-    float aa = ga * is;
-    a[o] = aa; b[o] = be - m * aa;
   }
-  if (training) { rmean[c] = rm; rvar[c] = rv; }
+  if (!training) return;
+  __syncthreads();
+  if (live && gl == 0) {
+    float rm = rm0, rv = rv0;
+    for (int g = 0; g < G; ++g) {
+      rm = (1.f - mom) * rm + mom * fin_sh[g * 32 + cl];
+      rv = (1.f - mom) * rv + mom * fin_sh[(G + g) * 32 + cl];
+    }
+    rmean[c] = rm; rvar[c] = rv;
+  }
 }
 // y = act(a*x+b), optional nearest x2 upsample on write.  One thread per output element.
 __global__ void bn_apply_kernel(const float* __restrict__ x, const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ y,
@@ -1016,23 +1042,24 @@ int dgmr_upsample(const float* x, float* y, int N, int D, int H, int W, int C, i
   DGMR_CHECK_LAUNCH("dgmr_upsample");
   return 0;
 }
-int dgmr_gru_gate_fwd(const float* pre_r, int ld, const float* h, float* rh, int64_t rows, int Ch, int flags, dgmr_stream_t stream) {
+int dgmr_gru_gate_fwd(float* pre_r, int ld, const float* x_r, const float* h, float* rh, int64_t rows, int Ch, int flags, dgmr_stream_t stream) {
   int64_t n = rows * Ch; if (n == 0) return 0;
   const int rnd = (flags & DGMR_FLAG_ROUND_TF32) ? 1 : 0;
-  if (Ch % 4 == 0 && ld % 4 == 0 && al16(pre_r) && al16(h) && al16(rh))
-    gru_gate_fwd4_kernel<<<ew_grid(n / 4, 256, 1), 256, 0, S(stream)>>>(pre_r, ld, (const float4*)h, (float4*)rh, rows, Ch / 4, rnd);
+  if (Ch % 4 == 0 && ld % 4 == 0 && al16(pre_r) && al16(x_r) && al16(h) && al16(rh))
+    gru_gate_fwd4_kernel<<<ew_grid(n / 4, 256, 1), 256, 0, S(stream)>>>(pre_r, ld, x_r, (const float4*)h, (float4*)rh, rows, Ch / 4, rnd);
   else
-    gru_gate_fwd_kernel<<<ew_grid(n, 256, 2), 256, 0, S(stream)>>>(pre_r, ld, h, rh, rows, Ch, rnd);
+    gru_gate_fwd_kernel<<<ew_grid(n, 256, 2), 256, 0, S(stream)>>>(pre_r, ld, x_r, h, rh, rows, Ch, rnd);
   DGMR_CHECK_LAUNCH("dgmr_gru_gate_fwd");
   return 0;
 }
-int dgmr_gru_blend_fwd(const float* pre_u, int ld, const float* h, const float* c, float* hnew, float* hnew_tf32, int64_t rows, int Ch, int relu_c,
-                       dgmr_stream_t stream) {
+int dgmr_gru_blend_fwd(float* pre_u, int ld, const float* x_u, const float* h, float* c, const float* x_c, float* hnew, float* hnew_tf32, int64_t rows, int Ch,
+                       int relu_c, dgmr_stream_t stream) {
   int64_t n = rows * Ch; if (n == 0) return 0;
-  if (Ch % 4 == 0 && ld % 4 == 0 && al16(pre_u) && al16(h) && al16(c) && al16(hnew) && al16(hnew_tf32))
-    gru_blend_fwd4_kernel<<<ew_grid(n / 4, 256, 1), 256, 0, S(stream)>>>(pre_u, ld, (const float4*)h, (const float4*)c, (float4*)hnew, (float4*)hnew_tf32, rows, Ch / 4, relu_c);
+  if (Ch % 4 == 0 && ld % 4 == 0 && al16(pre_u) && al16(x_u) && al16(h) && al16(c) && al16(x_c) && al16(hnew) && al16(hnew_tf32))
+    gru_blend_fwd4_kernel<<<ew_grid(n / 4, 256, 1), 256, 0, S(stream)>>>(pre_u, ld, x_u, (const float4*)h, (float4*)c, (const float4*)x_c, (float4*)hnew,
+                                                                         (float4*)hnew_tf32, rows, Ch / 4, relu_c);
   else
-    gru_blend_fwd_kernel<<<ew_grid(n, 256, 2), 256, 0, S(stream)>>>(pre_u, ld, h, c, hnew, hnew_tf32, rows, Ch, relu_c);
+    gru_blend_fwd_kernel<<<ew_grid(n, 256, 2), 256, 0, S(stream)>>>(pre_u, ld, x_u, h, c, x_c, hnew, hnew_tf32, rows, Ch, relu_c);
   DGMR_CHECK_LAUNCH("dgmr_gru_blend_fwd");
   return 0;
 }
@@ -1076,7 +1103,9 @@ int dgmr_bn_stats(const float* x, double* sums, int64_t rows, int G, int C, dgmr
 }
 int dgmr_bn_finalize(const double* sums, const float* gamma, const float* beta, float* running_mean, float* running_var, int64_t rows, int G, int C,
                      float eps, float momentum, int training, float* mean, float* invstd, float* a, float* b, dgmr_stream_t stream) {
-  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, S(stream)>>>(sums, gamma, beta, running_mean, running_var, rows, G, C, eps, momentum, training, mean, invstd, a, b);
+  DGMR_REQUIRE(G >= 1 && G <= 128, "dgmr_bn_finalize: G out of range (1..128)");
+  bn_finalize_kernel<<<(C + 31) / 32, 256, sizeof(float) * 2 * G * 32, S(stream)>>>(sums, gamma, beta, running_mean, running_var, rows, G, C, eps, momentum, training, mean,
+                                                                                    invstd, a, b);
   DGMR_CHECK_LAUNCH("dgmr_bn_finalize");
   return 0;
 }

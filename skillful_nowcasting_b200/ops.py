@@ -36,6 +36,9 @@ class config:
     split_taps = True
     # ConvGRU: fused read|update gate conv + whole recurrence as one autograd node (False: the per-step reference wiring)
     gru_sequence = True
+    # ... in the tap-split mode its step convolutions accumulate into buffers zeroed once per sequence and the gate kernels add the x parts
+    # (False: one copy of the x part per convolution and step)
+    gru_defer_x = True
     # "nearest x2 -> 3x3 conv" in sub-pixel form (csrc/conv_subpix.cu) wherever the tensor-core kernels serve the shape (1xTF32 mode)
     upconv = True
     # 3x3x3 weight gradients of narrow layers with the depth taps folded into the channel axis (see _Conv.backward)
@@ -673,18 +676,29 @@ def clear_pack_cache():
     _packed_params.clear()
 
 
-def _conv_launch(x, wp, bias, scale, res, y, n, d, h, wd, c, cout, kd, kh, kw, G, act):
+def _takes_split_taps(n, d, h, wd, c, cout, kd, kh, kw, has_bias, act, has_lo) -> bool:
+    """Whether `_conv_launch` serves this call in the tap-split accumulate mode (callers that pre-zero the output ask first)."""
+    return _use_split_taps(n, d, h, wd, c, cout, kd * kh * kw, has_bias, act) and _be().conv_umma_supported(n, d, h, wd, c, cout, kd, kh, kw) \
+        and (config.precision == PREC_TF32 or has_lo)   # (any epilogue flag in `act` makes act != ACT_NONE: no tap split)
+
+
+def _conv_launch(x, wp, bias, scale, res, y, n, d, h, wd, c, cout, kd, kh, kw, G, act, y_is_zero=False):
     """y = act(conv(x, wp) * scale + bias + res) through the C ABI; picks the tap-split accumulate mode for launches that
     would otherwise leave most SMs idle.  `res` may alias `y` (each element is read, then written, by the same thread).
-    wp of shape [2, n] is a 3xTF32 (hi, lo) pair (parity mode): x is split the same way here."""
+    wp of shape [2, n] is a 3xTF32 (hi, lo) pair (parity mode): x is split the same way here.
+    y_is_zero: the caller zeroed `y` (one fill for a whole sequence of calls) after `_takes_split_taps` said the accumulate mode applies."""
     be = _be()
     x_lo = wp_lo = None
     if wp.dim() == 2:
         wp, wp_lo = wp[0], wp[1]
         x, x_lo = _split(x)
-    if _use_split_taps(n, d, h, wd, c, cout, kd * kh * kw, bias is not None, act) and be.conv_umma_supported(n, d, h, wd, c, cout, kd, kh, kw) \
-            and (config.precision == PREC_TF32 or x_lo is not None):   # (any epilogue flag in `act` makes act != ACT_NONE: no tap split)
-        if res is None:
+    split = _takes_split_taps(n, d, h, wd, c, cout, kd, kh, kw, bias is not None, act, x_lo is not None)
+    if y_is_zero and not (split and res is None):
+        raise RuntimeError("dgmr_b200: _conv_launch(y_is_zero=True) outside the tap-split accumulate mode")
+    if split:
+        if y_is_zero:
+            pass
+        elif res is None:
             be.fill(y, 0.0)
         elif res.data_ptr() != y.data_ptr():
             be.axpby(1.0, res, 0.0, None, y)   # y starts as the residual, the taps accumulate on top
@@ -1217,8 +1231,12 @@ class _GruSequence(Function):
         wp_ru = packed_weight(w_ru, cx, ch, FLAG_SPLIT if x3 else rnd_ru)
         wp_c = packed_weight(w_c, cx, ch, FLAG_SPLIT if x3 else rnd_c)
         out = _new((T * B, 1, H, W, ch), h0)
-        pru = _new((T * B, 1, H, W, 2 * ch), h0)
-        cp = _new((T * B, 1, H, W, ch), h0)
+        # tap-split accumulate mode (the small levels): the convolutions add into pre-zeroed buffers (ONE fill per sequence) and the gate kernels add
+        # the x parts and write the complete pre-activations back -- instead of one copy of the x part per convolution and step
+        defer_ru = config.gru_defer_x and _takes_split_taps(B, 1, H, W, ch, 2 * ch, 1, 3, 3, False, ACT_NONE, x3)
+        defer_c = config.gru_defer_x and _takes_split_taps(B, 1, H, W, ch, ch, 1, 3, 3, False, ACT_NONE, x3)
+        pru = (_zeros if defer_ru else _new)((T * B, 1, H, W, 2 * ch), h0)
+        cp = (_zeros if defer_c else _new)((T * B, 1, H, W, ch), h0)
         rh = _new((T * B, 1, H, W, ch), h0)
         # conv operand of step t = h_{t-1}; when the tensor-core path rounds operands it reads a rounded private copy (the gate
         # arithmetic must see the unrounded state), written by the previous step's blend kernel
@@ -1227,16 +1245,18 @@ class _GruSequence(Function):
         hop = _new(((T + 1) * B, 1, H, W, ch), h0) if rnd_ru else None
         if rnd_ru:
             be.round_tf32(h0, hop[0:B])
-        pru_flat = pru.view(-1)
+        pru_flat, xru_flat = pru.view(-1), xru.view(-1)
         for t in range(T):
             sl = slice(t * B, (t + 1) * B)
             h_prev = h0 if t == 0 else out[(t - 1) * B:t * B]
             a = hop[sl] if rnd_ru else h_prev
-            _conv_launch(a, wp_ru, None, s_ru[t:t + 1], xru[sl], pru[sl], B, 1, H, W, ch, 2 * ch, 1, 3, 3, 1, ACT_NONE)
-            be.gru_gate_fwd(pru[sl], 2 * ch, h_prev, rh[sl], rows, ch, rnd_c)
-            _conv_launch(rh[sl], wp_c, None, s_c[t:t + 1], xc[sl], cp[sl], B, 1, H, W, ch, ch, 1, 3, 3, 1, ACT_NONE)
+            off_u = t * rows * 2 * ch + ch
+            _conv_launch(a, wp_ru, None, s_ru[t:t + 1], None if defer_ru else xru[sl], pru[sl], B, 1, H, W, ch, 2 * ch, 1, 3, 3, 1, ACT_NONE, y_is_zero=defer_ru)
+            be.gru_gate_fwd(pru[sl], 2 * ch, h_prev, rh[sl], rows, ch, rnd_c, x_r=xru[sl] if defer_ru else None)
+            _conv_launch(rh[sl], wp_c, None, s_c[t:t + 1], None if defer_c else xc[sl], cp[sl], B, 1, H, W, ch, ch, 1, 3, 3, 1, ACT_NONE, y_is_zero=defer_c)
             nxt = hop[(t + 1) * B:(t + 2) * B] if rnd_ru else None
-            be.gru_blend_fwd(pru_flat[t * rows * 2 * ch + ch:], 2 * ch, h_prev, cp[sl], out[sl], nxt, rows, ch, True)
+            be.gru_blend_fwd(pru_flat[off_u:], 2 * ch, h_prev, cp[sl], out[sl], nxt, rows, ch, True,
+                             x_u=xru_flat[off_u:] if defer_ru else None, x_c=xc[sl] if defer_c else None)
         ctx.save_for_backward(xru, xc, h0, w_ru, w_c, s_ru, s_c, out, pru, cp, rh, hop)
         ctx.meta = (T, cx, bool(rnd_c))
         if rnd_ru:
@@ -1270,7 +1290,9 @@ class _GruSequence(Function):
         dxru, dzru = torch.empty_like(pru), torch.empty_like(pru)
         dxc, dzc = torch.empty_like(cp), torch.empty_like(cp)
         ds_ru, ds_c = _new((T, 2 * ch), h0), _new((T, ch), h0)
-        drh = _new(h0.shape, h0)
+        # d(r h) of each step: in the tap-split accumulate mode one pre-zeroed buffer for all steps (ONE fill), else a single reused slot
+        defer_rh = config.gru_defer_x and _takes_split_taps(B, 1, H, W, ch, ch, 1, 3, 3, False, ACT_NONE, x3)
+        drh_all = _zeros((T * B, 1, H, W, ch), h0) if defer_rh else _new(h0.shape, h0)
         pru_flat, dxru_flat = pru.view(-1), dxru.view(-1)
         rnd_ru = rnd_c = bool(tc_dg_ru or tc_wg_ru or tc_dg_c or tc_wg_c)     # (both convolutions have Ch input channels: served alike)
         dzru_flat = dzru.view(-1)
@@ -1284,7 +1306,8 @@ class _GruSequence(Function):
             # reduced in ONE grouped pass per weight after the loop)
             be.gru_blend_bwd(gh[sl], pru_flat[off + ch:], 2 * ch, h_prev, cp[sl], dxru_flat[off + ch:], 2 * ch, dxc[sl], tgt, t > 0, rows, ch, True,
                              dz_u_scale=s_ru[t, ch:], dz_u=dzru_flat[off + ch:], dz_c_scale=s_c[t], dz_c=dzc[sl], dz_round=rnd_c)
-            _conv_launch(dzc[sl], wpt_c, None, None, None, drh, B, 1, H, W, ch, ch, 1, 3, 3, 1, ACT_NONE)
+            drh = drh_all[sl] if defer_rh else drh_all
+            _conv_launch(dzc[sl], wpt_c, None, None, None, drh, B, 1, H, W, ch, ch, 1, 3, 3, 1, ACT_NONE, y_is_zero=defer_rh)
             # rh = r h:  d pre_r -> dxru[:, :ch], r * drh added to tgt
             be.gru_gate_bwd(drh, pru[sl], 2 * ch, h_prev, dxru[sl], 2 * ch, tgt, True, rows, ch, dz_scale=s_ru[t, :ch], dz=dzru[sl], dz_round=rnd_ru)
             _conv_launch(dzru[sl], wpt_ru, None, None, tgt, tgt, B, 1, H, W, 2 * ch, ch, 1, 3, 3, 1, ACT_NONE)

@@ -93,15 +93,23 @@ class EmuBackend:
         y.copy_(out.reshape(y.shape))
 
     # ---- GRU
-    def gru_gate_fwd(self, pre_r, ld, h, rh, rows, Ch, flags=0):
-        g = torch.sigmoid(_rows(pre_r, rows, ld, Ch))
+    def gru_gate_fwd(self, pre_r, ld, h, rh, rows, Ch, flags=0, x_r=None):
+        pre = _rows(pre_r, rows, ld, Ch)
+        if x_r is not None:
+            pre += _rows(x_r, rows, ld, Ch)     # completed in place (a view of pre_r)
+        g = torch.sigmoid(pre)
         v = g * h.reshape(rows, Ch)
         if flags & 256:
             v = self._rna_tf32(v)
         rh.copy_(v.reshape(rh.shape))
 
-    def gru_blend_fwd(self, pre_u, ld, h, c, hnew, hnew_tf32, rows, Ch, relu_c=False):
-        u = torch.sigmoid(_rows(pre_u, rows, ld, Ch))
+    def gru_blend_fwd(self, pre_u, ld, h, c, hnew, hnew_tf32, rows, Ch, relu_c=False, x_u=None, x_c=None):
+        pre = _rows(pre_u, rows, ld, Ch)
+        if x_u is not None:
+            pre += _rows(x_u, rows, ld, Ch)
+        if x_c is not None:
+            c += x_c.reshape(c.shape)
+        u = torch.sigmoid(pre)
         cv = torch.relu(c.reshape(rows, Ch)) if relu_c else c.reshape(rows, Ch)
         v = u * h.reshape(rows, Ch) + (1 - u) * cv
         hnew.copy_(v.reshape(hnew.shape))

@@ -17,7 +17,7 @@ def _both(method, args, cuda_backend, rtol=1e-5, atol=1e-6, kwargs=None, check=N
     a_cpu = [a.clone() if torch.is_tensor(a) else a for a in args]
     a_gpu = [a.cuda() if torch.is_tensor(a) else a for a in args]
     getattr(emu, method)(*a_cpu, **kwargs)
-    getattr(cuda_backend, method)(*a_gpu, **kwargs)
+    getattr(cuda_backend, method)(*a_gpu, **{k: (v.cuda() if torch.is_tensor(v) else v) for k, v in kwargs.items()})
     torch.cuda.synchronize()
     for i, (c, g) in enumerate(zip(a_cpu, a_gpu)):
         if torch.is_tensor(c) and (check is None or i in check):
@@ -96,6 +96,13 @@ def test_gru_pointwise(cuda_backend):
         _both("gru_blend_bwd", [g, pre, ch, h, c, torch.empty(rows, ch), ch, torch.empty(rows, ch), torch.empty(rows, ch), False, rows, ch, relu_c],
               cuda_backend, atol=1e-6)
     _both("gru_gate_bwd", [g, pre, ch, h, torch.empty(rows, ch), ch, torch.empty(rows, ch), False, rows, ch], cuda_backend, atol=1e-6)
+    # deferred x part: pre-activation = (h part, in the buffer) + (x part), completed in place; r | u side by side (pitch 2 ch) and an odd width
+    for chx in (24, 7):
+        pru, xru, hh, cc, xcc = torch.randn(rows, 2 * chx), torch.randn(rows, 2 * chx), torch.randn(rows, chx), torch.randn(rows, chx), torch.randn(rows, chx)
+        _both("gru_gate_fwd", [pru, 2 * chx, hh, torch.empty(rows, chx), rows, chx, 0], cuda_backend, atol=1e-6, kwargs=dict(x_r=xru))
+        for x_u, x_c in ((xru.view(-1)[chx:], xcc), (None, xcc), (xru.view(-1)[chx:], None)):
+            _both("gru_blend_fwd", [pru.view(-1)[chx:].clone(), 2 * chx, hh, cc, torch.empty(rows, chx), torch.empty(rows, chx), rows, chx, True], cuda_backend,
+                  atol=2e-6, kwargs=dict(x_u=x_u, x_c=x_c), check=(0, 3, 4))
     # fused backward operands: dz = d_pre * scale[c], fp32 and tf32-rounded
     sc, sc2 = torch.rand(ch) + 0.5, torch.rand(ch) + 0.5
     for rnd in (False, True):
@@ -106,7 +113,8 @@ def test_gru_pointwise(cuda_backend):
 
 
 @pytest.mark.parametrize("G,rows,C,relu,up2", [(1, 500, 24, True, False), (3, 2 * 8 * 8, 96, True, True), (4, 6, 768, False, False), (2, 4 * 4, 4, True, True),
-                                               (2, 700000, 8, True, False), (1, 2 * 512 * 512, 8, True, True)])   # long chunks: the multi-row main loops
+                                               (2, 700000, 8, True, False), (1, 2 * 512 * 512, 8, True, True),   # long chunks: the multi-row main loops
+                                               (18, 64, 40, True, False)])              # G > the finalize kernel's 8 group lanes, C not a multiple of 32
 def test_batchnorm(cuda_backend, G, rows, C, relu, up2):
     torch.manual_seed(4)
     H = W = int((rows // 2) ** 0.5) if up2 else 1
@@ -316,7 +324,7 @@ def test_sn_bwd_multi(cuda_backend):
     be = cuda_backend
     torch.manual_seed(20)
     items, refs = [], []
-    for R, K, G, acc in ((24, 72, 3, False), (8, 9, 1, True), (96, 864, 18, False)):
+    for R, K, G, acc in ((24, 72, 3, False), (8, 9, 1, True), (96, 864, 18, False), (16, 64, 5, True), (4, 36, 70, True)):
         t = [torch.randn(G, device="cuda"), torch.rand(G, device="cuda") + 0.5, torch.randn(G, R, device="cuda"), torch.randn(G, K, device="cuda")]
         dw0 = torch.randn(R, K, device="cuda")
         ref, dw = dw0.clone(), dw0.clone()
