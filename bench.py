@@ -295,6 +295,8 @@ def main():
     ap.add_argument("--batch", type=int, default=None, help="per-GPU batch (default: the configuration's)")
     ap.add_argument("--generation-steps", type=int, default=None)
     ap.add_argument("--cuda-graph", action="store_true", help="c2 only: replay the eval forward from a CUDA graph (skillful_nowcasting_b200.inference)")
+    ap.add_argument("--no-d-phase-graph", dest="d_phase_graph", action="store_false",
+                    help="training configs: run the D phase's gradient-free generator forwards eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-gpu", action="store_true", help="skip the reference's own GPU path (reference_gpu_eager)")
     ap.add_argument("--cpu-batch", type=int, default=1)
@@ -343,6 +345,7 @@ def main():
     x, y = host_x.to(dev), host_y.to(dev)
     host_out = torch.empty(B, T, 1, S, S).pin_memory() if c["kind"] == "inference" else None
 
+    d_graph, d_graph_note = None, None
     if args.mode == "dropin":
         from baseline import reference_arm as R
 
@@ -377,8 +380,22 @@ def main():
             g_opt = Adam(gen.parameters(), lr=5e-5, betas=(0.0, 0.999))
             d_opt = Adam(disc.parameters(), lr=2e-4, betas=(0.0, 0.999))
 
-            def run_step(xi, yi):
-                return gan_step(gen, disc, g_opt, d_opt, xi, yi, generation_steps=K)
+            # the two gradient-free generator forwards of the D phase replay from a CUDA graph (launch-bound ConvGRU steps); the
+            # instrumented step below runs them eagerly so that every launch carries its events
+            d_graph_note = "eager"
+            if args.d_phase_graph and args.precision == "tf32":
+                try:
+                    from skillful_nowcasting_b200.inference import GraphedGenerator
+
+                    d_graph = GraphedGenerator(gen, x, train_mode=True)
+                    d_graph_note = f"cuda-graph ({d_graph.launches} launches per replay)"
+                except Exception as e:  # noqa: BLE001 -- a failed capture must not cost the measurement: run the eager path and say so
+                    d_graph, d_graph_note = None, f"eager (graph capture failed: {type(e).__name__}: {str(e)[:120]})"
+                    print(f"bench: D-phase graph capture failed, running eagerly: {e}", file=sys.stderr)
+                    torch.cuda.synchronize()
+
+            def run_step(xi, yi, graphed=True):
+                return gan_step(gen, disc, g_opt, d_opt, xi, yi, generation_steps=K, d_phase_generator=d_graph if graphed else None)
 
     def barrier():
         if world > 1:
@@ -428,6 +445,8 @@ def main():
     be.profile = []
     if inference and args.cuda_graph:
         run_eager(x, y)       # a graph replay issues no host launches: the per-launch events come from one eager forward of the same model
+    elif not inference and args.mode != "dropin":
+        run_step(x, y, graphed=False)
     else:
         step_resident()
     torch.cuda.synchronize()
@@ -484,9 +503,10 @@ def main():
         config=dict(config, mode=args.mode + ("+cuda-graph" if args.cuda_graph else ""), precision=args.precision,
                     l2="inputs+activations per step (>10 GB) exceed the 126 MB L2; no explicit flush needed",
                     schedule=("reference wrapper's literal schedule (checkpoint recompute, trailing forward), torch.optim.Adam" if args.mode == "dropin"
-                              else "generator forward only, eval mode" if inference else "parity-preserving minimal schedule (SURVEY.md 8d)")),
+                              else "generator forward only, eval mode" if inference else "parity-preserving minimal schedule (SURVEY.md 8d)"),
+                    **({"d_phase_generator_forwards": d_graph_note} if d_graph_note else {})),
         e2e=dict(value=e2e_value, unit="frames/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h),
-        gpu_launches=launches // args.steps,
+        gpu_launches=launches // args.steps + (2 * d_graph.launches if d_graph is not None else 0),   # host launches + the kernels of the 2 graph replays
         clocks=clocks,
         step_tflops=step_flops / (ms_per_step * 1e-3) / 1e12,
         roofline=dict(bound="tensor", kernel=f"{top_tag} {top_info} (tcgen05 kind::tf32 implicit GEMM; the tensor-core launch with the largest share of the step)",

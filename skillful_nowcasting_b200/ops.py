@@ -636,7 +636,8 @@ def packed_weight_padded(w: torch.Tensor, ci0: int, cin: int, cin_p: int, mode: 
 def refresh_packs(params) -> int:
     """Re-pack, IN PLACE and in one launch per 64 packs, every cached packed copy of `params` that an optimiser step made stale
     (the optimiser calls this right after its update): from the second step on a network's ~100-200 packs cost a couple of
-    launches instead of one launch each at first use.  Parity-mode (hi, lo) pairs are simply dropped and rebuilt on demand."""
+    launches instead of one launch each at first use.  Parity-mode (hi, lo) pairs are simply dropped and rebuilt on demand.
+    In the 1xTF32 mode every pack keeps its address across optimiser steps (inference.GraphedGenerator(train_mode=True) relies on it)."""
     items, touched = [], []
     for w in params:
         slot = w.__dict__.get("_dgmr_packs")
@@ -650,8 +651,9 @@ def refresh_packs(params) -> int:
                 continue
             ci0, cin, m = key
             pad = cin
-            if isinstance(m, tuple) and m[0] == "sub":   # pre-summed sub-pixel tiles: rebuilt on demand (8 small launches per step)
-                del slot[key]
+            if isinstance(m, tuple) and m[0] == "sub":   # pre-summed sub-pixel tiles: their own kernel (8 small launches per step), also in place --
+                _be().pack_weight_subpix(_c(w.detach()), slot[key][1], cout, cintot, 0, cin, m[1])   # a captured CUDA graph keeps reading this buffer
+                slot[key] = (tag, slot[key][1])
                 continue
             if isinstance(m, tuple):
                 _, pad, m = m

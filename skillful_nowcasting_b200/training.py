@@ -131,19 +131,24 @@ class Adam(torch.optim.Optimizer):
 
 
 def gan_step(generator, discriminator, g_opt, d_opt, images: torch.Tensor, future: torch.Tensor,
-             generation_steps: int = 1, grid_lambda: float = 20.0, precip_weight_cap: float = 24.0):
+             generation_steps: int = 1, grid_lambda: float = 20.0, precip_weight_cap: float = 24.0, d_phase_generator=None):
     """One GAN step: 2 discriminator updates + 1 generator update with the losses, gradients and parameter
     updates of the reference's `DGMR.training_step` (dgmr/dgmr.py:137-218), minus its wasted work:
     the generator is not back-propagated in the D phase (its grads are discarded there, :199), no checkpoint
     recompute, no trailing forward, and the D weights take no gradient in the G phase.  In the G phase D still
-    sees real||generated in one batch because BatchNorm1d statistics couple the halves."""
+    sees real||generated in one batch because BatchNorm1d statistics couple the halves.
+    d_phase_generator: optional `inference.GraphedGenerator(generator, images, train_mode=True)`: the two gradient-free generator forwards of
+    the D phase replayed from a CUDA graph (same arithmetic and state updates; its output buffer is consumed before the next replay)."""
     b = images.shape[0]
     real_seq = torch.cat([images, future], dim=1)
     d_loss = None
     for _ in range(2):
         d_opt.zero_grad()
-        with torch.no_grad():
-            pred = generator(images)
+        if d_phase_generator is not None:
+            pred = d_phase_generator(images)
+        else:
+            with torch.no_grad():
+                pred = generator(images)
         scores = discriminator(torch.cat([real_seq, torch.cat([images, pred], dim=1)], dim=0))
         d_loss = loss_hinge_disc_both(scores)
         d_loss.backward()

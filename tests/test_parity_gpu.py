@@ -292,3 +292,48 @@ def test_graphed_generator_matches_eager_and_oracle(cuda_backend, c1_state):
     torch.manual_seed(3)
     assert torch.equal(runner.z, gen.latent_stack.sample_z(xc))
     gen.cpu()
+
+
+def test_graphed_train_mode_generator_matches_eager(cuda_backend, c1_state):
+    """The D phase's gradient-free TRAIN-mode generator forward (ref: dgmr/dgmr.py:159-160) replayed from a CUDA graph: outputs of two
+    successive replays and the state they leave behind (spectral-norm u / v after 2 x T power iterations, BatchNorm running statistics,
+    num_batches_tracked) equal two eager forwards from the same start; the capture's warm-up forwards leave no trace; gan_step accepts it.
+    Bounds: run-to-run noise of the 1xTF32 path (fp32 atomics of the tap-split convolutions) through train-mode BatchNorm."""
+    from skillful_nowcasting_b200.inference import GraphedGenerator
+
+    gen, disc, g0, d0 = c1_state
+    _set_mode(cuda_backend, "tf32")
+    gen.load_state_dict(g0)
+    gen.cuda().train()
+    x, y = c1_inputs()
+    xc = x.cuda()
+    runner = GraphedGenerator(gen, xc, train_mode=True)
+    assert runner.launches > 100
+    for k, v in gen.state_dict().items():
+        assert torch.equal(v.cpu(), g0[k]), f"{k} changed during the capture"
+    n0 = cuda_backend.launches
+    outs_g = []
+    for seed in (2, 3):
+        torch.manual_seed(seed)
+        outs_g.append(runner(xc).clone())
+    assert cuda_backend.launches == n0
+    st_g = {k: v.detach().cpu().clone() for k, v in gen.state_dict().items()}
+    gen.load_state_dict(g0)
+    outs_e = []
+    with torch.no_grad():
+        for seed in (2, 3):
+            torch.manual_seed(seed)
+            outs_e.append(gen(xc))
+    st_e = {k: v.detach().cpu().clone() for k, v in gen.state_dict().items()}
+    for a, b in zip(outs_g, outs_e):
+        assert rel_err(a, b) < 2e-2
+    assert rel_err(outs_g[0], outs_g[1]) > 1e-3      # a fresh latent per replay
+    moved = 0
+    for k in st_e:
+        if st_e[k].dtype.is_floating_point:
+            assert rel_err(st_g[k], st_e[k]) < 2e-2, k
+            moved += int(not torch.equal(st_e[k], g0[k]))
+        else:
+            assert torch.equal(st_g[k], st_e[k]), k
+    assert moved > 10                                # the buffers did advance (u, v, running statistics)
+    gen.cpu()
