@@ -54,8 +54,14 @@ class GraphedGenerator:
         torch.cuda.current_stream().wait_stream(side)
         self.graph = torch.cuda.CUDAGraph()
         n0 = be.launches
-        with torch.cuda.graph(self.graph):
-            self.out = self._forward_static()
+        cur = torch.cuda.current_stream()
+        try:
+            with torch.cuda.graph(self.graph):
+                self.out = self._forward_static()
+        except BaseException:
+            torch.cuda.set_stream(cur)                    # a failed capture leaves torch's capture stream current: put the caller's back
+            be.launches = n0
+            raise
         self.launches = be.launches - n0
         be.launches = n0                                  # recorded, not executed
 
