@@ -182,7 +182,7 @@ def oracle_gan_step(g_state, d_state, x, y, cfg, seed, generation_steps=1):
                 g_t=g_opt.t, d_t=d_opt.t)
 
 
-def module_gan_step(gen, disc, x, y, seed, device, generation_steps=1):
+def module_gan_step(gen, disc, x, y, seed, device, generation_steps=1, d_phase_generator=None):
     """training.gan_step through the B200 modules and the fused Adam: the same quantities as oracle_gan_step."""
     from skillful_nowcasting_b200.training import Adam, gan_step
 
@@ -190,7 +190,7 @@ def module_gan_step(gen, disc, x, y, seed, device, generation_steps=1):
     g_opt = Adam(gen.parameters(), lr=5e-5, betas=(0.0, 0.999))
     d_opt = Adam(disc.parameters(), lr=2e-4, betas=(0.0, 0.999))
     torch.manual_seed(seed)
-    losses = gan_step(gen, disc, g_opt, d_opt, x.to(device), y.to(device), generation_steps=generation_steps)
+    losses = gan_step(gen, disc, g_opt, d_opt, x.to(device), y.to(device), generation_steps=generation_steps, d_phase_generator=d_phase_generator)
 
     def moments(opt, module):
         names = [n for n, _ in module.named_parameters()]

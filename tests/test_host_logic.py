@@ -135,6 +135,36 @@ def test_gan_step_matches_oracle_step(emu):
     compare_gan_step(got, ref, g0, d0, GAN_STEP_TOL_FP32)
 
 
+def test_gan_step_with_a_d_phase_generator_runner(emu):
+    """gan_step(d_phase_generator=...): the D phase's gradient-free generator forwards go through the supplied runner (on the GPU a CUDA-graph
+    replay, inference.GraphedGenerator(train_mode=True); here a plain callable with the same contract: train mode, no autograd, a reused
+    output buffer) -- two calls per step, and the step's results are those of the default path bit for bit."""
+    from parity_util import module_gan_step
+
+    x, y = c1_inputs()
+    results, calls = [], []
+    for use_runner in (False, True):
+        gen, disc = build_gan(C1, seed=0, gamma=0.5)
+        buf = {}
+
+        def runner(images, gen=gen, buf=buf):
+            assert gen.training
+            with torch.no_grad():
+                out = gen(images)
+            calls.append(tuple(out.shape))
+            buf.setdefault("out", torch.empty_like(out)).copy_(out)     # static output buffer, overwritten by the next call
+            return buf["out"]
+
+        results.append(module_gan_step(gen, disc, x, y, seed=4, device="cpu", d_phase_generator=runner if use_runner else None))
+    assert len(calls) == 2
+    a, b = results
+    for k in ("d_loss", "g_loss", "grid_loss"):
+        assert torch.equal(a["losses"][k], b["losses"][k]), k
+    for part in ("g_state", "d_state"):
+        for k in a[part]:
+            assert torch.equal(a[part][k], b[part][k]), (part, k)
+
+
 @pytest.mark.parametrize("which", ["spatial", "temporal"])
 @pytest.mark.parametrize("training", [False, True], ids=["eval", "train"])
 def test_discriminators_separately(emu, which, training):
