@@ -135,6 +135,20 @@ def test_gan_step_matches_oracle_step(emu):
     compare_gan_step(got, ref, g0, d0, GAN_STEP_TOL_FP32)
 
 
+def test_gan_step_with_two_generation_steps_matches_oracle_step(emu):
+    """generation_steps = 2 (ref: dgmr/dgmr.py:171-190: K generator samples per input, grid-cell loss on their mean, every sample scored by
+    the discriminator next to the real sequence): the same comparison as above, same fp32 bounds."""
+    from parity_util import GAN_STEP_TOL_FP32, compare_gan_step, module_gan_step, oracle_gan_step
+
+    gen, disc = build_gan(C1, seed=0, gamma=0.5)
+    g0 = {k: v.clone() for k, v in gen.state_dict().items()}
+    d0 = {k: v.clone() for k, v in disc.state_dict().items()}
+    x, y = c1_inputs()
+    ref = oracle_gan_step(g0, d0, x, y, C1, seed=4, generation_steps=2)
+    got = module_gan_step(gen, disc, x, y, seed=4, device="cpu", generation_steps=2)
+    compare_gan_step(got, ref, g0, d0, GAN_STEP_TOL_FP32)
+
+
 def test_gan_step_with_a_d_phase_generator_runner(emu):
     """gan_step(d_phase_generator=...): the D phase's gradient-free generator forwards go through the supplied runner (on the GPU a CUDA-graph
     replay, inference.GraphedGenerator(train_mode=True); here a plain callable with the same contract: train mode, no autograd, a reused
@@ -241,9 +255,11 @@ def test_stale_prefetched_sigma_is_dropped(emu):
 
 
 @pytest.mark.refpkg
-def test_unmodified_reference_wrapper_runs_on_these_modules(emu):
+@pytest.mark.parametrize("generation_steps", [1, 2])
+def test_unmodified_reference_wrapper_runs_on_these_modules(emu, generation_steps):
     """SURVEY 8b / 8d mode (i): the reference's OWN dgmr/dgmr.py (unmodified, from /root/reference or baseline/_ref) constructs and trains
-    these modules through the import swap of INTEGRATION.md, and logs the losses the reference itself logs from the same seeds."""
+    these modules through the import swap of INTEGRATION.md, and logs the losses the reference itself logs from the same seeds.
+    generation_steps = 2: several generator samples per input (ref: dgmr/dgmr.py:171-190; the paper configuration uses 6, BASELINE.json C5)."""
     import os
     import sys
 
@@ -255,7 +271,7 @@ def test_unmodified_reference_wrapper_runs_on_these_modules(emu):
     x, y = torch.rand(2, 4, 1, 128, 128), torch.rand(2, 2, 1, 128, 128)
     logs = {}
     for dropin in (False, True):
-        model = R.build_dgmr(cfg, generation_steps=1, dropin=dropin, anomaly=False, seed=0)
+        model = R.build_dgmr(cfg, generation_steps=generation_steps, dropin=dropin, anomaly=False, seed=0)
         assert type(model).__module__ == "dgmr.dgmr"
         assert type(model.generator).__module__.startswith("skillful_nowcasting_b200" if dropin else "dgmr.")
         torch.manual_seed(2)
