@@ -18,6 +18,7 @@ What the line carries besides the contract's keys:
                        native arm runs -- the denominators of the ">= 5x the cuDNN-backed step" target
 """
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -524,8 +525,9 @@ def main():
     # free the benchmark's own state before the reference's eager path needs the memory
     del prof
     if not args.no_ref_gpu and world == 1 and not inference and args.mode == "native":
-        gen = disc = g_opt = d_opt = None
+        gen = disc = g_opt = d_opt = d_graph = None     # (the graph runner holds the generator and its private memory pool)
         ops.clear_pack_cache()
+        gc.collect()
         torch.cuda.empty_cache()
         try:
             line["reference_gpu_eager"] = gpu_reference_eager(cfg, B, K, dev)
