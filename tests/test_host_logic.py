@@ -149,6 +149,55 @@ def test_gan_step_with_two_generation_steps_matches_oracle_step(emu):
     compare_gan_step(got, ref, g0, d0, GAN_STEP_TOL_FP32)
 
 
+def test_packed_weights_keep_their_addresses_across_optimiser_steps(emu):
+    """What inference.GraphedGenerator(train_mode=True) relies on: in the 1xTF32 mode every cached packed copy of a generator weight (ordinary,
+    channel-padded, dgrad, pre-summed sub-pixel tiles) is refreshed IN PLACE by the optimiser step -- same buffer address before and after,
+    tag = the parameter's new version, contents = a fresh pack of the updated weight -- so a captured graph keeps reading live weights."""
+    from skillful_nowcasting_b200 import _lib, ops
+    from skillful_nowcasting_b200.training import Adam, gan_step
+
+    ops.config._force_upconv = True          # the sub-pixel form (and its packs) on the host emulator too
+    try:
+        gen, disc = build_gan(C1, seed=0, gamma=0.5)
+        gen.train(); disc.train()
+        g_opt = Adam(gen.parameters(), lr=5e-5, betas=(0.0, 0.999))
+        d_opt = Adam(disc.parameters(), lr=2e-4, betas=(0.0, 0.999))
+        x, y = c1_inputs()
+
+        def packs():
+            return {(n, key): buf for n, p in gen.named_parameters() for key, (_, buf) in p.__dict__.get("_dgmr_packs", {}).items()}
+
+        torch.manual_seed(1)
+        gan_step(gen, disc, g_opt, d_opt, x, y)
+        before = {k: (b.data_ptr(), b.clone()) for k, b in packs().items()}
+        assert len(before) > 50 and any(isinstance(k[1][2], tuple) and k[1][2][0] == "sub" for k in before)
+        torch.manual_seed(2)
+        gan_step(gen, disc, g_opt, d_opt, x, y)
+        after = packs()
+        assert set(after) == set(before)
+        be = _lib.backend()
+        params = dict(gen.named_parameters())
+        changed = 0
+        for (n, key), buf in after.items():
+            w = params[n]
+            assert buf.data_ptr() == before[(n, key)][0], (n, key)
+            assert w.__dict__["_dgmr_packs"][key][0] == (w._version, w.data_ptr(), str(w.device)), (n, key)
+            changed += int(not torch.equal(buf, before[(n, key)][1]))
+            ci0, cin, m = key
+            cout, cintot = w.shape[0], w.shape[1]
+            fresh = torch.zeros_like(buf)
+            if isinstance(m, tuple) and m[0] == "sub":
+                be.pack_weight_subpix(w.detach().contiguous(), fresh, cout, cintot, 0, cin, m[1])
+            elif isinstance(m, tuple):
+                continue                      # channel-padded packs: address and tag checked above
+            else:
+                be.pack_weight(w.detach().contiguous(), fresh, cout, cintot, ci0, cin, w.numel() // (cout * cintot), m)
+            assert torch.equal(buf, fresh), (n, key)
+        assert changed > 50                   # the second step did move the weights
+    finally:
+        ops.config._force_upconv = False
+
+
 def test_gan_step_with_a_d_phase_generator_runner(emu):
     """gan_step(d_phase_generator=...): the D phase's gradient-free generator forwards go through the supplied runner (on the GPU a CUDA-graph
     replay, inference.GraphedGenerator(train_mode=True); here a plain callable with the same contract: train mode, no autograd, a reused
